@@ -1,0 +1,427 @@
+// C-ABI: sessions and the image entry points (host-buffer and device-resident).
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "api_internal.cuh"
+
+namespace ie {
+
+int session_reserve(uint8_t **p, size_t *cap, size_t need) {
+    if (*cap >= need && *p) return IE_OK;
+    if (*p) IE_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    need = (need + 255) / 256 * 256;
+    IE_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return IE_OK;
+}
+
+int session_ensure_scan(ie_session *s, unsigned images, unsigned tiles) {
+    if (s->d_tile_state && s->images >= images && s->max_tiles >= tiles) return IE_OK;
+    if (s->d_tile_state) { cudaFree(s->d_tile_state); cudaFree(s->d_bnd); cudaFree(s->d_ticket); cudaFree(s->d_counter); }
+    images = std::max(images, s->images);
+    tiles = std::max(tiles, s->max_tiles);
+    const size_t n = (size_t)images * tiles;
+    IE_CUDA(cudaMalloc(&s->d_tile_state, n * sizeof(unsigned long long)));
+    IE_CUDA(cudaMalloc(&s->d_bnd, n * sizeof(TileBoundary)));
+    IE_CUDA(cudaMalloc(&s->d_ticket, images * sizeof(unsigned)));
+    IE_CUDA(cudaMalloc(&s->d_counter, images * sizeof(unsigned long long)));
+    IE_CUDA(cudaMemset(s->d_tile_state, 0, n * sizeof(unsigned long long)));
+    IE_CUDA(cudaMemset(s->d_bnd, 0, n * sizeof(TileBoundary)));
+    IE_CUDA(cudaMemset(s->d_ticket, 0, images * sizeof(unsigned)));
+    IE_CUDA(cudaMemset(s->d_counter, 0, images * sizeof(unsigned long long)));
+    s->images = images;
+    s->max_tiles = tiles;
+    s->epoch = 0;
+    return IE_OK;
+}
+
+int check_quant(const uint16_t *quant, int N) {
+    if (!quant) { set_error("quant matrix is NULL"); return IE_EINVAL; }
+    for (int i = 0; i < N * N; i++)
+        if (quant[i] == 0) { set_error("quant matrix entry 0 (division by zero in the reference, MatrixReader.cpp:104)"); return IE_EINVAL; }
+    return IE_OK;
+}
+
+int check_dims(uint32_t W, uint32_t H, uint32_t N) {
+    if (N != 4 && N != 8) { set_error("block size must be 4 or 8"); return IE_EINVAL; }
+    if (W == 0 || H == 0 || W > 32767 || H > 32767) { set_error("width/height must be in 1..32767 (DIM_BITS=15, ImageBase.hpp:76)"); return IE_EINVAL; }
+    if (W % N || H % N) { set_error("width/height must be multiples of the block size (ImageEncoder.cpp:26-27)"); return IE_EINVAL; }
+    return IE_OK;
+}
+
+// Writes the stream prefix (zero bits up to first_bit, then the header) into whole chunks and sets the bit counters.
+__global__ void stream_init_kernel(uint8_t *out, size_t out_stride, unsigned images, HeaderParam hdr, unsigned first_bit,
+                                   unsigned long long *counter) {
+    const unsigned img = blockIdx.x;
+    if (img >= images) return;
+    const unsigned total = first_bit + hdr.bits;
+    const unsigned nwords = ((total + 127) / 128) * 4;
+    unsigned *o = reinterpret_cast<unsigned *>(out + (size_t)img * out_stride);
+    for (unsigned i = threadIdx.x; i < nwords; i += blockDim.x) {
+        // word i of the stream = header bits [32 i - first_bit, +32)
+        const long long hb = (long long)i * 32 - (long long)first_bit;
+        unsigned v = 0;
+        const int sh = (int)(((hb % 32) + 32) % 32);
+        const long long wi = (hb - sh) / 32;               // floor division
+        const unsigned hi = (wi >= 0 && wi < kHdrWordsMax) ? hdr.words[wi] : 0u;
+        const unsigned lo = (wi + 1 >= 0 && wi + 1 < kHdrWordsMax) ? hdr.words[wi + 1] : 0u;
+        v = sh ? ((hi << sh) | (lo >> (32 - sh))) : hi;
+        o[i] = __byte_perm(v, 0, 0x0123);
+    }
+    if (threadIdx.x == 0) counter[img] = total;
+}
+
+int launch_stream_init(uint8_t *out, size_t out_stride, unsigned images, const HeaderParam &hdr, unsigned first_bit,
+                       unsigned long long *counter, cudaStream_t stream) {
+    stream_init_kernel<<<images, 64, 0, stream>>>(out, out_stride, images, hdr, first_bit, counter);
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
+int make_quant(QuantParam &q, const uint16_t *quant, int N) {
+    memset(&q, 0, sizeof q);
+    for (int i = 0; i < N * N; i++) q.m[i] = (double)quant[i];          // MatrixReader.cpp:128,195-198
+    for (int i = N * N; i < kMaxNN; i++) q.m[i] = 1.0;
+    return IE_OK;
+}
+
+// Encode `images` equally sized images that are resident on the device.
+int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, unsigned images, uint32_t W, uint32_t H, int N,
+                      const uint16_t *quant, int use_rle, int lead_bit, int write_header, unsigned first_bit, int bits_only,
+                      uint8_t *d_out, size_t out_stride, size_t out_cap, cudaStream_t stream) {
+    IE_TRY(check_dims(W, H, N));
+    IE_TRY(check_quant(quant, N));
+    if (first_bit >= 128) { set_error("first_bit must be < 128"); return IE_EINVAL; }
+    if (!bits_only && ((uintptr_t)d_out % 16 || out_stride % 16)) { set_error("stream buffers must be 16-byte aligned"); return IE_EINVAL; }
+    const unsigned nblocks = (W / N) * (H / N);
+    const unsigned TB = encode_tile_blocks(N);
+    const unsigned tiles = (nblocks + TB - 1) / TB;
+    IE_TRY(session_ensure_scan(s, images, tiles));
+    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+
+    HeaderParam hdr;
+    memset(&hdr, 0, sizeof hdr);
+    if (write_header) IE_TRY(build_header(hdr, N, quant, use_rle, W, H, lead_bit, 0, 0, 0, 0));
+    if (!bits_only) {
+        const size_t need = ((size_t)first_bit + hdr.bits + 127) / 128 * 16;
+        if (out_cap < need) { set_error("output buffer too small for the header"); return IE_ENOSPC; }
+        IE_TRY(launch_stream_init(d_out, out_stride, images, hdr, first_bit, s->d_counter, stream));
+    } else {
+        IE_CUDA(cudaMemsetAsync(s->d_counter, 0, images * sizeof(unsigned long long), stream));
+    }
+
+    EncodeParams p;
+    memset(&p, 0, sizeof p);
+    p.src = d_raw; p.pitch = W; p.img_stride = img_stride;
+    p.bx = W / N; p.nblocks = nblocks; p.tiles_per_image = tiles;
+    p.use_rle = use_rle ? 1 : 0; p.bits_only = bits_only;
+    make_quant(p.quant, quant, N);
+    p.tab = (N == 8) ? s->dev->d_t8 : s->dev->d_t4;
+    p.out = d_out; p.out_stride = out_stride; p.out_cap = out_cap;
+    p.bit_counter = s->d_counter; p.err = s->d_err;
+    p.scan = s->scan_state();
+    // scan arrays are indexed [image][tile] with stride tiles_per_image (the allocation is at least that large)
+    return launch_encode_tiles(N, p, images, stream);
+}
+
+int read_err_flag(ie_session *s, cudaStream_t stream) {
+    if (!s->d_err) return IE_OK;
+    int e = 0;
+    IE_CUDA(cudaMemcpyAsync(&e, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    IE_CUDA(cudaStreamSynchronize(stream));
+    if (e != 0) {
+        IE_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), stream));
+        set_error(e == IE_ENOSPC ? "output buffer too small" : (e == IE_EFORMAT ? "malformed stream" : "device-side error"));
+        return e;
+    }
+    return IE_OK;
+}
+
+// ---- header parsing on the host (MatrixReader.cpp:45-57, ImageBase.cpp:122-128, VideoBase.cpp:72-83) ---------------
+namespace {
+struct HostReader {
+    const uint8_t *b;
+    size_t n;
+    size_t pos;
+    uint32_t get(unsigned l) {
+        uint32_t v = 0;
+        for (unsigned i = 0; i < l; i++) {
+            uint32_t bit = 0;
+            if ((pos >> 3) < n) { bit = (b[pos >> 3] >> (7 - (pos & 7))) & 1u; pos++; }
+            v |= bit << (l - i - 1);
+        }
+        return v;
+    }
+};
+}  // namespace
+
+int parse_header(const uint8_t *bytes, size_t n, size_t start_bit, int N, ParsedHeader &h, int video) {
+    HostReader r{bytes, n, start_bit};
+    const unsigned qb = r.get(5);
+    for (int i = 0; i < N * N; i++) h.quant[i] = (uint16_t)r.get(qb);
+    h.use_rle = (int)r.get(1);
+    h.W = r.get(15);
+    h.H = r.get(15);
+    h.frames = h.gop = h.merange = 0;
+    if (video) { h.frames = r.get(15); h.gop = r.get(15); h.merange = r.get(15); }
+    h.end_bit = r.pos;
+    return IE_OK;
+}
+
+int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size_t start_bit, int N, const ParsedHeader &h,
+                     uint8_t *d_out, size_t out_cap, cudaStream_t stream) {
+    const uint32_t W = h.W, H = h.H;
+    IE_TRY(check_dims(W, H, N));
+    if ((size_t)W * H > out_cap) { set_error("decoded image does not fit the output buffer"); return IE_ENOSPC; }
+    for (int i = 0; i < N * N; i++)
+        if (h.quant[i] == 0) { /* a zero entry decodes to zero coefficients * 0: allowed */ }
+    const unsigned nblocks = (W / N) * (H / N);
+    IE_TRY(session_ensure_scan(s, 1, 1));
+    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+    const size_t need_off = ((size_t)nblocks + 1) * sizeof(unsigned long long) + 64;
+    if (s->block_off_cap < need_off) {
+        if (s->d_block_off) IE_CUDA(cudaFree(s->d_block_off));
+        IE_CUDA(cudaMalloc(&s->d_block_off, need_off));
+        s->block_off_cap = need_off;
+    }
+    // two u64 of launch constants live at the end of the offsets array: [stream bits, first block bit]
+    unsigned long long consts[2] = {(unsigned long long)enc_bytes * 8ull, (unsigned long long)h.end_bit};
+    (void)start_bit;
+    unsigned long long *d_consts = s->d_block_off + (nblocks + 1);
+    IE_CUDA(cudaMemcpyAsync(d_consts, consts, sizeof consts, cudaMemcpyHostToDevice, stream));
+    DecodeParams p;
+    memset(&p, 0, sizeof p);
+    p.enc = d_enc; p.enc_stride = 0; p.enc_bits = d_consts; p.start_bit = d_consts + 1;
+    p.block_off = s->d_block_off; p.nblocks = nblocks; p.bx = W / N; p.N = N; p.use_rle = h.use_rle;
+    make_quant(p.quant, h.quant, N);
+    p.tab = (N == 8) ? s->dev->d_t8 : s->dev->d_t4;
+    p.out = d_out; p.out_stride = 0; p.pitch = W; p.err = s->d_err;
+    IE_TRY(launch_parse_blocks(p, 1, stream));
+    return launch_decode_blocks(p, 1, stream);
+}
+
+// ---- cached sessions for the host-buffer entry points -----------------------------------------------------------
+static std::mutex g_smu;
+static std::map<std::tuple<int, int, uint32_t, uint32_t, uint32_t, uint32_t>, ie_session *> g_sessions;
+
+int cached_session(ie_session **out, int kind, uint32_t W, uint32_t H, uint32_t N, uint32_t frames) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("no CUDA device (this library has no CPU path)"); return IE_ENODEVICE; }
+    std::lock_guard<std::mutex> lk(g_smu);
+    auto key = std::make_tuple(dev, kind, W, H, N, frames);
+    auto it = g_sessions.find(key);
+    if (it != g_sessions.end()) { *out = it->second; return IE_OK; }
+    ie_session *s = nullptr;
+    IE_TRY(ie_session_create(&s, kind, W, H, N, frames));
+    g_sessions[key] = s;
+    *out = s;
+    return IE_OK;
+}
+
+void drop_cached_sessions() {
+    std::lock_guard<std::mutex> lk(g_smu);
+    for (auto &kv : g_sessions) ie_session_destroy(kv.second);
+    g_sessions.clear();
+}
+
+}  // namespace ie
+
+using namespace ie;
+
+extern "C" {
+
+int ie_session_create(ie_session **out, int kind, uint32_t W, uint32_t H, uint32_t N, uint32_t frames) {
+    if (!out) return IE_EINVAL;
+    DeviceState *dev = nullptr;
+    IE_TRY(get_device_state(&dev));
+    ie_session *s = new ie_session();
+    s->kind = kind; s->W = W; s->H = H; s->N = N; s->frames = frames ? frames : 1;
+    s->dev = dev; s->device = dev->device;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&s->h_pinned, 64 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { delete s; return cuda_fail(e, "session create", __FILE__, __LINE__); }
+    *out = s;
+    return IE_OK;
+}
+
+void ie_session_destroy(ie_session *s) {
+    if (!s) return;
+    cudaFree(s->d_tile_state); cudaFree(s->d_bnd); cudaFree(s->d_ticket); cudaFree(s->d_counter); cudaFree(s->d_err);
+    cudaFree(s->d_block_off); cudaFree(s->d_scratch); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_tmp);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int ie_encode_image_dev(ie_session *s, const uint8_t *d_raw, uint32_t W, uint32_t H, const uint16_t *quant, int use_rle,
+                        int lead_bit, int write_header, uint64_t first_bit, uint8_t *d_out, size_t out_cap,
+                        uint64_t *d_out_bits, void *stream) {
+    if (!s || !d_raw || !d_out) { set_error("NULL argument"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    IE_TRY(encode_images_dev(s, d_raw, 0, 1, W, H, (int)s->N, quant, use_rle, lead_bit, write_header, (unsigned)first_bit, 0,
+                             d_out, 0, out_cap, st));
+    if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, s->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return IE_OK;
+}
+
+int ie_image_bits_dev(ie_session *s, const uint8_t *d_raw, uint32_t W, uint32_t H, const uint16_t *quant, int use_rle,
+                      uint64_t *d_total_bits, void *stream) {
+    if (!s || !d_raw || !d_total_bits) { set_error("NULL argument"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    IE_TRY(encode_images_dev(s, d_raw, 0, 1, W, H, (int)s->N, quant, use_rle, 0, 0, 0, 1, nullptr, 0, 0, st));
+    IE_CUDA(cudaMemcpyAsync(d_total_bits, s->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return IE_OK;
+}
+
+int ie_encode_image(const uint8_t *raw, uint32_t W, uint32_t H, uint32_t N, const uint16_t *quant, int use_rle, int huffman,
+                    uint8_t *out, size_t out_cap, size_t *out_bytes) {
+    if (!raw || !out || !out_bytes) { set_error("NULL argument"); return IE_EINVAL; }
+    IE_TRY(check_dims(W, H, N));
+    IE_TRY(check_quant(quant, (int)N));
+    ie_session *s = nullptr;
+    IE_TRY(cached_session(&s, 0, W, H, N, 1));
+    const size_t npx = (size_t)W * H;
+    const size_t cap = ie_max_encoded_bytes(W, H, N, 1);
+    IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, npx));
+    IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, cap));
+    cudaStream_t st = s->stream;
+    IE_CUDA(cudaMemcpyAsync(s->d_in, raw, npx, cudaMemcpyHostToDevice, st));
+    IE_TRY(encode_images_dev(s, s->d_in, 0, 1, W, H, (int)N, quant, use_rle, huffman ? 0 : 1, 1, 0, 0, s->d_out, 0, s->d_out_cap, st));
+    IE_CUDA(cudaMemcpyAsync(s->h_pinned, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    IE_TRY(read_err_flag(s, st));                              // synchronises
+    size_t bytes = (size_t)((s->h_pinned[0] + 7) / 8);        // util::round_to_byte, ImageBase.cpp:316
+    const uint8_t *d_result = s->d_out;
+    if (huffman) {
+        IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, bytes + 4096 + 32));
+        size_t hb = 0;
+        IE_TRY(ie_huffman_encode_dev(s, s->d_out, bytes, s->d_tmp, s->d_tmp_cap, &hb, st));
+        bytes = hb;
+        d_result = s->d_tmp;
+    }
+    *out_bytes = bytes;
+    if (bytes > out_cap) { set_error("output buffer too small"); return IE_ENOSPC; }
+    IE_CUDA(cudaMemcpyAsync(out, d_result, bytes, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    return IE_OK;
+}
+
+int ie_encode_images(const uint8_t *raws, uint32_t count, uint32_t W, uint32_t H, uint32_t N, const uint16_t *quant, int use_rle,
+                     int huffman, uint8_t *out, size_t out_stride, size_t *out_bytes) {
+    if (!raws || !out || !out_bytes || count == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    IE_TRY(check_dims(W, H, N));
+    IE_TRY(check_quant(quant, (int)N));
+    const size_t npx = (size_t)W * H;
+    const size_t slot = ie_max_encoded_bytes(W, H, N, 1);
+    // sub-batches keep the staging footprint bounded (<= ~8 GiB of raw pixels in flight)
+    const uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(count, ((size_t)8 << 30) / (npx + slot)));
+    ie_session *s = nullptr;
+    IE_TRY(cached_session(&s, 0, W, H, N, sub));
+    IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, npx * sub));
+    IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, slot * sub));
+    cudaStream_t st = s->stream;
+    std::vector<unsigned long long> bits(sub);
+    for (uint32_t first = 0; first < count; first += sub) {
+        const uint32_t n = std::min(sub, count - first);
+        IE_CUDA(cudaMemcpyAsync(s->d_in, raws + (size_t)first * npx, npx * n, cudaMemcpyHostToDevice, st));
+        IE_TRY(encode_images_dev(s, s->d_in, npx, n, W, H, (int)N, quant, use_rle, huffman ? 0 : 1, 1, 0, 0, s->d_out, slot, slot, st));
+        IE_CUDA(cudaMemcpyAsync(bits.data(), s->d_counter, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        IE_TRY(read_err_flag(s, st));
+        for (uint32_t i = 0; i < n; i++) {
+            size_t bytes = (size_t)((bits[i] + 7) / 8);
+            const uint8_t *d_result = s->d_out + (size_t)i * slot;
+            if (huffman) {
+                IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, slot + 4096));
+                size_t hb = 0;
+                IE_TRY(ie_huffman_encode_dev(s, d_result, bytes, s->d_tmp, s->d_tmp_cap, &hb, st));
+                bytes = hb;
+                d_result = s->d_tmp;
+            }
+            out_bytes[first + i] = bytes;
+            if (bytes > out_stride) { set_error("output slot too small"); return IE_ENOSPC; }
+            IE_CUDA(cudaMemcpyAsync(out + (size_t)(first + i) * out_stride, d_result, bytes, cudaMemcpyDeviceToHost, st));
+            if (huffman) IE_CUDA(cudaStreamSynchronize(st));     // d_tmp is reused by the next image
+        }
+        IE_CUDA(cudaStreamSynchronize(st));
+    }
+    return IE_OK;
+}
+
+int ie_decode_images(const uint8_t *encs, size_t enc_stride, const size_t *enc_bytes, uint32_t count, uint32_t N, uint8_t *raws_out,
+                     size_t raw_stride, uint32_t *W, uint32_t *H) {
+    if (!encs || !enc_bytes || !raws_out || count == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    // streams of a batch are independent; each goes through the single-image path
+    for (uint32_t i = 0; i < count; i++) {
+        uint32_t w = 0, h = 0;
+        IE_TRY(ie_decode_image(encs + (size_t)i * enc_stride, enc_bytes[i], N, raws_out + (size_t)i * raw_stride, raw_stride, &w, &h));
+        if (W) *W = w;
+        if (H) *H = h;
+    }
+    return IE_OK;
+}
+
+int ie_decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, uint64_t start_bit, uint8_t *d_raw_out,
+                        size_t raw_cap, uint32_t *W, uint32_t *H, void *stream) {
+    if (!s || !d_enc || !d_raw_out) { set_error("NULL argument"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = (int)s->N;
+    // the header (<= 134 bytes) is parsed on the host
+    uint8_t hb[160];
+    const size_t first = (size_t)(start_bit / 8);
+    if (first >= enc_bytes) { set_error("start_bit beyond the stream"); return IE_EFORMAT; }
+    const size_t n = std::min(sizeof hb, enc_bytes - first);
+    IE_CUDA(cudaMemcpyAsync(hb, d_enc + first, n, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    ParsedHeader h;
+    parse_header(hb, n, (size_t)(start_bit % 8), N, h, 0);
+    h.end_bit += first * 8;
+    if (W) *W = h.W;
+    if (H) *H = h.H;
+    return decode_image_dev(s, d_enc, enc_bytes, (size_t)start_bit, N, h, d_raw_out, raw_cap, st);
+}
+
+int ie_decode_image(const uint8_t *enc, size_t enc_bytes, uint32_t N, uint8_t *raw_out, size_t raw_cap, uint32_t *W, uint32_t *H) {
+    if (!enc || !raw_out || enc_bytes == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    if (N != 4 && N != 8) { set_error("block size must be 4 or 8"); return IE_EINVAL; }
+    ie_session *s = nullptr;
+    IE_TRY(cached_session(&s, 1, 0, 0, N, 1));
+    cudaStream_t st = s->stream;
+    IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, enc_bytes + 16));
+    IE_CUDA(cudaMemcpyAsync(s->d_in, enc, enc_bytes, cudaMemcpyHostToDevice, st));
+    const uint8_t *d_plain = s->d_in;
+    size_t plain_bytes = enc_bytes;
+    uint64_t start_bit = 1;                                         // '0' = no Huffman table (Huffman.cpp:361-371)
+    if (enc[0] & 0x80) {
+        size_t cap = enc_bytes * 8 + 64;                            // a code is at least 1 bit per byte
+        IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, cap));
+        IE_TRY(ie_huffman_decode_dev(s, s->d_in, enc_bytes, s->d_tmp, s->d_tmp_cap, &plain_bytes, &start_bit, st));
+        d_plain = s->d_tmp;
+    }
+    uint32_t w = 0, h = 0;
+    // decode straight into a device buffer sized after the header is known
+    uint8_t hb[160];
+    const size_t n = std::min(sizeof hb, plain_bytes);
+    IE_CUDA(cudaMemcpyAsync(hb, d_plain, n, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    ParsedHeader ph;
+    parse_header(hb, n, (size_t)start_bit, (int)N, ph, 0);
+    w = ph.W; h = ph.H;
+    if (W) *W = w;
+    if (H) *H = h;
+    IE_TRY(check_dims(w, h, N));
+    if ((size_t)w * h > raw_cap) { set_error("raw_out too small"); return IE_ENOSPC; }
+    IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, (size_t)w * h));
+    IE_TRY(decode_image_dev(s, d_plain, plain_bytes, (size_t)start_bit, (int)N, ph, s->d_out, s->d_out_cap, st));
+    IE_TRY(read_err_flag(s, st));
+    IE_CUDA(cudaMemcpyAsync(raw_out, s->d_out, (size_t)w * h, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    return IE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// Shared declarations of the sm_100a block-codec kernels and their host launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/imageencoder_b200.h"
+
+namespace ie {
+
+constexpr int kMaxN = 8;
+constexpr int kMaxNN = 64;
+constexpr int kMB = 16;                 // MacroBlock size (Block.hpp:14)
+constexpr int kHdrWordsMax = 40;        // 1 + 5 + 64*16 + 31 + 45 bits < 40 words
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define IE_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) return ::ie::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define IE_TRY(call)                  \
+    do {                              \
+        int rc__ = (call);            \
+        if (rc__ != IE_OK) return rc__; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-block-size arithmetic tables, resident in HBM (read through L1, warp-uniform addresses).
+//   fw [uv*NN + ij] = fl(cs[i][u] * cs[j][v])                 forward product  (algo.cpp:318-319)
+//   inv[uv*NN + ij] = fl(fl(cc[uv] * cs[i][u]) * cs[j][v])    inverse product  (algo.cpp:352-354)
+//   cc [uv]         = fl(C(u) * C(v))                         (algo.cpp:294-297,325)
+//   zz [k]          = raster index of the k-th zigzag position (algo.cpp:68-87); izz = inverse
+// ---------------------------------------------------------------------------------------------------------
+struct BlockTables {
+    double fw[kMaxNN * kMaxNN];
+    double inv[kMaxNN * kMaxNN];
+    double cc[kMaxNN];
+    double cs[kMaxNN];
+    uint8_t zz[kMaxNN];
+    uint8_t izz[kMaxNN];
+};
+
+struct HostTables {
+    BlockTables t4, t8;
+};
+const HostTables &host_tables();
+
+// Quantisation matrix as the kernels take it (by value, in the kernel parameter block).
+struct QuantParam {
+    double m[kMaxNN];      // double(Q[u][v])   (MatrixReader.cpp:128)
+};
+
+// Header bits prepared on the host (ImageEncoder.cpp:84-94, MatrixReader.cpp:144-158, VideoEncoder.cpp:60-73),
+// MSB-first, zero padded.
+struct HeaderParam {
+    uint32_t words[kHdrWordsMax];
+    uint32_t bits;
+};
+// lead_bit: the '0' "no Huffman" bit of non-Huffman builds.  video: append frames/gop/merange (15 bits each).
+int build_header(HeaderParam &h, int N, const uint16_t *quant, int use_rle, uint32_t W, uint32_t H, int lead_bit,
+                 int video, uint32_t frames, uint32_t gop, uint32_t merange);
+
+struct DeviceState {
+    int device = -1;
+    BlockTables *d_t4 = nullptr, *d_t8 = nullptr;
+    int sm_count = 0;
+};
+int get_device_state(DeviceState **out);      // ie_init(current device) if needed
+
+// ---------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// util::bits_needed (utils.hpp:226-243) for a value that fits int16: minimal two's complement width.
+__device__ __forceinline__ int dev_bits_needed(int v) { return 33 - __clz(v ^ (v >> 31)); }
+// util::ffs (utils.hpp:210-216) with ffs(0) = 0
+__device__ __forceinline__ int dev_ffs(unsigned v) { return 32 - __clz(v); }
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+#endif
+
+}  // namespace ie

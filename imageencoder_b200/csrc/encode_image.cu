@@ -1,0 +1,155 @@
+// Fused image-block encode: one CTA per tile of consecutive blocks (raster order, ImageBase.cpp:187-199):
+//   pixels -> (-128) -> forward DCT -> quant divide/round -> zigzag -> RLE info        (lane per block)
+//   -> CTA scan of block bit counts -> decoupled look-back for the tile's stream offset
+//   -> chunk-centric gather/pack straight into the stream                              (thread per 128-bit chunk)
+// One pass over HBM: W*H bytes in, the stream out.  Replaces ImageEncoder.cpp:121-138 (parallel DCT loop + the
+// strictly serial streamEncoded loop) and Frame.cpp:141-158 (I-frames).
+#include "encode_image.cuh"
+
+namespace ie {
+
+template <int N, int BPL>
+__global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodeParams p) {
+    constexpr int NN = N * N;
+    constexpr int TB = kThreads * BPL;            // blocks per tile
+    constexpr int STRIDE = NN + 2;                // halfwords per block in the staging area (bank spread)
+    extern __shared__ __align__(16) unsigned char smem[];
+    short *s_coef = reinterpret_cast<short *>(smem);
+    unsigned *s_off = reinterpret_cast<unsigned *>(smem + (size_t)TB * STRIDE * sizeof(short));
+    unsigned char *s_w = reinterpret_cast<unsigned char *>(s_off + TB + 1);
+    unsigned char *s_len = s_w + TB;
+    __shared__ unsigned s_warp[kThreads / 32 + 1];
+    __shared__ unsigned long long s_bcast;
+    __shared__ unsigned s_tile;
+
+    const unsigned img = blockIdx.y;
+    ScanState st = p.scan;
+    st.tile_state += (size_t)img * p.tiles_per_image;
+    st.bnd += (size_t)img * p.tiles_per_image;
+    st.ticket += img;
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(st.ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const unsigned ntiles = p.tiles_per_image;
+    const unsigned first_blk = tile * TB;
+    const int nblk = min((unsigned)TB, p.nblocks - first_blk);
+
+    const uint8_t *src = p.src + (size_t)img * p.img_stride;
+    const BlockTables *tab = p.tab;
+
+    // ---- phase 1: transform + quantise + RLE info, lane per block ---------------------------------------
+    unsigned my_bits = 0;
+#pragma unroll 1
+    for (int r = 0; r < BPL; r++) {
+        const int lb = threadIdx.x * BPL + r;
+        if (lb >= nblk) { if (lb < TB) s_off[lb] = 0; continue; }
+        const unsigned gb = first_blk + lb;
+        const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
+        double x[NN];
+#pragma unroll
+        for (int y = 0; y < N; y++) {
+            const uint8_t *row = src + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N;
+            if (N == 8) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row));
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    x[y * N + k] = (double)(int)((v.x >> (8 * k)) & 0xff) - 128.0;       // Block.cpp:52-54, 141-143
+                    x[y * N + 4 + k] = (double)(int)((v.y >> (8 * k)) & 0xff) - 128.0;
+                }
+            } else {
+                const unsigned v = __ldg(reinterpret_cast<const unsigned *>(row));
+#pragma unroll
+                for (int k = 0; k < 4; k++) x[y * N + k] = (double)(int)((v >> (8 * k)) & 0xff) - 128.0;
+            }
+        }
+        short *cf = s_coef + (size_t)lb * STRIDE;
+        int lastnz = 0, prevnz = 0;      // (zigzag index + 1) of the last / of the last-but-final-position non-zero
+        unsigned orbits = 0;
+#pragma unroll 1
+        for (int uv = 0; uv < NN; uv++) {
+            const double e = fdct_coef_exact<NN>(tab->fw + uv * NN, x, tab->cc[uv]);
+            const double qd = round_half_away(__ddiv_rn(e, p.quant.m[uv]));               // Block.cpp:152
+            const int q = (int)(short)__double2int_rz(qd);                                // Block.cpp:205: int16_t(double)
+            const int k = tab->izz[uv];
+            cf[k] = (short)q;
+            if (q != 0) {
+                orbits |= (unsigned)(q ^ (q >> 31));
+                lastnz = max(lastnz, k + 1);
+                if (k < NN - 1) prevnz = max(prevnz, k + 1);
+            }
+        }
+        // Block.cpp:214-219, 231: data_bits = max(max bits_needed(nz), ffs(data)), data = last non-zero index + 1
+        int w = lastnz ? (33 - __clz(orbits)) : 0;
+        w = max(w, dev_ffs((unsigned)lastnz));
+        int len = lastnz;
+        if (p.use_rle) {
+            // Block.cpp:388-390: a full-length block whose last entry has leading zeroes loses that entry
+            if (lastnz == NN && prevnz != NN - 1) len = prevnz;
+        } else {
+            len = NN;                                                                     // Block.cpp:396
+        }
+        s_w[lb] = (unsigned char)w;
+        s_len[lb] = (unsigned char)len;
+        const unsigned bits = 4u + (p.use_rle ? w : 0) + (unsigned)len * (unsigned)w;
+        s_off[lb] = bits;
+        my_bits += bits;
+    }
+    __syncthreads();
+
+    // ---- phase 2: offsets ----------------------------------------------------------------------------------
+    unsigned T;
+    unsigned excl = cta_exclusive_scan(my_bits, s_warp, &T);
+#pragma unroll
+    for (int r = 0; r < BPL; r++) {
+        const int lb = threadIdx.x * BPL + r;
+        const unsigned b = s_off[lb];
+        s_off[lb] = excl;
+        excl += b;
+    }
+    if (threadIdx.x == kThreads - 1) s_off[TB] = T;
+    unsigned long long base = 0;
+    if (tile == 0) base = p.bit_counter[img];
+    const unsigned long long G = tile_lookback(st, tile, (unsigned long long)T + base, &s_bcast) + (tile == 0 ? base : 0ull);
+    // tile 0 published base + T as its inclusive prefix, so every G is an absolute stream position.
+    const bool last_tile = (tile == ntiles - 1);
+
+    // ---- phase 3: pack ---------------------------------------------------------------------------------------
+    if (!p.bits_only) {
+        BlockFieldTile ft;
+        ft.coef = s_coef; ft.w = s_w; ft.len = s_len; ft.off = s_off; ft.stride = STRIDE; ft.nblk = nblk; ft.rle = p.use_rle;
+        tile_write_chunks(ft, st, tile, tile == 0, last_tile, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
+    }
+    if (last_tile && threadIdx.x == 0) {
+        p.bit_counter[img] = G + T;
+        atomicExch(st.ticket, 0u);                 // every ticket of this launch has been taken
+    }
+}
+
+template <int N, int BPL>
+static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t stream) {
+    constexpr int TB = kThreads * BPL;
+    constexpr int STRIDE = N * N + 2;
+    const size_t smem = (size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 2 * TB;
+    static bool configured = false;
+    if (!configured) {
+        IE_CUDA(cudaFuncSetAttribute(encode_tiles_kernel<N, BPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(p.tiles_per_image, images);
+    encode_tiles_kernel<N, BPL><<<grid, kThreads, smem, stream>>>(p);
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
+unsigned encode_tile_blocks(int N) { return N == 8 ? kThreads * 1 : kThreads * 4; }
+
+int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream) {
+    if (N == 8) return launch_cfg<8, 1>(p, images, stream);
+    if (N == 4) return launch_cfg<4, 4>(p, images, stream);
+    set_error("block size must be 4 or 8");
+    return IE_EINVAL;
+}
+
+}  // namespace ie

@@ -1,0 +1,497 @@
+// Byte-wise Huffman stage (Huffman.cpp / Huffman.hpp of the reference) on a device-resident stream.
+//
+//   byte_hist_kernel      256-bin histogram, warp-aggregated, plus the position of every symbol's FIRST occurrence
+//                         (Huffman.cpp:236-243: the reference's tie-breaking depends on insertion order)
+//   host                  the 256-entry tree and dictionary, built with the same libstdc++ containers fed in the same
+//                         order as the reference (Huffman.cpp:246-272) -- tie order is *defined* by those containers
+//   huff_encode_kernel    per-byte code length -> CTA scan -> look-back -> chunk-centric pack after the dictionary
+//                         header (Huffman.cpp:314-319), same append contract as the block packer (pack.cuh)
+//   shift_copy_kernel     the "no extra compression" revert: '0' bit + the input bytes (Huffman.cpp:329-341)
+//   huff_decode_kernel    table-driven decode (Huffman.cpp:190-204, 376-383)
+#include <algorithm>
+#include <cstring>
+#include <queue>
+#include <unordered_map>
+#include <vector>
+
+#include "api_internal.cuh"
+
+namespace ie {
+
+constexpr int kHuffTileBytes = kThreads * 16;
+
+// ---------------------------------------------------------------------------------------------------------
+// histogram + first occurrence
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t *__restrict__ in, size_t n, unsigned *hist,
+                                                        unsigned long long *first_pos) {
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_first[256];
+    s_hist[threadIdx.x] = 0;
+    s_first[threadIdx.x] = ~0ull;
+    __syncthreads();
+    const size_t nvec = (n + 15) / 16;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec + 31; v += (size_t)gridDim.x * blockDim.x) {
+        // keep whole warps in the loop so the match below is convergent
+        const size_t wbase = v - (threadIdx.x & 31);
+        if (wbase >= nvec) break;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        int valid = 0;
+        if (v < nvec) {
+            const size_t b = v * 16;
+            if (b + 16 <= n) { q = __ldg(reinterpret_cast<const uint4 *>(in) + v); valid = 16; }
+            else {
+                unsigned w[4] = {0, 0, 0, 0};
+                valid = (int)(n - b);
+                for (int i = 0; i < valid; i++) w[i >> 2] |= (unsigned)in[b + i] << (8 * (i & 3));
+                q = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        const unsigned words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const unsigned byte = (words[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            const bool ok = i < valid;
+            // warp aggregation: lanes holding the same byte value elect their lowest lane (= lowest position)
+            const unsigned key = ok ? byte : 0x100u + (threadIdx.x & 31);
+            const unsigned m = __match_any_sync(0xffffffffu, key);
+            if (ok && (unsigned)(threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
+                atomicAdd(&s_hist[byte], (unsigned)__popc(m));
+                atomicMin(&s_first[byte], (unsigned long long)(v * 16 + i));
+            }
+        }
+    }
+    __syncthreads();
+    if (s_hist[threadIdx.x]) {
+        atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
+        atomicMin(&first_pos[threadIdx.x], s_first[threadIdx.x]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// encode
+// ---------------------------------------------------------------------------------------------------------
+struct HuffCodes {
+    unsigned word[256];
+    unsigned char len[256];
+};
+
+struct ByteCodeTile {
+    const unsigned char *bytes;      // shared: the tile's input bytes
+    int nbytes;
+    const unsigned *grp_off;         // shared: [kThreads + 1] exclusive bit offsets of the 16-byte groups
+    const unsigned *word;            // shared [256]
+    const unsigned char *len;        // shared [256]
+};
+
+__device__ __forceinline__ uint4 gather_chunk(const ByteCodeTile &t, long long ls) {
+    unsigned ow0 = 0, ow1 = 0, ow2 = 0, ow3 = 0;
+    int widx = 0, nacc = 0;
+    unsigned long long acc = 0;
+    if (ls < 0) {
+        const int skip = (int)(-ls);
+        widx = skip >> 5;
+        nacc = skip & 31;
+        ls = 0;
+    }
+    const unsigned total = t.grp_off[kThreads];
+    if ((unsigned long long)ls < (unsigned long long)total) {
+        int lo = 0, hi = kThreads;                       // largest g with grp_off[g] <= ls
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (t.grp_off[mid] <= (unsigned)ls) lo = mid; else hi = mid;
+        }
+        int i = lo * 16;
+        unsigned pos = t.grp_off[lo];
+        while (i < t.nbytes && pos + t.len[t.bytes[i]] <= (unsigned)ls) { pos += t.len[t.bytes[i]]; i++; }
+        int fo = (int)((unsigned)ls - pos);
+        for (; i < t.nbytes && widx < 4; i++) {
+            const unsigned sym = t.bytes[i];
+            int fw = t.len[sym];
+            unsigned long long v = t.word[sym];
+            if (fo) { fw -= fo; v &= (1ull << fw) - 1ull; fo = 0; }
+            acc = (acc << fw) | v;
+            nacc += fw;
+            while (nacc >= 32 && widx < 4) {
+                const unsigned word = (unsigned)(acc >> (nacc - 32));
+                if (widx == 0) ow0 = word; else if (widx == 1) ow1 = word; else if (widx == 2) ow2 = word; else ow3 = word;
+                widx++;
+                nacc -= 32;
+            }
+        }
+    }
+    if (widx < 4 && nacc > 0) {
+        const unsigned word = (unsigned)(acc << (32 - nacc));
+        if (widx == 0) ow0 = word; else if (widx == 1) ow1 = word; else if (widx == 2) ow2 = word; else ow3 = word;
+    }
+    return make_uint4(__byte_perm(ow0, 0, 0x0123), __byte_perm(ow1, 0, 0x0123), __byte_perm(ow2, 0, 0x0123), __byte_perm(ow3, 0, 0x0123));
+}
+
+struct HuffEncodeParams {
+    const uint8_t *in;
+    size_t n;
+    unsigned ntiles;
+    const HuffCodes *codes;          // device
+    uint8_t *out;
+    size_t out_cap;
+    unsigned long long *bit_counter;
+    int *err;
+    ScanState scan;
+};
+
+__global__ void __launch_bounds__(kThreads) huff_encode_kernel(const HuffEncodeParams p) {
+    __shared__ __align__(16) unsigned char s_bytes[kHuffTileBytes];
+    __shared__ unsigned s_grp[kThreads + 1];
+    __shared__ unsigned s_word[256];
+    __shared__ unsigned char s_len[256];
+    __shared__ unsigned s_warp[kThreads / 32 + 1];
+    __shared__ unsigned long long s_bcast;
+    __shared__ unsigned s_tile;
+    ScanState st = p.scan;
+    if (threadIdx.x == 0) s_tile = atomicAdd(st.ticket, 1u);
+    s_word[threadIdx.x] = p.codes->word[threadIdx.x];
+    s_len[threadIdx.x] = p.codes->len[threadIdx.x];
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const size_t base_byte = (size_t)tile * kHuffTileBytes;
+    const int nbytes = (int)min((size_t)kHuffTileBytes, p.n - base_byte);
+
+    // stage 16 bytes per thread, sum their code lengths
+    unsigned bits = 0;
+    {
+        const int b0 = threadIdx.x * 16;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (b0 + 16 <= nbytes && ((uintptr_t)(p.in + base_byte) % 16 == 0)) {
+            q = __ldg(reinterpret_cast<const uint4 *>(p.in + base_byte) + threadIdx.x);
+        } else if (b0 < nbytes) {
+            unsigned w[4] = {0, 0, 0, 0};
+            for (int i = 0; i < 16 && b0 + i < nbytes; i++) w[i >> 2] |= (unsigned)p.in[base_byte + b0 + i] << (8 * (i & 3));
+            q = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        reinterpret_cast<uint4 *>(s_bytes)[threadIdx.x] = q;
+        const unsigned words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (b0 + i < nbytes) bits += s_len[(words[i >> 2] >> (8 * (i & 3))) & 0xffu];
+    }
+    unsigned T;
+    const unsigned excl = cta_exclusive_scan(bits, s_warp, &T);
+    s_grp[threadIdx.x] = excl;
+    if (threadIdx.x == kThreads - 1) s_grp[kThreads] = T;
+    unsigned long long base = 0;
+    if (tile == 0) base = *p.bit_counter;
+    const unsigned long long G = tile_lookback(st, tile, (unsigned long long)T + base, &s_bcast) + (tile == 0 ? base : 0ull);
+    const bool last_tile = (tile == p.ntiles - 1);
+    ByteCodeTile bt;
+    bt.bytes = s_bytes; bt.nbytes = nbytes; bt.grp_off = s_grp; bt.word = s_word; bt.len = s_len;
+    tile_write_chunks(bt, st, tile, tile == 0, last_tile, G, T, p.out, p.out_cap, p.err);
+    if (last_tile && threadIdx.x == 0) {
+        *p.bit_counter = G + T;
+        atomicExch(st.ticket, 0u);
+    }
+}
+
+// out bits [shift, shift + 8 n) = in bytes; out bits [0, shift) = 0; whole 32-bit words, zero padded.
+__global__ void shift_copy_kernel(const uint8_t *__restrict__ in, size_t n, uint8_t *out, unsigned shift) {
+    const size_t nwords = (n * 8 + shift + 31) / 32;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (size_t)gridDim.x * blockDim.x) {
+        // out word w covers stream bits [32w, 32w+32) = in bits [32w - shift, ...)
+        unsigned long long window = 0;     // in bytes 4w-1 .. 4w+3 (5 bytes), MSB first
+        for (int i = -1; i < 4; i++) {
+            const long long bi = (long long)w * 4 + i;
+            const unsigned byte = (bi >= 0 && (size_t)bi < n) ? in[bi] : 0u;
+            window = (window << 8) | byte;
+        }
+        // window (40 bits) starts at in bit 32w - 8; skip 8 - shift bits, keep 32, drop the low `shift` bits
+        const unsigned v = (unsigned)((window >> shift) & 0xffffffffull);
+        reinterpret_cast<unsigned *>(out)[w] = __byte_perm(v, 0, 0x0123);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// decode (one lane; 12-bit primary lookup table, tree walk for longer codes)
+// ---------------------------------------------------------------------------------------------------------
+struct HuffDecodeTables {
+    // entry: (len << 16) | symbol for codes <= 12 bits; 0xFFFF0000 | node index for longer codes; 0 = invalid
+    unsigned lut[4096];
+    short child[512][2];       // tree for the slow path: >= 0 node index, -(sym+1)-1 ... see host builder
+    int nodes;
+};
+
+__global__ void huff_decode_kernel(const uint8_t *__restrict__ in, size_t n, unsigned long long start_bit,
+                                   const HuffDecodeTables *tab, uint8_t *out, size_t out_cap, unsigned long long *out_count, int *err) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long total = (unsigned long long)n * 8ull;
+    unsigned long long pos = start_bit;
+    size_t o = 0;
+    while (pos < total) {
+        // 32-bit window at pos (zero beyond the end: BitStream.cpp:17-20)
+        const unsigned long long b = pos >> 3;
+        unsigned long long win = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) win = (win << 8) | ((b + i < n) ? (unsigned long long)__ldg(in + b + i) : 0ull);
+        const unsigned w32 = (unsigned)(win >> (16 - (pos & 7)));     // 32 bits starting at pos
+        unsigned e = tab->lut[w32 >> 20];
+        unsigned sym, len;
+        if ((e >> 16) != 0xFFFFu) {
+            if (e == 0) { atomicExch(err, IE_EFORMAT); break; }
+            sym = e & 0xffffu;
+            len = e >> 16;
+        } else {
+            int node = (int)(e & 0xffffu);
+            len = 12;
+            sym = 0;
+            bool found = false;
+            while (len < 32) {
+                const int bit = (w32 >> (31 - len)) & 1;
+                const int c = tab->child[node][bit];
+                len++;
+                if (c == -1) { break; }
+                if (c <= -2) { sym = (unsigned)(-c - 2); found = true; break; }
+                node = c;
+            }
+            if (!found) { atomicExch(err, IE_EFORMAT); break; }
+        }
+        if (o >= out_cap) { atomicExch(err, IE_ENOSPC); break; }
+        out[o++] = (uint8_t)sym;
+        pos = min(pos + len, total);              // a final code may run past the end: zero bits, no advance
+    }
+    *out_count = o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: tree / dictionary exactly as the reference builds them
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct HNode { uint8_t data; size_t freq; HNode *left, *right; };
+struct HNodeCmp { bool operator()(const HNode *a, const HNode *b) const { return a->freq > b->freq; } };   // Huffman.hpp:70-74
+struct HCode { uint32_t word, len; };
+
+void walk(const HNode *n, uint32_t word, uint32_t len, std::unordered_map<uint8_t, HCode> &dict) {       // Huffman.cpp:79-104
+    if (!n) return;
+    if (!n->left && !n->right) { dict[n->data] = HCode{word, len}; return; }
+    walk(n->left, word << 1, len + 1, dict);
+    walk(n->right, (word << 1) | 1u, len + 1, dict);
+}
+void destroy(HNode *n) { if (!n) return; destroy(n->left); destroy(n->right); delete n; }
+
+struct HostBitWriter {
+    std::vector<uint8_t> buf;
+    size_t pos = 0;
+    void put(unsigned len, uint32_t v) {
+        for (unsigned p = 0; p < len; p++) {
+            if ((pos >> 3) >= buf.size()) buf.resize(buf.size() + 256, 0);
+            if ((v >> (len - 1 - p)) & 1u) buf[pos >> 3] |= uint8_t(1u << (7 - (pos & 7)));
+            pos++;
+        }
+    }
+};
+}  // namespace
+
+// hist/first -> codes + dictionary header bits.  Returns IE_EINVAL when a code would exceed 32 bits (the reference's
+// uint32 code words overflow there, Huffman.cpp:86-88).
+static int build_dictionary(const unsigned *hist, const unsigned long long *first, HuffCodes &codes, HostBitWriter &hdr) {
+    std::vector<int> syms;
+    for (int i = 0; i < 256; i++) if (hist[i]) syms.push_back(i);
+    if (syms.empty()) { set_error("empty input for the Huffman stage"); return IE_EINVAL; }
+    std::sort(syms.begin(), syms.end(), [&](int a, int b) { return first[a] < first[b]; });
+    std::unordered_map<uint8_t, uint32_t> freqs;                           // Huffman.cpp:237-243 (insertion = first occurrence)
+    for (int s : syms) freqs[(uint8_t)s] = hist[s];
+    std::priority_queue<HNode *, std::vector<HNode *>, HNodeCmp> pq;       // Huffman.cpp:246-251
+    for (const auto &pr : freqs) pq.push(new HNode{pr.first, pr.second, nullptr, nullptr});
+    while (pq.size() > 1) {                                                // Huffman.cpp:253-260
+        HNode *l = pq.top(); pq.pop();
+        HNode *r = pq.top(); pq.pop();
+        pq.push(new HNode{0xFF, l->freq + r->freq, l, r});
+    }
+    HNode *root = pq.top();
+    std::unordered_map<uint8_t, HCode> dict;
+    walk(root, 0, 0, dict);                                                // Huffman.cpp:266
+    destroy(root);
+    std::vector<std::pair<uint8_t, HCode>> sorted(dict.begin(), dict.end());   // Huffman.cpp:269
+    std::sort(sorted.begin(), sorted.end(),                                 // Huffman.cpp:272 (unstable, len descending)
+              [](const std::pair<uint8_t, HCode> &a, const std::pair<uint8_t, HCode> &b) { return a.second.len > b.second.len; });
+    std::unordered_map<uint32_t, uint32_t> bit_freqs;
+    for (const auto &w : sorted) bit_freqs[w.second.len]++;
+    uint32_t seq_len = 0, bit_len = 0;
+    for (const auto &w : sorted) {                                         // Huffman.cpp:298-309
+        if (w.second.len > 32) { set_error("Huffman code longer than 32 bits (undefined in the reference)"); return IE_EINVAL; }
+        if (seq_len == 0) {
+            bit_len = w.second.len;
+            seq_len = bit_freqs[bit_len];
+            hdr.put(8, 0x80u | (seq_len & 0x7Fu));                         // Huffman.cpp:36-46
+            hdr.put(4, bit_len & 0xFu);
+        }
+        hdr.put(8, w.first);
+        hdr.put(bit_len, w.second.word);
+        seq_len--;
+    }
+    hdr.put(1, 0);                                                         // Huffman.cpp:311
+    memset(&codes, 0, sizeof codes);
+    for (const auto &pr : dict) { codes.word[pr.first] = pr.second.word; codes.len[pr.first] = (unsigned char)pr.second.len; }
+    return IE_OK;
+}
+
+static int ensure_scratch(ie_session *s, size_t need) { return session_reserve(&s->d_scratch, &s->scratch_cap, need); }
+
+}  // namespace ie
+
+using namespace ie;
+
+extern "C" {
+
+int ie_byte_histogram_dev(const uint8_t *d_in, size_t n, uint32_t *hist, uint64_t *first_pos, void *stream) {
+    if (!d_in || !hist || !first_pos) { set_error("NULL argument"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceState *dev;
+    IE_TRY(get_device_state(&dev));
+    uint8_t *d = nullptr;
+    IE_CUDA(cudaMalloc(&d, 256 * 4 + 256 * 8));
+    unsigned *d_hist = reinterpret_cast<unsigned *>(d + 256 * 8);
+    unsigned long long *d_first = reinterpret_cast<unsigned long long *>(d);
+    cudaMemsetAsync(d_hist, 0, 256 * 4, st);
+    cudaMemsetAsync(d_first, 0xff, 256 * 8, st);
+    const int grid = (int)std::min<size_t>((n / 16 + 255) / 256 + 1, (size_t)dev->sm_count * 8);
+    byte_hist_kernel<<<grid, 256, 0, st>>>(d_in, n, d_hist, d_first);
+    count_launch();
+    cudaMemcpyAsync(hist, d_hist, 256 * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(first_pos, d_first, 256 * 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "byte histogram", __FILE__, __LINE__);
+    return IE_OK;
+}
+
+int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap, size_t *out_bytes,
+                          void *stream) {
+    if (!s || !d_in || !d_out || !out_bytes || n == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    if ((uintptr_t)d_out % 16) { set_error("stream buffers must be 16-byte aligned"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    // scratch layout: first[256] u64 | hist[256] u32 | HuffCodes | counter u64
+    const size_t need = 256 * 8 + 256 * 4 + sizeof(HuffCodes) + 64;
+    IE_TRY(ensure_scratch(s, need));
+    unsigned long long *d_first = reinterpret_cast<unsigned long long *>(s->d_scratch);
+    unsigned *d_hist = reinterpret_cast<unsigned *>(s->d_scratch + 256 * 8);
+    HuffCodes *d_codes = reinterpret_cast<HuffCodes *>(s->d_scratch + 256 * 8 + 256 * 4);
+    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+
+    IE_CUDA(cudaMemsetAsync(d_hist, 0, 256 * 4, st));
+    IE_CUDA(cudaMemsetAsync(d_first, 0xff, 256 * 8, st));
+    const int grid = (int)std::min<size_t>((n / 16 + 255) / 256 + 1, (size_t)s->dev->sm_count * 8);
+    byte_hist_kernel<<<grid, 256, 0, st>>>(d_in, n, d_hist, d_first);
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    unsigned hist[256];
+    unsigned long long first[256];
+    IE_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaMemcpyAsync(first, d_first, sizeof first, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+
+    HuffCodes codes;
+    HostBitWriter hdr;
+    IE_TRY(build_dictionary(hist, first, codes, hdr));
+    const size_t hdr_bytes16 = (hdr.pos + 127) / 128 * 16;
+    hdr.buf.resize(hdr_bytes16, 0);
+    if (out_cap < hdr_bytes16 + 16) { set_error("output buffer too small"); return IE_ENOSPC; }
+    IE_CUDA(cudaMemcpyAsync(d_out, hdr.buf.data(), hdr_bytes16, cudaMemcpyHostToDevice, st));
+    IE_CUDA(cudaMemcpyAsync(d_codes, &codes, sizeof codes, cudaMemcpyHostToDevice, st));
+    const unsigned ntiles = (unsigned)((n + kHuffTileBytes - 1) / kHuffTileBytes);
+    IE_TRY(session_ensure_scan(s, 1, ntiles));
+    const unsigned long long hb = hdr.pos;
+    IE_CUDA(cudaMemcpyAsync(s->d_counter, &hb, sizeof hb, cudaMemcpyHostToDevice, st));
+    HuffEncodeParams p;
+    p.in = d_in; p.n = n; p.ntiles = ntiles; p.codes = d_codes; p.out = d_out; p.out_cap = out_cap;
+    p.bit_counter = s->d_counter; p.err = s->d_err; p.scan = s->scan_state();
+    huff_encode_kernel<<<ntiles, kThreads, 0, st>>>(p);
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    IE_CUDA(cudaMemcpyAsync(s->h_pinned, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    IE_TRY(read_err_flag(s, st));
+    size_t total = (size_t)((s->h_pinned[0] + 7) / 8);
+    if (n < total) {                                                       // Huffman.cpp:329-341
+        total = n + 1;
+        if (out_cap < (total + 3) / 4 * 4) { set_error("output buffer too small"); return IE_ENOSPC; }
+        const size_t nwords = (n * 8 + 1 + 31) / 32;
+        shift_copy_kernel<<<(unsigned)std::min<size_t>((nwords + 255) / 256, 65535), 256, 0, st>>>(d_in, n, d_out, 1);
+        count_launch();
+        IE_CUDA(cudaGetLastError());
+    }
+    *out_bytes = total;
+    return IE_OK;
+}
+
+int ie_huffman_decode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap, size_t *out_bytes,
+                          uint64_t *start_bit, void *stream) {
+    if (!s || !d_in || !d_out || !out_bytes || !start_bit || n == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+    // dictionary header: at most 256 * (8 + 15) + 16 * 12 + 1 bits < 1 KiB (4-bit length field); parse it on the host
+    std::vector<uint8_t> head(std::min<size_t>(n, 1024));
+    IE_CUDA(cudaMemcpyAsync(head.data(), d_in, head.size(), cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    size_t pos = 0;
+    auto get_bit = [&]() -> uint32_t { if ((pos >> 3) >= head.size()) return 0; uint32_t b = (head[pos >> 3] >> (7 - (pos & 7))) & 1u; pos++; return b; };
+    auto get = [&](unsigned l) { uint32_t v = 0; for (unsigned i = 0; i < l; i++) v |= get_bit() << (l - i - 1); return v; };
+    std::vector<HuffDecodeTables> tabv(1);
+    HuffDecodeTables &t = tabv[0];
+    memset(&t, 0, sizeof t);
+    for (auto &c : t.child) c[0] = c[1] = -1;
+    t.nodes = 1;                                                           // node 0 = root (Huffman.cpp:123)
+    bool any = false;
+    while (get_bit()) {                                                    // Huffman.cpp:57-65, 128-142
+        uint32_t seq = get(7), bl = get(4);
+        while (seq--) {
+            const uint32_t key = get(8), word = get(bl);
+            if (bl == 0) { set_error("zero-length Huffman code (undefined in the reference decoder)"); return IE_EFORMAT; }
+            int cur = 0;                                                   // Huffman.cpp:153-180
+            for (int b = (int)bl - 1; b >= 0; b--) {
+                const int dir = (word >> b) & 1;
+                if (b == 0) { t.child[cur][dir] = (short)(-(int)key - 2); }
+                else {
+                    if (t.child[cur][dir] < 0) {
+                        if (t.nodes >= 512) { set_error("Huffman dictionary too large"); return IE_EFORMAT; }
+                        t.child[cur][dir] = (short)t.nodes++;
+                    }
+                    cur = t.child[cur][dir];
+                }
+            }
+            any = true;
+        }
+    }
+    if (!any) {                                                            // pass-through (Huffman.cpp:361-371)
+        if (out_cap < n) { set_error("output buffer too small"); return IE_ENOSPC; }
+        IE_CUDA(cudaMemcpyAsync(d_out, d_in, n, cudaMemcpyDeviceToDevice, st));
+        *out_bytes = n;
+        *start_bit = pos;
+        return IE_OK;
+    }
+    // primary 12-bit table by walking the tree for every prefix
+    for (unsigned pre = 0; pre < 4096; pre++) {
+        int cur = 0;
+        unsigned entry = 0;
+        for (int l = 0; l < 12; l++) {
+            const int dir = (pre >> (11 - l)) & 1;
+            const int c = t.child[cur][dir];
+            if (c == -1) { entry = 0; cur = -1; break; }
+            if (c <= -2) { entry = ((unsigned)(l + 1) << 16) | (unsigned)(-c - 2); cur = -1; break; }
+            cur = c;
+        }
+        if (cur >= 0) entry = 0xFFFF0000u | (unsigned)cur;
+        t.lut[pre] = entry;
+    }
+    const size_t need = sizeof(HuffDecodeTables) + 64;
+    IE_TRY(ensure_scratch(s, need));
+    HuffDecodeTables *d_tab = reinterpret_cast<HuffDecodeTables *>(s->d_scratch);
+    unsigned long long *d_count = reinterpret_cast<unsigned long long *>(s->d_scratch + sizeof(HuffDecodeTables));
+    IE_CUDA(cudaMemcpyAsync(d_tab, &t, sizeof t, cudaMemcpyHostToDevice, st));
+    huff_decode_kernel<<<1, 32, 0, st>>>(d_in, n, (unsigned long long)pos, d_tab, d_out, out_cap, d_count, s->d_err);
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    IE_CUDA(cudaMemcpyAsync(s->h_pinned, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    IE_TRY(read_err_flag(s, st));
+    *out_bytes = (size_t)s->h_pinned[0];
+    *start_bit = 0;
+    return IE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+// Tile-level bitstream append: CTA-wide exclusive scan of per-block bit counts, decoupled look-back across
+// tiles for the global bit offset, and an output-chunk-centric gather that writes the variable-length fields
+// MSB-first straight into the stream with 128-bit stores.  Replaces the reference's strictly serial
+// Block::streamEncoded -> BitStreamWriter::put -> put_bit chain (Block.cpp:371-413, BitStream.cpp:61-77,
+// ImageEncoder.cpp:135-138).
+//
+// Stream contract (all "append" kernels share it):
+//   * a stream buffer is addressed in 128-bit chunks; bit 0 is the MSB of byte 0.
+//   * a launch appends bits [B, B+T): B is read from a device-resident counter (+ a launch constant);
+//     the chunk holding bit B is merged (OR) with what an EARLIER launch left there, interior chunks are
+//     written whole, the last chunk is written zero padded (the reference's pad bits are 0: utils.hpp:443-446).
+//   * inside a launch, a chunk shared by two neighbouring tiles is combined through a small hand-off record
+//     (TileBoundary); the second arriver writes the chunk.  No atomics on the stream itself, no pre-zeroing.
+#pragma once
+#include "common.cuh"
+
+namespace ie {
+
+constexpr int kThreads = 256;
+constexpr int kChunkBits = 128;
+
+// status word of the decoupled look-back: [epoch:24][flag:2][value:38]
+constexpr unsigned long long kFlagAggregate = 1ull, kFlagPrefix = 2ull;
+constexpr int kValueBits = 38;
+constexpr unsigned long long kValueMask = (1ull << kValueBits) - 1;
+
+struct TileBoundary {
+    unsigned w[4];
+    unsigned count;
+    unsigned pad[3];
+};
+
+struct ScanState {
+    unsigned long long *tile_state;   // [max_tiles]
+    TileBoundary *bnd;                // [max_tiles]
+    unsigned *ticket;                 // dynamic tile id
+    unsigned epoch;                   // differs from the previous launch on these arrays
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned long long make_state(unsigned epoch, unsigned long long flag, unsigned long long v) {
+    return ((unsigned long long)(epoch & 0xFFFFFFu) << 40) | (flag << kValueBits) | (v & kValueMask);
+}
+
+// CTA-wide exclusive scan of one value per thread.  Returns the exclusive prefix; *total = CTA sum (all threads).
+__device__ __forceinline__ unsigned cta_exclusive_scan(unsigned v, unsigned *s_warp /*[kThreads/32 + 1]*/, unsigned *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned ws = (lane < kThreads / 32) ? s_warp[lane] : 0u;
+        unsigned wi = ws;
+#pragma unroll
+        for (int d = 1; d < kThreads / 32; d <<= 1) {
+            unsigned o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        if (lane < kThreads / 32) s_warp[lane] = wi - ws;
+        if (lane == kThreads / 32 - 1) s_warp[kThreads / 32] = wi;
+    }
+    __syncthreads();
+    *total = s_warp[kThreads / 32];
+    return s_warp[wid] + inc - v;
+}
+
+// Decoupled look-back (single-pass chained scan).  Called by every thread of the CTA; returns the exclusive prefix
+// (sum of the totals of tiles 0..tile-1).  Tiles get their ids from a ticket so every predecessor is already running.
+__device__ __forceinline__ unsigned long long tile_lookback(const ScanState &st, unsigned tile, unsigned long long total,
+                                                            unsigned long long *s_bcast) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_relaxed_u64(&st.tile_state[0], make_state(st.epoch, kFlagPrefix, total));
+        } else {
+            if (lane == 0) st_relaxed_u64(&st.tile_state[tile], make_state(st.epoch, kFlagAggregate, total));
+            int base = (int)tile - 1;
+            const unsigned long long ep = (unsigned long long)(st.epoch & 0xFFFFFFu);
+            while (true) {
+                const int idx = base - lane;
+                unsigned long long s = 0;
+                if (idx >= 0) {
+                    // every predecessor already runs (ticket order), so this terminates
+                    do {
+                        s = ld_relaxed_u64(&st.tile_state[idx]);
+                    } while ((s >> 40) != ep || ((s >> kValueBits) & 3ull) == 0ull);
+                }
+                __syncwarp();
+                const bool is_prefix = (idx >= 0) && (((s >> kValueBits) & 3ull) == kFlagPrefix);
+                const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+                // lanes from the nearest predecessor (lane 0) up to and including the first published prefix contribute
+                const int first = pm ? (__ffs(pm) - 1) : 31;
+                unsigned long long c = (idx >= 0 && lane <= first) ? (s & kValueMask) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                excl += c;
+                if (pm || base - 32 < 0) break;
+                base -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(&st.tile_state[tile], make_state(st.epoch, kFlagPrefix, excl + total));
+        }
+        if (lane == 0) *s_bcast = excl;
+    }
+    __syncthreads();
+    return *s_bcast;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Field source for a tile of transform blocks (image blocks, I/P-frame micro blocks).
+//   per block b (tile local): s_w[b] = bit_len, s_len[b] = length field, coefficients int16 in zigzag order
+//   fields: [4: bit_len & 15] [w: length (if rle)] [w * length: coefficients]        (Block.cpp:381-407)
+// ---------------------------------------------------------------------------------------------------------
+struct BlockFieldTile {
+    const short *coef;          // [nblk][stride] (shared memory)
+    const unsigned char *w;     // [nblk]
+    const unsigned char *len;   // [nblk]
+    const unsigned *off;        // [nblk + 1] exclusive bit offsets inside the tile
+    int stride;                 // halfwords
+    int nblk;
+    int rle;
+};
+
+__device__ __forceinline__ int upper_block(const unsigned *off, int n, unsigned p) {
+    // largest b in [0, n) with off[b] <= p   (off is non-decreasing, off[0] == 0, p < off[n])
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= p) lo = mid; else hi = mid;
+    }
+    // blocks are never empty (>= 4 bits) so off is strictly increasing
+    return lo;
+}
+
+// Produces the 128-bit chunk whose first bit is tile-local bit `ls` (may be negative: leading bits stay 0).
+__device__ __forceinline__ uint4 gather_chunk(const BlockFieldTile &t, long long ls) {
+    unsigned ow0 = 0, ow1 = 0, ow2 = 0, ow3 = 0;
+    int widx = 0, nacc = 0;
+    unsigned long long acc = 0;
+    if (ls < 0) {
+        const int skip = (int)(-ls);
+        widx = skip >> 5;
+        nacc = skip & 31;
+        ls = 0;
+    }
+    const unsigned total = t.off[t.nblk];
+    if ((unsigned long long)ls < (unsigned long long)total) {
+        int b = upper_block(t.off, t.nblk, (unsigned)ls);
+        int rel = (int)((unsigned)ls - t.off[b]);
+        const int hsf = t.rle ? 2 : 1;
+        while (widx < 4 && b < t.nblk) {
+            const int w = t.w[b];
+            const int len = t.len[b];
+            const unsigned mask = (w >= 32) ? 0xffffffffu : ((1u << w) - 1u);
+            const short *cf = t.coef + (size_t)b * t.stride;
+            const int nfields = hsf + len;
+            int f, fo;
+            if (rel < 4) { f = 0; fo = rel; }
+            else if (t.rle && rel < 4 + w) { f = 1; fo = rel - 4; }
+            else {
+                const int r2 = rel - (t.rle ? 4 + w : 4);
+                const int k = (w > 0) ? (r2 / w) : 0;
+                f = hsf + k;
+                fo = r2 - k * w;
+            }
+            rel = 0;
+            for (; f < nfields && widx < 4; f++) {
+                unsigned v;
+                int fw;
+                if (f == 0) { v = (unsigned)w & 15u; fw = 4; }
+                else if (f < hsf) { v = (unsigned)len & mask; fw = w; }
+                else { v = (unsigned)(int)cf[f - hsf] & mask; fw = w; }
+                if (fo) { fw -= fo; v &= (1u << fw) - 1u; fo = 0; }
+                acc = (acc << fw) | v;
+                nacc += fw;
+                if (nacc >= 32) {
+                    const unsigned word = (unsigned)(acc >> (nacc - 32));
+                    if (widx == 0) ow0 = word; else if (widx == 1) ow1 = word; else if (widx == 2) ow2 = word; else ow3 = word;
+                    widx++;
+                    nacc -= 32;
+                }
+            }
+            b++;
+        }
+    }
+    if (widx < 4 && nacc > 0) {
+        const unsigned word = (unsigned)(acc << (32 - nacc));
+        if (widx == 0) ow0 = word; else if (widx == 1) ow1 = word; else if (widx == 2) ow2 = word; else ow3 = word;
+    }
+    // stream bit 0 is the MSB of byte 0 -> big-endian words
+    return make_uint4(__byte_perm(ow0, 0, 0x0123), __byte_perm(ow1, 0, 0x0123), __byte_perm(ow2, 0, 0x0123), __byte_perm(ow3, 0, 0x0123));
+}
+
+// Writes the tile's bits [G, G+T) into `out`.  first_tile/last_tile refer to the launch.  See the contract above.
+template <class Tile>
+__device__ __forceinline__ void tile_write_chunks(const Tile &t, const ScanState &st, unsigned tile, bool first_tile, bool last_tile,
+                                                  unsigned long long G, unsigned T, uint8_t *out, unsigned long long out_cap_bytes,
+                                                  int *d_err) {
+    if (T == 0) return;
+    const unsigned long long c0 = G / kChunkBits, c1 = (G + T - 1) / kChunkBits;
+    const bool head_shared = (G % kChunkBits) != 0;
+    const bool tail_shared = ((G + T) % kChunkBits) != 0 && !last_tile;
+    for (unsigned long long c = c0 + threadIdx.x; c <= c1; c += kThreads) {
+        const long long ls = (long long)(c * kChunkBits) - (long long)G;
+        uint4 v = gather_chunk(t, ls);
+        if ((c + 1) * 16ull > out_cap_bytes) { if (d_err) atomicExch(d_err, IE_ENOSPC); continue; }
+        uint4 *dst = reinterpret_cast<uint4 *>(out) + c;
+        const bool is_head = (c == c0) && head_shared;
+        const bool is_tail = (c == c1) && tail_shared;
+        if (is_head && first_tile) {
+            // merge with what an earlier launch (header copy / previous frame) left in this chunk
+            const uint4 o = *dst;
+            v.x |= o.x; v.y |= o.y; v.z |= o.z; v.w |= o.w;
+        } else if (is_head || is_tail) {
+            // chunk shared with the neighbouring tile of this launch (every non-last tile has >= 128 bits, so a chunk is
+            // never head and tail at once): both sides OR their bits into the hand-off record, the second one stores.
+            TileBoundary *bd = &st.bnd[is_head ? tile - 1 : tile];
+            if (v.x) atomicOr(&bd->w[0], v.x);
+            if (v.y) atomicOr(&bd->w[1], v.y);
+            if (v.z) atomicOr(&bd->w[2], v.z);
+            if (v.w) atomicOr(&bd->w[3], v.w);
+            __threadfence();
+            if (atomicAdd(&bd->count, 1u) != 1u) continue;      // first arriver: the neighbour writes the chunk
+            __threadfence();
+            v.x = atomicExch(&bd->w[0], 0u); v.y = atomicExch(&bd->w[1], 0u);
+            v.z = atomicExch(&bd->w[2], 0u); v.w = atomicExch(&bd->w[3], 0u);
+            atomicExch(&bd->count, 0u);                          // record is clean again for the next launch
+        }
+        *dst = v;
+    }
+}
+
+#endif  // __CUDACC__
+}  // namespace ie

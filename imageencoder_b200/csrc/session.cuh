@@ -1,0 +1,52 @@
+// ie_session: scratch that one problem shape needs (look-back states, hand-off records, counters, staging).
+#pragma once
+#include "common.cuh"
+#include "pack.cuh"
+
+struct ie_session {
+    int kind = 0;
+    uint32_t W = 0, H = 0, N = 0, frames = 1;
+    int device = -1;
+    ie::DeviceState *dev = nullptr;
+
+    // scan scratch, sized for `images` streams of `max_tiles` tiles (zeroed once; self-cleaning afterwards)
+    unsigned images = 1;
+    unsigned max_tiles = 0;
+    unsigned long long *d_tile_state = nullptr;
+    ie::TileBoundary *d_bnd = nullptr;
+    unsigned *d_ticket = nullptr;
+    unsigned long long *d_counter = nullptr;      // [images] stream bit counters
+    int *d_err = nullptr;
+    unsigned epoch = 0;
+
+    // decode scratch
+    unsigned long long *d_block_off = nullptr;    // [images * nblocks (+1)]
+    size_t block_off_cap = 0;
+
+    // generic device scratch (Huffman stage, video)
+    uint8_t *d_scratch = nullptr;
+    size_t scratch_cap = 0;
+
+    // staging for the host-buffer entry points
+    uint8_t *d_in = nullptr;  size_t d_in_cap = 0;
+    uint8_t *d_out = nullptr; size_t d_out_cap = 0;
+    uint8_t *d_tmp = nullptr; size_t d_tmp_cap = 0;
+    unsigned long long *h_pinned = nullptr;       // small pinned read-back area (64 u64)
+    cudaStream_t stream = nullptr;                // used by the host-buffer entry points
+
+    ie::ScanState scan_state() {
+        ie::ScanState st;
+        st.tile_state = d_tile_state;
+        st.bnd = d_bnd;
+        st.ticket = d_ticket;
+        epoch = (epoch + 1) & 0xFFFFFFu;
+        if (epoch == 0) epoch = 1;                // 0 is the "never written" value of a fresh array
+        st.epoch = epoch;
+        return st;
+    }
+};
+
+namespace ie {
+int session_reserve(uint8_t **p, size_t *cap, size_t need);
+int session_ensure_scan(ie_session *s, unsigned images, unsigned tiles);
+}  // namespace ie

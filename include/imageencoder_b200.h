@@ -1,0 +1,123 @@
+/*
+ * imageencoder_b200 -- C-ABI of the B200-native block-transform hot path of ThenTech/ImageEncoder.
+ *
+ * The reference has no FFI; the path sits behind four C++ classes.  Each entry point below names
+ * the reference interface it replaces; the thin C++ classes in imageencoder_b200/csrc/host/ keep the
+ * reference's class names / ctor signatures and call these functions.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - return 0 on success, a negative IE_E* code on failure; ie_last_error() gives a thread-local message.
+ *     Nothing here calls exit()/assert() (the reference does: ImageBase.cpp:24-27, ImageEncoder.cpp:26-28).
+ *   - host entry points take HOST buffers and include the H2D/D2H copies; `_dev` entry points take DEVICE
+ *     buffers + a cudaStream_t (passed as void*) and are what the HBM-resident benchmark times.
+ *   - block size (4|8) and Huffman on/off are compile-time in the reference (Block.hpp:13, makefile:13)
+ *     and run-time arguments here.
+ *   - there is NO CPU fallback: every call fails with IE_ENODEVICE when no sm_100 device is usable.
+ */
+#ifndef IMAGEENCODER_B200_H
+#define IMAGEENCODER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IE_OK            0
+#define IE_EINVAL       -1   /* bad argument (dims not multiple of block size, > 32767, quant entry 0, ...) */
+#define IE_ENODEVICE    -2   /* no CUDA device / wrong architecture / CUDA error at init */
+#define IE_ECUDA        -3   /* CUDA runtime error during the call */
+#define IE_ENOSPC       -4   /* caller-provided output buffer too small */
+#define IE_EFORMAT      -5   /* malformed encoded stream */
+#define IE_ENOMEM       -6
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+/* Select `device`, create the per-device state (LUTs: zigzag algo.cpp:68-87, cos/C tables algo.cpp:294-297,312,
+ * MER pattern algo.cpp:90-139).  Idempotent per device; thread-safe. */
+int ie_init(int device);
+void ie_shutdown(void);
+const char *ie_last_error(void);
+/* "imageencoder_b200 x.y (sm_100a)" */
+const char *ie_version(void);
+
+/* ---- sizing helpers --------------------------------------------------------------------------------------- */
+/* Upper bound of the encoded size in bytes (header + blocks * (4 + 16 + 16*N*N) bits, Block.cpp:346-354
+ * streamSize(), + Huffman dictionary slack). */
+size_t ie_max_encoded_bytes(uint32_t width, uint32_t height, uint32_t block, uint32_t frames);
+
+/* ---- images: replaces dc::ImageEncoder::process (ImageEncoder.cpp:52-175) and dc::ImageDecoder
+ *      (ImageBase.cpp:98-129 + ImageDecoder.cpp:55-122) ------------------------------------------------------- */
+/* raw: width*height bytes, row-major 8-bit grayscale.  quant: block*block u16, row-major (MatrixReader.cpp:65-134).
+ * huffman != 0 produces what the reference's ENABLE_HUFFMAN build writes.  out receives the exact .enc bytes. */
+int ie_encode_image(const uint8_t *raw, uint32_t width, uint32_t height, uint32_t block,
+                    const uint16_t *quant, int use_rle, int huffman,
+                    uint8_t *out, size_t out_cap, size_t *out_bytes);
+/* enc: the .enc bytes.  The stream does not record the block size (compile-time in the reference) -> `block`.
+ * raw_out receives width x height bytes; the width and height outputs are set even when IE_ENOSPC is returned. */
+int ie_decode_image(const uint8_t *enc, size_t enc_bytes, uint32_t block,
+                    uint8_t *raw_out, size_t raw_cap, uint32_t *width, uint32_t *height);
+/* Batch of `count` equally sized images (BASELINE config 4).  raws: count*width*height contiguous bytes;
+ * out: count slots of out_stride bytes; out_bytes[count]. */
+int ie_encode_images(const uint8_t *raws, uint32_t count, uint32_t width, uint32_t height, uint32_t block,
+                     const uint16_t *quant, int use_rle, int huffman,
+                     uint8_t *out, size_t out_stride, size_t *out_bytes);
+int ie_decode_images(const uint8_t *encs, size_t enc_stride, const size_t *enc_bytes, uint32_t count, uint32_t block,
+                     uint8_t *raws_out, size_t raw_stride, uint32_t *width, uint32_t *height);
+
+/* ---- video: replaces dc::VideoEncoder::process (VideoEncoder.cpp:22-111 + Frame.cpp:129-247) and
+ *      dc::VideoDecoder (VideoBase.cpp:45-85 + VideoDecoder.cpp:33-62 + Frame.cpp:47-127) -------------------- */
+/* yuv420: frames * (w*h*3/2) bytes, planar; only Y is coded.  Block size is 4, MacroBlock 16 (Block.hpp:13-14).
+ * recon_out (optional, may be NULL): receives the encoder-side reconstruction the reference leaves in its raw buffer. */
+int ie_encode_video(const uint8_t *yuv420, size_t yuv_bytes, uint32_t width, uint32_t height,
+                    const uint16_t *quant, int use_rle, uint32_t gop, uint32_t merange, int huffman,
+                    uint8_t *out, size_t out_cap, size_t *out_bytes);
+int ie_decode_video(const uint8_t *enc, size_t enc_bytes, int motioncompensation,
+                    uint8_t *yuv_out, size_t yuv_cap, size_t *yuv_bytes,
+                    uint32_t *width, uint32_t *height, uint32_t *frames);
+
+/* ---- device-resident variants (what bench.py's HBM-resident `value` times) --------------------------------- */
+typedef struct ie_session ie_session;   /* owns scratch (tile states, staging) sized for one problem shape */
+
+/* kind: 0 image encode, 1 image decode, 2 video encode, 3 video decode.  frames = 1 for images (or the batch size). */
+int ie_session_create(ie_session **s, int kind, uint32_t width, uint32_t height, uint32_t block, uint32_t frames);
+void ie_session_destroy(ie_session *s);
+
+/* d_raw/d_out are DEVICE pointers.  Asynchronous on `stream`; *d_out_bits (DEVICE u64, may be NULL) receives the
+ * stream length in bits.  `first_bit` lets a shard write into a larger stream: the shard's first block lands at
+ * that bit of d_out (multi-GPU stitching); header is written only when write_header != 0.
+ * Huffman is a separate stage (ie_huffman_encode_dev). */
+int ie_encode_image_dev(ie_session *s, const uint8_t *d_raw, uint32_t width, uint32_t height,
+                        const uint16_t *quant, int use_rle, int lead_bit, int write_header, uint64_t first_bit,
+                        uint8_t *d_out, size_t out_cap, uint64_t *d_out_bits, void *stream);
+/* Only the per-block bit lengths (first pass of a sharded encode): *d_total_bits = sum over the shard's blocks. */
+int ie_image_bits_dev(ie_session *s, const uint8_t *d_raw, uint32_t width, uint32_t height,
+                      const uint16_t *quant, int use_rle, uint64_t *d_total_bits, void *stream);
+/* Decode of a plain (not Huffman-coded) device-resident stream whose header starts at bit `start_bit`. */
+int ie_decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, uint64_t start_bit,
+                        uint8_t *d_raw_out, size_t raw_cap, uint32_t *width, uint32_t *height, void *stream);
+/* Byte-wise Huffman stage over a device-resident, byte-rounded plain stream (Huffman.cpp:232-344).
+ * Synchronises `stream` once (the 256-entry tree is built on the host exactly as the reference does). */
+int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes,
+                          uint8_t *d_out, size_t out_cap, size_t *out_bytes, void *stream);
+int ie_huffman_decode_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes,
+                          uint8_t *d_out, size_t out_cap, size_t *out_bytes, uint64_t *start_bit, void *stream);
+/* Device histogram + first-occurrence positions of a byte stream (Huffman.cpp:236-243); hist[256] u32,
+ * first_pos[256] u64 (UINT64_MAX = absent).  HOST outputs; synchronises `stream`. */
+int ie_byte_histogram_dev(const uint8_t *d_in, size_t in_bytes, uint32_t *hist, uint64_t *first_pos, void *stream);
+
+int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv420, size_t yuv_bytes, uint32_t width, uint32_t height,
+                        const uint16_t *quant, int use_rle, uint32_t gop, uint32_t merange, int lead_bit,
+                        uint8_t *d_out, size_t out_cap, uint64_t *d_out_bits, int16_t *d_mvecs, void *stream);
+int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, uint64_t start_bit, int motioncompensation,
+                        uint8_t *d_yuv_out, size_t yuv_cap, uint32_t *width, uint32_t *height, uint32_t *frames,
+                        void *stream);
+
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+uint64_t ie_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMAGEENCODER_B200_H */

@@ -149,6 +149,16 @@ def huffman_encode(data: bytes, with_dict: bool = False):
     return res
 
 
+def huffman_header_overflows(plain: bytes) -> bool:
+    """True when the dictionary header cannot represent the code (Huffman.cpp:39-42: length & 0xF, group & 0x7F):
+    the reference then cannot decode its own output, so only encoder parity is defined."""
+    _, lens, _, rev = huffman_encode(plain, with_dict=True)
+    if rev:
+        return False
+    l = lens[lens != 0xFFFFFFFF]
+    return bool(l.max() >= 16 or np.bincount(l).max() >= 128)
+
+
 def huffman_decode(data: bytes):
     """Returns (bytes, start_bit)."""
     a = np.frombuffer(data, dtype=np.uint8)
@@ -249,11 +259,17 @@ def _ref_bin(N, huffman) -> str:
     return str(p)
 
 
-def _run_ref(cmd, threads=None):
+def _run_ref(cmd, threads=None, timeout=3600):
     env = dict(os.environ)
     if threads is not None:
         env["OMP_NUM_THREADS"] = str(threads)
-    r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env, text=True)
+    import resource
+
+    def _limits():          # a corrupt header makes the reference allocate frames*W*H bytes: cap it instead of the box
+        resource.setrlimit(resource.RLIMIT_AS, (48 << 30, 48 << 30))
+
+    r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env, text=True, preexec_fn=_limits,
+                       timeout=timeout)
     for line in r.stderr.splitlines():
         if line.startswith("@@RESULT "):
             return json.loads(line[len("@@RESULT "):])
