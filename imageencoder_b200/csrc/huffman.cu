@@ -479,10 +479,10 @@ int ie_huffman_decode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
         if (cur >= 0) entry = 0xFFFF0000u | (unsigned)cur;
         t.lut[pre] = entry;
     }
-    const size_t need = sizeof(HuffDecodeTables) + 64;
-    IE_TRY(ensure_scratch(s, need));
+    const size_t tab_bytes = (sizeof(HuffDecodeTables) + 63) / 64 * 64;
+    IE_TRY(ensure_scratch(s, tab_bytes + 64));
     HuffDecodeTables *d_tab = reinterpret_cast<HuffDecodeTables *>(s->d_scratch);
-    unsigned long long *d_count = reinterpret_cast<unsigned long long *>(s->d_scratch + sizeof(HuffDecodeTables));
+    unsigned long long *d_count = reinterpret_cast<unsigned long long *>(s->d_scratch + tab_bytes);
     IE_CUDA(cudaMemcpyAsync(d_tab, &t, sizeof t, cudaMemcpyHostToDevice, st));
     huff_decode_kernel<<<1, 32, 0, st>>>(d_in, n, (unsigned long long)pos, d_tab, d_out, out_cap, d_count, s->d_err);
     count_launch();
