@@ -1,0 +1,79 @@
+"""Device-resident calls (torch tensors in HBM, torch's current stream).  torch is plumbing only: it owns the memory
+and the stream; the work is done by the C-ABI `_dev` entry points."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+
+
+def _dp(t: torch.Tensor):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Session:
+    """ie_session wrapper (scratch for one problem shape)."""
+    IMAGE_ENCODE, IMAGE_DECODE, VIDEO_ENCODE, VIDEO_DECODE = 0, 1, 2, 3
+
+    def __init__(self, kind: int, width: int, height: int, block: int, frames: int = 1):
+        self.h = C.c_void_p()
+        check(lib().ie_session_create(C.byref(self.h), kind, width, height, block, frames))
+        self.width, self.height, self.block, self.frames = width, height, block, frames
+
+    def close(self):
+        if self.h:
+            lib().ie_session_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _q(quant):
+    q = np.ascontiguousarray(np.asarray(quant, dtype=np.uint16)).reshape(-1)
+    return q, q.ctypes.data_as(C.POINTER(C.c_uint16))
+
+
+def encode_image_dev(s: Session, d_raw: torch.Tensor, quant, rle: bool, d_out: torch.Tensor, d_bits: torch.Tensor | None = None,
+                     lead_bit: bool = True, write_header: bool = True, first_bit: int = 0, width=None, height=None) -> None:
+    """Asynchronous on torch's current stream.  d_raw u8 [H*W], d_out u8 (16-byte aligned), d_bits u64/int64 [1]."""
+    q, qp = _q(quant)
+    check(lib().ie_encode_image_dev(s.h, _dp(d_raw), width or s.width, height or s.height, qp, int(rle), int(lead_bit),
+                                    int(write_header), first_bit, _dp(d_out), d_out.numel(),
+                                    _dp(d_bits) if d_bits is not None else None, _stream()))
+
+
+def image_bits_dev(s: Session, d_raw: torch.Tensor, quant, rle: bool, d_bits: torch.Tensor, width=None, height=None) -> None:
+    q, qp = _q(quant)
+    check(lib().ie_image_bits_dev(s.h, _dp(d_raw), width or s.width, height or s.height, qp, int(rle), _dp(d_bits), _stream()))
+
+
+def decode_image_dev(s: Session, d_enc: torch.Tensor, enc_bytes: int, d_raw_out: torch.Tensor, start_bit: int = 1):
+    w, h = C.c_uint32(0), C.c_uint32(0)
+    check(lib().ie_decode_image_dev(s.h, _dp(d_enc), enc_bytes, start_bit, _dp(d_raw_out), d_raw_out.numel(), C.byref(w),
+                                    C.byref(h), _stream()))
+    return w.value, h.value
+
+
+def huffman_encode_dev(s: Session, d_in: torch.Tensor, in_bytes: int, d_out: torch.Tensor) -> int:
+    n = C.c_size_t(0)
+    check(lib().ie_huffman_encode_dev(s.h, _dp(d_in), in_bytes, _dp(d_out), d_out.numel(), C.byref(n), _stream()))
+    return n.value
+
+
+def byte_histogram_dev(d_in: torch.Tensor, n: int):
+    hist = np.zeros(256, dtype=np.uint32)
+    first = np.zeros(256, dtype=np.uint64)
+    check(lib().ie_byte_histogram_dev(_dp(d_in), n, hist.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                      first.ctypes.data_as(C.POINTER(C.c_uint64)), _stream()))
+    return hist, first
