@@ -1,17 +1,399 @@
-// C-ABI: video entry points (placeholder until video.cu lands in this round).
+// Video path: MacroBlock motion estimation, mvec pack, P-frame residual encode + in-place reconstruction, decode.
+//
+//   me_search_kernel   warp per 16x16 MacroBlock: the reference's fixed 2-D-log search (Block.cpp:267-339) over the
+//                      pattern of algo.cpp:90-139 -- levels merange/2, /4, ..., 1; 9 candidates per level in MER_SIGNS
+//                      order around the current best; candidate coordinate clamped into the frame (ImageBase.cpp:253-254);
+//                      for p>0 skip when the clamped coordinate is the block's own (Block.cpp:297-301); `<=` so the
+//                      later candidate wins ties (Block.cpp:306); the UNCLAMPED offset is stored (Block.cpp:333-334).
+//   mvec_pack_kernel   all motion vectors of the frame, MVEC_BIT_SIZE bits each, x then y (Block.cpp:415-423)
+//   P-frame blocks     encode_tiles_kernel<4,4,PF=true> (encode_image.cu)
+//   mc_copy_kernel     decoder: out[MB] = ref[clamp(MB + mv)] (Block.cpp:481-496)
+// Frames are strictly sequential inside a GOP (each P-frame searches the reconstruction of its predecessor,
+// Frame.cpp:210-242); frames append to one stream through the device-resident bit counter (pack.cuh contract).
+#include <cstring>
+#include <vector>
+
 #include "api_internal.cuh"
+
+namespace ie {
+
+__constant__ int c_mer_sx[9] = {0, +1, +1, 0, -1, -1, -1, 0, +1};      // algo.cpp:90-100
+__constant__ int c_mer_sy[9] = {0, 0, +1, +1, +1, 0, -1, -1, -1};
+
+struct MEParams {
+    const uint8_t *cur;
+    const uint8_t *ref;
+    int W, H, mx, nmb, merange;
+    short *mv;           // [nmb][2] unclamped offsets
+    short *res_coord;    // [nmb][2] clamped pixel coordinate of the best block (residual source)
+    short *copy_coord;   // [nmb][2] clamp(MB + mv)  (Frame.cpp:218-220)
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__global__ void __launch_bounds__(256) me_search_kernel(const MEParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * 8 + warp;
+    if (mb >= p.nmb) return;
+    const int mbx = (mb % p.mx) * kMB, mby = (mb / p.mx) * kMB;
+    const int row = lane >> 1, half = lane & 1;
+    const uint2 c = *reinterpret_cast<const uint2 *>(p.cur + (size_t)(mby + row) * p.W + mbx + half * 8);
+    int best_x = 0, best_y = 0;
+    int bcx = 0, bcy = 0;                                  // Block.cpp:273: the initial block is the one at pixel (0,0)
+    unsigned best_d = 0xffffffffu;
+    for (int step = p.merange / 2; step > 0; step >>= 1) {  // algo.cpp:129,138
+        bool have = false;
+        int nx = 0, ny = 0, ncx = 0, ncy = 0;
+        unsigned nd = best_d;
+        for (int q = 0; q < 9; q++) {
+            const int ox = best_x + c_mer_sx[q] * step, oy = best_y + c_mer_sy[q] * step;
+            const int px = clampi((int)(short)(ox + mbx), 0, p.W - kMB), py = clampi((int)(short)(oy + mby), 0, p.H - kMB);
+            if (q > 0 && px == mbx && py == mby) continue;                     // Block.cpp:297-301
+            const uint8_t *rp = p.ref + (size_t)(py + row) * p.W + px + half * 8;
+            const uintptr_t a = (uintptr_t)rp;
+            const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
+            const unsigned sh = (unsigned)(a & 3) * 8;
+            const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = sh ? __ldg(wp + 2) : 0u;
+            const unsigned r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh);
+            unsigned d = __vsadu4(c.x, r0) + __vsadu4(c.y, r1);                // Block.cpp:241-254
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            if (d <= nd) { have = true; nx = ox; ny = oy; nd = d; ncx = px; ncy = py; }   // Block.cpp:306
+        }
+        if (!have) break;                                                       // Block.cpp:318-321 (never taken)
+        best_x = nx; best_y = ny; best_d = nd; bcx = ncx; bcy = ncy;
+    }
+    if (lane == 0) {
+        p.mv[2 * mb] = (short)best_x;
+        p.mv[2 * mb + 1] = (short)best_y;
+        p.res_coord[2 * mb] = (short)bcx;
+        p.res_coord[2 * mb + 1] = (short)bcy;
+        p.copy_coord[2 * mb] = (short)clampi((int)(short)(mbx + best_x), 0, p.W - kMB);
+        p.copy_coord[2 * mb + 1] = (short)clampi((int)(short)(mby + best_y), 0, p.H - kMB);
+    }
+}
+
+// fixed-width fields: field i = low `bits` bits of val[i]
+struct FixedFieldTile {
+    const short *val;
+    unsigned nfields;
+    unsigned bits;
+};
+
+__device__ __forceinline__ uint4 gather_chunk(const FixedFieldTile &t, long long ls) {
+    unsigned ow[4] = {0, 0, 0, 0};
+    const unsigned long long total = (unsigned long long)t.nfields * t.bits;
+#pragma unroll
+    for (int wd = 0; wd < 4; wd++) {
+        unsigned word = 0;
+        // bits [ls + 32 wd, +32): walk the fields that overlap
+        long long b0 = ls + 32 * wd;
+        for (int done = 0; done < 32;) {
+            const long long pos = b0 + done;
+            if (pos < 0) { done += (int)min((long long)(32 - done), -pos); continue; }
+            if ((unsigned long long)pos >= total) break;
+            const unsigned f = (unsigned)(pos / t.bits), fo = (unsigned)(pos % t.bits);
+            const unsigned take = min(t.bits - fo, (unsigned)(32 - done));
+            const unsigned v = ((unsigned)(int)t.val[f] & ((1u << t.bits) - 1u)) >> (t.bits - fo - take) & ((1u << take) - 1u);
+            word |= v << (32 - done - take);
+            done += (int)take;
+        }
+        ow[wd] = __byte_perm(word, 0, 0x0123);
+    }
+    return make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
+__global__ void __launch_bounds__(kThreads) mvec_pack_kernel(const short *mv, unsigned nfields, unsigned bits, uint8_t *out, size_t out_cap,
+                                                             unsigned long long *bit_counter, int *err) {
+    FixedFieldTile t{mv, nfields, bits};
+    ScanState st{};
+    const unsigned long long G = *bit_counter;
+    const unsigned T = nfields * bits;
+    tile_write_chunks(t, st, 0, true, true, G, T, out, out_cap, err);
+    __syncthreads();
+    if (threadIdx.x == 0) *bit_counter = G + T;
+}
+
+struct MCParams {
+    const uint8_t *enc;
+    unsigned long long enc_bits;
+    const unsigned long long *cursor;   // frame's first bit
+    unsigned mvbits;
+    const uint8_t *ref;
+    uint8_t *cur;
+    int W, H, mx, nmb;
+};
+
+__device__ __forceinline__ unsigned read_bits_dev(const uint8_t *s, unsigned long long total_bits, unsigned long long p, int n) {
+    if (n == 0) return 0u;
+    const unsigned long long nbytes = (total_bits + 7) >> 3, b = p >> 3;
+    unsigned v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) v = (v << 8) | ((b + i < nbytes) ? (unsigned)__ldg(s + b + i) : 0u);
+    return (v >> (32 - (int)(p & 7) - n)) & ((1u << n) - 1u);
+}
+
+__global__ void __launch_bounds__(256) mc_copy_kernel(const MCParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * 8 + warp;
+    if (mb >= p.nmb) return;
+    const int mbx = (mb % p.mx) * kMB, mby = (mb / p.mx) * kMB;
+    const unsigned long long base = *p.cursor + (unsigned long long)mb * 2 * p.mvbits;
+    const int sh = 16 - (int)p.mvbits;
+    const int vx = (int)(short)(unsigned short)(read_bits_dev(p.enc, p.enc_bits, min(base, p.enc_bits), p.mvbits) << sh) >> sh;   // Block.cpp:484-485
+    const int vy = (int)(short)(unsigned short)(read_bits_dev(p.enc, p.enc_bits, min(base + p.mvbits, p.enc_bits), p.mvbits) << sh) >> sh;
+    const int cx = clampi((int)(short)(mbx + vx), 0, p.W - kMB), cy = clampi((int)(short)(mby + vy), 0, p.H - kMB);
+    const int row = lane >> 1, half = lane & 1;
+    const uint8_t *rp = p.ref + (size_t)(cy + row) * p.W + cx + half * 8;
+    uint8_t *dp = p.cur + (size_t)(mby + row) * p.W + mbx + half * 8;
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { lo |= (unsigned)__ldg(rp + k) << (8 * k); hi |= (unsigned)__ldg(rp + 4 + k) << (8 * k); }
+    *reinterpret_cast<uint2 *>(dp) = make_uint2(lo, hi);
+}
+
+__global__ void fill_uv_kernel(uint8_t *yuv, size_t ysz, size_t fsz, unsigned frames) {
+    const size_t uv = fsz - ysz;
+    const size_t total = uv * frames;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total / 16; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t byte = i * 16;
+        const size_t f = byte / uv, o = byte % uv;
+        *reinterpret_cast<uint4 *>(yuv + f * fsz + ysz + o) = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    }
+}
+
+static unsigned host_bits_needed(int v) {                    // utils.hpp:226-243
+    const short value = (short)v;
+    unsigned bits = 1;
+    while ((short)((short)((value & ((1 << bits) - 1)) << (16 - bits)) >> (16 - bits)) != value) bits++;
+    return bits;
+}
+
+static int check_video_dims(uint32_t W, uint32_t H) {
+    IE_TRY(check_dims(W, H, 4));
+    if (W % kMB || H % kMB) {
+        set_error("video width/height must be multiples of 16: micro blocks outside a MacroBlock are never coded (Block.cpp:373-375)");
+        return IE_EINVAL;
+    }
+    return IE_OK;
+}
+
+// scratch layout inside s->d_scratch for video: mv | res_coord | copy_coord (shorts), cursor (u64)
+struct VideoScratch { short *mv, *res, *copy; unsigned long long *cursor; };
+static int video_scratch(ie_session *s, size_t nmb, VideoScratch &v) {
+    const size_t sec = (nmb * 2 * sizeof(short) + 63) / 64 * 64;
+    IE_TRY(session_reserve(&s->d_scratch, &s->scratch_cap, 3 * sec + 64));
+    v.mv = reinterpret_cast<short *>(s->d_scratch);
+    v.res = reinterpret_cast<short *>(s->d_scratch + sec);
+    v.copy = reinterpret_cast<short *>(s->d_scratch + 2 * sec);
+    v.cursor = reinterpret_cast<unsigned long long *>(s->d_scratch + 3 * sec);
+    return IE_OK;
+}
+
+}  // namespace ie
+
 using namespace ie;
+
 extern "C" {
-int ie_encode_video(const uint8_t *, size_t, uint32_t, uint32_t, const uint16_t *, int, uint32_t, uint32_t, int, uint8_t *, size_t, size_t *) {
-    set_error("video path not built yet"); return IE_EINVAL;
+
+int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_t W, uint32_t H, const uint16_t *quant, int use_rle,
+                        uint32_t gop, uint32_t merange, int lead_bit, uint8_t *d_out, size_t out_cap, uint64_t *d_out_bits,
+                        int16_t *d_mvecs, void *stream) {
+    if (!s || !d_yuv || !d_out) { set_error("NULL argument"); return IE_EINVAL; }
+    IE_TRY(check_video_dims(W, H));
+    IE_TRY(check_quant(quant, 4));
+    if ((uintptr_t)d_out % 16) { set_error("stream buffers must be 16-byte aligned"); return IE_EINVAL; }
+    if (merange > 32767) { set_error("merange must fit 15 bits"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gop < 1) gop = 1;                                                      // VideoBase.cpp:34
+    const size_t ysz = (size_t)W * H, fsz = ysz + ysz / 2;
+    const uint32_t frames = (uint32_t)(yuv_bytes / fsz);                      // VideoBase.cpp:39-40
+    if (frames > 32767) { set_error("more than 32767 frames do not fit the 15-bit header field"); return IE_EINVAL; }
+    const unsigned nblocks = (W / 4) * (H / 4), nmb = (W / kMB) * (H / kMB);
+    const unsigned TB = encode_tile_blocks(4), tiles = (nblocks + TB - 1) / TB;
+    IE_TRY(session_ensure_scan(s, 1, tiles));
+    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+    VideoScratch vs;
+    IE_TRY(video_scratch(s, nmb, vs));
+    const unsigned mvbits = host_bits_needed((int)(short)merange);           // VideoBase.cpp:42
+
+    HeaderParam hdr;
+    IE_TRY(build_header(hdr, 4, quant, use_rle, W, H, lead_bit, 1, frames, gop, merange));
+    if (out_cap < 256) { set_error("output buffer too small"); return IE_ENOSPC; }
+    IE_TRY(launch_stream_init(d_out, 0, 1, hdr, 0, s->d_counter, st));
+
+    EncodeParams p;
+    memset(&p, 0, sizeof p);
+    p.pitch = W; p.bx = W / 4; p.nblocks = nblocks; p.tiles_per_image = tiles; p.use_rle = use_rle ? 1 : 0;
+    make_quant(p.quant, quant, 4);
+    p.tab = s->dev->d_t4;
+    p.out = d_out; p.out_cap = out_cap; p.bit_counter = s->d_counter; p.err = s->d_err;
+    p.mbx = W / kMB;
+    for (uint32_t f = 0; f < frames; f++) {
+        uint8_t *cur = d_yuv + (size_t)f * fsz;
+        p.src = cur;
+        p.scan = s->scan_state();
+        if (f % gop == 0) {                                                    // VideoBase.hpp:32, Frame.cpp:130-159
+            IE_TRY(launch_encode_tiles(4, p, 1, st));
+            if (d_mvecs) IE_CUDA(cudaMemsetAsync(d_mvecs + (size_t)f * nmb * 2, 0, nmb * 2 * sizeof(short), st));
+            continue;
+        }
+        MEParams me;
+        me.cur = cur; me.ref = d_yuv + (size_t)(f - 1) * fsz; me.W = (int)W; me.H = (int)H; me.mx = (int)(W / kMB); me.nmb = (int)nmb;
+        me.merange = (int)merange; me.mv = vs.mv; me.res_coord = vs.res; me.copy_coord = vs.copy;
+        me_search_kernel<<<(nmb + 7) / 8, 256, 0, st>>>(me);
+        count_launch();
+        mvec_pack_kernel<<<1, kThreads, 0, st>>>(vs.mv, nmb * 2, mvbits, d_out, out_cap, s->d_counter, s->d_err);
+        count_launch();
+        IE_CUDA(cudaGetLastError());
+        if (d_mvecs) IE_CUDA(cudaMemcpyAsync(d_mvecs + (size_t)f * nmb * 2, vs.mv, nmb * 2 * sizeof(short), cudaMemcpyDeviceToDevice, st));
+        p.ref = me.ref; p.res_coord = vs.res; p.copy_coord = vs.copy; p.cur_rw = cur;
+        IE_TRY(launch_pframe_tiles(p, st));
+    }
+    if (frames == 0) { /* header only */ }
+    if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, s->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return IE_OK;
 }
-int ie_decode_video(const uint8_t *, size_t, int, uint8_t *, size_t, size_t *, uint32_t *, uint32_t *, uint32_t *) {
-    set_error("video path not built yet"); return IE_EINVAL;
+
+int ie_encode_video(const uint8_t *yuv, size_t yuv_bytes, uint32_t W, uint32_t H, const uint16_t *quant, int use_rle, uint32_t gop,
+                    uint32_t merange, int huffman, uint8_t *out, size_t out_cap, size_t *out_bytes) {
+    if (!yuv || !out || !out_bytes) { set_error("NULL argument"); return IE_EINVAL; }
+    IE_TRY(check_video_dims(W, H));
+    const size_t fsz = (size_t)W * H * 3 / 2;
+    const uint32_t frames = (uint32_t)(yuv_bytes / fsz);
+    ie_session *s = nullptr;
+    IE_TRY(cached_session(&s, 2, W, H, 4, frames));
+    const size_t cap = ie_max_encoded_bytes(W, H, 4, std::max(1u, frames));
+    IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, std::max<size_t>(yuv_bytes, 16)));
+    IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, cap));
+    cudaStream_t st = s->stream;
+    IE_CUDA(cudaMemcpyAsync(s->d_in, yuv, yuv_bytes, cudaMemcpyHostToDevice, st));
+    IE_TRY(ie_encode_video_dev(s, s->d_in, yuv_bytes, W, H, quant, use_rle, gop, merange, huffman ? 0 : 1, s->d_out, s->d_out_cap,
+                               nullptr, nullptr, st));
+    IE_CUDA(cudaMemcpyAsync(s->h_pinned, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    IE_TRY(read_err_flag(s, st));
+    size_t bytes = (size_t)((s->h_pinned[0] + 7) / 8);
+    const uint8_t *d_result = s->d_out;
+    if (huffman) {
+        IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, bytes + 4096 + 32));
+        size_t hb = 0;
+        IE_TRY(ie_huffman_encode_dev(s, s->d_out, bytes, s->d_tmp, s->d_tmp_cap, &hb, st));
+        bytes = hb;
+        d_result = s->d_tmp;
+    }
+    *out_bytes = bytes;
+    if (bytes > out_cap) { set_error("output buffer too small"); return IE_ENOSPC; }
+    IE_CUDA(cudaMemcpyAsync(out, d_result, bytes, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    return IE_OK;
 }
-int ie_encode_video_dev(ie_session *, uint8_t *, size_t, uint32_t, uint32_t, const uint16_t *, int, uint32_t, uint32_t, int, uint8_t *, size_t, uint64_t *, int16_t *, void *) {
-    set_error("video path not built yet"); return IE_EINVAL;
+
+int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, uint64_t start_bit, int motioncomp, uint8_t *d_out,
+                        size_t out_cap, uint32_t *Wo, uint32_t *Ho, uint32_t *Fo, void *stream) {
+    if (!s || !d_enc || !d_out) { set_error("NULL argument"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t hb[192];
+    const size_t first = (size_t)(start_bit / 8);
+    if (first >= enc_bytes) { set_error("start_bit beyond the stream"); return IE_EFORMAT; }
+    const size_t n = std::min(sizeof hb, enc_bytes - first);
+    IE_CUDA(cudaMemcpyAsync(hb, d_enc + first, n, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    ParsedHeader h;
+    parse_header(hb, n, (size_t)(start_bit % 8), 4, h, 1);
+    h.end_bit += first * 8;
+    if (Wo) *Wo = h.W;
+    if (Ho) *Ho = h.H;
+    if (Fo) *Fo = h.frames;
+    IE_TRY(check_video_dims(h.W, h.H));
+    if (h.gop < 1) { set_error("gop 0 in the stream header"); return IE_EFORMAT; }
+    const uint32_t W = h.W, H = h.H, frames = h.frames;
+    const size_t ysz = (size_t)W * H, fsz = ysz + ysz / 2;
+    if (fsz * frames > out_cap) { set_error("decoded video does not fit the output buffer"); return IE_ENOSPC; }
+    const unsigned nblocks = (W / 4) * (H / 4), nmb = (W / kMB) * (H / kMB);
+    const unsigned mvbits = host_bits_needed((int)(short)h.merange);
+    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+    VideoScratch vs;
+    IE_TRY(video_scratch(s, nmb, vs));
+    const size_t need_off = ((size_t)nblocks + 1) * sizeof(unsigned long long) + 64;
+    if (s->block_off_cap < need_off) {
+        if (s->d_block_off) IE_CUDA(cudaFree(s->d_block_off));
+        IE_CUDA(cudaMalloc(&s->d_block_off, need_off));
+        s->block_off_cap = need_off;
+    }
+    unsigned long long consts[2] = {(unsigned long long)enc_bytes * 8ull, (unsigned long long)h.end_bit};
+    unsigned long long *d_consts = s->d_block_off + (nblocks + 1);
+    IE_CUDA(cudaMemcpyAsync(d_consts, consts, sizeof consts, cudaMemcpyHostToDevice, st));
+    IE_CUDA(cudaMemcpyAsync(vs.cursor, &consts[1], sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+
+    DecodeParams p;
+    memset(&p, 0, sizeof p);
+    p.enc = d_enc; p.enc_bits = d_consts; p.start_bit = d_consts + 1; p.block_off = s->d_block_off; p.nblocks = nblocks;
+    p.bx = W / 4; p.N = 4; p.use_rle = h.use_rle; make_quant(p.quant, h.quant, 4); p.tab = s->dev->d_t4; p.pitch = W; p.err = s->d_err;
+    p.cursor = vs.cursor;
+    for (uint32_t f = 0; f < frames; f++) {
+        uint8_t *cur = d_out + (size_t)f * fsz;
+        const bool is_i = (f % h.gop) == 0;
+        p.out = cur;
+        if (is_i) {
+            p.skip_bits = 0; p.add_mode = 0;
+            IE_TRY(launch_parse_blocks(p, 1, st));
+            IE_TRY(launch_decode_blocks(p, 1, st));
+        } else {
+            MCParams mc;
+            mc.enc = d_enc; mc.enc_bits = consts[0]; mc.cursor = vs.cursor; mc.mvbits = mvbits; mc.ref = d_out + (size_t)(f - 1) * fsz;
+            mc.cur = cur; mc.W = (int)W; mc.H = (int)H; mc.mx = (int)(W / kMB); mc.nmb = (int)nmb;
+            mc_copy_kernel<<<(nmb + 7) / 8, 256, 0, st>>>(mc);
+            count_launch();
+            IE_CUDA(cudaGetLastError());
+            p.skip_bits = nmb * 2 * mvbits; p.add_mode = 1;
+            IE_TRY(launch_parse_blocks(p, 1, st));                           // advances the cursor past this frame
+            if (motioncomp) IE_TRY(launch_decode_blocks(p, 1, st));           // Frame.cpp:107-117
+        }
+    }
+    if (frames) {
+        fill_uv_kernel<<<256, 256, 0, st>>>(d_out, ysz, fsz, frames);         // Frame.cpp:122-124 (W*H/2 is a multiple of 16)
+        count_launch();
+        IE_CUDA(cudaGetLastError());
+    }
+    return IE_OK;
 }
-int ie_decode_video_dev(ie_session *, const uint8_t *, size_t, uint64_t, int, uint8_t *, size_t, uint32_t *, uint32_t *, uint32_t *, void *) {
-    set_error("video path not built yet"); return IE_EINVAL;
+
+int ie_decode_video(const uint8_t *enc, size_t enc_bytes, int motioncomp, uint8_t *yuv_out, size_t yuv_cap, size_t *yuv_bytes,
+                    uint32_t *Wo, uint32_t *Ho, uint32_t *Fo) {
+    if (!enc || !yuv_out || enc_bytes == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    ie_session *s = nullptr;
+    IE_TRY(cached_session(&s, 3, 0, 0, 4, 0));
+    cudaStream_t st = s->stream;
+    IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, enc_bytes + 16));
+    IE_CUDA(cudaMemcpyAsync(s->d_in, enc, enc_bytes, cudaMemcpyHostToDevice, st));
+    const uint8_t *d_plain = s->d_in;
+    size_t plain_bytes = enc_bytes;
+    uint64_t start_bit = 1;
+    if (enc[0] & 0x80) {
+        IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, enc_bytes * 8 + 64));
+        IE_TRY(ie_huffman_decode_dev(s, s->d_in, enc_bytes, s->d_tmp, s->d_tmp_cap, &plain_bytes, &start_bit, st));
+        d_plain = s->d_tmp;
+    }
+    uint8_t hb[192];
+    const size_t n = std::min(sizeof hb, plain_bytes);
+    IE_CUDA(cudaMemcpyAsync(hb, d_plain, n, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    ParsedHeader h;
+    parse_header(hb, n, (size_t)start_bit, 4, h, 1);
+    if (Wo) *Wo = h.W;
+    if (Ho) *Ho = h.H;
+    if (Fo) *Fo = h.frames;
+    IE_TRY(check_video_dims(h.W, h.H));
+    const size_t total = (size_t)h.W * h.H * 3 / 2 * h.frames;
+    if (yuv_bytes) *yuv_bytes = total;
+    if (total > yuv_cap) { set_error("yuv_out too small"); return IE_ENOSPC; }
+    IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, std::max<size_t>(total, 16)));
+    uint32_t w, hh, ff;
+    IE_TRY(ie_decode_video_dev(s, d_plain, plain_bytes, start_bit, motioncomp, s->d_out, s->d_out_cap, &w, &hh, &ff, st));
+    IE_TRY(read_err_flag(s, st));
+    IE_CUDA(cudaMemcpyAsync(yuv_out, s->d_out, total, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    return IE_OK;
 }
-}
+
+}  // extern "C"

@@ -31,7 +31,7 @@ __global__ void parse_blocks_kernel(const DecodeParams p) {
     if (threadIdx.x != 0) return;
     const uint8_t *s = p.enc + (size_t)img * p.enc_stride;
     const unsigned long long total = p.enc_bits[img];
-    unsigned long long pos = p.start_bit[img];
+    unsigned long long pos = p.cursor ? (*p.cursor + p.skip_bits) : p.start_bit[img];
     unsigned long long *off = p.block_off + (size_t)img * (p.nblocks + 1);
     const int NN = p.N * p.N;
     for (unsigned k = 0; k < p.nblocks; k++) {
@@ -44,9 +44,10 @@ __global__ void parse_blocks_kernel(const DecodeParams p) {
         pos = q;
     }
     off[p.nblocks] = pos;
+    if (p.cursor) *p.cursor = pos;
 }
 
-template <int N>
+template <int N, bool ADD>
 __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecodeParams p) {
     constexpr int NN = N * N;
     constexpr int STRIDE = NN + 2;
@@ -94,12 +95,16 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecodeParams p
 #pragma unroll
     for (int y = 0; y < N; y++) {
         unsigned lo = 0, hi = 0;
+        uint8_t *row = dst + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N;
+        unsigned cur_lo = 0;
+        if (ADD) cur_lo = *reinterpret_cast<const unsigned *>(row);
 #pragma unroll
         for (int x = 0; x < N; x++) {
-            const unsigned px = clamp_trunc_u8(__dadd_rn(X[y * N + x], 128.0));  // Block.cpp:173-175, 99-107
+            double v = __dadd_rn(X[y * N + x], 128.0);                           // Block.cpp:173-175
+            if (ADD) v = __dadd_rn((double)(int)((cur_lo >> (8 * (x & 3))) & 0xff), v);   // Block.cpp:114-116
+            const unsigned px = clamp_trunc_u8(v);                               // Block.cpp:99-107 (truncation)
             if (x < 4) lo |= px << (8 * x); else hi |= px << (8 * (x - 4));
         }
-        uint8_t *row = dst + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N;
         if (N == 8) *reinterpret_cast<uint2 *>(row) = make_uint2(lo, hi);
         else *reinterpret_cast<unsigned *>(row) = lo;
     }
@@ -114,8 +119,9 @@ int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t str
 
 int launch_decode_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream) {
     dim3 grid((p.nblocks + 255) / 256, images);
-    if (p.N == 8) decode_blocks_kernel<8><<<grid, 256, 0, stream>>>(p);
-    else if (p.N == 4) decode_blocks_kernel<4><<<grid, 256, 0, stream>>>(p);
+    if (p.N == 8) decode_blocks_kernel<8, false><<<grid, 256, 0, stream>>>(p);
+    else if (p.N == 4 && p.add_mode) decode_blocks_kernel<4, true><<<grid, 256, 0, stream>>>(p);
+    else if (p.N == 4) decode_blocks_kernel<4, false><<<grid, 256, 0, stream>>>(p);
     else { set_error("block size must be 4 or 8"); return IE_EINVAL; }
     count_launch();
     IE_CUDA(cudaGetLastError());

@@ -19,6 +19,10 @@ struct DecodeParams {
     size_t out_stride;
     size_t pitch;
     int *err;
+    // video (Frame.cpp:47-127): the frame's first bit comes from a device-resident cursor that the parse kernel advances
+    unsigned long long *cursor;             // device; NULL for images
+    unsigned skip_bits;                     // bits between the cursor and the first block (the mvec section of a P-frame)
+    int add_mode;                           // 1: pixel = (u8)clamp(cur + (X + 128))   (Block.cpp:110-119, P-frames)
 };
 
 int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream);

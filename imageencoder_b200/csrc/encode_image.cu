@@ -8,7 +8,7 @@
 
 namespace ie {
 
-template <int N, int BPL>
+template <int N, int BPL, bool PF>
 __global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodeParams p) {
     constexpr int NN = N * N;
     constexpr int TB = kThreads * BPL;            // blocks per tile
@@ -47,6 +47,13 @@ __global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodePara
         const unsigned gb = first_blk + lb;
         const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
         double x[NN];
+        int rx = 0, ry = 0, kx = 0, ky = 0;        // P-frame: top-left of this micro block inside the residual / copy source
+        if (PF) {
+            const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
+            const int ox = (int)(bxi & 3) * 4, oy = (int)(byi & 3) * 4;
+            rx = p.res_coord[2 * mb] + ox;  ry = p.res_coord[2 * mb + 1] + oy;
+            kx = p.copy_coord[2 * mb] + ox; ky = p.copy_coord[2 * mb + 1] + oy;
+        }
 #pragma unroll
         for (int y = 0; y < N; y++) {
             const uint8_t *row = src + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N;
@@ -58,9 +65,16 @@ __global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodePara
                     x[y * N + 4 + k] = (double)(int)((v.y >> (8 * k)) & 0xff) - 128.0;
                 }
             } else {
-                const unsigned v = __ldg(reinterpret_cast<const unsigned *>(row));
+                const unsigned v = PF ? *reinterpret_cast<const unsigned *>(row) : __ldg(reinterpret_cast<const unsigned *>(row));
 #pragma unroll
-                for (int k = 0; k < 4; k++) x[y * N + k] = (double)(int)((v >> (8 * k)) & 0xff) - 128.0;
+                for (int k = 0; k < 4; k++) {
+                    double px = (double)(int)((v >> (8 * k)) & 0xff);
+                    if (PF) {
+                        const double r = (double)(int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + k);
+                        px = __dsub_rn(px, r);                                           // Block.cpp:262
+                    }
+                    x[y * N + k] = __dadd_rn(px, -128.0);                                // applied to residuals too
+                }
             }
         }
         short *cf = s_coef + (size_t)lb * STRIDE;
@@ -88,6 +102,34 @@ __global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodePara
             if (lastnz == NN && prevnz != NN - 1) len = prevnz;
         } else {
             len = NN;                                                                     // Block.cpp:396
+        }
+        if (PF) {
+            // ImageBase.cpp:303 + Frame.cpp:218-242 + Block.cpp:110-119: decode what was just encoded and rebuild the
+            // frame in place: cur = (u8)clamp(double(ref[copy block]) + (IDCT(coef*Q) + 128))
+            double X[NN];
+#pragma unroll
+            for (int i = 0; i < NN; i++) X[i] = 0.0;
+#pragma unroll 1
+            for (int uv = 0; uv < NN; uv++) {
+                const int c = cf[tab->izz[uv]];
+                if (c != 0) {
+                    const double d = __dmul_rn((double)c, p.quant.m[uv]);
+                    const double *t = tab->inv + uv * NN;
+#pragma unroll
+                    for (int ij = 0; ij < NN; ij++) X[ij] = __dadd_rn(X[ij], __dmul_rn(__ldg(t + ij), d));
+                }
+            }
+#pragma unroll
+            for (int y = 0; y < N; y++) {
+                unsigned outw = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const double r = (double)(int)__ldg(p.ref + (size_t)(ky + y) * p.pitch + kx + k);
+                    const unsigned v = clamp_trunc_u8(__dadd_rn(r, __dadd_rn(X[y * N + k], 128.0)));
+                    outw |= v << (8 * k);
+                }
+                *reinterpret_cast<unsigned *>(p.cur_rw + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N) = outw;
+            }
         }
         s_w[lb] = (unsigned char)w;
         s_len[lb] = (unsigned char)len;
@@ -126,18 +168,18 @@ __global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodePara
     }
 }
 
-template <int N, int BPL>
+template <int N, int BPL, bool PF>
 static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t stream) {
     constexpr int TB = kThreads * BPL;
     constexpr int STRIDE = N * N + 2;
     const size_t smem = (size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 2 * TB;
     static bool configured = false;
     if (!configured) {
-        IE_CUDA(cudaFuncSetAttribute(encode_tiles_kernel<N, BPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IE_CUDA(cudaFuncSetAttribute(encode_tiles_kernel<N, BPL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid(p.tiles_per_image, images);
-    encode_tiles_kernel<N, BPL><<<grid, kThreads, smem, stream>>>(p);
+    encode_tiles_kernel<N, BPL, PF><<<grid, kThreads, smem, stream>>>(p);
     count_launch();
     IE_CUDA(cudaGetLastError());
     return IE_OK;
@@ -146,10 +188,12 @@ static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t strea
 unsigned encode_tile_blocks(int N) { return N == 8 ? kThreads * 1 : kThreads * 4; }
 
 int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream) {
-    if (N == 8) return launch_cfg<8, 1>(p, images, stream);
-    if (N == 4) return launch_cfg<4, 4>(p, images, stream);
+    if (N == 8) return launch_cfg<8, 1, false>(p, images, stream);
+    if (N == 4) return launch_cfg<4, 4, false>(p, images, stream);
     set_error("block size must be 4 or 8");
     return IE_EINVAL;
 }
+
+int launch_pframe_tiles(const EncodeParams &p, cudaStream_t stream) { return launch_cfg<4, 4, true>(p, 1, stream); }
 
 }  // namespace ie

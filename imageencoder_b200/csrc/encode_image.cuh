@@ -22,9 +22,18 @@ struct EncodeParams {
     unsigned long long *bit_counter;  // [images] in: first free bit of the stream, out: one past the last written bit
     int *err;                         // device error flag
     ScanState scan;
+    // P-frame mode (Frame.cpp:160-244): src is the CURRENT frame (read, then overwritten with the reconstruction),
+    // ref the previous frame as the encoder left it; per-MacroBlock pixel coordinates of the block the residual is
+    // taken from (res_coord, Block.cpp:337) and of the block copied in (copy_coord, Frame.cpp:218-225).
+    const uint8_t *ref;
+    const short *res_coord;           // [nMB][2] (x, y)
+    const short *copy_coord;          // [nMB][2]
+    uint8_t *cur_rw;                  // == src, writable
+    unsigned mbx;                     // MacroBlocks per row
 };
 
 unsigned encode_tile_blocks(int N);
 int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream);
+int launch_pframe_tiles(const EncodeParams &p, cudaStream_t stream);
 
 }  // namespace ie

@@ -1,0 +1,71 @@
+"""Parity of the CUDA video path (C-ABI) against the CPU oracle: byte-identical stream, identical motion vectors
+(observable through the stream), identical decoded frames with and without motion compensation."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, INPUTS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("W,H,F,gop,mer", [(64, 48, 7, 4, 16), (128, 96, 9, 3, 8), (176, 144, 6, 6, 32),
+                                            (64, 64, 5, 1, 16), (64, 48, 6, 7, 2), (64, 48, 5, 4, 1), (96, 64, 6, 4, 10)])
+@pytest.mark.parametrize("huffman", [False, True])
+def test_video_matches_oracle(gpu, oracle_mod, W, H, F, gop, mer, huffman):
+    from imageencoder_b200.synth import synth_video
+    q = oracle_mod.read_matrix(INPUTS / "matrix.txt")
+    yuv = synth_video(W, H, F, 4000)
+    got = gpu.encode_video(yuv, W, H, q, True, gop, mer, huffman)
+    want = oracle_mod.video_encode(yuv, W, H, q, True, gop, mer, huffman)
+    assert got == want, f"stream differs ({len(got)} vs {len(want)} bytes)"
+    key = f"synth4000|{W}x{H}x{F}|gop{gop}|mer{mer}|{'huff' if huffman else 'plain'}"
+    gold = json.loads((GOLDEN / "golden.json").read_text())["video"].get(key)
+    if gold:
+        assert hashlib.sha256(got).hexdigest() == gold["enc_sha256"]
+    if huffman:
+        import ctypes as C
+        # only decodable when the dictionary header did not overflow (Huffman.cpp:39-42)
+        plain = oracle_mod.video_encode(yuv, W, H, q, True, gop, mer, False)
+        if gold and gold["dec_mc1_sha256"] is None:
+            return
+    for mc in (True, False):
+        dec, w, h, f = gpu.decode_video(got, mc)
+        odec = oracle_mod.video_decode(want, mc)[0]
+        assert (w, h, f) == (W, H, F)
+        assert np.array_equal(dec, odec), f"decoded frames differ (motioncompensation={mc})"
+        if gold:
+            assert hashlib.sha256(dec.tobytes()).hexdigest() == gold["dec_mc1_sha256" if mc else "dec_mc0_sha256"]
+
+
+def test_video_rle_off_and_other_matrix(gpu, oracle_mod):
+    from imageencoder_b200.synth import synth_video
+    q = oracle_mod.read_matrix(INPUTS / "matrix4_2.txt")
+    yuv = synth_video(80, 48, 5, 4001)
+    for rle in (True, False):
+        got = gpu.encode_video(yuv, 80, 48, q, rle, 3, 16, False)
+        assert got == oracle_mod.video_encode(yuv, 80, 48, q, rle, 3, 16, False)
+        assert np.array_equal(gpu.decode_video(got, True)[0], oracle_mod.video_decode(got, True)[0])
+
+
+def test_video_scene_cut_and_saturation(gpu, oracle_mod):
+    """frames with nothing in common (large residuals, DC down to -766) and saturated pixels."""
+    rng = np.random.default_rng(5)
+    W, H, F = 64, 48, 6
+    fsz = W * H * 3 // 2
+    yuv = np.full(F * fsz, 0x80, np.uint8)
+    for t in range(F):
+        y = rng.integers(0, 256, (H, W)).astype(np.uint8) if t % 2 else np.full((H, W), 255 * (t // 2 % 2), np.uint8)
+        yuv[t * fsz: t * fsz + W * H] = y.reshape(-1)
+    q = oracle_mod.read_matrix(INPUTS / "matrix.txt")
+    got = gpu.encode_video(yuv, W, H, q, True, 6, 16, False)
+    assert got == oracle_mod.video_encode(yuv, W, H, q, True, 6, 16, False)
+    assert np.array_equal(gpu.decode_video(got, True)[0], oracle_mod.video_decode(got, True)[0])
+
+
+def test_video_errors(gpu):
+    from imageencoder_b200 import IEError
+    with pytest.raises(IEError):
+        gpu.encode_video(np.zeros(40 * 40 * 3 // 2, np.uint8), 40, 40, np.full(16, 2))   # not a multiple of 16
