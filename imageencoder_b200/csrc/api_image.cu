@@ -108,7 +108,7 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
 
     HeaderParam hdr;
     memset(&hdr, 0, sizeof hdr);
-    if (write_header) IE_TRY(build_header(hdr, N, quant, use_rle, W, H, lead_bit, 0, 0, 0, 0));
+    if (write_header) IE_TRY(build_header(hdr, N, quant, use_rle, W, s->header_height ? s->header_height : H, lead_bit, 0, 0, 0, 0));
     if (!bits_only) {
         const size_t need = ((size_t)first_bit + hdr.bits + 127) / 128 * 16;
         if (out_cap < need) { set_error("output buffer too small for the header"); return IE_ENOSPC; }
@@ -268,6 +268,12 @@ int ie_encode_image_dev(ie_session *s, const uint8_t *d_raw, uint32_t W, uint32_
     IE_TRY(encode_images_dev(s, d_raw, 0, 1, W, H, (int)s->N, quant, use_rle, lead_bit, write_header, (unsigned)first_bit, 0,
                              d_out, 0, out_cap, st));
     if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, s->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return IE_OK;
+}
+
+int ie_session_set_header_height(ie_session *s, uint32_t full_height) {
+    if (!s || full_height > 32767) { set_error("bad argument"); return IE_EINVAL; }
+    s->header_height = full_height;
     return IE_OK;
 }
 

@@ -208,6 +208,40 @@ __global__ void shift_copy_kernel(const uint8_t *__restrict__ in, size_t n, uint
     }
 }
 
+// Multi-GPU stitch helper: re-aligns a shard's stream to the chunk grid of the global stream.
+// params[0] = nbits of the shard stream (it starts at bit 0 of `in`), params[1] = the shard's global bit offset.
+// out bit (params[1] % 128 + i) = in bit i; everything else in the written chunks is 0, so neighbouring shards can be
+// OR-merged at their one shared chunk.  Thread per 32-bit output word.
+__global__ void stream_shift_kernel(const uint8_t *__restrict__ in, const unsigned long long *__restrict__ params, uint8_t *out,
+                                    size_t out_cap) {
+    const unsigned long long nbits = params[0];
+    const unsigned shift = (unsigned)(params[1] % kChunkBits);
+    const unsigned long long nwords = ((nbits + shift + kChunkBits - 1) / kChunkBits) * 4;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        if ((w + 1) * 4 > out_cap) return;
+        const long long b0 = (long long)(w * 32) - (long long)shift;          // first input bit of this word
+        unsigned v = 0;
+        if (b0 + 32 > 0 && b0 < (long long)nbits) {
+            // 5 input bytes starting at floor(b0 / 8)
+            const long long by = (b0 >= 0) ? (b0 >> 3) : -((-b0 + 7) >> 3);
+            const unsigned bo = (unsigned)(b0 - by * 8);                       // 0..7
+            unsigned long long win = 0;
+            for (int i = 0; i < 5; i++) {
+                const long long bi = by + i;
+                const unsigned byte = (bi >= 0 && (unsigned long long)bi * 8 < nbits) ? in[bi] : 0u;
+                win = (win << 8) | byte;
+            }
+            v = (unsigned)((win >> (8 - bo)) & 0xffffffffull);
+            // clear bits at or beyond nbits
+            const long long over = b0 + 32 - (long long)nbits;
+            if (over > 0) v &= (over >= 32) ? 0u : (0xffffffffu << over);
+            if (b0 < 0) v &= (0xffffffffu >> (unsigned)(-b0));
+        }
+        reinterpret_cast<unsigned *>(out)[w] = __byte_perm(v, 0, 0x0123);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // decode (one lane; 12-bit primary lookup table, tree walk for longer codes)
 // ---------------------------------------------------------------------------------------------------------
@@ -417,6 +451,18 @@ int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
         IE_CUDA(cudaGetLastError());
     }
     *out_bytes = total;
+    return IE_OK;
+}
+
+int ie_stream_shift_dev(const uint8_t *d_in, const uint64_t *d_params, uint8_t *d_out, size_t out_cap, void *stream) {
+    if (!d_in || !d_params || !d_out) { set_error("NULL argument"); return IE_EINVAL; }
+    if ((uintptr_t)d_out % 16) { set_error("stream buffers must be 16-byte aligned"); return IE_EINVAL; }
+    DeviceState *dev;
+    IE_TRY(get_device_state(&dev));
+    stream_shift_kernel<<<dev->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(d_in, reinterpret_cast<const unsigned long long *>(d_params),
+                                                                            d_out, out_cap);
+    count_launch();
+    IE_CUDA(cudaGetLastError());
     return IE_OK;
 }
 

@@ -7,6 +7,7 @@ struct ie_session {
     int kind = 0;
     uint32_t W = 0, H = 0, N = 0, frames = 1;
     int device = -1;
+    uint32_t header_height = 0;                   // 0: use the height of the call
     ie::DeviceState *dev = nullptr;
 
     // scan scratch, sized for `images` streams of `max_tiles` tiles (zeroed once; self-cleaning afterwards)

@@ -91,6 +91,9 @@ void ie_session_destroy(ie_session *s);
 int ie_encode_image_dev(ie_session *s, const uint8_t *d_raw, uint32_t width, uint32_t height,
                         const uint16_t *quant, int use_rle, int lead_bit, int write_header, uint64_t first_bit,
                         uint8_t *d_out, size_t out_cap, uint64_t *d_out_bits, void *stream);
+/* Height written into the header by the next ie_encode_image_dev calls on this session (0 = the height passed to
+ * the call).  A block-row shard of a larger image writes the FULL image height (ImageEncoder.cpp:93-94). */
+int ie_session_set_header_height(ie_session *s, uint32_t full_height);
 /* Only the per-block bit lengths (first pass of a sharded encode): *d_total_bits = sum over the shard's blocks. */
 int ie_image_bits_dev(ie_session *s, const uint8_t *d_raw, uint32_t width, uint32_t height,
                       const uint16_t *quant, int use_rle, uint64_t *d_total_bits, void *stream);
@@ -113,6 +116,11 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv420, size_t yuv_bytes, uint
 int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, uint64_t start_bit, int motioncompensation,
                         uint8_t *d_yuv_out, size_t yuv_cap, uint32_t *width, uint32_t *height, uint32_t *frames,
                         void *stream);
+
+/* Multi-GPU stitch: re-align a shard stream (bit 0 of d_in, d_params[0] bits long) to the 128-bit chunk
+ * grid of the global stream in which it starts at bit d_params[1]; d_params is a DEVICE array of two u64 so that the
+ * offsets can come straight from an NCCL all-gather + scan without a host round trip. */
+int ie_stream_shift_dev(const uint8_t *d_in, const uint64_t *d_params, uint8_t *d_out, size_t out_cap, void *stream);
 
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 uint64_t ie_kernel_launch_count(void);

@@ -1,0 +1,139 @@
+"""CPU tests of the oracle: the C restatement against the golden vectors made from the compiled reference
+(tests/golden/golden.json, tests/golden/make_golden.py), and live against oracle/_ref when it is present."""
+import hashlib
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, INPUTS
+
+REF_BIN = Path("/root/reference/bin")
+SAMPLES = {"ex0": (8, 8), "ex1": (936, 936), "ex2": (512, 512), "ex3": (400, 400), "ex4": (4096, 912), "ex6": (512, 256)}
+sha = lambda b: hashlib.sha256(bytes(b)).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return json.loads((GOLDEN / "golden.json").read_text())
+
+
+def _sample(name):
+    for d in (INPUTS, REF_BIN):
+        p = d / f"{name}.raw"
+        if p.exists():
+            return np.fromfile(p, dtype=np.uint8)
+    pytest.skip(f"{name}.raw not available here")
+
+
+@pytest.mark.parametrize("name", list(SAMPLES))
+@pytest.mark.parametrize("huff", [False, True])
+def test_reference_samples(oracle_mod, gold, name, huff):
+    W, H = SAMPLES[name]
+    raw = _sample(name)
+    assert sha(raw) == gold["images"][f"{name}|input"]["sha256"]
+    g = gold["images"][f"{name}|matrix.txt|rle1|{'huff' if huff else 'plain'}"]
+    q = oracle_mod.read_matrix(INPUTS / "matrix.txt")
+    enc = oracle_mod.image_encode(raw, W, H, 4, q, True, huff)
+    assert len(enc) == g["enc_bytes"] and sha(enc) == g["enc_sha256"]
+    dec, w, h = oracle_mod.image_decode(enc, 4)
+    assert (w, h) == (W, H) and sha(dec.tobytes()) == g["dec_sha256"]
+
+
+def test_readme_sizes(gold):
+    """known-answer pins inside the reference itself (README.md:177-183) where they agree with the current source"""
+    im = gold["images"]
+    assert im["ex1|matrix.txt|rle1|plain"]["enc_bytes"] == 413210
+    assert im["ex1|matrix.txt|rle1|huff"]["enc_bytes"] == 327658
+    assert im["ex2|matrix.txt|rle1|plain"]["enc_bytes"] == 104597
+    assert im["ex3|matrix.txt|rle1|plain"]["enc_bytes"] == 76033
+    assert im["ex6|matrix.txt|rle1|plain"]["enc_bytes"] == 42198
+
+
+def test_header_length(oracle_mod):
+    """README.md:40: 20.5 bytes of header for matrix.txt (164 bits + the Huffman flag bit of plain builds)"""
+    q = oracle_mod.read_matrix(INPUTS / "matrix.txt")
+    assert oracle_mod.header_bits(4, q, lead_bit=False) == 164
+    assert oracle_mod.header_bits(4, q, lead_bit=True) == 165
+    q8 = oracle_mod.read_matrix(INPUTS / "matrix8_1.txt")
+    assert oracle_mod.header_bits(8, q8, lead_bit=True) == 549
+    assert oracle_mod.header_bits(4, q, lead_bit=True, video=True) == 210
+
+
+@pytest.mark.parametrize("seed,W,H,flat", [(1234, 1024, 1024, False), (1235, 512, 768, True), (2000, 256, 256, False)])
+def test_synthetic_golden(oracle_mod, gold, seed, W, H, flat):
+    from imageencoder_b200.synth import synth_image
+    img = synth_image(W, H, seed, flat=flat)
+    assert sha(img) == gold["images"][f"synth{seed}|input"]["sha256"], "synthetic generator is not reproducible"
+    for m in ("matrix.txt", "matrix4_2.txt", "matrix8_1.txt", "matrix8_2.txt"):
+        q = oracle_mod.read_matrix(INPUTS / m)
+        N = q.shape[0]
+        for rle in (True, False):
+            for huff in (False, True):
+                g = gold["images"][f"synth{seed}|{m}|rle{int(rle)}|{'huff' if huff else 'plain'}"]
+                enc = oracle_mod.image_encode(img, W, H, N, q, rle, huff)
+                assert sha(enc) == g["enc_sha256"], (m, rle, huff)
+                if g["dec_sha256"] is not None:
+                    assert sha(oracle_mod.image_decode(enc, N)[0].tobytes()) == g["dec_sha256"]
+
+
+def test_video_golden(oracle_mod, gold):
+    from imageencoder_b200.synth import synth_video
+    q = oracle_mod.read_matrix(INPUTS / "matrix.txt")
+    for key, g in gold["video"].items():
+        _, dims, gop, mer, kind = key.split("|")
+        W, H, F = (int(v) for v in dims.split("x"))
+        yuv = synth_video(W, H, F, 4000)
+        assert sha(yuv) == g["input_sha256"]
+        enc = oracle_mod.video_encode(yuv, W, H, q, True, int(gop[3:]), int(mer[3:]), kind == "huff")
+        assert len(enc) == g["enc_bytes"] and sha(enc) == g["enc_sha256"], key
+        if g["dec_mc1_sha256"] is not None:
+            assert sha(oracle_mod.video_decode(enc, True)[0]) == g["dec_mc1_sha256"]
+            assert sha(oracle_mod.video_decode(enc, False)[0]) == g["dec_mc0_sha256"]
+
+
+def test_bit_helpers(oracle_mod):
+    """utils.hpp:226-243 / :210-216 semantics (ffs(0) := 0)"""
+    for v, b in [(0, 1), (-1, 1), (1, 2), (-2, 2), (127, 8), (-128, 8), (128, 9), (-129, 9), (32767, 16), (-32768, 16)]:
+        assert oracle_mod.bits_needed(v) == b
+    assert [oracle_mod.ffs(v) for v in (0, 1, 2, 3, 16, 64, 255, 256)] == [0, 1, 2, 2, 5, 7, 8, 9]
+    assert list(oracle_mod.zigzag(4)) == [0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15]
+
+
+def test_rle_quirk_and_allzero(oracle_mod):
+    """all-zero block is exactly '0000'; a full-length block whose last coefficient follows zeroes loses that run
+    (Block.cpp:387-390)"""
+    q = np.ones((4, 4), np.uint16)
+    flat = np.full((4, 4), 128, np.uint8)
+    enc, bits, coef, bl, lf = oracle_mod.image_encode_plain(flat, 4, 4, 4, q, True, True, stages=True)
+    assert bl[0] == 0 and lf[0] == 0 and bits == oracle_mod.header_bits(4, q) + 4
+    rng = np.random.default_rng(0)
+    hit = 0
+    for _ in range(300):
+        img = rng.integers(0, 256, (4, 4)).astype(np.uint8)
+        qq = np.full((4, 4), 24, np.uint16)
+        _, _, coef, bl, lf = oracle_mod.image_encode_plain(img, 4, 4, 4, qq, True, True, stages=True)
+        c = coef[0]
+        nz = np.nonzero(c)[0]
+        if len(nz) and nz[-1] == 15 and (len(nz) == 1 or nz[-2] != 14):
+            hit += 1
+            assert lf[0] == (nz[-2] + 1 if len(nz) > 1 else 0)
+    assert hit > 0
+
+
+@pytest.mark.skipif(not Path(__file__).resolve().parents[1].joinpath("oracle/_ref/ref_n4_plain").exists(),
+                    reason="compiled reference not built (needs /root/reference)")
+def test_oracle_vs_compiled_reference_live(oracle_mod):
+    """random small inputs through the real reference binary and through the restatement"""
+    rng = np.random.default_rng(11)
+    for N, mats in ((4, ("matrix.txt", "matrix4_2.txt")), (8, ("matrix8_1.txt", "matrix8_2.txt"))):
+        for m in mats:
+            q = oracle_mod.read_matrix(INPUTS / m)
+            img = rng.integers(0, 256, (48, 64)).astype(np.uint8)
+            img[8:24, 8:40] = 128
+            for rle in (True, False):
+                ref, _ = oracle_mod.ref_image_encode(img, 64, 48, N, q, rle, False, threads=2)
+                assert oracle_mod.image_encode(img, 64, 48, N, q, rle, False) == ref
+                rdec, _ = oracle_mod.ref_image_decode(ref, N, 64, 48, threads=2)
+                assert np.array_equal(oracle_mod.image_decode(ref, N)[0], rdec)

@@ -1,0 +1,104 @@
+"""CPU tests of the multi-GPU host logic: shard ranges, the offset scan, and a world_size-2 gloo run that exchanges
+bit totals with the same all-gather the NCCL path uses and stitches two shard streams into the oracle's single stream."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import INPUTS
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_shard_ranges():
+    from imageencoder_b200.parallel import shard_block_rows, shard_gops, shard_items
+    for H, N, world in ((16384, 8, 8), (936, 4, 3), (8, 8, 4)):
+        ranges = [shard_block_rows(H, N, world, r) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == H
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert all((y1 - y0) % N == 0 for y0, y1 in ranges)
+    assert [shard_items(1024, 8, r) for r in (0, 7)] == [(0, 128), (896, 1024)]
+    sizes = [(lambda f: (f[1] - f[0]) // 12)(shard_gops(240, 12, 8, r)) for r in range(8)]
+    assert sizes == [3, 3, 3, 3, 2, 2, 2, 2]                  # ideal speed-up 6.67x at 8 GPUs
+    assert shard_gops(10, 4, 2, 1) == (8, 10)
+
+
+def test_place_shards():
+    from imageencoder_b200.parallel import place_shards, total_bytes
+    pl = place_shards([549 + 1000, 300, 0, 77])
+    assert [p.global_bit for p in pl] == [0, 1549, 1849, 1849]
+    assert pl[1].shift == 1549 % 128 and pl[1].byte_offset == 1549 // 128 * 16 and pl[1].shares_first_chunk
+    assert not pl[0].shares_first_chunk and pl[2].nbytes == 0
+    assert total_bytes(pl) == (1849 + 77 + 7) // 8
+
+
+def _bits_of(data: bytes, start: int, n: int) -> np.ndarray:
+    return np.unpackbits(np.frombuffer(data, np.uint8))[start:start + n]
+
+
+def _aligned_shard(bits: np.ndarray, shift: int) -> bytes:
+    padded = np.concatenate([np.zeros(shift, np.uint8), bits])
+    padded = np.concatenate([padded, np.zeros((-len(padded)) % 128, np.uint8)])
+    return np.packbits(padded).tobytes()
+
+
+def _worker(rank: int, world: int, port: int, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    import oracle
+    from imageencoder_b200.parallel import exchange_bit_totals, merge_shard_into, place_shards, shard_block_rows, total_bytes
+    from imageencoder_b200.synth import synth_image
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        W, H, N = 128, 96, 8
+        quant = oracle.read_matrix(INPUTS / "matrix8_1.txt")
+        img = synth_image(W, H, 5, flat=True)
+        full, full_bits, coef, bl, lf = oracle.image_encode_plain(img, W, H, N, quant, True, True, stages=True)
+        hdr = oracle.header_bits(N, quant, True)
+        per_block = 4 + bl.astype(np.int64) + lf.astype(np.int64) * bl.astype(np.int64)
+        y0, y1 = shard_block_rows(H, N, world, rank)
+        b0, b1 = (y0 // N) * (W // N), (y1 // N) * (W // N)
+        start = hdr + int(per_block[:b0].sum())
+        nbits = int(per_block[b0:b1].sum()) + (hdr if rank == 0 else 0)      # rank 0's shard stream carries the header
+        if rank == 0:
+            start = 0
+        totals, offsets = exchange_bit_totals(torch.tensor([nbits], dtype=torch.int64))
+        assert int(offsets[rank]) == start, (rank, int(offsets[rank]), start)
+        pl = place_shards([int(t) for t in totals])
+        shard = _aligned_shard(_bits_of(full, start, nbits), pl[rank].shift)
+        # stitch on rank 0 (byte copies + one OR-merged chunk per boundary)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, shard)
+        if rank == 0:
+            stream = bytearray()
+            for r in range(world):
+                merge_shard_into(stream, gathered[r], pl[r])
+            out = bytes(stream[:total_bytes(pl)])
+            q.put(("ok", out == full, len(out), len(full)))
+    except Exception as e:  # pragma: no cover
+        q.put(("err", repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_offset_scan_and_stitch():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0] == "ok", res
+    assert res[1], f"stitched stream differs from the oracle's ({res[2]} vs {res[3]} bytes)"
