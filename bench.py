@@ -182,10 +182,24 @@ def ours(args):
     d_out = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in range(RING)]
     d_bits = torch.zeros(RING, dtype=torch.int64, device="cuda")
     sess = device.Session(device.Session.IMAGE_ENCODE, W, H, BLOCK)
+    sharded = None
+    if world > 1:
+        # block-row shards of one 8192 x (8192*world) image: encode, all-gather of ONE u64 per rank, offset scan,
+        # re-alignment of the shard to the chunk grid of the single output stream (imageencoder_b200/parallel.py)
+        from imageencoder_b200.parallel import ShardedImageEncoder
+        if H * world > 32767:
+            full_h = None          # > 15-bit header field: the shards are still encoded/placed, only the header height saturates
+        else:
+            full_h = H * world
+        sharded = [ShardedImageEncoder(W, H, BLOCK, full_h) for _ in range(RING)]
 
     def step(i):
         k = i % RING
-        device.encode_image_dev(sess, d_raw[k], q, True, d_out[k], d_bits[k:k + 1])
+        if sharded is None:
+            device.encode_image_dev(sess, d_raw[k], q, True, d_out[k], d_bits[k:k + 1])
+        else:
+            sharded[k].encode(d_raw[k], q, True, rank)
+            d_bits[k:k + 1].copy_(sharded[k].d_bits)
 
     def barrier():
         torch.cuda.synchronize()

@@ -35,9 +35,20 @@ int session_ensure_scan(ie_session *s, unsigned images, unsigned tiles) {
     IE_CUDA(cudaMemset(s->d_bnd, 0, n * sizeof(TileBoundary)));
     IE_CUDA(cudaMemset(s->d_ticket, 0, images * sizeof(unsigned)));
     IE_CUDA(cudaMemset(s->d_counter, 0, images * sizeof(unsigned long long)));
+    // cudaMemset on device memory is asynchronous on the legacy default stream, which the sessions' non-blocking streams
+    // do not wait for: make the zeroes visible before any kernel can touch these arrays
+    IE_CUDA(cudaDeviceSynchronize());
     s->images = images;
     s->max_tiles = tiles;
     s->epoch = 0;
+    return IE_OK;
+}
+
+int session_ensure_err(ie_session *s) {
+    if (s->d_err) return IE_OK;
+    IE_CUDA(cudaMalloc(&s->d_err, sizeof(int)));
+    IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int)));
+    IE_CUDA(cudaDeviceSynchronize());        // see session_ensure_scan
     return IE_OK;
 }
 
@@ -104,7 +115,7 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     const unsigned TB = encode_tile_blocks(N);
     const unsigned tiles = (nblocks + TB - 1) / TB;
     IE_TRY(session_ensure_scan(s, images, tiles));
-    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+    IE_TRY(session_ensure_err(s));
 
     HeaderParam hdr;
     memset(&hdr, 0, sizeof hdr);
@@ -123,6 +134,7 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     p.bx = W / N; p.nblocks = nblocks; p.tiles_per_image = tiles;
     p.use_rle = use_rle ? 1 : 0; p.bits_only = bits_only;
     make_quant(p.quant, quant, N);
+    make_fast_quant(p.fq, quant, N, 128.0);
     p.tab = (N == 8) ? s->dev->d_t8 : s->dev->d_t4;
     p.out = d_out; p.out_stride = out_stride; p.out_cap = out_cap;
     p.bit_counter = s->d_counter; p.err = s->d_err;
@@ -184,7 +196,7 @@ int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size
         if (h.quant[i] == 0) { /* a zero entry decodes to zero coefficients * 0: allowed */ }
     const unsigned nblocks = (W / N) * (H / N);
     IE_TRY(session_ensure_scan(s, 1, 1));
-    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+    IE_TRY(session_ensure_err(s));
     const size_t need_off = ((size_t)nblocks + 1) * sizeof(unsigned long long) + 64;
     if (s->block_off_cap < need_off) {
         if (s->d_block_off) IE_CUDA(cudaFree(s->d_block_off));

@@ -212,7 +212,7 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     const unsigned nblocks = (W / 4) * (H / 4), nmb = (W / kMB) * (H / kMB);
     const unsigned TB = encode_tile_blocks(4), tiles = (nblocks + TB - 1) / TB;
     IE_TRY(session_ensure_scan(s, 1, tiles));
-    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+    IE_TRY(session_ensure_err(s));
     VideoScratch vs;
     IE_TRY(video_scratch(s, nmb, vs));
     const unsigned mvbits = host_bits_needed((int)(short)merange);           // VideoBase.cpp:42
@@ -226,6 +226,9 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     memset(&p, 0, sizeof p);
     p.pitch = W; p.bx = W / 4; p.nblocks = nblocks; p.tiles_per_image = tiles; p.use_rle = use_rle ? 1 : 0;
     make_quant(p.quant, quant, 4);
+    FastQuant fq_i, fq_p;
+    make_fast_quant(fq_i, quant, 4, 128.0);      // I-frames: pixel - 128
+    make_fast_quant(fq_p, quant, 4, 383.0);      // P-frames: (pixel - ref) - 128 in [-383, 127]
     p.tab = s->dev->d_t4;
     p.out = d_out; p.out_cap = out_cap; p.bit_counter = s->d_counter; p.err = s->d_err;
     p.mbx = W / kMB;
@@ -234,6 +237,7 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
         p.src = cur;
         p.scan = s->scan_state();
         if (f % gop == 0) {                                                    // VideoBase.hpp:32, Frame.cpp:130-159
+            p.fq = fq_i;
             IE_TRY(launch_encode_tiles(4, p, 1, st));
             if (d_mvecs) IE_CUDA(cudaMemsetAsync(d_mvecs + (size_t)f * nmb * 2, 0, nmb * 2 * sizeof(short), st));
             continue;
@@ -247,6 +251,7 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
         count_launch();
         IE_CUDA(cudaGetLastError());
         if (d_mvecs) IE_CUDA(cudaMemcpyAsync(d_mvecs + (size_t)f * nmb * 2, vs.mv, nmb * 2 * sizeof(short), cudaMemcpyDeviceToDevice, st));
+        p.fq = fq_p;
         p.ref = me.ref; p.res_coord = vs.res; p.copy_coord = vs.copy; p.cur_rw = cur;
         IE_TRY(launch_pframe_tiles(p, st));
     }
@@ -311,7 +316,7 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
     if (fsz * frames > out_cap) { set_error("decoded video does not fit the output buffer"); return IE_ENOSPC; }
     const unsigned nblocks = (W / 4) * (H / 4), nmb = (W / kMB) * (H / kMB);
     const unsigned mvbits = host_bits_needed((int)(short)h.merange);
-    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+    IE_TRY(session_ensure_err(s));
     VideoScratch vs;
     IE_TRY(video_scratch(s, nmb, vs));
     const size_t need_off = ((size_t)nblocks + 1) * sizeof(unsigned long long) + 64;

@@ -1,5 +1,6 @@
 // Host-side core: error plumbing, arithmetic tables, header builder, per-device state.
 #include "common.cuh"
+#include "transform_fast.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -10,6 +11,7 @@
 
 namespace ie {
 
+extern std::atomic<int> g_exact_transform;   // encode_image.cu
 static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
 
@@ -120,6 +122,22 @@ int build_header(HeaderParam &h, int N, const uint16_t *quant, int use_rle, uint
     return IE_OK;
 }
 
+// fast-path constants: k = C(u)C(v)/Q, thr = 0.5 - delta with delta = 1.25 * (768 + 64) * 2^-24 * X * k  (transform_fast.cuh)
+void make_fast_quant(FastQuant &fq, const uint16_t *quant, int N, double max_abs_sample) {
+    memset(&fq, 0, sizeof fq);
+    for (int u = 0; u < N; u++)
+        for (int v = 0; v < N; v++) {
+            const double cu = (u == 0) ? 0.5 : M_SQRT1_2, cv = (v == 0) ? 0.5 : M_SQRT1_2;
+            const double k = cu * cv / (double)quant[u * N + v];
+            const double delta = 1.25 * (768.0 + 64.0) * ldexp(1.0, -24) * max_abs_sample * k + 1e-6;
+            fq.k[u * N + v] = (float)k;
+            double thr = 0.5 - delta;
+            if (thr < 0.0) thr = 0.0;                       // absurd quant/geometry: every coefficient takes the exact path
+            fq.thr[u * N + v] = nextafterf((float)thr, 0.0f);
+        }
+    for (int i = N * N; i < kMaxNN; i++) { fq.k[i] = 0.f; fq.thr[i] = 1.f; }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // per-device state
 // ---------------------------------------------------------------------------------------------------------
@@ -149,6 +167,7 @@ int get_device_state(DeviceState **out) {
         IE_CUDA(cudaMalloc(&s.d_t8, sizeof(BlockTables)));
         IE_CUDA(cudaMemcpy(s.d_t4, &ht.t4, sizeof(BlockTables), cudaMemcpyHostToDevice));
         IE_CUDA(cudaMemcpy(s.d_t8, &ht.t8, sizeof(BlockTables), cudaMemcpyHostToDevice));
+        IE_CUDA(cudaDeviceSynchronize());   // pageable H2D may still be in flight; other streams do not wait for stream 0
         s.sm_count = prop.multiProcessorCount;
         s.device = dev;
     }
@@ -185,6 +204,12 @@ void ie_shutdown(void) {
 const char *ie_last_error(void) { return ie::t_error.c_str(); }
 const char *ie_version(void) { return "imageencoder_b200 0.1 (sm_100a)"; }
 uint64_t ie_kernel_launch_count(void) { return ie::g_launches.load(); }
+
+int ie_set_option(const char *name, int value) {
+    if (name && !strcmp(name, "exact_transform")) { ie::g_exact_transform.store(value); return IE_OK; }
+    ie::set_error("unknown option");
+    return IE_EINVAL;
+}
 
 size_t ie_max_encoded_bytes(uint32_t width, uint32_t height, uint32_t block, uint32_t frames) {
     if (block != 4 && block != 8) return 0;

@@ -3,13 +3,39 @@
 //   -> CTA scan of block bit counts -> decoupled look-back for the tile's stream offset
 //   -> chunk-centric gather/pack straight into the stream                              (thread per 128-bit chunk)
 // One pass over HBM: W*H bytes in, the stream out.  Replaces ImageEncoder.cpp:121-138 (parallel DCT loop + the
-// strictly serial streamEncoded loop) and Frame.cpp:141-158 (I-frames).
+// strictly serial streamEncoded loop), Frame.cpp:141-158 (I-frames) and, with PF, Frame.cpp:160-244 (P-frame blocks).
+//
+// Template switches: N block size, BPL blocks per lane, PF P-frame mode (residual in, reconstruction out),
+// FAST = FP32 factorised transform + guard band + exact fallback (transform_fast.cuh); FAST=false evaluates every
+// coefficient in the reference's exact order (kept for cross-checking: ie_set_option("exact_transform", 1)).
 #include "encode_image.cuh"
+#include "transform_fast.cuh"
 
 namespace ie {
 
-template <int N, int BPL, bool PF>
-__global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodeParams p) {
+// inverse zigzag (raster index -> zigzag position), algo.cpp:68-87, for compile-time use in the unrolled fast path
+__device__ constexpr unsigned char kZigzagInv4[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};
+__device__ constexpr unsigned char kZigzagInv8[64] = {
+    0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30, 41, 43, 9,  11, 18, 24, 31, 40, 44, 53,
+    10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+
+// RLE info from the staged zigzag coefficients (slow generic path; used after a guard-band patch and by FAST=false)
+template <int NN>
+__device__ __forceinline__ void block_stats_from_staging(const short *cf, int &lastnz, int &prevnz, unsigned &orbits) {
+    lastnz = 0; prevnz = 0; orbits = 0;
+#pragma unroll 4
+    for (int k = 0; k < NN; k++) {
+        const int q = cf[k];
+        if (q != 0) {
+            orbits |= (unsigned)(q ^ (q >> 31));
+            prevnz = (k < NN - 1) ? (k + 1) : prevnz;
+            lastnz = k + 1;
+        }
+    }
+}
+
+template <int N, int BPL, bool PF, bool FAST>
+__global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_tiles_kernel(const EncodeParams p) {
     constexpr int NN = N * N;
     constexpr int TB = kThreads * BPL;            // blocks per tile
     constexpr int STRIDE = NN + 2;                // halfwords per block in the staging area (bank spread)
@@ -46,7 +72,7 @@ __global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodePara
         if (lb >= nblk) { if (lb < TB) s_off[lb] = 0; continue; }
         const unsigned gb = first_blk + lb;
         const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
-        double x[NN];
+        short *cf = s_coef + (size_t)lb * STRIDE;
         int rx = 0, ry = 0, kx = 0, ky = 0;        // P-frame: top-left of this micro block inside the residual / copy source
         if (PF) {
             const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
@@ -54,44 +80,99 @@ __global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodePara
             rx = p.res_coord[2 * mb] + ox;  ry = p.res_coord[2 * mb + 1] + oy;
             kx = p.copy_coord[2 * mb] + ox; ky = p.copy_coord[2 * mb + 1] + oy;
         }
+        // raw pixel words of the block: N rows x N bytes (kept for the exact fallback)
+        unsigned raw[N * (N / 4)];
 #pragma unroll
         for (int y = 0; y < N; y++) {
             const uint8_t *row = src + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N;
             if (N == 8) {
                 const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row));
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    x[y * N + k] = (double)(int)((v.x >> (8 * k)) & 0xff) - 128.0;       // Block.cpp:52-54, 141-143
-                    x[y * N + 4 + k] = (double)(int)((v.y >> (8 * k)) & 0xff) - 128.0;
-                }
+                raw[2 * y] = v.x; raw[2 * y + 1] = v.y;
             } else {
-                const unsigned v = PF ? *reinterpret_cast<const unsigned *>(row) : __ldg(reinterpret_cast<const unsigned *>(row));
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    double px = (double)(int)((v >> (8 * k)) & 0xff);
-                    if (PF) {
-                        const double r = (double)(int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + k);
-                        px = __dsub_rn(px, r);                                           // Block.cpp:262
-                    }
-                    x[y * N + k] = __dadd_rn(px, -128.0);                                // applied to residuals too
-                }
+                raw[y] = PF ? *reinterpret_cast<const unsigned *>(row) : __ldg(reinterpret_cast<const unsigned *>(row));
             }
         }
-        short *cf = s_coef + (size_t)lb * STRIDE;
-        int lastnz = 0, prevnz = 0;      // (zigzag index + 1) of the last / of the last-but-final-position non-zero
+        // integer sample values: pixel (images) or pixel - reference pixel (P-frames, Block.cpp:262); -128 is applied
+        // on top (Block.cpp:141-143: to residuals too)
+        int ref_px[PF ? NN : 1];
+        if (PF) {
+#pragma unroll
+            for (int y = 0; y < N; y++)
+#pragma unroll
+                for (int k = 0; k < N; k++) ref_px[y * N + k] = (int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + k);
+        }
+        auto sample = [&](int ij) -> int {
+            const int px = (int)((raw[ij >> 2] >> (8 * (ij & 3))) & 0xffu);
+            return PF ? (px - ref_px[PF ? ij : 0]) : px;
+        };
+
+        int lastnz = 0, prevnz = 0;      // (zigzag index + 1) of the last / of the last non-final-position non-zero
         unsigned orbits = 0;
-#pragma unroll 1
-        for (int uv = 0; uv < NN; uv++) {
-            const double e = fdct_coef_exact<NN>(tab->fw + uv * NN, x, tab->cc[uv]);
-            const double qd = round_half_away(__ddiv_rn(e, p.quant.m[uv]));               // Block.cpp:152
-            const int q = (int)(short)__double2int_rz(qd);                                // Block.cpp:205: int16_t(double)
-            const int k = tab->izz[uv];
-            cf[k] = (short)q;
-            if (q != 0) {
-                orbits |= (unsigned)(q ^ (q >> 31));
-                lastnz = max(lastnz, k + 1);
-                if (k < NN - 1) prevnz = max(prevnz, k + 1);
+        if (FAST) {
+            float x[NN];
+#pragma unroll
+            for (int ij = 0; ij < NN; ij++) {
+                if (PF) x[ij] = (float)(sample(ij) - 128);
+                else x[ij] = __uint_as_float(__byte_perm(raw[ij >> 2], 0x4B000000u, 0x7650u | (unsigned)(ij & 3))) - 8388736.0f;
             }
+            fdct2d_fast<N>(x);
+            unsigned long long near = 0;
+            constexpr int NSEG = NN / 8;
+            unsigned orseg[NSEG];
+#pragma unroll
+            for (int s = 0; s < NSEG; s++) orseg[s] = 0;
+#pragma unroll
+            for (int uv = 0; uv < NN; uv++) {
+                const float rr = fmaf(x[uv], p.fq.k[uv], kMagic);          // rn(q~) in the mantissa
+                const float rf = rr - kMagic;
+                const float d = fmaf(x[uv], p.fq.k[uv], -rf);
+                if (fabsf(d) >= p.fq.thr[uv]) near |= 1ull << uv;           // inside the guard band -> exact recompute
+                const int q = __float_as_int(rr) - kMagicBits;
+                const int k = (N == 8) ? kZigzagInv8[uv] : kZigzagInv4[uv];
+                cf[k] = (short)q;
+                orseg[k >> 3] |= (unsigned)q;                               // non-zero detection per zigzag segment
+                orbits |= (unsigned)(q ^ (q >> 31));                        // bits_needed of the widest value (-1 -> 0)
+            }
+            bool patched = false;
+            while (near) {
+                const int uv = __ffsll((long long)near) - 1;
+                near &= near - 1;
+                const double *t = tab->fw + uv * NN;
+                double acc = 0.0;
+#pragma unroll
+                for (int ij = 0; ij < NN; ij++) acc = __dadd_rn(acc, __dmul_rn(__ldg(t + ij), (double)(sample(ij) - 128)));
+                const double e = __dmul_rn(acc, tab->cc[uv]);
+                const int q = (int)(short)__double2int_rz(round_half_away(__ddiv_rn(e, p.quant.m[uv])));
+                const int k = tab->izz[uv];
+                if (cf[k] != (short)q) { cf[k] = (short)q; patched = true; }
+            }
+            if (patched) {
+                block_stats_from_staging<NN>(cf, lastnz, prevnz, orbits);
+            } else {
+                int lastseg = -1;
+#pragma unroll
+                for (int s = 0; s < NSEG; s++) if (orseg[s]) lastseg = s;
+                if (lastseg >= 0) {
+                    // last non-zero inside the last non-empty 8-coefficient zigzag segment
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (cf[lastseg * 8 + j] != 0) lastnz = lastseg * 8 + j + 1;
+                    if (lastnz == NN) {          // rare: the RLE quirk needs the previous non-zero as well
+                        for (int k = 0; k < NN - 1; k++) if (cf[k] != 0) prevnz = k + 1;
+                    }
+                }
+            }
+        } else {
+            double x[NN];
+#pragma unroll
+            for (int ij = 0; ij < NN; ij++) x[ij] = __dadd_rn((double)sample(ij), -128.0);
+#pragma unroll 1
+            for (int uv = 0; uv < NN; uv++) {
+                const double e = fdct_coef_exact<NN>(tab->fw + uv * NN, x, tab->cc[uv]);
+                const double qd = round_half_away(__ddiv_rn(e, p.quant.m[uv]));               // Block.cpp:152
+                const int q = (int)(short)__double2int_rz(qd);                                // Block.cpp:205: int16_t(double)
+                cf[tab->izz[uv]] = (short)q;
+            }
+            block_stats_from_staging<NN>(cf, lastnz, prevnz, orbits);
         }
         // Block.cpp:214-219, 231: data_bits = max(max bits_needed(nz), ffs(data)), data = last non-zero index + 1
         int w = lastnz ? (33 - __clz(orbits)) : 0;
@@ -124,8 +205,8 @@ __global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodePara
                 unsigned outw = 0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const double r = (double)(int)__ldg(p.ref + (size_t)(ky + y) * p.pitch + kx + k);
-                    const unsigned v = clamp_trunc_u8(__dadd_rn(r, __dadd_rn(X[y * N + k], 128.0)));
+                    const double rpx = (double)(int)__ldg(p.ref + (size_t)(ky + y) * p.pitch + kx + k);
+                    const unsigned v = clamp_trunc_u8(__dadd_rn(rpx, __dadd_rn(X[y * N + k], 128.0)));
                     outw |= v << (8 * k);
                 }
                 *reinterpret_cast<unsigned *>(p.cur_rw + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N) = outw;
@@ -168,18 +249,18 @@ __global__ void __launch_bounds__(kThreads) encode_tiles_kernel(const EncodePara
     }
 }
 
-template <int N, int BPL, bool PF>
+template <int N, int BPL, bool PF, bool FAST>
 static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t stream) {
     constexpr int TB = kThreads * BPL;
     constexpr int STRIDE = N * N + 2;
     const size_t smem = (size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 2 * TB;
     static bool configured = false;
     if (!configured) {
-        IE_CUDA(cudaFuncSetAttribute(encode_tiles_kernel<N, BPL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IE_CUDA(cudaFuncSetAttribute(encode_tiles_kernel<N, BPL, PF, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid(p.tiles_per_image, images);
-    encode_tiles_kernel<N, BPL, PF><<<grid, kThreads, smem, stream>>>(p);
+    encode_tiles_kernel<N, BPL, PF, FAST><<<grid, kThreads, smem, stream>>>(p);
     count_launch();
     IE_CUDA(cudaGetLastError());
     return IE_OK;
@@ -187,13 +268,18 @@ static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t strea
 
 unsigned encode_tile_blocks(int N) { return N == 8 ? kThreads * 1 : kThreads * 4; }
 
+std::atomic<int> g_exact_transform{0};
+
 int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream) {
-    if (N == 8) return launch_cfg<8, 1, false>(p, images, stream);
-    if (N == 4) return launch_cfg<4, 4, false>(p, images, stream);
+    const bool exact = g_exact_transform.load() != 0;
+    if (N == 8) return exact ? launch_cfg<8, 1, false, false>(p, images, stream) : launch_cfg<8, 1, false, true>(p, images, stream);
+    if (N == 4) return exact ? launch_cfg<4, 4, false, false>(p, images, stream) : launch_cfg<4, 4, false, true>(p, images, stream);
     set_error("block size must be 4 or 8");
     return IE_EINVAL;
 }
 
-int launch_pframe_tiles(const EncodeParams &p, cudaStream_t stream) { return launch_cfg<4, 4, true>(p, 1, stream); }
+int launch_pframe_tiles(const EncodeParams &p, cudaStream_t stream) {
+    return g_exact_transform.load() ? launch_cfg<4, 4, true, false>(p, 1, stream) : launch_cfg<4, 4, true, true>(p, 1, stream);
+}
 
 }  // namespace ie

@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include "pack.cuh"
 #include "transform.cuh"
+#include "transform_fast.cuh"
+#include <atomic>
 
 namespace ie {
 
@@ -15,6 +17,7 @@ struct EncodeParams {
     int use_rle;
     int bits_only;                    // 1: only the bit totals (first pass of a sharded encode)
     QuantParam quant;
+    FastQuant fq;                     // fast-path constants + guard-band thresholds (transform_fast.cuh)
     const BlockTables *tab;
     uint8_t *out;                     // device stream buffer(s), 16-byte aligned
     size_t out_stride;                // bytes between the streams of a batch
@@ -33,6 +36,9 @@ struct EncodeParams {
 };
 
 unsigned encode_tile_blocks(int N);
+extern std::atomic<int> g_exact_transform;
+// max_abs_sample: 128 for pixels - 128, 383 for P-frame residuals - 128
+void make_fast_quant(FastQuant &fq, const uint16_t *quant, int N, double max_abs_sample);
 int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream);
 int launch_pframe_tiles(const EncodeParams &p, cudaStream_t stream);
 

@@ -407,7 +407,7 @@ int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
     unsigned long long *d_first = reinterpret_cast<unsigned long long *>(s->d_scratch);
     unsigned *d_hist = reinterpret_cast<unsigned *>(s->d_scratch + 256 * 8);
     HuffCodes *d_codes = reinterpret_cast<HuffCodes *>(s->d_scratch + 256 * 8 + 256 * 4);
-    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+    IE_TRY(session_ensure_err(s));
 
     IE_CUDA(cudaMemsetAsync(d_hist, 0, 256 * 4, st));
     IE_CUDA(cudaMemsetAsync(d_first, 0xff, 256 * 8, st));
@@ -470,7 +470,7 @@ int ie_huffman_decode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
                           uint64_t *start_bit, void *stream) {
     if (!s || !d_in || !d_out || !out_bytes || !start_bit || n == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
-    if (!s->d_err) { IE_CUDA(cudaMalloc(&s->d_err, sizeof(int))); IE_CUDA(cudaMemset(s->d_err, 0, sizeof(int))); }
+    IE_TRY(session_ensure_err(s));
     // dictionary header: at most 256 * (8 + 15) + 16 * 12 + 1 bits < 1 KiB (4-bit length field); parse it on the host
     std::vector<uint8_t> head(std::min<size_t>(n, 1024));
     IE_CUDA(cudaMemcpyAsync(head.data(), d_in, head.size(), cudaMemcpyDeviceToHost, st));

@@ -50,4 +50,5 @@ struct ie_session {
 namespace ie {
 int session_reserve(uint8_t **p, size_t *cap, size_t need);
 int session_ensure_scan(ie_session *s, unsigned images, unsigned tiles);
+int session_ensure_err(ie_session *s);
 }  // namespace ie

@@ -122,6 +122,10 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
  * offsets can come straight from an NCCL all-gather + scan without a host round trip. */
 int ie_stream_shift_dev(const uint8_t *d_in, const uint64_t *d_params, uint8_t *d_out, size_t out_cap, void *stream);
 
+/* Diagnostics switch.  "exact_transform" = 1 makes the encoders evaluate every coefficient in the reference's exact
+ * binary64 order instead of the guarded FP32 fast path (both produce identical streams; tests cross-check them). */
+int ie_set_option(const char *name, int value);
+
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 uint64_t ie_kernel_launch_count(void);
 

@@ -125,3 +125,28 @@ def test_properties_at_scale(gpu, oracle_mod):
     enc_h = gpu.encode_image(img, W, H, q, True, True)
     assert enc_h == oracle_mod.image_encode(img, W, H, 8, q, True, True)
     assert np.array_equal(gpu.decode_image(enc_h, 8), dec)
+
+
+def test_fast_path_equals_exact_path_at_scale(gpu):
+    """size-independent property at BASELINE size: the guarded FP32 fast path and the exact-order FP64 path produce the
+    same stream on 8192x8192 (too large for the CPU oracle in a test), plus adversarial tie-heavy content."""
+    from imageencoder_b200.synth import synth_image
+    L = gpu.lib()
+    q8 = gpu.read_matrix(INPUTS / "matrix8_1.txt")
+    q4 = gpu.read_matrix(INPUTS / "matrix.txt")
+    rng = np.random.default_rng(9)
+    cases = [("synth8192", synth_image(8192, 8192, 1234), q8),
+             ("synth4096_4x4", synth_image(4096, 4096, 2000), q4),
+             # 2-level images make many exact .5 ties at the rational coefficient positions (SURVEY 0.3)
+             ("ties8", (rng.integers(0, 2, (1024, 1024)) * 16 + 120).astype(np.uint8), q8),
+             ("ties4", (rng.integers(0, 4, (1024, 1024)) * 8 + 112).astype(np.uint8), q4),
+             ("noise8", rng.integers(0, 256, (1024, 1024)).astype(np.uint8), np.ones((8, 8), np.uint16))]
+    for name, img, q in cases:
+        H, W = img.shape
+        fast = gpu.encode_image(img, W, H, q, True, False)
+        assert L.ie_set_option(b"exact_transform", 1) == 0
+        try:
+            exact = gpu.encode_image(img, W, H, q, True, False)
+        finally:
+            L.ie_set_option(b"exact_transform", 0)
+        assert fast == exact, f"{name}: fast path differs from the exact path"
