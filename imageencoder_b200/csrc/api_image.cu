@@ -135,6 +135,7 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     p.use_rle = use_rle ? 1 : 0; p.bits_only = bits_only;
     make_quant(p.quant, quant, N);
     make_fast_quant(p.fq, quant, N, 128.0);
+    p.dc_den2 = 8 * (int)quant[0]; p.dc_rcp = 1.0f / (float)p.dc_den2;
     p.tab = (N == 8) ? s->dev->d_t8 : s->dev->d_t4;
     p.out = d_out; p.out_stride = out_stride; p.out_cap = out_cap;
     p.bit_counter = s->d_counter; p.err = s->d_err;

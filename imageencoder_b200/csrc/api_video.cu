@@ -229,6 +229,7 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     FastQuant fq_i, fq_p;
     make_fast_quant(fq_i, quant, 4, 128.0);      // I-frames: pixel - 128
     make_fast_quant(fq_p, quant, 4, 383.0);      // P-frames: (pixel - ref) - 128 in [-383, 127]
+    p.dc_den2 = 8 * (int)quant[0]; p.dc_rcp = 1.0f / (float)p.dc_den2;
     p.tab = s->dev->d_t4;
     p.out = d_out; p.out_cap = out_cap; p.bit_counter = s->d_counter; p.err = s->d_err;
     p.mbx = W / kMB;

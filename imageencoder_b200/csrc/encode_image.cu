@@ -34,19 +34,65 @@ __device__ __forceinline__ void block_stats_from_staging(const short *cf, int &l
     }
 }
 
+// Sample (pixel, or pixel - reference pixel for P-frames) of block (byi, bxi) at raster position ij, minus 128, re-read
+// from global memory (used by the exact fallback, which runs on a different thread than the one that owns the block).
+struct ExactCtx {              // the few launch constants the exact path needs (passed by value: no param-space copy)
+    const uint8_t *src, *ref;
+    const short *res_coord;
+    const BlockTables *tab;
+    size_t pitch;
+    unsigned bx, mbx;
+};
+
+template <int N, bool PF>
+__device__ __forceinline__ double exact_sample(const ExactCtx &p, const uint8_t *src, unsigned byi, unsigned bxi, int rx, int ry, int ij) {
+    const int y = ij / N, x = ij % N;
+    int v = (int)__ldg(src + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N + x);
+    if (PF) v -= (int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + x);                 // Block.cpp:262
+    return __dadd_rn((double)v, -128.0);                                                    // Block.cpp:141-143
+}
+
+// One coefficient of one block in the reference's exact order and precision (algo.cpp:309-331, Block.cpp:152).
+template <int N, bool PF>
+__device__ __noinline__ int exact_coefficient(const ExactCtx p, unsigned gb, int uv, double m_uv) {
+    const uint8_t *src = p.src;
+    constexpr int NN = N * N;
+    const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
+    int rx = 0, ry = 0;
+    if (PF) {
+        const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
+        rx = p.res_coord[2 * mb] + (int)(bxi & 3) * 4;
+        ry = p.res_coord[2 * mb + 1] + (int)(byi & 3) * 4;
+    }
+    const double *t = p.tab->fw + uv * NN;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int ij = 0; ij < NN; ij++) acc = __dadd_rn(acc, __dmul_rn(__ldg(t + ij), exact_sample<N, PF>(p, src, byi, bxi, rx, ry, ij)));
+    const double e = __dmul_rn(acc, p.tab->cc[uv]);
+    return (int)(short)__double2int_rz(round_half_away(__ddiv_rn(e, m_uv)));
+}
+
+constexpr int kQueueCap = 1024;       // guard-band fallback entries per tile handled by the CTA-wide queue
+
 template <int N, int BPL, bool PF, bool FAST>
 __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_tiles_kernel(const EncodeParams p) {
     constexpr int NN = N * N;
     constexpr int TB = kThreads * BPL;            // blocks per tile
-    constexpr int STRIDE = NN + 2;                // halfwords per block in the staging area (bank spread)
+    constexpr int STRIDE = NN + 2;                // halfwords per block in the staging area: NN/2 + 1 words (odd -> bank spread)
+    constexpr int NSEG = NN / 8;
+    constexpr int MAXCHUNKS = (TB * (4 + 16 + 16 * NN) + 127) / 128 + 2;
     extern __shared__ __align__(16) unsigned char smem[];
     short *s_coef = reinterpret_cast<short *>(smem);
     unsigned *s_off = reinterpret_cast<unsigned *>(smem + (size_t)TB * STRIDE * sizeof(short));
-    unsigned char *s_w = reinterpret_cast<unsigned char *>(s_off + TB + 1);
+    unsigned short *s_map = reinterpret_cast<unsigned short *>(s_off + TB + 1);
+    unsigned *s_queue = reinterpret_cast<unsigned *>(s_map + ((MAXCHUNKS + 1) & ~1));
+    unsigned char *s_w = reinterpret_cast<unsigned char *>(s_queue + kQueueCap);
     unsigned char *s_len = s_w + TB;
+    unsigned char *s_dirty = s_len + TB;
     __shared__ unsigned s_warp[kThreads / 32 + 1];
     __shared__ unsigned long long s_bcast;
     __shared__ unsigned s_tile;
+    __shared__ unsigned s_qn;
 
     const unsigned img = blockIdx.y;
     ScanState st = p.scan;
@@ -54,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
     st.bnd += (size_t)img * p.tiles_per_image;
     st.ticket += img;
 
-    if (threadIdx.x == 0) s_tile = atomicAdd(st.ticket, 1u);
+    if (threadIdx.x == 0) { s_tile = atomicAdd(st.ticket, 1u); s_qn = 0; }
     __syncthreads();
     const unsigned tile = s_tile;
     const unsigned ntiles = p.tiles_per_image;
@@ -63,116 +109,147 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
 
     const uint8_t *src = p.src + (size_t)img * p.img_stride;
     const BlockTables *tab = p.tab;
+    ExactCtx ex;
+    ex.src = src; ex.ref = p.ref; ex.res_coord = p.res_coord; ex.tab = tab; ex.pitch = p.pitch; ex.bx = p.bx; ex.mbx = p.mbx;
 
-    // ---- phase 1: transform + quantise + RLE info, lane per block ---------------------------------------
-    unsigned my_bits = 0;
-#pragma unroll 1
+    // ---- phase 1: transform + quantise, lane per block ---------------------------------------------------
+    unsigned r_orbits[BPL];
+    unsigned r_orseg[BPL][NSEG];
+#pragma unroll
     for (int r = 0; r < BPL; r++) {
         const int lb = threadIdx.x * BPL + r;
-        if (lb >= nblk) { if (lb < TB) s_off[lb] = 0; continue; }
+        r_orbits[r] = 0;
+#pragma unroll
+        for (int s = 0; s < NSEG; s++) r_orseg[r][s] = 0;
+        if (lb >= nblk) continue;
+        s_dirty[lb] = 0;
         const unsigned gb = first_blk + lb;
         const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
         short *cf = s_coef + (size_t)lb * STRIDE;
-        int rx = 0, ry = 0, kx = 0, ky = 0;        // P-frame: top-left of this micro block inside the residual / copy source
+        int rx = 0, ry = 0;
         if (PF) {
             const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
-            const int ox = (int)(bxi & 3) * 4, oy = (int)(byi & 3) * 4;
-            rx = p.res_coord[2 * mb] + ox;  ry = p.res_coord[2 * mb + 1] + oy;
-            kx = p.copy_coord[2 * mb] + ox; ky = p.copy_coord[2 * mb + 1] + oy;
+            rx = p.res_coord[2 * mb] + (int)(bxi & 3) * 4;
+            ry = p.res_coord[2 * mb + 1] + (int)(byi & 3) * 4;
         }
-        // raw pixel words of the block: N rows x N bytes (kept for the exact fallback)
-        unsigned raw[N * (N / 4)];
-#pragma unroll
-        for (int y = 0; y < N; y++) {
-            const uint8_t *row = src + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N;
-            if (N == 8) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row));
-                raw[2 * y] = v.x; raw[2 * y + 1] = v.y;
-            } else {
-                raw[y] = PF ? *reinterpret_cast<const unsigned *>(row) : __ldg(reinterpret_cast<const unsigned *>(row));
-            }
-        }
-        // integer sample values: pixel (images) or pixel - reference pixel (P-frames, Block.cpp:262); -128 is applied
-        // on top (Block.cpp:141-143: to residuals too)
-        int ref_px[PF ? NN : 1];
-        if (PF) {
-#pragma unroll
-            for (int y = 0; y < N; y++)
-#pragma unroll
-                for (int k = 0; k < N; k++) ref_px[y * N + k] = (int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + k);
-        }
-        auto sample = [&](int ij) -> int {
-            const int px = (int)((raw[ij >> 2] >> (8 * (ij & 3))) & 0xffu);
-            return PF ? (px - ref_px[PF ? ij : 0]) : px;
-        };
-
-        int lastnz = 0, prevnz = 0;      // (zigzag index + 1) of the last / of the last non-final-position non-zero
-        unsigned orbits = 0;
         if (FAST) {
             float x[NN];
 #pragma unroll
-            for (int ij = 0; ij < NN; ij++) {
-                if (PF) x[ij] = (float)(sample(ij) - 128);
-                else x[ij] = __uint_as_float(__byte_perm(raw[ij >> 2], 0x4B000000u, 0x7650u | (unsigned)(ij & 3))) - 8388736.0f;
+            for (int y = 0; y < N; y++) {
+                const uint8_t *row = src + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N;
+                unsigned raw[N / 4];
+                if (N == 8) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row));
+                    raw[0] = v.x; raw[N / 4 - 1] = v.y;
+                } else {
+                    raw[0] = PF ? *reinterpret_cast<const unsigned *>(row) : __ldg(reinterpret_cast<const unsigned *>(row));
+                }
+#pragma unroll
+                for (int k = 0; k < N; k++) {
+                    // byte -> float by planting it in the mantissa of 2^23, then subtracting 2^23 + 128 (exact)
+                    float f = __uint_as_float(__byte_perm(raw[k >> 2], 0x4B000000u, 0x7650u | (unsigned)(k & 3))) - 8388736.0f;
+                    if (PF) f -= (float)(int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + k);      // exact small integers
+                    x[y * N + k] = f;
+                }
             }
             fdct2d_fast<N>(x);
             unsigned long long near = 0;
-            constexpr int NSEG = NN / 8;
-            unsigned orseg[NSEG];
-#pragma unroll
-            for (int s = 0; s < NSEG; s++) orseg[s] = 0;
 #pragma unroll
             for (int uv = 0; uv < NN; uv++) {
-                const float rr = fmaf(x[uv], p.fq.k[uv], kMagic);          // rn(q~) in the mantissa
-                const float rf = rr - kMagic;
-                const float d = fmaf(x[uv], p.fq.k[uv], -rf);
-                if (fabsf(d) >= p.fq.thr[uv]) near |= 1ull << uv;           // inside the guard band -> exact recompute
-                const int q = __float_as_int(rr) - kMagicBits;
+                int q;
+                if (uv == 0) {
+                    // DC: the sum of the samples is an exact integer in FP32 and so is the reference's value
+                    // (cos(0) = 1, C(0)^2 = 0.25): q = round_half_away(S / (4 Q00)) in integer arithmetic
+                    const int S = (int)x[0];
+                    const int n = abs(S);
+                    const int D2 = p.dc_den2;                              // 2 * 4 * Q00
+                    const int num = 2 * n + (D2 >> 1);
+                    int qq = (int)((float)num * p.dc_rcp);                  // floor estimate, corrected below
+                    const int rem = num - qq * D2;
+                    qq += (rem >= D2) ? 1 : 0;
+                    qq -= (rem < 0) ? 1 : 0;
+                    q = (S < 0) ? -qq : qq;
+                } else {
+                    const float rr = fmaf(x[uv], p.fq.k[uv], kMagic);      // rn(q~) in the mantissa
+                    const float rf = rr - kMagic;
+                    const float d = fmaf(x[uv], p.fq.k[uv], -rf);
+                    if (fabsf(d) >= p.fq.thr[uv]) near |= 1ull << uv;       // inside the guard band -> exact recompute
+                    q = __float_as_int(rr) - kMagicBits;
+                }
                 const int k = (N == 8) ? kZigzagInv8[uv] : kZigzagInv4[uv];
                 cf[k] = (short)q;
-                orseg[k >> 3] |= (unsigned)q;                               // non-zero detection per zigzag segment
-                orbits |= (unsigned)(q ^ (q >> 31));                        // bits_needed of the widest value (-1 -> 0)
+                r_orseg[r][k >> 3] |= (unsigned)q;                          // non-zero detection per zigzag segment
+                r_orbits[r] |= (unsigned)(q ^ (q >> 31));                   // bits_needed of the widest value (-1 -> 0)
             }
-            bool patched = false;
-            while (near) {
-                const int uv = __ffsll((long long)near) - 1;
-                near &= near - 1;
-                const double *t = tab->fw + uv * NN;
-                double acc = 0.0;
-#pragma unroll
-                for (int ij = 0; ij < NN; ij++) acc = __dadd_rn(acc, __dmul_rn(__ldg(t + ij), (double)(sample(ij) - 128)));
-                const double e = __dmul_rn(acc, tab->cc[uv]);
-                const int q = (int)(short)__double2int_rz(round_half_away(__ddiv_rn(e, p.quant.m[uv])));
-                const int k = tab->izz[uv];
-                if (cf[k] != (short)q) { cf[k] = (short)q; patched = true; }
-            }
-            if (patched) {
-                block_stats_from_staging<NN>(cf, lastnz, prevnz, orbits);
-            } else {
-                int lastseg = -1;
-#pragma unroll
-                for (int s = 0; s < NSEG; s++) if (orseg[s]) lastseg = s;
-                if (lastseg >= 0) {
-                    // last non-zero inside the last non-empty 8-coefficient zigzag segment
-#pragma unroll
-                    for (int j = 0; j < 8; j++) if (cf[lastseg * 8 + j] != 0) lastnz = lastseg * 8 + j + 1;
-                    if (lastnz == NN) {          // rare: the RLE quirk needs the previous non-zero as well
-                        for (int k = 0; k < NN - 1; k++) if (cf[k] != 0) prevnz = k + 1;
+            if (near) {
+                // hand the guard-band coefficients to the CTA-wide queue (filled lanes instead of one lane per warp)
+                const int n = __popcll(near);
+                unsigned slot = atomicAdd(&s_qn, (unsigned)n);
+                while (near) {
+                    const int uv = __ffsll((long long)near) - 1;
+                    near &= near - 1;
+                    if (slot < (unsigned)kQueueCap) {
+                        s_queue[slot++] = ((unsigned)lb << 8) | (unsigned)uv;
+                    } else {                                                // queue full (adversarial input): do it here
+                        const int q = exact_coefficient<N, PF>(ex, gb, uv, p.quant.m[uv]);
+                        const int k = tab->izz[uv];
+                        if (cf[k] != (short)q) { cf[k] = (short)q; s_dirty[lb] = 1; }
                     }
                 }
             }
         } else {
             double x[NN];
 #pragma unroll
-            for (int ij = 0; ij < NN; ij++) x[ij] = __dadd_rn((double)sample(ij), -128.0);
+            for (int ij = 0; ij < NN; ij++) x[ij] = exact_sample<N, PF>(ex, src, byi, bxi, rx, ry, ij);
 #pragma unroll 1
             for (int uv = 0; uv < NN; uv++) {
                 const double e = fdct_coef_exact<NN>(tab->fw + uv * NN, x, tab->cc[uv]);
                 const double qd = round_half_away(__ddiv_rn(e, p.quant.m[uv]));               // Block.cpp:152
-                const int q = (int)(short)__double2int_rz(qd);                                // Block.cpp:205: int16_t(double)
-                cf[tab->izz[uv]] = (short)q;
+                cf[tab->izz[uv]] = (short)__double2int_rz(qd);                                // Block.cpp:205: int16_t(double)
             }
+            s_dirty[lb] = 1;                       // stats come from the staging area
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1b: exact recomputation of the queued guard-band coefficients, one per thread -------------------
+    if (FAST) {
+        const unsigned qn = min(s_qn, (unsigned)kQueueCap);
+        for (unsigned e = threadIdx.x; e < qn; e += kThreads) {
+            const unsigned ent = s_queue[e];
+            const int lb = (int)(ent >> 8), uv = (int)(ent & 0xff);
+            const int q = exact_coefficient<N, PF>(ex, first_blk + lb, uv, p.quant.m[uv]);
+            short *cf = s_coef + (size_t)lb * STRIDE;
+            const int k = tab->izz[uv];
+            if (cf[k] != (short)q) { cf[k] = (short)q; s_dirty[lb] = 1; }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 1c: RLE info, P-frame reconstruction, header unit + coefficient pairs ----------------------------
+    unsigned my_bits = 0;
+#pragma unroll 1
+    for (int r = 0; r < BPL; r++) {
+        const int lb = threadIdx.x * BPL + r;
+        if (lb >= nblk) { if (lb < TB) s_off[lb] = 0; continue; }
+        short *cf = s_coef + (size_t)lb * STRIDE;
+        int lastnz = 0, prevnz = 0;      // (zigzag index + 1) of the last / of the last non-final-position non-zero
+        unsigned orbits = 0;
+        if (s_dirty[lb]) {
             block_stats_from_staging<NN>(cf, lastnz, prevnz, orbits);
+        } else {
+            orbits = r_orbits[r];
+            int lastseg = -1;
+#pragma unroll
+            for (int s = 0; s < NSEG; s++) if (r_orseg[r][s]) lastseg = s;
+            if (lastseg >= 0) {
+                // last non-zero inside the last non-empty 8-coefficient zigzag segment
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (cf[lastseg * 8 + j] != 0) lastnz = lastseg * 8 + j + 1;
+                if (lastnz == NN) {          // rare: the RLE quirk needs the previous non-zero as well
+                    for (int k = 0; k < NN - 1; k++) if (cf[k] != 0) prevnz = k + 1;
+                }
+            }
         }
         // Block.cpp:214-219, 231: data_bits = max(max bits_needed(nz), ffs(data)), data = last non-zero index + 1
         int w = lastnz ? (33 - __clz(orbits)) : 0;
@@ -187,6 +264,10 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
         if (PF) {
             // ImageBase.cpp:303 + Frame.cpp:218-242 + Block.cpp:110-119: decode what was just encoded and rebuild the
             // frame in place: cur = (u8)clamp(double(ref[copy block]) + (IDCT(coef*Q) + 128))
+            const unsigned gb = first_blk + lb;
+            const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
+            const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
+            const int kx = p.copy_coord[2 * mb] + (int)(bxi & 3) * 4, ky = p.copy_coord[2 * mb + 1] + (int)(byi & 3) * 4;
             double X[NN];
 #pragma unroll
             for (int i = 0; i < NN; i++) X[i] = 0.0;
@@ -211,6 +292,19 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
                 }
                 *reinterpret_cast<unsigned *>(p.cur_rw + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N) = outw;
             }
+        }
+        // units, built in place over the staged coefficients (descending, so nothing is overwritten before it is read):
+        // word j holds coefficients (2j, 2j+1) and becomes unit j + 1; unit 0 is the header
+        {
+            unsigned *uw = reinterpret_cast<unsigned *>(cf);
+            const unsigned mask = (1u << w) - 1u;             // w <= 16
+            const int npairs = (len + 1) >> 1;
+            for (int j = npairs - 1; j >= 0; j--) {
+                const unsigned x2 = uw[j];
+                const unsigned lo = x2 & mask, hi = (x2 >> 16) & mask;
+                uw[j + 1] = (2 * j + 1 == len) ? lo : ((lo << w) | hi);
+            }
+            uw[0] = p.use_rle ? ((((unsigned)w & 15u) << w) | (unsigned)len) : ((unsigned)w & 15u);
         }
         s_w[lb] = (unsigned char)w;
         s_len[lb] = (unsigned char)len;
@@ -239,9 +333,22 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
 
     // ---- phase 3: pack ---------------------------------------------------------------------------------------
     if (!p.bits_only) {
-        BlockFieldTile ft;
-        ft.coef = s_coef; ft.w = s_w; ft.len = s_len; ft.off = s_off; ft.stride = STRIDE; ft.nblk = nblk; ft.rle = p.use_rle;
-        tile_write_chunks(ft, st, tile, tile == 0, last_tile, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
+        // chunk -> block map: block b owns every chunk whose first bit lies inside it
+        const unsigned gmod = (unsigned)(G % kChunkBits);
+#pragma unroll
+        for (int r = 0; r < BPL; r++) {
+            const int lb = threadIdx.x * BPL + r;
+            if (lb < nblk) {
+                const unsigned o0 = s_off[lb] + gmod, o1 = s_off[lb + 1] + gmod;     // chunk-grid relative bit range
+                for (unsigned c = (o0 + kChunkBits - 1) / kChunkBits; c * kChunkBits < o1; c++) s_map[c] = (unsigned short)lb;
+            }
+        }
+        if (threadIdx.x == 0) s_map[0] = 0;
+        __syncthreads();
+        UnitTile ut;
+        ut.units = reinterpret_cast<const unsigned *>(s_coef); ut.w = s_w; ut.len = s_len; ut.off = s_off; ut.map = s_map;
+        ut.stride = STRIDE / 2; ut.nblk = nblk; ut.rle = p.use_rle; ut.g_mod = gmod;
+        tile_write_chunks(ut, st, tile, tile == 0, last_tile, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
     }
     if (last_tile && threadIdx.x == 0) {
         p.bit_counter[img] = G + T;
@@ -253,7 +360,9 @@ template <int N, int BPL, bool PF, bool FAST>
 static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t stream) {
     constexpr int TB = kThreads * BPL;
     constexpr int STRIDE = N * N + 2;
-    const size_t smem = (size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 2 * TB;
+    constexpr int MAXCHUNKS = (TB * (4 + 16 + 16 * N * N) + 127) / 128 + 2;
+    const size_t smem = (size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + ((MAXCHUNKS + 1) & ~1) * sizeof(unsigned short) +
+                        kQueueCap * sizeof(unsigned) + 3 * TB;
     static bool configured = false;
     if (!configured) {
         IE_CUDA(cudaFuncSetAttribute(encode_tiles_kernel<N, BPL, PF, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -18,6 +18,8 @@ struct EncodeParams {
     int bits_only;                    // 1: only the bit totals (first pass of a sharded encode)
     QuantParam quant;
     FastQuant fq;                     // fast-path constants + guard-band thresholds (transform_fast.cuh)
+    int dc_den2;                      // 2 * 4 * Q[0][0]: exact integer DC rounding
+    float dc_rcp;                     // 1 / dc_den2
     const BlockTables *tab;
     uint8_t *out;                     // device stream buffer(s), 16-byte aligned
     size_t out_stride;                // bytes between the streams of a batch

@@ -115,35 +115,33 @@ __device__ __forceinline__ unsigned long long tile_lookback(const ScanState &st,
 
 // ---------------------------------------------------------------------------------------------------------
 // Field source for a tile of transform blocks (image blocks, I/P-frame micro blocks).
-//   per block b (tile local): s_w[b] = bit_len, s_len[b] = length field, coefficients int16 in zigzag order
-//   fields: [4: bit_len & 15] [w: length (if rle)] [w * length: coefficients]        (Block.cpp:381-407)
+// A block's bits  [4: bit_len & 15][w: length (if rle)][w * length: coefficients]  (Block.cpp:381-407) are staged in
+// shared memory as 32-bit "units" so that the packer handles ~15 bits per step instead of one coefficient:
+//   unit 0      header: ((w & 15) << w) | length  (4 + w bits)   -- or (w & 15) (4 bits) without RLE
+//   unit 1 + j  coefficient pair (2j, 2j+1): ((c0 & m) << w) | (c1 & m)  (2w bits); an odd trailing coefficient is
+//               stored alone (w bits)
+// `map` gives, for every 128-bit output chunk of the tile, the block that holds the chunk's first bit (no search).
 // ---------------------------------------------------------------------------------------------------------
-struct BlockFieldTile {
-    const short *coef;          // [nblk][stride] (shared memory)
-    const unsigned char *w;     // [nblk]
-    const unsigned char *len;   // [nblk]
-    const unsigned *off;        // [nblk + 1] exclusive bit offsets inside the tile
-    int stride;                 // halfwords
+struct UnitTile {
+    const unsigned *units;       // [nblk][stride] (shared memory)
+    const unsigned char *w;      // [nblk]
+    const unsigned char *len;    // [nblk]   number of coefficients written
+    const unsigned *off;         // [nblk + 1] exclusive bit offsets inside the tile
+    const unsigned short *map;   // [chunks of the tile] -> block
+    int stride;                  // words per block
     int nblk;
     int rle;
+    unsigned g_mod;              // (global bit position of the tile) % 128
 };
 
-__device__ __forceinline__ int upper_block(const unsigned *off, int n, unsigned p) {
-    // largest b in [0, n) with off[b] <= p   (off is non-decreasing, off[0] == 0, p < off[n])
-    int lo = 0, hi = n;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (off[mid] <= p) lo = mid; else hi = mid;
-    }
-    // blocks are never empty (>= 4 bits) so off is strictly increasing
-    return lo;
-}
+static __constant__ unsigned short c_inv2w[17] = {0, 32768, 16384, 10923, 8192, 6554, 5462, 4682, 4096, 3641, 3277, 2979, 2731, 2521, 2341, 2185, 2048};
 
-// Produces the 128-bit chunk whose first bit is tile-local bit `ls` (may be negative: leading bits stay 0).
-__device__ __forceinline__ uint4 gather_chunk(const BlockFieldTile &t, long long ls) {
+// Produces the 128-bit chunk whose first bit is tile-local bit `ls` (negative in the tile's first chunk: leading bits 0).
+__device__ __forceinline__ uint4 gather_chunk(const UnitTile &t, long long ls) {
     unsigned ow0 = 0, ow1 = 0, ow2 = 0, ow3 = 0;
     int widx = 0, nacc = 0;
     unsigned long long acc = 0;
+    const int ci = (int)((ls + (long long)t.g_mod) >> 7);
     if (ls < 0) {
         const int skip = (int)(-ls);
         widx = skip >> 5;
@@ -151,35 +149,33 @@ __device__ __forceinline__ uint4 gather_chunk(const BlockFieldTile &t, long long
         ls = 0;
     }
     const unsigned total = t.off[t.nblk];
-    if ((unsigned long long)ls < (unsigned long long)total) {
-        int b = upper_block(t.off, t.nblk, (unsigned)ls);
+    if ((unsigned)ls < total) {
+        int b = t.map[ci];
         int rel = (int)((unsigned)ls - t.off[b]);
-        const int hsf = t.rle ? 2 : 1;
+        bool first = true;
         while (widx < 4 && b < t.nblk) {
             const int w = t.w[b];
             const int len = t.len[b];
-            const unsigned mask = (w >= 32) ? 0xffffffffu : ((1u << w) - 1u);
-            const short *cf = t.coef + (size_t)b * t.stride;
-            const int nfields = hsf + len;
-            int f, fo;
-            if (rel < 4) { f = 0; fo = rel; }
-            else if (t.rle && rel < 4 + w) { f = 1; fo = rel - 4; }
-            else {
-                const int r2 = rel - (t.rle ? 4 + w : 4);
-                const int k = (w > 0) ? (r2 / w) : 0;
-                f = hsf + k;
-                fo = r2 - k * w;
+            const int hb = t.rle ? 4 + w : 4;
+            const int nun = 1 + ((len + 1) >> 1);
+            const unsigned *u = t.units + b * t.stride;
+            int i = 0, fo = 0;
+            if (first) {
+                first = false;
+                if (rel < hb) { fo = rel; }
+                else {
+                    const int r2 = rel - hb;
+                    const int j = (r2 * (int)c_inv2w[w]) >> 16;     // r2 / (2w), exact for r2 < 2048
+                    i = 1 + j;
+                    fo = r2 - j * 2 * w;
+                }
             }
-            rel = 0;
-            for (; f < nfields && widx < 4; f++) {
-                unsigned v;
-                int fw;
-                if (f == 0) { v = (unsigned)w & 15u; fw = 4; }
-                else if (f < hsf) { v = (unsigned)len & mask; fw = w; }
-                else { v = (unsigned)(int)cf[f - hsf] & mask; fw = w; }
-                if (fo) { fw -= fo; v &= (1u << fw) - 1u; fo = 0; }
-                acc = (acc << fw) | v;
-                nacc += fw;
+            for (; i < nun && widx < 4; i++) {
+                unsigned v = u[i];
+                int uw = (i == 0) ? hb : ((i == nun - 1 && (len & 1)) ? w : 2 * w);
+                if (fo) { uw -= fo; v &= (uw >= 32) ? 0xffffffffu : ((1u << uw) - 1u); fo = 0; }
+                acc = (acc << uw) | v;
+                nacc += uw;
                 if (nacc >= 32) {
                     const unsigned word = (unsigned)(acc >> (nacc - 32));
                     if (widx == 0) ow0 = word; else if (widx == 1) ow1 = word; else if (widx == 2) ow2 = word; else ow3 = word;
