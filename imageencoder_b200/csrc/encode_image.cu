@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
     extern __shared__ __align__(16) unsigned char smem[];
     short *s_coef = reinterpret_cast<short *>(smem);
     unsigned *s_off = reinterpret_cast<unsigned *>(smem + (size_t)TB * STRIDE * sizeof(short));
-    unsigned short *s_map = reinterpret_cast<unsigned short *>(s_off + TB + 1);
-    unsigned *s_queue = reinterpret_cast<unsigned *>(s_map + ((MAXCHUNKS + 1) & ~1));
+    uint4 *s_out = reinterpret_cast<uint4 *>(smem + (((size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 15) & ~(size_t)15));
+    unsigned *s_queue = reinterpret_cast<unsigned *>(s_out + MAXCHUNKS);
     unsigned char *s_w = reinterpret_cast<unsigned char *>(s_queue + kQueueCap);
     unsigned char *s_len = s_w + TB;
     unsigned char *s_dirty = s_len + TB;
@@ -293,19 +293,6 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
                 *reinterpret_cast<unsigned *>(p.cur_rw + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N) = outw;
             }
         }
-        // units, built in place over the staged coefficients (descending, so nothing is overwritten before it is read):
-        // word j holds coefficients (2j, 2j+1) and becomes unit j + 1; unit 0 is the header
-        {
-            unsigned *uw = reinterpret_cast<unsigned *>(cf);
-            const unsigned mask = (1u << w) - 1u;             // w <= 16
-            const int npairs = (len + 1) >> 1;
-            for (int j = npairs - 1; j >= 0; j--) {
-                const unsigned x2 = uw[j];
-                const unsigned lo = x2 & mask, hi = (x2 >> 16) & mask;
-                uw[j + 1] = (2 * j + 1 == len) ? lo : ((lo << w) | hi);
-            }
-            uw[0] = p.use_rle ? ((((unsigned)w & 15u) << w) | (unsigned)len) : ((unsigned)w & 15u);
-        }
         s_w[lb] = (unsigned char)w;
         s_len[lb] = (unsigned char)len;
         const unsigned bits = 4u + (p.use_rle ? w : 0) + (unsigned)len * (unsigned)w;
@@ -332,23 +319,58 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
     const bool last_tile = (tile == ntiles - 1);
 
     // ---- phase 3: pack ---------------------------------------------------------------------------------------
+    // Block-centric: every lane writes its block's fields MSB-first into a shared-memory image of the tile's part of the
+    // stream (already on the 128-bit chunk grid of the global stream), whole words with plain stores, the <= 2 words it
+    // shares with its neighbours with shared-memory atomicOr; then the chunks go out with coalesced 128-bit stores.
     if (!p.bits_only) {
-        // chunk -> block map: block b owns every chunk whose first bit lies inside it
         const unsigned gmod = (unsigned)(G % kChunkBits);
-#pragma unroll
+        const unsigned nchunks = (gmod + T + kChunkBits - 1) / kChunkBits;
+        for (unsigned c = threadIdx.x; c < nchunks; c += kThreads) s_out[c] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        unsigned *s_outw = reinterpret_cast<unsigned *>(s_out);
+#pragma unroll 1
         for (int r = 0; r < BPL; r++) {
             const int lb = threadIdx.x * BPL + r;
-            if (lb < nblk) {
-                const unsigned o0 = s_off[lb] + gmod, o1 = s_off[lb + 1] + gmod;     // chunk-grid relative bit range
-                for (unsigned c = (o0 + kChunkBits - 1) / kChunkBits; c * kChunkBits < o1; c++) s_map[c] = (unsigned short)lb;
+            if (lb >= nblk) break;
+            const int w = s_w[lb], len = s_len[lb];
+            const unsigned pos = s_off[lb] + gmod;
+            const unsigned bo = pos & 31u;
+            unsigned *ow = s_outw + (pos >> 5);
+            const unsigned *cw = reinterpret_cast<const unsigned *>(s_coef + (size_t)lb * STRIDE);
+            const unsigned mask = (1u << w) - 1u;                                             // w <= 16
+            // header: bit_len (low 4 bits survive, Block.cpp:381) and, with RLE, the length field (Block.cpp:393)
+            unsigned long long acc = p.use_rle ? ((((unsigned long long)w & 15ull) << w) | (unsigned long long)len) : ((unsigned long long)w & 15ull);
+            int nacc = (int)bo + 4 + (p.use_rle ? w : 0);
+            bool shared_word = (bo != 0);       // the first word also holds bits of the previous block(s)
+            // big-endian byte order inside the words of the image (bit 0 of the stream = MSB of byte 0)
+#define IE_EMIT_WORD()                                                                     \
+            do {                                                                               \
+                const unsigned word_ = __byte_perm((unsigned)(acc >> (nacc - 32)), 0, 0x0123); \
+                if (shared_word) { atomicOr(ow, word_); shared_word = false; } else { *ow = word_; } \
+                ow++;                                                                          \
+                nacc -= 32;                                                                    \
+            } while (0)
+            if (nacc >= 32) IE_EMIT_WORD();
+            const int nfull = len >> 1;
+            for (int j = 0; j < nfull; j++) {                                                  // coefficient pairs (2j, 2j+1)
+                const unsigned x2 = cw[j];
+                const unsigned v = ((x2 & mask) << w) | ((x2 >> 16) & mask);
+                acc = (acc << (2 * w)) | v;
+                nacc += 2 * w;
+                if (nacc >= 32) IE_EMIT_WORD();
             }
+            if (len & 1) {
+                acc = (acc << w) | (cw[nfull] & mask);
+                nacc += w;
+                if (nacc >= 32) IE_EMIT_WORD();
+            }
+#undef IE_EMIT_WORD
+            if (nacc > 0) atomicOr(ow, __byte_perm((unsigned)(acc << (32 - nacc)), 0, 0x0123));   // tail shared with the next block
         }
-        if (threadIdx.x == 0) s_map[0] = 0;
         __syncthreads();
-        UnitTile ut;
-        ut.units = reinterpret_cast<const unsigned *>(s_coef); ut.w = s_w; ut.len = s_len; ut.off = s_off; ut.map = s_map;
-        ut.stride = STRIDE / 2; ut.nblk = nblk; ut.rle = p.use_rle; ut.g_mod = gmod;
-        tile_write_chunks(ut, st, tile, tile == 0, last_tile, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
+        SmemStreamTile stt;
+        stt.buf = s_out; stt.g_mod = gmod;
+        tile_write_chunks(stt, st, tile, tile == 0, last_tile, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
     }
     if (last_tile && threadIdx.x == 0) {
         p.bit_counter[img] = G + T;
@@ -361,7 +383,7 @@ static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t strea
     constexpr int TB = kThreads * BPL;
     constexpr int STRIDE = N * N + 2;
     constexpr int MAXCHUNKS = (TB * (4 + 16 + 16 * N * N) + 127) / 128 + 2;
-    const size_t smem = (size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + ((MAXCHUNKS + 1) & ~1) * sizeof(unsigned short) +
+    const size_t smem = (((size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 15) & ~(size_t)15) + (size_t)MAXCHUNKS * 16 +
                         kQueueCap * sizeof(unsigned) + 3 * TB;
     static bool configured = false;
     if (!configured) {

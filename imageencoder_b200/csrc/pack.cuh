@@ -194,6 +194,15 @@ __device__ __forceinline__ uint4 gather_chunk(const UnitTile &t, long long ls) {
     return make_uint4(__byte_perm(ow0, 0, 0x0123), __byte_perm(ow1, 0, 0x0123), __byte_perm(ow2, 0, 0x0123), __byte_perm(ow3, 0, 0x0123));
 }
 
+// Tile whose bits were already assembled in shared memory on the chunk grid of the global stream (block-centric packer).
+struct SmemStreamTile {
+    const uint4 *buf;            // chunk 0 = the chunk that holds the tile's first bit
+    unsigned g_mod;              // (global bit position of the tile) % 128
+};
+__device__ __forceinline__ uint4 gather_chunk(const SmemStreamTile &t, long long ls) {
+    return t.buf[(int)((ls + (long long)t.g_mod) >> 7)];
+}
+
 // Writes the tile's bits [G, G+T) into `out`.  first_tile/last_tile refer to the launch.  See the contract above.
 template <class Tile>
 __device__ __forceinline__ void tile_write_chunks(const Tile &t, const ScanState &st, unsigned tile, bool first_tile, bool last_tile,
