@@ -314,26 +314,27 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
     if (threadIdx.x == kThreads - 1) s_off[TB] = T;
     unsigned long long base = 0;
     if (tile == 0) base = p.bit_counter[img];
-    const unsigned long long G = tile_lookback(st, tile, (unsigned long long)T + base, &s_bcast) + (tile == 0 ? base : 0ull);
-    // tile 0 published base + T as its inclusive prefix, so every G is an absolute stream position.
+    // publish this tile's bit total right away; the prefix is only needed for the copy-out, after the local packing
+    if (threadIdx.x == 0) tile_publish_aggregate(st, tile, (unsigned long long)T + base);
     const bool last_tile = (tile == ntiles - 1);
+    unsigned long long G = 0;
 
     // ---- phase 3: pack ---------------------------------------------------------------------------------------
-    // Block-centric: every lane writes its block's fields MSB-first into a shared-memory image of the tile's part of the
-    // stream (already on the 128-bit chunk grid of the global stream), whole words with plain stores, the <= 2 words it
-    // shares with its neighbours with shared-memory atomicOr; then the chunks go out with coalesced 128-bit stores.
+    // Block-centric: every lane writes its block's fields MSB-first into a shared-memory image of the tile's bits (tile
+    // local alignment), whole words with plain stores, the <= 2 words it shares with its neighbours with shared-memory
+    // atomicOr.  Then the tile's stream offset is resolved (look-back) and the image goes out re-aligned to the chunk
+    // grid of the global stream with coalesced 128-bit stores.
     if (!p.bits_only) {
-        const unsigned gmod = (unsigned)(G % kChunkBits);
-        const unsigned nchunks = (gmod + T + kChunkBits - 1) / kChunkBits;
-        for (unsigned c = threadIdx.x; c < nchunks; c += kThreads) s_out[c] = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
         unsigned *s_outw = reinterpret_cast<unsigned *>(s_out);
+        const unsigned nwords = (T + 31) / 32;
+        for (unsigned c = threadIdx.x; c < (nwords + 3) / 4; c += kThreads) s_out[c] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
 #pragma unroll 1
         for (int r = 0; r < BPL; r++) {
             const int lb = threadIdx.x * BPL + r;
             if (lb >= nblk) break;
             const int w = s_w[lb], len = s_len[lb];
-            const unsigned pos = s_off[lb] + gmod;
+            const unsigned pos = s_off[lb];
             const unsigned bo = pos & 31u;
             unsigned *ow = s_outw + (pos >> 5);
             const unsigned *cw = reinterpret_cast<const unsigned *>(s_coef + (size_t)lb * STRIDE);
@@ -342,10 +343,9 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
             unsigned long long acc = p.use_rle ? ((((unsigned long long)w & 15ull) << w) | (unsigned long long)len) : ((unsigned long long)w & 15ull);
             int nacc = (int)bo + 4 + (p.use_rle ? w : 0);
             bool shared_word = (bo != 0);       // the first word also holds bits of the previous block(s)
-            // big-endian byte order inside the words of the image (bit 0 of the stream = MSB of byte 0)
 #define IE_EMIT_WORD()                                                                     \
             do {                                                                               \
-                const unsigned word_ = __byte_perm((unsigned)(acc >> (nacc - 32)), 0, 0x0123); \
+                const unsigned word_ = (unsigned)(acc >> (nacc - 32));                         \
                 if (shared_word) { atomicOr(ow, word_); shared_word = false; } else { *ow = word_; } \
                 ow++;                                                                          \
                 nacc -= 32;                                                                    \
@@ -365,12 +365,14 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
                 if (nacc >= 32) IE_EMIT_WORD();
             }
 #undef IE_EMIT_WORD
-            if (nacc > 0) atomicOr(ow, __byte_perm((unsigned)(acc << (32 - nacc)), 0, 0x0123));   // tail shared with the next block
+            if (nacc > 0) atomicOr(ow, (unsigned)(acc << (32 - nacc)));                        // tail shared with the next block
         }
-        __syncthreads();
+        G = tile_resolve_prefix(st, tile, (unsigned long long)T, &s_bcast) + (tile == 0 ? base : 0ull);   // syncs the CTA
         SmemStreamTile stt;
-        stt.buf = s_out; stt.g_mod = gmod;
+        stt.words = s_outw; stt.nwords = nwords;
         tile_write_chunks(stt, st, tile, tile == 0, last_tile, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
+    } else {
+        G = tile_resolve_prefix(st, tile, (unsigned long long)T, &s_bcast) + (tile == 0 ? base : 0ull);
     }
     if (last_tile && threadIdx.x == 0) {
         p.bit_counter[img] = G + T;

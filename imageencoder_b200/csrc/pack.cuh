@@ -70,40 +70,56 @@ __device__ __forceinline__ unsigned cta_exclusive_scan(unsigned v, unsigned *s_w
     return s_warp[wid] + inc - v;
 }
 
-// Decoupled look-back (single-pass chained scan).  Called by every thread of the CTA; returns the exclusive prefix
-// (sum of the totals of tiles 0..tile-1).  Tiles get their ids from a ticket so every predecessor is already running.
-__device__ __forceinline__ unsigned long long tile_lookback(const ScanState &st, unsigned tile, unsigned long long total,
-                                                            unsigned long long *s_bcast) {
+// Decoupled look-back (single-pass chained scan), split in two so that a tile can publish its aggregate as soon as it
+// knows it and resolve its prefix only when it needs it (after it has packed its bits locally):
+//   tile_publish_aggregate : one thread; tile 0 publishes its inclusive prefix (base + total) directly.
+//   tile_resolve_prefix    : warp 0 sums predecessor aggregates back to the nearest published prefix, 8 states per lane
+//                            per round (256 predecessors in flight: one L2 round trip covers a whole wave of CTAs), then
+//                            publishes this tile's inclusive prefix.  Returns the exclusive prefix to every thread.
+// Tiles get their ids from a ticket, so every predecessor is already running (forward progress).
+__device__ __forceinline__ void tile_publish_aggregate(const ScanState &st, unsigned tile, unsigned long long total_incl_base) {
+    st_relaxed_u64(&st.tile_state[tile], make_state(st.epoch, tile == 0 ? kFlagPrefix : kFlagAggregate, total_incl_base));
+}
+
+__device__ __forceinline__ unsigned long long tile_resolve_prefix(const ScanState &st, unsigned tile, unsigned long long total,
+                                                                  unsigned long long *s_bcast) {
+    constexpr int R = 8;                                   // states per lane per round
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         unsigned long long excl = 0;
-        if (tile == 0) {
-            if (lane == 0) st_relaxed_u64(&st.tile_state[0], make_state(st.epoch, kFlagPrefix, total));
-        } else {
-            if (lane == 0) st_relaxed_u64(&st.tile_state[tile], make_state(st.epoch, kFlagAggregate, total));
-            int base = (int)tile - 1;
+        if (tile != 0) {
             const unsigned long long ep = (unsigned long long)(st.epoch & 0xFFFFFFu);
-            while (true) {
-                const int idx = base - lane;
-                unsigned long long s = 0;
-                if (idx >= 0) {
-                    // every predecessor already runs (ticket order), so this terminates
-                    do {
-                        s = ld_relaxed_u64(&st.tile_state[idx]);
-                    } while ((s >> 40) != ep || ((s >> kValueBits) & 3ull) == 0ull);
-                }
-                __syncwarp();
-                const bool is_prefix = (idx >= 0) && (((s >> kValueBits) & 3ull) == kFlagPrefix);
-                const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-                // lanes from the nearest predecessor (lane 0) up to and including the first published prefix contribute
-                const int first = pm ? (__ffs(pm) - 1) : 31;
-                unsigned long long c = (idx >= 0 && lane <= first) ? (s & kValueMask) : 0ull;
+            int base = (int)tile - 1;
+            bool done = false;
+            while (!done) {
+                unsigned long long sv[R];
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
-                c = __shfl_sync(0xffffffffu, c, 0);
-                excl += c;
-                if (pm || base - 32 < 0) break;
-                base -= 32;
+                for (int k = 0; k < R; k++) {
+                    const int idx = base - 32 * k - lane;
+                    sv[k] = (idx >= 0) ? ld_relaxed_u64(&st.tile_state[idx]) : 0ull;
+                }
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    if (done) break;
+                    const int idx = base - 32 * k - lane;
+                    unsigned long long s = sv[k];
+                    if (idx >= 0) {
+                        // every predecessor already runs (ticket order), so this terminates
+                        while ((s >> 40) != ep || ((s >> kValueBits) & 3ull) == 0ull) s = ld_relaxed_u64(&st.tile_state[idx]);
+                    }
+                    __syncwarp();
+                    const bool is_prefix = (idx >= 0) && (((s >> kValueBits) & 3ull) == kFlagPrefix);
+                    const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+                    // lanes from the nearest predecessor (lane 0) up to and including the first published prefix contribute
+                    const int first = pm ? (__ffs(pm) - 1) : 31;
+                    unsigned long long c = (idx >= 0 && lane <= first) ? (s & kValueMask) : 0ull;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+                    c = __shfl_sync(0xffffffffu, c, 0);
+                    excl += c;
+                    if (pm || base - 32 * (k + 1) < 0) done = true;
+                }
+                base -= 32 * R;
             }
             if (lane == 0) st_relaxed_u64(&st.tile_state[tile], make_state(st.epoch, kFlagPrefix, excl + total));
         }
@@ -111,6 +127,13 @@ __device__ __forceinline__ unsigned long long tile_lookback(const ScanState &st,
     }
     __syncthreads();
     return *s_bcast;
+}
+
+// Both steps back to back (kernels that have nothing to overlap with the wait).
+__device__ __forceinline__ unsigned long long tile_lookback(const ScanState &st, unsigned tile, unsigned long long total,
+                                                            unsigned long long *s_bcast) {
+    if (threadIdx.x == 0) tile_publish_aggregate(st, tile, total);
+    return tile_resolve_prefix(st, tile, total, s_bcast);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -194,13 +217,28 @@ __device__ __forceinline__ uint4 gather_chunk(const UnitTile &t, long long ls) {
     return make_uint4(__byte_perm(ow0, 0, 0x0123), __byte_perm(ow1, 0, 0x0123), __byte_perm(ow2, 0, 0x0123), __byte_perm(ow3, 0, 0x0123));
 }
 
-// Tile whose bits were already assembled in shared memory on the chunk grid of the global stream (block-centric packer).
+// Tile whose bits were already assembled in shared memory, starting at bit 0 of `words` (32 stream bits per word, MSB
+// first, zero beyond the tile's last bit).  The copy-out re-aligns them to the chunk grid of the global stream.
 struct SmemStreamTile {
-    const uint4 *buf;            // chunk 0 = the chunk that holds the tile's first bit
-    unsigned g_mod;              // (global bit position of the tile) % 128
+    const unsigned *words;
+    unsigned nwords;             // words that hold tile bits
 };
 __device__ __forceinline__ uint4 gather_chunk(const SmemStreamTile &t, long long ls) {
-    return t.buf[(int)((ls + (long long)t.g_mod) >> 7)];
+    // chunk bits [ls, ls + 128) of the tile-local image; ls may be negative (leading bits of the tile's first chunk)
+    const long long wi = ls >> 5;                          // floor
+    const unsigned sh = (unsigned)(ls & 31);
+    unsigned w[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const long long i = wi + k;
+        w[k] = (i >= 0 && i < (long long)t.nwords) ? t.words[i] : 0u;
+    }
+    uint4 o;
+    o.x = __byte_perm(__funnelshift_l(w[1], w[0], sh), 0, 0x0123);
+    o.y = __byte_perm(__funnelshift_l(w[2], w[1], sh), 0, 0x0123);
+    o.z = __byte_perm(__funnelshift_l(w[3], w[2], sh), 0, 0x0123);
+    o.w = __byte_perm(__funnelshift_l(w[4], w[3], sh), 0, 0x0123);
+    return o;
 }
 
 // Writes the tile's bits [G, G+T) into `out`.  first_tile/last_tile refer to the launch.  See the contract above.
