@@ -86,13 +86,15 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
     unsigned *s_off = reinterpret_cast<unsigned *>(smem + (size_t)TB * STRIDE * sizeof(short));
     uint4 *s_out = reinterpret_cast<uint4 *>(smem + (((size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 15) & ~(size_t)15));
     unsigned *s_queue = reinterpret_cast<unsigned *>(s_out + MAXCHUNKS);
-    unsigned char *s_w = reinterpret_cast<unsigned char *>(s_queue + kQueueCap);
+    unsigned char *s_w = reinterpret_cast<unsigned char *>(s_queue + kQueueCap + TB + (kQueueCap + TB) / 2);
     unsigned char *s_len = s_w + TB;
     unsigned char *s_dirty = s_len + TB;
+    unsigned *s_stats = reinterpret_cast<unsigned *>(s_queue + kQueueCap);          // [TB] packed RLE info of patched blocks
+    unsigned short *s_dlist = reinterpret_cast<unsigned short *>(s_stats + TB);      // [kQueueCap + TB] patched blocks (duplicates allowed)
     __shared__ unsigned s_warp[kThreads / 32 + 1];
     __shared__ unsigned long long s_bcast;
     __shared__ unsigned s_tile;
-    __shared__ unsigned s_qn;
+    __shared__ unsigned s_qn, s_nd;
 
     const unsigned img = blockIdx.y;
     ScanState st = p.scan;
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
     st.bnd += (size_t)img * p.tiles_per_image;
     st.ticket += img;
 
-    if (threadIdx.x == 0) { s_tile = atomicAdd(st.ticket, 1u); s_qn = 0; }
+    if (threadIdx.x == 0) { s_tile = atomicAdd(st.ticket, 1u); s_qn = 0; s_nd = 0; }
     __syncthreads();
     const unsigned tile = s_tile;
     const unsigned ntiles = p.tiles_per_image;
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
                     } else {                                                // queue full (adversarial input): do it here
                         const int q = exact_coefficient<N, PF>(ex, gb, uv, p.quant.m[uv]);
                         const int k = tab->izz[uv];
-                        if (cf[k] != (short)q) { cf[k] = (short)q; s_dirty[lb] = 1; }
+                        if (cf[k] != (short)q) { cf[k] = (short)q; if (!s_dirty[lb]) { s_dirty[lb] = 1; s_dlist[atomicAdd(&s_nd, 1u)] = (unsigned short)lb; } }
                     }
                 }
             }
@@ -207,7 +209,6 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
                 const double qd = round_half_away(__ddiv_rn(e, p.quant.m[uv]));               // Block.cpp:152
                 cf[tab->izz[uv]] = (short)__double2int_rz(qd);                                // Block.cpp:205: int16_t(double)
             }
-            s_dirty[lb] = 1;                       // stats come from the staging area
         }
     }
     __syncthreads();
@@ -215,15 +216,31 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
     // ---- phase 1b: exact recomputation of the queued guard-band coefficients, one per thread -------------------
     if (FAST) {
         const unsigned qn = min(s_qn, (unsigned)kQueueCap);
-        for (unsigned e = threadIdx.x; e < qn; e += kThreads) {
-            const unsigned ent = s_queue[e];
-            const int lb = (int)(ent >> 8), uv = (int)(ent & 0xff);
-            const int q = exact_coefficient<N, PF>(ex, first_blk + lb, uv, p.quant.m[uv]);
-            short *cf = s_coef + (size_t)lb * STRIDE;
-            const int k = tab->izz[uv];
-            if (cf[k] != (short)q) { cf[k] = (short)q; s_dirty[lb] = 1; }
+        if (qn) {                                                              // uniform
+            for (unsigned e = threadIdx.x; e < qn; e += kThreads) {
+                const unsigned ent = s_queue[e];
+                const int lb = (int)(ent >> 8), uv = (int)(ent & 0xff);
+                const int q = exact_coefficient<N, PF>(ex, first_blk + lb, uv, p.quant.m[uv]);
+                short *cf = s_coef + (size_t)lb * STRIDE;
+                const int k = tab->izz[uv];
+                if (cf[k] != (short)q) {
+                    cf[k] = (short)q;
+                    // first patch of this block: put it on the list of blocks whose RLE info must be recomputed.
+                    // (two threads patching the same block may both list it; recomputing twice is harmless)
+                    if (!s_dirty[lb]) { s_dirty[lb] = 1; s_dlist[atomicAdd(&s_nd, 1u)] = (unsigned short)lb; }
+                }
+            }
+            __syncthreads();
+            const unsigned nd = s_nd;
+            for (unsigned e = threadIdx.x; e < nd; e += kThreads) {
+                const int lb = s_dlist[e];
+                int lastnz, prevnz;
+                unsigned orbits;
+                block_stats_from_staging<NN>(s_coef + (size_t)lb * STRIDE, lastnz, prevnz, orbits);
+                s_stats[lb] = (unsigned)lastnz | ((unsigned)prevnz << 8) | (orbits << 16);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     // ---- phase 1c: RLE info, P-frame reconstruction, header unit + coefficient pairs ----------------------------
@@ -235,8 +252,11 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
         short *cf = s_coef + (size_t)lb * STRIDE;
         int lastnz = 0, prevnz = 0;      // (zigzag index + 1) of the last / of the last non-final-position non-zero
         unsigned orbits = 0;
-        if (s_dirty[lb]) {
+        if (!FAST) {
             block_stats_from_staging<NN>(cf, lastnz, prevnz, orbits);
+        } else if (s_dirty[lb]) {
+            const unsigned sp = s_stats[lb];
+            lastnz = (int)(sp & 0xff); prevnz = (int)((sp >> 8) & 0xff); orbits = sp >> 16;
         } else {
             orbits = r_orbits[r];
             int lastseg = -1;
@@ -386,7 +406,7 @@ static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t strea
     constexpr int STRIDE = N * N + 2;
     constexpr int MAXCHUNKS = (TB * (4 + 16 + 16 * N * N) + 127) / 128 + 2;
     const size_t smem = (((size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 15) & ~(size_t)15) + (size_t)MAXCHUNKS * 16 +
-                        kQueueCap * sizeof(unsigned) + 3 * TB;
+                        (kQueueCap + TB + (kQueueCap + TB) / 2) * sizeof(unsigned) + 3 * TB;
     static bool configured = false;
     if (!configured) {
         IE_CUDA(cudaFuncSetAttribute(encode_tiles_kernel<N, BPL, PF, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -149,8 +149,7 @@ __global__ void __launch_bounds__(kThreads) huff_encode_kernel(const HuffEncodeP
     __shared__ unsigned s_tile;
     ScanState st = p.scan;
     if (threadIdx.x == 0) s_tile = atomicAdd(st.ticket, 1u);
-    s_word[threadIdx.x] = p.codes->word[threadIdx.x];
-    s_len[threadIdx.x] = p.codes->len[threadIdx.x];
+    for (int i = threadIdx.x; i < 256; i += kThreads) { s_word[i] = p.codes->word[i]; s_len[i] = p.codes->len[i]; }
     __syncthreads();
     const unsigned tile = s_tile;
     const size_t base_byte = (size_t)tile * kHuffTileBytes;

@@ -16,7 +16,7 @@
 
 namespace ie {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;            // small CTAs: several tiles per SM overlap each other's barriers and look-back waits
 constexpr int kChunkBits = 128;
 
 // status word of the decoupled look-back: [epoch:24][flag:2][value:38]
@@ -24,10 +24,12 @@ constexpr unsigned long long kFlagAggregate = 1ull, kFlagPrefix = 2ull;
 constexpr int kValueBits = 38;
 constexpr unsigned long long kValueMask = (1ull << kValueBits) - 1;
 
+// Hand-off record for the 128-bit chunk two neighbouring tiles share: per 32-bit word one 64-bit cell that both tiles
+// atomicAdd ((1 << 32) | their bits) to -- the bits of the two tiles are disjoint, so add == or; whoever finds the other's
+// arrival mark already there owns the complete word, stores it and clears the cell.  Data and arrival travel in the same
+// atomic, so no fence is needed.
 struct TileBoundary {
-    unsigned w[4];
-    unsigned count;
-    unsigned pad[3];
+    unsigned long long w[4];
 };
 
 struct ScanState {
@@ -263,18 +265,19 @@ __device__ __forceinline__ void tile_write_chunks(const Tile &t, const ScanState
             v.x |= o.x; v.y |= o.y; v.z |= o.z; v.w |= o.w;
         } else if (is_head || is_tail) {
             // chunk shared with the neighbouring tile of this launch (every non-last tile has >= 128 bits, so a chunk is
-            // never head and tail at once): both sides OR their bits into the hand-off record, the second one stores.
+            // never head and tail at once)
             TileBoundary *bd = &st.bnd[is_head ? tile - 1 : tile];
-            if (v.x) atomicOr(&bd->w[0], v.x);
-            if (v.y) atomicOr(&bd->w[1], v.y);
-            if (v.z) atomicOr(&bd->w[2], v.z);
-            if (v.w) atomicOr(&bd->w[3], v.w);
-            __threadfence();
-            if (atomicAdd(&bd->count, 1u) != 1u) continue;      // first arriver: the neighbour writes the chunk
-            __threadfence();
-            v.x = atomicExch(&bd->w[0], 0u); v.y = atomicExch(&bd->w[1], 0u);
-            v.z = atomicExch(&bd->w[2], 0u); v.w = atomicExch(&bd->w[3], 0u);
-            atomicExch(&bd->count, 0u);                          // record is clean again for the next launch
+            unsigned *dw = reinterpret_cast<unsigned *>(dst);
+            const unsigned mine[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const unsigned long long old = atomicAdd(&bd->w[i], (1ull << 32) | (unsigned long long)mine[i]);
+                if ((old >> 32) == 1ull) {                       // second arriver for this word: it is complete
+                    dw[i] = (unsigned)old | mine[i];
+                    atomicExch(&bd->w[i], 0ull);                 // clean for the next launch
+                }
+            }
+            continue;
         }
         *dst = v;
     }
