@@ -53,9 +53,10 @@ __device__ __forceinline__ double exact_sample(const ExactCtx &p, const uint8_t 
 }
 
 // One coefficient of one block in the reference's exact order and precision (algo.cpp:309-331, Block.cpp:152).
+// The 2*N*N-operation chain is inherently sequential (every partial sum is rounded), so everything that does not depend
+// on the running sum -- pixel rows, table entries, conversions -- is fetched up front, 16 terms at a time.
 template <int N, bool PF>
 __device__ __noinline__ int exact_coefficient(const ExactCtx p, unsigned gb, int uv, double m_uv) {
-    const uint8_t *src = p.src;
     constexpr int NN = N * N;
     const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
     int rx = 0, ry = 0;
@@ -65,14 +66,34 @@ __device__ __noinline__ int exact_coefficient(const ExactCtx p, unsigned gb, int
         ry = p.res_coord[2 * mb + 1] + (int)(byi & 3) * 4;
     }
     const double *t = p.tab->fw + uv * NN;
+    const uint8_t *blk = p.src + (size_t)(byi * N) * p.pitch + (size_t)bxi * N;
     double acc = 0.0;
-#pragma unroll 8
-    for (int ij = 0; ij < NN; ij++) acc = __dadd_rn(acc, __dmul_rn(__ldg(t + ij), exact_sample<N, PF>(p, src, byi, bxi, rx, ry, ij)));
+    constexpr int ROWS_PER_BATCH = 16 / N;                  // 16 terms per batch
+#pragma unroll 1
+    for (int y0 = 0; y0 < N; y0 += ROWS_PER_BATCH) {
+        double xs[16], ts[16];
+#pragma unroll
+        for (int yy = 0; yy < ROWS_PER_BATCH; yy++) {
+            const int y = y0 + yy;
+            unsigned lo, hi = 0;
+            if (N == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2 *>(blk + (size_t)y * p.pitch)); lo = v.x; hi = v.y; }
+            else lo = *reinterpret_cast<const unsigned *>(blk + (size_t)y * p.pitch);
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                int v = (int)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xffu);
+                if (PF) v -= (int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + k);               // Block.cpp:262
+                xs[yy * N + k] = (double)(v - 128);                                                  // Block.cpp:141-143 (exact)
+                ts[yy * N + k] = __ldg(t + y * N + k);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc = __dadd_rn(acc, __dmul_rn(ts[i], xs[i]));                 // algo.cpp:318-320
+    }
     const double e = __dmul_rn(acc, p.tab->cc[uv]);
     return (int)(short)__double2int_rz(round_half_away(__ddiv_rn(e, m_uv)));
 }
 
-constexpr int kQueueCap = 1024;       // guard-band fallback entries per tile handled by the CTA-wide queue
+constexpr int kQueueCap = 512;        // guard-band fallback entries per tile handled by the CTA-wide queue
 
 template <int N, int BPL, bool PF, bool FAST>
 __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_tiles_kernel(const EncodeParams p) {
