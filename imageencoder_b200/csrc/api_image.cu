@@ -216,7 +216,8 @@ int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size
     make_quant(p.quant, h.quant, N);
     p.tab = (N == 8) ? s->dev->d_t8 : s->dev->d_t4;
     p.out = d_out; p.out_stride = 0; p.pitch = W; p.err = s->d_err;
-    IE_TRY(launch_parse_blocks(p, 1, stream));
+    IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, parse_scratch_bytes(enc_bytes, N)));
+    IE_TRY(launch_parallel_parse(p, enc_bytes * 8, s->d_parse, stream));
     return launch_decode_blocks(p, 1, stream);
 }
 
@@ -267,7 +268,7 @@ int ie_session_create(ie_session **out, int kind, uint32_t W, uint32_t H, uint32
 void ie_session_destroy(ie_session *s) {
     if (!s) return;
     cudaFree(s->d_tile_state); cudaFree(s->d_bnd); cudaFree(s->d_ticket); cudaFree(s->d_counter); cudaFree(s->d_err);
-    cudaFree(s->d_block_off); cudaFree(s->d_scratch); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_tmp);
+    cudaFree(s->d_block_off); cudaFree(s->d_parse); cudaFree(s->d_scratch); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_tmp);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;

@@ -162,6 +162,8 @@ __global__ void fill_uv_kernel(uint8_t *yuv, size_t ysz, size_t fsz, unsigned fr
     }
 }
 
+constexpr unsigned long long kGroupSpanSlack = 1ull << 18;   // the parser rounds spans up to whole groups
+
 static unsigned host_bits_needed(int v) {                    // utils.hpp:226-243
     const short value = (short)v;
     unsigned bits = 1;
@@ -336,14 +338,18 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
     p.enc = d_enc; p.enc_bits = d_consts; p.start_bit = d_consts + 1; p.block_off = s->d_block_off; p.nblocks = nblocks;
     p.bx = W / 4; p.N = 4; p.use_rle = h.use_rle; make_quant(p.quant, h.quant, 4); p.tab = s->dev->d_t4; p.pitch = W; p.err = s->d_err;
     p.cursor = vs.cursor;
+    IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, parse_scratch_bytes(enc_bytes, 4)));
+    // The chain of a frame is followed over a bounded span of the stream (its size is not known in advance): start from the
+    // average frame size, grow from what the previous frames needed, retry with a larger span when the last block was not
+    // reached (the cursor did not move).  One 8-byte read-back per frame.
+    unsigned long long cursor_h = consts[1];
+    size_t span = std::max<size_t>((enc_bytes * 8 / std::max(1u, frames)) * 2, (size_t)1 << 16);
     for (uint32_t f = 0; f < frames; f++) {
         uint8_t *cur = d_out + (size_t)f * fsz;
         const bool is_i = (f % h.gop) == 0;
         p.out = cur;
         if (is_i) {
             p.skip_bits = 0; p.add_mode = 0;
-            IE_TRY(launch_parse_blocks(p, 1, st));
-            IE_TRY(launch_decode_blocks(p, 1, st));
         } else {
             MCParams mc;
             mc.enc = d_enc; mc.enc_bits = consts[0]; mc.cursor = vs.cursor; mc.mvbits = mvbits; mc.ref = d_out + (size_t)(f - 1) * fsz;
@@ -352,9 +358,19 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
             count_launch();
             IE_CUDA(cudaGetLastError());
             p.skip_bits = nmb * 2 * mvbits; p.add_mode = 1;
-            IE_TRY(launch_parse_blocks(p, 1, st));                           // advances the cursor past this frame
-            if (motioncomp) IE_TRY(launch_decode_blocks(p, 1, st));           // Frame.cpp:107-117
         }
+        const unsigned long long first_block = std::min<unsigned long long>(cursor_h + p.skip_bits, consts[0]);
+        while (true) {
+            IE_TRY(launch_parallel_parse(p, span, s->d_parse, st));          // advances the cursor past this frame
+            IE_CUDA(cudaMemcpyAsync(s->h_pinned, vs.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            IE_CUDA(cudaStreamSynchronize(st));
+            if (s->h_pinned[0] != cursor_h || first_block + span >= consts[0] + kGroupSpanSlack) break;
+            span *= 4;
+        }
+        const unsigned long long used = s->h_pinned[0] - std::min(s->h_pinned[0], first_block);
+        cursor_h = s->h_pinned[0];
+        span = std::max<size_t>(span / 2, (size_t)used * 2 + ((size_t)1 << 16));
+        if (is_i || motioncomp) IE_TRY(launch_decode_blocks(p, 1, st));      // Frame.cpp:107-117
     }
     if (frames) {
         fill_uv_kernel<<<256, 256, 0, st>>>(d_out, ysz, fsz, frames);         // Frame.cpp:122-124 (W*H/2 is a multiple of 16)

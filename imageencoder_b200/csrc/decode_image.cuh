@@ -27,5 +27,7 @@ struct DecodeParams {
 
 int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream);
 int launch_decode_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream);
+size_t parse_scratch_bytes(size_t enc_bytes, int N);
+int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scratch, cudaStream_t stream);
 
 }  // namespace ie

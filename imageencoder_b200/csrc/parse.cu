@@ -1,0 +1,229 @@
+// Parallel discovery of block offsets in the marker-less stream.
+//
+// A block's size is in its own header (Block.cpp:443-444: bit_len(4) [length(bit_len)] length x bit_len), so block k's
+// first bit depends on every earlier block -- the reference reads the stream strictly in sequence (ImageDecoder.cpp:89-92).
+// Here the chain is resolved with transfer functions over spans of the stream, measured from the first block's bit B0:
+//   * a block that starts before a span boundary ends at most E = 4 + 16 + 16 N^2 bits after it, so the chain can enter
+//     a span only at offsets [0, E).  A span's transfer function maps every possible entry offset to (offset at which the
+//     chain enters the next span, number of blocks started inside).
+//   * parse_group_tables : one CTA per group (kSubsPerGroup sub-spans of kSubBits bits).  All E hypothetical chains are
+//                          advanced sub-span by sub-span; at every sub-span boundary identical chains are merged (only one
+//                          walk per DISTINCT entry offset), and real streams merge to a single chain almost at once.
+//   * parse_super_tables : composes kSuper group tables for all E entries in parallel (E independent lookup chains).
+//   * parse_top_walk     : one thread walks the super-groups from the true entry (offset 0).
+//   * parse_down_super   : one thread per super-group hands every group its true entry and first block index.
+//   * parse_emit_offsets : one thread per group walks its true chain and writes block_off[].
+// Exact for any stream (no statistical self-synchronisation assumption).  Reads past the end of the stream give 0 bits and
+// do not advance (BitStream.cpp:17-20): a chain that reaches the end is DEAD and every remaining block starts at `total`.
+#include <cstdio>
+#include <cstdlib>
+
+#include "decode_image.cuh"
+
+namespace ie {
+
+constexpr int kSubBits = 8192;
+constexpr int kSubsPerGroup = 16;
+constexpr int kGroupBits = kSubBits * kSubsPerGroup;     // 16 KiB of stream per group
+constexpr int kSuper = 64;                               // groups per super-group (1 MiB of stream)
+constexpr unsigned kDead = 0xFFFFu;
+
+struct ParseParams {
+    const uint8_t *enc;
+    const unsigned long long *enc_bits;     // device: stream size in bits
+    const unsigned long long *start;        // device: cursor / first-block bit (skip_bits is added)
+    unsigned skip_bits;
+    int NN, use_rle, E;
+    unsigned ngroups, nsuper, nblocks;
+    uint2 *group_table;                     // [ngroups][E] (exit offset | kDead, blocks)
+    uint2 *super_table;                     // [nsuper][E]
+    uint2 *super_entry;                     // [nsuper]  (entry offset | kDead, first block index)
+    uint2 *group_entry;                     // [ngroups]
+    unsigned long long *block_off;          // [nblocks + 1]
+    unsigned long long *cursor_out;         // device, may be NULL: receives the bit after the last block
+    int *err;
+};
+
+__device__ __forceinline__ unsigned parse_read_bits(const uint8_t *__restrict__ s, unsigned long long total_bits, unsigned long long p, int n) {
+    if (n == 0) return 0u;
+    const unsigned long long nbytes = (total_bits + 7) >> 3, b = p >> 3;
+    unsigned v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) v = (v << 8) | ((b + i < nbytes) ? (unsigned)__ldg(s + b + i) : 0u);
+    return (v >> (32 - (int)(p & 7) - n)) & ((1u << n) - 1u);
+}
+
+// size in bits of the block whose header is at absolute bit p (p < total); kBadBlock if the length field exceeds N*N.
+// A hypothetical chain that starts at a wrong offset reads garbage headers; one with length > N*N cannot be the real
+// chain of a valid stream (Block.cpp:185-232 never produces it) and is dropped (DEAD).  If the REAL chain contains such
+// a block the stream is malformed: parse_emit_offsets reports IE_EFORMAT (the reference indexes out of bounds there).
+constexpr unsigned kBadBlock = 0xFFFFFFFFu;
+__device__ __forceinline__ unsigned block_bits_at(const uint8_t *s, unsigned long long total, unsigned long long p, int NN, int rle) {
+    const unsigned w = parse_read_bits(s, total, p, 4);
+    unsigned len = (unsigned)NN;
+    if (rle) len = parse_read_bits(s, total, min(p + 4, total), (int)w);
+    if (len > (unsigned)NN) return kBadBlock;
+    return 4u + (rle ? w : 0u) + len * w;
+}
+
+__global__ void __launch_bounds__(256) parse_group_tables(const ParseParams p) {
+    extern __shared__ unsigned s_parse[];
+    const int E = p.E;
+    unsigned *s_cnt = s_parse;                                            // [E]
+    unsigned *s_memo = s_cnt + E;                                         // [E] exit << 16 | blocks
+    unsigned short *s_cur = reinterpret_cast<unsigned short *>(s_memo + E);   // [E]
+    unsigned char *s_need = reinterpret_cast<unsigned char *>(s_cur + E + (E & 1));   // [E]
+    const unsigned g = blockIdx.x;
+    const unsigned long long total = *p.enc_bits;
+    const unsigned long long B0 = *p.start + p.skip_bits;
+    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) { s_cur[e] = (unsigned short)e; s_cnt[e] = 0; }
+    __syncthreads();
+    for (int sub = 0; sub < kSubsPerGroup; sub++) {
+        const unsigned long long s_start = g_start + (unsigned long long)sub * kSubBits;
+        for (int e = threadIdx.x; e < E; e += blockDim.x) { s_need[e] = 0; }
+        __syncthreads();
+        for (int e = threadIdx.x; e < E; e += blockDim.x) { const unsigned c = s_cur[e]; if (c != kDead) s_need[c] = 1; }
+        __syncthreads();
+        for (int t = threadIdx.x; t < E; t += blockDim.x) {
+            if (!s_need[t]) continue;
+            unsigned long long pos = s_start + (unsigned)t;
+            const unsigned long long s_end = s_start + kSubBits;
+            unsigned cnt = 0;
+            unsigned res;
+            while (true) {
+                if (pos >= total) { res = (kDead << 16) | cnt; break; }
+                if (pos >= s_end) { res = ((unsigned)(pos - s_end) << 16) | cnt; break; }
+                const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
+                if (bits == kBadBlock) { res = (kDead << 16) | cnt; break; }
+                pos += bits;
+                cnt++;
+            }
+            s_memo[t] = res;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < E; e += blockDim.x) {
+            const unsigned c = s_cur[e];
+            if (c != kDead) { const unsigned m = s_memo[c]; s_cur[e] = (unsigned short)(m >> 16); s_cnt[e] += m & 0xFFFFu; }
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < E; e += blockDim.x) p.group_table[(size_t)g * E + e] = make_uint2(s_cur[e], s_cnt[e]);
+}
+
+__global__ void __launch_bounds__(256) parse_super_tables(const ParseParams p) {
+    const unsigned sg = blockIdx.x;
+    const unsigned g0 = sg * kSuper, g1 = min(g0 + kSuper, p.ngroups);
+    for (int e = threadIdx.x; e < p.E; e += blockDim.x) {
+        unsigned cur = (unsigned)e, cnt = 0;
+        for (unsigned g = g0; g < g1 && cur != kDead; g++) {
+            const uint2 t = __ldg(p.group_table + (size_t)g * p.E + cur);
+            cur = t.x;
+            cnt += t.y;
+        }
+        p.super_table[(size_t)sg * p.E + e] = make_uint2(cur, cnt);
+    }
+}
+
+__global__ void parse_top_walk(const ParseParams p) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned cur = 0, cnt = 0;
+    for (unsigned sg = 0; sg < p.nsuper; sg++) {
+        p.super_entry[sg] = make_uint2(cur, cnt);
+        if (cur != kDead) { const uint2 t = p.super_table[(size_t)sg * p.E + cur]; cur = t.x; cnt += t.y; }
+    }
+}
+
+__global__ void __launch_bounds__(64) parse_down_super(const ParseParams p) {
+    const unsigned sg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sg >= p.nsuper) return;
+    const uint2 se = p.super_entry[sg];
+    unsigned cur = se.x, cnt = se.y;
+    const unsigned g0 = sg * kSuper, g1 = min(g0 + kSuper, p.ngroups);
+    for (unsigned g = g0; g < g1; g++) {
+        p.group_entry[g] = make_uint2(cur, cnt);
+        if (cur != kDead) { const uint2 t = __ldg(p.group_table + (size_t)g * p.E + cur); cur = t.x; cnt += t.y; }
+    }
+}
+
+__global__ void __launch_bounds__(64) parse_emit_offsets(const ParseParams p) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.ngroups) return;
+    const uint2 ge = p.group_entry[g];
+    if (ge.x == kDead) return;
+    const unsigned long long total = *p.enc_bits;
+    const unsigned long long B0 = *p.start + p.skip_bits;
+    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
+    unsigned long long pos = g_start + ge.x;
+    unsigned idx = ge.y;
+    while (pos < g_end && pos < total && idx < p.nblocks) {
+        const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
+        if (bits == kBadBlock) { if (p.err) atomicExch(p.err, IE_EFORMAT); pos = total; break; }   // malformed stream
+        p.block_off[idx++] = pos;
+        pos = min(pos + bits, total);
+    }
+    if (idx <= p.nblocks && pos >= total) {
+        // the chain reached the end of the stream in this group: every remaining block starts (and ends) at `total`
+        for (; idx < p.nblocks; idx++) p.block_off[idx] = total;
+        p.block_off[p.nblocks] = total;
+        if (p.cursor_out) *p.cursor_out = total;
+    } else if (idx == p.nblocks && ge.y < p.nblocks) {
+        p.block_off[idx] = pos;                 // this thread emitted the last block
+        if (p.cursor_out) *p.cursor_out = pos;
+    }
+}
+
+static void parse_sizes(size_t span_bits, int N, unsigned &E, unsigned &ngroups, unsigned &nsuper) {
+    E = 4 + 16 + 16 * N * N;
+    ngroups = (unsigned)((span_bits + kGroupBits - 1) / kGroupBits + 1);
+    nsuper = (ngroups + kSuper - 1) / kSuper;
+}
+
+size_t parse_scratch_bytes(size_t enc_bytes, int N) {
+    unsigned E, ng, ns;
+    parse_sizes(enc_bytes * 8, N, E, ng, ns);
+    return ((size_t)ng * E + (size_t)ns * E + ns + ng) * sizeof(uint2) + 256;
+}
+
+// Fills d.block_off[0..nblocks] for one stream (and advances d.cursor when the last block lies inside the span).
+// `span_bits`: how far past the first block the chain is followed (the whole stream for images; a per-frame budget for
+// video, where the caller retries with a larger span if the cursor did not move).  `scratch`: parse_scratch_bytes(bytes
+// of the whole stream) bytes, 16-aligned.
+int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scratch, cudaStream_t stream) {
+    ParseParams p;
+    unsigned E;
+    parse_sizes(span_bits, d.N, E, p.ngroups, p.nsuper);
+    p.enc = d.enc; p.enc_bits = d.enc_bits;
+    p.start = d.cursor ? d.cursor : d.start_bit;
+    p.skip_bits = d.cursor ? d.skip_bits : 0;
+    p.NN = d.N * d.N; p.use_rle = d.use_rle; p.E = (int)E;
+    p.nblocks = d.nblocks;
+    uint2 *s = reinterpret_cast<uint2 *>(scratch);
+    p.group_table = s; s += (size_t)p.ngroups * E;
+    p.super_table = s; s += (size_t)p.nsuper * E;
+    p.super_entry = s; s += p.nsuper;
+    p.group_entry = s;
+    p.block_off = d.block_off;
+    p.cursor_out = d.cursor;
+    p.err = d.err;
+    const size_t smem = (size_t)E * (4 + 4 + 2 + 1) + 16;
+    static const bool dbg = getenv("IE_DEBUG_SYNC") != nullptr;
+#define IE_DBG_STEP(name) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(stream); if (e_ != cudaSuccess) { fprintf(stderr, "[ie] %s failed: %s\n", name, cudaGetErrorString(e_)); return cuda_fail(e_, name, __FILE__, __LINE__); } } } while (0)
+    IE_DBG_STEP("before parse");
+    parse_group_tables<<<p.ngroups, 256, smem, stream>>>(p);
+    IE_DBG_STEP("parse_group_tables");
+    parse_super_tables<<<p.nsuper, 256, 0, stream>>>(p);
+    IE_DBG_STEP("parse_super_tables");
+    parse_top_walk<<<1, 32, 0, stream>>>(p);
+    IE_DBG_STEP("parse_top_walk");
+    parse_down_super<<<(p.nsuper + 63) / 64, 64, 0, stream>>>(p);
+    IE_DBG_STEP("parse_down_super");
+    parse_emit_offsets<<<(p.ngroups + 63) / 64, 64, 0, stream>>>(p);
+    IE_DBG_STEP("parse_emit_offsets");
+#undef IE_DBG_STEP
+    count_launch(5);
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
+}  // namespace ie

@@ -24,6 +24,9 @@ struct ie_session {
     unsigned long long *d_block_off = nullptr;    // [images * nblocks (+1)]
     size_t block_off_cap = 0;
 
+    uint8_t *d_parse = nullptr;                   // transfer-function tables of the parallel parser
+    size_t parse_cap = 0;
+
     // generic device scratch (Huffman stage, video)
     uint8_t *d_scratch = nullptr;
     size_t scratch_cap = 0;
