@@ -6,7 +6,7 @@
 //   * a block that starts before a span boundary ends at most E = 4 + 16 + 16 N^2 bits after it, so the chain can enter
 //     a span only at offsets [0, E).  A span's transfer function maps every possible entry offset to (offset at which the
 //     chain enters the next span, number of blocks started inside).
-//   * parse_group_tables : one CTA per group (kSubsPerGroup sub-spans of kSubBits bits).  All E hypothetical chains are
+//   * parse_group_tables : one CTA per group (kSubsPerGroup sub-spans, short ones first).  All E hypothetical chains are
 //                          advanced sub-span by sub-span; at every sub-span boundary identical chains are merged (only one
 //                          walk per DISTINCT entry offset), and real streams merge to a single chain almost at once.
 //   * parse_super_tables : composes kSuper group tables for all E entries in parallel (E independent lookup chains).
@@ -22,10 +22,12 @@
 
 namespace ie {
 
-constexpr int kSubBits = 8192;
-constexpr int kSubsPerGroup = 16;
-constexpr int kGroupBits = kSubBits * kSubsPerGroup;     // 16 KiB of stream per group
-constexpr int kSuper = 64;                               // groups per super-group (1 MiB of stream)
+// Sub-span boundaries inside a group: short spans first, so that the E hypothetical chains of a group are merged after
+// a block or two instead of each being walked through kilobits of stream.
+constexpr int kSubsPerGroup = 12;
+__constant__ int c_sub_bounds[kSubsPerGroup + 1] = {0, 256, 512, 1024, 1536, 2048, 3072, 4096, 8192, 12288, 16384, 24576, 32768};
+constexpr int kGroupBits = 32768;                        // 4 KiB of stream per group
+constexpr int kSuper = 64;                               // groups per super-group (256 KiB of stream)
 constexpr unsigned kDead = 0xFFFFu;
 
 struct ParseParams {
@@ -42,6 +44,9 @@ struct ParseParams {
     unsigned long long *block_off;          // [nblocks + 1]
     unsigned long long *cursor_out;         // device, may be NULL: receives the bit after the last block
     int *err;
+    // speculative path
+    uint2 *spec_exit;                       // [ngroups] (exit offset | kDead, blocks started in the group)
+    unsigned *spec_flags;                   // [0] number of groups repaired in the last round, [1] spec_ok
 };
 
 __device__ __forceinline__ unsigned parse_read_bits(const uint8_t *__restrict__ s, unsigned long long total_bits, unsigned long long p, int n) {
@@ -54,19 +59,28 @@ __device__ __forceinline__ unsigned parse_read_bits(const uint8_t *__restrict__ 
 }
 
 // size in bits of the block whose header is at absolute bit p (p < total); kBadBlock if the length field exceeds N*N.
+// bit_len (4 bits) and the length field (<= 15 bits) fit one 32-bit window at any bit alignment (7 + 4 + 15 <= 32).
 // A hypothetical chain that starts at a wrong offset reads garbage headers; one with length > N*N cannot be the real
 // chain of a valid stream (Block.cpp:185-232 never produces it) and is dropped (DEAD).  If the REAL chain contains such
 // a block the stream is malformed: parse_emit_offsets reports IE_EFORMAT (the reference indexes out of bounds there).
 constexpr unsigned kBadBlock = 0xFFFFFFFFu;
 __device__ __forceinline__ unsigned block_bits_at(const uint8_t *s, unsigned long long total, unsigned long long p, int NN, int rle) {
-    const unsigned w = parse_read_bits(s, total, p, 4);
+    // 32 stream bits starting at p from two aligned words (the stream buffer is 4-byte aligned and padded; bits past
+    // `total` are forced to zero, BitStream.cpp:17-20)
+    const unsigned *wp = reinterpret_cast<const unsigned *>(s) + (p >> 5);
+    const unsigned long long nwords = (total + 31) >> 5;
+    const unsigned w0 = __byte_perm(__ldg(wp), 0, 0x0123);
+    const unsigned w1 = ((p >> 5) + 1 < nwords) ? __byte_perm(__ldg(wp + 1), 0, 0x0123) : 0u;
+    unsigned v = __funnelshift_l(w1, w0, (unsigned)(p & 31));
+    if (p + 32 > total) v &= ~((total - p >= 32) ? 0u : (0xFFFFFFFFu >> (unsigned)(total - p)));
+    const unsigned w = v >> 28;
     unsigned len = (unsigned)NN;
-    if (rle) len = parse_read_bits(s, total, min(p + 4, total), (int)w);
+    if (rle) len = w ? ((v << 4) >> (32 - w)) : 0u;
     if (len > (unsigned)NN) return kBadBlock;
     return 4u + (rle ? w : 0u) + len * w;
 }
 
-__global__ void __launch_bounds__(256) parse_group_tables(const ParseParams p) {
+__global__ void __launch_bounds__(64) parse_group_tables(const ParseParams p) {
     extern __shared__ unsigned s_parse[];
     const int E = p.E;
     unsigned *s_cnt = s_parse;                                            // [E]
@@ -74,13 +88,14 @@ __global__ void __launch_bounds__(256) parse_group_tables(const ParseParams p) {
     unsigned short *s_cur = reinterpret_cast<unsigned short *>(s_memo + E);   // [E]
     unsigned char *s_need = reinterpret_cast<unsigned char *>(s_cur + E + (E & 1));   // [E]
     const unsigned g = blockIdx.x;
+    if (p.spec_flags[1]) return;                                          // the speculative parse verified: nothing to do
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
     const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits;
     for (int e = threadIdx.x; e < E; e += blockDim.x) { s_cur[e] = (unsigned short)e; s_cnt[e] = 0; }
     __syncthreads();
     for (int sub = 0; sub < kSubsPerGroup; sub++) {
-        const unsigned long long s_start = g_start + (unsigned long long)sub * kSubBits;
+        const unsigned long long s_start = g_start + (unsigned long long)c_sub_bounds[sub];
         for (int e = threadIdx.x; e < E; e += blockDim.x) { s_need[e] = 0; }
         __syncthreads();
         for (int e = threadIdx.x; e < E; e += blockDim.x) { const unsigned c = s_cur[e]; if (c != kDead) s_need[c] = 1; }
@@ -88,7 +103,7 @@ __global__ void __launch_bounds__(256) parse_group_tables(const ParseParams p) {
         for (int t = threadIdx.x; t < E; t += blockDim.x) {
             if (!s_need[t]) continue;
             unsigned long long pos = s_start + (unsigned)t;
-            const unsigned long long s_end = s_start + kSubBits;
+            const unsigned long long s_end = g_start + (unsigned long long)c_sub_bounds[sub + 1];
             unsigned cnt = 0;
             unsigned res;
             while (true) {
@@ -113,6 +128,7 @@ __global__ void __launch_bounds__(256) parse_group_tables(const ParseParams p) {
 
 __global__ void __launch_bounds__(256) parse_super_tables(const ParseParams p) {
     const unsigned sg = blockIdx.x;
+    if (p.spec_flags[1]) return;
     const unsigned g0 = sg * kSuper, g1 = min(g0 + kSuper, p.ngroups);
     for (int e = threadIdx.x; e < p.E; e += blockDim.x) {
         unsigned cur = (unsigned)e, cnt = 0;
@@ -126,7 +142,7 @@ __global__ void __launch_bounds__(256) parse_super_tables(const ParseParams p) {
 }
 
 __global__ void parse_top_walk(const ParseParams p) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0 || p.spec_flags[1]) return;
     unsigned cur = 0, cnt = 0;
     for (unsigned sg = 0; sg < p.nsuper; sg++) {
         p.super_entry[sg] = make_uint2(cur, cnt);
@@ -136,7 +152,7 @@ __global__ void parse_top_walk(const ParseParams p) {
 
 __global__ void __launch_bounds__(64) parse_down_super(const ParseParams p) {
     const unsigned sg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sg >= p.nsuper) return;
+    if (sg >= p.nsuper || p.spec_flags[1]) return;
     const uint2 se = p.super_entry[sg];
     unsigned cur = se.x, cnt = se.y;
     const unsigned g0 = sg * kSuper, g1 = min(g0 + kSuper, p.ngroups);
@@ -144,6 +160,104 @@ __global__ void __launch_bounds__(64) parse_down_super(const ParseParams p) {
         p.group_entry[g] = make_uint2(cur, cnt);
         if (cur != kDead) { const uint2 t = __ldg(p.group_table + (size_t)g * p.E + cur); cur = t.x; cnt += t.y; }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Speculative fast path.  Real streams re-synchronise: a walk started at an arbitrary bit lands on the true chain after
+// a few kilobits (measured: all 1044 entry offsets of a group merge into ONE chain within 3072 bits).  So every group
+// starts kSpecLead bits early at an arbitrary position and *assumes* it is on the true chain when it reaches its first bit.
+// The assumption is then VERIFIED exactly: group g's speculative entry must equal group g-1's exit; group 0 starts at the
+// true first block, so if all neighbours agree every group is on the true chain (induction).  Groups that disagree are
+// re-walked from their predecessor's exit (a few rounds); if disagreement remains, spec_ok stays 0 and the exact
+// transfer-function kernels above do the work instead (they return immediately when spec_ok is 1).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSpecLead = 8192;
+constexpr int kSpecRounds = 3;
+
+// walks the chain from absolute bit `pos` (inside or before the group) to the group's end
+__device__ __forceinline__ uint2 walk_group(const ParseParams &p, unsigned long long total, unsigned long long pos, unsigned long long g_end) {
+    unsigned cnt = 0;
+    while (true) {
+        if (pos >= total) return make_uint2(kDead, cnt);
+        if (pos >= g_end) return make_uint2((unsigned)(pos - g_end), cnt);
+        const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
+        if (bits == kBadBlock) return make_uint2(kDead, cnt);
+        pos += bits;
+        cnt++;
+    }
+}
+
+__global__ void __launch_bounds__(64) parse_spec_walk(const ParseParams p) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0 && threadIdx.x == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; }
+    if (g >= p.ngroups) return;
+    const unsigned long long total = *p.enc_bits;
+    const unsigned long long B0 = *p.start + p.skip_bits;
+    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
+    unsigned long long pos = (g == 0) ? B0 : g_start - kSpecLead;
+    unsigned entry;
+    if (g_start >= total) { entry = kDead; }
+    else {
+        while (pos < g_start) {                            // lead-in on an arbitrary phase; garbage headers just slide by a bit
+            const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
+            pos += (bits == kBadBlock) ? 1u : bits;
+        }
+        entry = (pos >= total) ? kDead : (unsigned)(pos - g_start);
+    }
+    const uint2 ex = (entry == kDead) ? make_uint2(kDead, 0u) : walk_group(p, total, pos, g_end);
+    p.group_entry[g] = make_uint2(entry, 0u);
+    p.spec_exit[g] = ex;
+}
+
+__global__ void __launch_bounds__(64) parse_spec_repair(const ParseParams p, int round) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.ngroups || g == 0) return;
+    // only trust a predecessor that is itself consistent with ITS predecessor: a group whose lead-in failed to synchronise
+    // walks garbage (and may even die on a bad header); adopting its exit would push the error forward round after round
+    if (g >= 2 && p.spec_exit[g - 2].x != p.group_entry[g - 1].x) return;
+    const unsigned want = p.spec_exit[g - 1].x;
+    const unsigned have = p.group_entry[g].x;
+    if (want == have) return;
+    atomicAdd(&p.spec_flags[0], 1u + (unsigned)round * 0u);
+    const unsigned long long total = *p.enc_bits;
+    const unsigned long long B0 = *p.start + p.skip_bits;
+    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
+    // NOTE: reading spec_exit[g-1] while thread g-1 may rewrite it in this same launch is a benign race: whatever is read
+    // is re-verified by the final check.
+    p.group_entry[g] = make_uint2(want, 0u);
+    p.spec_exit[g] = (want == kDead || want >= (unsigned)kGroupBits) ? make_uint2(kDead, 0u) : walk_group(p, total, g_start + want, g_end);
+}
+
+// final exact verification + exclusive scan of the per-group block counts (single CTA)
+__global__ void __launch_bounds__(1024) parse_spec_finish(const ParseParams p) {
+    __shared__ unsigned s_bad;
+    __shared__ unsigned s_sum[1024];
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    const unsigned per = (p.ngroups + 1023) / 1024;
+    const unsigned g0 = threadIdx.x * per, g1 = min(g0 + per, p.ngroups);
+    unsigned sum = 0, bad = 0;
+    for (unsigned g = g0; g < g1; g++) {
+        if (g > 0 && p.spec_exit[g - 1].x != p.group_entry[g].x) bad = 1;
+        sum += p.spec_exit[g].y;
+    }
+    if (bad) atomicOr(&s_bad, 1u);
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {                    // Hillis-Steele inclusive scan
+        const unsigned v = (threadIdx.x >= (unsigned)d) ? s_sum[threadIdx.x - d] : 0u;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    if (s_bad) return;                                      // spec_ok stays 0: the exact kernels run
+    unsigned base = s_sum[threadIdx.x] - sum;
+    for (unsigned g = g0; g < g1; g++) {
+        const uint2 ge = p.group_entry[g];
+        p.group_entry[g] = make_uint2(ge.x, base);
+        base += p.spec_exit[g].y;
+    }
+    if (threadIdx.x == 0) p.spec_flags[1] = 1;
 }
 
 __global__ void __launch_bounds__(64) parse_emit_offsets(const ParseParams p) {
@@ -182,7 +296,7 @@ static void parse_sizes(size_t span_bits, int N, unsigned &E, unsigned &ngroups,
 size_t parse_scratch_bytes(size_t enc_bytes, int N) {
     unsigned E, ng, ns;
     parse_sizes(enc_bytes * 8, N, E, ng, ns);
-    return ((size_t)ng * E + (size_t)ns * E + ns + ng) * sizeof(uint2) + 256;
+    return ((size_t)ng * E + (size_t)ns * E + ns + ng + ng + 8) * sizeof(uint2) + 256;
 }
 
 // Fills d.block_off[0..nblocks] for one stream (and advances d.cursor when the last block lies inside the span).
@@ -202,7 +316,9 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     p.group_table = s; s += (size_t)p.ngroups * E;
     p.super_table = s; s += (size_t)p.nsuper * E;
     p.super_entry = s; s += p.nsuper;
-    p.group_entry = s;
+    p.group_entry = s; s += p.ngroups;
+    p.spec_exit = s; s += p.ngroups;
+    p.spec_flags = reinterpret_cast<unsigned *>(s);
     p.block_off = d.block_off;
     p.cursor_out = d.cursor;
     p.err = d.err;
@@ -210,7 +326,11 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     static const bool dbg = getenv("IE_DEBUG_SYNC") != nullptr;
 #define IE_DBG_STEP(name) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(stream); if (e_ != cudaSuccess) { fprintf(stderr, "[ie] %s failed: %s\n", name, cudaGetErrorString(e_)); return cuda_fail(e_, name, __FILE__, __LINE__); } } } while (0)
     IE_DBG_STEP("before parse");
-    parse_group_tables<<<p.ngroups, 256, smem, stream>>>(p);
+    parse_spec_walk<<<(p.ngroups + 63) / 64, 64, 0, stream>>>(p);
+    for (int r = 0; r < kSpecRounds; r++) parse_spec_repair<<<(p.ngroups + 63) / 64, 64, 0, stream>>>(p, r);
+    parse_spec_finish<<<1, 1024, 0, stream>>>(p);
+    IE_DBG_STEP("parse_spec");
+    parse_group_tables<<<p.ngroups, 64, smem, stream>>>(p);
     IE_DBG_STEP("parse_group_tables");
     parse_super_tables<<<p.nsuper, 256, 0, stream>>>(p);
     IE_DBG_STEP("parse_super_tables");
@@ -221,7 +341,7 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     parse_emit_offsets<<<(p.ngroups + 63) / 64, 64, 0, stream>>>(p);
     IE_DBG_STEP("parse_emit_offsets");
 #undef IE_DBG_STEP
-    count_launch(5);
+    count_launch(7 + kSpecRounds);
     IE_CUDA(cudaGetLastError());
     return IE_OK;
 }
