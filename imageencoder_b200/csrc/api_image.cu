@@ -96,6 +96,15 @@ int launch_stream_init(uint8_t *out, size_t out_stride, unsigned images, const H
     return IE_OK;
 }
 
+void make_k2(float *k2, const uint16_t *quant, int N) {
+    for (int u = 0; u < N; u++)
+        for (int v = 0; v < N; v++) {
+            const double cu = (u == 0) ? 0.5 : 0.70710678118654752440, cv = (v == 0) ? 0.5 : 0.70710678118654752440;
+            k2[u * N + v] = (float)(cu * cv * (double)quant[u * N + v]);
+        }
+    for (int i = N * N; i < kMaxNN; i++) k2[i] = 0.f;
+}
+
 int make_quant(QuantParam &q, const uint16_t *quant, int N) {
     memset(&q, 0, sizeof q);
     for (int i = 0; i < N * N; i++) q.m[i] = (double)quant[i];          // MatrixReader.cpp:128,195-198
@@ -215,6 +224,7 @@ int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size
     p.enc = d_enc; p.enc_stride = 0; p.enc_bits = d_consts; p.start_bit = d_consts + 1;
     p.block_off = s->d_block_off; p.nblocks = nblocks; p.bx = W / N; p.N = N; p.use_rle = h.use_rle;
     make_quant(p.quant, h.quant, N);
+    make_k2(p.k2, h.quant, N);
     p.tab = (N == 8) ? s->dev->d_t8 : s->dev->d_t4;
     p.out = d_out; p.out_stride = 0; p.pitch = W; p.err = s->d_err;
     IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, parse_scratch_bytes(enc_bytes, N)));

@@ -17,6 +17,7 @@ struct ParsedHeader {
 int check_quant(const uint16_t *quant, int N);
 int check_dims(uint32_t W, uint32_t H, uint32_t N);
 int make_quant(QuantParam &q, const uint16_t *quant, int N);
+void make_k2(float *k2, const uint16_t *quant, int N);
 int parse_header(const uint8_t *bytes, size_t n, size_t start_bit, int N, ParsedHeader &h, int video);
 int launch_stream_init(uint8_t *out, size_t out_stride, unsigned images, const HeaderParam &hdr, unsigned first_bit,
                        unsigned long long *counter, cudaStream_t stream);

@@ -336,7 +336,7 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
     DecodeParams p;
     memset(&p, 0, sizeof p);
     p.enc = d_enc; p.enc_bits = d_consts; p.start_bit = d_consts + 1; p.block_off = s->d_block_off; p.nblocks = nblocks;
-    p.bx = W / 4; p.N = 4; p.use_rle = h.use_rle; make_quant(p.quant, h.quant, 4); p.tab = s->dev->d_t4; p.pitch = W; p.err = s->d_err;
+    p.bx = W / 4; p.N = 4; p.use_rle = h.use_rle; make_quant(p.quant, h.quant, 4); make_k2(p.k2, h.quant, 4); p.tab = s->dev->d_t4; p.pitch = W; p.err = s->d_err;
     p.cursor = vs.cursor;
     IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, parse_scratch_bytes(enc_bytes, 4)));
     // The chain of a frame is followed over a bounded span of the stream (its size is not known in advance): start from the

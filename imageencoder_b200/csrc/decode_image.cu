@@ -7,8 +7,15 @@
 //                         (Block.cpp:441-472, 162-177, 99-107; algo.cpp:343-363).
 #include "decode_image.cuh"
 #include "transform.cuh"
+#include "transform_fast.cuh"
+#include <atomic>
 
 namespace ie {
+
+__device__ constexpr unsigned char kZigzagInvD4[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};
+__device__ constexpr unsigned char kZigzagInvD8[64] = {
+    0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30, 41, 43, 9,  11, 18, 24, 31, 40, 44, 53,
+    10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
 
 // n <= 25 bits at bit position p (MSB-first).  Bits past the end read as 0 (BitStream.cpp:17-20).
 __device__ __forceinline__ unsigned read_bits(const uint8_t *__restrict__ s, unsigned long long total_bits, unsigned long long p, int n) {
@@ -110,6 +117,155 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecodeParams p
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fast decode: fields through a 64-bit bit buffer fed by aligned word loads; separable FP32 inverse DCT; every pixel
+// whose fast value lies within the block's error bound of an integer boundary (where the reference's truncation,
+// Block.cpp:103, could go either way) is recomputed in the reference's exact order over the non-zero coefficients.
+//   error bound: |X_fast - X_real| <= 14 u S with S = sum |C(u)C(v) Q c| (8 u S_row from pass 1 carried through pass 2,
+//   6 u S from pass 2, u = 2^-24); the +128 / +prediction add rounds at <= u (S + 383).  delta = 32 u S + 2 u (S + 383)
+//   + 2e-6 is used (> 2x margin).  Pixels that are certainly clamped (v < -delta or v > 255 + delta) need no check.
+// ---------------------------------------------------------------------------------------------------------
+__constant__ unsigned char c_zz4[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+__constant__ unsigned char c_zz8[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                        41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                        30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct BitReader {
+    const unsigned *words;
+    unsigned long long nwords, total;
+    unsigned long long wi;       // next word to load
+    unsigned long long buf;      // upcoming bits, left aligned
+    int n;                       // valid bits in buf
+    __device__ __forceinline__ unsigned load(unsigned long long i) const {
+        if (i >= nwords) return 0u;
+        unsigned w = __byte_perm(__ldg(words + i), 0, 0x0123);
+        if ((i + 1) * 32 > total) w &= ~(0xFFFFFFFFu >> (unsigned)(total - i * 32));      // bits past the end read 0
+        return w;
+    }
+    __device__ __forceinline__ void init(const uint8_t *s, unsigned long long total_bits, unsigned long long pos) {
+        words = reinterpret_cast<const unsigned *>(s);
+        total = total_bits; nwords = (total_bits + 31) >> 5;
+        wi = pos >> 5;
+        const unsigned sh = (unsigned)(pos & 31);
+        buf = ((unsigned long long)load(wi) << 32) | load(wi + 1);
+        buf <<= sh;
+        n = 64 - (int)sh;
+        wi += 2;
+    }
+    __device__ __forceinline__ unsigned get(int k) {          // k <= 16
+        if (k == 0) return 0u;
+        if (n < 32) { buf |= (unsigned long long)load(wi++) << (32 - n); n += 32; }
+        const unsigned v = (unsigned)(buf >> (64 - k));
+        buf <<= k;
+        n -= k;
+        return v;
+    }
+};
+
+template <int N, bool ADD>
+__global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodeParams p) {
+    constexpr int NN = N * N;
+    constexpr int STRIDE = NN + 2;
+    __shared__ short s_coef[128 * STRIDE];
+    const unsigned img = blockIdx.y;
+    const unsigned gb = blockIdx.x * 128 + threadIdx.x;
+    if (gb >= p.nblocks) return;
+    const uint8_t *s = p.enc + (size_t)img * p.enc_stride;
+    const unsigned long long total = p.enc_bits[img];
+    const unsigned long long *off = p.block_off + (size_t)img * (p.nblocks + 1);
+    const BlockTables *tab = p.tab;
+
+    // ---- fields (Block.cpp:441-472) -------------------------------------------------------------------------
+    BitReader br;
+    br.init(s, total, off[gb]);
+    const int w = (int)br.get(4);
+    int len = NN;
+    if (p.use_rle) len = (int)br.get(w);
+    if (len > NN) { atomicExch(p.err, IE_EFORMAT); len = NN; }   // the reference indexes out of bounds here
+    short *cf = s_coef + threadIdx.x * STRIDE;
+    unsigned *cfw = reinterpret_cast<unsigned *>(cf);
+#pragma unroll
+    for (int j = 0; j < NN / 2; j++) cfw[j] = 0u;
+    unsigned long long nzmask = 0;           // raster positions of the non-zero coefficients
+    const int sh = 32 - w;
+    for (int k = 0; k < len; k++) {
+        const int v = (w == 0) ? 0 : ((int)(br.get(w) << sh) >> sh);          // util::shift_signed<int16_t>
+        if (v != 0) {
+            cf[k] = (short)v;
+            nzmask |= 1ull << ((N == 8) ? c_zz8[k] : c_zz4[k]);
+        }
+    }
+    // ---- fast inverse transform --------------------------------------------------------------------------------
+    float x[NN];
+    float S = 0.f;
+#pragma unroll
+    for (int uv = 0; uv < NN; uv++) {
+        const int k = (N == 8) ? kZigzagInvD8[uv] : kZigzagInvD4[uv];
+        const float d = (float)(int)cf[k] * p.k2[uv];                         // coefficient * Q * C(u)C(v)
+        x[uv] = d;
+        S += fabsf(d);
+    }
+    idct2d_fast<N>(x);
+    const float delta = (32.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
+    const bool all_unsure = !(delta < 0.49f);                                   // absurd coefficients: take the exact path everywhere
+    const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
+    uint8_t *dst = p.out + (size_t)img * p.out_stride + (size_t)(byi * N) * p.pitch + (size_t)bxi * N;
+    unsigned outw[N * (N / 4)];
+    unsigned long long unsure = 0;
+#pragma unroll
+    for (int y = 0; y < N; y++) {
+        unsigned curw[N / 4];
+        if (ADD) {
+            if (N == 8) { const uint2 c2 = *reinterpret_cast<const uint2 *>(dst + (size_t)y * p.pitch); curw[0] = c2.x; curw[N / 4 - 1] = c2.y; }
+            else curw[0] = *reinterpret_cast<const unsigned *>(dst + (size_t)y * p.pitch);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < N / 4; q4++) {
+            unsigned word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int ij = y * N + q4 * 4 + b;
+                float v = x[ij] + 128.f;
+                if (ADD) v += (float)((curw[q4] >> (8 * b)) & 0xffu);
+                const float vc = fminf(fmaxf(v, 0.f), 255.f);
+                const float r = (vc + kMagic) - kMagic;                       // rn(vc)
+                const float fl = (r > vc) ? r - 1.f : r;                      // floor(vc)
+                // an integer boundary k in [1, 255] within delta of v could flip the truncation
+                if ((fabsf(v - r) <= delta && r >= 1.f && r <= 255.f) || all_unsure) unsure |= 1ull << ij;
+                word |= (unsigned)(int)fl << (8 * b);
+            }
+            outw[y * (N / 4) + q4] = word;
+        }
+    }
+    // ---- exact recomputation of the uncertain pixels (algo.cpp:343-363 order: u outer, v inner; zeros skipped) -------
+    while (unsure) {
+        const int ij = __ffsll((long long)unsure) - 1;
+        unsure &= unsure - 1;
+        double acc = 0.0;
+        unsigned long long nz = nzmask;
+        while (nz) {
+            const int uv = __ffsll((long long)nz) - 1;
+            nz &= nz - 1;
+            const double d = __dmul_rn((double)(int)cf[tab->izz[uv]], p.quant.m[uv]);   // Block.cpp:165-168
+            acc = __dadd_rn(acc, __dmul_rn(__ldg(tab->inv + uv * NN + ij), d));         // algo.cpp:352-355
+        }
+        double v = __dadd_rn(acc, 128.0);                                               // Block.cpp:173-175
+        if (ADD) v = __dadd_rn((double)(int)dst[(size_t)(ij / N) * p.pitch + (ij % N)], v);   // Block.cpp:114-116
+        const unsigned px = clamp_trunc_u8(v);
+        const int wi = ij >> 2, bsh = 8 * (ij & 3);
+#pragma unroll
+        for (int r = 0; r < N * (N / 4); r++)
+            if (r == wi) outw[r] = (outw[r] & ~(0xffu << bsh)) | (px << bsh);
+    }
+#pragma unroll
+    for (int y = 0; y < N; y++) {
+        if (N == 8) *reinterpret_cast<uint2 *>(dst + (size_t)y * p.pitch) = make_uint2(outw[2 * y], outw[2 * y + 1]);
+        else *reinterpret_cast<unsigned *>(dst + (size_t)y * p.pitch) = outw[y];
+    }
+}
+
+extern std::atomic<int> g_exact_transform;
+
 int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream) {
     parse_blocks_kernel<<<images, 32, 0, stream>>>(p);
     count_launch();
@@ -118,6 +274,16 @@ int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t str
 }
 
 int launch_decode_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream) {
+    if (!g_exact_transform.load()) {
+        dim3 gridf((p.nblocks + 127) / 128, images);
+        if (p.N == 8) decode_blocks_fast_kernel<8, false><<<gridf, 128, 0, stream>>>(p);
+        else if (p.N == 4 && p.add_mode) decode_blocks_fast_kernel<4, true><<<gridf, 128, 0, stream>>>(p);
+        else if (p.N == 4) decode_blocks_fast_kernel<4, false><<<gridf, 128, 0, stream>>>(p);
+        else { set_error("block size must be 4 or 8"); return IE_EINVAL; }
+        count_launch();
+        IE_CUDA(cudaGetLastError());
+        return IE_OK;
+    }
     dim3 grid((p.nblocks + 255) / 256, images);
     if (p.N == 8) decode_blocks_kernel<8, false><<<grid, 256, 0, stream>>>(p);
     else if (p.N == 4 && p.add_mode) decode_blocks_kernel<4, true><<<grid, 256, 0, stream>>>(p);

@@ -14,6 +14,7 @@ struct DecodeParams {
     int N;
     int use_rle;
     QuantParam quant;
+    float k2[kMaxNN];                       // float(Q[u][v] * C(u)C(v)): dequantisation folded into the fast inverse transform
     const BlockTables *tab;
     uint8_t *out;                           // device, decoded pixels
     size_t out_stride;

@@ -71,6 +71,45 @@ __device__ __forceinline__ void dct4_inplace(float *v) {
     v[3 * S] = fmaf(d0, IE_C6, -(d1 * IE_C2));
 }
 
+// inverse of the above (unnormalised DCT-III): x[i] = sum_u y[u] cos((2i+1) u pi / 16)
+template <int S>
+__device__ __forceinline__ void idct8_inplace(float *v) {
+    const float y0 = v[0 * S], y1 = v[1 * S], y2 = v[2 * S], y3 = v[3 * S], y4 = v[4 * S], y5 = v[5 * S], y6 = v[6 * S], y7 = v[7 * S];
+    const float t4 = y4 * IE_C4;
+    const float a = y0 + t4, b = y0 - t4;
+    const float p = fmaf(y2, IE_C2, y6 * IE_C6), q = fmaf(y2, IE_C6, -(y6 * IE_C2));
+    const float e0 = a + p, e3 = a - p, e1 = b + q, e2 = b - q;
+    const float o0 = fmaf(y1, IE_C1, fmaf(y3, IE_C3, fmaf(y5, IE_C5, y7 * IE_C7)));
+    const float o1 = fmaf(y1, IE_C3, fmaf(y3, -IE_C7, fmaf(y5, -IE_C1, y7 * -IE_C5)));
+    const float o2 = fmaf(y1, IE_C5, fmaf(y3, -IE_C1, fmaf(y5, IE_C7, y7 * IE_C3)));
+    const float o3 = fmaf(y1, IE_C7, fmaf(y3, -IE_C5, fmaf(y5, IE_C3, y7 * -IE_C1)));
+    v[0 * S] = e0 + o0; v[7 * S] = e0 - o0;
+    v[1 * S] = e1 + o1; v[6 * S] = e1 - o1;
+    v[2 * S] = e2 + o2; v[5 * S] = e2 - o2;
+    v[3 * S] = e3 + o3; v[4 * S] = e3 - o3;
+}
+
+template <int S>
+__device__ __forceinline__ void idct4_inplace(float *v) {
+    const float y0 = v[0 * S], y1 = v[1 * S], y2 = v[2 * S], y3 = v[3 * S];
+    const float t2 = y2 * IE_C4;
+    const float a = y0 + t2, b = y0 - t2;
+    const float p = fmaf(y1, IE_C2, y3 * IE_C6), q = fmaf(y1, IE_C6, -(y3 * IE_C2));
+    v[0 * S] = a + p; v[3 * S] = a - p; v[1 * S] = b + q; v[2 * S] = b - q;
+}
+
+template <int N>
+__device__ __forceinline__ void idct2d_fast(float *x) {
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        if (N == 8) idct8_inplace<1>(x + u * N); else idct4_inplace<1>(x + u * N);
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        if (N == 8) idct8_inplace<N>(x + j); else idct4_inplace<N>(x + j);
+    }
+}
+
 template <int N>
 __device__ __forceinline__ void fdct2d_fast(float *x) {
 #pragma unroll

@@ -150,3 +150,37 @@ def test_fast_path_equals_exact_path_at_scale(gpu):
         finally:
             L.ie_set_option(b"exact_transform", 0)
         assert fast == exact, f"{name}: fast path differs from the exact path"
+
+
+def test_fast_decode_equals_exact_decode_at_scale(gpu, oracle_mod):
+    """the guarded FP32 inverse transform and the exact-order FP64 one give identical pixels (images and P-frames)"""
+    from imageencoder_b200.synth import synth_image, synth_video
+    L = gpu.lib()
+    rng = np.random.default_rng(4)
+    cases = [(synth_image(4096, 4096, 1234), gpu.read_matrix(INPUTS / "matrix8_1.txt")),
+             (synth_image(2048, 2048, 77, flat=True), gpu.read_matrix(INPUTS / "matrix8_2.txt")),
+             (synth_image(2048, 1024, 2001), gpu.read_matrix(INPUTS / "matrix.txt")),
+             (rng.integers(0, 256, (512, 512)).astype(np.uint8), np.ones((8, 8), np.uint16)),
+             (rng.integers(0, 256, (512, 512)).astype(np.uint8), np.ones((4, 4), np.uint16))]
+    for img, q in cases:
+        H, W = img.shape
+        N = q.shape[0]
+        enc = gpu.encode_image(img, W, H, q, True, False)
+        fast = gpu.decode_image(enc, N)
+        L.ie_set_option(b"exact_transform", 1)
+        try:
+            exact = gpu.decode_image(enc, N)
+        finally:
+            L.ie_set_option(b"exact_transform", 0)
+        assert np.array_equal(fast, exact)
+    yuv = synth_video(256, 192, 8, 4000)
+    q = gpu.read_matrix(INPUTS / "matrix.txt")
+    enc = gpu.encode_video(yuv, 256, 192, q, True, 4, 16, False)
+    fast = gpu.decode_video(enc, True)[0].copy()
+    L.ie_set_option(b"exact_transform", 1)
+    try:
+        exact = gpu.decode_video(enc, True)[0].copy()
+    finally:
+        L.ie_set_option(b"exact_transform", 0)
+    assert np.array_equal(fast, exact)
+    assert np.array_equal(fast, oracle_mod.video_decode(enc, True)[0])
