@@ -252,8 +252,10 @@ struct HuffDecodeTables {
 };
 
 __global__ void huff_decode_kernel(const uint8_t *__restrict__ in, size_t n, unsigned long long start_bit,
-                                   const HuffDecodeTables *tab, uint8_t *out, size_t out_cap, unsigned long long *out_count, int *err) {
+                                   const HuffDecodeTables *tab, uint8_t *out, size_t out_cap, unsigned long long *out_count, int *err,
+                                   const unsigned *spec_ok) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (spec_ok && *spec_ok) return;                 // the parallel decode verified: nothing to do
     const unsigned long long total = (unsigned long long)n * 8ull;
     unsigned long long pos = start_bit;
     size_t o = 0;
@@ -290,6 +292,145 @@ __global__ void huff_decode_kernel(const uint8_t *__restrict__ in, size_t n, uns
         pos = min(pos + len, total);              // a final code may run past the end: zero bits, no advance
     }
     *out_count = o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Parallel decode: speculate + verify (same scheme as the block parser, parse.cu).  The code stream is cut into groups of
+// kHuffGroupBits bits.  Huffman codes re-synchronise quickly, so every group starts kHuffLead bits early at an arbitrary
+// bit and ASSUMES it is on a codeword boundary when it reaches its first bit; the assumption is then verified exactly
+// (group g's entry offset must equal group g-1's exit offset; group 0 starts at the true first code).  Mismatching groups
+// are re-walked from their predecessor's exit for a few rounds; if any mismatch remains, spec_ok stays 0 and the serial
+// kernel above decodes instead.  Symbol counts per group are scanned to place every group's symbols in the output.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kHuffGroupBits = 8192;
+constexpr int kHuffLead = 2048;
+constexpr int kHuffRounds = 3;
+constexpr unsigned kHuffDead = 0xFFFFFFFFu;
+
+struct HuffParParams {
+    const uint8_t *in;                 // 4-byte aligned
+    unsigned long long total;          // bits
+    unsigned long long start_bit;      // first code
+    const HuffDecodeTables *tab;
+    unsigned ngroups;
+    uint2 *entry;                      // [ngroups] (entry offset, first symbol index)
+    uint2 *exit_;                      // [ngroups] (exit offset | dead, symbols started in the group)
+    unsigned *flags;                   // [1] spec_ok
+    uint8_t *out;
+    size_t out_cap;
+    unsigned long long *out_count;
+    int *err;
+};
+
+// length of the code at absolute bit p (p < total) and its symbol; len 0 = no such code (garbage phase or malformed)
+__device__ __forceinline__ unsigned huff_code_at(const HuffParParams &p, unsigned long long pos, unsigned &sym) {
+    const unsigned *wp = reinterpret_cast<const unsigned *>(p.in) + (pos >> 5);
+    const unsigned long long nwords = (p.total + 31) >> 5;
+    const unsigned w0 = __byte_perm(__ldg(wp), 0, 0x0123);
+    const unsigned w1 = ((pos >> 5) + 1 < nwords) ? __byte_perm(__ldg(wp + 1), 0, 0x0123) : 0u;
+    unsigned w32 = __funnelshift_l(w1, w0, (unsigned)(pos & 31));
+    if (pos + 32 > p.total) w32 &= ~((p.total - pos >= 32) ? 0u : (0xFFFFFFFFu >> (unsigned)(p.total - pos)));   // zero bits past the end
+    const unsigned e = __ldg(&p.tab->lut[w32 >> 20]);
+    if ((e >> 16) != 0xFFFFu) { sym = e & 0xffffu; return e >> 16; }        // e == 0 -> len 0
+    int node = (int)(e & 0xffffu);
+    unsigned len = 12;
+    while (len < 32) {
+        const int c = p.tab->child[node][(w32 >> (31 - len)) & 1];
+        len++;
+        if (c == -1) return 0u;
+        if (c <= -2) { sym = (unsigned)(-c - 2); return len; }
+        node = c;
+    }
+    return 0u;
+}
+
+// decodes from absolute bit pos to the end of the group; optionally writes the symbols
+__device__ __forceinline__ uint2 huff_walk_group(const HuffParParams &p, unsigned long long pos, unsigned long long g_end, uint8_t *dst, size_t dst_cap) {
+    unsigned cnt = 0;
+    while (true) {
+        if (pos >= p.total) return make_uint2(kHuffDead, cnt);
+        if (pos >= g_end) return make_uint2((unsigned)(pos - g_end), cnt);
+        unsigned sym = 0;
+        const unsigned len = huff_code_at(p, pos, sym);
+        if (len == 0) return make_uint2(kHuffDead - 1, cnt);               // malformed on this phase
+        if (dst) { if (cnt < dst_cap) dst[cnt] = (uint8_t)sym; }
+        cnt++;
+        pos += len;                                                        // a final code may run past the end (zero bits)
+    }
+}
+
+__global__ void __launch_bounds__(64) huff_spec_walk(const HuffParParams p) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) p.flags[0] = 0;
+    if (g >= p.ngroups) return;
+    const unsigned long long g_start = p.start_bit + (unsigned long long)g * kHuffGroupBits, g_end = g_start + kHuffGroupBits;
+    unsigned entry;
+    unsigned long long pos = (g == 0) ? p.start_bit : g_start - kHuffLead;
+    if (g_start >= p.total) entry = kHuffDead;
+    else {
+        while (pos < g_start) {
+            unsigned sym;
+            const unsigned len = huff_code_at(p, pos, sym);
+            pos += len ? len : 1u;
+        }
+        entry = (pos >= p.total) ? kHuffDead : (unsigned)(pos - g_start);
+    }
+    p.entry[g] = make_uint2(entry, 0u);
+    p.exit_[g] = (entry == kHuffDead) ? make_uint2(kHuffDead, 0u) : huff_walk_group(p, pos, g_end, nullptr, 0);
+}
+
+__global__ void __launch_bounds__(64) huff_spec_repair(const HuffParParams p) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.ngroups || g == 0) return;
+    if (g >= 2 && p.exit_[g - 2].x != p.entry[g - 1].x) return;            // only adopt the exit of a consistent predecessor
+    const unsigned want = p.exit_[g - 1].x;
+    if (want == p.entry[g].x) return;
+    const unsigned long long g_start = p.start_bit + (unsigned long long)g * kHuffGroupBits, g_end = g_start + kHuffGroupBits;
+    p.entry[g] = make_uint2(want, 0u);
+    p.exit_[g] = (want >= kHuffDead - 1) ? make_uint2(kHuffDead, 0u) : huff_walk_group(p, g_start + want, g_end, nullptr, 0);
+}
+
+__global__ void __launch_bounds__(1024) huff_spec_finish(const HuffParParams p) {
+    __shared__ unsigned s_bad;
+    __shared__ unsigned long long s_sum[1024];
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    const unsigned per = (p.ngroups + 1023) / 1024;
+    const unsigned g0 = threadIdx.x * per, g1 = min(g0 + per, p.ngroups);
+    unsigned long long sum = 0;
+    unsigned bad = 0;
+    for (unsigned g = g0; g < g1; g++) {
+        if (g > 0 && p.exit_[g - 1].x != p.entry[g].x) bad = 1;
+        if (p.exit_[g].x == kHuffDead - 1) bad = 1;                        // malformed code on the (supposedly) true chain
+        sum += p.exit_[g].y;
+    }
+    if (bad) atomicOr(&s_bad, 1u);
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned long long v = (threadIdx.x >= (unsigned)d) ? s_sum[threadIdx.x - d] : 0ull;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    if (s_bad) return;                                                    // spec_ok stays 0: the serial kernel decodes
+    unsigned long long base = s_sum[threadIdx.x] - sum;
+    for (unsigned g = g0; g < g1; g++) {
+        p.entry[g].y = (unsigned)base;                                     // first symbol index of the group (< 2^32 checked by the host)
+        base += p.exit_[g].y;
+    }
+    if (threadIdx.x == 1023) *p.out_count = s_sum[1023];
+    if (threadIdx.x == 0) p.flags[0] = 1;
+}
+
+__global__ void __launch_bounds__(64) huff_spec_emit(const HuffParParams p) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.ngroups || !p.flags[0]) return;
+    const uint2 en = p.entry[g];
+    if (en.x == kHuffDead) return;
+    const unsigned long long g_start = p.start_bit + (unsigned long long)g * kHuffGroupBits, g_end = g_start + kHuffGroupBits;
+    if ((size_t)en.y + p.exit_[g].y > p.out_cap) { atomicExch(p.err, IE_ENOSPC); return; }
+    huff_walk_group(p, g_start + en.x, g_end, p.out + en.y, p.out_cap - en.y);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -529,7 +670,25 @@ int ie_huffman_decode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
     HuffDecodeTables *d_tab = reinterpret_cast<HuffDecodeTables *>(s->d_scratch);
     unsigned long long *d_count = reinterpret_cast<unsigned long long *>(s->d_scratch + tab_bytes);
     IE_CUDA(cudaMemcpyAsync(d_tab, &t, sizeof t, cudaMemcpyHostToDevice, st));
-    huff_decode_kernel<<<1, 32, 0, st>>>(d_in, n, (unsigned long long)pos, d_tab, d_out, out_cap, d_count, s->d_err);
+    {
+        if ((uintptr_t)d_in % 4) { set_error("Huffman stream must be 4-byte aligned"); return IE_EINVAL; }
+        HuffParParams hp;
+        hp.in = d_in; hp.total = (unsigned long long)n * 8ull; hp.start_bit = (unsigned long long)pos; hp.tab = d_tab;
+        hp.ngroups = (unsigned)((hp.total - std::min<unsigned long long>(hp.total, hp.start_bit) + kHuffGroupBits - 1) / kHuffGroupBits + 1);
+        const size_t need_par = (size_t)hp.ngroups * 2 * sizeof(uint2) + 64;
+        IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, need_par));
+        hp.entry = reinterpret_cast<uint2 *>(s->d_parse);
+        hp.exit_ = hp.entry + hp.ngroups;
+        hp.flags = reinterpret_cast<unsigned *>(hp.exit_ + hp.ngroups);
+        hp.out = d_out; hp.out_cap = out_cap; hp.out_count = d_count; hp.err = s->d_err;
+        const unsigned gb = (hp.ngroups + 63) / 64;
+        huff_spec_walk<<<gb, 64, 0, st>>>(hp);
+        for (int r = 0; r < kHuffRounds; r++) huff_spec_repair<<<gb, 64, 0, st>>>(hp);
+        huff_spec_finish<<<1, 1024, 0, st>>>(hp);
+        huff_spec_emit<<<gb, 64, 0, st>>>(hp);
+        huff_decode_kernel<<<1, 32, 0, st>>>(d_in, n, (unsigned long long)pos, d_tab, d_out, out_cap, d_count, s->d_err, hp.flags);
+        count_launch(4 + kHuffRounds);
+    }
     count_launch();
     IE_CUDA(cudaGetLastError());
     IE_CUDA(cudaMemcpyAsync(s->h_pinned, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
