@@ -24,10 +24,10 @@ namespace ie {
 
 // Sub-span boundaries inside a group: short spans first, so that the E hypothetical chains of a group are merged after
 // a block or two instead of each being walked through kilobits of stream.
-constexpr int kSubsPerGroup = 12;
-__constant__ int c_sub_bounds[kSubsPerGroup + 1] = {0, 256, 512, 1024, 1536, 2048, 3072, 4096, 8192, 12288, 16384, 24576, 32768};
-constexpr int kGroupBits = 32768;                        // 4 KiB of stream per group
-constexpr int kSuper = 64;                               // groups per super-group (256 KiB of stream)
+constexpr int kSubsPerGroup = 9;
+__constant__ int c_sub_bounds[kSubsPerGroup + 1] = {0, 256, 512, 1024, 1536, 2048, 3072, 4096, 6144, 8192};
+constexpr int kGroupBits = 8192;                         // 1 KiB of stream per group
+constexpr int kSuper = 128;                              // groups per super-group (128 KiB of stream)
 constexpr unsigned kDead = 0xFFFFu;
 
 struct ParseParams {
@@ -165,13 +165,13 @@ __global__ void __launch_bounds__(64) parse_down_super(const ParseParams p) {
 // ---------------------------------------------------------------------------------------------------------
 // Speculative fast path.  Real streams re-synchronise: a walk started at an arbitrary bit lands on the true chain after
 // a few kilobits (measured: all 1044 entry offsets of a group merge into ONE chain within 3072 bits).  So every group
-// starts kSpecLead bits early at an arbitrary position and *assumes* it is on the true chain when it reaches its first bit.
+// starts a lead-in (4096 or 8192 bits) early at an arbitrary position and *assumes* it is on the true chain when it reaches its first bit.
 // The assumption is then VERIFIED exactly: group g's speculative entry must equal group g-1's exit; group 0 starts at the
 // true first block, so if all neighbours agree every group is on the true chain (induction).  Groups that disagree are
 // re-walked from their predecessor's exit (a few rounds); if disagreement remains, spec_ok stays 0 and the exact
 // transfer-function kernels above do the work instead (they return immediately when spec_ok is 1).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSpecLead = 8192;
+// lead-in before a group's first bit (measured on 8x8 streams: 4096 bits leave 3 % of the groups unsynchronised, 8192 none)
 constexpr int kSpecRounds = 3;
 
 // walks the chain from absolute bit `pos` (inside or before the group) to the group's end
@@ -189,12 +189,13 @@ __device__ __forceinline__ uint2 walk_group(const ParseParams &p, unsigned long 
 
 __global__ void __launch_bounds__(64) parse_spec_walk(const ParseParams p) {
     const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g == 0 && threadIdx.x == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; }
+    if (g == 0 && threadIdx.x == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; p.spec_flags[2] = 0; }
     if (g >= p.ngroups) return;
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
     const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
-    unsigned long long pos = (g == 0) ? B0 : g_start - kSpecLead;
+    const unsigned lead = (p.NN == 64) ? 8192u : 4096u;
+    unsigned long long pos = (g == 0 || g_start < B0 + lead) ? B0 : g_start - lead;
     unsigned entry;
     if (g_start >= total) { entry = kDead; }
     else {
@@ -228,20 +229,21 @@ __global__ void __launch_bounds__(64) parse_spec_repair(const ParseParams p, int
     p.spec_exit[g] = (want == kDead || want >= (unsigned)kGroupBits) ? make_uint2(kDead, 0u) : walk_group(p, total, g_start + want, g_end);
 }
 
-// final exact verification + exclusive scan of the per-group block counts (single CTA)
+// final exact verification + exclusive scan of the per-group block counts (single CTA).  Only the groups that hold the
+// stream's nblocks blocks have to be consistent: behind the last block the chain runs into whatever follows (pad bits, the
+// next frame's motion vectors), where the speculative walks may legitimately disagree.
 __global__ void __launch_bounds__(1024) parse_spec_finish(const ParseParams p) {
-    __shared__ unsigned s_bad;
+    __shared__ unsigned s_firstbad;
     __shared__ unsigned s_sum[1024];
-    if (threadIdx.x == 0) s_bad = 0;
+    if (threadIdx.x == 0) s_firstbad = p.ngroups;
     __syncthreads();
     const unsigned per = (p.ngroups + 1023) / 1024;
     const unsigned g0 = threadIdx.x * per, g1 = min(g0 + per, p.ngroups);
-    unsigned sum = 0, bad = 0;
+    unsigned sum = 0;
     for (unsigned g = g0; g < g1; g++) {
-        if (g > 0 && p.spec_exit[g - 1].x != p.group_entry[g].x) bad = 1;
+        if (g > 0 && p.spec_exit[g - 1].x != p.group_entry[g].x) atomicMin(&s_firstbad, g);
         sum += p.spec_exit[g].y;
     }
-    if (bad) atomicOr(&s_bad, 1u);
     s_sum[threadIdx.x] = sum;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1) {                    // Hillis-Steele inclusive scan
@@ -250,14 +252,18 @@ __global__ void __launch_bounds__(1024) parse_spec_finish(const ParseParams p) {
         s_sum[threadIdx.x] += v;
         __syncthreads();
     }
-    if (s_bad) return;                                      // spec_ok stays 0: the exact kernels run
+    const unsigned firstbad = s_firstbad;
     unsigned base = s_sum[threadIdx.x] - sum;
     for (unsigned g = g0; g < g1; g++) {
         const uint2 ge = p.group_entry[g];
-        p.group_entry[g] = make_uint2(ge.x, base);
+        // groups from the first inconsistent one on are switched off (they only hold blocks beyond nblocks, checked below)
+        p.group_entry[g] = make_uint2(g >= firstbad ? kDead : ge.x, base);
+        if (g == firstbad && base < p.nblocks) p.spec_flags[2] = 1;         // a needed group is unverified: not usable
         base += p.spec_exit[g].y;
     }
-    if (threadIdx.x == 0) p.spec_flags[1] = 1;
+    __syncthreads();
+    __threadfence_block();
+    if (threadIdx.x == 0) p.spec_flags[1] = p.spec_flags[2] ? 0u : 1u;
 }
 
 __global__ void __launch_bounds__(64) parse_emit_offsets(const ParseParams p) {
