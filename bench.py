@@ -237,6 +237,32 @@ def ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
 
+    # ---- decode of the same stream (second half of BASELINE's "encode/decode Mpixels/s"), device-resident, rank-local
+    dec_ms = None
+    try:
+        sess_d = device.Session(device.Session.IMAGE_DECODE, W, H, BLOCK)
+        d_dec = torch.empty(W * H, dtype=torch.uint8, device="cuda")
+        if sharded is None:
+            d_stream, nb = d_out[0], out_bytes[0]
+        else:
+            # a shard stream has no header of its own except on rank 0: decode rank 0's shard only as a per-rank figure
+            d_stream, nb = sharded[0].d_local, int((int(sharded[0].d_bits.item()) + 7) // 8)
+        if rank == 0 or sharded is None:
+            for _ in range(2):
+                device.decode_image_dev(sess_d, d_stream, nb, d_dec, 1)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            a.record()
+            for _ in range(reps):
+                device.decode_image_dev(sess_d, d_stream, nb, d_dec, 1)
+            b.record()
+            torch.cuda.synchronize()
+            dec_ms = a.elapsed_time(b) / reps
+    except Exception as e:      # decode is an extra figure; never fail the encode bench on it
+        dec_ms = None
+        dec_err = str(e)
+
     # ---- e2e: the public host-buffer call (pinned host memory in, pinned host memory out), copies inside the region
     h_raw = torch.from_numpy(base).reshape(-1).pin_memory()
     h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
@@ -287,6 +313,9 @@ def ours(args):
                     "api": "ie_encode_image (C-ABI, pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "decode": ({"value": px / (dec_ms / 1e3) / 1e6, "unit": "Mpixels/s", "ms": dec_ms, "n_gpus": 1,
+                        "what": "ie_decode_image_dev of rank 0's stream (parallel parse + guarded inverse transform), HBM-resident, "
+                                "includes one 160-byte header read-back"} if dec_ms else None),
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
