@@ -1,5 +1,6 @@
 // C-ABI: sessions and the image entry points (host-buffer and device-resident).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -142,6 +143,7 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     p.src = d_raw; p.pitch = W; p.img_stride = img_stride;
     p.bx = W / N; p.nblocks = nblocks; p.tiles_per_image = tiles;
     p.use_rle = use_rle ? 1 : 0; p.bits_only = bits_only;
+    { static const char *dbg = getenv("IE_DEBUG_SKIP"); p.debug_skip = dbg ? atoi(dbg) : 0; }
     make_quant(p.quant, quant, N);
     make_fast_quant(p.fq, quant, N, 128.0);
     p.dc_den2 = 8 * (int)quant[0]; p.dc_rcp = 1.0f / (float)p.dc_den2;
@@ -149,6 +151,15 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     p.out = d_out; p.out_stride = out_stride; p.out_cap = out_cap;
     p.bit_counter = s->d_counter; p.err = s->d_err;
     p.scan = s->scan_state();
+    {
+        const size_t ntot = (size_t)images * tiles;
+        p.slot_bytes = encode_tile_slot_bytes(N);
+        if (!bits_only) IE_TRY(session_reserve(&s->d_tile_scratch, &s->tile_scratch_cap, ntot * p.slot_bytes));
+        IE_TRY(session_reserve(&s->d_tile_meta, &s->tile_meta_cap, ntot * (sizeof(unsigned long long) + sizeof(unsigned)) + 64));
+        p.tile_scratch = s->d_tile_scratch;
+        p.tile_off = reinterpret_cast<unsigned long long *>(s->d_tile_meta);
+        p.tile_bits = reinterpret_cast<unsigned *>(s->d_tile_meta + ntot * sizeof(unsigned long long));
+    }
     // scan arrays are indexed [image][tile] with stride tiles_per_image (the allocation is at least that large)
     return launch_encode_tiles(N, p, images, stream);
 }
@@ -279,7 +290,7 @@ int ie_session_create(ie_session **out, int kind, uint32_t W, uint32_t H, uint32
 void ie_session_destroy(ie_session *s) {
     if (!s) return;
     cudaFree(s->d_tile_state); cudaFree(s->d_bnd); cudaFree(s->d_ticket); cudaFree(s->d_counter); cudaFree(s->d_err);
-    cudaFree(s->d_block_off); cudaFree(s->d_parse); cudaFree(s->d_scratch); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_tmp);
+    cudaFree(s->d_block_off); cudaFree(s->d_parse); cudaFree(s->d_tile_scratch); cudaFree(s->d_tile_meta); cudaFree(s->d_scratch); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_tmp);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;

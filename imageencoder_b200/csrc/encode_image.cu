@@ -113,8 +113,6 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
     unsigned *s_stats = reinterpret_cast<unsigned *>(s_queue + kQueueCap);          // [TB] packed RLE info of patched blocks
     unsigned short *s_dlist = reinterpret_cast<unsigned short *>(s_stats + TB);      // [kQueueCap + TB] patched blocks (duplicates allowed)
     __shared__ unsigned s_warp[kThreads / 32 + 1];
-    __shared__ unsigned long long s_bcast;
-    __shared__ unsigned s_tile;
     __shared__ unsigned s_qn, s_nd;
 
     const unsigned img = blockIdx.y;
@@ -123,9 +121,12 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
     st.bnd += (size_t)img * p.tiles_per_image;
     st.ticket += img;
 
-    if (threadIdx.x == 0) { s_tile = atomicAdd(st.ticket, 1u); s_qn = 0; s_nd = 0; }
+    // Tile id = blockIdx.x: CTAs of a 1-D grid row are dispatched in increasing index order (the same assumption CUB's
+    // single-pass scan makes), so every predecessor of a spinning tile is resident or done.  (A ticket atomic costs a
+    // global round trip at the start of every tile.)
+    if (threadIdx.x == 0) { s_qn = 0; s_nd = 0; }
     __syncthreads();
-    const unsigned tile = s_tile;
+    const unsigned tile = blockIdx.x;
     const unsigned ntiles = p.tiles_per_image;
     const unsigned first_blk = tile * TB;
     const int nblk = min((unsigned)TB, p.nblocks - first_blk);
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
 
     // ---- phase 1b: exact recomputation of the queued guard-band coefficients, one per thread -------------------
     if (FAST) {
-        const unsigned qn = min(s_qn, (unsigned)kQueueCap);
+        const unsigned qn = (p.debug_skip & 1) ? 0u : min(s_qn, (unsigned)kQueueCap);
         if (qn) {                                                              // uniform
             for (unsigned e = threadIdx.x; e < qn; e += kThreads) {
                 const unsigned ent = s_queue[e];
@@ -353,12 +354,8 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
         excl += b;
     }
     if (threadIdx.x == kThreads - 1) s_off[TB] = T;
-    unsigned long long base = 0;
-    if (tile == 0) base = p.bit_counter[img];
-    // publish this tile's bit total right away; the prefix is only needed for the copy-out, after the local packing
-    if (threadIdx.x == 0) tile_publish_aggregate(st, tile, (unsigned long long)T + base);
     const bool last_tile = (tile == ntiles - 1);
-    unsigned long long G = 0;
+    (void)last_tile;
 
     // ---- phase 3: pack ---------------------------------------------------------------------------------------
     // Block-centric: every lane writes its block's fields MSB-first into a shared-memory image of the tile's bits (tile
@@ -373,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
 #pragma unroll 1
         for (int r = 0; r < BPL; r++) {
             const int lb = threadIdx.x * BPL + r;
-            if (lb >= nblk) break;
+            if (lb >= nblk || (p.debug_skip & 2)) break;
             const int w = s_w[lb], len = s_len[lb];
             const unsigned pos = s_off[lb];
             const unsigned bo = pos & 31u;
@@ -383,42 +380,105 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
             // header: bit_len (low 4 bits survive, Block.cpp:381) and, with RLE, the length field (Block.cpp:393)
             unsigned long long acc = p.use_rle ? ((((unsigned long long)w & 15ull) << w) | (unsigned long long)len) : ((unsigned long long)w & 15ull);
             int nacc = (int)bo + 4 + (p.use_rle ? w : 0);
-            bool shared_word = (bo != 0);       // the first word also holds bits of the previous block(s)
-#define IE_EMIT_WORD()                                                                     \
-            do {                                                                               \
-                const unsigned word_ = (unsigned)(acc >> (nacc - 32));                         \
-                if (shared_word) { atomicOr(ow, word_); shared_word = false; } else { *ow = word_; } \
-                ow++;                                                                          \
-                nacc -= 32;                                                                    \
-            } while (0)
-            if (nacc >= 32) IE_EMIT_WORD();
             const int nfull = len >> 1;
-            for (int j = 0; j < nfull; j++) {                                                  // coefficient pairs (2j, 2j+1)
-                const unsigned x2 = cw[j];
-                const unsigned v = ((x2 & mask) << w) | ((x2 >> 16) & mask);
-                acc = (acc << (2 * w)) | v;
-                nacc += 2 * w;
-                if (nacc >= 32) IE_EMIT_WORD();
+            const int s2 = 2 * w;
+            int j = 0;
+            bool odd_left = (len & 1) != 0;
+            // stage A: up to the first completed word -- the only one that can hold bits of the previous block(s)
+            while (nacc < 32 && j < nfull) {
+                const unsigned x2 = cw[j++];
+                acc = (acc << s2) | (((x2 & mask) << w) | ((x2 >> 16) & mask));
+                nacc += s2;
             }
-            if (len & 1) {
-                acc = (acc << w) | (cw[nfull] & mask);
-                nacc += w;
-                if (nacc >= 32) IE_EMIT_WORD();
+            if (nacc < 32 && odd_left) { acc = (acc << w) | (cw[nfull] & mask); nacc += w; odd_left = false; }
+            if (nacc >= 32) {
+                const unsigned word = (unsigned)(acc >> (nacc - 32));
+                if (bo) atomicOr(ow, word); else *ow = word;
+                ow++;
+                nacc -= 32;
+                // stage B: whole words that belong to this block alone
+                for (; j < nfull; j++) {
+                    const unsigned x2 = cw[j];
+                    acc = (acc << s2) | (((x2 & mask) << w) | ((x2 >> 16) & mask));
+                    nacc += s2;
+                    if (nacc >= 32) { nacc -= 32; *ow++ = (unsigned)(acc >> nacc); }
+                }
+                if (odd_left) {
+                    acc = (acc << w) | (cw[nfull] & mask);
+                    nacc += w;
+                    if (nacc >= 32) { nacc -= 32; *ow++ = (unsigned)(acc >> nacc); }
+                }
             }
-#undef IE_EMIT_WORD
             if (nacc > 0) atomicOr(ow, (unsigned)(acc << (32 - nacc)));                        // tail shared with the next block
         }
-        G = tile_resolve_prefix(st, tile, (unsigned long long)T, &s_bcast) + (tile == 0 ? base : 0ull);   // syncs the CTA
-        SmemStreamTile stt;
-        stt.words = s_outw; stt.nwords = nwords;
-        tile_write_chunks(stt, st, tile, tile == 0, last_tile, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
-    } else {
-        G = tile_resolve_prefix(st, tile, (unsigned long long)T, &s_bcast) + (tile == 0 ? base : 0ull);
+        __syncthreads();
+        // the tile's image goes to its slot of the scratch buffer; tile_copyout_kernel re-aligns it into the stream once the
+        // exclusive scan of the tile totals is known (no inter-CTA dependency in this kernel: no look-back wait)
+        uint4 *slot = reinterpret_cast<uint4 *>(p.tile_scratch + ((size_t)img * ntiles + tile) * p.slot_bytes);
+        for (unsigned c = threadIdx.x; c < (nwords + 3) / 4; c += kThreads) slot[c] = s_out[c];
     }
-    if (last_tile && threadIdx.x == 0) {
-        p.bit_counter[img] = G + T;
-        atomicExch(st.ticket, 0u);                 // every ticket of this launch has been taken
+    if (threadIdx.x == 0) p.tile_bits[(size_t)img * ntiles + tile] = T;
+}
+
+// exclusive scan of the tile bit totals of one stream (one CTA per stream): tile_off[t] = first bit of tile t in the stream
+__global__ void __launch_bounds__(1024) tile_offsets_kernel(const unsigned *__restrict__ tile_bits, unsigned long long *tile_off,
+                                                            unsigned ntiles, unsigned long long *bit_counter) {
+    __shared__ unsigned long long s_sum[1024];
+    const unsigned img = blockIdx.x;
+    tile_bits += (size_t)img * ntiles;
+    tile_off += (size_t)img * ntiles;
+    const unsigned per = (ntiles + 1023) / 1024;
+    const unsigned t0 = threadIdx.x * per, t1 = min(t0 + per, ntiles);
+    unsigned long long sum = 0;
+    for (unsigned t = t0; t < t1; t++) sum += tile_bits[t];
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned long long v = (threadIdx.x >= (unsigned)d) ? s_sum[threadIdx.x - d] : 0ull;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
     }
+    const unsigned long long base = bit_counter[img];
+    unsigned long long run = base + s_sum[threadIdx.x] - sum;
+    for (unsigned t = t0; t < t1; t++) { tile_off[t] = run; run += tile_bits[t]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) bit_counter[img] = base + s_sum[1023];
+}
+
+// Tile image in global scratch (tile-local alignment, 32 stream bits per word, MSB first, zero beyond the last bit)
+struct GlobalStreamTile {
+    const unsigned *words;
+    unsigned nwords;
+};
+__device__ __forceinline__ uint4 gather_chunk(const GlobalStreamTile &t, long long ls) {
+    const long long wi = ls >> 5;
+    const unsigned sh = (unsigned)(ls & 31);
+    unsigned w[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const long long i = wi + k;
+        w[k] = (i >= 0 && i < (long long)t.nwords) ? __ldg(t.words + i) : 0u;
+    }
+    uint4 o;
+    o.x = __byte_perm(__funnelshift_l(w[1], w[0], sh), 0, 0x0123);
+    o.y = __byte_perm(__funnelshift_l(w[2], w[1], sh), 0, 0x0123);
+    o.z = __byte_perm(__funnelshift_l(w[3], w[2], sh), 0, 0x0123);
+    o.w = __byte_perm(__funnelshift_l(w[4], w[3], sh), 0, 0x0123);
+    return o;
+}
+
+__global__ void __launch_bounds__(kThreads) tile_copyout_kernel(const EncodeParams p) {
+    const unsigned img = blockIdx.y, tile = blockIdx.x, ntiles = p.tiles_per_image;
+    const size_t ti = (size_t)img * ntiles + tile;
+    const unsigned T = p.tile_bits[ti];
+    const unsigned long long G = p.tile_off[ti];
+    ScanState st = p.scan;
+    st.bnd += (size_t)img * ntiles;
+    GlobalStreamTile gt;
+    gt.words = reinterpret_cast<const unsigned *>(p.tile_scratch + ti * p.slot_bytes);
+    gt.nwords = (T + 31) / 32;
+    tile_write_chunks(gt, st, tile, tile == 0, tile == ntiles - 1, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
 }
 
 template <int N, int BPL, bool PF, bool FAST>
@@ -435,12 +495,21 @@ static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t strea
     }
     dim3 grid(p.tiles_per_image, images);
     encode_tiles_kernel<N, BPL, PF, FAST><<<grid, kThreads, smem, stream>>>(p);
-    count_launch();
+    tile_offsets_kernel<<<images, 1024, 0, stream>>>(p.tile_bits, p.tile_off, p.tiles_per_image, p.bit_counter);
+    count_launch(2);
+    if (!p.bits_only) {
+        tile_copyout_kernel<<<grid, kThreads, 0, stream>>>(p);
+        count_launch();
+    }
     IE_CUDA(cudaGetLastError());
     return IE_OK;
 }
 
 unsigned encode_tile_blocks(int N) { return N == 8 ? kThreads * 1 : kThreads * 4; }
+size_t encode_tile_slot_bytes(int N) {
+    const size_t tb = encode_tile_blocks(N);
+    return ((tb * (4 + 16 + 16 * (size_t)N * N) + 127) / 128 + 2) * 16;
+}
 
 std::atomic<int> g_exact_transform{0};
 

@@ -16,6 +16,7 @@ struct EncodeParams {
     unsigned tiles_per_image;
     int use_rle;
     int bits_only;                    // 1: only the bit totals (first pass of a sharded encode)
+    int debug_skip;                   // timing experiments only (IE_DEBUG_SKIP): 1 skip exact queue, 2 skip pack loop, 4 skip copy-out
     QuantParam quant;
     FastQuant fq;                     // fast-path constants + guard-band thresholds (transform_fast.cuh)
     int dc_den2;                      // 2 * 4 * Q[0][0]: exact integer DC rounding
@@ -26,7 +27,11 @@ struct EncodeParams {
     size_t out_cap;                   // bytes per stream
     unsigned long long *bit_counter;  // [images] in: first free bit of the stream, out: one past the last written bit
     int *err;                         // device error flag
-    ScanState scan;
+    ScanState scan;                   // only the tile-boundary hand-off records are used by the image path
+    uint8_t *tile_scratch;            // [images * tiles] slots of slot_bytes: packed tile images (tile-local alignment)
+    size_t slot_bytes;
+    unsigned *tile_bits;              // [images * tiles] bits per tile
+    unsigned long long *tile_off;     // [images * tiles] first bit of every tile in its stream
     // P-frame mode (Frame.cpp:160-244): src is the CURRENT frame (read, then overwritten with the reconstruction),
     // ref the previous frame as the encoder left it; per-MacroBlock pixel coordinates of the block the residual is
     // taken from (res_coord, Block.cpp:337) and of the block copied in (copy_coord, Frame.cpp:218-225).
@@ -38,6 +43,7 @@ struct EncodeParams {
 };
 
 unsigned encode_tile_blocks(int N);
+size_t encode_tile_slot_bytes(int N);      // bytes of scratch per tile
 extern std::atomic<int> g_exact_transform;
 // max_abs_sample: 128 for pixels - 128, 383 for P-frame residuals - 128
 void make_fast_quant(FastQuant &fq, const uint16_t *quant, int N, double max_abs_sample);

@@ -83,49 +83,62 @@ __device__ __forceinline__ void tile_publish_aggregate(const ScanState &st, unsi
     st_relaxed_u64(&st.tile_state[tile], make_state(st.epoch, tile == 0 ? kFlagPrefix : kFlagAggregate, total_incl_base));
 }
 
+// Warp-level look-back, nearest predecessor first: lanes examine predecessors tile-1-lane (32 at a time).  The walk stops
+// at the nearest predecessor that has published an inclusive prefix; it only ever WAITS for predecessors that are nearer
+// than that one (they must at least have published their aggregate).  Must be called by all 32 lanes of one warp.
+// Publishes this tile's inclusive prefix and returns the exclusive prefix (in every lane).
+__device__ __forceinline__ unsigned long long tile_lookback_warp(const ScanState &st, unsigned tile, unsigned long long total) {
+    constexpr int R = 8;                                   // windows fetched per round trip (256 predecessors in flight)
+    const int lane = threadIdx.x & 31;
+    unsigned long long excl = 0;
+    if (tile != 0) {
+        const unsigned long long ep = (unsigned long long)(st.epoch & 0xFFFFFFu);
+        int base = (int)tile - 1;
+        bool done = false;
+        while (!done) {
+            unsigned long long sv[R];
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                const int idx = base - 32 * k - lane;
+                sv[k] = (idx >= 0) ? ld_relaxed_u64(&st.tile_state[idx]) : 0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (done) break;
+                const int idx = base - 32 * k - lane;
+                unsigned long long s = sv[k];
+                unsigned pm;
+                while (true) {
+                    const bool valid = (idx < 0) || ((s >> 40) == ep && ((s >> kValueBits) & 3ull) != 0ull);
+                    const bool is_prefix = (idx >= 0) && valid && (((s >> kValueBits) & 3ull) == kFlagPrefix);
+                    pm = __ballot_sync(0xffffffffu, is_prefix);
+                    const unsigned inval = __ballot_sync(0xffffffffu, !valid);
+                    // this window is settled as soon as nothing nearer than its nearest prefix is still missing
+                    // (or, without a prefix here, every entry is there); only then do we wait -- and only on this window
+                    const unsigned nearer = pm ? ((1u << (__ffs(pm) - 1)) - 1u) : 0xffffffffu;
+                    if ((inval & nearer) == 0u) break;
+                    if (idx >= 0) s = ld_relaxed_u64(&st.tile_state[idx]);
+                }
+                const int first = pm ? (__ffs(pm) - 1) : 31;
+                unsigned long long c = (idx >= 0 && lane <= first) ? (s & kValueMask) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                excl += c;
+                if (pm || base - 32 * (k + 1) < 0) done = true;
+            }
+            base -= 32 * R;
+        }
+        if (lane == 0) st_relaxed_u64(&st.tile_state[tile], make_state(st.epoch, kFlagPrefix, excl + total));
+    }
+    return excl;
+}
+
 __device__ __forceinline__ unsigned long long tile_resolve_prefix(const ScanState &st, unsigned tile, unsigned long long total,
                                                                   unsigned long long *s_bcast) {
-    constexpr int R = 8;                                   // states per lane per round
     if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        unsigned long long excl = 0;
-        if (tile != 0) {
-            const unsigned long long ep = (unsigned long long)(st.epoch & 0xFFFFFFu);
-            int base = (int)tile - 1;
-            bool done = false;
-            while (!done) {
-                unsigned long long sv[R];
-#pragma unroll
-                for (int k = 0; k < R; k++) {
-                    const int idx = base - 32 * k - lane;
-                    sv[k] = (idx >= 0) ? ld_relaxed_u64(&st.tile_state[idx]) : 0ull;
-                }
-#pragma unroll
-                for (int k = 0; k < R; k++) {
-                    if (done) break;
-                    const int idx = base - 32 * k - lane;
-                    unsigned long long s = sv[k];
-                    if (idx >= 0) {
-                        // every predecessor already runs (ticket order), so this terminates
-                        while ((s >> 40) != ep || ((s >> kValueBits) & 3ull) == 0ull) s = ld_relaxed_u64(&st.tile_state[idx]);
-                    }
-                    __syncwarp();
-                    const bool is_prefix = (idx >= 0) && (((s >> kValueBits) & 3ull) == kFlagPrefix);
-                    const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-                    // lanes from the nearest predecessor (lane 0) up to and including the first published prefix contribute
-                    const int first = pm ? (__ffs(pm) - 1) : 31;
-                    unsigned long long c = (idx >= 0 && lane <= first) ? (s & kValueMask) : 0ull;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
-                    c = __shfl_sync(0xffffffffu, c, 0);
-                    excl += c;
-                    if (pm || base - 32 * (k + 1) < 0) done = true;
-                }
-                base -= 32 * R;
-            }
-            if (lane == 0) st_relaxed_u64(&st.tile_state[tile], make_state(st.epoch, kFlagPrefix, excl + total));
-        }
-        if (lane == 0) *s_bcast = excl;
+        const unsigned long long excl = tile_lookback_warp(st, tile, total);
+        if (threadIdx.x == 0) *s_bcast = excl;
     }
     __syncthreads();
     return *s_bcast;

@@ -20,6 +20,10 @@ struct ie_session {
     int *d_err = nullptr;
     unsigned epoch = 0;
 
+    // tile scratch of the encoder (packed tile images, per-tile bit totals and stream offsets)
+    uint8_t *d_tile_scratch = nullptr; size_t tile_scratch_cap = 0;
+    uint8_t *d_tile_meta = nullptr;    size_t tile_meta_cap = 0;
+
     // decode scratch
     unsigned long long *d_block_off = nullptr;    // [images * nblocks (+1)]
     size_t block_off_cap = 0;
