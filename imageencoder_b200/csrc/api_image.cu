@@ -157,7 +157,7 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
         if (!bits_only) IE_TRY(session_reserve(&s->d_tile_scratch, &s->tile_scratch_cap, ntot * p.slot_bytes));
         IE_TRY(session_reserve(&s->d_tile_meta, &s->tile_meta_cap, ntot * (sizeof(unsigned long long) + sizeof(unsigned)) + 64));
         p.tile_scratch = s->d_tile_scratch;
-        p.tile_off = reinterpret_cast<unsigned long long *>(s->d_tile_meta);
+        p.bit_base = reinterpret_cast<unsigned long long *>(s->d_tile_meta);
         p.tile_bits = reinterpret_cast<unsigned *>(s->d_tile_meta + ntot * sizeof(unsigned long long));
     }
     // scan arrays are indexed [image][tile] with stride tiles_per_image (the allocation is at least that large)

@@ -239,7 +239,7 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     IE_TRY(session_reserve(&s->d_tile_scratch, &s->tile_scratch_cap, (size_t)tiles * p.slot_bytes));
     IE_TRY(session_reserve(&s->d_tile_meta, &s->tile_meta_cap, (size_t)tiles * (sizeof(unsigned long long) + sizeof(unsigned)) + 64));
     p.tile_scratch = s->d_tile_scratch;
-    p.tile_off = reinterpret_cast<unsigned long long *>(s->d_tile_meta);
+    p.bit_base = reinterpret_cast<unsigned long long *>(s->d_tile_meta);
     p.tile_bits = reinterpret_cast<unsigned *>(s->d_tile_meta + (size_t)tiles * sizeof(unsigned long long));
     for (uint32_t f = 0; f < frames; f++) {
         uint8_t *cur = d_yuv + (size_t)f * fsz;

@@ -417,33 +417,11 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_ti
         uint4 *slot = reinterpret_cast<uint4 *>(p.tile_scratch + ((size_t)img * ntiles + tile) * p.slot_bytes);
         for (unsigned c = threadIdx.x; c < (nwords + 3) / 4; c += kThreads) slot[c] = s_out[c];
     }
-    if (threadIdx.x == 0) p.tile_bits[(size_t)img * ntiles + tile] = T;
-}
-
-// exclusive scan of the tile bit totals of one stream (one CTA per stream): tile_off[t] = first bit of tile t in the stream
-__global__ void __launch_bounds__(1024) tile_offsets_kernel(const unsigned *__restrict__ tile_bits, unsigned long long *tile_off,
-                                                            unsigned ntiles, unsigned long long *bit_counter) {
-    __shared__ unsigned long long s_sum[1024];
-    const unsigned img = blockIdx.x;
-    tile_bits += (size_t)img * ntiles;
-    tile_off += (size_t)img * ntiles;
-    const unsigned per = (ntiles + 1023) / 1024;
-    const unsigned t0 = threadIdx.x * per, t1 = min(t0 + per, ntiles);
-    unsigned long long sum = 0;
-    for (unsigned t = t0; t < t1; t++) sum += tile_bits[t];
-    s_sum[threadIdx.x] = sum;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        const unsigned long long v = (threadIdx.x >= (unsigned)d) ? s_sum[threadIdx.x - d] : 0ull;
-        __syncthreads();
-        s_sum[threadIdx.x] += v;
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        p.tile_bits[(size_t)img * ntiles + tile] = T;
+        if (p.bits_only) atomicAdd(p.bit_counter + img, (unsigned long long)T);
+        else if (tile == 0) p.bit_base[img] = p.bit_counter[img];      // the copy-out kernel of this launch starts here
     }
-    const unsigned long long base = bit_counter[img];
-    unsigned long long run = base + s_sum[threadIdx.x] - sum;
-    for (unsigned t = t0; t < t1; t++) { tile_off[t] = run; run += tile_bits[t]; }
-    __syncthreads();
-    if (threadIdx.x == 1023) bit_counter[img] = base + s_sum[1023];
 }
 
 // Tile image in global scratch (tile-local alignment, 32 stream bits per word, MSB first, zero beyond the last bit)
@@ -468,17 +446,71 @@ __device__ __forceinline__ uint4 gather_chunk(const GlobalStreamTile &t, long lo
     return o;
 }
 
+// A group of consecutive tile images seen as one piece of the stream: off[j] = first bit of tile j relative to the group.
+struct GroupStreamTiles {
+    const uint8_t *slots;          // slot of the group's first tile
+    size_t slot_bytes;
+    const unsigned *off;           // shared memory, n + 1 entries
+    unsigned n;
+};
+__device__ __forceinline__ uint4 gather_chunk(const GroupStreamTiles &g, long long ls) {
+    const unsigned lo = (unsigned)max(ls, 0ll);
+    unsigned j = 0;
+#pragma unroll
+    for (unsigned step = 16; step >= 1; step >>= 1)
+        if (j + step < g.n && g.off[j + step] <= lo) j += step;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    for (;;) {
+        GlobalStreamTile t;
+        t.words = reinterpret_cast<const unsigned *>(g.slots + (size_t)j * g.slot_bytes);
+        t.nwords = (g.off[j + 1] - g.off[j] + 31) / 32;
+        const uint4 a = gather_chunk(t, ls - (long long)g.off[j]);
+        v.x |= a.x; v.y |= a.y; v.z |= a.z; v.w |= a.w;
+        if (j + 1 >= g.n || ls + (long long)kChunkBits <= (long long)g.off[j + 1]) break;     // the chunk ends inside tile j
+        j++;
+    }
+    return v;
+}
+
+// Re-aligns the tile images into the stream.  One CTA per group of kTilesPerGroup consecutive tiles: it sums the bit totals of
+// every earlier tile of the stream (<= 32 KiB of L2 reads, all of them final: the tile kernel has completed) and then writes
+// the group's chunks, a thread per 128-bit chunk.  No scan kernel, no inter-CTA wait; only the chunks two groups share go
+// through the hand-off records.
+constexpr unsigned kTilesPerGroup = 8;
 __global__ void __launch_bounds__(kThreads) tile_copyout_kernel(const EncodeParams p) {
-    const unsigned img = blockIdx.y, tile = blockIdx.x, ntiles = p.tiles_per_image;
-    const size_t ti = (size_t)img * ntiles + tile;
-    const unsigned T = p.tile_bits[ti];
-    const unsigned long long G = p.tile_off[ti];
+    __shared__ unsigned long long s_part[kThreads / 32];
+    __shared__ unsigned s_goff[kTilesPerGroup + 1];
+    const unsigned img = blockIdx.y, ntiles = p.tiles_per_image;
+    const unsigned t0 = blockIdx.x * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
+    const unsigned *tb = p.tile_bits + (size_t)img * ntiles;
+    unsigned long long sum = 0;
+    for (unsigned i = threadIdx.x; i < t0; i += kThreads) sum += tb[i];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = sum;
+    if (threadIdx.x < 32) {                                    // kTilesPerGroup <= 32: one warp scans the group's totals
+        const unsigned t = t0 + threadIdx.x;
+        const unsigned v = (t < t1) ? tb[t] : 0u;
+        unsigned inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)threadIdx.x >= d) inc += o; }
+        if (threadIdx.x < kTilesPerGroup) s_goff[threadIdx.x + 1] = inc;
+        if (threadIdx.x == 0) s_goff[0] = 0;
+    }
+    __syncthreads();
+    unsigned long long G = p.bit_base[img];
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) G += s_part[w];
     ScanState st = p.scan;
     st.bnd += (size_t)img * ntiles;
-    GlobalStreamTile gt;
-    gt.words = reinterpret_cast<const unsigned *>(p.tile_scratch + ti * p.slot_bytes);
-    gt.nwords = (T + 31) / 32;
-    tile_write_chunks(gt, st, tile, tile == 0, tile == ntiles - 1, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
+    GroupStreamTiles g;
+    g.slots = p.tile_scratch + ((size_t)img * ntiles + t0) * p.slot_bytes;
+    g.slot_bytes = p.slot_bytes;
+    g.off = s_goff;
+    g.n = t1 - t0;
+    const unsigned T = s_goff[g.n];
+    tile_write_chunks(g, st, blockIdx.x, t0 == 0, t1 == ntiles, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
+    if (t1 == ntiles && threadIdx.x == 0) p.bit_counter[img] = G + T;
 }
 
 template <int N, int BPL, bool PF, bool FAST>
@@ -495,10 +527,10 @@ static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t strea
     }
     dim3 grid(p.tiles_per_image, images);
     encode_tiles_kernel<N, BPL, PF, FAST><<<grid, kThreads, smem, stream>>>(p);
-    tile_offsets_kernel<<<images, 1024, 0, stream>>>(p.tile_bits, p.tile_off, p.tiles_per_image, p.bit_counter);
-    count_launch(2);
+    count_launch();
     if (!p.bits_only) {
-        tile_copyout_kernel<<<grid, kThreads, 0, stream>>>(p);
+        dim3 cgrid((p.tiles_per_image + kTilesPerGroup - 1) / kTilesPerGroup, images);
+        tile_copyout_kernel<<<cgrid, kThreads, 0, stream>>>(p);
         count_launch();
     }
     IE_CUDA(cudaGetLastError());

@@ -31,7 +31,7 @@ struct EncodeParams {
     uint8_t *tile_scratch;            // [images * tiles] slots of slot_bytes: packed tile images (tile-local alignment)
     size_t slot_bytes;
     unsigned *tile_bits;              // [images * tiles] bits per tile
-    unsigned long long *tile_off;     // [images * tiles] first bit of every tile in its stream
+    unsigned long long *bit_base;     // [images] bit position each stream had when this launch started
     // P-frame mode (Frame.cpp:160-244): src is the CURRENT frame (read, then overwritten with the reconstruction),
     // ref the previous frame as the encoder left it; per-MacroBlock pixel coordinates of the block the residual is
     // taken from (res_coord, Block.cpp:337) and of the block copied in (copy_coord, Frame.cpp:218-225).
