@@ -116,7 +116,9 @@ int make_quant(QuantParam &q, const uint16_t *quant, int N) {
 // Encode `images` equally sized images that are resident on the device.
 int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, unsigned images, uint32_t W, uint32_t H, int N,
                       const uint16_t *quant, int use_rle, int lead_bit, int write_header, unsigned first_bit, int bits_only,
-                      uint8_t *d_out, size_t out_stride, size_t out_cap, cudaStream_t stream) {
+                      uint8_t *d_out, size_t out_stride, size_t out_cap, cudaStream_t stream, int append, uint32_t header_H) {
+    // append: the streams continue at their device-resident bit counters (no prefix is written); header_H: the height the
+    // header announces when this call encodes only the first stripe of a taller image
     IE_TRY(check_dims(W, H, N));
     IE_TRY(check_quant(quant, N));
     if (first_bit >= 128) { set_error("first_bit must be < 128"); return IE_EINVAL; }
@@ -129,8 +131,11 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
 
     HeaderParam hdr;
     memset(&hdr, 0, sizeof hdr);
-    if (write_header) IE_TRY(build_header(hdr, N, quant, use_rle, W, s->header_height ? s->header_height : H, lead_bit, 0, 0, 0, 0));
-    if (!bits_only) {
+    if (write_header && !append)
+        IE_TRY(build_header(hdr, N, quant, use_rle, W, header_H ? header_H : (s->header_height ? s->header_height : H), lead_bit, 0, 0, 0, 0));
+    if (append) {
+        if (bits_only) { set_error("append and bits_only exclude each other"); return IE_EINVAL; }
+    } else if (!bits_only) {
         const size_t need = ((size_t)first_bit + hdr.bits + 127) / 128 * 16;
         if (out_cap < need) { set_error("output buffer too small for the header"); return IE_ENOSPC; }
         IE_TRY(launch_stream_init(d_out, out_stride, images, hdr, first_bit, s->d_counter, stream));
@@ -162,6 +167,17 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     }
     // scan arrays are indexed [image][tile] with stride tiles_per_image (the allocation is at least that large)
     return launch_encode_tiles(N, p, images, stream);
+}
+
+int session_ensure_pipeline(ie_session *s) {
+    if (s->stream_in) return IE_OK;
+    IE_CUDA(cudaStreamCreateWithFlags(&s->stream_in, cudaStreamNonBlocking));
+    IE_CUDA(cudaStreamCreateWithFlags(&s->stream_out, cudaStreamNonBlocking));
+    for (int i = 0; i < ie_session::kMaxStripes; i++) {
+        IE_CUDA(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
+        IE_CUDA(cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming));
+    }
+    return IE_OK;
 }
 
 int read_err_flag(ie_session *s, cudaStream_t stream) {
@@ -293,6 +309,10 @@ void ie_session_destroy(ie_session *s) {
     cudaFree(s->d_block_off); cudaFree(s->d_parse); cudaFree(s->d_tile_scratch); cudaFree(s->d_tile_meta); cudaFree(s->d_scratch); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_tmp);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->stream_in) {
+        cudaStreamDestroy(s->stream_in); cudaStreamDestroy(s->stream_out);
+        for (int i = 0; i < ie_session::kMaxStripes; i++) { cudaEventDestroy(s->ev_in[i]); cudaEventDestroy(s->ev_done[i]); }
+    }
     delete s;
 }
 
@@ -333,24 +353,57 @@ int ie_encode_image(const uint8_t *raw, uint32_t W, uint32_t H, uint32_t N, cons
     const size_t cap = ie_max_encoded_bytes(W, H, N, 1);
     IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, npx));
     IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, cap));
+    IE_TRY(session_ensure_pipeline(s));
     cudaStream_t st = s->stream;
-    IE_CUDA(cudaMemcpyAsync(s->d_in, raw, npx, cudaMemcpyHostToDevice, st));
-    IE_TRY(encode_images_dev(s, s->d_in, 0, 1, W, H, (int)N, quant, use_rle, huffman ? 0 : 1, 1, 0, 0, s->d_out, 0, s->d_out_cap, st));
-    IE_CUDA(cudaMemcpyAsync(s->h_pinned, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+
+    // Stripes of whole block rows (>= 4 MiB of pixels each, at most kMaxStripes): stripe i is copied in on stream_in, encoded
+    // on `st` as an append to the stream (device-resident bit counter), and every 128-bit chunk it completed leaves on
+    // stream_out while the following stripes are still on their way in.  PCIe runs in both directions at once; what is left
+    // after the last pixel arrived is one stripe of encoding and its share of the output.
+    const uint32_t block_rows = H / N;
+    uint32_t stripes = (uint32_t)std::min<size_t>(ie_session::kMaxStripes, std::max<size_t>(1, npx / ((size_t)4 << 20)));
+    stripes = std::min(stripes, block_rows);
+    const uint32_t rows_per = (block_rows + stripes - 1) / stripes;          // block rows per stripe
+    stripes = (block_rows + rows_per - 1) / rows_per;
+    for (uint32_t i = 0; i < stripes; i++) {
+        const uint32_t r0 = i * rows_per, r1 = std::min(block_rows, r0 + rows_per);
+        const size_t off = (size_t)r0 * N * W, len = (size_t)(r1 - r0) * N * W;
+        IE_CUDA(cudaMemcpyAsync(s->d_in + off, raw + off, len, cudaMemcpyHostToDevice, s->stream_in));
+        IE_CUDA(cudaEventRecord(s->ev_in[i], s->stream_in));
+        IE_CUDA(cudaStreamWaitEvent(st, s->ev_in[i], 0));
+        IE_TRY(encode_images_dev(s, s->d_in + off, 0, 1, W, (r1 - r0) * N, (int)N, quant, use_rle, huffman ? 0 : 1, 1, 0, 0, s->d_out, 0,
+                                 s->d_out_cap, st, i > 0, H));
+        IE_CUDA(cudaMemcpyAsync(s->h_pinned + 1 + i, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        IE_CUDA(cudaEventRecord(s->ev_done[i], st));
+    }
+    size_t bytes = 0, sent = 0;
+    bool fits = true;
+    for (uint32_t i = 0; i < stripes; i++) {
+        IE_CUDA(cudaEventSynchronize(s->ev_done[i]));
+        const unsigned long long bits = s->h_pinned[1 + i];
+        const bool last = (i + 1 == stripes);
+        bytes = (size_t)((bits + 7) / 8);                                  // util::round_to_byte, ImageBase.cpp:316
+        if (huffman) continue;
+        const size_t fin = last ? bytes : (size_t)(bits / 128) * 16;      // chunks no later launch will touch
+        if (fin > out_cap) { fits = false; continue; }
+        if (fin > sent) {
+            IE_CUDA(cudaMemcpyAsync(out + sent, s->d_out + sent, fin - sent, cudaMemcpyDeviceToHost, s->stream_out));
+            sent = fin;
+        }
+    }
     IE_TRY(read_err_flag(s, st));                              // synchronises
-    size_t bytes = (size_t)((s->h_pinned[0] + 7) / 8);        // util::round_to_byte, ImageBase.cpp:316
-    const uint8_t *d_result = s->d_out;
     if (huffman) {
         IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, bytes + 4096 + 32));
         size_t hb = 0;
         IE_TRY(ie_huffman_encode_dev(s, s->d_out, bytes, s->d_tmp, s->d_tmp_cap, &hb, st));
         bytes = hb;
-        d_result = s->d_tmp;
+        fits = bytes <= out_cap;
+        if (fits) IE_CUDA(cudaMemcpyAsync(out, s->d_tmp, bytes, cudaMemcpyDeviceToHost, st));
+        IE_CUDA(cudaStreamSynchronize(st));
     }
+    IE_CUDA(cudaStreamSynchronize(s->stream_out));
     *out_bytes = bytes;
-    if (bytes > out_cap) { set_error("output buffer too small"); return IE_ENOSPC; }
-    IE_CUDA(cudaMemcpyAsync(out, d_result, bytes, cudaMemcpyDeviceToHost, st));
-    IE_CUDA(cudaStreamSynchronize(st));
+    if (!fits) { set_error("output buffer too small"); return IE_ENOSPC; }
     return IE_OK;
 }
 

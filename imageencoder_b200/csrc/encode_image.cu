@@ -53,11 +53,11 @@ __device__ __forceinline__ double exact_sample(const ExactCtx &p, const uint8_t 
 }
 
 // One coefficient of one block in the reference's exact order and precision (algo.cpp:309-331, Block.cpp:152).
-// The 2*N*N-operation chain is inherently sequential (every partial sum is rounded), so everything that does not depend
-// on the running sum -- pixel rows, table entries, conversions -- is fetched up front, 16 terms at a time.
+// The 2*N*N-operation chain is inherently sequential (every partial sum is rounded); everything that does not depend on
+// the running sum is fetched before it starts: the N pixel rows and the 2N cosines whose rounded products
+// fl(cs[i][u] * cs[j][v]) are the reference's factors (algo.cpp:318-319) -- one round of loads instead of N*N table reads.
 template <int N, bool PF>
 __device__ __noinline__ int exact_coefficient(const ExactCtx p, unsigned gb, int uv, double m_uv) {
-    constexpr int NN = N * N;
     const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
     int rx = 0, ry = 0;
     if (PF) {
@@ -65,38 +65,37 @@ __device__ __noinline__ int exact_coefficient(const ExactCtx p, unsigned gb, int
         rx = p.res_coord[2 * mb] + (int)(bxi & 3) * 4;
         ry = p.res_coord[2 * mb + 1] + (int)(byi & 3) * 4;
     }
-    const double *t = p.tab->fw + uv * NN;
+    const int u = uv / N, v = uv % N;
     const uint8_t *blk = p.src + (size_t)(byi * N) * p.pitch + (size_t)bxi * N;
+    unsigned lo[N], hi[N];
+    double a[N], b[N];
+#pragma unroll
+    for (int y = 0; y < N; y++) {
+        hi[y] = 0;
+        if (N == 8) { const uint2 w = *reinterpret_cast<const uint2 *>(blk + (size_t)y * p.pitch); lo[y] = w.x; hi[y] = w.y; }
+        else lo[y] = *reinterpret_cast<const unsigned *>(blk + (size_t)y * p.pitch);
+        a[y] = __ldg(p.tab->cs + y * N + u);
+        b[y] = __ldg(p.tab->cs + y * N + v);
+    }
     double acc = 0.0;
-    constexpr int ROWS_PER_BATCH = 16 / N;                  // 16 terms per batch
-#pragma unroll 1
-    for (int y0 = 0; y0 < N; y0 += ROWS_PER_BATCH) {
-        double xs[16], ts[16];
 #pragma unroll
-        for (int yy = 0; yy < ROWS_PER_BATCH; yy++) {
-            const int y = y0 + yy;
-            unsigned lo, hi = 0;
-            if (N == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2 *>(blk + (size_t)y * p.pitch)); lo = v.x; hi = v.y; }
-            else lo = *reinterpret_cast<const unsigned *>(blk + (size_t)y * p.pitch);
+    for (int y = 0; y < N; y++) {
 #pragma unroll
-            for (int k = 0; k < N; k++) {
-                int v = (int)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xffu);
-                if (PF) v -= (int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + k);               // Block.cpp:262
-                xs[yy * N + k] = (double)(v - 128);                                                  // Block.cpp:141-143 (exact)
-                ts[yy * N + k] = __ldg(t + y * N + k);
-            }
+        for (int k = 0; k < N; k++) {
+            int px = (int)(((k < 4 ? lo[y] : hi[y]) >> (8 * (k & 3))) & 0xffu);
+            if (PF) px -= (int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + k);                  // Block.cpp:262
+            const double x = (double)(px - 128);                                                   // Block.cpp:141-143 (exact)
+            acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(a[y], b[k]), x));                             // algo.cpp:318-320
         }
-#pragma unroll
-        for (int i = 0; i < 16; i++) acc = __dadd_rn(acc, __dmul_rn(ts[i], xs[i]));                 // algo.cpp:318-320
     }
     const double e = __dmul_rn(acc, p.tab->cc[uv]);
     return (int)(short)__double2int_rz(round_half_away(__ddiv_rn(e, m_uv)));
 }
 
-constexpr int kQueueCap = 512;        // guard-band fallback entries per tile handled by the CTA-wide queue
+constexpr int kQueueCap = 128;        // guard-band fallback entries per tile handled by the CTA-wide queue
 
 template <int N, int BPL, bool PF, bool FAST>
-__global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : 2) encode_tiles_kernel(const EncodeParams p) {
+__global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF ? 6 : 2)) encode_tiles_kernel(const EncodeParams p) {
     constexpr int NN = N * N;
     constexpr int TB = kThreads * BPL;            // blocks per tile
     constexpr int STRIDE = NN + 2;                // halfwords per block in the staging area: NN/2 + 1 words (odd -> bank spread)

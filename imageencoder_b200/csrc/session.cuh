@@ -42,6 +42,12 @@ struct ie_session {
     unsigned long long *h_pinned = nullptr;       // small pinned read-back area (64 u64)
     cudaStream_t stream = nullptr;                // used by the host-buffer entry points
 
+    // copy/compute pipeline of the host-buffer image entry points: pixels come in by stripes on stream_in, the encoded
+    // bytes leave on stream_out while later stripes are still being copied in / encoded
+    static constexpr int kMaxStripes = 32;
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;
+    cudaEvent_t ev_in[kMaxStripes] = {}, ev_done[kMaxStripes] = {};
+
     ie::ScanState scan_state() {
         ie::ScanState st;
         st.tile_state = d_tile_state;

@@ -85,6 +85,20 @@ def test_large_synthetic_8x8(gpu, oracle_mod):
     assert np.array_equal(gpu.decode_image(got, 8), oracle_mod.image_decode(want, 8)[0])
 
 
+@pytest.mark.parametrize("N,W,H,huffman", [(8, 4096, 2056, False), (4, 2052, 4100, False), (8, 2048, 4096, True)])
+def test_striped_host_pipeline_matches_oracle(gpu, oracle_mod, N, W, H, huffman):
+    """ie_encode_image copies/encodes/returns images above 8 MiB in stripes of block rows (copy-compute pipeline): the bytes
+    must be those of a one-launch encode, i.e. the oracle's."""
+    from imageencoder_b200.synth import synth_image
+    img = synth_image(W, H, 77)
+    q = _mat(oracle_mod, "matrix8_1.txt" if N == 8 else "matrix.txt")
+    got = gpu.encode_image(img, W, H, q, True, huffman)
+    want = oracle_mod.image_encode(img, W, H, N, q, True, huffman)
+    assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest()
+    if not huffman:
+        assert np.array_equal(gpu.decode_image(got, N), np.asarray(oracle_mod.image_decode(want, N)[0]))
+
+
 def test_errors(gpu):
     from imageencoder_b200 import IEError
     with pytest.raises(IEError):
