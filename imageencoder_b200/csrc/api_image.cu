@@ -228,7 +228,7 @@ int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size
                      uint8_t *d_out, size_t out_cap, cudaStream_t stream) {
     const uint32_t W = h.W, H = h.H;
     IE_TRY(check_dims(W, H, N));
-    if ((uintptr_t)d_enc % 4) { set_error("encoded stream must be 4-byte aligned (and readable up to its size rounded up to 4)"); return IE_EINVAL; }
+    if ((uintptr_t)d_enc % 16) { set_error("encoded stream must be 16-byte aligned (and readable up to its size rounded up to 4)"); return IE_EINVAL; }
     if ((size_t)W * H > out_cap) { set_error("decoded image does not fit the output buffer"); return IE_ENOSPC; }
     for (int i = 0; i < N * N; i++)
         if (h.quant[i] == 0) { /* a zero entry decodes to zero coefficients * 0: allowed */ }

@@ -17,6 +17,7 @@
 // do not advance (BitStream.cpp:17-20): a chain that reaches the end is DEAD and every remaining block starts at `total`.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 
 #include "decode_image.cuh"
 
@@ -87,11 +88,12 @@ __global__ void __launch_bounds__(64) parse_group_tables(const ParseParams p) {
     unsigned *s_memo = s_cnt + E;                                         // [E] exit << 16 | blocks
     unsigned short *s_cur = reinterpret_cast<unsigned short *>(s_memo + E);   // [E]
     unsigned char *s_need = reinterpret_cast<unsigned char *>(s_cur + E + (E & 1));   // [E]
-    const unsigned g = blockIdx.x;
     if (p.spec_flags[1]) return;                                          // the speculative parse verified: nothing to do
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
+    for (unsigned g = blockIdx.x; g < p.ngroups; g += gridDim.x) {
     const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits;
+    __syncthreads();
     for (int e = threadIdx.x; e < E; e += blockDim.x) { s_cur[e] = (unsigned short)e; s_cnt[e] = 0; }
     __syncthreads();
     for (int sub = 0; sub < kSubsPerGroup; sub++) {
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(64) parse_group_tables(const ParseParams p) {
         __syncthreads();
     }
     for (int e = threadIdx.x; e < E; e += blockDim.x) p.group_table[(size_t)g * E + e] = make_uint2(s_cur[e], s_cnt[e]);
+    }
 }
 
 __global__ void __launch_bounds__(256) parse_super_tables(const ParseParams p) {
@@ -172,112 +175,238 @@ __global__ void __launch_bounds__(64) parse_down_super(const ParseParams p) {
 // transfer-function kernels above do the work instead (they return immediately when spec_ok is 1).
 // ---------------------------------------------------------------------------------------------------------
 // lead-in before a group's first bit (measured on 8x8 streams: 4096 bits leave 3 % of the groups unsynchronised, 8192 none)
-constexpr int kSpecRounds = 3;
+constexpr int kSpecRounds = 3;            // repair rounds inside a CTA
+constexpr int kWalkGroups = 64;           // groups (= threads) per CTA of the staged kernels
+
+// ---- stream staging: the bits a CTA walks are first copied to shared memory with 16-byte cp.async (coalesced, no
+// registers, zero fill past the end), because a walk is a chain of dependent reads: ~80 of them per group, each a round
+// trip to L2/HBM when done on global memory (measured: 127 us for the walk kernel on 27.7 MB), ~30 cycles in shared memory.
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, unsigned src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+
+struct StagedStream {
+    const unsigned *w;                 // shared memory, raw little-endian words of the stream
+    unsigned long long w0;             // index (in 32-bit words of the stream) of w[0]
+    unsigned long long total;          // stream size in bits
+};
+
+// stage the words holding bits [first_bit, last_bit) (+ the 64-bit header window) of the stream; returns the view
+__device__ __forceinline__ StagedStream stage_stream(unsigned *s_w, unsigned cap_words, const uint8_t *enc, unsigned long long total,
+                                                     unsigned long long first_bit, unsigned long long last_bit) {
+    StagedStream st;
+    st.total = total;
+    st.w = s_w;
+    st.w0 = (first_bit >> 7) << 2;                                          // 16-byte granules
+    const unsigned long long nbytes = ((total + 31) >> 5) << 2;            // readable bytes (whole words, as block_bits_at)
+    const unsigned long long b0 = st.w0 * 4;
+    unsigned long long b1 = ((last_bit + 64 + 127) >> 7) << 4;
+    if (b1 > b0 + (unsigned long long)cap_words * 4) b1 = b0 + (unsigned long long)cap_words * 4;
+    for (unsigned long long b = b0 + (unsigned long long)threadIdx.x * 16; b < b1; b += (unsigned long long)blockDim.x * 16) {
+        const unsigned have = (b >= nbytes) ? 0u : (unsigned)min(16ull, nbytes - b);
+        cp_async16_zfill(s_w + ((b - b0) >> 2), enc + (have ? b : 0ull), have);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    return st;
+}
+
+// block_bits_at on the staged copy (same result for every p inside the staged range)
+__device__ __forceinline__ unsigned block_bits_staged(const StagedStream &st, unsigned long long p, int NN, int rle) {
+    const unsigned i = (unsigned)((p >> 5) - st.w0);
+    const unsigned w0 = __byte_perm(st.w[i], 0, 0x0123);
+    const unsigned w1 = __byte_perm(st.w[i + 1], 0, 0x0123);                // zero past the last word (zero fill)
+    unsigned v = __funnelshift_l(w1, w0, (unsigned)(p & 31));
+    if (p + 32 > st.total) v &= ~((st.total - p >= 32) ? 0u : (0xFFFFFFFFu >> (unsigned)(st.total - p)));
+    const unsigned w = v >> 28;
+    unsigned len = (unsigned)NN;
+    if (rle) len = w ? ((v << 4) >> (32 - w)) : 0u;
+    if (len > (unsigned)NN) return kBadBlock;
+    return 4u + (rle ? w : 0u) + len * w;
+}
 
 // walks the chain from absolute bit `pos` (inside or before the group) to the group's end
-__device__ __forceinline__ uint2 walk_group(const ParseParams &p, unsigned long long total, unsigned long long pos, unsigned long long g_end) {
+template <class Src>
+__device__ __forceinline__ uint2 walk_group_t(const Src &src, int NN, int rle, unsigned long long total, unsigned long long pos,
+                                              unsigned long long g_end);
+struct GlobalSrc { const uint8_t *enc; unsigned long long total; };
+__device__ __forceinline__ unsigned src_block_bits(const GlobalSrc &g, unsigned long long p, int NN, int rle) { return block_bits_at(g.enc, g.total, p, NN, rle); }
+__device__ __forceinline__ unsigned src_block_bits(const StagedStream &s, unsigned long long p, int NN, int rle) { return block_bits_staged(s, p, NN, rle); }
+template <class Src>
+__device__ __forceinline__ uint2 walk_group_t(const Src &src, int NN, int rle, unsigned long long total, unsigned long long pos,
+                                              unsigned long long g_end) {
     unsigned cnt = 0;
     while (true) {
         if (pos >= total) return make_uint2(kDead, cnt);
         if (pos >= g_end) return make_uint2((unsigned)(pos - g_end), cnt);
-        const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
+        const unsigned bits = src_block_bits(src, pos, NN, rle);
         if (bits == kBadBlock) return make_uint2(kDead, cnt);
         pos += bits;
         cnt++;
     }
 }
 
-__global__ void __launch_bounds__(64) parse_spec_walk(const ParseParams p) {
-    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g == 0 && threadIdx.x == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; p.spec_flags[2] = 0; }
-    if (g >= p.ngroups) return;
+constexpr unsigned kStageWords = (kWalkGroups + 1) * (kGroupBits / 32) + 16;      // groups + lead-in + window/alignment slack
+
+// One CTA = kWalkGroups consecutive groups, one thread each, on a staged copy of their bits.  After the walks the CTA checks
+// its own neighbours and re-walks the groups whose entry disagrees with their predecessor's exit (kSpecRounds rounds);
+// the first group of every CTA is checked against the previous CTA by parse_spec_boundary.
+__global__ void __launch_bounds__(kWalkGroups) parse_spec_walk(const ParseParams p) {
+    extern __shared__ __align__(16) unsigned s_stage[];
+    __shared__ unsigned s_entry[kWalkGroups], s_exit[kWalkGroups];
+    const unsigned g = blockIdx.x * kWalkGroups + threadIdx.x;
+    if (g == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; p.spec_flags[2] = 0; }
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
-    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
     const unsigned lead = (p.NN == 64) ? 8192u : 4096u;
+    const unsigned long long c_start = B0 + (unsigned long long)blockIdx.x * kWalkGroups * kGroupBits;
+    const unsigned long long c_first = (c_start < B0 + lead) ? B0 : c_start - lead;
+    const unsigned long long c_end = min(total, c_start + (unsigned long long)kWalkGroups * kGroupBits);
+    if (c_first >= total) {                                 // uniform: nothing of the stream in this CTA's range
+        if (g < p.ngroups) { p.group_entry[g] = make_uint2(kDead, 0u); p.spec_exit[g] = make_uint2(kDead, 0u); }
+        return;
+    }
+    const StagedStream st = stage_stream(s_stage, kStageWords, p.enc, total, c_first, c_end);
+    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
     unsigned long long pos = (g == 0 || g_start < B0 + lead) ? B0 : g_start - lead;
     unsigned entry;
-    if (g_start >= total) { entry = kDead; }
+    uint2 ex = make_uint2(kDead, 0u);
+    if (g >= p.ngroups || g_start >= total) { entry = kDead; }
     else {
         while (pos < g_start) {                            // lead-in on an arbitrary phase; garbage headers just slide by a bit
-            const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
+            const unsigned bits = block_bits_staged(st, pos, p.NN, p.use_rle);
             pos += (bits == kBadBlock) ? 1u : bits;
         }
         entry = (pos >= total) ? kDead : (unsigned)(pos - g_start);
+        if (entry != kDead) ex = walk_group_t(st, p.NN, p.use_rle, total, pos, g_end);
     }
-    const uint2 ex = (entry == kDead) ? make_uint2(kDead, 0u) : walk_group(p, total, pos, g_end);
-    p.group_entry[g] = make_uint2(entry, 0u);
-    p.spec_exit[g] = ex;
+    s_entry[threadIdx.x] = entry;
+    s_exit[threadIdx.x] = ex.x;
+    __syncthreads();
+    for (int r = 0; r < kSpecRounds; r++) {
+        // only trust a predecessor that is itself consistent with ITS predecessor: a group whose lead-in failed to
+        // synchronise walks garbage; adopting its exit would push the error forward round after round
+        const int t = (int)threadIdx.x;
+        bool redo = false;
+        unsigned want = 0;
+        if (t >= 1 && g < p.ngroups && (t < 2 || s_exit[t - 2] == s_entry[t - 1])) {
+            want = s_exit[t - 1];
+            redo = (want != s_entry[t]);
+        }
+        if (!__syncthreads_or(redo)) break;
+        if (redo) {
+            entry = want;
+            ex = (want == kDead || want >= (unsigned)kGroupBits) ? make_uint2(kDead, 0u)
+                                                               : walk_group_t(st, p.NN, p.use_rle, total, g_start + want, g_end);
+        }
+        __syncthreads();
+        if (redo) { s_entry[t] = entry; s_exit[t] = ex.x; }
+        __syncthreads();
+    }
+    if (g < p.ngroups) { p.group_entry[g] = make_uint2(entry, 0u); p.spec_exit[g] = ex; }
 }
 
-__global__ void __launch_bounds__(64) parse_spec_repair(const ParseParams p, int round) {
-    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.ngroups || g == 0) return;
-    // only trust a predecessor that is itself consistent with ITS predecessor: a group whose lead-in failed to synchronise
-    // walks garbage (and may even die on a bad header); adopting its exit would push the error forward round after round
-    if (g >= 2 && p.spec_exit[g - 2].x != p.group_entry[g - 1].x) return;
-    const unsigned want = p.spec_exit[g - 1].x;
-    const unsigned have = p.group_entry[g].x;
-    if (want == have) return;
-    atomicAdd(&p.spec_flags[0], 1u + (unsigned)round * 0u);
+// CTA seams: thread k checks the first group of CTA k against the last group of CTA k-1 and, on a mismatch, re-walks
+// groups (on global memory: rare) until the chain agrees again or its CTA ends.  What it cannot settle is caught by
+// parse_spec_finish (-> exact kernels).
+__global__ void __launch_bounds__(64) parse_spec_boundary(const ParseParams p) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned g = k * kWalkGroups;
+    if (k == 0 || g >= p.ngroups) return;
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
-    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
-    // NOTE: reading spec_exit[g-1] while thread g-1 may rewrite it in this same launch is a benign race: whatever is read
-    // is re-verified by the final check.
-    p.group_entry[g] = make_uint2(want, 0u);
-    p.spec_exit[g] = (want == kDead || want >= (unsigned)kGroupBits) ? make_uint2(kDead, 0u) : walk_group(p, total, g_start + want, g_end);
+    const GlobalSrc src{p.enc, total};
+    unsigned want = p.spec_exit[g - 1].x;
+    for (unsigned n = 0; n < (unsigned)kWalkGroups && g < p.ngroups; n++, g++) {
+        if (p.group_entry[g].x == want) break;
+        const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
+        const uint2 ex = (want == kDead || want >= (unsigned)kGroupBits) ? make_uint2(kDead, 0u)
+                                                                       : walk_group_t(src, p.NN, p.use_rle, total, g_start + want, g_end);
+        p.group_entry[g] = make_uint2(want, 0u);
+        p.spec_exit[g] = ex;
+        want = ex.x;
+    }
 }
 
-// final exact verification + exclusive scan of the per-group block counts (single CTA).  Only the groups that hold the
-// stream's nblocks blocks have to be consistent: behind the last block the chain runs into whatever follows (pad bits, the
-// next frame's motion vectors), where the speculative walks may legitimately disagree.
+// final exact verification + exclusive scan of the per-group block counts (single CTA, coalesced passes over the group
+// arrays, kFinishChunk groups at a time through shared memory).  Only the groups that hold the stream's nblocks blocks
+// have to be consistent: behind the last block the chain runs into whatever follows (pad bits, the next frame's motion
+// vectors), where the speculative walks may legitimately disagree.
+constexpr unsigned kFinishChunk = 8192;
 __global__ void __launch_bounds__(1024) parse_spec_finish(const ParseParams p) {
-    __shared__ unsigned s_firstbad;
-    __shared__ unsigned s_sum[1024];
-    if (threadIdx.x == 0) s_firstbad = p.ngroups;
+    __shared__ unsigned s_cnt[kFinishChunk];
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_firstbad, s_base;
+    if (threadIdx.x == 0) { s_firstbad = p.ngroups; s_base = 0; }
     __syncthreads();
-    const unsigned per = (p.ngroups + 1023) / 1024;
-    const unsigned g0 = threadIdx.x * per, g1 = min(g0 + per, p.ngroups);
-    unsigned sum = 0;
-    for (unsigned g = g0; g < g1; g++) {
-        if (g > 0 && p.spec_exit[g - 1].x != p.group_entry[g].x) atomicMin(&s_firstbad, g);
-        sum += p.spec_exit[g].y;
-    }
-    s_sum[threadIdx.x] = sum;
+    // pass 1: first inconsistent seam
+    unsigned fb = p.ngroups;
+    for (unsigned g = threadIdx.x + 1; g < p.ngroups; g += 1024)
+        if (p.spec_exit[g - 1].x != p.group_entry[g].x) { fb = g; break; }        // strided: the smallest of this thread
+    if (fb < p.ngroups) atomicMin(&s_firstbad, fb);
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {                    // Hillis-Steele inclusive scan
-        const unsigned v = (threadIdx.x >= (unsigned)d) ? s_sum[threadIdx.x - d] : 0u;
-        __syncthreads();
-        s_sum[threadIdx.x] += v;
-        __syncthreads();
-    }
     const unsigned firstbad = s_firstbad;
-    unsigned base = s_sum[threadIdx.x] - sum;
-    for (unsigned g = g0; g < g1; g++) {
-        const uint2 ge = p.group_entry[g];
-        // groups from the first inconsistent one on are switched off (they only hold blocks beyond nblocks, checked below)
-        p.group_entry[g] = make_uint2(g >= firstbad ? kDead : ge.x, base);
-        if (g == firstbad && base < p.nblocks) p.spec_flags[2] = 1;         // a needed group is unverified: not usable
-        base += p.spec_exit[g].y;
+    // pass 2: exclusive scan of the counts, chunk by chunk
+    constexpr unsigned PER = kFinishChunk / 1024;
+    for (unsigned c0 = 0; c0 < p.ngroups; c0 += kFinishChunk) {
+        const unsigned n = min(kFinishChunk, p.ngroups - c0);
+        for (unsigned i = threadIdx.x; i < kFinishChunk; i += 1024) s_cnt[i] = (i < n) ? p.spec_exit[c0 + i].y : 0u;
+        __syncthreads();
+        unsigned v[PER], sum = 0;
+#pragma unroll
+        for (unsigned j = 0; j < PER; j++) { v[j] = s_cnt[threadIdx.x * PER + j]; sum += v[j]; }
+        unsigned inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)(threadIdx.x & 31) >= d) inc += o; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, w, d); if ((int)threadIdx.x >= d) w += o; }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        unsigned run = s_base + inc - sum + ((threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u);
+#pragma unroll
+        for (unsigned j = 0; j < PER; j++) { s_cnt[threadIdx.x * PER + j] = run; run += v[j]; }
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < n; i += 1024) {
+            const unsigned g = c0 + i, base = s_cnt[i];
+            // groups from the first inconsistent one on are switched off (they only hold blocks beyond nblocks, checked here)
+            p.group_entry[g] = make_uint2(g >= firstbad ? kDead : p.group_entry[g].x, base);
+            if (g == firstbad && base < p.nblocks) p.spec_flags[2] = 1;            // a needed group is unverified: not usable
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_warp[31];
+        __syncthreads();
     }
-    __syncthreads();
     __threadfence_block();
+    __syncthreads();
     if (threadIdx.x == 0) p.spec_flags[1] = p.spec_flags[2] ? 0u : 1u;
 }
 
-__global__ void __launch_bounds__(64) parse_emit_offsets(const ParseParams p) {
-    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+// One CTA = kWalkGroups groups on a staged copy: every thread walks its group's TRUE chain and writes block_off[].
+__global__ void __launch_bounds__(kWalkGroups) parse_emit_offsets(const ParseParams p) {
+    extern __shared__ __align__(16) unsigned s_stage[];
+    const unsigned g = blockIdx.x * kWalkGroups + threadIdx.x;
+    const unsigned long long total = *p.enc_bits;
+    const unsigned long long B0 = *p.start + p.skip_bits;
+    const unsigned long long c_start = B0 + (unsigned long long)blockIdx.x * kWalkGroups * kGroupBits;
+    if (c_start >= total) return;                            // uniform
+    // a block that starts inside the CTA's last group may end (and the next header be read) up to E bits behind it; the
+    // walk itself only reads headers of blocks that START before the group's end
+    const StagedStream st = stage_stream(s_stage, kStageWords, p.enc, total, c_start, min(total, c_start + (unsigned long long)kWalkGroups * kGroupBits));
     if (g >= p.ngroups) return;
     const uint2 ge = p.group_entry[g];
     if (ge.x == kDead) return;
-    const unsigned long long total = *p.enc_bits;
-    const unsigned long long B0 = *p.start + p.skip_bits;
     const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
     unsigned long long pos = g_start + ge.x;
     unsigned idx = ge.y;
     while (pos < g_end && pos < total && idx < p.nblocks) {
-        const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
+        const unsigned bits = block_bits_staged(st, pos, p.NN, p.use_rle);
         if (bits == kBadBlock) { if (p.err) atomicExch(p.err, IE_EFORMAT); pos = total; break; }   // malformed stream
         p.block_off[idx++] = pos;
         pos = min(pos + bits, total);
@@ -332,11 +461,16 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     static const bool dbg = getenv("IE_DEBUG_SYNC") != nullptr;
 #define IE_DBG_STEP(name) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(stream); if (e_ != cudaSuccess) { fprintf(stderr, "[ie] %s failed: %s\n", name, cudaGetErrorString(e_)); return cuda_fail(e_, name, __FILE__, __LINE__); } } } while (0)
     IE_DBG_STEP("before parse");
-    parse_spec_walk<<<(p.ngroups + 63) / 64, 64, 0, stream>>>(p);
-    for (int r = 0; r < kSpecRounds; r++) parse_spec_repair<<<(p.ngroups + 63) / 64, 64, 0, stream>>>(p, r);
+    const unsigned nwalk = (p.ngroups + kWalkGroups - 1) / kWalkGroups;
+    const size_t stage_bytes = (size_t)kStageWords * sizeof(unsigned);
+    if ((uintptr_t)d.enc % 16) { set_error("encoded stream must be 16-byte aligned on the device"); return IE_EINVAL; }
+    IE_CUDA(cudaFuncSetAttribute(parse_spec_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    IE_CUDA(cudaFuncSetAttribute(parse_emit_offsets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    parse_spec_walk<<<nwalk, kWalkGroups, stage_bytes, stream>>>(p);
+    parse_spec_boundary<<<(nwalk + 63) / 64, 64, 0, stream>>>(p);
     parse_spec_finish<<<1, 1024, 0, stream>>>(p);
     IE_DBG_STEP("parse_spec");
-    parse_group_tables<<<p.ngroups, 64, smem, stream>>>(p);
+    parse_group_tables<<<std::min(p.ngroups, 148u * 8u), 64, smem, stream>>>(p);
     IE_DBG_STEP("parse_group_tables");
     parse_super_tables<<<p.nsuper, 256, 0, stream>>>(p);
     IE_DBG_STEP("parse_super_tables");
@@ -344,10 +478,10 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     IE_DBG_STEP("parse_top_walk");
     parse_down_super<<<(p.nsuper + 63) / 64, 64, 0, stream>>>(p);
     IE_DBG_STEP("parse_down_super");
-    parse_emit_offsets<<<(p.ngroups + 63) / 64, 64, 0, stream>>>(p);
+    parse_emit_offsets<<<nwalk, kWalkGroups, stage_bytes, stream>>>(p);
     IE_DBG_STEP("parse_emit_offsets");
 #undef IE_DBG_STEP
-    count_launch(7 + kSpecRounds);
+    count_launch(8);
     IE_CUDA(cudaGetLastError());
     return IE_OK;
 }

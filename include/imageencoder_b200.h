@@ -97,7 +97,8 @@ int ie_session_set_header_height(ie_session *s, uint32_t full_height);
 /* Only the per-block bit lengths (first pass of a sharded encode): *d_total_bits = sum over the shard's blocks. */
 int ie_image_bits_dev(ie_session *s, const uint8_t *d_raw, uint32_t width, uint32_t height,
                       const uint16_t *quant, int use_rle, uint64_t *d_total_bits, void *stream);
-/* Decode of a plain (not Huffman-coded) device-resident stream whose header starts at bit `start_bit`. */
+/* Decode of a plain (not Huffman-coded) device-resident stream whose header starts at bit `start_bit`.
+ * d_enc must be 16-byte aligned (cudaMalloc'ed buffers are) and readable up to enc_bytes rounded up to 4. */
 int ie_decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, uint64_t start_bit,
                         uint8_t *d_raw_out, size_t raw_cap, uint32_t *width, uint32_t *height, void *stream);
 /* Byte-wise Huffman stage over a device-resident, byte-rounded plain stream (Huffman.cpp:232-344).
