@@ -47,7 +47,8 @@ struct ParseParams {
     int *err;
     // speculative path
     uint2 *spec_exit;                       // [ngroups] (exit offset | kDead, blocks started in the group)
-    unsigned *spec_flags;                   // [0] number of groups repaired in the last round, [1] spec_ok
+    unsigned *spec_flags;                   // [0] CTA ticket of parse_spec_check, [1] spec_ok, [2] unused, [3] first inconsistent group
+    unsigned *walk_base;                    // [nwalk] block count per walk CTA, then (in place) its exclusive scan
 };
 
 __device__ __forceinline__ unsigned parse_read_bits(const uint8_t *__restrict__ s, unsigned long long total_bits, unsigned long long p, int n) {
@@ -189,37 +190,41 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 
 struct StagedStream {
     const unsigned *w;                 // shared memory, raw little-endian words of the stream
-    unsigned long long w0;             // index (in 32-bit words of the stream) of w[0]
-    unsigned long long total;          // stream size in bits
+    unsigned long long base;           // absolute bit of w[0]
+    unsigned total_rel;                // stream end relative to base (clamped)
 };
 
-// stage the words holding bits [first_bit, last_bit) (+ the 64-bit header window) of the stream; returns the view
+// stage the words holding bits [first_bit, last_bit) (+ the 64-bit header window) of the stream; returns the view.
+// Positions inside the view are 32-bit offsets from `base` (a CTA's range is < 2^20 bits).
 __device__ __forceinline__ StagedStream stage_stream(unsigned *s_w, unsigned cap_words, const uint8_t *enc, unsigned long long total,
                                                      unsigned long long first_bit, unsigned long long last_bit) {
     StagedStream st;
-    st.total = total;
     st.w = s_w;
-    st.w0 = (first_bit >> 7) << 2;                                          // 16-byte granules
+    const unsigned long long w0 = (first_bit >> 7) << 2;                   // 16-byte granules
+    st.base = w0 * 32;
+    st.total_rel = (unsigned)min(total - min(total, st.base), 0x7FFFFFFFull);
     const unsigned long long nbytes = ((total + 31) >> 5) << 2;            // readable bytes (whole words, as block_bits_at)
-    const unsigned long long b0 = st.w0 * 4;
+    const unsigned long long b0 = w0 * 4;
     unsigned long long b1 = ((last_bit + 64 + 127) >> 7) << 4;
     if (b1 > b0 + (unsigned long long)cap_words * 4) b1 = b0 + (unsigned long long)cap_words * 4;
-    for (unsigned long long b = b0 + (unsigned long long)threadIdx.x * 16; b < b1; b += (unsigned long long)blockDim.x * 16) {
+    const unsigned n16 = (unsigned)((b1 - b0) >> 4);
+    for (unsigned i = threadIdx.x; i < n16; i += blockDim.x) {
+        const unsigned long long b = b0 + (unsigned long long)i * 16;
         const unsigned have = (b >= nbytes) ? 0u : (unsigned)min(16ull, nbytes - b);
-        cp_async16_zfill(s_w + ((b - b0) >> 2), enc + (have ? b : 0ull), have);
+        cp_async16_zfill(s_w + i * 4, enc + (have ? b : 0ull), have);
     }
     cp_async_wait_all();
     __syncthreads();
     return st;
 }
 
-// block_bits_at on the staged copy (same result for every p inside the staged range)
-__device__ __forceinline__ unsigned block_bits_staged(const StagedStream &st, unsigned long long p, int NN, int rle) {
-    const unsigned i = (unsigned)((p >> 5) - st.w0);
+// block_bits_at on the staged copy, `rel` < total_rel relative to the view's base (same result as block_bits_at)
+__device__ __forceinline__ unsigned block_bits_staged(const StagedStream &st, unsigned rel, int NN, int rle) {
+    const unsigned i = rel >> 5;
     const unsigned w0 = __byte_perm(st.w[i], 0, 0x0123);
     const unsigned w1 = __byte_perm(st.w[i + 1], 0, 0x0123);                // zero past the last word (zero fill)
-    unsigned v = __funnelshift_l(w1, w0, (unsigned)(p & 31));
-    if (p + 32 > st.total) v &= ~((st.total - p >= 32) ? 0u : (0xFFFFFFFFu >> (unsigned)(st.total - p)));
+    unsigned v = __funnelshift_l(w1, w0, rel & 31u);
+    if (rel + 32u > st.total_rel) v &= ~(0xFFFFFFFFu >> (st.total_rel - rel));      // 1..31 bits left
     const unsigned w = v >> 28;
     unsigned len = (unsigned)NN;
     if (rle) len = w ? ((v << 4) >> (32 - w)) : 0u;
@@ -227,21 +232,27 @@ __device__ __forceinline__ unsigned block_bits_staged(const StagedStream &st, un
     return 4u + (rle ? w : 0u) + len * w;
 }
 
-// walks the chain from absolute bit `pos` (inside or before the group) to the group's end
-template <class Src>
-__device__ __forceinline__ uint2 walk_group_t(const Src &src, int NN, int rle, unsigned long long total, unsigned long long pos,
-                                              unsigned long long g_end);
-struct GlobalSrc { const uint8_t *enc; unsigned long long total; };
-__device__ __forceinline__ unsigned src_block_bits(const GlobalSrc &g, unsigned long long p, int NN, int rle) { return block_bits_at(g.enc, g.total, p, NN, rle); }
-__device__ __forceinline__ unsigned src_block_bits(const StagedStream &s, unsigned long long p, int NN, int rle) { return block_bits_staged(s, p, NN, rle); }
-template <class Src>
-__device__ __forceinline__ uint2 walk_group_t(const Src &src, int NN, int rle, unsigned long long total, unsigned long long pos,
-                                              unsigned long long g_end) {
+// walks the chain from `rel` to the group's end (both relative to the view): (exit offset | kDead, blocks started)
+__device__ __forceinline__ uint2 walk_group_staged(const StagedStream &st, int NN, int rle, unsigned rel, unsigned g_end_rel) {
+    unsigned cnt = 0;
+    const unsigned lim = min(st.total_rel, g_end_rel);
+    while (rel < lim) {
+        const unsigned bits = block_bits_staged(st, rel, NN, rle);
+        if (bits == kBadBlock) return make_uint2(kDead, cnt);
+        rel += bits;
+        cnt++;
+    }
+    if (rel >= st.total_rel) return make_uint2(kDead, cnt);
+    return make_uint2(rel - g_end_rel, cnt);
+}
+
+// the same on global memory (seam repairs)
+__device__ __forceinline__ uint2 walk_group(const ParseParams &p, unsigned long long total, unsigned long long pos, unsigned long long g_end) {
     unsigned cnt = 0;
     while (true) {
         if (pos >= total) return make_uint2(kDead, cnt);
         if (pos >= g_end) return make_uint2((unsigned)(pos - g_end), cnt);
-        const unsigned bits = src_block_bits(src, pos, NN, rle);
+        const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
         if (bits == kBadBlock) return make_uint2(kDead, cnt);
         pos += bits;
         cnt++;
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(kWalkGroups) parse_spec_walk(const ParseParams
     extern __shared__ __align__(16) unsigned s_stage[];
     __shared__ unsigned s_entry[kWalkGroups], s_exit[kWalkGroups];
     const unsigned g = blockIdx.x * kWalkGroups + threadIdx.x;
-    if (g == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; p.spec_flags[2] = 0; }
+    if (g == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; p.spec_flags[2] = 0; p.spec_flags[3] = 0xFFFFFFFFu; }
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
     const unsigned lead = (p.NN == 64) ? 8192u : 4096u;
@@ -269,18 +280,20 @@ __global__ void __launch_bounds__(kWalkGroups) parse_spec_walk(const ParseParams
         return;
     }
     const StagedStream st = stage_stream(s_stage, kStageWords, p.enc, total, c_first, c_end);
-    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
-    unsigned long long pos = (g == 0 || g_start < B0 + lead) ? B0 : g_start - lead;
+    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits;
+    const unsigned g_rel = (unsigned)(g_start - st.base), g_end_rel = g_rel + kGroupBits;     // CTA-local: fits 32 bits
     unsigned entry;
     uint2 ex = make_uint2(kDead, 0u);
     if (g >= p.ngroups || g_start >= total) { entry = kDead; }
     else {
-        while (pos < g_start) {                            // lead-in on an arbitrary phase; garbage headers just slide by a bit
-            const unsigned bits = block_bits_staged(st, pos, p.NN, p.use_rle);
-            pos += (bits == kBadBlock) ? 1u : bits;
+        unsigned rel = (g == 0 || g_start < B0 + lead) ? (unsigned)(B0 - st.base) : g_rel - lead;
+        const unsigned lim = min(g_rel, st.total_rel);
+        while (rel < lim) {                                // lead-in on an arbitrary phase; garbage headers just slide by a bit
+            const unsigned bits = block_bits_staged(st, rel, p.NN, p.use_rle);
+            rel += (bits == kBadBlock) ? 1u : bits;
         }
-        entry = (pos >= total) ? kDead : (unsigned)(pos - g_start);
-        if (entry != kDead) ex = walk_group_t(st, p.NN, p.use_rle, total, pos, g_end);
+        entry = (rel >= st.total_rel) ? kDead : rel - g_rel;
+        if (entry != kDead) ex = walk_group_staged(st, p.NN, p.use_rle, rel, g_end_rel);
     }
     s_entry[threadIdx.x] = entry;
     s_exit[threadIdx.x] = ex.x;
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(kWalkGroups) parse_spec_walk(const ParseParams
         if (redo) {
             entry = want;
             ex = (want == kDead || want >= (unsigned)kGroupBits) ? make_uint2(kDead, 0u)
-                                                               : walk_group_t(st, p.NN, p.use_rle, total, g_start + want, g_end);
+                                                               : walk_group_staged(st, p.NN, p.use_rle, g_rel + want, g_end_rel);
         }
         __syncthreads();
         if (redo) { s_entry[t] = entry; s_exit[t] = ex.x; }
@@ -317,75 +330,75 @@ __global__ void __launch_bounds__(64) parse_spec_boundary(const ParseParams p) {
     if (k == 0 || g >= p.ngroups) return;
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
-    const GlobalSrc src{p.enc, total};
     unsigned want = p.spec_exit[g - 1].x;
     for (unsigned n = 0; n < (unsigned)kWalkGroups && g < p.ngroups; n++, g++) {
         if (p.group_entry[g].x == want) break;
         const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
         const uint2 ex = (want == kDead || want >= (unsigned)kGroupBits) ? make_uint2(kDead, 0u)
-                                                                       : walk_group_t(src, p.NN, p.use_rle, total, g_start + want, g_end);
+                                                                       : walk_group(p, total, g_start + want, g_end);
         p.group_entry[g] = make_uint2(want, 0u);
         p.spec_exit[g] = ex;
         want = ex.x;
     }
 }
 
-// final exact verification + exclusive scan of the per-group block counts (single CTA, coalesced passes over the group
-// arrays, kFinishChunk groups at a time through shared memory).  Only the groups that hold the stream's nblocks blocks
+// Final exact verification + block counts.  One thread per group: the seam in front of it must agree (first disagreeing
+// group -> spec_flags[3]); every CTA adds up the blocks of its kWalkGroups groups.  The last CTA to finish (ticket) turns
+// the per-CTA counts into their exclusive scan and decides spec_ok.  Only the groups that hold the stream's nblocks blocks
 // have to be consistent: behind the last block the chain runs into whatever follows (pad bits, the next frame's motion
 // vectors), where the speculative walks may legitimately disagree.
-constexpr unsigned kFinishChunk = 8192;
-__global__ void __launch_bounds__(1024) parse_spec_finish(const ParseParams p) {
-    __shared__ unsigned s_cnt[kFinishChunk];
-    __shared__ unsigned s_warp[32];
-    __shared__ unsigned s_firstbad, s_base;
-    if (threadIdx.x == 0) { s_firstbad = p.ngroups; s_base = 0; }
-    __syncthreads();
-    // pass 1: first inconsistent seam
-    unsigned fb = p.ngroups;
-    for (unsigned g = threadIdx.x + 1; g < p.ngroups; g += 1024)
-        if (p.spec_exit[g - 1].x != p.group_entry[g].x) { fb = g; break; }        // strided: the smallest of this thread
-    if (fb < p.ngroups) atomicMin(&s_firstbad, fb);
-    __syncthreads();
-    const unsigned firstbad = s_firstbad;
-    // pass 2: exclusive scan of the counts, chunk by chunk
-    constexpr unsigned PER = kFinishChunk / 1024;
-    for (unsigned c0 = 0; c0 < p.ngroups; c0 += kFinishChunk) {
-        const unsigned n = min(kFinishChunk, p.ngroups - c0);
-        for (unsigned i = threadIdx.x; i < kFinishChunk; i += 1024) s_cnt[i] = (i < n) ? p.spec_exit[c0 + i].y : 0u;
-        __syncthreads();
-        unsigned v[PER], sum = 0;
+__global__ void __launch_bounds__(kWalkGroups) parse_spec_check(const ParseParams p) {
+    __shared__ unsigned s_part[kWalkGroups];
+    __shared__ unsigned s_last;
+    const unsigned g = blockIdx.x * kWalkGroups + threadIdx.x;
+    unsigned cnt = 0;
+    if (g < p.ngroups) {
+        cnt = p.spec_exit[g].y;
+        if (g > 0 && p.spec_exit[g - 1].x != p.group_entry[g].x) atomicMin(&p.spec_flags[3], g);
+    }
 #pragma unroll
-        for (unsigned j = 0; j < PER; j++) { v[j] = s_cnt[threadIdx.x * PER + j]; sum += v[j]; }
-        unsigned inc = sum;
+    for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned sum = 0;
+        for (int w = 0; w < kWalkGroups / 32; w++) sum += s_part[w];
+        p.walk_base[blockIdx.x] = sum;
+        __threadfence();
+        s_last = (atomicAdd(&p.spec_flags[0], 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // exclusive scan of walk_base[0 .. gridDim.x), kWalkGroups values at a time (read past L1: other CTAs wrote them)
+    unsigned run = 0;
+    for (unsigned c0 = 0; c0 < gridDim.x; c0 += kWalkGroups) {
+        const unsigned i = c0 + threadIdx.x;
+        const unsigned v = (i < gridDim.x) ? __ldcg(p.walk_base + i) : 0u;
+        unsigned inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)(threadIdx.x & 31) >= d) inc += o; }
-        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
         __syncthreads();
-        if (threadIdx.x < 32) {
-            unsigned w = s_warp[threadIdx.x];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, w, d); if ((int)threadIdx.x >= d) w += o; }
-            s_warp[threadIdx.x] = w;
-        }
+        if ((threadIdx.x & 31) == 31) s_part[threadIdx.x >> 5] = inc;
         __syncthreads();
-        unsigned run = s_base + inc - sum + ((threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u);
-#pragma unroll
-        for (unsigned j = 0; j < PER; j++) { s_cnt[threadIdx.x * PER + j] = run; run += v[j]; }
-        __syncthreads();
-        for (unsigned i = threadIdx.x; i < n; i += 1024) {
-            const unsigned g = c0 + i, base = s_cnt[i];
-            // groups from the first inconsistent one on are switched off (they only hold blocks beyond nblocks, checked here)
-            p.group_entry[g] = make_uint2(g >= firstbad ? kDead : p.group_entry[g].x, base);
-            if (g == firstbad && base < p.nblocks) p.spec_flags[2] = 1;            // a needed group is unverified: not usable
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_base += s_warp[31];
-        __syncthreads();
+        unsigned before = run;
+        for (unsigned w = 0; w < (threadIdx.x >> 5); w++) before += s_part[w];
+        if (i < gridDim.x) p.walk_base[i] = before + inc - v;
+        for (int w = 0; w < kWalkGroups / 32; w++) run += s_part[w];
     }
-    __threadfence_block();
     __syncthreads();
-    if (threadIdx.x == 0) p.spec_flags[1] = p.spec_flags[2] ? 0u : 1u;
+    if (threadIdx.x == 0) {
+        const unsigned firstbad = __ldcg(&p.spec_flags[3]);
+        unsigned ok = 1;
+        if (firstbad < p.ngroups) {
+            // blocks that start before the first unverified group; if that does not cover the stream's blocks, give up
+            __threadfence();
+            unsigned base = p.walk_base[firstbad / kWalkGroups];
+            for (unsigned gg = firstbad / kWalkGroups * kWalkGroups; gg < firstbad; gg++) base += p.spec_exit[gg].y;
+            if (base < p.nblocks) ok = 0;
+        }
+        p.spec_flags[1] = ok;
+    }
 }
 
 // One CTA = kWalkGroups groups on a staged copy: every thread walks its group's TRUE chain and writes block_off[].
@@ -399,18 +412,34 @@ __global__ void __launch_bounds__(kWalkGroups) parse_emit_offsets(const ParsePar
     // a block that starts inside the CTA's last group may end (and the next header be read) up to E bits behind it; the
     // walk itself only reads headers of blocks that START before the group's end
     const StagedStream st = stage_stream(s_stage, kStageWords, p.enc, total, c_start, min(total, c_start + (unsigned long long)kWalkGroups * kGroupBits));
-    if (g >= p.ngroups) return;
-    const uint2 ge = p.group_entry[g];
-    if (ge.x == kDead) return;
-    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
-    unsigned long long pos = g_start + ge.x;
-    unsigned idx = ge.y;
-    while (pos < g_end && pos < total && idx < p.nblocks) {
-        const unsigned bits = block_bits_staged(st, pos, p.NN, p.use_rle);
-        if (bits == kBadBlock) { if (p.err) atomicExch(p.err, IE_EFORMAT); pos = total; break; }   // malformed stream
-        p.block_off[idx++] = pos;
-        pos = min(pos + bits, total);
+    // entry offset and first block index of the group: from the exact kernels (group_entry), or, when the speculative
+    // parse verified, from the walk (entry) and the scanned block counts (walk_base + the counts of the CTA's earlier groups)
+    __shared__ unsigned s_wsum;
+    uint2 ge = (g < p.ngroups) ? p.group_entry[g] : make_uint2(kDead, 0u);
+    if (p.spec_flags[1]) {                                   // uniform
+        const unsigned cnt = (g < p.ngroups) ? p.spec_exit[g].y : 0u;
+        unsigned inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)(threadIdx.x & 31) >= d) inc += o; }
+        if (threadIdx.x == 31) s_wsum = inc;
+        __syncthreads();
+        static_assert(kWalkGroups == 64, "two warps");
+        ge.y = p.walk_base[blockIdx.x] + inc - cnt + ((threadIdx.x >= 32) ? s_wsum : 0u);
+        if (g >= p.spec_flags[3]) ge.x = kDead;              // unverified tail: holds no block of this stream
     }
+    if (g >= p.ngroups || ge.x == kDead) return;
+    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits;
+    const unsigned g_end_rel = (unsigned)(g_start - st.base) + kGroupBits;
+    unsigned rel = (unsigned)(g_start - st.base) + ge.x;
+    unsigned idx = ge.y;
+    const unsigned lim = min(g_end_rel, st.total_rel);
+    while (rel < lim && idx < p.nblocks) {
+        const unsigned bits = block_bits_staged(st, rel, p.NN, p.use_rle);
+        if (bits == kBadBlock) { if (p.err) atomicExch(p.err, IE_EFORMAT); rel = st.total_rel; break; }   // malformed stream
+        p.block_off[idx++] = st.base + rel;
+        rel = min(rel + bits, st.total_rel);
+    }
+    const unsigned long long pos = st.base + rel;
     if (idx <= p.nblocks && pos >= total) {
         // the chain reached the end of the stream in this group: every remaining block starts (and ends) at `total`
         for (; idx < p.nblocks; idx++) p.block_off[idx] = total;
@@ -431,7 +460,7 @@ static void parse_sizes(size_t span_bits, int N, unsigned &E, unsigned &ngroups,
 size_t parse_scratch_bytes(size_t enc_bytes, int N) {
     unsigned E, ng, ns;
     parse_sizes(enc_bytes * 8, N, E, ng, ns);
-    return ((size_t)ng * E + (size_t)ns * E + ns + ng + ng + 8) * sizeof(uint2) + 256;
+    return ((size_t)ng * E + (size_t)ns * E + ns + ng + ng + 8) * sizeof(uint2) + 256 + ((size_t)ng / kWalkGroups + 8) * sizeof(unsigned);
 }
 
 // Fills d.block_off[0..nblocks] for one stream (and advances d.cursor when the last block lies inside the span).
@@ -454,6 +483,7 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     p.group_entry = s; s += p.ngroups;
     p.spec_exit = s; s += p.ngroups;
     p.spec_flags = reinterpret_cast<unsigned *>(s);
+    p.walk_base = p.spec_flags + 8;
     p.block_off = d.block_off;
     p.cursor_out = d.cursor;
     p.err = d.err;
@@ -468,7 +498,7 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     IE_CUDA(cudaFuncSetAttribute(parse_emit_offsets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
     parse_spec_walk<<<nwalk, kWalkGroups, stage_bytes, stream>>>(p);
     parse_spec_boundary<<<(nwalk + 63) / 64, 64, 0, stream>>>(p);
-    parse_spec_finish<<<1, 1024, 0, stream>>>(p);
+    parse_spec_check<<<nwalk, kWalkGroups, 0, stream>>>(p);
     IE_DBG_STEP("parse_spec");
     parse_group_tables<<<std::min(p.ngroups, 148u * 8u), 64, smem, stream>>>(p);
     IE_DBG_STEP("parse_group_tables");
