@@ -6,6 +6,7 @@
 //                         reference's summation order with exact zero-skipping, +128, clamp, truncate to u8
 //                         (Block.cpp:441-472, 162-177, 99-107; algo.cpp:343-363).
 #include "decode_image.cuh"
+#include "stage.cuh"
 #include "transform.cuh"
 #include "transform_fast.cuh"
 #include <atomic>
@@ -166,48 +167,62 @@ template <int N, bool ADD>
 __global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodeParams p) {
     constexpr int NN = N * N;
     constexpr int STRIDE = NN + 2;
+    // the bits of the CTA's 128 blocks are one contiguous span of the stream (<= 128 * (4 + 16 + 16 NN) bits): staged with
+    // 16-byte cp.async, then every lane reads its block's fields from shared memory (no bounds or end-of-stream tests)
+    constexpr unsigned kStage = (128u * (4 + 16 + 16 * NN) + 31) / 32 + 12;
     __shared__ short s_coef[128 * STRIDE];
+    __shared__ __align__(16) unsigned s_bits[kStage];
     const unsigned img = blockIdx.y;
-    const unsigned gb = blockIdx.x * 128 + threadIdx.x;
-    if (gb >= p.nblocks) return;
+    const unsigned first = blockIdx.x * 128;
+    const unsigned gb = first + threadIdx.x;
     const uint8_t *s = p.enc + (size_t)img * p.enc_stride;
     const unsigned long long total = p.enc_bits[img];
     const unsigned long long *off = p.block_off + (size_t)img * (p.nblocks + 1);
     const BlockTables *tab = p.tab;
+    const StagedStream st = stage_stream(s_bits, kStage, s, total, off[first], off[min(first + 128u, p.nblocks)]);
+    if (gb >= p.nblocks) return;
 
     // ---- fields (Block.cpp:441-472) -------------------------------------------------------------------------
-    BitReader br;
-    br.init(s, total, off[gb]);
-    const int w = (int)br.get(4);
+    unsigned pos = (unsigned)(off[gb] - st.base);
+    auto peek = [&](unsigned at) -> unsigned {                 // 32 stream bits starting at `at`, MSB first
+        const unsigned i = at >> 5;
+        return __funnelshift_l(__byte_perm(st.w[i + 1], 0, 0x0123), __byte_perm(st.w[i], 0, 0x0123), at & 31u);
+    };
+    const unsigned head = peek(pos);
+    const int w = (int)(head >> 28);
     int len = NN;
-    if (p.use_rle) len = (int)br.get(w);
+    if (p.use_rle) len = w ? (int)((head << 4) >> (32 - w)) : 0;
+    pos += 4u + (p.use_rle ? (unsigned)w : 0u);
     if (len > NN) { atomicExch(p.err, IE_EFORMAT); len = NN; }   // the reference indexes out of bounds here
     short *cf = s_coef + threadIdx.x * STRIDE;
     unsigned *cfw = reinterpret_cast<unsigned *>(cf);
 #pragma unroll
     for (int j = 0; j < NN / 2; j++) cfw[j] = 0u;
-    unsigned long long nzmask = 0;           // raster positions of the non-zero coefficients
-    const int sh = 32 - w;
-    for (int k = 0; k < len; k++) {
-        const int v = (w == 0) ? 0 : ((int)(br.get(w) << sh) >> sh);          // util::shift_signed<int16_t>
-        if (v != 0) {
-            cf[k] = (short)v;
-            nzmask |= 1ull << ((N == 8) ? c_zz8[k] : c_zz4[k]);
+    if (w != 0) {
+        const int sh = 32 - w;
+        for (int k = 0; k < len; k++) {
+            const int v = (int)peek(pos) >> sh;                    // util::shift_signed<int16_t>: the top w bits, sign extended
+            pos += (unsigned)w;
+            if (v != 0) cf[k] = (short)v;
         }
     }
     // ---- fast inverse transform --------------------------------------------------------------------------------
     float x[NN];
     float S = 0.f;
+    unsigned long long nzmask = 0;
 #pragma unroll
     for (int uv = 0; uv < NN; uv++) {
         const int k = (N == 8) ? kZigzagInvD8[uv] : kZigzagInvD4[uv];
-        const float d = (float)(int)cf[k] * p.k2[uv];                         // coefficient * Q * C(u)C(v)
+        const int c = cf[k];
+        if (c != 0) nzmask |= 1ull << uv;                                     // raster positions of the non-zero coefficients
+        const float d = (float)c * p.k2[uv];                                  // coefficient * Q * C(u)C(v)
         x[uv] = d;
         S += fabsf(d);
     }
     idct2d_fast<N>(x);
     const float delta = (32.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
-    const bool all_unsure = !(delta < 0.49f);                                   // absurd coefficients: take the exact path everywhere
+    // unsure: |frac - 0.5| >= 0.5 - delta; absurd coefficients (delta >= 0.49) take the exact path everywhere
+    const float hi_thr = (delta < 0.49f) ? 0.5f - delta : 0.f;
     const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
     uint8_t *dst = p.out + (size_t)img * p.out_stride + (size_t)(byi * N) * p.pitch + (size_t)bxi * N;
     unsigned outw[N * (N / 4)];
@@ -221,19 +236,22 @@ __global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodePar
         }
 #pragma unroll
         for (int q4 = 0; q4 < N / 4; q4++) {
-            unsigned word = 0;
+            unsigned fl[4];
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 const int ij = y * N + q4 * 4 + b;
                 float v = x[ij] + 128.f;
                 if (ADD) v += (float)((curw[q4] >> (8 * b)) & 0xffu);
-                const float vc = fminf(fmaxf(v, 0.f), 255.f);
-                const float r = (vc + kMagic) - kMagic;                       // rn(vc)
-                const float fl = (r > vc) ? r - 1.f : r;                      // floor(vc)
-                // an integer boundary k in [1, 255] within delta of v could flip the truncation
-                if ((fabsf(v - r) <= delta && r >= 1.f && r <= 255.f) || all_unsure) unsure |= 1ull << ij;
-                word |= (unsigned)(int)fl << (8 * b);
+                // the reference truncates after clamping to [0, 255] (Block.cpp:103): floor(u) with u clamped to
+                // [0.5, 255.5] is the same pixel, and u sits exactly on x.5 wherever the clamp decided
+                const float u = fminf(fmaxf(v, 0.5f), 255.5f);
+                const float fm = __fadd_rd(u, 8388608.0f);                    // 2^23 + floor(u): the pixel is the low byte
+                const float frac = u - (fm - 8388608.0f);                     // [0, 1), exact
+                // an integer boundary within delta of u could flip the truncation
+                if (fabsf(frac - 0.5f) >= hi_thr) unsure |= 1ull << ij;
+                fl[b] = __float_as_uint(fm);
             }
+            const unsigned word = __byte_perm(__byte_perm(fl[0], fl[1], 0x0040), __byte_perm(fl[2], fl[3], 0x0040), 0x5410);
             outw[y * (N / 4) + q4] = word;
         }
     }
