@@ -180,16 +180,23 @@ __global__ void __launch_bounds__(64) parse_down_super(const ParseParams p) {
 constexpr int kSpecRounds = 3;            // repair rounds inside a CTA
 constexpr int kWalkGroups = 64;           // groups (= threads) per CTA of the staged kernels
 
-// block_bits_at on the staged copy, `rel` < total_rel relative to the view's base (same result as block_bits_at)
-__device__ __forceinline__ unsigned block_bits_staged(const StagedStream &st, unsigned rel, int NN, int rle) {
+// One step of a walk on the staged copy, `rel` < lim relative to the view's base.  Returns the bits consumed and the number
+// of blocks they hold: an all-zero block is 4 zero bits (bit_len 0, no length/values), so a run of zero nibbles is a run of
+// blocks and is taken in one step (up to 8, never starting a block at or past `lim`).  0 blocks = invalid length field.
+__device__ __forceinline__ unsigned staged_step(const StagedStream &st, unsigned rel, unsigned lim, int NN, int rle, unsigned &blocks) {
     const unsigned i = rel >> 5;
     const unsigned w0 = __byte_perm(st.w[i], 0, 0x0123);
-    const unsigned w1 = __byte_perm(st.w[i + 1], 0, 0x0123);                // zero past the last word (zero fill)
-    unsigned v = __funnelshift_l(w1, w0, rel & 31u);
+    const unsigned w1 = __byte_perm(st.w[i + 1], 0, 0x0123);                // zero past the end of the stream (stage_stream)
+    const unsigned v = __funnelshift_l(w1, w0, rel & 31u);
     const unsigned w = v >> 28;
+    if (w == 0) {
+        const unsigned k = min(min((unsigned)__clz((int)v) >> 2, 8u), (lim - rel + 3u) >> 2);
+        blocks = k;
+        return 4u * k;
+    }
     unsigned len = (unsigned)NN;
-    if (rle) len = w ? ((v << 4) >> (32 - w)) : 0u;
-    if (len > (unsigned)NN) return kBadBlock;
+    if (rle) len = (v << 4) >> (32 - w);
+    blocks = (len > (unsigned)NN) ? 0u : 1u;
     return 4u + (rle ? w : 0u) + len * w;
 }
 
@@ -198,10 +205,11 @@ __device__ __forceinline__ uint2 walk_group_staged(const StagedStream &st, int N
     unsigned cnt = 0;
     const unsigned lim = min(st.total_rel, g_end_rel);
     while (rel < lim) {
-        const unsigned bits = block_bits_staged(st, rel, NN, rle);
-        if (bits == kBadBlock) return make_uint2(kDead, cnt);
+        unsigned nb;
+        const unsigned bits = staged_step(st, rel, lim, NN, rle, nb);
+        if (nb == 0) return make_uint2(kDead, cnt);
         rel += bits;
-        cnt++;
+        cnt += nb;
     }
     if (rel >= st.total_rel) return make_uint2(kDead, cnt);
     return make_uint2(rel - g_end_rel, cnt);
@@ -249,9 +257,10 @@ __global__ void __launch_bounds__(kWalkGroups) parse_spec_walk(const ParseParams
     else {
         unsigned rel = (g == 0 || g_start < B0 + lead) ? (unsigned)(B0 - st.base) : g_rel - lead;
         const unsigned lim = min(g_rel, st.total_rel);
-        while (rel < lim) {                                // lead-in on an arbitrary phase; garbage headers just slide by a bit
-            const unsigned bits = block_bits_staged(st, rel, p.NN, p.use_rle);
-            rel += (bits == kBadBlock) ? 1u : bits;
+        while (rel < lim) {                                // lead-in on an arbitrary phase; invalid headers slide by a bit
+            unsigned nb;
+            const unsigned bits = staged_step(st, rel, lim, p.NN, p.use_rle, nb);
+            rel += nb ? bits : 1u;
         }
         entry = (rel >= st.total_rel) ? kDead : rel - g_rel;
         if (entry != kDead) ex = walk_group_staged(st, p.NN, p.use_rle, rel, g_end_rel);
@@ -395,9 +404,10 @@ __global__ void __launch_bounds__(kWalkGroups) parse_emit_offsets(const ParsePar
     unsigned idx = ge.y;
     const unsigned lim = min(g_end_rel, st.total_rel);
     while (rel < lim && idx < p.nblocks) {
-        const unsigned bits = block_bits_staged(st, rel, p.NN, p.use_rle);
-        if (bits == kBadBlock) { if (p.err) atomicExch(p.err, IE_EFORMAT); rel = st.total_rel; break; }   // malformed stream
-        p.block_off[idx++] = st.base + rel;
+        unsigned nb;
+        const unsigned bits = staged_step(st, rel, lim, p.NN, p.use_rle, nb);
+        if (nb == 0) { if (p.err) atomicExch(p.err, IE_EFORMAT); rel = st.total_rel; break; }             // malformed stream
+        for (unsigned j = 0; j < nb && idx < p.nblocks; j++) p.block_off[idx++] = st.base + rel + 4u * j;  // nb > 1: zero blocks
         rel = min(rel + bits, st.total_rel);
     }
     const unsigned long long pos = st.base + rel;
