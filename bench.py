@@ -199,7 +199,6 @@ def ours(args):
             device.encode_image_dev(sess, d_raw[k], q, True, d_out[k], d_bits[k:k + 1])
         else:
             sharded[k].encode(d_raw[k], q, True, rank)
-            d_bits[k:k + 1].copy_(sharded[k].d_bits)
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,9 +206,14 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    for k in range(RING):          # set-up, not warm-up: every ring slot allocates its session scratch on first use
+        step(k)
+    barrier()
     for i in range(args.warmup):
         step(i)
     barrier()
+    if sharded is not None:
+        d_bits = torch.cat([sh.d_total for sh in sharded])
     out_bytes = [int((int(b) + 7) // 8) for b in d_bits.cpu().tolist()]
     if 0 in out_bytes[: min(RING, args.warmup)]:
         raise SystemExit("warm-up produced an empty stream")
@@ -242,12 +246,9 @@ def ours(args):
     try:
         sess_d = device.Session(device.Session.IMAGE_DECODE, W, H, BLOCK)
         d_dec = torch.empty(W * H, dtype=torch.uint8, device="cuda")
+        # (multi-GPU runs: a shard is not a stream of its own, the decode figure is reported by the N=1 run)
         if sharded is None:
             d_stream, nb = d_out[0], out_bytes[0]
-        else:
-            # a shard stream has no header of its own except on rank 0: decode rank 0's shard only as a per-rank figure
-            d_stream, nb = sharded[0].d_local, int((int(sharded[0].d_bits.item()) + 7) // 8)
-        if rank == 0 or sharded is None:
             for _ in range(2):
                 device.decode_image_dev(sess_d, d_stream, nb, d_dec, 1)
             torch.cuda.synchronize()

@@ -89,6 +89,35 @@ __global__ void stream_init_kernel(uint8_t *out, size_t out_stride, unsigned ima
     if (threadIdx.x == 0) counter[img] = total;
 }
 
+// The same for a shard of a multi-GPU stream: the shard's first bit in the global stream is the sum of the totals of the
+// shards in front of it (a device array, straight from the all-gather); the local buffer starts at the 128-bit chunk that
+// holds that bit, so the prefix is (first % 128) zero bits, then the header (rank 0 only).
+__global__ void stream_init_shard_kernel(uint8_t *out, HeaderParam hdr, const unsigned long long *shard_totals, unsigned shard_index,
+                                         unsigned long long *counter, unsigned long long *bit_base, unsigned long long *first_out) {
+    __shared__ unsigned s_fb;
+    if (threadIdx.x == 0) {
+        unsigned long long first = 0;
+        for (unsigned i = 0; i < shard_index; i++) first += shard_totals[i];
+        s_fb = (unsigned)(first % 128);
+        if (first_out) *first_out = first;
+    }
+    __syncthreads();
+    const unsigned first_bit = s_fb;
+    const unsigned total = first_bit + hdr.bits;
+    const unsigned nwords = ((total + 127) / 128) * 4;
+    unsigned *o = reinterpret_cast<unsigned *>(out);
+    for (unsigned i = threadIdx.x; i < max(nwords, 4u); i += blockDim.x) {
+        const long long hb = (long long)i * 32 - (long long)first_bit;
+        const int sh = (int)(((hb % 32) + 32) % 32);
+        const long long wi = (hb - sh) / 32;               // floor division
+        const unsigned hi = (wi >= 0 && wi < kHdrWordsMax) ? hdr.words[wi] : 0u;
+        const unsigned lo = (wi + 1 >= 0 && wi + 1 < kHdrWordsMax) ? hdr.words[wi + 1] : 0u;
+        const unsigned v = sh ? ((hi << sh) | (lo >> (32 - sh))) : hi;
+        o[i] = __byte_perm(v, 0, 0x0123);
+    }
+    if (threadIdx.x == 0) { counter[0] = total; bit_base[0] = total; }
+}
+
 int launch_stream_init(uint8_t *out, size_t out_stride, unsigned images, const HeaderParam &hdr, unsigned first_bit,
                        unsigned long long *counter, cudaStream_t stream) {
     stream_init_kernel<<<images, 64, 0, stream>>>(out, out_stride, images, hdr, first_bit, counter);
@@ -116,7 +145,9 @@ int make_quant(QuantParam &q, const uint16_t *quant, int N) {
 // Encode `images` equally sized images that are resident on the device.
 int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, unsigned images, uint32_t W, uint32_t H, int N,
                       const uint16_t *quant, int use_rle, int lead_bit, int write_header, unsigned first_bit, int bits_only,
-                      uint8_t *d_out, size_t out_stride, size_t out_cap, cudaStream_t stream, int append, uint32_t header_H) {
+                      uint8_t *d_out, size_t out_stride, size_t out_cap, cudaStream_t stream, int append, uint32_t header_H, int split) {
+    // split: only the tile kernel runs (tile images stay in the session's scratch), the parameters and the header are kept in
+    // the session for ie_encode_image_end_dev
     // append: the streams continue at their device-resident bit counters (no prefix is written); header_H: the height the
     // header announces when this call encodes only the first stripe of a taller image
     IE_TRY(check_dims(W, H, N));
@@ -133,8 +164,8 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     memset(&hdr, 0, sizeof hdr);
     if (write_header && !append)
         IE_TRY(build_header(hdr, N, quant, use_rle, W, header_H ? header_H : (s->header_height ? s->header_height : H), lead_bit, 0, 0, 0, 0));
-    if (append) {
-        if (bits_only) { set_error("append and bits_only exclude each other"); return IE_EINVAL; }
+    if (append || split) {
+        if (bits_only) { set_error("append/split and bits_only exclude each other"); return IE_EINVAL; }
     } else if (!bits_only) {
         const size_t need = ((size_t)first_bit + hdr.bits + 127) / 128 * 16;
         if (out_cap < need) { set_error("output buffer too small for the header"); return IE_ENOSPC; }
@@ -148,7 +179,6 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     p.src = d_raw; p.pitch = W; p.img_stride = img_stride;
     p.bx = W / N; p.nblocks = nblocks; p.tiles_per_image = tiles;
     p.use_rle = use_rle ? 1 : 0; p.bits_only = bits_only;
-    { static const char *dbg = getenv("IE_DEBUG_SKIP"); p.debug_skip = dbg ? atoi(dbg) : 0; }
     make_quant(p.quant, quant, N);
     make_fast_quant(p.fq, quant, N, 128.0);
     p.dc_den2 = 8 * (int)quant[0]; p.dc_rcp = 1.0f / (float)p.dc_den2;
@@ -166,6 +196,15 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
         p.tile_bits = reinterpret_cast<unsigned *>(s->d_tile_meta + ntot * sizeof(unsigned long long));
     }
     // scan arrays are indexed [image][tile] with stride tiles_per_image (the allocation is at least that large)
+    if (split) {
+        p.phase = 1;
+        IE_TRY(launch_encode_tiles(N, p, images, stream));
+        p.phase = 2;
+        s->split_params = p;
+        s->split_hdr = hdr;
+        s->split_pending = true;
+        return IE_OK;
+    }
     return launch_encode_tiles(N, p, images, stream);
 }
 
@@ -323,6 +362,33 @@ int ie_encode_image_dev(ie_session *s, const uint8_t *d_raw, uint32_t W, uint32_
     cudaStream_t st = (cudaStream_t)stream;
     IE_TRY(encode_images_dev(s, d_raw, 0, 1, W, H, (int)s->N, quant, use_rle, lead_bit, write_header, (unsigned)first_bit, 0,
                              d_out, 0, out_cap, st));
+    if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, s->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return IE_OK;
+}
+
+int ie_encode_image_begin_dev(ie_session *s, const uint8_t *d_raw, uint32_t W, uint32_t H, const uint16_t *quant, int use_rle,
+                              int lead_bit, int write_header, uint64_t *d_total_bits, void *stream) {
+    if (!s || !d_raw || !d_total_bits) { set_error("NULL argument"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    IE_TRY(encode_images_dev(s, d_raw, 0, 1, W, H, (int)s->N, quant, use_rle, lead_bit, write_header, 0, 0, nullptr, 0, 0, st, 0, 0, 1));
+    return launch_tile_totals(s->split_params.tile_bits, s->split_params.tiles_per_image, 1, s->split_hdr.bits,
+                              reinterpret_cast<unsigned long long *>(d_total_bits), st);
+}
+
+int ie_encode_image_end_dev(ie_session *s, const uint64_t *d_shard_totals, uint32_t shard_index, uint8_t *d_out, size_t out_cap,
+                            uint64_t *d_out_bits, uint64_t *d_first_bit, void *stream) {
+    if (!s || !d_shard_totals || !d_out) { set_error("NULL argument"); return IE_EINVAL; }
+    if (!s->split_pending) { set_error("ie_encode_image_end_dev without ie_encode_image_begin_dev"); return IE_EINVAL; }
+    if ((uintptr_t)d_out % 16) { set_error("stream buffers must be 16-byte aligned"); return IE_EINVAL; }
+    if (out_cap < ((size_t)128 + s->split_hdr.bits + 127) / 128 * 16) { set_error("output buffer too small for the header"); return IE_ENOSPC; }
+    cudaStream_t st = (cudaStream_t)stream;
+    EncodeParams p = s->split_params;
+    s->split_pending = false;
+    p.out = d_out; p.out_stride = 0; p.out_cap = out_cap;
+    stream_init_shard_kernel<<<1, 64, 0, st>>>(d_out, s->split_hdr, reinterpret_cast<const unsigned long long *>(d_shard_totals), shard_index,
+                                              s->d_counter, p.bit_base, reinterpret_cast<unsigned long long *>(d_first_bit));
+    count_launch();
+    IE_TRY(launch_tile_copyout(p, 1, st));
     if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, s->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     return IE_OK;
 }

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
 
     // ---- phase 1b: exact recomputation of the queued guard-band coefficients, one per thread -------------------
     if (FAST) {
-        const unsigned qn = (p.debug_skip & 1) ? 0u : min(s_qn, (unsigned)kQueueCap);
+        const unsigned qn = min(s_qn, (unsigned)kQueueCap);
         if (qn) {                                                              // uniform
             for (unsigned e = threadIdx.x; e < qn; e += kThreads) {
                 const unsigned ent = s_queue[e];
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
 #pragma unroll 1
         for (int r = 0; r < BPL; r++) {
             const int lb = threadIdx.x * BPL + r;
-            if (lb >= nblk || (p.debug_skip & 2)) break;
+            if (lb >= nblk) break;
             const int w = s_w[lb], len = s_len[lb];
             const unsigned pos = s_off[lb];
             const unsigned bo = pos & 31u;
@@ -512,6 +512,39 @@ __global__ void __launch_bounds__(kThreads) tile_copyout_kernel(const EncodePara
     if (t1 == ntiles && threadIdx.x == 0) p.bit_counter[img] = G + T;
 }
 
+int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t stream) {
+    dim3 cgrid((p.tiles_per_image + kTilesPerGroup - 1) / kTilesPerGroup, images);
+    tile_copyout_kernel<<<cgrid, kThreads, 0, stream>>>(p);
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
+__global__ void __launch_bounds__(256) tile_totals_kernel(const unsigned *__restrict__ tile_bits, unsigned ntiles, unsigned long long add,
+                                                          unsigned long long *d_total) {
+    __shared__ unsigned long long s_part[8];
+    const unsigned *tb = tile_bits + (size_t)blockIdx.x * ntiles;
+    unsigned long long sum = 0;
+    for (unsigned i = threadIdx.x; i < ntiles; i += 256) sum += tb[i];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = add;
+        for (int w = 0; w < 8; w++) t += s_part[w];
+        d_total[blockIdx.x] = t;
+    }
+}
+
+int launch_tile_totals(const unsigned *tile_bits, unsigned ntiles, unsigned images, unsigned long long add, unsigned long long *d_total,
+                       cudaStream_t stream) {
+    tile_totals_kernel<<<images, 256, 0, stream>>>(tile_bits, ntiles, add, d_total);
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
 template <int N, int BPL, bool PF, bool FAST>
 static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t stream) {
     constexpr int TB = kThreads * BPL;
@@ -527,11 +560,7 @@ static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t strea
     dim3 grid(p.tiles_per_image, images);
     encode_tiles_kernel<N, BPL, PF, FAST><<<grid, kThreads, smem, stream>>>(p);
     count_launch();
-    if (!p.bits_only) {
-        dim3 cgrid((p.tiles_per_image + kTilesPerGroup - 1) / kTilesPerGroup, images);
-        tile_copyout_kernel<<<cgrid, kThreads, 0, stream>>>(p);
-        count_launch();
-    }
+    if (!p.bits_only && p.phase == 0) return launch_tile_copyout(p, images, stream);
     IE_CUDA(cudaGetLastError());
     return IE_OK;
 }

@@ -16,7 +16,6 @@ struct EncodeParams {
     unsigned tiles_per_image;
     int use_rle;
     int bits_only;                    // 1: only the bit totals (first pass of a sharded encode)
-    int debug_skip;                   // timing experiments only (IE_DEBUG_SKIP): 1 skip exact queue, 2 skip pack loop, 4 skip copy-out
     QuantParam quant;
     FastQuant fq;                     // fast-path constants + guard-band thresholds (transform_fast.cuh)
     int dc_den2;                      // 2 * 4 * Q[0][0]: exact integer DC rounding
@@ -30,6 +29,7 @@ struct EncodeParams {
     ScanState scan;                   // only the tile-boundary hand-off records are used by the image path
     uint8_t *tile_scratch;            // [images * tiles] slots of slot_bytes: packed tile images (tile-local alignment)
     size_t slot_bytes;
+    int phase;                        // 0: tile kernel + copy-out; 1: tile kernel only (tile images stay in scratch); 2: copy-out only
     unsigned *tile_bits;              // [images * tiles] bits per tile
     unsigned long long *bit_base;     // [images] bit position each stream had when this launch started
     // P-frame mode (Frame.cpp:160-244): src is the CURRENT frame (read, then overwritten with the reconstruction),
@@ -49,5 +49,8 @@ extern std::atomic<int> g_exact_transform;
 void make_fast_quant(FastQuant &fq, const uint16_t *quant, int N, double max_abs_sample);
 int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream);
 int launch_pframe_tiles(const EncodeParams &p, cudaStream_t stream);
+int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t stream);          // phase 2 of a split encode
+int launch_tile_totals(const unsigned *tile_bits, unsigned ntiles, unsigned images, unsigned long long add, unsigned long long *d_total,
+                       cudaStream_t stream);                                                   // d_total[img] = add + sum of the image's tile bits
 
 }  // namespace ie

@@ -151,87 +151,6 @@ __device__ __forceinline__ unsigned long long tile_lookback(const ScanState &st,
     return tile_resolve_prefix(st, tile, total, s_bcast);
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Field source for a tile of transform blocks (image blocks, I/P-frame micro blocks).
-// A block's bits  [4: bit_len & 15][w: length (if rle)][w * length: coefficients]  (Block.cpp:381-407) are staged in
-// shared memory as 32-bit "units" so that the packer handles ~15 bits per step instead of one coefficient:
-//   unit 0      header: ((w & 15) << w) | length  (4 + w bits)   -- or (w & 15) (4 bits) without RLE
-//   unit 1 + j  coefficient pair (2j, 2j+1): ((c0 & m) << w) | (c1 & m)  (2w bits); an odd trailing coefficient is
-//               stored alone (w bits)
-// `map` gives, for every 128-bit output chunk of the tile, the block that holds the chunk's first bit (no search).
-// ---------------------------------------------------------------------------------------------------------
-struct UnitTile {
-    const unsigned *units;       // [nblk][stride] (shared memory)
-    const unsigned char *w;      // [nblk]
-    const unsigned char *len;    // [nblk]   number of coefficients written
-    const unsigned *off;         // [nblk + 1] exclusive bit offsets inside the tile
-    const unsigned short *map;   // [chunks of the tile] -> block
-    int stride;                  // words per block
-    int nblk;
-    int rle;
-    unsigned g_mod;              // (global bit position of the tile) % 128
-};
-
-static __constant__ unsigned short c_inv2w[17] = {0, 32768, 16384, 10923, 8192, 6554, 5462, 4682, 4096, 3641, 3277, 2979, 2731, 2521, 2341, 2185, 2048};
-
-// Produces the 128-bit chunk whose first bit is tile-local bit `ls` (negative in the tile's first chunk: leading bits 0).
-__device__ __forceinline__ uint4 gather_chunk(const UnitTile &t, long long ls) {
-    unsigned ow0 = 0, ow1 = 0, ow2 = 0, ow3 = 0;
-    int widx = 0, nacc = 0;
-    unsigned long long acc = 0;
-    const int ci = (int)((ls + (long long)t.g_mod) >> 7);
-    if (ls < 0) {
-        const int skip = (int)(-ls);
-        widx = skip >> 5;
-        nacc = skip & 31;
-        ls = 0;
-    }
-    const unsigned total = t.off[t.nblk];
-    if ((unsigned)ls < total) {
-        int b = t.map[ci];
-        int rel = (int)((unsigned)ls - t.off[b]);
-        bool first = true;
-        while (widx < 4 && b < t.nblk) {
-            const int w = t.w[b];
-            const int len = t.len[b];
-            const int hb = t.rle ? 4 + w : 4;
-            const int nun = 1 + ((len + 1) >> 1);
-            const unsigned *u = t.units + b * t.stride;
-            int i = 0, fo = 0;
-            if (first) {
-                first = false;
-                if (rel < hb) { fo = rel; }
-                else {
-                    const int r2 = rel - hb;
-                    const int j = (r2 * (int)c_inv2w[w]) >> 16;     // r2 / (2w), exact for r2 < 2048
-                    i = 1 + j;
-                    fo = r2 - j * 2 * w;
-                }
-            }
-            for (; i < nun && widx < 4; i++) {
-                unsigned v = u[i];
-                int uw = (i == 0) ? hb : ((i == nun - 1 && (len & 1)) ? w : 2 * w);
-                if (fo) { uw -= fo; v &= (uw >= 32) ? 0xffffffffu : ((1u << uw) - 1u); fo = 0; }
-                acc = (acc << uw) | v;
-                nacc += uw;
-                if (nacc >= 32) {
-                    const unsigned word = (unsigned)(acc >> (nacc - 32));
-                    if (widx == 0) ow0 = word; else if (widx == 1) ow1 = word; else if (widx == 2) ow2 = word; else ow3 = word;
-                    widx++;
-                    nacc -= 32;
-                }
-            }
-            b++;
-        }
-    }
-    if (widx < 4 && nacc > 0) {
-        const unsigned word = (unsigned)(acc << (32 - nacc));
-        if (widx == 0) ow0 = word; else if (widx == 1) ow1 = word; else if (widx == 2) ow2 = word; else ow3 = word;
-    }
-    // stream bit 0 is the MSB of byte 0 -> big-endian words
-    return make_uint4(__byte_perm(ow0, 0, 0x0123), __byte_perm(ow1, 0, 0x0123), __byte_perm(ow2, 0, 0x0123), __byte_perm(ow3, 0, 0x0123));
-}
-
 // Tile whose bits were already assembled in shared memory, starting at bit 0 of `words` (32 stream bits per word, MSB
 // first, zero beyond the tile's last bit).  The copy-out re-aligns them to the chunk grid of the global stream.
 struct SmemStreamTile {

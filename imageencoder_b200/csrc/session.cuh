@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "pack.cuh"
+#include "encode_image.cuh"
 
 struct ie_session {
     int kind = 0;
@@ -23,6 +24,11 @@ struct ie_session {
     // tile scratch of the encoder (packed tile images, per-tile bit totals and stream offsets)
     uint8_t *d_tile_scratch = nullptr; size_t tile_scratch_cap = 0;
     uint8_t *d_tile_meta = nullptr;    size_t tile_meta_cap = 0;
+
+    // split encode (ie_encode_image_begin_dev / _end_dev): what `begin` left for `end`
+    bool split_pending = false;
+    ie::EncodeParams split_params;
+    ie::HeaderParam split_hdr;
 
     // decode scratch
     unsigned long long *d_block_off = nullptr;    // [images * nblocks (+1)]

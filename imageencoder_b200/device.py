@@ -53,6 +53,22 @@ def encode_image_dev(s: Session, d_raw: torch.Tensor, quant, rle: bool, d_out: t
                                     _dp(d_bits) if d_bits is not None else None, _stream()))
 
 
+def encode_image_begin_dev(s: Session, d_raw: torch.Tensor, quant, rle: bool, d_total_bits: torch.Tensor, lead_bit: bool = True,
+                           write_header: bool = True, width=None, height=None) -> None:
+    """First half of a sharded encode: blocks -> tile scratch; d_total_bits[0] = header bits + block bits of this shard."""
+    q, qp = _q(quant)
+    check(lib().ie_encode_image_begin_dev(s.h, _dp(d_raw), width or s.width, height or s.height, qp, int(rle), int(lead_bit),
+                                          int(write_header), _dp(d_total_bits), _stream()))
+
+
+def encode_image_end_dev(s: Session, d_shard_totals: torch.Tensor, shard_index: int, d_out: torch.Tensor,
+                         d_out_bits: torch.Tensor | None = None, d_first_bit: torch.Tensor | None = None) -> None:
+    """Second half: the shard's bytes of the global stream, from byte (first // 128) * 16, into d_out."""
+    check(lib().ie_encode_image_end_dev(s.h, _dp(d_shard_totals), shard_index, _dp(d_out), d_out.numel(),
+                                        _dp(d_out_bits) if d_out_bits is not None else None,
+                                        _dp(d_first_bit) if d_first_bit is not None else None, _stream()))
+
+
 def image_bits_dev(s: Session, d_raw: torch.Tensor, quant, rle: bool, d_bits: torch.Tensor, width=None, height=None) -> None:
     q, qp = _q(quant)
     check(lib().ie_image_bits_dev(s.h, _dp(d_raw), width or s.width, height or s.height, qp, int(rle), _dp(d_bits), _stream()))
@@ -63,6 +79,25 @@ def decode_image_dev(s: Session, d_enc: torch.Tensor, enc_bytes: int, d_raw_out:
     check(lib().ie_decode_image_dev(s.h, _dp(d_enc), enc_bytes, start_bit, _dp(d_raw_out), d_raw_out.numel(), C.byref(w),
                                     C.byref(h), _stream()))
     return w.value, h.value
+
+
+def encode_video_dev(s: Session, d_yuv: torch.Tensor, width: int, height: int, quant, rle: bool, gop: int, merange: int,
+                     d_out: torch.Tensor, d_bits: torch.Tensor | None = None, lead_bit: bool = True, d_mvecs: torch.Tensor | None = None) -> None:
+    """``dc::VideoEncoder::process`` on device-resident YUV420 frames (the Y planes are rebuilt in place, Frame.cpp:218-242).
+    Asynchronous on torch's current stream."""
+    q, qp = _q(quant)
+    check(lib().ie_encode_video_dev(s.h, _dp(d_yuv), d_yuv.numel(), width, height, qp, int(rle), gop, merange, int(lead_bit),
+                                    _dp(d_out), d_out.numel(), _dp(d_bits) if d_bits is not None else None,
+                                    _dp(d_mvecs) if d_mvecs is not None else None, _stream()))
+
+
+def decode_video_dev(s: Session, d_enc: torch.Tensor, enc_bytes: int, d_yuv_out: torch.Tensor, motioncompensation: bool = True,
+                     start_bit: int = 1):
+    """``dc::VideoDecoder`` on a device-resident plain stream; returns (width, height, frames)."""
+    w, h, f = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    check(lib().ie_decode_video_dev(s.h, _dp(d_enc), enc_bytes, start_bit, int(motioncompensation), _dp(d_yuv_out),
+                                    d_yuv_out.numel(), C.byref(w), C.byref(h), C.byref(f), _stream()))
+    return w.value, h.value, f.value
 
 
 def huffman_encode_dev(s: Session, d_in: torch.Tensor, in_bytes: int, d_out: torch.Tensor) -> int:

@@ -109,7 +109,11 @@ def exchange_bit_totals(local_bits, group=None):
 
 
 class ShardedImageEncoder:
-    """Encodes this rank's block-row shard of one large image and re-aligns it for the single output stream."""
+    """Encodes this rank's block-row shard of one large image straight into its place in the single output stream.
+
+    tile kernel (blocks -> packed tile images in scratch, shard bit total) -> all-gather of one u64 per rank -> copy-out
+    kernel that writes the shard at its global bit offset.  The collective sits between the two kernels; there is no
+    re-alignment pass over the output."""
 
     def __init__(self, width: int, shard_height: int, block: int, full_height: int | None = None):
         import torch
@@ -123,27 +127,29 @@ class ShardedImageEncoder:
             from ._lib import check
             check(lib().ie_session_set_header_height(self.sess.h, full_height))
         self.cap = int(lib().ie_max_encoded_bytes(width, shard_height, block, 1))
-        self.d_local = torch.empty(self.cap, dtype=torch.uint8, device="cuda")
-        self.d_aligned = torch.empty(self.cap + 16, dtype=torch.uint8, device="cuda")
-        self.d_bits = torch.zeros(1, dtype=torch.int64, device="cuda")
-        self.d_params = torch.zeros(2, dtype=torch.int64, device="cuda")
+        self.d_aligned = torch.empty(self.cap + 32, dtype=torch.uint8, device="cuda")
+        self.d_total = torch.zeros(1, dtype=torch.int64, device="cuda")     # this shard's bits (header included on rank 0)
+        self.d_bits = torch.zeros(1, dtype=torch.int64, device="cuda")      # (first % 128) + this shard's bits
+        self.d_first = torch.zeros(1, dtype=torch.int64, device="cuda")     # first bit of this shard in the global stream
+        self.d_totals = None
 
     def encode(self, d_raw, quant, rle: bool, rank: int, lead_bit: bool = True, group=None):
-        """Asynchronous.  Returns (totals, offsets) device tensors; self.d_aligned then holds this rank's bytes of the
-        global stream starting at byte (offsets[rank] // 128) * 16."""
-        import ctypes as C
-
+        """Asynchronous.  Returns the device tensor of all shards' bit totals; self.d_aligned then holds this rank's bytes
+        of the global stream starting at byte (self.d_first // 128) * 16."""
         import torch
+        import torch.distributed as dist
 
         from . import device
-        from ._lib import check, lib
 
-        device.encode_image_dev(self.sess, d_raw, quant, rle, self.d_local, self.d_bits, lead_bit=lead_bit,
-                                write_header=(rank == 0), first_bit=0, width=self.width, height=self.shard_height)
-        totals, offsets = exchange_bit_totals(self.d_bits, group)
-        self.d_params[0] = self.d_bits[0]
-        self.d_params[1] = offsets[rank]
-        check(lib().ie_stream_shift_dev(C.c_void_p(self.d_local.data_ptr()), C.c_void_p(self.d_params.data_ptr()),
-                                        C.c_void_p(self.d_aligned.data_ptr()), self.d_aligned.numel(),
-                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return totals, offsets
+        device.encode_image_begin_dev(self.sess, d_raw, quant, rle, self.d_total, lead_bit=lead_bit, write_header=(rank == 0),
+                                      width=self.width, height=self.shard_height)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            totals = self.d_total
+        else:
+            if self.d_totals is None or self.d_totals.numel() != world:
+                self.d_totals = torch.empty(world, dtype=torch.int64, device="cuda")
+            totals = self.d_totals
+            dist.all_gather_into_tensor(totals, self.d_total, group=group)
+        device.encode_image_end_dev(self.sess, totals, rank, self.d_aligned, self.d_bits, self.d_first)
+        return totals

@@ -91,6 +91,20 @@ void ie_session_destroy(ie_session *s);
 int ie_encode_image_dev(ie_session *s, const uint8_t *d_raw, uint32_t width, uint32_t height,
                         const uint16_t *quant, int use_rle, int lead_bit, int write_header, uint64_t first_bit,
                         uint8_t *d_out, size_t out_cap, uint64_t *d_out_bits, void *stream);
+/* Split encode for a shard of a multi-GPU stream, so that the ONE collective of a sharded encode sits between
+ * the two kernels and no re-alignment pass is needed:
+ *   begin: transform/quantise/pack the shard's blocks into the session's tile scratch; *d_total_bits (device) = header bits
+ *          (if write_header) + block bits of this shard                      -> all-gather of one u64 per rank
+ *   end:   d_shard_totals (device, one u64 per shard, from the all-gather); this shard starts at bit
+ *          first = sum(d_shard_totals[0 .. shard_index)) of the global stream.  d_out receives this shard's bytes of the
+ *          global stream starting at byte (first / 128) * 16 (leading bits of that chunk zero); *d_out_bits (device,
+ *          optional) = (first % 128) + this shard's bits; *d_first_bit (device, optional) = first.
+ * Replaces ie_encode_image_dev + ie_stream_shift_dev. */
+int ie_encode_image_begin_dev(ie_session *s, const uint8_t *d_raw, uint32_t width, uint32_t height,
+                              const uint16_t *quant, int use_rle, int lead_bit, int write_header,
+                              uint64_t *d_total_bits, void *stream);
+int ie_encode_image_end_dev(ie_session *s, const uint64_t *d_shard_totals, uint32_t shard_index,
+                            uint8_t *d_out, size_t out_cap, uint64_t *d_out_bits, uint64_t *d_first_bit, void *stream);
 /* Height written into the header by the next ie_encode_image_dev calls on this session (0 = the height passed to
  * the call).  A block-row shard of a larger image writes the FULL image height (ImageEncoder.cpp:93-94). */
 int ie_session_set_header_height(ie_session *s, uint32_t full_height);

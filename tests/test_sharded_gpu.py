@@ -49,6 +49,48 @@ def test_block_row_shards_stitch_to_single_stream(gpu, oracle_mod):
         assert got == want, f"{matrix} x{world}: stitched stream differs"
 
 
+def test_split_encode_places_shards_without_realignment(gpu, oracle_mod):
+    """ie_encode_image_begin_dev -> (all-gather, here a torch.cat) -> ie_encode_image_end_dev: every emulated rank writes its
+    shard at its global bit offset; the stitched stream is the oracle's."""
+    import torch
+    from imageencoder_b200 import device
+    from imageencoder_b200._lib import check, lib
+    from imageencoder_b200.parallel import merge_shard_into, place_shards, shard_block_rows, total_bytes
+    from imageencoder_b200.synth import synth_image
+    W, H = 512, 384
+    for matrix, world in (("matrix8_1.txt", 3), ("matrix.txt", 4), ("matrix8_2.txt", 2), ("matrix4_2.txt", 1)):
+        q = oracle_mod.read_matrix(INPUTS / matrix)
+        N = q.shape[0]
+        img = synth_image(W, H, 78, flat=True)
+        want = oracle_mod.image_encode(img, W, H, N, q, True, False)
+        sessions, totals = [], []
+        for r in range(world):
+            y0, y1 = shard_block_rows(H, N, world, r)
+            sess = device.Session(device.Session.IMAGE_ENCODE, W, y1 - y0, N)
+            check(lib().ie_session_set_header_height(sess.h, H))
+            d_raw = torch.from_numpy(img[y0:y1].copy()).cuda().reshape(-1)
+            d_total = torch.zeros(1, dtype=torch.int64, device="cuda")
+            device.encode_image_begin_dev(sess, d_raw, q, True, d_total, lead_bit=True, write_header=(r == 0), width=W, height=y1 - y0)
+            sessions.append((sess, y1 - y0))
+            totals.append(d_total)
+        d_totals = torch.cat(totals)                       # what the all-gather delivers
+        bits = [int(b) for b in d_totals.cpu().tolist()]
+        pl = place_shards(bits)
+        stream = bytearray()
+        for r in range(world):
+            sess, sh = sessions[r]
+            d_al = torch.zeros(int(lib().ie_max_encoded_bytes(W, sh, N, 1)) + 32, dtype=torch.uint8, device="cuda")
+            d_bits = torch.zeros(1, dtype=torch.int64, device="cuda")
+            d_first = torch.zeros(1, dtype=torch.int64, device="cuda")
+            device.encode_image_end_dev(sess, d_totals, r, d_al, d_bits, d_first)
+            torch.cuda.synchronize()
+            assert int(d_first.item()) == pl[r].global_bit
+            assert int(d_bits.item()) == pl[r].global_bit % 128 + bits[r]
+            merge_shard_into(stream, d_al[: pl[r].nbytes].cpu().numpy().tobytes(), pl[r])
+        got = bytes(stream[: total_bytes(pl)])
+        assert got == want, f"{matrix} x{world}: stitched stream differs"
+
+
 def test_batch_entry_point(gpu, oracle_mod):
     from imageencoder_b200._lib import check, lib
     from imageencoder_b200.synth import synth_image

@@ -97,4 +97,20 @@ ms = wall(venc, reps=2, warm=1)
 out["video_encode_host_ms_per_frame"] = ms / F; out["video_encode_host_gpx_s"] = W * H * F / ms / 1e6; out["video_bytes"] = len(enc[0])
 ms = wall(lambda: ie.decode_video(enc[0], True), reps=2, warm=1)
 out["video_decode_host_ms_per_frame"] = ms / F; out["video_decode_host_gpx_s"] = W * H * F / ms / 1e6
+# device-resident video (frames and stream stay in HBM)
+d_yuv0 = torch.from_numpy(np.ascontiguousarray(yuv)).cuda().reshape(-1)
+d_yuv = d_yuv0.clone()
+d_vout = torch.empty(int(L.ie_max_encoded_bytes(W, H, 4, F)) + 4096, dtype=torch.uint8, device="cuda")
+sv = device.Session(2, W, H, 4, F)
+def venc_dev():
+    d_yuv.copy_(d_yuv0)                                   # the encoder rebuilds the frames in place
+    device.encode_video_dev(sv, d_yuv, W, H, qv, True, 12, 16, d_vout, d_bits, lead_bit=True)
+copy_ms = ev_time(lambda: d_yuv.copy_(d_yuv0))
+ms = ev_time(venc_dev, reps=3, warm=1) - copy_ms
+vb = (int(d_bits.item()) + 7) // 8
+out["video_encode_dev_ms_per_frame"] = ms / F; out["video_encode_dev_gpx_s"] = W * H * F / ms / 1e6
+svd = device.Session(3, W, H, 4, F)
+d_vdec = torch.empty(W * H * 3 // 2 * F, dtype=torch.uint8, device="cuda")
+ms = wall(lambda: (device.decode_video_dev(svd, d_vout, vb, d_vdec, True), torch.cuda.synchronize()), reps=3, warm=1)
+out["video_decode_dev_ms_per_frame"] = ms / F; out["video_decode_dev_gpx_s"] = W * H * F / ms / 1e6
 print(json.dumps(out, indent=1))
