@@ -1,9 +1,12 @@
-// Fused image-block encode: one CTA per tile of consecutive blocks (raster order, ImageBase.cpp:187-199):
-//   pixels -> (-128) -> forward DCT -> quant divide/round -> zigzag -> RLE info        (lane per block)
-//   -> CTA scan of block bit counts -> decoupled look-back for the tile's stream offset
-//   -> chunk-centric gather/pack straight into the stream                              (thread per 128-bit chunk)
-// One pass over HBM: W*H bytes in, the stream out.  Replaces ImageEncoder.cpp:121-138 (parallel DCT loop + the
-// strictly serial streamEncoded loop), Frame.cpp:141-158 (I-frames) and, with PF, Frame.cpp:160-244 (P-frame blocks).
+// Image-block encode: one CTA per tile of consecutive blocks (raster order, ImageBase.cpp:187-199):
+//   encode_tiles_kernel:  pixels -> (-128) -> forward DCT -> quant divide/round -> zigzag -> RLE info   (lane per block)
+//                         -> CTA scan of block bit counts -> block-centric pack into a shared-memory image of the tile's
+//                         bits -> the tile's scratch slot + its bit count                      (no inter-CTA dependency)
+//   tile_copyout_kernel:  per group of tiles: sum of the earlier tiles' bit counts, then the tile images re-aligned into
+//                         the stream                                                          (thread per 128-bit chunk)
+// HBM traffic: W*H bytes in, the stream out, plus one L2-resident round trip of the stream through the tile scratch.
+// Replaces ImageEncoder.cpp:121-138 (parallel DCT loop + the strictly serial streamEncoded loop), Frame.cpp:141-158
+// (I-frames) and, with PF, Frame.cpp:160-244 (P-frame blocks).
 //
 // Template switches: N block size, BPL blocks per lane, PF P-frame mode (residual in, reconstruction out),
 // FAST = FP32 factorised transform + guard band + exact fallback (transform_fast.cuh); FAST=false evaluates every
