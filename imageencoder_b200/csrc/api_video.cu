@@ -27,41 +27,96 @@ struct MEParams {
     short *mv;           // [nmb][2] unclamped offsets
     short *res_coord;    // [nmb][2] clamped pixel coordinate of the best block (residual source)
     short *copy_coord;   // [nmb][2] clamp(MB + mv)  (Frame.cpp:218-220)
+    // blockIdx.y = GOP of the batch: frame pointers advance by frame_stride bytes, the three arrays by mv_stride shorts
+    size_t frame_stride, mv_stride;
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-__global__ void __launch_bounds__(256) me_search_kernel(const MEParams p) {
+__global__ void __launch_bounds__(256) me_search_kernel(MEParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb = blockIdx.x * 8 + warp;
     if (mb >= p.nmb) return;
+    p.cur += (size_t)blockIdx.y * p.frame_stride; p.ref += (size_t)blockIdx.y * p.frame_stride;
+    p.mv += (size_t)blockIdx.y * p.mv_stride; p.res_coord += (size_t)blockIdx.y * p.mv_stride; p.copy_coord += (size_t)blockIdx.y * p.mv_stride;
     const int mbx = (mb % p.mx) * kMB, mby = (mb / p.mx) * kMB;
     const int row = lane >> 1, half = lane & 1;
     const uint2 c = *reinterpret_cast<const uint2 *>(p.cur + (size_t)(mby + row) * p.W + mbx + half * 8);
+    // Search window of this MacroBlock in shared memory (per warp): every candidate of the log search lies within +-15
+    // pixels of the block (steps merange/2 .. 1 with merange <= 16) and inside the frame, i.e. in the 46 x 46 pixels from
+    // (mbx - 15, mby - 15); rows are kept 13 words apart (odd: the 16 rows a candidate touches fall into different banks).
+    // Candidates read straight from global memory cost 16 sectors per load instruction (one per row) -- 19x the traffic.
+    constexpr int kWinRows = 46, kWinWords = 13;
+    __shared__ unsigned s_win[8][kWinRows * kWinWords];
+    const bool staged = p.merange <= 16;
+    const int wy0 = max(mby - 15, 0), wxa = max(mbx - 15, 0) & ~3;
+    unsigned *win = s_win[warp];
+    if (staged) {
+        constexpr int kIters = (kWinRows * kWinWords + 31) / 32;
+        unsigned v[kIters];
+#pragma unroll
+        for (int i = 0; i < kIters; i++) {                  // all loads in flight before the first store
+            const int idx = lane + 32 * i;
+            const int r = idx / kWinWords, k = idx - r * kWinWords;
+            const int y = wy0 + r, x = wxa + 4 * k;
+            v[i] = (idx < kWinRows * kWinWords && y < p.H && x + 4 <= p.W) ? __ldg(reinterpret_cast<const unsigned *>(p.ref + (size_t)y * p.W + x)) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < kIters; i++) {
+            const int idx = lane + 32 * i;
+            if (idx < kWinRows * kWinWords) win[idx] = v[i];
+        }
+        __syncwarp();
+    }
     int best_x = 0, best_y = 0;
     int bcx = 0, bcy = 0;                                  // Block.cpp:273: the initial block is the one at pixel (0,0)
     unsigned best_d = 0xffffffffu;
     for (int step = p.merange / 2; step > 0; step >>= 1) {  // algo.cpp:129,138
-        bool have = false;
-        int nx = 0, ny = 0, ncx = 0, ncy = 0;
-        unsigned nd = best_d;
+        // the 9 candidates of a level are independent: all their loads are issued first, the 9 SAD partial sums are
+        // reduced two to a register (a MacroBlock's SAD is <= 256 * 255 < 2^16), and only the selection runs in the
+        // reference's order (Block.cpp:289-317)
+        int cpx[9], cpy[9];
+        unsigned w0[9], w1[9], w2[9], shq[9];
+#pragma unroll
         for (int q = 0; q < 9; q++) {
             const int ox = best_x + c_mer_sx[q] * step, oy = best_y + c_mer_sy[q] * step;
-            const int px = clampi((int)(short)(ox + mbx), 0, p.W - kMB), py = clampi((int)(short)(oy + mby), 0, p.H - kMB);
-            if (q > 0 && px == mbx && py == mby) continue;                     // Block.cpp:297-301
-            const uint8_t *rp = p.ref + (size_t)(py + row) * p.W + px + half * 8;
-            const uintptr_t a = (uintptr_t)rp;
-            const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
-            const unsigned sh = (unsigned)(a & 3) * 8;
-            const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = sh ? __ldg(wp + 2) : 0u;
-            const unsigned r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh);
-            unsigned d = __vsadu4(c.x, r0) + __vsadu4(c.y, r1);                // Block.cpp:241-254
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            if (d <= nd) { have = true; nx = ox; ny = oy; nd = d; ncx = px; ncy = py; }   // Block.cpp:306
+            cpx[q] = clampi((int)(short)(ox + mbx), 0, p.W - kMB);
+            cpy[q] = clampi((int)(short)(oy + mby), 0, p.H - kMB);
+            if (staged) {
+                const int bx = cpx[q] - wxa + half * 8;                         // byte offset inside the window row
+                const unsigned *wp = win + (cpy[q] - wy0 + row) * kWinWords + (bx >> 2);
+                shq[q] = (unsigned)(bx & 3) * 8;
+                w0[q] = wp[0]; w1[q] = wp[1]; w2[q] = shq[q] ? wp[2] : 0u;
+            } else {
+                const uint8_t *rp = p.ref + (size_t)(cpy[q] + row) * p.W + cpx[q] + half * 8;
+                const uintptr_t a = (uintptr_t)rp;
+                const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
+                shq[q] = (unsigned)(a & 3) * 8;
+                w0[q] = __ldg(wp); w1[q] = __ldg(wp + 1); w2[q] = shq[q] ? __ldg(wp + 2) : 0u;
+            }
         }
-        if (!have) break;                                                       // Block.cpp:318-321 (never taken)
-        best_x = nx; best_y = ny; best_d = nd; bcx = ncx; bcy = ncy;
+        unsigned d[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            const unsigned r0 = __funnelshift_r(w0[q], w1[q], shq[q]), r1 = __funnelshift_r(w1[q], w2[q], shq[q]);
+            d[q] = __vsadu4(c.x, r0) + __vsadu4(c.y, r1);                      // Block.cpp:241-254 (this lane's 8 pixels)
+        }
+        unsigned pk[5] = {d[0] | (d[1] << 16), d[2] | (d[3] << 16), d[4] | (d[5] << 16), d[6] | (d[7] << 16), d[8]};
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) pk[k] += __shfl_xor_sync(0xffffffffu, pk[k], o);
+        }
+        int bq = -1, ncx = 0, ncy = 0;
+        unsigned nd = best_d;
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            if (q > 0 && cpx[q] == mbx && cpy[q] == mby) continue;             // Block.cpp:297-301
+            const unsigned dq = (q == 8) ? pk[4] : ((q & 1) ? (pk[q >> 1] >> 16) : (pk[q >> 1] & 0xffffu));
+            if (dq <= nd) { bq = q; nd = dq; ncx = cpx[q]; ncy = cpy[q]; }     // Block.cpp:306
+        }
+        if (bq < 0) break;                                                      // Block.cpp:318-321 (never taken)
+        best_x += c_mer_sx[bq] * step; best_y += c_mer_sy[bq] * step; best_d = nd; bcx = ncx; bcy = ncy;
     }
     if (lane == 0) {
         p.mv[2 * mb] = (short)best_x;
@@ -103,8 +158,9 @@ __device__ __forceinline__ uint4 gather_chunk(const FixedFieldTile &t, long long
     return make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
-__global__ void __launch_bounds__(kThreads) mvec_pack_kernel(const short *mv, unsigned nfields, unsigned bits, uint8_t *out, size_t out_cap,
-                                                             unsigned long long *bit_counter, int *err) {
+__global__ void __launch_bounds__(kThreads) mvec_pack_kernel(const short *mv, size_t mv_stride, unsigned nfields, unsigned bits, uint8_t *out,
+                                                             size_t out_stride, size_t out_cap, unsigned long long *bit_counter, int *err) {
+    mv += (size_t)blockIdx.y * mv_stride; out += (size_t)blockIdx.y * out_stride; bit_counter += blockIdx.y;
     FixedFieldTile t{mv, nfields, bits};
     ScanState st{};
     const unsigned long long G = *bit_counter;
@@ -181,14 +237,74 @@ static int check_video_dims(uint32_t W, uint32_t H) {
 }
 
 // scratch layout inside s->d_scratch for video: mv | res_coord | copy_coord (shorts), cursor (u64)
-struct VideoScratch { short *mv, *res, *copy; unsigned long long *cursor; };
-static int video_scratch(ie_session *s, size_t nmb, VideoScratch &v) {
-    const size_t sec = (nmb * 2 * sizeof(short) + 63) / 64 * 64;
-    IE_TRY(session_reserve(&s->d_scratch, &s->scratch_cap, 3 * sec + 64));
+// ---------------------------------------------------------------------------------------------------------
+// GOP batches.  GOPs are independent (VideoBase.hpp:32, VideoBase.cpp:105-118), so frame k of every GOP of a batch is
+// encoded by ONE launch (blockIdx.y = GOP) into that GOP's own stream buffer; after the last frame the GOP streams are
+// appended, in order, to the video stream (one offsets kernel + one copy kernel).
+// ---------------------------------------------------------------------------------------------------------
+// off[j] = first bit of GOP j in the video stream; chunks two GOPs share are zeroed so that both can OR their part in.
+__global__ void gop_offsets_kernel(const unsigned long long *gop_bits, unsigned ngops, unsigned long long *stream_bits,
+                                   unsigned long long *off, uint8_t *out, size_t out_cap) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long pos = *stream_bits;
+    for (unsigned j = 0; j < ngops; j++) {
+        off[j] = pos;
+        if (j > 0 && pos % kChunkBits && (pos / kChunkBits + 1) * 16 <= out_cap)
+            reinterpret_cast<uint4 *>(out)[pos / kChunkBits] = make_uint4(0u, 0u, 0u, 0u);
+        pos += gop_bits[j];
+    }
+    *stream_bits = pos;
+}
+
+// GOP stream j (bit 0 of its buffer, gop_bits[j] bits, zero padded to a chunk) -> bits [off[j], off[j] + gop_bits[j]) of out.
+// Thread per 128-bit chunk of the output; chunks shared with a neighbour (or with what earlier launches wrote: the header,
+// the previous batch) are merged with atomicOr, the rest are plain 128-bit stores.
+__global__ void __launch_bounds__(256) gop_append_kernel(const uint8_t *gop_streams, size_t gop_stride, const unsigned long long *gop_bits,
+                                                         const unsigned long long *off, unsigned ngops, uint8_t *out, size_t out_cap, int *err) {
+    const unsigned j = blockIdx.y;
+    const unsigned long long G = off[j], T = gop_bits[j];
+    if (T == 0) return;
+    const unsigned *w = reinterpret_cast<const unsigned *>(gop_streams + (size_t)j * gop_stride);
+    const long long nwords = (long long)((T + 31) / 32);
+    const unsigned long long c0 = G / kChunkBits, c1 = (G + T - 1) / kChunkBits;
+    for (unsigned long long c = c0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c <= c1; c += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long ls = (long long)(c * kChunkBits) - (long long)G;      // first GOP bit of this chunk (may be < 0)
+        const long long wi = ls >> 5;
+        const unsigned sh = (unsigned)(ls & 31);
+        unsigned x[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const long long i = wi + k;
+            x[k] = (i >= 0 && i < nwords) ? __byte_perm(__ldg(w + i), 0, 0x0123) : 0u;
+        }
+        // the last word may hold pad bits beyond T: they are zero (the encoder zero-pads its last chunk)
+        uint4 v;
+        v.x = __byte_perm(__funnelshift_l(x[1], x[0], sh), 0, 0x0123);
+        v.y = __byte_perm(__funnelshift_l(x[2], x[1], sh), 0, 0x0123);
+        v.z = __byte_perm(__funnelshift_l(x[3], x[2], sh), 0, 0x0123);
+        v.w = __byte_perm(__funnelshift_l(x[4], x[3], sh), 0, 0x0123);
+        if ((c + 1) * 16ull > out_cap) { if (err) atomicExch(err, IE_ENOSPC); continue; }
+        const bool shared = (c == c0 && (G % kChunkBits) != 0) || (c == c1 && ((G + T) % kChunkBits) != 0 && j + 1 < ngops);
+        if (shared) {
+            unsigned *d = reinterpret_cast<unsigned *>(out) + c * 4;
+            atomicOr(d + 0, v.x); atomicOr(d + 1, v.y); atomicOr(d + 2, v.z); atomicOr(d + 3, v.w);
+        } else {
+            reinterpret_cast<uint4 *>(out)[c] = v;
+        }
+    }
+}
+
+struct VideoScratch { short *mv, *res, *copy; unsigned long long *cursor, *gop_off; };
+// motion vectors / residual / copy coordinates of `ngops` frames in flight ([gop][nmb][2] each), the stream's bit cursor and
+// the GOP offsets of a batch
+static int video_scratch(ie_session *s, size_t nmb, size_t ngops, VideoScratch &v) {
+    const size_t sec = (nmb * 2 * sizeof(short) * ngops + 63) / 64 * 64;
+    IE_TRY(session_reserve(&s->d_scratch, &s->scratch_cap, 3 * sec + 64 + ngops * sizeof(unsigned long long)));
     v.mv = reinterpret_cast<short *>(s->d_scratch);
     v.res = reinterpret_cast<short *>(s->d_scratch + sec);
     v.copy = reinterpret_cast<short *>(s->d_scratch + 2 * sec);
     v.cursor = reinterpret_cast<unsigned long long *>(s->d_scratch + 3 * sec);
+    v.gop_off = v.cursor + 8;
     return IE_OK;
 }
 
@@ -213,16 +329,25 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     if (frames > 32767) { set_error("more than 32767 frames do not fit the 15-bit header field"); return IE_EINVAL; }
     const unsigned nblocks = (W / 4) * (H / 4), nmb = (W / kMB) * (H / kMB);
     const unsigned TB = encode_tile_blocks(4), tiles = (nblocks + TB - 1) / TB;
-    IE_TRY(session_ensure_scan(s, 1, tiles));
+    const unsigned mvbits = host_bits_needed((int)(short)merange);           // VideoBase.cpp:42
+    // GOP batches: at most kMaxGopBatch GOPs (and ~2 GiB of per-GOP stream buffers) in flight
+    const uint32_t ngops = (frames + gop - 1) / gop;
+    const size_t frame_cap_bits = (size_t)nblocks * (4 + 16 + 16 * 16) + (size_t)nmb * 2 * mvbits;
+    const size_t gop_cap = ((frame_cap_bits * std::min<size_t>(gop, std::max<uint32_t>(frames, 1)) + 127) / 128 + 2) * 16;
+    constexpr uint32_t kMaxGopBatch = 64;
+    const uint32_t mem_batch = (uint32_t)std::max<size_t>(1, ((size_t)2 << 30) / gop_cap);
+    const uint32_t batch = std::max<uint32_t>(1, std::min(std::min(ngops, kMaxGopBatch), mem_batch));
+    IE_TRY(session_ensure_scan(s, batch, tiles));
     IE_TRY(session_ensure_err(s));
     VideoScratch vs;
-    IE_TRY(video_scratch(s, nmb, vs));
-    const unsigned mvbits = host_bits_needed((int)(short)merange);           // VideoBase.cpp:42
+    IE_TRY(video_scratch(s, nmb, batch, vs));
+    IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, (size_t)batch * gop_cap));          // the GOP streams of a batch
 
-    HeaderParam hdr;
+    HeaderParam hdr, nohdr;
+    memset(&nohdr, 0, sizeof nohdr);
     IE_TRY(build_header(hdr, 4, quant, use_rle, W, H, lead_bit, 1, frames, gop, merange));
     if (out_cap < 256) { set_error("output buffer too small"); return IE_ENOSPC; }
-    IE_TRY(launch_stream_init(d_out, 0, 1, hdr, 0, s->d_counter, st));
+    IE_TRY(launch_stream_init(d_out, 0, 1, hdr, 0, vs.cursor, st));
 
     EncodeParams p;
     memset(&p, 0, sizeof p);
@@ -233,39 +358,60 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     make_fast_quant(fq_p, quant, 4, 383.0);      // P-frames: (pixel - ref) - 128 in [-383, 127]
     p.dc_den2 = 8 * (int)quant[0]; p.dc_rcp = 1.0f / (float)p.dc_den2;
     p.tab = s->dev->d_t4;
-    p.out = d_out; p.out_cap = out_cap; p.bit_counter = s->d_counter; p.err = s->d_err;
+    p.out = s->d_tmp; p.out_stride = gop_cap; p.out_cap = gop_cap; p.bit_counter = s->d_counter; p.err = s->d_err;
     p.mbx = W / kMB;
+    p.img_stride = (size_t)gop * fsz;            // image i of a launch = the same frame index of GOP i
+    p.coord_stride = (size_t)nmb * 2;
     p.slot_bytes = encode_tile_slot_bytes(4);
-    IE_TRY(session_reserve(&s->d_tile_scratch, &s->tile_scratch_cap, (size_t)tiles * p.slot_bytes));
-    IE_TRY(session_reserve(&s->d_tile_meta, &s->tile_meta_cap, (size_t)tiles * (sizeof(unsigned long long) + sizeof(unsigned)) + 64));
+    const size_t ntot = (size_t)batch * tiles;
+    IE_TRY(session_reserve(&s->d_tile_scratch, &s->tile_scratch_cap, ntot * p.slot_bytes));
+    IE_TRY(session_reserve(&s->d_tile_meta, &s->tile_meta_cap, ntot * (sizeof(unsigned long long) + sizeof(unsigned)) + 64));
     p.tile_scratch = s->d_tile_scratch;
     p.bit_base = reinterpret_cast<unsigned long long *>(s->d_tile_meta);
-    p.tile_bits = reinterpret_cast<unsigned *>(s->d_tile_meta + (size_t)tiles * sizeof(unsigned long long));
-    for (uint32_t f = 0; f < frames; f++) {
-        uint8_t *cur = d_yuv + (size_t)f * fsz;
-        p.src = cur;
-        p.scan = s->scan_state();
-        if (f % gop == 0) {                                                    // VideoBase.hpp:32, Frame.cpp:130-159
-            p.fq = fq_i;
-            IE_TRY(launch_encode_tiles(4, p, 1, st));
-            if (d_mvecs) IE_CUDA(cudaMemsetAsync(d_mvecs + (size_t)f * nmb * 2, 0, nmb * 2 * sizeof(short), st));
-            continue;
+    p.tile_bits = reinterpret_cast<unsigned *>(s->d_tile_meta + ntot * sizeof(unsigned long long));
+    for (uint32_t g0 = 0; g0 < ngops; g0 += batch) {
+        const uint32_t nb = std::min(batch, ngops - g0);
+        IE_TRY(launch_stream_init(s->d_tmp, gop_cap, nb, nohdr, 0, s->d_counter, st));   // empty GOP streams, counters = 0
+        for (uint32_t k = 0; k < gop; k++) {
+            // GOPs of this batch that have a frame k (only the clip's last GOP can be short)
+            const uint32_t last_len = frames - (g0 + nb - 1) * gop;                      // >= 1
+            const uint32_t act = (k < last_len) ? nb : nb - 1;
+            if (act == 0) break;
+            const uint32_t f = g0 * gop + k;                                             // frame of the batch's first GOP
+            uint8_t *cur = d_yuv + (size_t)f * fsz;
+            p.src = cur;
+            p.scan = s->scan_state();
+            if (k == 0) {                                                                // VideoBase.hpp:32, Frame.cpp:130-159
+                p.fq = fq_i;
+                IE_TRY(launch_encode_tiles(4, p, act, st));
+                if (d_mvecs) IE_CUDA(cudaMemset2DAsync(d_mvecs + (size_t)f * nmb * 2, (size_t)gop * nmb * 2 * sizeof(short), 0,
+                                                       nmb * 2 * sizeof(short), act, st));
+                continue;
+            }
+            MEParams me;
+            me.cur = cur; me.ref = cur - fsz; me.W = (int)W; me.H = (int)H; me.mx = (int)(W / kMB); me.nmb = (int)nmb;
+            me.merange = (int)merange; me.mv = vs.mv; me.res_coord = vs.res; me.copy_coord = vs.copy;
+            me.frame_stride = p.img_stride; me.mv_stride = p.coord_stride;
+            me_search_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, st>>>(me);
+            count_launch();
+            mvec_pack_kernel<<<dim3(1, act), kThreads, 0, st>>>(vs.mv, p.coord_stride, nmb * 2, mvbits, s->d_tmp, gop_cap, gop_cap, s->d_counter,
+                                                               s->d_err);
+            count_launch();
+            IE_CUDA(cudaGetLastError());
+            if (d_mvecs) IE_CUDA(cudaMemcpy2DAsync(d_mvecs + (size_t)f * nmb * 2, (size_t)gop * nmb * 2 * sizeof(short), vs.mv,
+                                                   nmb * 2 * sizeof(short), nmb * 2 * sizeof(short), act, cudaMemcpyDeviceToDevice, st));
+            p.fq = fq_p;
+            p.ref = me.ref; p.res_coord = vs.res; p.copy_coord = vs.copy; p.cur_rw = cur;
+            IE_TRY(launch_pframe_tiles(p, act, st));
         }
-        MEParams me;
-        me.cur = cur; me.ref = d_yuv + (size_t)(f - 1) * fsz; me.W = (int)W; me.H = (int)H; me.mx = (int)(W / kMB); me.nmb = (int)nmb;
-        me.merange = (int)merange; me.mv = vs.mv; me.res_coord = vs.res; me.copy_coord = vs.copy;
-        me_search_kernel<<<(nmb + 7) / 8, 256, 0, st>>>(me);
-        count_launch();
-        mvec_pack_kernel<<<1, kThreads, 0, st>>>(vs.mv, nmb * 2, mvbits, d_out, out_cap, s->d_counter, s->d_err);
-        count_launch();
+        // the batch's GOP streams, in order, onto the video stream
+        gop_offsets_kernel<<<1, 32, 0, st>>>(s->d_counter, nb, vs.cursor, vs.gop_off, d_out, out_cap);
+        gop_append_kernel<<<dim3(s->dev->sm_count * 2, nb), 256, 0, st>>>(s->d_tmp, gop_cap, s->d_counter, vs.gop_off, nb, d_out, out_cap, s->d_err);
+        count_launch(2);
         IE_CUDA(cudaGetLastError());
-        if (d_mvecs) IE_CUDA(cudaMemcpyAsync(d_mvecs + (size_t)f * nmb * 2, vs.mv, nmb * 2 * sizeof(short), cudaMemcpyDeviceToDevice, st));
-        p.fq = fq_p;
-        p.ref = me.ref; p.res_coord = vs.res; p.copy_coord = vs.copy; p.cur_rw = cur;
-        IE_TRY(launch_pframe_tiles(p, st));
     }
     if (frames == 0) { /* header only */ }
-    if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, s->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, vs.cursor, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     return IE_OK;
 }
 
@@ -279,12 +425,14 @@ int ie_encode_video(const uint8_t *yuv, size_t yuv_bytes, uint32_t W, uint32_t H
     IE_TRY(cached_session(&s, 2, W, H, 4, frames));
     const size_t cap = ie_max_encoded_bytes(W, H, 4, std::max(1u, frames));
     IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, std::max<size_t>(yuv_bytes, 16)));
-    IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, cap));
+    const size_t cap16 = (cap + 15) / 16 * 16;
+    IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, cap16 + 64));
+    uint64_t *d_total = reinterpret_cast<uint64_t *>(s->d_out + cap16);           // the stream's bit count, behind the stream
     cudaStream_t st = s->stream;
     IE_CUDA(cudaMemcpyAsync(s->d_in, yuv, yuv_bytes, cudaMemcpyHostToDevice, st));
-    IE_TRY(ie_encode_video_dev(s, s->d_in, yuv_bytes, W, H, quant, use_rle, gop, merange, huffman ? 0 : 1, s->d_out, s->d_out_cap,
-                               nullptr, nullptr, st));
-    IE_CUDA(cudaMemcpyAsync(s->h_pinned, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    IE_TRY(ie_encode_video_dev(s, s->d_in, yuv_bytes, W, H, quant, use_rle, gop, merange, huffman ? 0 : 1, s->d_out, cap16,
+                               d_total, nullptr, st));
+    IE_CUDA(cudaMemcpyAsync(s->h_pinned, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     IE_TRY(read_err_flag(s, st));
     size_t bytes = (size_t)((s->h_pinned[0] + 7) / 8);
     const uint8_t *d_result = s->d_out;
@@ -327,7 +475,7 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
     const unsigned mvbits = host_bits_needed((int)(short)h.merange);
     IE_TRY(session_ensure_err(s));
     VideoScratch vs;
-    IE_TRY(video_scratch(s, nmb, vs));
+    IE_TRY(video_scratch(s, nmb, 1, vs));
     const size_t need_off = ((size_t)nblocks + 1) * sizeof(unsigned long long) + 64;
     if (s->block_off_cap < need_off) {
         if (s->d_block_off) IE_CUDA(cudaFree(s->d_block_off));

@@ -134,9 +134,15 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
     const int nblk = min((unsigned)TB, p.nblocks - first_blk);
 
     const uint8_t *src = p.src + (size_t)img * p.img_stride;
+    // P-frames of several GOPs in one launch: image i = the frame of GOP i (same strides for the reference frame, which is
+    // the frame before it, and for the frame being rebuilt in place)
+    const uint8_t *ref_i = PF ? p.ref + (size_t)img * p.img_stride : nullptr;
+    uint8_t *cur_rw_i = PF ? p.cur_rw + (size_t)img * p.img_stride : nullptr;
+    const short *res_coord_i = PF ? p.res_coord + (size_t)img * p.coord_stride : nullptr;
+    const short *copy_coord_i = PF ? p.copy_coord + (size_t)img * p.coord_stride : nullptr;
     const BlockTables *tab = p.tab;
     ExactCtx ex;
-    ex.src = src; ex.ref = p.ref; ex.res_coord = p.res_coord; ex.tab = tab; ex.pitch = p.pitch; ex.bx = p.bx; ex.mbx = p.mbx;
+    ex.src = src; ex.ref = ref_i; ex.res_coord = res_coord_i; ex.tab = tab; ex.pitch = p.pitch; ex.bx = p.bx; ex.mbx = p.mbx;
 
     // ---- phase 1: transform + quantise, lane per block ---------------------------------------------------
     unsigned r_orbits[BPL];
@@ -155,8 +161,8 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
         int rx = 0, ry = 0;
         if (PF) {
             const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
-            rx = p.res_coord[2 * mb] + (int)(bxi & 3) * 4;
-            ry = p.res_coord[2 * mb + 1] + (int)(byi & 3) * 4;
+            rx = res_coord_i[2 * mb] + (int)(bxi & 3) * 4;
+            ry = res_coord_i[2 * mb + 1] + (int)(byi & 3) * 4;
         }
         if (FAST) {
             float x[NN];
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
                 for (int k = 0; k < N; k++) {
                     // byte -> float by planting it in the mantissa of 2^23, then subtracting 2^23 + 128 (exact)
                     float f = __uint_as_float(__byte_perm(raw[k >> 2], 0x4B000000u, 0x7650u | (unsigned)(k & 3))) - 8388736.0f;
-                    if (PF) f -= (float)(int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + k);      // exact small integers
+                    if (PF) f -= (float)(int)__ldg(ref_i + (size_t)(ry + y) * p.pitch + rx + k);      // exact small integers
                     x[y * N + k] = f;
                 }
             }
@@ -311,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
             const unsigned gb = first_blk + lb;
             const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
             const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
-            const int kx = p.copy_coord[2 * mb] + (int)(bxi & 3) * 4, ky = p.copy_coord[2 * mb + 1] + (int)(byi & 3) * 4;
+            const int kx = copy_coord_i[2 * mb] + (int)(bxi & 3) * 4, ky = copy_coord_i[2 * mb + 1] + (int)(byi & 3) * 4;
             double X[NN];
 #pragma unroll
             for (int i = 0; i < NN; i++) X[i] = 0.0;
@@ -330,11 +336,11 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
                 unsigned outw = 0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const double rpx = (double)(int)__ldg(p.ref + (size_t)(ky + y) * p.pitch + kx + k);
+                    const double rpx = (double)(int)__ldg(ref_i + (size_t)(ky + y) * p.pitch + kx + k);
                     const unsigned v = clamp_trunc_u8(__dadd_rn(rpx, __dadd_rn(X[y * N + k], 128.0)));
                     outw |= v << (8 * k);
                 }
-                *reinterpret_cast<unsigned *>(p.cur_rw + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N) = outw;
+                *reinterpret_cast<unsigned *>(cur_rw_i + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N) = outw;
             }
         }
         s_w[lb] = (unsigned char)w;
@@ -584,8 +590,8 @@ int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStrea
     return IE_EINVAL;
 }
 
-int launch_pframe_tiles(const EncodeParams &p, cudaStream_t stream) {
-    return g_exact_transform.load() ? launch_cfg<4, 4, true, false>(p, 1, stream) : launch_cfg<4, 4, true, true>(p, 1, stream);
+int launch_pframe_tiles(const EncodeParams &p, unsigned images, cudaStream_t stream) {
+    return g_exact_transform.load() ? launch_cfg<4, 4, true, false>(p, images, stream) : launch_cfg<4, 4, true, true>(p, images, stream);
 }
 
 }  // namespace ie

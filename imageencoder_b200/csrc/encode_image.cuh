@@ -40,6 +40,7 @@ struct EncodeParams {
     const short *copy_coord;          // [nMB][2]
     uint8_t *cur_rw;                  // == src, writable
     unsigned mbx;                     // MacroBlocks per row
+    size_t coord_stride;              // shorts between the coordinate arrays of consecutive images (GOP batch)
 };
 
 unsigned encode_tile_blocks(int N);
@@ -48,7 +49,7 @@ extern std::atomic<int> g_exact_transform;
 // max_abs_sample: 128 for pixels - 128, 383 for P-frame residuals - 128
 void make_fast_quant(FastQuant &fq, const uint16_t *quant, int N, double max_abs_sample);
 int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream);
-int launch_pframe_tiles(const EncodeParams &p, cudaStream_t stream);
+int launch_pframe_tiles(const EncodeParams &p, unsigned images, cudaStream_t stream);
 int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t stream);          // phase 2 of a split encode
 int launch_tile_totals(const unsigned *tile_bits, unsigned ntiles, unsigned images, unsigned long long add, unsigned long long *d_total,
                        cudaStream_t stream);                                                   // d_total[img] = add + sum of the image's tile bits

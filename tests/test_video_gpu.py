@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("W,H,F,gop,mer", [(64, 48, 7, 4, 16), (128, 96, 9, 3, 8), (176, 144, 6, 6, 32),
-                                            (64, 64, 5, 1, 16), (64, 48, 6, 7, 2), (64, 48, 5, 4, 1), (96, 64, 6, 4, 10)])
+                                            (64, 64, 5, 1, 16), (64, 48, 6, 7, 2), (64, 48, 5, 4, 1), (96, 64, 6, 4, 10),
+                                            (64, 48, 70, 1, 4), (64, 48, 131, 2, 8)])      # more GOPs than one launch batch (64)
 @pytest.mark.parametrize("huffman", [False, True])
 def test_video_matches_oracle(gpu, oracle_mod, W, H, F, gop, mer, huffman):
     from imageencoder_b200.synth import synth_video

@@ -113,4 +113,19 @@ svd = device.Session(3, W, H, 4, F)
 d_vdec = torch.empty(W * H * 3 // 2 * F, dtype=torch.uint8, device="cuda")
 ms = wall(lambda: (device.decode_video_dev(svd, d_vout, vb, d_vdec, True), torch.cuda.synchronize()), reps=3, warm=1)
 out["video_decode_dev_ms_per_frame"] = ms / F; out["video_decode_dev_gpx_s"] = W * H * F / ms / 1e6
+# ---- config 5 shape: 240 frames, GOP 12 -> 20 GOPs per launch ------------------------------------------------
+del d_yuv, d_yuv0, d_vout, d_vdec
+F5 = 240
+yuv5 = synth_video(W, H, F5, 4000)
+d_yuv0 = torch.from_numpy(np.ascontiguousarray(yuv5)).cuda().reshape(-1)
+d_yuv = d_yuv0.clone()
+d_vout = torch.empty(int(L.ie_max_encoded_bytes(W, H, 4, F5)) + 4096, dtype=torch.uint8, device="cuda")
+sv5 = device.Session(2, W, H, 4, F5)
+def venc5():
+    d_yuv.copy_(d_yuv0)
+    device.encode_video_dev(sv5, d_yuv, W, H, qv, True, 12, 16, d_vout, d_bits, lead_bit=True)
+copy_ms = ev_time(lambda: d_yuv.copy_(d_yuv0))
+ms = ev_time(venc5, reps=3, warm=1) - copy_ms
+out["video240_encode_dev_ms_per_frame"] = ms / F5; out["video240_encode_dev_gpx_s"] = W * H * F5 / ms / 1e6
+out["video240_bytes"] = (int(d_bits.item()) + 7) // 8
 print(json.dumps(out, indent=1))
