@@ -508,6 +508,34 @@ static int build_dictionary(const unsigned *hist, const unsigned long long *firs
 
 static int ensure_scratch(ie_session *s, size_t need) { return session_reserve(&s->d_scratch, &s->scratch_cap, need); }
 
+// Dictionary from a (global) histogram, then the scan-pack of `n` bytes behind it (write_dict) or from bit 0 (a later shard of
+// a multi-GPU stream).  Leaves the stream's bit count in s->d_counter[0].  The scratch must be ensured by the caller.
+static int huffman_pack_dev(ie_session *s, const uint8_t *d_in, size_t n, const unsigned *hist, const unsigned long long *first,
+                            int write_dict, uint8_t *d_out, size_t out_cap, cudaStream_t st) {
+    HuffCodes *d_codes = reinterpret_cast<HuffCodes *>(s->d_scratch + 256 * 8 + 256 * 4);
+    HuffCodes codes;
+    HostBitWriter hdr;
+    IE_TRY(build_dictionary(hist, first, codes, hdr));
+    if (!write_dict) { hdr.pos = 0; hdr.buf.assign(16, 0); }
+    const size_t hdr_bytes16 = std::max<size_t>(16, (hdr.pos + 127) / 128 * 16);
+    hdr.buf.resize(hdr_bytes16, 0);
+    if (out_cap < hdr_bytes16 + 16) { set_error("output buffer too small"); return IE_ENOSPC; }
+    IE_CUDA(cudaMemcpyAsync(d_out, hdr.buf.data(), hdr_bytes16, cudaMemcpyHostToDevice, st));
+    IE_CUDA(cudaMemcpyAsync(d_codes, &codes, sizeof codes, cudaMemcpyHostToDevice, st));
+    const unsigned ntiles = (unsigned)((n + kHuffTileBytes - 1) / kHuffTileBytes);
+    IE_TRY(session_ensure_scan(s, 1, ntiles));
+    const unsigned long long hb = hdr.pos;
+    IE_CUDA(cudaMemcpyAsync(s->d_counter, &hb, sizeof hb, cudaMemcpyHostToDevice, st));
+    HuffEncodeParams p;
+    p.in = d_in; p.n = n; p.ntiles = ntiles; p.codes = d_codes; p.out = d_out; p.out_cap = out_cap;
+    p.bit_counter = s->d_counter; p.err = s->d_err; p.scan = s->scan_state();
+    huff_encode_kernel<<<ntiles, kThreads, 0, st>>>(p);
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    IE_CUDA(cudaStreamSynchronize(st));            // `codes` / `hdr` are host objects of this frame
+    return IE_OK;
+}
+
 }  // namespace ie
 
 using namespace ie;
@@ -561,24 +589,7 @@ int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
     IE_CUDA(cudaMemcpyAsync(first, d_first, sizeof first, cudaMemcpyDeviceToHost, st));
     IE_CUDA(cudaStreamSynchronize(st));
 
-    HuffCodes codes;
-    HostBitWriter hdr;
-    IE_TRY(build_dictionary(hist, first, codes, hdr));
-    const size_t hdr_bytes16 = (hdr.pos + 127) / 128 * 16;
-    hdr.buf.resize(hdr_bytes16, 0);
-    if (out_cap < hdr_bytes16 + 16) { set_error("output buffer too small"); return IE_ENOSPC; }
-    IE_CUDA(cudaMemcpyAsync(d_out, hdr.buf.data(), hdr_bytes16, cudaMemcpyHostToDevice, st));
-    IE_CUDA(cudaMemcpyAsync(d_codes, &codes, sizeof codes, cudaMemcpyHostToDevice, st));
-    const unsigned ntiles = (unsigned)((n + kHuffTileBytes - 1) / kHuffTileBytes);
-    IE_TRY(session_ensure_scan(s, 1, ntiles));
-    const unsigned long long hb = hdr.pos;
-    IE_CUDA(cudaMemcpyAsync(s->d_counter, &hb, sizeof hb, cudaMemcpyHostToDevice, st));
-    HuffEncodeParams p;
-    p.in = d_in; p.n = n; p.ntiles = ntiles; p.codes = d_codes; p.out = d_out; p.out_cap = out_cap;
-    p.bit_counter = s->d_counter; p.err = s->d_err; p.scan = s->scan_state();
-    huff_encode_kernel<<<ntiles, kThreads, 0, st>>>(p);
-    count_launch();
-    IE_CUDA(cudaGetLastError());
+    IE_TRY(huffman_pack_dev(s, d_in, n, hist, first, 1, d_out, out_cap, st));
     IE_CUDA(cudaMemcpyAsync(s->h_pinned, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     IE_TRY(read_err_flag(s, st));
     size_t total = (size_t)((s->h_pinned[0] + 7) / 8);
@@ -592,6 +603,21 @@ int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
     }
     *out_bytes = total;
     return IE_OK;
+}
+
+int ie_huffman_encode_shard_dev(ie_session *s, const uint8_t *d_in, size_t n, const uint32_t *hist, const uint64_t *first_pos,
+                                int write_dictionary, uint8_t *d_out, size_t out_cap, uint64_t *d_out_bits, void *stream) {
+    if (!s || !d_in || !d_out || !hist || !first_pos || n == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    if ((uintptr_t)d_out % 16) { set_error("stream buffers must be 16-byte aligned"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    IE_TRY(ensure_scratch(s, 256 * 8 + 256 * 4 + sizeof(HuffCodes) + 64));
+    IE_TRY(session_ensure_err(s));
+    unsigned h[256];
+    unsigned long long f[256];
+    for (int i = 0; i < 256; i++) { h[i] = hist[i]; f[i] = first_pos[i]; }
+    IE_TRY(huffman_pack_dev(s, d_in, n, h, f, write_dictionary, d_out, out_cap, st));
+    if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, s->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return read_err_flag(s, st);
 }
 
 int ie_stream_shift_dev(const uint8_t *d_in, const uint64_t *d_params, uint8_t *d_out, size_t out_cap, void *stream) {

@@ -106,6 +106,21 @@ def huffman_encode_dev(s: Session, d_in: torch.Tensor, in_bytes: int, d_out: tor
     return n.value
 
 
+def huffman_encode_shard_dev(s: Session, d_in: torch.Tensor, in_bytes: int, hist, first_pos, write_dictionary: bool,
+                             d_out: torch.Tensor, d_out_bits: torch.Tensor) -> None:
+    """Huffman stage of one shard with the GLOBAL histogram / first-occurrence positions (host arrays)."""
+    h = np.ascontiguousarray(hist, dtype=np.uint32)
+    f = np.ascontiguousarray(first_pos, dtype=np.uint64)
+    check(lib().ie_huffman_encode_shard_dev(s.h, _dp(d_in), in_bytes, h.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                            f.ctypes.data_as(C.POINTER(C.c_uint64)), int(write_dictionary), _dp(d_out),
+                                            d_out.numel(), _dp(d_out_bits), _stream()))
+
+
+def stream_shift_dev(d_in: torch.Tensor, d_params: torch.Tensor, d_out: torch.Tensor) -> None:
+    """d_out bit (params[1] % 128 + i) = d_in bit i for i < params[0]  (re-alignment of a shard stream)."""
+    check(lib().ie_stream_shift_dev(_dp(d_in), _dp(d_params), _dp(d_out), d_out.numel(), _stream()))
+
+
 def byte_histogram_dev(d_in: torch.Tensor, n: int):
     hist = np.zeros(256, dtype=np.uint32)
     first = np.zeros(256, dtype=np.uint64)

@@ -74,6 +74,33 @@ def total_bytes(placements: list[ShardPlacement]) -> int:
     return (last.global_bit + last.nbits + 7) // 8
 
 
+ABSENT = (1 << 64) - 1        # first-occurrence value of a byte that does not occur (ie_byte_histogram_dev)
+
+
+def shard_byte_range(placements: list[ShardPlacement], rank: int) -> tuple[int, int]:
+    """Bytes [b0, b1) of the global plain stream whose Huffman codes `rank` produces: a byte belongs to the shard that holds
+    its first bit (the byte two shards share goes to the left one, which gets the right one's bits of it)."""
+    b0 = 0 if rank == 0 else (placements[rank].global_bit + 7) // 8
+    last = rank == len(placements) - 1
+    end_bit = placements[rank].global_bit + placements[rank].nbits
+    b1 = (end_bit + 7) // 8                     # the last shard ends the stream; otherwise: ceil(first bit of rank+1 / 8)
+    return b0, max(b0, b1) if last or placements[rank].nbits else b0
+
+
+def reduce_histograms(hists, firsts, byte_offsets):
+    """What the all-reduce computes: sum of the shard histograms, min of the shard-local first occurrences moved to
+    global byte positions (Huffman.cpp:236-243 feeds its containers in first-occurrence order)."""
+    import numpy as np
+    hist = np.zeros(256, dtype=np.uint64)
+    first = np.full(256, ABSENT, dtype=np.uint64)
+    for h, f, off in zip(hists, firsts, byte_offsets):
+        hist += np.asarray(h, dtype=np.uint64)
+        f = np.asarray(f, dtype=np.uint64)
+        g = np.where(f == ABSENT, f, f + np.uint64(off))
+        first = np.minimum(first, g)
+    return hist.astype(np.uint32), first
+
+
 def merge_shard_into(stream: bytearray, shard: bytes, pl: ShardPlacement) -> None:
     """Host-side merge of one re-aligned shard buffer into the global stream (the writer side of the stitch)."""
     if pl.nbytes == 0:
@@ -153,3 +180,116 @@ class ShardedImageEncoder:
             dist.all_gather_into_tensor(totals, self.d_total, group=group)
         device.encode_image_end_dev(self.sess, totals, rank, self.d_aligned, self.d_bits, self.d_first)
         return totals
+
+
+class ShardedHuffmanStage:
+    """Huffman stage of a block-row sharded encode (BASELINE config 3): every rank codes the bytes of the plain stream it
+    holds with the dictionary of the WHOLE stream.
+
+    exchange 1 (all-gather, one byte per rank): the bits a rank has of the byte it shares with its left neighbour
+    exchange 2 (all-reduce): 256-bin histogram (sum) and first-occurrence positions (min)
+    exchange 3 (all-gather, one u64 per rank): code bits per shard -> offsets of the Huffman shards
+    The tree is built on every rank from identical inputs (same libstdc++ containers as the reference, csrc/huffman.cu).
+    """
+
+    def __init__(self, enc: ShardedImageEncoder):
+        import torch
+
+        from . import device
+        self.enc = enc
+        self.sess = device.Session(device.Session.IMAGE_ENCODE, enc.width, enc.shard_height, enc.block)
+        self.d_plain = torch.zeros(enc.cap + 64, dtype=torch.uint8, device="cuda")
+        self.d_code = torch.zeros(enc.cap + (1 << 16), dtype=torch.uint8, device="cuda")
+        self.d_out = torch.zeros(enc.cap + (1 << 16) + 32, dtype=torch.uint8, device="cuda")
+        self.d_bits = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self.d_params = torch.zeros(2, dtype=torch.int64, device="cuda")
+
+    # -- step 1: what the left neighbour needs ----------------------------------------------------------------------
+    def head_byte(self, pl: list[ShardPlacement], rank: int) -> int:
+        p = pl[rank]
+        if rank == 0 or p.global_bit % 8 == 0 or p.nbits == 0:
+            return 0
+        return int(self.enc.d_aligned[p.global_bit // 8 - p.byte_offset].item())
+
+    # -- step 2: this rank's bytes, then their histogram --------------------------------------------------------------
+    def local_histogram(self, pl: list[ShardPlacement], rank: int, heads: list[int]):
+        from . import device
+        p = pl[rank]
+        self.b0, self.b1 = shard_byte_range(pl, rank)
+        self.n = self.b1 - self.b0
+        if rank + 1 < len(pl) and pl[rank + 1].global_bit % 8 and self.n:
+            self.enc.d_aligned[self.b1 - 1 - p.byte_offset] |= heads[rank + 1]
+        if self.n == 0:
+            import numpy as np
+            return np.zeros(256, np.uint32), np.full(256, ABSENT, np.uint64)
+        self.d_plain[: self.n].copy_(self.enc.d_aligned[self.b0 - p.byte_offset: self.b1 - p.byte_offset])
+        return device.byte_histogram_dev(self.d_plain, self.n)
+
+    # -- step 3: code this rank's bytes ---------------------------------------------------------------------------------
+    def encode(self, hist, first, rank: int) -> int:
+        import torch
+
+        from . import device
+        if self.n == 0:
+            self.d_bits.zero_()
+            return 0
+        device.huffman_encode_shard_dev(self.sess, self.d_plain, self.n, hist, first, rank == 0, self.d_code, self.d_bits)
+        torch.cuda.synchronize()
+        return int(self.d_bits.item())
+
+    # -- step 4: place the shard (or, by the reference's revert rule, the raw bytes behind a '0' bit) -----------------------
+    def place(self, code_bits: list[int], plain_pl: list[ShardPlacement], rank: int) -> tuple[list[ShardPlacement], bool]:
+        from . import device
+        total_code_bytes = (sum(code_bits) + 7) // 8
+        reverted = total_bytes(plain_pl) < total_code_bytes                        # Huffman.cpp:329-341: no gain
+        if reverted:
+            # '0' + the plain bytes: rank r's bytes start at bit 1 + 8 * b0(r); nothing more to exchange
+            ranges = [shard_byte_range(plain_pl, r) for r in range(len(plain_pl))]
+            bits = [8 * (b1 - b0) + (1 if r == 0 else 0) for r, (b0, b1) in enumerate(ranges)]
+            pl = place_shards(bits)
+            self.d_params[0] = 8 * self.n
+            self.d_params[1] = 1 + 8 * self.b0
+            device.stream_shift_dev(self.d_plain, self.d_params, self.d_out)
+            return pl, True
+        pl = place_shards(code_bits)
+        self.d_params[0] = code_bits[rank]
+        self.d_params[1] = pl[rank].global_bit
+        device.stream_shift_dev(self.d_code, self.d_params, self.d_out)
+        return pl, False
+
+
+def sharded_image_encode_huffman(enc: ShardedImageEncoder, stage: ShardedHuffmanStage, d_raw, quant, rle: bool, rank: int, group=None):
+    """Block-row sharded encode + Huffman stage over `torch.distributed`.  Returns (placements of the Huffman shards, this
+    rank's aligned shard bytes as a device tensor view)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    totals = enc.encode(d_raw, quant, rle, rank, lead_bit=False, group=group)
+    pl = place_shards([int(b) for b in totals.cpu().tolist()])
+    heads = [stage.head_byte(pl, rank)]
+    if world > 1:
+        t = torch.tensor(heads, dtype=torch.int64, device="cuda")
+        g = torch.empty(world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(g, t, group=group)
+        heads = [int(x) for x in g.cpu().tolist()]
+    hist, first = stage.local_histogram(pl, rank, heads)
+    h = torch.from_numpy(hist.astype(np.int64)).cuda()
+    f = np.where(first == ABSENT, np.uint64((1 << 62)), first + np.uint64(stage.b0)).astype(np.int64)
+    f = torch.from_numpy(f).cuda()
+    if world > 1:
+        dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN, group=group)
+    hist_g = h.cpu().numpy().astype(np.uint32)
+    f_g = f.cpu().numpy().astype(np.uint64)
+    first_g = np.where(f_g >= np.uint64(1 << 62), np.uint64(ABSENT), f_g)
+    bits = stage.encode(hist_g, first_g, rank)
+    code_bits = [bits]
+    if world > 1:
+        t = torch.tensor(code_bits, dtype=torch.int64, device="cuda")
+        g = torch.empty(world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(g, t, group=group)
+        code_bits = [int(x) for x in g.cpu().tolist()]
+    hpl, _ = stage.place(code_bits, pl, rank)
+    return hpl, stage.d_out[: hpl[rank].nbytes]

@@ -121,6 +121,14 @@ int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes,
                           uint8_t *d_out, size_t out_cap, size_t *out_bytes, void *stream);
 int ie_huffman_decode_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes,
                           uint8_t *d_out, size_t out_cap, size_t *out_bytes, uint64_t *start_bit, void *stream);
+/* Huffman stage of one shard of a multi-GPU stream: the dictionary is built from the GLOBAL histogram and
+ * first-occurrence positions (host arrays: the ranks' ie_byte_histogram_dev results, summed / min-reduced with the shard's
+ * byte offset added), so every rank derives the same codes; `write_dictionary` (rank 0) puts the dictionary header in
+ * front.  The shard's code bits start at bit 0 of d_out (after the dictionary on rank 0); *d_out_bits (device) = bits
+ * written.  The "no gain" revert rule (Huffman.cpp:329-341) needs the global total and is the caller's decision. */
+int ie_huffman_encode_shard_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes, const uint32_t *hist,
+                                const uint64_t *first_pos, int write_dictionary, uint8_t *d_out, size_t out_cap,
+                                uint64_t *d_out_bits, void *stream);
 /* Device histogram + first-occurrence positions of a byte stream (Huffman.cpp:236-243); hist[256] u32,
  * first_pos[256] u64 (UINT64_MAX = absent).  HOST outputs; synchronises `stream`. */
 int ie_byte_histogram_dev(const uint8_t *d_in, size_t in_bytes, uint32_t *hist, uint64_t *first_pos, void *stream);

@@ -102,3 +102,74 @@ def test_gloo_world2_offset_scan_and_stitch():
         p.join(timeout=60)
     assert res[0] == "ok", res
     assert res[1], f"stitched stream differs from the oracle's ({res[2]} vs {res[3]} bytes)"
+
+
+def _hist_first(b: np.ndarray):
+    hist = np.bincount(b, minlength=256).astype(np.int64)
+    first = np.full(256, 1 << 62, dtype=np.int64)
+    idx = np.arange(len(b), dtype=np.int64)
+    for v in np.unique(b):
+        first[v] = idx[b == v][0]
+    return hist, first
+
+
+def _huff_worker(rank: int, world: int, port: int, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    import oracle
+    from imageencoder_b200.parallel import place_shards, shard_block_rows, shard_byte_range
+    from imageencoder_b200.synth import synth_image
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        W, H, N = 128, 96, 8
+        quant = oracle.read_matrix(INPUTS / "matrix8_2.txt")
+        img = synth_image(W, H, 6, flat=True)
+        full, full_bits, coef, bl, lf = oracle.image_encode_plain(img, W, H, N, quant, True, False, stages=True)   # no lead bit
+        hdr = oracle.header_bits(N, quant, False)
+        per_block = 4 + bl.astype(np.int64) + lf.astype(np.int64) * bl.astype(np.int64)
+        y0, y1 = shard_block_rows(H, N, world, rank)
+        b0, b1 = (y0 // N) * (W // N), (y1 // N) * (W // N)
+        nbits = int(per_block[b0:b1].sum()) + (hdr if rank == 0 else 0)
+        t = torch.tensor([nbits], dtype=torch.int64)
+        totals = torch.empty(world, dtype=torch.int64)
+        dist.all_gather_into_tensor(totals, t)
+        pl = place_shards([int(x) for x in totals])
+        lo, hi = shard_byte_range(pl, rank)
+        mine = np.frombuffer(full, np.uint8)[lo:hi]                       # the bytes this rank would Huffman-code
+        hist, first = _hist_first(mine)
+        first = np.where(first == (1 << 62), first, first + lo)
+        h, f = torch.from_numpy(hist), torch.from_numpy(first)
+        dist.all_reduce(h, op=dist.ReduceOp.SUM)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        gh, gf = _hist_first(np.frombuffer(full, np.uint8))
+        ranges = [shard_byte_range(pl, r) for r in range(world)]
+        cover = ranges[0][0] == 0 and ranges[-1][1] == len(full) and all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+        if rank == 0:
+            q.put(("ok", bool(np.array_equal(h.numpy(), gh)) and bool(np.array_equal(f.numpy(), gf)), cover))
+    except Exception as e:  # pragma: no cover
+        q.put(("err", repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_huffman_histogram_exchange():
+    """The exchange of the sharded Huffman stage: byte ranges tile the plain stream; all-reduced histogram (sum) and
+    first-occurrence positions (min) equal those of the whole stream -> every rank builds the reference's dictionary."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_huff_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0] == "ok", res
+    assert res[1], "reduced histogram / first occurrences differ from the whole stream's"
+    assert res[2], "byte ranges do not tile the stream"

@@ -91,6 +91,49 @@ def test_split_encode_places_shards_without_realignment(gpu, oracle_mod):
         assert got == want, f"{matrix} x{world}: stitched stream differs"
 
 
+def test_sharded_huffman_stage_matches_single_stream(gpu, oracle_mod):
+    """BASELINE config 3 shape on one GPU: block-row shards, then every emulated rank Huffman-codes its bytes with the
+    dictionary of the whole stream (histogram sum / first-occurrence min = what the all-reduce computes); the stitched
+    result is the oracle's ENABLE_HUFFMAN file."""
+    import torch
+    from imageencoder_b200._lib import check, lib
+    from imageencoder_b200.parallel import (ShardedHuffmanStage, ShardedImageEncoder, merge_shard_into, place_shards, reduce_histograms,
+                                            shard_block_rows, total_bytes)
+    from imageencoder_b200.synth import synth_image
+    W, H = 512, 384
+    for matrix, world, seed, flat in (("matrix8_2.txt", 3, 81, True), ("matrix.txt", 4, 82, False), ("matrix8_1.txt", 2, 83, True)):
+        q = oracle_mod.read_matrix(INPUTS / matrix)
+        N = q.shape[0]
+        img = synth_image(W, H, seed, flat=flat)
+        want = oracle_mod.image_encode(img, W, H, N, q, True, True)
+        encs, d_totals = [], []
+        for r in range(world):
+            y0, y1 = shard_block_rows(H, N, world, r)
+            e = ShardedImageEncoder(W, y1 - y0, N, H)
+            from imageencoder_b200 import device
+            device.encode_image_begin_dev(e.sess, torch.from_numpy(img[y0:y1].copy()).cuda().reshape(-1), q, True, e.d_total,
+                                          lead_bit=False, write_header=(r == 0), width=W, height=y1 - y0)
+            encs.append(e)
+            d_totals.append(e.d_total)
+        totals = torch.cat(d_totals)                                   # all-gather 1
+        for r in range(world):
+            device.encode_image_end_dev(encs[r].sess, totals, r, encs[r].d_aligned, encs[r].d_bits, encs[r].d_first)
+        torch.cuda.synchronize()
+        pl = place_shards([int(b) for b in totals.cpu().tolist()])
+        stages = [ShardedHuffmanStage(e) for e in encs]
+        heads = [stages[r].head_byte(pl, r) for r in range(world)]     # all-gather 2
+        hf = [stages[r].local_histogram(pl, r, heads) for r in range(world)]
+        hist, first = reduce_histograms([h for h, _ in hf], [f for _, f in hf], [st.b0 for st in stages])   # all-reduce
+        code_bits = [stages[r].encode(hist, first, r) for r in range(world)]                               # all-gather 3
+        stream = bytearray()
+        for r in range(world):
+            hpl, reverted = stages[r].place(code_bits, pl, r)
+            torch.cuda.synchronize()
+            merge_shard_into(stream, stages[r].d_out[: hpl[r].nbytes].cpu().numpy().tobytes(), hpl[r])
+        got = bytes(stream[: total_bytes(hpl)])
+        assert got == want, f"{matrix} x{world}: sharded Huffman stream differs ({len(got)} vs {len(want)} bytes, reverted={reverted})"
+
+
 def test_batch_entry_point(gpu, oracle_mod):
     from imageencoder_b200._lib import check, lib
     from imageencoder_b200.synth import synth_image
