@@ -218,7 +218,6 @@ __global__ void fill_uv_kernel(uint8_t *yuv, size_t ysz, size_t fsz, unsigned fr
     }
 }
 
-constexpr unsigned long long kGroupSpanSlack = 1ull << 18;   // the parser rounds spans up to whole groups
 
 static unsigned host_bits_needed(int v) {                    // utils.hpp:226-243
     const short value = (short)v;
@@ -492,12 +491,12 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
     p.enc = d_enc; p.enc_bits = d_consts; p.start_bit = d_consts + 1; p.block_off = s->d_block_off; p.nblocks = nblocks;
     p.bx = W / 4; p.N = 4; p.use_rle = h.use_rle; make_quant(p.quant, h.quant, 4); make_k2(p.k2, h.quant, 4); p.tab = s->dev->d_t4; p.pitch = W; p.err = s->d_err;
     p.cursor = vs.cursor;
-    IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, parse_scratch_bytes(enc_bytes, 4)));
-    // The chain of a frame is followed over a bounded span of the stream (its size is not known in advance): start from the
-    // average frame size, grow from what the previous frames needed, retry with a larger span when the last block was not
-    // reached (the cursor did not move).  One 8-byte read-back per frame.
-    unsigned long long cursor_h = consts[1];
-    size_t span = std::max<size_t>((enc_bytes * 8 / std::max(1u, frames)) * 2, (size_t)1 << 16);
+    // The chain of a frame is followed over a span of the stream that covers the largest possible frame (every block at its
+    // maximum size): the frame's end is not known in advance, and a read-back per frame to size the span would serialise the
+    // host with the device.  What the walkers find behind the frame's last block is ignored (parse.cu); the cursor stays on
+    // the device.
+    const size_t span = (size_t)nblocks * (4 + 16 + 16 * 16) + ((size_t)1 << 16);
+    IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, parse_scratch_bytes(std::max(enc_bytes, span / 8 + 1), 4)));
     for (uint32_t f = 0; f < frames; f++) {
         uint8_t *cur = d_out + (size_t)f * fsz;
         const bool is_i = (f % h.gop) == 0;
@@ -513,17 +512,7 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
             IE_CUDA(cudaGetLastError());
             p.skip_bits = nmb * 2 * mvbits; p.add_mode = 1;
         }
-        const unsigned long long first_block = std::min<unsigned long long>(cursor_h + p.skip_bits, consts[0]);
-        while (true) {
-            IE_TRY(launch_parallel_parse(p, span, s->d_parse, st));          // advances the cursor past this frame
-            IE_CUDA(cudaMemcpyAsync(s->h_pinned, vs.cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            IE_CUDA(cudaStreamSynchronize(st));
-            if (s->h_pinned[0] != cursor_h || first_block + span >= consts[0] + kGroupSpanSlack) break;
-            span *= 4;
-        }
-        const unsigned long long used = s->h_pinned[0] - std::min(s->h_pinned[0], first_block);
-        cursor_h = s->h_pinned[0];
-        span = std::max<size_t>(span / 2, (size_t)used * 2 + ((size_t)1 << 16));
+        IE_TRY(launch_parallel_parse(p, span, s->d_parse, st));              // advances the cursor past this frame
         if (is_i || motioncomp) IE_TRY(launch_decode_blocks(p, 1, st));      // Frame.cpp:107-117
     }
     if (frames) {

@@ -184,20 +184,18 @@ constexpr int kWalkGroups = 64;           // groups (= threads) per CTA of the s
 // of blocks they hold: an all-zero block is 4 zero bits (bit_len 0, no length/values), so a run of zero nibbles is a run of
 // blocks and is taken in one step (up to 8, never starting a block at or past `lim`).  0 blocks = invalid length field.
 __device__ __forceinline__ unsigned staged_step(const StagedStream &st, unsigned rel, unsigned lim, int NN, int rle, unsigned &blocks) {
+    // branch-free: the lanes of a warp are at unrelated places of the stream, every data-dependent branch would serialise them
     const unsigned i = rel >> 5;
     const unsigned w0 = __byte_perm(st.w[i], 0, 0x0123);
     const unsigned w1 = __byte_perm(st.w[i + 1], 0, 0x0123);                // zero past the end of the stream (stage_stream)
     const unsigned v = __funnelshift_l(w1, w0, rel & 31u);
     const unsigned w = v >> 28;
-    if (w == 0) {
-        const unsigned k = min(min((unsigned)__clz((int)v) >> 2, 8u), (lim - rel + 3u) >> 2);
-        blocks = k;
-        return 4u * k;
-    }
-    unsigned len = (unsigned)NN;
-    if (rle) len = (v << 4) >> (32 - w);
-    blocks = (len > (unsigned)NN) ? 0u : 1u;
-    return 4u + (rle ? w : 0u) + len * w;
+    const unsigned zk = min(min((unsigned)__clz((int)v) >> 2, 8u), (lim - rel + 3u) >> 2);    // zero nibbles = all-zero blocks
+    const unsigned lenf = __funnelshift_rc(v << 4, 0u, 32u - w);                               // (v << 4) >> (32 - w), 0 for w = 0
+    const unsigned len = rle ? lenf : (unsigned)NN;
+    const unsigned one = 4u + (rle ? w : 0u) + len * w;
+    blocks = (w == 0) ? zk : ((len > (unsigned)NN) ? 0u : 1u);
+    return (w == 0) ? 4u * zk : one;
 }
 
 // walks the chain from `rel` to the group's end (both relative to the view): (exit offset | kDead, blocks started)
