@@ -49,6 +49,7 @@ SIGNATURES = {
     "ie_byte_histogram_dev": (C.c_int, [_vp, C.c_size_t, _u32p, _u64p, _vp]),
     "ie_encode_video_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, C.c_uint32, _u16p, C.c_int, C.c_uint32, C.c_uint32,
                                       C.c_int, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "ie_session_set_video_shard": (C.c_int, [_vp, C.c_uint32, C.c_int]),
     "ie_decode_video_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, C.c_int, _vp, C.c_size_t, _u32p, _u32p, _u32p, _vp]),
     "ie_stream_shift_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "ie_set_option": (C.c_int, [C.c_char_p, C.c_int]),

@@ -344,7 +344,8 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
 
     HeaderParam hdr, nohdr;
     memset(&nohdr, 0, sizeof nohdr);
-    IE_TRY(build_header(hdr, 4, quant, use_rle, W, H, lead_bit, 1, frames, gop, merange));
+    if (s->video_no_header) hdr = nohdr;         // a later GOP shard of a clip: its stream starts with its first frame
+    else IE_TRY(build_header(hdr, 4, quant, use_rle, W, H, lead_bit, 1, s->header_frames ? s->header_frames : frames, gop, merange));
     if (out_cap < 256) { set_error("output buffer too small"); return IE_ENOSPC; }
     IE_TRY(launch_stream_init(d_out, 0, 1, hdr, 0, vs.cursor, st));
 
@@ -411,6 +412,13 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     }
     if (frames == 0) { /* header only */ }
     if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, vs.cursor, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return IE_OK;
+}
+
+int ie_session_set_video_shard(ie_session *s, uint32_t total_frames, int write_header) {
+    if (!s || total_frames > 32767) { set_error("bad argument"); return IE_EINVAL; }
+    s->header_frames = total_frames;
+    s->video_no_header = write_header ? 0 : 1;
     return IE_OK;
 }
 

@@ -574,7 +574,6 @@ int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
     IE_TRY(ensure_scratch(s, need));
     unsigned long long *d_first = reinterpret_cast<unsigned long long *>(s->d_scratch);
     unsigned *d_hist = reinterpret_cast<unsigned *>(s->d_scratch + 256 * 8);
-    HuffCodes *d_codes = reinterpret_cast<HuffCodes *>(s->d_scratch + 256 * 8 + 256 * 4);
     IE_TRY(session_ensure_err(s));
 
     IE_CUDA(cudaMemsetAsync(d_hist, 0, 256 * 4, st));

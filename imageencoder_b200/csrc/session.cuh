@@ -9,6 +9,10 @@ struct ie_session {
     uint32_t W = 0, H = 0, N = 0, frames = 1;
     int device = -1;
     uint32_t header_height = 0;                   // 0: use the height of the call
+    // GOP shard of a longer clip (multi-GPU): frame count announced by the header (0: the frames of the call) and whether
+    // this shard writes the header at all (the first shard does)
+    uint32_t header_frames = 0;
+    int video_no_header = 0;
     ie::DeviceState *dev = nullptr;
 
     // scan scratch, sized for `images` streams of `max_tiles` tiles (zeroed once; self-cleaning afterwards)

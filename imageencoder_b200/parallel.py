@@ -293,3 +293,42 @@ def sharded_image_encode_huffman(enc: ShardedImageEncoder, stage: ShardedHuffman
         code_bits = [int(x) for x in g.cpu().tolist()]
     hpl, _ = stage.place(code_bits, pl, rank)
     return hpl, stage.d_out[: hpl[rank].nbytes]
+
+
+class ShardedVideoEncoder:
+    """Encodes this rank's whole GOPs of a clip (BASELINE config 5) and re-aligns the result for the single output stream.
+    GOPs are independent (VideoBase.hpp:32), so the only exchange is the all-gather of one u64 per rank."""
+
+    def __init__(self, width: int, height: int, total_frames: int, gop: int, world: int, rank: int):
+        import torch
+
+        from . import device
+        from ._lib import check, lib
+        self.width, self.height, self.gop = width, height, max(1, gop)
+        self.f0, self.f1 = shard_gops(total_frames, self.gop, world, rank)
+        self.frames = self.f1 - self.f0
+        self.sess = device.Session(device.Session.VIDEO_ENCODE, width, height, 4, max(1, self.frames))
+        check(lib().ie_session_set_video_shard(self.sess.h, total_frames, int(rank == 0)))
+        cap = int(lib().ie_max_encoded_bytes(width, height, 4, max(1, self.frames))) + 4096
+        self.d_local = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        self.d_aligned = torch.zeros(cap + 32, dtype=torch.uint8, device="cuda")
+        self.d_bits = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self.d_params = torch.zeros(2, dtype=torch.int64, device="cuda")
+
+    def encode(self, d_yuv_shard, quant, rle: bool, merange: int, rank: int, lead_bit: bool = True, group=None):
+        """d_yuv_shard: this rank's frames [f0, f1) (YUV420, rebuilt in place).  Returns the device tensor of all ranks' bit
+        totals; self.d_aligned holds this rank's bytes of the global stream from byte (offset // 128) * 16."""
+        import torch
+        import torch.distributed as dist
+
+        from . import device
+        if self.frames or rank == 0:
+            device.encode_video_dev(self.sess, d_yuv_shard, self.width, self.height, quant, rle, self.gop, merange, self.d_local,
+                                    self.d_bits, lead_bit=lead_bit)
+        else:
+            self.d_bits.zero_()
+        totals, offsets = exchange_bit_totals(self.d_bits, group)
+        self.d_params[0] = self.d_bits[0]
+        self.d_params[1] = offsets[rank]
+        device.stream_shift_dev(self.d_local, self.d_params, self.d_aligned)
+        return totals

@@ -136,6 +136,11 @@ int ie_byte_histogram_dev(const uint8_t *d_in, size_t in_bytes, uint32_t *hist, 
 int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv420, size_t yuv_bytes, uint32_t width, uint32_t height,
                         const uint16_t *quant, int use_rle, uint32_t gop, uint32_t merange, int lead_bit,
                         uint8_t *d_out, size_t out_cap, uint64_t *d_out_bits, int16_t *d_mvecs, void *stream);
+/* GOP shard of a longer clip (multi-GPU): the next ie_encode_video_dev calls on this session announce
+ * `total_frames` in the header (0 = the frames of the call) and write the header only if write_header != 0 (the shard that
+ * holds frame 0).  Shards start on GOP boundaries, so they are independent; their streams concatenate bit-contiguously
+ * (all-gather of the bit totals + ie_stream_shift_dev, as for image shards). */
+int ie_session_set_video_shard(ie_session *s, uint32_t total_frames, int write_header);
 int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, uint64_t start_bit, int motioncompensation,
                         uint8_t *d_yuv_out, size_t yuv_cap, uint32_t *width, uint32_t *height, uint32_t *frames,
                         void *stream);

@@ -134,6 +134,39 @@ def test_sharded_huffman_stage_matches_single_stream(gpu, oracle_mod):
         assert got == want, f"{matrix} x{world}: sharded Huffman stream differs ({len(got)} vs {len(want)} bytes, reverted={reverted})"
 
 
+def test_gop_shards_stitch_to_single_video_stream(gpu, oracle_mod):
+    """BASELINE config 5 sharding on one GPU: whole GOPs per emulated rank, header (with the clip's frame count) on rank 0,
+    stitched bit-contiguously into the oracle's stream."""
+    import torch
+    from imageencoder_b200.parallel import ShardedVideoEncoder, merge_shard_into, place_shards, total_bytes
+    from imageencoder_b200.synth import synth_video
+    W, H, F, gop, mer = 64, 48, 14, 4, 8
+    q = oracle_mod.read_matrix(INPUTS / "matrix.txt")
+    yuv = synth_video(W, H, F, 4000)
+    fsz = W * H * 3 // 2
+    want = oracle_mod.video_encode(yuv, W, H, q, True, gop, mer, False)
+    for world in (1, 2, 3):
+        encs, bits = [], []
+        for r in range(world):
+            e = ShardedVideoEncoder(W, H, F, gop, world, r)
+            d = torch.from_numpy(yuv[e.f0 * fsz: e.f1 * fsz].copy()).cuda()
+            from imageencoder_b200 import device
+            device.encode_video_dev(e.sess, d, W, H, q, True, gop, mer, e.d_local, e.d_bits, lead_bit=True)
+            torch.cuda.synchronize()
+            encs.append(e)
+            bits.append(int(e.d_bits.item()))
+        pl = place_shards(bits)
+        stream = bytearray()
+        for r, e in enumerate(encs):
+            e.d_params[0] = bits[r]
+            e.d_params[1] = pl[r].global_bit
+            device.stream_shift_dev(e.d_local, e.d_params, e.d_aligned)
+            torch.cuda.synchronize()
+            merge_shard_into(stream, e.d_aligned[: pl[r].nbytes].cpu().numpy().tobytes(), pl[r])
+        got = bytes(stream[: total_bytes(pl)])
+        assert got == want, f"x{world}: stitched video stream differs ({len(got)} vs {len(want)} bytes)"
+
+
 def test_batch_entry_point(gpu, oracle_mod):
     from imageencoder_b200._lib import check, lib
     from imageencoder_b200.synth import synth_image
