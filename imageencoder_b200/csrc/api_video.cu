@@ -75,19 +75,37 @@ __global__ void __launch_bounds__(256) me_search_kernel(MEParams p) {
         // the 9 candidates of a level are independent: all their loads are issued first, the 9 SAD partial sums are
         // reduced two to a register (a MacroBlock's SAD is <= 256 * 255 < 2^16), and only the selection runs in the
         // reference's order (Block.cpp:289-317)
+        // candidate coordinates come from three x and three y values (offset -step, 0, +step): clamp each once
+        int cx3[3], cy3[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            cx3[j] = clampi((int)(short)(best_x + (j - 1) * step + mbx), 0, p.W - kMB);
+            cy3[j] = clampi((int)(short)(best_y + (j - 1) * step + mby), 0, p.H - kMB);
+        }
+        // compile-time candidate order (MER_SIGNS, algo.cpp:90-100): index into the three values
+        constexpr int kSX[9] = {1, 2, 2, 1, 0, 0, 0, 1, 2}, kSY[9] = {1, 1, 2, 2, 2, 1, 0, 0, 0};
         int cpx[9], cpy[9];
         unsigned w0[9], w1[9], w2[9], shq[9];
+        if (staged) {
+            int xw[3], rb[3];
+            unsigned xs[3];
 #pragma unroll
-        for (int q = 0; q < 9; q++) {
-            const int ox = best_x + c_mer_sx[q] * step, oy = best_y + c_mer_sy[q] * step;
-            cpx[q] = clampi((int)(short)(ox + mbx), 0, p.W - kMB);
-            cpy[q] = clampi((int)(short)(oy + mby), 0, p.H - kMB);
-            if (staged) {
-                const int bx = cpx[q] - wxa + half * 8;                         // byte offset inside the window row
-                const unsigned *wp = win + (cpy[q] - wy0 + row) * kWinWords + (bx >> 2);
-                shq[q] = (unsigned)(bx & 3) * 8;
-                w0[q] = wp[0]; w1[q] = wp[1]; w2[q] = shq[q] ? wp[2] : 0u;
-            } else {
+            for (int j = 0; j < 3; j++) {
+                const int bx = cx3[j] - wxa + half * 8;                         // byte offset inside the window row
+                xw[j] = bx >> 2; xs[j] = (unsigned)(bx & 3) * 8;
+                rb[j] = (cy3[j] - wy0 + row) * kWinWords;
+            }
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                cpx[q] = cx3[kSX[q]]; cpy[q] = cy3[kSY[q]];
+                const unsigned *wp = win + rb[kSY[q]] + xw[kSX[q]];
+                shq[q] = xs[kSX[q]];
+                w0[q] = wp[0]; w1[q] = wp[1]; w2[q] = wp[2];                    // word 2 is inside the window row (<= 12)
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                cpx[q] = cx3[kSX[q]]; cpy[q] = cy3[kSY[q]];
                 const uint8_t *rp = p.ref + (size_t)(cpy[q] + row) * p.W + cpx[q] + half * 8;
                 const uintptr_t a = (uintptr_t)rp;
                 const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
