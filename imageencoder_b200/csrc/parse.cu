@@ -47,7 +47,9 @@ struct ParseParams {
     unsigned long long *cursor_out;         // device, may be NULL: receives the bit after the last block
     int *err;
     // speculative path
-    uint2 *spec_exit;                       // [ngroups] (exit offset | kDead, blocks started in the group)
+    unsigned nspec;                         // groups of the speculative grid
+    uint2 *spec_entry;                      // [nspec] (entry offset | kDead, -)
+    uint2 *spec_exit;                       // [nspec] (exit offset | kDead, blocks started in the group)
     unsigned *spec_flags;                   // [0] CTA ticket of parse_spec_check, [1] spec_ok, [2] unused, [3] first inconsistent group
     unsigned *walk_base;                    // [nwalk] block count per walk CTA, then (in place) its exclusive scan
 };
@@ -178,7 +180,6 @@ __global__ void __launch_bounds__(64) parse_down_super(const ParseParams p) {
 // ---------------------------------------------------------------------------------------------------------
 // lead-in before a group's first bit (measured on 8x8 streams: 4096 bits leave 3 % of the groups unsynchronised, 8192 none)
 constexpr int kSpecRounds = 3;            // repair rounds inside a CTA
-constexpr int kWalkGroups = 64;           // groups (= threads) per CTA of the staged kernels
 
 // One step of a walk on the staged copy, `rel` < lim relative to the view's base.  Returns the bits consumed and the number
 // of blocks they hold: an all-zero block is 4 zero bits (bit_len 0, no length/values), so a run of zero nibbles is a run of
@@ -226,32 +227,39 @@ __device__ __forceinline__ uint2 walk_group(const ParseParams &p, unsigned long 
     }
 }
 
-constexpr unsigned kStageWords = (kWalkGroups + 1) * (kGroupBits / 32) + 16;      // groups + lead-in + window/alignment slack
+// Speculative grid: GB bits per group (one thread), TH groups per CTA, lead-in LEAD bits.  8x8 streams: 8192-bit groups,
+// 64 per CTA, lead-in 8192 (4096 leaves 3 % of the groups unsynchronised).  4x4 streams (blocks <= 276 bits, ~50 typical):
+// 2048-bit groups, 256 per CTA, lead-in 4096 -- a thread's serial chain is what the kernels' time is made of.
+template <int GB, int TH> struct SpecCfg {
+    static constexpr unsigned kLead = (GB == 8192) ? 8192u : 4096u;
+    static constexpr unsigned kStageWords = (TH * GB + kLead) / 32 + 16;             // groups + lead-in + window/alignment slack
+};
 
-// One CTA = kWalkGroups consecutive groups, one thread each, on a staged copy of their bits.  After the walks the CTA checks
+// One CTA = TH consecutive groups, one thread each, on a staged copy of their bits.  After the walks the CTA checks
 // its own neighbours and re-walks the groups whose entry disagrees with their predecessor's exit (kSpecRounds rounds);
 // the first group of every CTA is checked against the previous CTA by parse_spec_boundary.
-__global__ void __launch_bounds__(kWalkGroups) parse_spec_walk(const ParseParams p) {
+template <int GB, int TH>
+__global__ void __launch_bounds__(TH) parse_spec_walk(const ParseParams p) {
     extern __shared__ __align__(16) unsigned s_stage[];
-    __shared__ unsigned s_entry[kWalkGroups], s_exit[kWalkGroups];
-    const unsigned g = blockIdx.x * kWalkGroups + threadIdx.x;
+    __shared__ unsigned s_entry[TH], s_exit[TH];
+    const unsigned g = blockIdx.x * TH + threadIdx.x;
     if (g == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; p.spec_flags[2] = 0; p.spec_flags[3] = 0xFFFFFFFFu; }
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
-    const unsigned lead = (p.NN == 64) ? 8192u : 4096u;
-    const unsigned long long c_start = B0 + (unsigned long long)blockIdx.x * kWalkGroups * kGroupBits;
+    constexpr unsigned lead = SpecCfg<GB, TH>::kLead;
+    const unsigned long long c_start = B0 + (unsigned long long)blockIdx.x * TH * GB;
     const unsigned long long c_first = (c_start < B0 + lead) ? B0 : c_start - lead;
-    const unsigned long long c_end = min(total, c_start + (unsigned long long)kWalkGroups * kGroupBits);
+    const unsigned long long c_end = min(total, c_start + (unsigned long long)TH * GB);
     if (c_first >= total) {                                 // uniform: nothing of the stream in this CTA's range
-        if (g < p.ngroups) { p.group_entry[g] = make_uint2(kDead, 0u); p.spec_exit[g] = make_uint2(kDead, 0u); }
+        if (g < p.nspec) { p.spec_entry[g] = make_uint2(kDead, 0u); p.spec_exit[g] = make_uint2(kDead, 0u); }
         return;
     }
-    const StagedStream st = stage_stream(s_stage, kStageWords, p.enc, total, c_first, c_end);
-    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits;
-    const unsigned g_rel = (unsigned)(g_start - st.base), g_end_rel = g_rel + kGroupBits;     // CTA-local: fits 32 bits
+    const StagedStream st = stage_stream(s_stage, SpecCfg<GB, TH>::kStageWords, p.enc, total, c_first, c_end);
+    const unsigned long long g_start = B0 + (unsigned long long)g * GB;
+    const unsigned g_rel = (unsigned)(g_start - st.base), g_end_rel = g_rel + GB;     // CTA-local: fits 32 bits
     unsigned entry;
     uint2 ex = make_uint2(kDead, 0u);
-    if (g >= p.ngroups || g_start >= total) { entry = kDead; }
+    if (g >= p.nspec || g_start >= total) { entry = kDead; }
     else {
         unsigned rel = (g == 0 || g_start < B0 + lead) ? (unsigned)(B0 - st.base) : g_rel - lead;
         const unsigned lim = min(g_rel, st.total_rel);
@@ -272,57 +280,59 @@ __global__ void __launch_bounds__(kWalkGroups) parse_spec_walk(const ParseParams
         const int t = (int)threadIdx.x;
         bool redo = false;
         unsigned want = 0;
-        if (t >= 1 && g < p.ngroups && (t < 2 || s_exit[t - 2] == s_entry[t - 1])) {
+        if (t >= 1 && g < p.nspec && (t < 2 || s_exit[t - 2] == s_entry[t - 1])) {
             want = s_exit[t - 1];
             redo = (want != s_entry[t]);
         }
         if (!__syncthreads_or(redo)) break;
         if (redo) {
             entry = want;
-            ex = (want == kDead || want >= (unsigned)kGroupBits) ? make_uint2(kDead, 0u)
+            ex = (want == kDead || want >= (unsigned)GB) ? make_uint2(kDead, 0u)
                                                                : walk_group_staged(st, p.NN, p.use_rle, g_rel + want, g_end_rel);
         }
         __syncthreads();
         if (redo) { s_entry[t] = entry; s_exit[t] = ex.x; }
         __syncthreads();
     }
-    if (g < p.ngroups) { p.group_entry[g] = make_uint2(entry, 0u); p.spec_exit[g] = ex; }
+    if (g < p.nspec) { p.spec_entry[g] = make_uint2(entry, 0u); p.spec_exit[g] = ex; }
 }
 
 // CTA seams: thread k checks the first group of CTA k against the last group of CTA k-1 and, on a mismatch, re-walks
 // groups (on global memory: rare) until the chain agrees again or its CTA ends.  What it cannot settle is caught by
 // parse_spec_finish (-> exact kernels).
-__global__ void __launch_bounds__(64) parse_spec_boundary(const ParseParams p) {
+template <int GB, int TH>
+__global__ void __launch_bounds__(TH) parse_spec_boundary(const ParseParams p) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned g = k * kWalkGroups;
-    if (k == 0 || g >= p.ngroups) return;
+    unsigned g = k * TH;
+    if (k == 0 || g >= p.nspec) return;
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
     unsigned want = p.spec_exit[g - 1].x;
-    for (unsigned n = 0; n < (unsigned)kWalkGroups && g < p.ngroups; n++, g++) {
-        if (p.group_entry[g].x == want) break;
-        const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
-        const uint2 ex = (want == kDead || want >= (unsigned)kGroupBits) ? make_uint2(kDead, 0u)
+    for (unsigned n = 0; n < (unsigned)TH && g < p.nspec; n++, g++) {
+        if (p.spec_entry[g].x == want) break;
+        const unsigned long long g_start = B0 + (unsigned long long)g * GB, g_end = g_start + GB;
+        const uint2 ex = (want == kDead || want >= (unsigned)GB) ? make_uint2(kDead, 0u)
                                                                        : walk_group(p, total, g_start + want, g_end);
-        p.group_entry[g] = make_uint2(want, 0u);
+        p.spec_entry[g] = make_uint2(want, 0u);
         p.spec_exit[g] = ex;
         want = ex.x;
     }
 }
 
 // Final exact verification + block counts.  One thread per group: the seam in front of it must agree (first disagreeing
-// group -> spec_flags[3]); every CTA adds up the blocks of its kWalkGroups groups.  The last CTA to finish (ticket) turns
+// group -> spec_flags[3]); every CTA adds up the blocks of its TH groups.  The last CTA to finish (ticket) turns
 // the per-CTA counts into their exclusive scan and decides spec_ok.  Only the groups that hold the stream's nblocks blocks
 // have to be consistent: behind the last block the chain runs into whatever follows (pad bits, the next frame's motion
 // vectors), where the speculative walks may legitimately disagree.
-__global__ void __launch_bounds__(kWalkGroups) parse_spec_check(const ParseParams p) {
-    __shared__ unsigned s_part[kWalkGroups];
+template <int GB, int TH>
+__global__ void __launch_bounds__(TH) parse_spec_check(const ParseParams p) {
+    __shared__ unsigned s_part[TH];
     __shared__ unsigned s_last;
-    const unsigned g = blockIdx.x * kWalkGroups + threadIdx.x;
+    const unsigned g = blockIdx.x * TH + threadIdx.x;
     unsigned cnt = 0;
-    if (g < p.ngroups) {
+    if (g < p.nspec) {
         cnt = p.spec_exit[g].y;
-        if (g > 0 && p.spec_exit[g - 1].x != p.group_entry[g].x) atomicMin(&p.spec_flags[3], g);
+        if (g > 0 && p.spec_exit[g - 1].x != p.spec_entry[g].x) atomicMin(&p.spec_flags[3], g);
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
@@ -330,7 +340,7 @@ __global__ void __launch_bounds__(kWalkGroups) parse_spec_check(const ParseParam
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned sum = 0;
-        for (int w = 0; w < kWalkGroups / 32; w++) sum += s_part[w];
+        for (int w = 0; w < TH / 32; w++) sum += s_part[w];
         p.walk_base[blockIdx.x] = sum;
         __threadfence();
         s_last = (atomicAdd(&p.spec_flags[0], 1u) == gridDim.x - 1) ? 1u : 0u;
@@ -338,9 +348,9 @@ __global__ void __launch_bounds__(kWalkGroups) parse_spec_check(const ParseParam
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // exclusive scan of walk_base[0 .. gridDim.x), kWalkGroups values at a time (read past L1: other CTAs wrote them)
+    // exclusive scan of walk_base[0 .. gridDim.x), TH values at a time (read past L1: other CTAs wrote them)
     unsigned run = 0;
-    for (unsigned c0 = 0; c0 < gridDim.x; c0 += kWalkGroups) {
+    for (unsigned c0 = 0; c0 < gridDim.x; c0 += TH) {
         const unsigned i = c0 + threadIdx.x;
         const unsigned v = (i < gridDim.x) ? __ldcg(p.walk_base + i) : 0u;
         unsigned inc = v;
@@ -352,54 +362,52 @@ __global__ void __launch_bounds__(kWalkGroups) parse_spec_check(const ParseParam
         unsigned before = run;
         for (unsigned w = 0; w < (threadIdx.x >> 5); w++) before += s_part[w];
         if (i < gridDim.x) p.walk_base[i] = before + inc - v;
-        for (int w = 0; w < kWalkGroups / 32; w++) run += s_part[w];
+        for (int w = 0; w < TH / 32; w++) run += s_part[w];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned firstbad = __ldcg(&p.spec_flags[3]);
         unsigned ok = 1;
-        if (firstbad < p.ngroups) {
+        if (firstbad < p.nspec) {
             // blocks that start before the first unverified group; if that does not cover the stream's blocks, give up
             __threadfence();
-            unsigned base = p.walk_base[firstbad / kWalkGroups];
-            for (unsigned gg = firstbad / kWalkGroups * kWalkGroups; gg < firstbad; gg++) base += p.spec_exit[gg].y;
+            unsigned base = p.walk_base[firstbad / TH];
+            for (unsigned gg = firstbad / TH * TH; gg < firstbad; gg++) base += p.spec_exit[gg].y;
             if (base < p.nblocks) ok = 0;
         }
         p.spec_flags[1] = ok;
     }
 }
 
-// One CTA = kWalkGroups groups on a staged copy: every thread walks its group's TRUE chain and writes block_off[].
-__global__ void __launch_bounds__(kWalkGroups) parse_emit_offsets(const ParseParams p) {
+// block_off[] from the verified speculative walk.  One CTA = TH groups on a staged copy: every thread walks its group's TRUE
+// chain from its entry; the first block index of a group = scanned per-CTA counts + the counts of the CTA's earlier groups.
+template <int GB, int TH>
+__global__ void __launch_bounds__(TH) parse_spec_emit(const ParseParams p) {
     extern __shared__ __align__(16) unsigned s_stage[];
-    const unsigned g = blockIdx.x * kWalkGroups + threadIdx.x;
+    __shared__ unsigned s_wsum[TH / 32];
+    if (!p.spec_flags[1]) return;                            // uniform: the exact kernels produce the offsets
+    const unsigned g = blockIdx.x * TH + threadIdx.x;
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
-    const unsigned long long c_start = B0 + (unsigned long long)blockIdx.x * kWalkGroups * kGroupBits;
+    const unsigned long long c_start = B0 + (unsigned long long)blockIdx.x * TH * GB;
     if (c_start >= total) return;                            // uniform
-    // a block that starts inside the CTA's last group may end (and the next header be read) up to E bits behind it; the
-    // walk itself only reads headers of blocks that START before the group's end
-    const StagedStream st = stage_stream(s_stage, kStageWords, p.enc, total, c_start, min(total, c_start + (unsigned long long)kWalkGroups * kGroupBits));
-    // entry offset and first block index of the group: from the exact kernels (group_entry), or, when the speculative
-    // parse verified, from the walk (entry) and the scanned block counts (walk_base + the counts of the CTA's earlier groups)
-    __shared__ unsigned s_wsum;
-    uint2 ge = (g < p.ngroups) ? p.group_entry[g] : make_uint2(kDead, 0u);
-    if (p.spec_flags[1]) {                                   // uniform
-        const unsigned cnt = (g < p.ngroups) ? p.spec_exit[g].y : 0u;
-        unsigned inc = cnt;
+    const StagedStream st = stage_stream(s_stage, SpecCfg<GB, TH>::kStageWords, p.enc, total, c_start,
+                                         min(total, c_start + (unsigned long long)TH * GB));
+    const unsigned cnt = (g < p.nspec) ? p.spec_exit[g].y : 0u;
+    unsigned inc = cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)(threadIdx.x & 31) >= d) inc += o; }
-        if (threadIdx.x == 31) s_wsum = inc;
-        __syncthreads();
-        static_assert(kWalkGroups == 64, "two warps");
-        ge.y = p.walk_base[blockIdx.x] + inc - cnt + ((threadIdx.x >= 32) ? s_wsum : 0u);
-        if (g >= p.spec_flags[3]) ge.x = kDead;              // unverified tail: holds no block of this stream
-    }
-    if (g >= p.ngroups || ge.x == kDead) return;
-    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits;
-    const unsigned g_end_rel = (unsigned)(g_start - st.base) + kGroupBits;
-    unsigned rel = (unsigned)(g_start - st.base) + ge.x;
-    unsigned idx = ge.y;
+    for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)(threadIdx.x & 31) >= d) inc += o; }
+    if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    unsigned idx = p.walk_base[blockIdx.x] + inc - cnt;
+    for (unsigned w = 0; w < (threadIdx.x >> 5); w++) idx += s_wsum[w];
+    if (g >= p.nspec || g >= p.spec_flags[3]) return;        // unverified tail: holds no block of this stream
+    const unsigned entry = p.spec_entry[g].x;
+    if (entry == kDead) return;
+    const unsigned first_idx = idx;
+    const unsigned long long g_start = B0 + (unsigned long long)g * GB;
+    const unsigned g_end_rel = (unsigned)(g_start - st.base) + GB;
+    unsigned rel = (unsigned)(g_start - st.base) + entry;
     const unsigned lim = min(g_end_rel, st.total_rel);
     while (rel < lim && idx < p.nblocks) {
         unsigned nb;
@@ -411,6 +419,33 @@ __global__ void __launch_bounds__(kWalkGroups) parse_emit_offsets(const ParsePar
     const unsigned long long pos = st.base + rel;
     if (idx <= p.nblocks && pos >= total) {
         // the chain reached the end of the stream in this group: every remaining block starts (and ends) at `total`
+        for (; idx < p.nblocks; idx++) p.block_off[idx] = total;
+        p.block_off[p.nblocks] = total;
+        if (p.cursor_out) *p.cursor_out = total;
+    } else if (idx == p.nblocks && first_idx < p.nblocks) {
+        p.block_off[idx] = pos;                 // this thread emitted the last block
+        if (p.cursor_out) *p.cursor_out = pos;
+    }
+}
+
+// block_off[] from the exact kernels' group entries (only when the speculative parse did not verify)
+__global__ void __launch_bounds__(64) parse_emit_offsets(const ParseParams p) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.ngroups || p.spec_flags[1]) return;
+    const uint2 ge = p.group_entry[g];
+    if (ge.x == kDead) return;
+    const unsigned long long total = *p.enc_bits;
+    const unsigned long long B0 = *p.start + p.skip_bits;
+    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
+    unsigned long long pos = g_start + ge.x;
+    unsigned idx = ge.y;
+    while (pos < g_end && pos < total && idx < p.nblocks) {
+        const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
+        if (bits == kBadBlock) { if (p.err) atomicExch(p.err, IE_EFORMAT); pos = total; break; }   // malformed stream
+        p.block_off[idx++] = pos;
+        pos = min(pos + bits, total);
+    }
+    if (idx <= p.nblocks && pos >= total) {
         for (; idx < p.nblocks; idx++) p.block_off[idx] = total;
         p.block_off[p.nblocks] = total;
         if (p.cursor_out) *p.cursor_out = total;
@@ -426,10 +461,27 @@ static void parse_sizes(size_t span_bits, int N, unsigned &E, unsigned &ngroups,
     nsuper = (ngroups + kSuper - 1) / kSuper;
 }
 
+static unsigned spec_groups(size_t span_bits, int N) { const size_t gb = (N == 8) ? 8192 : 2048; return (unsigned)((span_bits + gb - 1) / gb + 1); }
+
 size_t parse_scratch_bytes(size_t enc_bytes, int N) {
     unsigned E, ng, ns;
     parse_sizes(enc_bytes * 8, N, E, ng, ns);
-    return ((size_t)ng * E + (size_t)ns * E + ns + ng + ng + 8) * sizeof(uint2) + 256 + ((size_t)ng / kWalkGroups + 8) * sizeof(unsigned);
+    const size_t nspec = spec_groups(enc_bytes * 8, N);
+    return ((size_t)ng * E + (size_t)ns * E + ns + ng + 8) * sizeof(uint2) + nspec * 2 * sizeof(uint2) + (nspec / 64 + 16) * sizeof(unsigned) + 256;
+}
+
+template <int GB, int TH>
+static int launch_spec(const ParseParams &p, cudaStream_t stream) {
+    const unsigned nwalk = (p.nspec + TH - 1) / TH;
+    const size_t stage_bytes = (size_t)SpecCfg<GB, TH>::kStageWords * sizeof(unsigned);
+    IE_CUDA(cudaFuncSetAttribute(parse_spec_walk<GB, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    IE_CUDA(cudaFuncSetAttribute(parse_spec_emit<GB, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    parse_spec_walk<GB, TH><<<nwalk, TH, stage_bytes, stream>>>(p);
+    parse_spec_boundary<GB, TH><<<(nwalk + 63) / 64, 64, 0, stream>>>(p);
+    parse_spec_check<GB, TH><<<nwalk, TH, 0, stream>>>(p);
+    parse_spec_emit<GB, TH><<<nwalk, TH, stage_bytes, stream>>>(p);
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
 }
 
 // Fills d.block_off[0..nblocks] for one stream (and advances d.cursor when the last block lies inside the span).
@@ -450,7 +502,9 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     p.super_table = s; s += (size_t)p.nsuper * E;
     p.super_entry = s; s += p.nsuper;
     p.group_entry = s; s += p.ngroups;
-    p.spec_exit = s; s += p.ngroups;
+    p.nspec = spec_groups(span_bits, d.N);
+    p.spec_entry = s; s += p.nspec;
+    p.spec_exit = s; s += p.nspec;
     p.spec_flags = reinterpret_cast<unsigned *>(s);
     p.walk_base = p.spec_flags + 8;
     p.block_off = d.block_off;
@@ -460,14 +514,9 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     static const bool dbg = getenv("IE_DEBUG_SYNC") != nullptr;
 #define IE_DBG_STEP(name) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(stream); if (e_ != cudaSuccess) { fprintf(stderr, "[ie] %s failed: %s\n", name, cudaGetErrorString(e_)); return cuda_fail(e_, name, __FILE__, __LINE__); } } } while (0)
     IE_DBG_STEP("before parse");
-    const unsigned nwalk = (p.ngroups + kWalkGroups - 1) / kWalkGroups;
-    const size_t stage_bytes = (size_t)kStageWords * sizeof(unsigned);
     if ((uintptr_t)d.enc % 16) { set_error("encoded stream must be 16-byte aligned on the device"); return IE_EINVAL; }
-    IE_CUDA(cudaFuncSetAttribute(parse_spec_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
-    IE_CUDA(cudaFuncSetAttribute(parse_emit_offsets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
-    parse_spec_walk<<<nwalk, kWalkGroups, stage_bytes, stream>>>(p);
-    parse_spec_boundary<<<(nwalk + 63) / 64, 64, 0, stream>>>(p);
-    parse_spec_check<<<nwalk, kWalkGroups, 0, stream>>>(p);
+    if (d.N == 8) IE_TRY((launch_spec<8192, 64>(p, stream)));
+    else IE_TRY((launch_spec<2048, 256>(p, stream)));
     IE_DBG_STEP("parse_spec");
     parse_group_tables<<<std::min(p.ngroups, 148u * 8u), 64, smem, stream>>>(p);
     IE_DBG_STEP("parse_group_tables");
@@ -477,10 +526,10 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     IE_DBG_STEP("parse_top_walk");
     parse_down_super<<<(p.nsuper + 63) / 64, 64, 0, stream>>>(p);
     IE_DBG_STEP("parse_down_super");
-    parse_emit_offsets<<<nwalk, kWalkGroups, stage_bytes, stream>>>(p);
+    parse_emit_offsets<<<(p.ngroups + 63) / 64, 64, 0, stream>>>(p);
     IE_DBG_STEP("parse_emit_offsets");
 #undef IE_DBG_STEP
-    count_launch(8);
+    count_launch(9);
     IE_CUDA(cudaGetLastError());
     return IE_OK;
 }
