@@ -169,7 +169,10 @@ __global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodePar
     constexpr int STRIDE = NN + 2;
     // the bits of the CTA's 128 blocks are one contiguous span of the stream (<= 128 * (4 + 16 + 16 NN) bits): staged with
     // 16-byte cp.async, then every lane reads its block's fields from shared memory (no bounds or end-of-stream tests)
-    constexpr unsigned kStage = (128u * (4 + 16 + 16 * NN) + 31) / 32 + 12;
+    // (+ one maximal block: in a truncated stream the last block's fields run past the end of the stream, where they must
+    // read as zero bits, BitStream.cpp:17-20, not as whatever the shared memory held)
+    constexpr unsigned kMaxBlockBits = 4 + 16 + 16 * NN;
+    constexpr unsigned kStage = (129u * kMaxBlockBits + 31) / 32 + 12;
     __shared__ short s_coef[128 * STRIDE];
     __shared__ __align__(16) unsigned s_bits[kStage];
     const unsigned img = blockIdx.y;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodePar
     const unsigned long long total = p.enc_bits[img];
     const unsigned long long *off = p.block_off + (size_t)img * (p.nblocks + 1);
     const BlockTables *tab = p.tab;
-    const StagedStream st = stage_stream(s_bits, kStage, s, total, off[first], off[min(first + 128u, p.nblocks)]);
+    const StagedStream st = stage_stream(s_bits, kStage, s, total, off[first], off[min(first + 128u, p.nblocks)] + kMaxBlockBits);
     if (gb >= p.nblocks) return;
 
     // ---- fields (Block.cpp:441-472) -------------------------------------------------------------------------

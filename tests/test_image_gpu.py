@@ -99,6 +99,35 @@ def test_striped_host_pipeline_matches_oracle(gpu, oracle_mod, N, W, H, huffman)
         assert np.array_equal(gpu.decode_image(got, N), np.asarray(oracle_mod.image_decode(want, N)[0]))
 
 
+@pytest.mark.parametrize("N,W,H", [(8, 32760, 8), (8, 8, 32760), (4, 32764, 4), (4, 4, 32764), (8, 8, 8), (4, 4, 4), (8, 1000, 24)])
+def test_extreme_shapes(gpu, oracle_mod, N, W, H):
+    """largest widths/heights the 15-bit header fields hold (ImageBase.hpp:76), single-block images, tiles straddling rows"""
+    rng = np.random.default_rng(W * 7 + H)
+    img = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    q = _mat(oracle_mod, "matrix8_1.txt" if N == 8 else "matrix.txt")
+    for huffman in (False, True):
+        got = gpu.encode_image(img, W, H, q, True, huffman)
+        want = oracle_mod.image_encode(img, W, H, N, q, True, huffman)
+        assert got == want, f"huffman={huffman}"
+    dec = gpu.decode_image(oracle_mod.image_encode(img, W, H, N, q, True, False), N)
+    assert np.array_equal(dec, np.asarray(oracle_mod.image_decode(oracle_mod.image_encode(img, W, H, N, q, True, False), N)[0]))
+
+
+@pytest.mark.parametrize("N", [4, 8])
+@pytest.mark.parametrize("keep", [0.97, 0.5, 0.1])
+def test_truncated_stream_decodes_like_the_reference(gpu, oracle_mod, N, keep):
+    """reads past the end of the stream return 0 bits (BitStream.cpp:17-20): a truncated file still decodes, identically"""
+    from imageencoder_b200.synth import synth_image
+    W, H = 256, 192
+    img = synth_image(W, H, 31)
+    q = _mat(oracle_mod, "matrix8_1.txt" if N == 8 else "matrix.txt")
+    enc = oracle_mod.image_encode(img, W, H, N, q, True, False)
+    cut = enc[: max(200, int(len(enc) * keep))]
+    want = np.asarray(oracle_mod.image_decode(cut, N)[0])
+    got = gpu.decode_image(cut, N)
+    assert np.array_equal(got, want)
+
+
 def test_errors(gpu):
     from imageencoder_b200 import IEError
     with pytest.raises(IEError):
