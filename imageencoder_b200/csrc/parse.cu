@@ -44,7 +44,8 @@ struct ParseParams {
     uint2 *super_entry;                     // [nsuper]  (entry offset | kDead, first block index)
     uint2 *group_entry;                     // [ngroups]
     unsigned long long *block_off;          // [nblocks + 1]
-    unsigned long long *cursor_out;         // device, may be NULL: receives the bit after the last block
+    unsigned long long *cursor_out;         // device, may be NULL: receives the bit after the last block (parse_commit_cursor)
+    unsigned long long *cursor_next;        // scratch: where the emit kernels leave it (cursor_out aliases `start`, which they read)
     int *err;
     // speculative path
     unsigned nspec;                         // groups of the speculative grid
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(TH) parse_spec_walk(const ParseParams p) {
     extern __shared__ __align__(16) unsigned s_stage[];
     __shared__ unsigned s_entry[TH], s_exit[TH];
     const unsigned g = blockIdx.x * TH + threadIdx.x;
-    if (g == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; p.spec_flags[2] = 0; p.spec_flags[3] = 0xFFFFFFFFu; }
+    if (g == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; p.spec_flags[2] = 0; p.spec_flags[3] = 0xFFFFFFFFu; *p.cursor_next = ~0ull; }
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
     constexpr unsigned lead = SpecCfg<GB, TH>::kLead;
@@ -389,6 +390,15 @@ __global__ void __launch_bounds__(TH) parse_spec_emit(const ParseParams p) {
     const unsigned g = blockIdx.x * TH + threadIdx.x;
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
+    if (B0 >= total) {
+        // nothing of the stream is left for this span (a truncated file): every block starts and ends at `total` and reads
+        // as zero bits (BitStream.cpp:17-20)
+        if (blockIdx.x == 0) {
+            for (unsigned i = threadIdx.x; i <= p.nblocks; i += TH) p.block_off[i] = total;
+            if (threadIdx.x == 0) *p.cursor_next = total;
+        }
+        return;
+    }
     const unsigned long long c_start = B0 + (unsigned long long)blockIdx.x * TH * GB;
     if (c_start >= total) return;                            // uniform
     const StagedStream st = stage_stream(s_stage, SpecCfg<GB, TH>::kStageWords, p.enc, total, c_start,
@@ -421,10 +431,10 @@ __global__ void __launch_bounds__(TH) parse_spec_emit(const ParseParams p) {
         // the chain reached the end of the stream in this group: every remaining block starts (and ends) at `total`
         for (; idx < p.nblocks; idx++) p.block_off[idx] = total;
         p.block_off[p.nblocks] = total;
-        if (p.cursor_out) *p.cursor_out = total;
+        *p.cursor_next = total;
     } else if (idx == p.nblocks && first_idx < p.nblocks) {
         p.block_off[idx] = pos;                 // this thread emitted the last block
-        if (p.cursor_out) *p.cursor_out = pos;
+        *p.cursor_next = pos;
     }
 }
 
@@ -448,11 +458,16 @@ __global__ void __launch_bounds__(64) parse_emit_offsets(const ParseParams p) {
     if (idx <= p.nblocks && pos >= total) {
         for (; idx < p.nblocks; idx++) p.block_off[idx] = total;
         p.block_off[p.nblocks] = total;
-        if (p.cursor_out) *p.cursor_out = total;
+        *p.cursor_next = total;
     } else if (idx == p.nblocks && ge.y < p.nblocks) {
         p.block_off[idx] = pos;                 // this thread emitted the last block
-        if (p.cursor_out) *p.cursor_out = pos;
+        *p.cursor_next = pos;
     }
+}
+
+__global__ void parse_commit_cursor(const ParseParams p) {
+    const unsigned long long next = *p.cursor_next;
+    if (next != ~0ull) *p.cursor_out = next;
 }
 
 static void parse_sizes(size_t span_bits, int N, unsigned &E, unsigned &ngroups, unsigned &nsuper) {
@@ -506,7 +521,8 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     p.spec_entry = s; s += p.nspec;
     p.spec_exit = s; s += p.nspec;
     p.spec_flags = reinterpret_cast<unsigned *>(s);
-    p.walk_base = p.spec_flags + 8;
+    p.cursor_next = reinterpret_cast<unsigned long long *>(p.spec_flags + 8);
+    p.walk_base = p.spec_flags + 12;
     p.block_off = d.block_off;
     p.cursor_out = d.cursor;
     p.err = d.err;
@@ -528,6 +544,7 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     IE_DBG_STEP("parse_down_super");
     parse_emit_offsets<<<(p.ngroups + 63) / 64, 64, 0, stream>>>(p);
     IE_DBG_STEP("parse_emit_offsets");
+    if (p.cursor_out) { parse_commit_cursor<<<1, 1, 0, stream>>>(p); count_launch(); }
 #undef IE_DBG_STEP
     count_launch(9);
     IE_CUDA(cudaGetLastError());

@@ -66,6 +66,22 @@ def test_video_scene_cut_and_saturation(gpu, oracle_mod):
     assert np.array_equal(gpu.decode_video(got, True)[0], oracle_mod.video_decode(got, True)[0])
 
 
+@pytest.mark.parametrize("keep", [0.9, 0.45])
+def test_truncated_video_decodes_like_the_reference(gpu, oracle_mod, keep):
+    """a cut file: fields past the end read as zero bits (BitStream.cpp:17-20), later frames decode from an exhausted stream"""
+    from imageencoder_b200.synth import synth_video
+    W, H, F = 96, 64, 7
+    q = oracle_mod.read_matrix(INPUTS / "matrix.txt")
+    yuv = synth_video(W, H, F, 4000)
+    enc = oracle_mod.video_encode(yuv, W, H, q, True, 3, 8, False)
+    cut = enc[: int(len(enc) * keep)]
+    for mc in (True, False):
+        want = oracle_mod.video_decode(cut, mc)[0]
+        got, w, h, f = gpu.decode_video(cut, mc)
+        assert (w, h, f) == (W, H, F)
+        assert np.array_equal(got, want), f"motioncompensation={mc}"
+
+
 def test_video_errors(gpu):
     from imageencoder_b200 import IEError
     with pytest.raises(IEError):
