@@ -128,6 +128,44 @@ def test_truncated_stream_decodes_like_the_reference(gpu, oracle_mod, N, keep):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("N", [4, 8])
+@pytest.mark.parametrize("keep,extra", [(0.8, 0), (1.0, 37)])
+def test_truncated_or_padded_huffman_file_decodes_like_the_reference(gpu, oracle_mod, N, keep, extra):
+    """Huffman-coded file cut inside the payload / followed by stray bytes: the reference decodes symbols until the input is
+    exhausted (Huffman.cpp:376-383) and then reads the blocks from whatever that produced"""
+    from imageencoder_b200.synth import synth_image
+    W, H = 256, 192
+    img = synth_image(W, H, 32)
+    q = _mat(oracle_mod, "matrix8_1.txt" if N == 8 else "matrix.txt")
+    plain = oracle_mod.image_encode_plain(img, W, H, N, q, True, lead_bit=False)[0]
+    if oracle_mod.huffman_header_overflows(plain):
+        pytest.skip("the reference cannot decode its own dictionary header here (Huffman.cpp:39-42)")
+    enc = oracle_mod.image_encode(img, W, H, N, q, True, True)
+    data = enc[: int(len(enc) * keep)] + bytes((i * 73 + 5) & 0xFF for i in range(extra))
+    want = np.asarray(oracle_mod.image_decode(data, N)[0])
+    got = gpu.decode_image(data, N)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("kind", ["zeros", "white", "mid", "stripes", "checker", "ramp"])
+def test_degenerate_images(gpu, oracle_mod, kind):
+    """constant and maximally busy images: all-zero blocks (bit_len 0), DC-only blocks, the widest AC fields, RLE on and off"""
+    W, H = 192, 160
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = {"zeros": np.zeros((H, W)), "white": np.full((H, W), 255), "mid": np.full((H, W), 128), "stripes": (xx % 2) * 255,
+           "checker": ((xx + yy) % 2) * 255, "ramp": (xx + yy) % 256}[kind].astype(np.uint8)
+    for mat in ("matrix.txt", "matrix8_1.txt"):
+        q = _mat(oracle_mod, mat)
+        N = q.shape[0]
+        for rle in (True, False):
+            for huffman in (False, True):
+                got = gpu.encode_image(img, W, H, q, rle, huffman)
+                want = oracle_mod.image_encode(img, W, H, N, q, rle, huffman)
+                assert got == want, f"{kind} {mat} rle={rle} huffman={huffman}"
+            plain = oracle_mod.image_encode(img, W, H, N, q, rle, False)
+            assert np.array_equal(gpu.decode_image(plain, N), np.asarray(oracle_mod.image_decode(plain, N)[0])), f"{kind} {mat} rle={rle}"
+
+
 def test_errors(gpu):
     from imageencoder_b200 import IEError
     with pytest.raises(IEError):

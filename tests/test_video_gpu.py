@@ -82,6 +82,24 @@ def test_truncated_video_decodes_like_the_reference(gpu, oracle_mod, keep):
         assert np.array_equal(got, want), f"motioncompensation={mc}"
 
 
+def test_static_and_flashing_clips(gpu, oracle_mod):
+    """identical frames (zero motion, residual = the -128 offset alone) and frames alternating black/white (residual +-255)"""
+    W, H, F = 64, 48, 6
+    q = oracle_mod.read_matrix(INPUTS / "matrix.txt")
+    fsz = W * H * 3 // 2
+    rng = np.random.default_rng(9)
+    base = rng.integers(0, 256, W * H).astype(np.uint8)
+    for name in ("static", "flash"):
+        yuv = np.full(F * fsz, 0x80, np.uint8)
+        for t in range(F):
+            yuv[t * fsz: t * fsz + W * H] = base if name == "static" else (255 if t % 2 else 0)
+        got = gpu.encode_video(yuv, W, H, q, True, 4, 16, False)
+        want = oracle_mod.video_encode(yuv, W, H, q, True, 4, 16, False)
+        assert got == want, name
+        dec, w, h, f = gpu.decode_video(got, True)
+        assert np.array_equal(dec, oracle_mod.video_decode(want, True)[0]), name
+
+
 def test_video_errors(gpu):
     from imageencoder_b200 import IEError
     with pytest.raises(IEError):
