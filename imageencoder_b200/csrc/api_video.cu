@@ -380,6 +380,7 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     p.mbx = W / kMB;
     p.img_stride = (size_t)gop * fsz;            // image i of a launch = the same frame index of GOP i
     p.coord_stride = (size_t)nmb * 2;
+    { float k2[kMaxNN]; make_k2(k2, quant, 4); for (int i = 0; i < 16; i++) p.k2[i] = k2[i]; }
     p.slot_bytes = encode_tile_slot_bytes(4);
     const size_t ntot = (size_t)batch * tiles;
     IE_TRY(session_reserve(&s->d_tile_scratch, &s->tile_scratch_cap, ntot * p.slot_bytes));

@@ -318,6 +318,69 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
             const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
             const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
             const int kx = copy_coord_i[2 * mb] + (int)(bxi & 3) * 4, ky = copy_coord_i[2 * mb + 1] + (int)(byi & 3) * 4;
+            if (FAST && N == 4) {
+                // fast reconstruction as in decode_blocks_fast_kernel<4, ADD>: FP32 inverse transform, and every pixel whose
+                // value lies within the block's error bound of an integer boundary is recomputed in the reference's exact
+                // order over the non-zero coefficients (transform bound: decode_image.cu)
+                float xf[NN];
+                float S = 0.f;
+                unsigned nzmask = 0;
+#pragma unroll
+                for (int uv = 0; uv < NN; uv++) {
+                    const int c = cf[kZigzagInv4[uv]];
+                    if (c != 0) nzmask |= 1u << uv;
+                    const float d = (float)c * p.k2[uv];
+                    xf[uv] = d;
+                    S += fabsf(d);
+                }
+                idct2d_fast<4>(xf);
+                const float delta = (32.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
+                const float hi_thr = (delta < 0.49f) ? 0.5f - delta : 0.f;
+                unsigned outw[4];
+                unsigned rpxw[4];                                     // the four reference pixels of each row, one per byte
+                unsigned unsure = 0;
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    unsigned fl[4];
+                    rpxw[y] = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const unsigned rp = __ldg(ref_i + (size_t)(ky + y) * p.pitch + kx + k);
+                        rpxw[y] |= rp << (8 * k);
+                        const float v = xf[y * 4 + k] + 128.f + (float)rp;
+                        const float u = fminf(fmaxf(v, 0.5f), 255.5f);
+                        const float fm = __fadd_rd(u, 8388608.0f);
+                        const float frac = u - (fm - 8388608.0f);
+                        if (fabsf(frac - 0.5f) >= hi_thr) unsure |= 1u << (y * 4 + k);
+                        fl[k] = __float_as_uint(fm);
+                    }
+                    outw[y] = __byte_perm(__byte_perm(fl[0], fl[1], 0x0040), __byte_perm(fl[2], fl[3], 0x0040), 0x5410);
+                }
+                while (unsure) {
+                    const int ij = __ffs((int)unsure) - 1;
+                    unsure &= unsure - 1;
+                    double acc = 0.0;
+                    unsigned nz = nzmask;
+                    while (nz) {
+                        const int uv = __ffs((int)nz) - 1;
+                        nz &= nz - 1;
+                        const double d = __dmul_rn((double)(int)cf[tab->izz[uv]], p.quant.m[uv]);       // Block.cpp:165-168
+                        acc = __dadd_rn(acc, __dmul_rn(__ldg(tab->inv + uv * NN + ij), d));             // algo.cpp:352-355
+                    }
+                    const int yy = ij >> 2, kk = ij & 3;
+                    unsigned rrow = 0, orow = 0;
+#pragma unroll
+                    for (int r4 = 0; r4 < 4; r4++) if (r4 == yy) { rrow = rpxw[r4]; orow = outw[r4]; }
+                    const double rpx = (double)(int)((rrow >> (8 * kk)) & 0xffu);
+                    const unsigned px = clamp_trunc_u8(__dadd_rn(rpx, __dadd_rn(acc, 128.0)));           // Frame.cpp:218-242
+                    orow = (orow & ~(0xffu << (8 * kk))) | (px << (8 * kk));
+#pragma unroll
+                    for (int r4 = 0; r4 < 4; r4++) if (r4 == yy) outw[r4] = orow;
+                }
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+                    *reinterpret_cast<unsigned *>(cur_rw_i + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N) = outw[y];
+            } else {
             double X[NN];
 #pragma unroll
             for (int i = 0; i < NN; i++) X[i] = 0.0;
@@ -341,6 +404,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
                     outw |= v << (8 * k);
                 }
                 *reinterpret_cast<unsigned *>(cur_rw_i + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N) = outw;
+            }
             }
         }
         s_w[lb] = (unsigned char)w;

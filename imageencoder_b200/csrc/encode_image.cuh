@@ -41,6 +41,7 @@ struct EncodeParams {
     uint8_t *cur_rw;                  // == src, writable
     unsigned mbx;                     // MacroBlocks per row
     size_t coord_stride;              // shorts between the coordinate arrays of consecutive images (GOP batch)
+    float k2[16];                     // P-frame reconstruction, fast path: C(u)C(v) * Q[u][v] (4x4)
 };
 
 unsigned encode_tile_blocks(int N);

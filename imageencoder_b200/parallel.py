@@ -149,11 +149,12 @@ class ShardedImageEncoder:
         from ._lib import lib
 
         self.width, self.shard_height, self.block = width, shard_height, block
-        self.sess = device.Session(device.Session.IMAGE_ENCODE, width, shard_height, block)
-        if full_height:
+        # more ranks than block rows leave some ranks without rows: they take part in the all-gather with 0 bits
+        self.sess = device.Session(device.Session.IMAGE_ENCODE, width, shard_height, block) if shard_height else None
+        if full_height and self.sess is not None:
             from ._lib import check
             check(lib().ie_session_set_header_height(self.sess.h, full_height))
-        self.cap = int(lib().ie_max_encoded_bytes(width, shard_height, block, 1))
+        self.cap = int(lib().ie_max_encoded_bytes(width, max(shard_height, block), block, 1))
         self.d_aligned = torch.empty(self.cap + 32, dtype=torch.uint8, device="cuda")
         self.d_total = torch.zeros(1, dtype=torch.int64, device="cuda")     # this shard's bits (header included on rank 0)
         self.d_bits = torch.zeros(1, dtype=torch.int64, device="cuda")      # (first % 128) + this shard's bits
@@ -168,8 +169,13 @@ class ShardedImageEncoder:
 
         from . import device
 
-        device.encode_image_begin_dev(self.sess, d_raw, quant, rle, self.d_total, lead_bit=lead_bit, write_header=(rank == 0),
-                                      width=self.width, height=self.shard_height)
+        if self.sess is None:
+            if rank == 0:
+                raise ValueError("rank 0 writes the header and needs at least one block row")
+            self.d_total.zero_()
+        else:
+            device.encode_image_begin_dev(self.sess, d_raw, quant, rle, self.d_total, lead_bit=lead_bit, write_header=(rank == 0),
+                                          width=self.width, height=self.shard_height)
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         if world == 1:
             totals = self.d_total
@@ -178,7 +184,11 @@ class ShardedImageEncoder:
                 self.d_totals = torch.empty(world, dtype=torch.int64, device="cuda")
             totals = self.d_totals
             dist.all_gather_into_tensor(totals, self.d_total, group=group)
-        device.encode_image_end_dev(self.sess, totals, rank, self.d_aligned, self.d_bits, self.d_first)
+        if self.sess is None:
+            self.d_bits.zero_()
+            self.d_first.copy_(totals[:rank].sum().reshape(1))
+        else:
+            device.encode_image_end_dev(self.sess, totals, rank, self.d_aligned, self.d_bits, self.d_first)
         return totals
 
 
