@@ -300,7 +300,13 @@ int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size
 
 // ---- cached sessions for the host-buffer entry points -----------------------------------------------------------
 static std::mutex g_smu;
-static std::map<std::tuple<int, int, uint32_t, uint32_t, uint32_t, uint32_t>, ie_session *> g_sessions;
+// A session owns scratch sized for its shape (tile scratch, staging buffers: hundreds of MB for large images), so the cache
+// is bounded: the least recently used session is destroyed when a new shape arrives (the host entry points are
+// synchronous, so a cached session is idle between calls).
+struct CachedSession { ie_session *s; unsigned long long last_use; };
+static std::map<std::tuple<int, int, uint32_t, uint32_t, uint32_t, uint32_t>, CachedSession> g_sessions;
+static unsigned long long g_session_clock = 0;
+constexpr size_t kMaxCachedSessions = 8;
 
 int cached_session(ie_session **out, int kind, uint32_t W, uint32_t H, uint32_t N, uint32_t frames) {
     int dev = 0;
@@ -308,17 +314,24 @@ int cached_session(ie_session **out, int kind, uint32_t W, uint32_t H, uint32_t 
     std::lock_guard<std::mutex> lk(g_smu);
     auto key = std::make_tuple(dev, kind, W, H, N, frames);
     auto it = g_sessions.find(key);
-    if (it != g_sessions.end()) { *out = it->second; return IE_OK; }
+    if (it != g_sessions.end()) { it->second.last_use = ++g_session_clock; *out = it->second.s; return IE_OK; }
+    if (g_sessions.size() >= kMaxCachedSessions) {
+        auto lru = g_sessions.begin();
+        for (auto jt = g_sessions.begin(); jt != g_sessions.end(); ++jt)
+            if (jt->second.last_use < lru->second.last_use) lru = jt;
+        ie_session_destroy(lru->second.s);
+        g_sessions.erase(lru);
+    }
     ie_session *s = nullptr;
     IE_TRY(ie_session_create(&s, kind, W, H, N, frames));
-    g_sessions[key] = s;
+    g_sessions[key] = CachedSession{s, ++g_session_clock};
     *out = s;
     return IE_OK;
 }
 
 void drop_cached_sessions() {
     std::lock_guard<std::mutex> lk(g_smu);
-    for (auto &kv : g_sessions) ie_session_destroy(kv.second);
+    for (auto &kv : g_sessions) ie_session_destroy(kv.second.s);
     g_sessions.clear();
 }
 
