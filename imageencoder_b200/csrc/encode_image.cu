@@ -262,12 +262,34 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
             }
             __syncthreads();
             const unsigned nd = s_nd;
-            for (unsigned e = threadIdx.x; e < nd; e += kThreads) {
-                const int lb = s_dlist[e];
-                int lastnz, prevnz;
-                unsigned orbits;
-                block_stats_from_staging<NN>(s_coef + (size_t)lb * STRIDE, lastnz, prevnz, orbits);
-                s_stats[lb] = (unsigned)lastnz | ((unsigned)prevnz << 8) | (orbits << 16);
+            // RLE info of the patched blocks, NN/8 lanes per block (8 coefficients each), combined with shuffles
+            constexpr int LPB = NN / 8;
+            for (unsigned e0 = 0; e0 < nd; e0 += kThreads / LPB) {              // uniform
+                const unsigned e = e0 + threadIdx.x / LPB;
+                const int part = (int)(threadIdx.x % LPB);
+                const bool act = e < nd;
+                const int lb = act ? (int)s_dlist[e] : 0;
+                const unsigned *cw = reinterpret_cast<const unsigned *>(s_coef + (size_t)lb * STRIDE + part * 8);
+                unsigned m8 = 0, ob = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const unsigned w2 = cw[j];
+                    const int q0 = (int)(short)(w2 & 0xffffu), q1 = (int)w2 >> 16;
+                    if (q0 != 0) { m8 |= 1u << (2 * j); ob |= (unsigned)(q0 ^ (q0 >> 31)); }
+                    if (q1 != 0) { m8 |= 1u << (2 * j + 1); ob |= (unsigned)(q1 ^ (q1 >> 31)); }
+                }
+                unsigned long long mask = (unsigned long long)m8 << (8 * part);
+#pragma unroll
+                for (int d = 1; d < LPB; d <<= 1) {
+                    mask |= __shfl_xor_sync(0xffffffffu, mask, d);
+                    ob |= __shfl_xor_sync(0xffffffffu, ob, d);
+                }
+                if (act && part == 0) {
+                    const unsigned long long m2 = mask & ~(1ull << (NN - 1));
+                    const unsigned lastnz = mask ? 64u - (unsigned)__clzll((long long)mask) : 0u;
+                    const unsigned prevnz = m2 ? 64u - (unsigned)__clzll((long long)m2) : 0u;
+                    s_stats[lb] = lastnz | (prevnz << 8) | (ob << 16);
+                }
             }
             __syncthreads();
         }
