@@ -145,7 +145,8 @@ int make_quant(QuantParam &q, const uint16_t *quant, int N) {
 // Encode `images` equally sized images that are resident on the device.
 int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, unsigned images, uint32_t W, uint32_t H, int N,
                       const uint16_t *quant, int use_rle, int lead_bit, int write_header, unsigned first_bit, int bits_only,
-                      uint8_t *d_out, size_t out_stride, size_t out_cap, cudaStream_t stream, int append, uint32_t header_H, int split) {
+                      uint8_t *d_out, size_t out_stride, size_t out_cap, cudaStream_t stream, int append, uint32_t header_H, int split,
+                      uint64_t *d_out_bits) {
     // split: only the tile kernel runs (tile images stay in the session's scratch), the parameters and the header are kept in
     // the session for ie_encode_image_end_dev
     // append: the streams continue at their device-resident bit counters (no prefix is written); header_H: the height the
@@ -169,7 +170,7 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     } else if (!bits_only) {
         const size_t need = ((size_t)first_bit + hdr.bits + 127) / 128 * 16;
         if (out_cap < need) { set_error("output buffer too small for the header"); return IE_ENOSPC; }
-        IE_TRY(launch_stream_init(d_out, out_stride, images, hdr, first_bit, s->d_counter, stream));
+        // (the prefix is written by tile 0 of the tile kernel: no launch of its own)
     } else {
         IE_CUDA(cudaMemsetAsync(s->d_counter, 0, images * sizeof(unsigned long long), stream));
     }
@@ -185,6 +186,10 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     p.tab = (N == 8) ? s->dev->d_t8 : s->dev->d_t4;
     p.out = d_out; p.out_stride = out_stride; p.out_cap = out_cap;
     p.bit_counter = s->d_counter; p.err = s->d_err;
+    p.write_prefix = (!append && !split && !bits_only) ? 1 : 0;
+    p.prefix_first = first_bit;
+    p.hdr = hdr;
+    p.out_bits = reinterpret_cast<unsigned long long *>(d_out_bits);
     p.scan = s->scan_state();
     {
         const size_t ntot = (size_t)images * tiles;
@@ -373,10 +378,8 @@ int ie_encode_image_dev(ie_session *s, const uint8_t *d_raw, uint32_t W, uint32_
                         uint64_t *d_out_bits, void *stream) {
     if (!s || !d_raw || !d_out) { set_error("NULL argument"); return IE_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
-    IE_TRY(encode_images_dev(s, d_raw, 0, 1, W, H, (int)s->N, quant, use_rle, lead_bit, write_header, (unsigned)first_bit, 0,
-                             d_out, 0, out_cap, st));
-    if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, s->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-    return IE_OK;
+    return encode_images_dev(s, d_raw, 0, 1, W, H, (int)s->N, quant, use_rle, lead_bit, write_header, (unsigned)first_bit, 0,
+                             d_out, 0, out_cap, st, 0, 0, 0, d_out_bits);
 }
 
 int ie_encode_image_begin_dev(ie_session *s, const uint8_t *d_raw, uint32_t W, uint32_t H, const uint16_t *quant, int use_rle,

@@ -23,7 +23,8 @@ int launch_stream_init(uint8_t *out, size_t out_stride, unsigned images, const H
                        unsigned long long *counter, cudaStream_t stream);
 int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, unsigned images, uint32_t W, uint32_t H, int N,
                       const uint16_t *quant, int use_rle, int lead_bit, int write_header, unsigned first_bit, int bits_only,
-                      uint8_t *d_out, size_t out_stride, size_t out_cap, cudaStream_t stream, int append = 0, uint32_t header_H = 0, int split = 0);
+                      uint8_t *d_out, size_t out_stride, size_t out_cap, cudaStream_t stream, int append = 0, uint32_t header_H = 0, int split = 0,
+                      uint64_t *d_out_bits = nullptr);
 int session_ensure_pipeline(ie_session *s);
 int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size_t start_bit, int N, const ParsedHeader &h,
                      uint8_t *d_out, size_t out_cap, cudaStream_t stream);

@@ -514,7 +514,24 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
     if (threadIdx.x == 0) {
         p.tile_bits[(size_t)img * ntiles + tile] = T;
         if (p.bits_only) atomicAdd(p.bit_counter + img, (unsigned long long)T);
-        else if (tile == 0) p.bit_base[img] = p.bit_counter[img];      // the copy-out kernel of this launch starts here
+        else if (tile == 0 && !p.write_prefix) p.bit_base[img] = p.bit_counter[img];   // the copy-out kernel of this launch starts here
+    }
+    if (p.write_prefix && tile == 0 && !p.bits_only) {
+        // the stream's first chunks: zero bits up to prefix_first, then the header, zero padded (the copy-out kernel merges
+        // the first tile's bits into the last of them)
+        const unsigned total = p.prefix_first + p.hdr.bits;
+        const unsigned nw = ((total + 127) / 128) * 4;
+        unsigned *o = reinterpret_cast<unsigned *>(p.out + (size_t)img * p.out_stride);
+        for (unsigned i = threadIdx.x; i < nw; i += kThreads) {
+            const long long hb = (long long)i * 32 - (long long)p.prefix_first;       // header bit of this word's first bit
+            const int sh = (int)(((hb % 32) + 32) % 32);
+            const long long wi = (hb - sh) / 32;                                      // floor division
+            const unsigned hi = (wi >= 0 && wi < kHdrWordsMax) ? p.hdr.words[wi] : 0u;
+            const unsigned lo = (wi + 1 >= 0 && wi + 1 < kHdrWordsMax) ? p.hdr.words[wi + 1] : 0u;
+            const unsigned v = sh ? ((hi << sh) | (lo >> (32 - sh))) : hi;
+            o[i] = __byte_perm(v, 0, 0x0123);
+        }
+        if (threadIdx.x == 0) p.bit_base[img] = total;
     }
 }
 
@@ -604,7 +621,10 @@ __global__ void __launch_bounds__(kThreads) tile_copyout_kernel(const EncodePara
     g.n = t1 - t0;
     const unsigned T = s_goff[g.n];
     tile_write_chunks(g, st, blockIdx.x, t0 == 0, t1 == ntiles, G, T, p.out + (size_t)img * p.out_stride, p.out_cap, p.err);
-    if (t1 == ntiles && threadIdx.x == 0) p.bit_counter[img] = G + T;
+    if (t1 == ntiles && threadIdx.x == 0) {
+        p.bit_counter[img] = G + T;
+        if (p.out_bits) p.out_bits[img] = G + T;
+    }
 }
 
 int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t stream) {

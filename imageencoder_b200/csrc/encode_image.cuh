@@ -30,6 +30,12 @@ struct EncodeParams {
     uint8_t *tile_scratch;            // [images * tiles] slots of slot_bytes: packed tile images (tile-local alignment)
     size_t slot_bytes;
     int phase;                        // 0: tile kernel + copy-out; 1: tile kernel only (tile images stay in scratch); 2: copy-out only
+    // stream prefix written by the tile kernel itself (tile 0 of every image) instead of a separate launch: `prefix_first`
+    // zero bits, then the header; the stream's blocks start behind it
+    int write_prefix;
+    unsigned prefix_first;
+    HeaderParam hdr;
+    unsigned long long *out_bits;     // optional [images]: receives the streams' final bit counts (copy-out kernel)
     unsigned *tile_bits;              // [images * tiles] bits per tile
     unsigned long long *bit_base;     // [images] bit position each stream had when this launch started
     // P-frame mode (Frame.cpp:160-244): src is the CURRENT frame (read, then overwritten with the reconstruction),
