@@ -591,6 +591,7 @@ constexpr unsigned kTilesPerGroup = 8;
 __global__ void __launch_bounds__(kThreads) tile_copyout_kernel(const EncodeParams p) {
     __shared__ unsigned long long s_part[kThreads / 32];
     __shared__ unsigned s_goff[kTilesPerGroup + 1];
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // everything the preceding kernel wrote is visible after this
     const unsigned img = blockIdx.y, ntiles = p.tiles_per_image;
     const unsigned t0 = blockIdx.x * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
     const unsigned *tb = p.tile_bits + (size_t)img * ntiles;
@@ -629,7 +630,15 @@ __global__ void __launch_bounds__(kThreads) tile_copyout_kernel(const EncodePara
 
 int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t stream) {
     dim3 cgrid((p.tiles_per_image + kTilesPerGroup - 1) / kTilesPerGroup, images);
-    tile_copyout_kernel<<<cgrid, kThreads, 0, stream>>>(p);
+    // programmatic dependent launch: the copy-out grid is set up while the tile kernel drains and waits on the device
+    // (griddepcontrol.wait) for its results instead of being launched after the tile kernel has completed
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = cgrid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_kernel, p));
     count_launch();
     IE_CUDA(cudaGetLastError());
     return IE_OK;
