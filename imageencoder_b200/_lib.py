@@ -38,6 +38,8 @@ SIGNATURES = {
     "ie_session_destroy": (None, [_vp]),
     "ie_encode_image_dev": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _u16p, C.c_int, C.c_int, C.c_int, C.c_uint64, _vp,
                                       C.c_size_t, _vp, _vp]),
+    "ie_encode_images_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, _u16p, C.c_int, C.c_int, _vp, C.c_size_t,
+                                       _vp, _vp]),
     "ie_encode_image_begin_dev": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _u16p, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "ie_encode_image_end_dev": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_size_t, _vp, _vp, _vp]),
     "ie_session_set_header_height": (C.c_int, [_vp, C.c_uint32]),

@@ -382,6 +382,15 @@ int ie_encode_image_dev(ie_session *s, const uint8_t *d_raw, uint32_t W, uint32_
                              d_out, 0, out_cap, st, 0, 0, 0, d_out_bits);
 }
 
+int ie_encode_images_dev(ie_session *s, const uint8_t *d_raws, size_t raw_stride, uint32_t count, uint32_t W, uint32_t H,
+                         const uint16_t *quant, int use_rle, int lead_bit, uint8_t *d_out, size_t out_stride, uint64_t *d_out_bits,
+                         void *stream) {
+    if (!s || !d_raws || !d_out || count == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    if (raw_stride < (size_t)W * H) { set_error("raw_stride smaller than an image"); return IE_EINVAL; }
+    return encode_images_dev(s, d_raws, raw_stride, count, W, H, (int)s->N, quant, use_rle, lead_bit, 1, 0, 0, d_out, out_stride, out_stride,
+                             (cudaStream_t)stream, 0, 0, 0, d_out_bits);
+}
+
 int ie_encode_image_begin_dev(ie_session *s, const uint8_t *d_raw, uint32_t W, uint32_t H, const uint16_t *quant, int use_rle,
                               int lead_bit, int write_header, uint64_t *d_total_bits, void *stream) {
     if (!s || !d_raw || !d_total_bits) { set_error("NULL argument"); return IE_EINVAL; }

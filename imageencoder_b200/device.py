@@ -53,6 +53,15 @@ def encode_image_dev(s: Session, d_raw: torch.Tensor, quant, rle: bool, d_out: t
                                     _dp(d_bits) if d_bits is not None else None, _stream()))
 
 
+def encode_images_dev(s: Session, d_raws: torch.Tensor, count: int, quant, rle: bool, d_out: torch.Tensor, out_stride: int,
+                      d_bits: torch.Tensor | None = None, lead_bit: bool = True, width=None, height=None) -> None:
+    """Batch of `count` equally sized images (contiguous in d_raws) in one launch of each kernel; stream i at d_out[i*out_stride:]."""
+    q, qp = _q(quant)
+    w, h = width or s.width, height or s.height
+    check(lib().ie_encode_images_dev(s.h, _dp(d_raws), w * h, count, w, h, qp, int(rle), int(lead_bit), _dp(d_out), out_stride,
+                                     _dp(d_bits) if d_bits is not None else None, _stream()))
+
+
 def encode_image_begin_dev(s: Session, d_raw: torch.Tensor, quant, rle: bool, d_total_bits: torch.Tensor, lead_bit: bool = True,
                            write_header: bool = True, width=None, height=None) -> None:
     """First half of a sharded encode: blocks -> tile scratch; d_total_bits[0] = header bits + block bits of this shard."""

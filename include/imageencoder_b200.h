@@ -91,6 +91,12 @@ void ie_session_destroy(ie_session *s);
 int ie_encode_image_dev(ie_session *s, const uint8_t *d_raw, uint32_t width, uint32_t height,
                         const uint16_t *quant, int use_rle, int lead_bit, int write_header, uint64_t first_bit,
                         uint8_t *d_out, size_t out_cap, uint64_t *d_out_bits, void *stream);
+/* Batch of equally sized device-resident images (BASELINE config 4), one launch of each kernel for all of them: image i is
+ * at d_raws + i * raw_stride, its stream goes to d_out + i * out_stride (out_stride >= ie_max_encoded_bytes of one image,
+ * multiple of 16), d_out_bits[i] (device, optional) receives its bit count. */
+int ie_encode_images_dev(ie_session *s, const uint8_t *d_raws, size_t raw_stride, uint32_t count, uint32_t width,
+                         uint32_t height, const uint16_t *quant, int use_rle, int lead_bit, uint8_t *d_out,
+                         size_t out_stride, uint64_t *d_out_bits, void *stream);
 /* Split encode for a shard of a multi-GPU stream, so that the ONE collective of a sharded encode sits between
  * the two kernels and no re-alignment pass is needed:
  *   begin: transform/quantise/pack the shard's blocks into the session's tile scratch; *d_total_bits (device) = header bits

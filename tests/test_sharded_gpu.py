@@ -167,6 +167,30 @@ def test_gop_shards_stitch_to_single_video_stream(gpu, oracle_mod):
         assert got == want, f"x{world}: stitched video stream differs ({len(got)} vs {len(want)} bytes)"
 
 
+def test_device_batch_one_launch(gpu, oracle_mod):
+    """ie_encode_images_dev: all images of a batch in one launch of each kernel, every stream the oracle's"""
+    import torch
+    from imageencoder_b200 import device
+    from imageencoder_b200._lib import lib
+    from imageencoder_b200.synth import synth_image
+    for (W, H, mat, count) in ((128, 64, "matrix4_2.txt", 5), (192, 128, "matrix8_1.txt", 3)):
+        q = oracle_mod.read_matrix(INPUTS / mat)
+        N = q.shape[0]
+        imgs = np.stack([synth_image(W, H, 2100 + i, flat=(i == 1)) for i in range(count)])
+        slot = (int(lib().ie_max_encoded_bytes(W, H, N, 1)) + 15) // 16 * 16
+        d_raws = torch.from_numpy(imgs).cuda().reshape(-1)
+        d_out = torch.zeros(count * slot, dtype=torch.uint8, device="cuda")
+        d_bits = torch.zeros(count, dtype=torch.int64, device="cuda")
+        sess = device.Session(device.Session.IMAGE_ENCODE, W, H, N)
+        device.encode_images_dev(sess, d_raws, count, q, True, d_out, slot, d_bits)
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy()
+        for i in range(count):
+            want = oracle_mod.image_encode(imgs[i], W, H, N, q, True, False)
+            nb = (int(d_bits[i].item()) + 7) // 8
+            assert out[i * slot: i * slot + nb].tobytes() == want, f"{mat} image {i}"
+
+
 def test_batch_entry_point(gpu, oracle_mod):
     from imageencoder_b200._lib import check, lib
     from imageencoder_b200.synth import synth_image

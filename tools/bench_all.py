@@ -76,6 +76,16 @@ qq = np.ascontiguousarray(q4, np.uint16).reshape(-1)
 ms = wall(lambda: _lib.check(L.ie_encode_images(C.c_void_p(imgs.ctypes.data), b, 4096, 4096, 4, qq.ctypes.data_as(C.POINTER(C.c_uint16)), 1, 0,
                                                 C.c_void_p(outb.ctypes.data), slot, sizes)))
 out["batch4_encode_host_ms_per_image"] = ms / b; out["batch4_encode_host_gpx_s"] = b * 4096 * 4096 / ms / 1e6
+# the same batch device-resident, one launch of each kernel for all images
+cnt = 16
+d_batch = torch.from_numpy(np.concatenate([imgs] * (cnt // b))).cuda().reshape(-1)
+slot16 = (slot + 15) // 16 * 16
+d_bout = torch.empty(cnt * slot16, dtype=torch.uint8, device="cuda")
+d_bbits = torch.zeros(cnt, dtype=torch.int64, device="cuda")
+sb = device.Session(0, 4096, 4096, 4)
+ms = ev_time(lambda: device.encode_images_dev(sb, d_batch, cnt, q4, True, d_bout, slot16, d_bbits))
+out["batch16_encode4_dev_ms_per_image"] = ms / cnt; out["batch16_encode4_dev_gpx_s"] = cnt * 4096 * 4096 / ms / 1e6
+del d_batch, d_bout
 d_raw4 = torch.from_numpy(imgs[0]).cuda().reshape(-1)
 d_out4 = torch.empty(slot, dtype=torch.uint8, device="cuda")
 s4 = device.Session(0, 4096, 4096, 4)
