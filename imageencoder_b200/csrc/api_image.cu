@@ -362,6 +362,11 @@ int ie_session_create(ie_session **out, int kind, uint32_t W, uint32_t H, uint32
 
 void ie_session_destroy(ie_session *s) {
     if (!s) return;
+    for (int k = 0; k < ie_session::kDecodeWorkers; k++) {
+        if (s->workers[k]) ie_session_destroy(s->workers[k]);
+        if (s->ev_join[k]) cudaEventDestroy(s->ev_join[k]);
+    }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     cudaFree(s->d_tile_state); cudaFree(s->d_bnd); cudaFree(s->d_ticket); cudaFree(s->d_counter); cudaFree(s->d_err);
     cudaFree(s->d_block_off); cudaFree(s->d_parse); cudaFree(s->d_tile_scratch); cudaFree(s->d_tile_meta); cudaFree(s->d_scratch); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_tmp);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
@@ -539,17 +544,93 @@ int ie_encode_images(const uint8_t *raws, uint32_t count, uint32_t W, uint32_t H
     return IE_OK;
 }
 
+int ie_decode_images_dev(ie_session *s, const uint8_t *d_encs, size_t enc_stride, const size_t *enc_bytes, uint32_t count,
+                         uint64_t start_bit, uint8_t *d_raws_out, size_t raw_stride, uint32_t *W, uint32_t *H, void *stream);
+
 int ie_decode_images(const uint8_t *encs, size_t enc_stride, const size_t *enc_bytes, uint32_t count, uint32_t N, uint8_t *raws_out,
                      size_t raw_stride, uint32_t *W, uint32_t *H) {
     if (!encs || !enc_bytes || !raws_out || count == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
-    // streams of a batch are independent; each goes through the single-image path
-    for (uint32_t i = 0; i < count; i++) {
-        uint32_t w = 0, h = 0;
-        IE_TRY(ie_decode_image(encs + (size_t)i * enc_stride, enc_bytes[i], N, raws_out + (size_t)i * raw_stride, raw_stride, &w, &h));
-        if (W) *W = w;
-        if (H) *H = h;
+    if (N != 4 && N != 8) { set_error("block size must be 4 or 8"); return IE_EINVAL; }
+    // streams of a batch are independent.  Plain streams go through the concurrent device batch in sub-batches;
+    // Huffman-coded ones (first bit 1, Huffman.cpp:361-371) through the single-image path.
+    bool plain = true;
+    size_t maxb = 0;
+    for (uint32_t i = 0; i < count; i++) { plain = plain && !(encs[(size_t)i * enc_stride] & 0x80); maxb = std::max(maxb, enc_bytes[i]); }
+    if (!plain || maxb > enc_stride) {
+        for (uint32_t i = 0; i < count; i++) {
+            uint32_t w = 0, h = 0;
+            IE_TRY(ie_decode_image(encs + (size_t)i * enc_stride, enc_bytes[i], N, raws_out + (size_t)i * raw_stride, raw_stride, &w, &h));
+            if (W) *W = w;
+            if (H) *H = h;
+        }
+        return IE_OK;
+    }
+    ie_session *s = nullptr;
+    IE_TRY(cached_session(&s, 1, 0, 0, N, 2));
+    cudaStream_t st = s->stream;
+    const size_t es = (maxb + 16 + 15) / 16 * 16;                                   // device stride of a stream
+    const uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(count, ((size_t)4 << 30) / (es + raw_stride)));
+    IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, es * sub));
+    IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, raw_stride * sub));
+    std::vector<uint32_t> ws(sub), hs(sub);
+    for (uint32_t first = 0; first < count; first += sub) {
+        const uint32_t n = std::min(sub, count - first);
+        IE_CUDA(cudaMemcpy2DAsync(s->d_in, es, encs + (size_t)first * enc_stride, enc_stride, std::min(es, enc_stride), n, cudaMemcpyHostToDevice, st));
+        IE_TRY(ie_decode_images_dev(s, s->d_in, es, enc_bytes + first, n, 1, s->d_out, raw_stride, ws.data(), hs.data(), st));
+        for (uint32_t i = 0; i < n; i++) {
+            const size_t px = (size_t)ws[i] * hs[i];
+            IE_CUDA(cudaMemcpyAsync(raws_out + (size_t)(first + i) * raw_stride, s->d_out + (size_t)i * raw_stride, px, cudaMemcpyDeviceToHost, st));
+        }
+        IE_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < ie_session::kDecodeWorkers; k++)
+            if (s->workers[k]) IE_TRY(read_err_flag(s->workers[k], s->workers[k]->stream));
+        if (W) *W = ws[n - 1];
+        if (H) *H = hs[n - 1];
     }
     return IE_OK;
+}
+
+int ie_decode_images_dev(ie_session *s, const uint8_t *d_encs, size_t enc_stride, const size_t *enc_bytes, uint32_t count,
+                         uint64_t start_bit, uint8_t *d_raws_out, size_t raw_stride, uint32_t *W, uint32_t *H, void *stream) {
+    if (!s || !d_encs || !enc_bytes || !d_raws_out || count == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    if (enc_stride % 16) { set_error("enc_stride must be a multiple of 16"); return IE_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = (int)s->N;
+    // all headers with one strided copy and one synchronisation
+    constexpr size_t kHdr = 160;
+    const size_t first = (size_t)(start_bit / 8);
+    std::vector<uint8_t> hb((size_t)count * kHdr, 0);
+    size_t minb = enc_bytes[0];
+    for (uint32_t i = 1; i < count; i++) minb = std::min(minb, enc_bytes[i]);
+    if (first >= minb) { set_error("start_bit beyond the stream"); return IE_EFORMAT; }
+    const size_t n = std::min(kHdr, std::min(minb - first, enc_stride - first));
+    IE_CUDA(cudaMemcpy2DAsync(hb.data(), kHdr, d_encs + first, enc_stride, n, count, cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    if (!s->ev_fork) IE_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    const int nw = (int)std::min<uint32_t>(count, ie_session::kDecodeWorkers);
+    for (int k = 0; k < nw; k++) {
+        if (!s->workers[k]) IE_TRY(ie_session_create(&s->workers[k], 1, 0, 0, (uint32_t)N, 1));
+        if (!s->ev_join[k]) IE_CUDA(cudaEventCreateWithFlags(&s->ev_join[k], cudaEventDisableTiming));
+    }
+    IE_CUDA(cudaEventRecord(s->ev_fork, st));
+    for (int k = 0; k < nw; k++) IE_CUDA(cudaStreamWaitEvent(s->workers[k]->stream, s->ev_fork, 0));
+    int rc = IE_OK;
+    for (uint32_t i = 0; i < count && rc == IE_OK; i++) {
+        ie_session *w = s->workers[i % nw];
+        ParsedHeader h;
+        parse_header(hb.data() + (size_t)i * kHdr, n, (size_t)(start_bit % 8), N, h, 0);
+        h.end_bit += first * 8;
+        if (W) W[i] = h.W;
+        if (H) H[i] = h.H;
+        if ((size_t)h.W * h.H > raw_stride) { set_error("raw_stride smaller than a decoded image"); rc = IE_ENOSPC; break; }
+        rc = decode_image_dev(w, d_encs + (size_t)i * enc_stride, enc_bytes[i], (size_t)start_bit, N, h, d_raws_out + (size_t)i * raw_stride,
+                              raw_stride, w->stream);
+    }
+    for (int k = 0; k < nw; k++) {                           // join, also on errors: the caller's stream stays ordered
+        cudaEventRecord(s->ev_join[k], s->workers[k]->stream);
+        cudaStreamWaitEvent(st, s->ev_join[k], 0);
+    }
+    return rc;
 }
 
 int ie_decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, uint64_t start_bit, uint8_t *d_raw_out,

@@ -29,6 +29,12 @@ struct ie_session {
     uint8_t *d_tile_scratch = nullptr; size_t tile_scratch_cap = 0;
     uint8_t *d_tile_meta = nullptr;    size_t tile_meta_cap = 0;
 
+    // batch decode (ie_decode_images_dev): worker sessions with their own streams, so that the latency-bound parse kernels
+    // of one stream overlap the block decode of another; fork/join events keep the caller's stream semantics
+    static constexpr int kDecodeWorkers = 4;
+    ie_session *workers[kDecodeWorkers] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kDecodeWorkers] = {};
+
     // split encode (ie_encode_image_begin_dev / _end_dev): what `begin` left for `end`
     bool split_pending = false;
     ie::EncodeParams split_params;

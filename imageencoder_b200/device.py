@@ -90,6 +90,16 @@ def decode_image_dev(s: Session, d_enc: torch.Tensor, enc_bytes: int, d_raw_out:
     return w.value, h.value
 
 
+def decode_images_dev(s: Session, d_encs: torch.Tensor, enc_stride: int, enc_bytes, d_raws_out: torch.Tensor, raw_stride: int,
+                      start_bit: int = 1):
+    """Batch decode of device-resident plain streams on the session's worker streams; returns the (W, H) lists."""
+    n = len(enc_bytes)
+    eb = (C.c_size_t * n)(*[int(b) for b in enc_bytes])
+    w, h = (C.c_uint32 * n)(), (C.c_uint32 * n)()
+    check(lib().ie_decode_images_dev(s.h, _dp(d_encs), enc_stride, eb, n, start_bit, _dp(d_raws_out), raw_stride, w, h, _stream()))
+    return list(w), list(h)
+
+
 def encode_video_dev(s: Session, d_yuv: torch.Tensor, width: int, height: int, quant, rle: bool, gop: int, merange: int,
                      d_out: torch.Tensor, d_bits: torch.Tensor | None = None, lead_bit: bool = True, d_mvecs: torch.Tensor | None = None) -> None:
     """``dc::VideoEncoder::process`` on device-resident YUV420 frames (the Y planes are rebuilt in place, Frame.cpp:218-242).

@@ -123,6 +123,13 @@ int ie_decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
                         uint8_t *d_raw_out, size_t raw_cap, uint32_t *width, uint32_t *height, void *stream);
 /* Byte-wise Huffman stage over a device-resident, byte-rounded plain stream (Huffman.cpp:232-344).
  * Synchronises `stream` once (the 256-entry tree is built on the host exactly as the reference does). */
+/* Batch of device-resident plain streams (stream i at d_encs + i * enc_stride, enc_bytes[i] bytes; enc_stride a multiple
+ * of 16), decoded concurrently on worker streams that fork from / join `stream`; image i goes to d_raws_out + i *
+ * raw_stride; W[i], H[i] (host, optional) from the headers.  Errors found on the device (malformed stream) are reported by
+ * the workers' error flags at the next synchronising call. */
+int ie_decode_images_dev(ie_session *s, const uint8_t *d_encs, size_t enc_stride, const size_t *enc_bytes, uint32_t count,
+                         uint64_t start_bit, uint8_t *d_raws_out, size_t raw_stride, uint32_t *W, uint32_t *H,
+                         void *stream);
 int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes,
                           uint8_t *d_out, size_t out_cap, size_t *out_bytes, void *stream);
 int ie_huffman_decode_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes,

@@ -185,10 +185,22 @@ def test_device_batch_one_launch(gpu, oracle_mod):
         device.encode_images_dev(sess, d_raws, count, q, True, d_out, slot, d_bits)
         torch.cuda.synchronize()
         out = d_out.cpu().numpy()
+        sizes = []
         for i in range(count):
             want = oracle_mod.image_encode(imgs[i], W, H, N, q, True, False)
             nb = (int(d_bits[i].item()) + 7) // 8
+            sizes.append(nb)
             assert out[i * slot: i * slot + nb].tobytes() == want, f"{mat} image {i}"
+        # ... and back: ie_decode_images_dev on the same device buffers (concurrent worker streams)
+        d_dec = torch.zeros(count * W * H, dtype=torch.uint8, device="cuda")
+        sd = device.Session(device.Session.IMAGE_DECODE, W, H, N)
+        ws, hs = device.decode_images_dev(sd, d_out, slot, sizes, d_dec, W * H)
+        torch.cuda.synchronize()
+        assert ws == [W] * count and hs == [H] * count
+        dec = d_dec.cpu().numpy().reshape(count, H, W)
+        for i in range(count):
+            want = oracle_mod.image_encode(imgs[i], W, H, N, q, True, False)
+            assert np.array_equal(dec[i], np.asarray(oracle_mod.image_decode(want, N)[0])), f"{mat} decoded image {i}"
 
 
 def test_batch_entry_point(gpu, oracle_mod):

@@ -85,7 +85,12 @@ d_bbits = torch.zeros(cnt, dtype=torch.int64, device="cuda")
 sb = device.Session(0, 4096, 4096, 4)
 ms = ev_time(lambda: device.encode_images_dev(sb, d_batch, cnt, q4, True, d_bout, slot16, d_bbits))
 out["batch16_encode4_dev_ms_per_image"] = ms / cnt; out["batch16_encode4_dev_gpx_s"] = cnt * 4096 * 4096 / ms / 1e6
-del d_batch, d_bout
+bsz = [(int(x) + 7) // 8 for x in d_bbits.cpu().tolist()]
+d_bdec = torch.empty(cnt * 4096 * 4096, dtype=torch.uint8, device="cuda")
+sbd = device.Session(1, 4096, 4096, 4)
+ms = ev_time(lambda: device.decode_images_dev(sbd, d_bout, slot16, bsz, d_bdec, 4096 * 4096), reps=3, warm=1)
+out["batch16_decode4_dev_ms_per_image"] = ms / cnt; out["batch16_decode4_dev_gpx_s"] = cnt * 4096 * 4096 / ms / 1e6
+del d_batch, d_bout, d_bdec
 d_raw4 = torch.from_numpy(imgs[0]).cuda().reshape(-1)
 d_out4 = torch.empty(slot, dtype=torch.uint8, device="cuda")
 s4 = device.Session(0, 4096, 4096, 4)
