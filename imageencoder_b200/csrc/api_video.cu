@@ -208,6 +208,7 @@ __device__ __forceinline__ unsigned read_bits_dev(const uint8_t *s, unsigned lon
 }
 
 __global__ void __launch_bounds__(256) mc_copy_kernel(const MCParams p) {
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mb = blockIdx.x * 8 + warp;
     if (mb >= p.nmb) return;
@@ -534,7 +535,7 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
             MCParams mc;
             mc.enc = d_enc; mc.enc_bits = consts[0]; mc.cursor = vs.cursor; mc.mvbits = mvbits; mc.ref = d_out + (size_t)(f - 1) * fsz;
             mc.cur = cur; mc.W = (int)W; mc.H = (int)H; mc.mx = (int)(W / kMB); mc.nmb = (int)nmb;
-            mc_copy_kernel<<<(nmb + 7) / 8, 256, 0, st>>>(mc);
+            IE_CUDA(launch_pdl(mc_copy_kernel, dim3((nmb + 7) / 8), dim3(256), 0, st, mc));
             count_launch();
             IE_CUDA(cudaGetLastError());
             p.skip_bits = nmb * 2 * mvbits; p.add_mode = 1;

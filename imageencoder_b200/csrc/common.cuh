@@ -101,4 +101,20 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
 }
 #endif
 
+#ifdef __CUDACC__
+// Programmatic dependent launch: the grid is set up while its predecessor in the stream drains; the kernel must execute
+// pdl_wait() before it touches anything an earlier kernel (or copy) of the stream produced.  The decode path is a chain of
+// short, latency-bound kernels (a dozen per video frame), where the launch latency otherwise adds up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 }  // namespace ie

@@ -165,6 +165,7 @@ struct BitReader {
 
 template <int N, bool ADD>
 __global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodeParams p) {
+    pdl_wait();
     constexpr int NN = N * N;
     constexpr int STRIDE = NN + 2;
     // the bits of the CTA's 128 blocks are one contiguous span of the stream (<= 128 * (4 + 16 + 16 NN) bits): staged with
@@ -297,9 +298,9 @@ int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t str
 int launch_decode_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream) {
     if (!g_exact_transform.load()) {
         dim3 gridf((p.nblocks + 127) / 128, images);
-        if (p.N == 8) decode_blocks_fast_kernel<8, false><<<gridf, 128, 0, stream>>>(p);
-        else if (p.N == 4 && p.add_mode) decode_blocks_fast_kernel<4, true><<<gridf, 128, 0, stream>>>(p);
-        else if (p.N == 4) decode_blocks_fast_kernel<4, false><<<gridf, 128, 0, stream>>>(p);
+        if (p.N == 8) IE_CUDA(launch_pdl(decode_blocks_fast_kernel<8, false>, gridf, dim3(128), 0, stream, p));
+        else if (p.N == 4 && p.add_mode) IE_CUDA(launch_pdl(decode_blocks_fast_kernel<4, true>, gridf, dim3(128), 0, stream, p));
+        else if (p.N == 4) IE_CUDA(launch_pdl(decode_blocks_fast_kernel<4, false>, gridf, dim3(128), 0, stream, p));
         else { set_error("block size must be 4 or 8"); return IE_EINVAL; }
         count_launch();
         IE_CUDA(cudaGetLastError());

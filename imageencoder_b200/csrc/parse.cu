@@ -87,6 +87,7 @@ __device__ __forceinline__ unsigned block_bits_at(const uint8_t *s, unsigned lon
 }
 
 __global__ void __launch_bounds__(64) parse_group_tables(const ParseParams p) {
+    pdl_wait();
     extern __shared__ unsigned s_parse[];
     const int E = p.E;
     unsigned *s_cnt = s_parse;                                            // [E]
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(64) parse_group_tables(const ParseParams p) {
 }
 
 __global__ void __launch_bounds__(256) parse_super_tables(const ParseParams p) {
+    pdl_wait();
     const unsigned sg = blockIdx.x;
     if (p.spec_flags[1]) return;
     const unsigned g0 = sg * kSuper, g1 = min(g0 + kSuper, p.ngroups);
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(256) parse_super_tables(const ParseParams p) {
 }
 
 __global__ void parse_top_walk(const ParseParams p) {
+    pdl_wait();
     if (threadIdx.x != 0 || blockIdx.x != 0 || p.spec_flags[1]) return;
     unsigned cur = 0, cnt = 0;
     for (unsigned sg = 0; sg < p.nsuper; sg++) {
@@ -159,6 +162,7 @@ __global__ void parse_top_walk(const ParseParams p) {
 }
 
 __global__ void __launch_bounds__(64) parse_down_super(const ParseParams p) {
+    pdl_wait();
     const unsigned sg = blockIdx.x * blockDim.x + threadIdx.x;
     if (sg >= p.nsuper || p.spec_flags[1]) return;
     const uint2 se = p.super_entry[sg];
@@ -241,6 +245,7 @@ template <int GB, int TH> struct SpecCfg {
 // the first group of every CTA is checked against the previous CTA by parse_spec_boundary.
 template <int GB, int TH>
 __global__ void __launch_bounds__(TH) parse_spec_walk(const ParseParams p) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned s_stage[];
     __shared__ unsigned s_entry[TH], s_exit[TH];
     const unsigned g = blockIdx.x * TH + threadIdx.x;
@@ -303,6 +308,7 @@ __global__ void __launch_bounds__(TH) parse_spec_walk(const ParseParams p) {
 // parse_spec_finish (-> exact kernels).
 template <int GB, int TH>
 __global__ void __launch_bounds__(TH) parse_spec_boundary(const ParseParams p) {
+    pdl_wait();
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned g = k * TH;
     if (k == 0 || g >= p.nspec) return;
@@ -327,6 +333,7 @@ __global__ void __launch_bounds__(TH) parse_spec_boundary(const ParseParams p) {
 // vectors), where the speculative walks may legitimately disagree.
 template <int GB, int TH>
 __global__ void __launch_bounds__(TH) parse_spec_check(const ParseParams p) {
+    pdl_wait();
     __shared__ unsigned s_part[TH];
     __shared__ unsigned s_last;
     const unsigned g = blockIdx.x * TH + threadIdx.x;
@@ -384,6 +391,7 @@ __global__ void __launch_bounds__(TH) parse_spec_check(const ParseParams p) {
 // chain from its entry; the first block index of a group = scanned per-CTA counts + the counts of the CTA's earlier groups.
 template <int GB, int TH>
 __global__ void __launch_bounds__(TH) parse_spec_emit(const ParseParams p) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned s_stage[];
     __shared__ unsigned s_wsum[TH / 32];
     if (!p.spec_flags[1]) return;                            // uniform: the exact kernels produce the offsets
@@ -440,6 +448,7 @@ __global__ void __launch_bounds__(TH) parse_spec_emit(const ParseParams p) {
 
 // block_off[] from the exact kernels' group entries (only when the speculative parse did not verify)
 __global__ void __launch_bounds__(64) parse_emit_offsets(const ParseParams p) {
+    pdl_wait();
     const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= p.ngroups || p.spec_flags[1]) return;
     const uint2 ge = p.group_entry[g];
@@ -466,6 +475,7 @@ __global__ void __launch_bounds__(64) parse_emit_offsets(const ParseParams p) {
 }
 
 __global__ void parse_commit_cursor(const ParseParams p) {
+    pdl_wait();
     const unsigned long long next = *p.cursor_next;
     if (next != ~0ull) *p.cursor_out = next;
 }
@@ -491,10 +501,10 @@ static int launch_spec(const ParseParams &p, cudaStream_t stream) {
     const size_t stage_bytes = (size_t)SpecCfg<GB, TH>::kStageWords * sizeof(unsigned);
     IE_CUDA(cudaFuncSetAttribute(parse_spec_walk<GB, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
     IE_CUDA(cudaFuncSetAttribute(parse_spec_emit<GB, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
-    parse_spec_walk<GB, TH><<<nwalk, TH, stage_bytes, stream>>>(p);
-    parse_spec_boundary<GB, TH><<<(nwalk + 63) / 64, 64, 0, stream>>>(p);
-    parse_spec_check<GB, TH><<<nwalk, TH, 0, stream>>>(p);
-    parse_spec_emit<GB, TH><<<nwalk, TH, stage_bytes, stream>>>(p);
+    IE_CUDA(launch_pdl(parse_spec_walk<GB, TH>, dim3(nwalk), dim3(TH), stage_bytes, stream, p));
+    IE_CUDA(launch_pdl(parse_spec_boundary<GB, TH>, dim3((nwalk + 63) / 64), dim3(64), 0, stream, p));
+    IE_CUDA(launch_pdl(parse_spec_check<GB, TH>, dim3(nwalk), dim3(TH), 0, stream, p));
+    IE_CUDA(launch_pdl(parse_spec_emit<GB, TH>, dim3(nwalk), dim3(TH), stage_bytes, stream, p));
     IE_CUDA(cudaGetLastError());
     return IE_OK;
 }
@@ -534,17 +544,17 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     if (d.N == 8) IE_TRY((launch_spec<8192, 64>(p, stream)));
     else IE_TRY((launch_spec<2048, 256>(p, stream)));
     IE_DBG_STEP("parse_spec");
-    parse_group_tables<<<std::min(p.ngroups, 148u * 8u), 64, smem, stream>>>(p);
+    IE_CUDA(launch_pdl(parse_group_tables, dim3(std::min(p.ngroups, 148u * 8u)), dim3(64), smem, stream, p));
     IE_DBG_STEP("parse_group_tables");
-    parse_super_tables<<<p.nsuper, 256, 0, stream>>>(p);
+    IE_CUDA(launch_pdl(parse_super_tables, dim3(p.nsuper), dim3(256), 0, stream, p));
     IE_DBG_STEP("parse_super_tables");
-    parse_top_walk<<<1, 32, 0, stream>>>(p);
+    IE_CUDA(launch_pdl(parse_top_walk, dim3(1), dim3(32), 0, stream, p));
     IE_DBG_STEP("parse_top_walk");
-    parse_down_super<<<(p.nsuper + 63) / 64, 64, 0, stream>>>(p);
+    IE_CUDA(launch_pdl(parse_down_super, dim3((p.nsuper + 63) / 64), dim3(64), 0, stream, p));
     IE_DBG_STEP("parse_down_super");
-    parse_emit_offsets<<<(p.ngroups + 63) / 64, 64, 0, stream>>>(p);
+    IE_CUDA(launch_pdl(parse_emit_offsets, dim3((p.ngroups + 63) / 64), dim3(64), 0, stream, p));
     IE_DBG_STEP("parse_emit_offsets");
-    if (p.cursor_out) { parse_commit_cursor<<<1, 1, 0, stream>>>(p); count_launch(); }
+    if (p.cursor_out) { IE_CUDA(launch_pdl(parse_commit_cursor, dim3(1), dim3(1), 0, stream, p)); count_launch(); }
 #undef IE_DBG_STEP
     count_launch(9);
     IE_CUDA(cudaGetLastError());
