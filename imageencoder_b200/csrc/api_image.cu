@@ -94,6 +94,7 @@ __global__ void stream_init_kernel(uint8_t *out, size_t out_stride, unsigned ima
 // holds that bit, so the prefix is (first % 128) zero bits, then the header (rank 0 only).
 __global__ void stream_init_shard_kernel(uint8_t *out, HeaderParam hdr, const unsigned long long *shard_totals, unsigned shard_index,
                                          unsigned long long *counter, unsigned long long *bit_base, unsigned long long *first_out) {
+    pdl_wait();
     __shared__ unsigned s_fb;
     if (threadIdx.x == 0) {
         unsigned long long first = 0;
@@ -415,8 +416,9 @@ int ie_encode_image_end_dev(ie_session *s, const uint64_t *d_shard_totals, uint3
     EncodeParams p = s->split_params;
     s->split_pending = false;
     p.out = d_out; p.out_stride = 0; p.out_cap = out_cap;
-    stream_init_shard_kernel<<<1, 64, 0, st>>>(d_out, s->split_hdr, reinterpret_cast<const unsigned long long *>(d_shard_totals), shard_index,
-                                              s->d_counter, p.bit_base, reinterpret_cast<unsigned long long *>(d_first_bit));
+    IE_CUDA(launch_pdl(stream_init_shard_kernel, dim3(1), dim3(64), 0, st, d_out, s->split_hdr,
+                       reinterpret_cast<const unsigned long long *>(d_shard_totals), (unsigned)shard_index, s->d_counter, p.bit_base,
+                       reinterpret_cast<unsigned long long *>(d_first_bit)));
     count_launch();
     IE_TRY(launch_tile_copyout(p, 1, st));
     if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, s->d_counter, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));

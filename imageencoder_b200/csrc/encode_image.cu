@@ -591,7 +591,7 @@ constexpr unsigned kTilesPerGroup = 8;
 __global__ void __launch_bounds__(kThreads) tile_copyout_kernel(const EncodeParams p) {
     __shared__ unsigned long long s_part[kThreads / 32];
     __shared__ unsigned s_goff[kTilesPerGroup + 1];
-    asm volatile("griddepcontrol.wait;" ::: "memory");       // everything the preceding kernel wrote is visible after this
+    pdl_wait();                                              // everything the preceding kernel wrote is visible after this
     const unsigned img = blockIdx.y, ntiles = p.tiles_per_image;
     const unsigned t0 = blockIdx.x * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
     const unsigned *tb = p.tile_bits + (size_t)img * ntiles;
@@ -646,6 +646,7 @@ int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t str
 
 __global__ void __launch_bounds__(256) tile_totals_kernel(const unsigned *__restrict__ tile_bits, unsigned ntiles, unsigned long long add,
                                                           unsigned long long *d_total) {
+    pdl_wait();
     __shared__ unsigned long long s_part[8];
     const unsigned *tb = tile_bits + (size_t)blockIdx.x * ntiles;
     unsigned long long sum = 0;
@@ -663,7 +664,7 @@ __global__ void __launch_bounds__(256) tile_totals_kernel(const unsigned *__rest
 
 int launch_tile_totals(const unsigned *tile_bits, unsigned ntiles, unsigned images, unsigned long long add, unsigned long long *d_total,
                        cudaStream_t stream) {
-    tile_totals_kernel<<<images, 256, 0, stream>>>(tile_bits, ntiles, add, d_total);
+    IE_CUDA(launch_pdl(tile_totals_kernel, dim3(images), dim3(256), 0, stream, tile_bits, ntiles, add, d_total));
     count_launch();
     IE_CUDA(cudaGetLastError());
     return IE_OK;
