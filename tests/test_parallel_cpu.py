@@ -173,3 +173,28 @@ def test_gloo_world2_huffman_histogram_exchange():
     assert res[0] == "ok", res
     assert res[1], "reduced histogram / first occurrences differ from the whole stream's"
     assert res[2], "byte ranges do not tile the stream"
+
+
+def test_random_shard_placement_and_merge_roundtrip():
+    """place_shards / merge_shard_into / shard_byte_range on random bit strings cut at random bit positions: the stitched
+    bytes are the original stream, and the byte ranges of the Huffman stage tile it exactly"""
+    from imageencoder_b200.parallel import merge_shard_into, place_shards, shard_byte_range, total_bytes
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        world = int(rng.integers(1, 7))
+        nbits = int(rng.integers(200 * world, 6000))
+        bits = rng.integers(0, 2, nbits).astype(np.uint8)
+        cuts = np.sort(rng.choice(np.arange(1, nbits), size=world - 1, replace=False)) if world > 1 else np.array([], int)
+        edges = [0, *[int(c) for c in cuts], nbits]
+        totals = [edges[i + 1] - edges[i] for i in range(world)]
+        pl = place_shards(totals)
+        stream = bytearray()
+        for r in range(world):
+            assert pl[r].global_bit == edges[r]
+            merge_shard_into(stream, _aligned_shard(bits[edges[r]:edges[r + 1]], pl[r].shift), pl[r])
+        want = np.packbits(np.concatenate([bits, np.zeros((-nbits) % 8, np.uint8)])).tobytes()
+        assert bytes(stream[: total_bytes(pl)]) == want
+        ranges = [shard_byte_range(pl, r) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(want)
+        assert all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+        assert all(b1 >= b0 for b0, b1 in ranges)
