@@ -97,7 +97,7 @@ __device__ __noinline__ int exact_coefficient(const ExactCtx p, unsigned gb, int
 
 constexpr int kQueueCap = 128;        // guard-band fallback entries per tile handled by the CTA-wide queue
 
-template <int N, int BPL, bool PF, bool FAST>
+template <int N, int BPL, bool PF, bool FAST, int VAR = 0>
 __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF ? 6 : 2)) encode_tiles_kernel(const EncodeParams p) {
     constexpr int NN = N * N;
     constexpr int TB = kThreads * BPL;            // blocks per tile
@@ -165,6 +165,35 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
             ry = res_coord_i[2 * mb + 1] + (int)(byi & 3) * 4;
         }
         if (FAST) {
+            unsigned long long near = 0;
+            if (VAR == 2 && !PF) {
+            // variant 2: the whole block is loaded first, rows 2r and 2r+1 are converted and transformed as f32x2 pairs
+            unsigned raw[N][N / 4];
+#pragma unroll
+            for (int y = 0; y < N; y++) {
+                const uint8_t *row = src + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N;
+                if (N == 8) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row));
+                    raw[y][0] = v.x; raw[y][N / 4 - 1] = v.y;
+                } else {
+                    raw[y][0] = __ldg(reinterpret_cast<const unsigned *>(row));
+                }
+            }
+            float2 x2[NN / 2], y2[NN / 2];
+#pragma unroll
+            for (int r2 = 0; r2 < N / 2; r2++)
+#pragma unroll
+                for (int k = 0; k < N; k++) {
+                    // bytes -> floats by planting them in the mantissa of 2^23, then one packed subtraction of 2^23 + 128 (exact)
+                    const float a = __uint_as_float(__byte_perm(raw[2 * r2][k >> 2], 0x4B000000u, 0x7650u | (unsigned)(k & 3)));
+                    const float b = __uint_as_float(__byte_perm(raw[2 * r2 + 1][k >> 2], 0x4B000000u, 0x7650u | (unsigned)(k & 3)));
+                    x2[r2 * N + k] = lean::add2(make_float2(a, b), make_float2(-8388736.0f, -8388736.0f));
+                }
+            lean::fdct2d_packed<N>(x2, y2);
+            unsigned nlo, nhi;
+            lean::quantise_block_packed<N>(y2, p.fq, p.dc_den2, p.dc_rcp, reinterpret_cast<unsigned *>(cf), nlo, nhi, r_orseg[r], r_orbits[r]);
+            near = ((unsigned long long)nhi << 32) | nlo;
+            } else {
             float x[NN];
 #pragma unroll
             for (int y = 0; y < N; y++) {
@@ -185,7 +214,16 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
                 }
             }
             fdct2d_fast<N>(x);
-            unsigned long long near = 0;
+            if (VAR == 1) {
+                // variant 1 (transform_fast.cuh, lean::): raster pairs quantised with packed f32x2 operations, zigzag pairs
+                // stored as words, max bits_needed from a packed running max / min -- same values, fewer instructions
+                float2 y2[NN / 2];
+#pragma unroll
+                for (int i = 0; i < NN / 2; i++) y2[i] = make_float2(x[2 * i], x[2 * i + 1]);
+                unsigned nlo, nhi;
+                lean::quantise_block_packed<N>(y2, p.fq, p.dc_den2, p.dc_rcp, reinterpret_cast<unsigned *>(cf), nlo, nhi, r_orseg[r], r_orbits[r]);
+                near = ((unsigned long long)nhi << 32) | nlo;
+            } else
 #pragma unroll
             for (int uv = 0; uv < NN; uv++) {
                 int q;
@@ -212,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
                 cf[k] = (short)q;
                 r_orseg[r][k >> 3] |= (unsigned)q;                          // non-zero detection per zigzag segment
                 r_orbits[r] |= (unsigned)(q ^ (q >> 31));                   // bits_needed of the widest value (-1 -> 0)
+            }
             }
             if (near) {
                 // hand the guard-band coefficients to the CTA-wide queue (filled lanes instead of one lane per warp)
@@ -670,7 +709,7 @@ int launch_tile_totals(const unsigned *tile_bits, unsigned ntiles, unsigned imag
     return IE_OK;
 }
 
-template <int N, int BPL, bool PF, bool FAST>
+template <int N, int BPL, bool PF, bool FAST, int VAR = 0>
 static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t stream) {
     constexpr int TB = kThreads * BPL;
     constexpr int STRIDE = N * N + 2;
@@ -679,11 +718,11 @@ static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t strea
                         (kQueueCap + TB + (kQueueCap + TB) / 2) * sizeof(unsigned) + 3 * TB;
     static bool configured = false;
     if (!configured) {
-        IE_CUDA(cudaFuncSetAttribute(encode_tiles_kernel<N, BPL, PF, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IE_CUDA(cudaFuncSetAttribute(encode_tiles_kernel<N, BPL, PF, FAST, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid(p.tiles_per_image, images);
-    encode_tiles_kernel<N, BPL, PF, FAST><<<grid, kThreads, smem, stream>>>(p);
+    encode_tiles_kernel<N, BPL, PF, FAST, VAR><<<grid, kThreads, smem, stream>>>(p);
     count_launch();
     if (!p.bits_only && p.phase == 0) return launch_tile_copyout(p, images, stream);
     IE_CUDA(cudaGetLastError());
@@ -697,9 +736,18 @@ size_t encode_tile_slot_bytes(int N) {
 }
 
 std::atomic<int> g_exact_transform{0};
+std::atomic<int> g_encode_variant{0};      // experimental instantiations of the tile kernel (same results; A/B timing)
 
 int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream) {
     const bool exact = g_exact_transform.load() != 0;
+    const int var = exact ? 0 : g_encode_variant.load();
+    if (var == 1) {
+        if (N == 8) return launch_cfg<8, 1, false, true, 1>(p, images, stream);
+        if (N == 4) return launch_cfg<4, 4, false, true, 1>(p, images, stream);
+    } else if (var == 2) {
+        if (N == 8) return launch_cfg<8, 1, false, true, 2>(p, images, stream);
+        if (N == 4) return launch_cfg<4, 4, false, true, 2>(p, images, stream);
+    }
     if (N == 8) return exact ? launch_cfg<8, 1, false, false>(p, images, stream) : launch_cfg<8, 1, false, true>(p, images, stream);
     if (N == 4) return exact ? launch_cfg<4, 4, false, false>(p, images, stream) : launch_cfg<4, 4, false, true>(p, images, stream);
     set_error("block size must be 4 or 8");

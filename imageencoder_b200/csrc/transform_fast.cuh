@@ -20,6 +20,21 @@
 #pragma once
 #include "common.cuh"
 #include "transform.cuh"
+#include <cmath>
+#include <cstring>
+#include <utility>
+
+// host + device code (the transform and quantisation arithmetic is also run on the CPU by tests/host/lean_check.cu)
+#if defined(__CUDACC__)
+#define IE_HD __host__ __device__ __forceinline__
+#else
+#define IE_HD inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define IE_UNROLL _Pragma("unroll")
+#else
+#define IE_UNROLL
+#endif
 
 namespace ie {
 
@@ -44,7 +59,7 @@ constexpr int kMagicBits = 0x4B400000;
 
 // unnormalised 8-point DCT-II: y[k] = sum_n x[n] cos((2n+1) k pi / 16), in place, stride `S` between elements
 template <int S>
-__device__ __forceinline__ void dct8_inplace(float *v) {
+IE_HD void dct8_inplace(float *v) {
     const float s0 = v[0 * S] + v[7 * S], d0 = v[0 * S] - v[7 * S];
     const float s1 = v[1 * S] + v[6 * S], d1 = v[1 * S] - v[6 * S];
     const float s2 = v[2 * S] + v[5 * S], d2 = v[2 * S] - v[5 * S];
@@ -62,7 +77,7 @@ __device__ __forceinline__ void dct8_inplace(float *v) {
 
 // unnormalised 4-point DCT-II: y[k] = sum_n x[n] cos((2n+1) k pi / 8)
 template <int S>
-__device__ __forceinline__ void dct4_inplace(float *v) {
+IE_HD void dct4_inplace(float *v) {
     const float s0 = v[0 * S] + v[3 * S], d0 = v[0 * S] - v[3 * S];
     const float s1 = v[1 * S] + v[2 * S], d1 = v[1 * S] - v[2 * S];
     v[0 * S] = s0 + s1;
@@ -73,7 +88,7 @@ __device__ __forceinline__ void dct4_inplace(float *v) {
 
 // inverse of the above (unnormalised DCT-III): x[i] = sum_u y[u] cos((2i+1) u pi / 16)
 template <int S>
-__device__ __forceinline__ void idct8_inplace(float *v) {
+IE_HD void idct8_inplace(float *v) {
     const float y0 = v[0 * S], y1 = v[1 * S], y2 = v[2 * S], y3 = v[3 * S], y4 = v[4 * S], y5 = v[5 * S], y6 = v[6 * S], y7 = v[7 * S];
     const float t4 = y4 * IE_C4;
     const float a = y0 + t4, b = y0 - t4;
@@ -90,7 +105,7 @@ __device__ __forceinline__ void idct8_inplace(float *v) {
 }
 
 template <int S>
-__device__ __forceinline__ void idct4_inplace(float *v) {
+IE_HD void idct4_inplace(float *v) {
     const float y0 = v[0 * S], y1 = v[1 * S], y2 = v[2 * S], y3 = v[3 * S];
     const float t2 = y2 * IE_C4;
     const float a = y0 + t2, b = y0 - t2;
@@ -99,28 +114,280 @@ __device__ __forceinline__ void idct4_inplace(float *v) {
 }
 
 template <int N>
-__device__ __forceinline__ void idct2d_fast(float *x) {
-#pragma unroll
+IE_HD void idct2d_fast(float *x) {
+IE_UNROLL
     for (int u = 0; u < N; u++) {
         if (N == 8) idct8_inplace<1>(x + u * N); else idct4_inplace<1>(x + u * N);
     }
-#pragma unroll
+IE_UNROLL
     for (int j = 0; j < N; j++) {
         if (N == 8) idct8_inplace<N>(x + j); else idct4_inplace<N>(x + j);
     }
 }
 
 template <int N>
-__device__ __forceinline__ void fdct2d_fast(float *x) {
-#pragma unroll
+IE_HD void fdct2d_fast(float *x) {
+IE_UNROLL
     for (int i = 0; i < N; i++) {
         if (N == 8) dct8_inplace<1>(x + i * N); else dct4_inplace<1>(x + i * N);
     }
-#pragma unroll
+IE_UNROLL
     for (int j = 0; j < N; j++) {
         if (N == 8) dct8_inplace<N>(x + j); else dct4_inplace<N>(x + j);
     }
 }
 
 #endif
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Experimental instantiations of the tile kernel's per-block arithmetic (ie_set_option("encode_variant", 1 | 2); the
+// default path is untouched).  Same arithmetic as the default path of encode_tiles_kernel -- rn(q~) by the magic constant,
+// guard-band test, exact integer DC -- with fewer instructions around it:
+//   * two coefficients are quantised per packed f32x2 instruction (FFMA2 x3; every component is an individually rounded
+//     FP32 operation) and a zigzag pair goes to the staging area as ONE 32-bit word (PRMT of the two mantissas: the low
+//     16 bits of 1.5*2^23 + q ARE q in two's complement, no subtraction of the magic bits);
+//   * max bits_needed comes from a packed s16x2 running max / min of those words (VIMNMX3.S16x2, two words per
+//     instruction) instead of q ^ (q >> 31) per coefficient: bits_needed is monotone on either side of zero, so
+//     max_q bits_needed(q) = max(bits_needed(q_max), bits_needed(q_min))   (utils.hpp:226-243);
+//   * non-zero detection per 8-coefficient zigzag segment = OR of the segment's four pair words;
+//   * the guard-band mask is updated by one predicated instruction per coefficient;
+//   * variant 2: the factorised transform itself in packed operations (below).
+// Static SASS of encode_tiles_kernel<8,1>: 3528 instructions (default), 3272 (variant 1), 2984 (variant 2).
+// Host + device: tests/host/lean_check.cu runs exactly this code on the CPU against a transcription of the default path
+// (the device-only instructions have bit-identical host shims below).
+// ---------------------------------------------------------------------------------------------------------------------
+
+namespace lean {
+
+constexpr float kMagicF = 12582912.0f;         // 1.5 * 2^23
+
+// zigzag position -> raster index (algo.cpp:68-87), compile-time copies for the unrolled loops
+struct ZZ4 { static constexpr unsigned char t[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15}; };
+struct ZZ8 {
+    static constexpr unsigned char t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                            41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                            30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+};
+
+IE_HD unsigned f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    unsigned u; memcpy(&u, &f, 4); return u;
+#endif
+}
+// low halfword of a in the low half, low halfword of b in the high half
+IE_HD unsigned pack_lo16(unsigned a, unsigned b) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, 0x5410);
+#else
+    return (a & 0xffffu) | (b << 16);
+#endif
+}
+IE_HD unsigned max3_s16x2(unsigned a, unsigned b, unsigned c) {
+#if defined(__CUDA_ARCH__)
+    return __vimax3_s16x2(a, b, c);
+#else
+    auto mx = [](int x, int y, int z) { int m = x > y ? x : y; return m > z ? m : z; };
+    const int lo = mx((short)(a & 0xffff), (short)(b & 0xffff), (short)(c & 0xffff));
+    const int hi = mx((short)(a >> 16), (short)(b >> 16), (short)(c >> 16));
+    return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16);
+#endif
+}
+IE_HD unsigned min3_s16x2(unsigned a, unsigned b, unsigned c) {
+#if defined(__CUDA_ARCH__)
+    return __vimin3_s16x2(a, b, c);
+#else
+    auto mn = [](int x, int y, int z) { int m = x < y ? x : y; return m < z ? m : z; };
+    const int lo = mn((short)(a & 0xffff), (short)(b & 0xffff), (short)(c & 0xffff));
+    const int hi = mn((short)(a >> 16), (short)(b >> 16), (short)(c >> 16));
+    return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16);
+#endif
+}
+// mask |= bit if |d| >= thr   (one FSETP + one predicated LOP3)
+template <unsigned BIT>
+IE_HD void or_if_near(unsigned &mask, float d, float thr) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(mask) : "f"(fabsf(d)), "f"(thr), "n"(BIT));
+#else
+    if (fabsf(d) >= thr) mask |= BIT;
+#endif
+}
+
+// exact integer DC (see encode_tiles_kernel): q = round_half_away(S / (4 Q00)), S = the block's sample sum (an integer)
+IE_HD int dc_quant(float y0, int dc_den2, float dc_rcp) {
+    const int S = (int)y0;
+    const int n = S < 0 ? -S : S;
+    const int num = 2 * n + (dc_den2 >> 1);
+    int qq = (int)((float)num * dc_rcp);
+    const int rem = num - qq * dc_den2;
+    qq += (rem >= dc_den2) ? 1 : 0;
+    qq -= (rem < 0) ? 1 : 0;
+    return (S < 0) ? -qq : qq;
+}
+
+// running state of quantise_block
+struct QuantAcc {
+    unsigned near_lo, near_hi;      // guard-band mask, bit uv (raster)
+    unsigned mx, mn;                // packed s16x2 running max (halves >= 0) / min (halves <= 0)
+    unsigned wprev;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant 2: the factorised transform itself in packed f32x2 operations (FADD2 / FMUL2 / FFMA2: two independent,
+// individually rounded FP32 operations per instruction; constants are immediates).  The operation DAG is exactly the one of
+// dct8_inplace / dct4_inplace above, so every output is bit-identical to the default fast path's.
+//   pass 1 (along a row):     rows 2r and 2r+1 ride in the two halves -> N/2 packed 1-D transforms;
+//   pass 2 (along a column):  the first butterfly stage is scalar (it reads single halves of the pass-1 pairs and may write
+//                             its results wherever it likes, i.e. into pairs made of columns 2c and 2c+1), the rest is packed;
+//   quantisation:             on the raster pairs (u, 2c), (u, 2c+1) pass 2 leaves behind; the zigzag pair words are then
+//                             formed by PRMT from any two of the results.
+// ---------------------------------------------------------------------------------------------------------------------
+IE_HD float2 add2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+IE_HD float2 sub2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+IE_HD float2 mulc2(float2 a, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(a, make_float2(c, c));
+#else
+    return make_float2(a.x * c, a.y * c);
+#endif
+}
+IE_HD float2 fmac2(float2 a, float c, float2 b) {      // a * c + b
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, make_float2(c, c), b);
+#else
+    return make_float2(fmaf(a.x, c, b.x), fmaf(a.y, c, b.y));
+#endif
+}
+
+// what follows the first butterfly stage of dct8_inplace / dct4_inplace: s[i] = v[i] + v[N-1-i], d[i] = v[i] - v[N-1-i]
+template <int N>
+IE_HD void dct_tail2(const float2 *s, const float2 *d, float2 *o) {
+    if (N == 8) {
+        const float2 t0 = add2(s[0], s[3]), t1 = add2(s[1], s[2]), t2 = sub2(s[0], s[3]), t3 = sub2(s[1], s[2]);
+        o[0] = add2(t0, t1);
+        o[4] = mulc2(sub2(t0, t1), IE_C4);
+        o[2] = fmac2(t2, IE_C2, mulc2(t3, IE_C6));
+        o[6] = fmac2(t2, IE_C6, mulc2(t3, -IE_C2));
+        o[1] = fmac2(d[0], IE_C1, fmac2(d[1], IE_C3, fmac2(d[2], IE_C5, mulc2(d[3], IE_C7))));
+        o[3] = fmac2(d[0], IE_C3, fmac2(d[1], -IE_C7, fmac2(d[2], -IE_C1, mulc2(d[3], -IE_C5))));
+        o[5] = fmac2(d[0], IE_C5, fmac2(d[1], -IE_C1, fmac2(d[2], IE_C7, mulc2(d[3], IE_C3))));
+        o[7] = fmac2(d[0], IE_C7, fmac2(d[1], -IE_C5, fmac2(d[2], IE_C3, mulc2(d[3], -IE_C1))));
+    } else {
+        o[0] = add2(s[0], s[1]);
+        o[2] = mulc2(sub2(s[0], s[1]), IE_C4);
+        o[1] = fmac2(d[0], IE_C2, mulc2(d[1], IE_C6));
+        o[3] = fmac2(d[0], IE_C6, mulc2(d[1], -IE_C2));
+    }
+}
+
+// X2[r * N + k] = (x[2r][k], x[2r+1][k]): the block's samples, two rows per pair.
+// Y2[u * (N/2) + c] = (Y[u][2c], Y[u][2c+1]), the unnormalised 2-D DCT outputs.
+template <int N>
+IE_HD void fdct2d_packed(const float2 *X2, float2 *Y2) {
+    constexpr int H = N / 2;
+    float2 T2[H][N];                                     // T2[r][v] = (T[2r][v], T[2r+1][v])
+IE_UNROLL
+    for (int r = 0; r < H; r++) {
+        float2 s[H], d[H];
+IE_UNROLL
+        for (int i = 0; i < H; i++) {
+            const float2 a = X2[r * N + i], b = X2[r * N + (N - 1 - i)];
+            s[i] = add2(a, b);
+            d[i] = sub2(a, b);
+        }
+        dct_tail2<N>(s, d, T2[r]);
+    }
+IE_UNROLL
+    for (int c = 0; c < H; c++) {
+        float2 s[H], d[H], o[N];
+IE_UNROLL
+        for (int i = 0; i < H; i++) {
+            const int j = N - 1 - i;
+            // scalar butterflies on single halves of the pass-1 pairs; the results pair up columns 2c and 2c+1
+            const float2 pi0 = T2[i >> 1][2 * c], pi1 = T2[i >> 1][2 * c + 1], pj0 = T2[j >> 1][2 * c], pj1 = T2[j >> 1][2 * c + 1];
+            const float ti0 = (i & 1) ? pi0.y : pi0.x, ti1 = (i & 1) ? pi1.y : pi1.x;
+            const float tj0 = (j & 1) ? pj0.y : pj0.x, tj1 = (j & 1) ? pj1.y : pj1.x;
+            s[i] = make_float2(ti0 + tj0, ti1 + tj1);
+            d[i] = make_float2(ti0 - tj0, ti1 - tj1);
+        }
+        dct_tail2<N>(s, d, o);
+IE_UNROLL
+        for (int u = 0; u < N; u++) Y2[u * H + c] = o[u];
+    }
+}
+
+// raster pair P = coefficients 2P, 2P+1: bits[] receive 1.5*2^23 + q as raw words (low 16 bits = q)
+template <int N, int P>
+IE_HD void quantise_raster_pair(const float2 *Y2, const FastQuant &fq, int dc_den2, float dc_rcp, unsigned *bits, QuantAcc &a) {
+    constexpr int ua = 2 * P, ub = 2 * P + 1;
+    const float2 yy = Y2[P];
+#if defined(__CUDA_ARCH__)
+    const float2 kk = make_float2(fq.k[ua], fq.k[ub]);
+    const float2 rr = __ffma2_rn(yy, kk, make_float2(kMagicF, kMagicF));
+    const float2 nrf = __ffma2_rn(rr, make_float2(-1.0f, -1.0f), make_float2(kMagicF, kMagicF));      // -(rr - magic), exact
+    const float2 dd = __ffma2_rn(yy, kk, nrf);
+    const float rra = rr.x, rrb = rr.y, da = dd.x, db = dd.y;
+#else
+    const float rra = fmaf(yy.x, fq.k[ua], kMagicF), rrb = fmaf(yy.y, fq.k[ub], kMagicF);
+    const float da = fmaf(yy.x, fq.k[ua], -(rra - kMagicF)), db = fmaf(yy.y, fq.k[ub], -(rrb - kMagicF));
+#endif
+    if (P == 0) {
+        bits[0] = (unsigned)dc_quant(yy.x, dc_den2, dc_rcp);
+    } else {
+        bits[ua] = f2u(rra);
+        or_if_near<(1u << (ua & 31))>(ua < 32 ? a.near_lo : a.near_hi, da, fq.thr[ua]);
+    }
+    bits[ub] = f2u(rrb);
+    or_if_near<(1u << (ub & 31))>(ub < 32 ? a.near_lo : a.near_hi, db, fq.thr[ub]);
+}
+
+template <int N, int M>
+IE_HD void pack_zigzag_pair(const unsigned *bits, unsigned *cfw, unsigned *orseg, QuantAcc &a) {
+    constexpr int ua = (N == 8) ? ZZ8::t[2 * M] : ZZ4::t[2 * M];
+    constexpr int ub = (N == 8) ? ZZ8::t[2 * M + 1] : ZZ4::t[2 * M + 1];
+    const unsigned w = pack_lo16(bits[ua], bits[ub]);
+    cfw[M] = w;
+    if ((M & 3) == 0) orseg[M >> 2] = w; else orseg[M >> 2] |= w;
+    if (M & 1) { a.mx = max3_s16x2(a.mx, a.wprev, w); a.mn = min3_s16x2(a.mn, a.wprev, w); }
+    a.wprev = w;
+}
+
+template <int N, int... P>
+IE_HD void quantise_block_packed_impl(const float2 *Y2, const FastQuant &fq, int dc_den2, float dc_rcp, unsigned *cfw, unsigned *orseg,
+                                      QuantAcc &a, std::integer_sequence<int, P...>) {
+    unsigned bits[N * N];
+    (quantise_raster_pair<N, P>(Y2, fq, dc_den2, dc_rcp, bits, a), ...);
+    (pack_zigzag_pair<N, P>(bits, cfw, orseg, a), ...);
+}
+
+// Y2[P] = (Y[2P], Y[2P+1]): the NN unnormalised 2-D DCT outputs of the block as raster pairs.  Writes the NN/2 zigzag pair
+// words to cfw, returns the guard-band mask (bit uv, raster) in near_lo/near_hi, the per-segment OR words in orseg[NN/8]
+// (non-zero <=> the segment holds a non-zero coefficient) and `orbits` with bit_length(orbits) + 1 = max bits_needed over
+// the block (0 -> all zero).
+template <int N>
+IE_HD void quantise_block_packed(const float2 *Y2, const FastQuant &fq, int dc_den2, float dc_rcp, unsigned *cfw, unsigned &near_lo,
+                                 unsigned &near_hi, unsigned *orseg, unsigned &orbits) {
+    QuantAcc a;
+    a.near_lo = 0; a.near_hi = 0; a.mx = 0; a.mn = 0; a.wprev = 0;
+    quantise_block_packed_impl<N>(Y2, fq, dc_den2, dc_rcp, cfw, orseg, a, std::make_integer_sequence<int, N * N / 2>{});
+    near_lo = a.near_lo; near_hi = a.near_hi;
+    const int hmx = (short)(a.mx >> 16), lmx = (short)(a.mx & 0xffffu), hmn = (short)(a.mn >> 16), lmn = (short)(a.mn & 0xffffu);
+    const int qmax = hmx > lmx ? hmx : lmx, qmin = hmn < lmn ? hmn : lmn;
+    orbits = (unsigned)qmax | (unsigned)(qmin ^ (qmin >> 31));
+}
+
+}  // namespace lean
 }  // namespace ie

@@ -1,0 +1,63 @@
+"""Runs in its own process (tests/test_zz_variants_gpu.py): encodes with ie_set_option("encode_variant", V) and compares the
+stream with the default kernel's and with the CPU oracle's.  Exit code 0 = identical."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def main(variant: int) -> int:
+    import imageencoder_b200 as ie
+    import oracle
+    from imageencoder_b200 import _lib
+    from imageencoder_b200.synth import synth_image, synth_video
+
+    L = ie.lib()
+    _lib.check(L.ie_init(0))
+    inputs = ROOT / "tests" / "golden" / "inputs"
+    rng = np.random.default_rng(5)
+    bad = 0
+    for mat in ("matrix8_1.txt", "matrix8_2.txt", "matrix.txt", "matrix4_2.txt"):
+        q = ie.read_matrix(inputs / mat)
+        n = q.shape[0]
+        cases = [("synth", synth_image(512, 384, 21)), ("flat", synth_image(512, 384, 22, flat=True)),
+                 ("noise", rng.integers(0, 256, (128, 96)).astype(np.uint8)),
+                 ("checker", ((np.indices((64, 64)).sum(0) & 1) * 255).astype(np.uint8)),
+                 ("all128", np.full((64, 64), 128, np.uint8)), ("extremes", (rng.integers(0, 2, (64, 128)) * 255).astype(np.uint8))]
+        for qq, qname in ((q, mat), (np.ones_like(q), "ones")):
+            for name, img in cases:
+                h, w = img.shape
+                for rle in (True, False):
+                    _lib.check(L.ie_set_option(b"encode_variant", 0))
+                    base = ie.encode_image(img, w, h, qq, rle, False)
+                    _lib.check(L.ie_set_option(b"encode_variant", variant))
+                    got = ie.encode_image(img, w, h, qq, rle, False)
+                    want = oracle.image_encode(img, w, h, n, qq, rle, False)
+                    if got != base or got != want:
+                        print(f"variant {variant}: {qname} {name} rle={rle}: differs (default==oracle: {base == want})")
+                        bad += 1
+    # larger image: the variant against the default kernel only (the oracle would take too long)
+    q = ie.read_matrix(inputs / "matrix8_1.txt")
+    img = synth_image(4096, 2048, 1234)
+    _lib.check(L.ie_set_option(b"encode_variant", 0))
+    base = ie.encode_image(img, 4096, 2048, q, True, False)
+    _lib.check(L.ie_set_option(b"encode_variant", variant))
+    if ie.encode_image(img, 4096, 2048, q, True, False) != base:
+        print(f"variant {variant}: 4096x2048 differs from the default kernel")
+        bad += 1
+    # video I-frames go through the same kernel (4x4)
+    q = ie.read_matrix(inputs / "matrix.txt")
+    yuv = synth_video(64, 48, 5)
+    if ie.encode_video(yuv, 64, 48, q, True, 3, 16, False) != oracle.video_encode(yuv, 64, 48, q, True, 3, 16, False):
+        print(f"variant {variant}: video stream differs")
+        bad += 1
+    _lib.check(L.ie_set_option(b"encode_variant", 0))
+    print(f"variant {variant}: {'ok' if not bad else f'{bad} mismatches'}")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(int(sys.argv[1])))

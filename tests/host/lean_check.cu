@@ -1,0 +1,211 @@
+// CPU check of the encode-variant arithmetic (imageencoder_b200/csrc/transform_fast.cuh, namespace ie::lean).
+// Test infrastructure, not product code.  Compiled with nvcc as HOST code: every device-only instruction used by the variants
+// (FFMA2/FADD2/FMUL2, PRMT, VIMNMX3.S16x2, the predicated OR) has a bit-identical host shim in the header, so this runs the
+// same C++ the kernels run, lane by lane, against a transcription of the default path of encode_tiles_kernel
+// (encode_image.cu, "phase 1": quantise loop) on millions of blocks:
+//   * variant 1 (scalar transform + lean::quantise_block_packed): staged zigzag coefficients, guard-band mask, max
+//     bits_needed, segment non-zero flags
+//   * variant 2 (lean::fdct2d_packed + quantise_block_packed): additionally the packed transform, bit for bit
+// and the integer DC rounding against round_half_away(S / (4 Q00)) in exact integer arithmetic.
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <random>
+#include <vector>
+
+#include "../../imageencoder_b200/csrc/transform_fast.cuh"
+
+using namespace ie;
+
+static const unsigned char kZigzagInv4[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};
+static const unsigned char kZigzagInv8[64] = {
+    0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30, 41, 43, 9,  11, 18, 24, 31, 40, 44, 53,
+    10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+
+// core.cu: make_fast_quant
+static void make_fq(FastQuant &fq, const uint16_t *quant, int N, double max_abs_sample) {
+    memset(&fq, 0, sizeof fq);
+    for (int u = 0; u < N; u++)
+        for (int v = 0; v < N; v++) {
+            const double cu = (u == 0) ? 0.5 : M_SQRT1_2, cv = (v == 0) ? 0.5 : M_SQRT1_2;
+            const double k = cu * cv / (double)quant[u * N + v];
+            const double delta = 1.25 * (768.0 + 64.0) * ldexp(1.0, -24) * max_abs_sample * k + 1e-6;
+            fq.k[u * N + v] = (float)k;
+            double thr = 0.5 - delta;
+            if (thr < 0.0) thr = 0.0;
+            fq.thr[u * N + v] = nextafterf((float)thr, 0.0f);
+        }
+    for (int i = N * N; i < kMaxNN; i++) { fq.k[i] = 0.f; fq.thr[i] = 1.f; }
+}
+
+static int bitlen(unsigned v) { int n = 0; while (v) { n++; v >>= 1; } return n; }
+
+struct Ref {
+    short cf[64];
+    unsigned long long near;
+    unsigned orbits;
+    unsigned orseg[8];
+};
+
+// transcription of the default path (encode_image.cu, quantise loop of encode_tiles_kernel<N, BPL, PF, FAST=true, VAR=0>)
+template <int N>
+static void ref_quantise(const float *y, const FastQuant &fq, int dc_den2, float dc_rcp, Ref &r) {
+    constexpr int NN = N * N;
+    constexpr float kMagic = 12582912.0f;
+    constexpr int kMagicBits = 0x4B400000;
+    r.near = 0; r.orbits = 0;
+    for (int s = 0; s < 8; s++) r.orseg[s] = 0;
+    for (int uv = 0; uv < NN; uv++) {
+        int q;
+        if (uv == 0) {
+            const int S = (int)y[0];
+            const int n = abs(S);
+            const int D2 = dc_den2;
+            const int num = 2 * n + (D2 >> 1);
+            int qq = (int)((float)num * dc_rcp);
+            const int rem = num - qq * D2;
+            qq += (rem >= D2) ? 1 : 0;
+            qq -= (rem < 0) ? 1 : 0;
+            q = (S < 0) ? -qq : qq;
+        } else {
+            const float rr = fmaf(y[uv], fq.k[uv], kMagic);
+            const float rf = rr - kMagic;
+            const float d = fmaf(y[uv], fq.k[uv], -rf);
+            if (fabsf(d) >= fq.thr[uv]) r.near |= 1ull << uv;
+            unsigned b; memcpy(&b, &rr, 4);
+            q = (int)b - kMagicBits;
+        }
+        const int k = (N == 8) ? kZigzagInv8[uv] : kZigzagInv4[uv];
+        r.cf[k] = (short)q;
+        r.orseg[k >> 3] |= (unsigned)q;
+        r.orbits |= (unsigned)(q ^ (q >> 31));
+    }
+}
+
+static long long g_fail = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { if (g_fail < 20) { printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } g_fail++; } } while (0)
+
+template <int N>
+static void check_block(const uint8_t *px, const uint16_t *quant, const FastQuant &fq, long long id) {
+    constexpr int NN = N * N;
+    float x[NN], y[NN];
+    for (int i = 0; i < NN; i++) x[i] = (float)px[i] - 128.0f;
+    memcpy(y, x, sizeof y);
+    fdct2d_fast<N>(y);
+    const int dc_den2 = 8 * (int)quant[0];
+    const float dc_rcp = 1.0f / (float)dc_den2;
+    Ref r;
+    ref_quantise<N>(y, fq, dc_den2, dc_rcp, r);
+
+    // DC against exact integer arithmetic: round_half_away(S / (4 Q00))
+    {
+        long long S = 0;
+        for (int i = 0; i < NN; i++) S += (int)px[i] - 128;
+        const long long D = 4LL * quant[0], a = S < 0 ? -S : S;
+        long long qq = (2 * a + D) / (2 * D);
+        if (S < 0) qq = -qq;
+        CHECK(r.cf[0] == (short)qq, "block %lld: DC %d, exact integer rounding gives %lld", id, r.cf[0], qq);
+    }
+
+    // ---- variant 1
+    {
+        float2 y2[NN / 2];
+        for (int i = 0; i < NN / 2; i++) y2[i] = make_float2(y[2 * i], y[2 * i + 1]);
+        unsigned cfw[NN / 2], nlo, nhi, orseg[8] = {0}, orbits;
+        lean::quantise_block_packed<N>(y2, fq, dc_den2, dc_rcp, cfw, nlo, nhi, orseg, orbits);
+        const unsigned long long near = ((unsigned long long)nhi << 32) | nlo;
+        CHECK(near == r.near, "block %lld v1: near mask %llx != %llx", id, near, r.near);
+        for (int k = 0; k < NN; k++) {
+            const short got = (short)((cfw[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+            CHECK(got == r.cf[k], "block %lld v1: zigzag %d: %d != %d", id, k, got, r.cf[k]);
+        }
+        CHECK(bitlen(orbits) == bitlen(r.orbits), "block %lld v1: orbits %x vs %x", id, orbits, r.orbits);
+        for (int s = 0; s < NN / 8; s++) CHECK((orseg[s] != 0) == (r.orseg[s] != 0), "block %lld v1: segment %d flag", id, s);
+    }
+    // ---- variant 2
+    {
+        float2 x2[NN / 2], y2[NN / 2];
+        for (int rr = 0; rr < N / 2; rr++)
+            for (int k = 0; k < N; k++) x2[rr * N + k] = make_float2(x[(2 * rr) * N + k], x[(2 * rr + 1) * N + k]);
+        lean::fdct2d_packed<N>(x2, y2);
+        for (int u = 0; u < N; u++)
+            for (int c = 0; c < N / 2; c++) {
+                const float2 v = y2[u * (N / 2) + c];
+                CHECK(memcmp(&v.x, &y[u * N + 2 * c], 4) == 0 && memcmp(&v.y, &y[u * N + 2 * c + 1], 4) == 0,
+                      "block %lld v2: transform output (%d,%d) differs: %a %a vs %a %a", id, u, 2 * c, v.x, v.y, y[u * N + 2 * c], y[u * N + 2 * c + 1]);
+            }
+        unsigned cfw[NN / 2], nlo, nhi, orseg[8] = {0}, orbits;
+        lean::quantise_block_packed<N>(y2, fq, dc_den2, dc_rcp, cfw, nlo, nhi, orseg, orbits);
+        const unsigned long long near = ((unsigned long long)nhi << 32) | nlo;
+        CHECK(near == r.near, "block %lld v2: near mask %llx != %llx", id, near, r.near);
+        for (int k = 0; k < NN; k++) {
+            const short got = (short)((cfw[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+            CHECK(got == r.cf[k], "block %lld v2: zigzag %d: %d != %d", id, k, got, r.cf[k]);
+        }
+        CHECK(bitlen(orbits) == bitlen(r.orbits), "block %lld v2: orbits %x vs %x", id, orbits, r.orbits);
+        for (int s = 0; s < NN / 8; s++) CHECK((orseg[s] != 0) == (r.orseg[s] != 0), "block %lld v2: segment %d flag", id, s);
+    }
+}
+
+template <int N>
+static long long run(long long nblocks, unsigned seed) {
+    constexpr int NN = N * N;
+    std::mt19937 rng(seed);
+    static const unsigned char zz4[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+    unsigned char zz[64];
+    for (int uv = 0; uv < NN; uv++) zz[(N == 8) ? kZigzagInv8[uv] : kZigzagInv4[uv]] = (unsigned char)uv;
+    if (N == 4) for (int i = 0; i < 16; i++) if (zz[i] != zz4[i]) { printf("zigzag table mismatch\n"); return 1; }
+    for (int i = 0; i < NN; i++) {
+        const int t = (N == 8) ? lean::ZZ8::t[i] : lean::ZZ4::t[i];
+        if (t != zz[i]) { printf("lean::ZZ%d::t[%d] = %d, expected %d\n", N, i, t, zz[i]); return 1; }
+    }
+    long long done = 0;
+    for (int qm = 0; qm < 6; qm++) {
+        uint16_t quant[64];
+        for (int i = 0; i < NN; i++) {
+            const int u = i / N, v = i % N;
+            switch (qm) {
+                case 0: quant[i] = 1; break;                                        // largest coefficients
+                case 1: quant[i] = (uint16_t)(2 + 3 * (u + v)); break;              // JPEG-like ramp
+                case 2: quant[i] = (uint16_t)(16 + 11 * u * v + 7 * (u + v)); break;
+                case 3: quant[i] = 255; break;
+                case 4: quant[i] = (uint16_t)(1 + (rng() % 64)); break;
+                default: quant[i] = (uint16_t)((i == 0) ? 3 : 2); break;            // odd DC divisor, many half-way cases
+            }
+        }
+        FastQuant fq;
+        make_fq(fq, quant, N, 128.0);
+        for (long long b = 0; b < nblocks; b++) {
+            uint8_t px[NN];
+            const int mode = (int)(rng() % 6);
+            const int base = (int)(rng() % 256), amp = (int)(rng() % 64);
+            const int gx = (int)(rng() % 17) - 8, gy = (int)(rng() % 17) - 8;
+            for (int i = 0; i < NN; i++) {
+                const int yy = i / N, xx = i % N;
+                int v;
+                switch (mode) {
+                    case 0: v = (int)(rng() % 256); break;                                         // noise
+                    case 1: v = base + gx * xx + gy * yy + (int)(rng() % (amp + 1)) - amp / 2; break;   // gradient + noise
+                    case 2: v = base + ((int)(rng() % 3) - 1); break;                              // nearly flat
+                    case 3: v = ((xx + yy) & 1) ? 255 : 0; break;                                  // checkerboard (extreme AC)
+                    case 4: v = (rng() & 1) ? 255 : 0; break;                                      // random extremes
+                    default: v = base; break;                                                      // constant (all AC zero)
+                }
+                px[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+            check_block<N>(px, quant, fq, done);
+            done++;
+        }
+    }
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    const long long n = (argc > 1) ? atoll(argv[1]) : 200000;
+    if (run<8>(n, 12345u) || run<4>(n, 54321u)) return 2;
+    if (g_fail) { printf("lean_check: %lld failures\n", g_fail); return 1; }
+    printf("lean_check: ok (%lld blocks per block size, 6 quant matrices each, variants 1 and 2)\n", n * 6);
+    return 0;
+}
