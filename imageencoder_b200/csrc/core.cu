@@ -13,6 +13,7 @@ namespace ie {
 
 extern std::atomic<int> g_exact_transform;   // encode_image.cu
 extern std::atomic<int> g_encode_variant;
+extern std::atomic<int> g_copyout_variant;
 static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
 
@@ -209,8 +210,13 @@ uint64_t ie_kernel_launch_count(void) { return ie::g_launches.load(); }
 int ie_set_option(const char *name, int value) {
     if (name && !strcmp(name, "exact_transform")) { ie::g_exact_transform.store(value); return IE_OK; }
     if (name && !strcmp(name, "encode_variant")) {
-        if (value < 0 || value > 2) { ie::set_error("encode_variant: 0 (default), 1 (lean quantise) or 2 (1 + packed f32x2 transform)"); return IE_EINVAL; }
+        if (value < 0 || value > 2) { ie::set_error("encode_variant: 0 (scalar kernel), 1 (lean quantise) or 2 (1 + packed f32x2 transform, the default)"); return IE_EINVAL; }
         ie::g_encode_variant.store(value);
+        return IE_OK;
+    }
+    if (name && !strcmp(name, "copyout_variant")) {
+        if (value < 0 || value > 2) { ie::set_error("copyout_variant: 0 (default), 1 (short path for interior chunks) or 2 (1 + four chunks in flight)"); return IE_EINVAL; }
+        ie::g_copyout_variant.store(value);
         return IE_OK;
     }
     ie::set_error("unknown option");

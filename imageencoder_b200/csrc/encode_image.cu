@@ -667,6 +667,144 @@ __global__ void __launch_bounds__(kThreads) tile_copyout_kernel(const EncodePara
     }
 }
 
+// Copy-out variant 1 (ie_set_option("copyout_variant", 1)): same result as tile_copyout_kernel, with a short path for the
+// chunks that lie inside one tile image and inside the group (all but ~1 %): 32-bit positions, a 3-step search over the
+// group's <= 8 tile offsets, five unconditional word loads (a word past the tile's last one is only ever read when the
+// funnel shift ignores it; the slot has two chunks of slack), funnel shifts, one 128-bit store.  Every other chunk -- first
+// and last of the group, chunks that span two tiles -- takes the generic path of tile_write_chunks, chunk by chunk.
+// U = chunks per thread in flight (copyout_variant 1: U = 1, 2: U = 4).
+template <int U>
+__global__ void __launch_bounds__(kThreads) tile_copyout_fast_kernel(const EncodeParams p) {
+    __shared__ unsigned long long s_part[kThreads / 32];
+    __shared__ unsigned s_goff[kTilesPerGroup + 1];
+    pdl_wait();
+    const unsigned img = blockIdx.y, ntiles = p.tiles_per_image;
+    const unsigned t0 = blockIdx.x * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
+    const unsigned *tb = p.tile_bits + (size_t)img * ntiles;
+    unsigned long long sum = 0;
+    if ((reinterpret_cast<size_t>(tb) & 15) == 0) {
+        // earlier tiles' totals: 128-bit loads (t0 is a multiple of 8)
+        const uint4 *tb4 = reinterpret_cast<const uint4 *>(tb);
+        for (unsigned i = threadIdx.x; i < t0 / 4; i += kThreads) {
+            const uint4 v = __ldg(tb4 + i);
+            sum += (unsigned long long)v.x + v.y + v.z + v.w;
+        }
+    } else {
+        for (unsigned i = threadIdx.x; i < t0; i += kThreads) sum += tb[i];
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = sum;
+    if (threadIdx.x < 32) {
+        const unsigned t = t0 + threadIdx.x;
+        const unsigned v = (t < t1) ? tb[t] : 0u;
+        unsigned inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)threadIdx.x >= d) inc += o; }
+        if (threadIdx.x < kTilesPerGroup) s_goff[threadIdx.x + 1] = inc;      // entries past the group's last tile repeat its end
+        if (threadIdx.x == 0) s_goff[0] = 0;
+    }
+    __syncthreads();
+    unsigned long long G = p.bit_base[img];
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) G += s_part[w];
+    ScanState st = p.scan;
+    st.bnd += (size_t)img * ntiles;
+    GroupStreamTiles g;
+    g.slots = p.tile_scratch + ((size_t)img * ntiles + t0) * p.slot_bytes;
+    g.slot_bytes = p.slot_bytes;
+    g.off = s_goff;
+    g.n = t1 - t0;
+    const unsigned T = s_goff[g.n];
+    uint8_t *out = p.out + (size_t)img * p.out_stride;
+    if (T != 0) {
+        const unsigned long long c0 = G / kChunkBits, c1 = (G + T - 1) / kChunkBits;
+        const unsigned nchunks = (unsigned)(c1 - c0) + 1u;
+        const int g0 = (int)(G % kChunkBits);
+        const bool first_group = (t0 == 0), last_group = (t1 == ntiles);
+        const bool head_shared = g0 != 0;
+        const bool tail_shared = ((G + T) % kChunkBits) != 0 && !last_group;
+        const unsigned slot_words = (unsigned)(p.slot_bytes / 4);
+        const unsigned *slot0 = reinterpret_cast<const unsigned *>(g.slots);
+        uint4 *dst0 = reinterpret_cast<uint4 *>(out) + c0;
+        const unsigned long long cap_chunks = p.out_cap / 16ull;
+        // U chunks per thread in flight: the positions of all U are resolved and their loads issued before the first is
+        // shifted and stored (a chunk's loads depend on its search, so one chunk at a time is one L2 round trip per chunk)
+        for (unsigned kb = threadIdx.x; kb < nchunks; kb += kThreads * U) {
+            unsigned w[U][5], sh[U];
+            bool fast[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned k = kb + (unsigned)u * kThreads;
+                const int ls = (int)(k * (unsigned)kChunkBits) - g0;          // group-local bit of the chunk's first bit
+                fast[u] = (k < nchunks) && (k != 0) && (k + 1 != nchunks) && (c0 + k < cap_chunks);
+                unsigned j = 0;
+                const unsigned lo = (unsigned)ls;                             // k != 0: ls > 0
+                if (fast[u]) {
+                    // s_goff is non-decreasing and has kTilesPerGroup + 1 valid entries (the tail repeats the group's end)
+                    if (s_goff[4] <= lo) j = 4;
+                    if (s_goff[j + 2] <= lo) j += 2;
+                    if (s_goff[j + 1] <= lo) j += 1;
+                    fast[u] = (j < g.n) && (lo + (unsigned)kChunkBits <= s_goff[j + 1]);   // the chunk ends inside tile j
+                }
+                if (fast[u]) {
+                    const unsigned tl = lo - s_goff[j];                       // tile-local bit
+                    sh[u] = tl & 31u;
+                    const unsigned *wp = slot0 + (size_t)j * slot_words + (tl >> 5);
+#pragma unroll
+                    for (int i = 0; i < 5; i++) w[u][i] = __ldg(wp + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned k = kb + (unsigned)u * kThreads;
+                if (k >= nchunks) break;
+                if (fast[u]) {
+                    uint4 o;
+                    o.x = __byte_perm(__funnelshift_l(w[u][1], w[u][0], sh[u]), 0, 0x0123);
+                    o.y = __byte_perm(__funnelshift_l(w[u][2], w[u][1], sh[u]), 0, 0x0123);
+                    o.z = __byte_perm(__funnelshift_l(w[u][3], w[u][2], sh[u]), 0, 0x0123);
+                    o.w = __byte_perm(__funnelshift_l(w[u][4], w[u][3], sh[u]), 0, 0x0123);
+                    dst0[k] = o;
+                    continue;
+                }
+                // generic path (tile_write_chunks, one chunk)
+                const int ls = (int)(k * (unsigned)kChunkBits) - g0;
+                const unsigned long long c = c0 + k;
+                uint4 v = gather_chunk(g, (long long)ls);
+                if ((c + 1) * 16ull > p.out_cap) { if (p.err) atomicExch(p.err, IE_ENOSPC); continue; }
+                uint4 *dst = reinterpret_cast<uint4 *>(out) + c;
+                const bool is_head = (k == 0) && head_shared;
+                const bool is_tail = (k + 1 == nchunks) && tail_shared;
+                if (is_head && first_group) {
+                    const uint4 o = *dst;
+                    v.x |= o.x; v.y |= o.y; v.z |= o.z; v.w |= o.w;
+                } else if (is_head || is_tail) {
+                    TileBoundary *bd = &st.bnd[is_head ? blockIdx.x - 1 : blockIdx.x];
+                    unsigned *dw = reinterpret_cast<unsigned *>(dst);
+                    const unsigned mine[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const unsigned long long old = atomicAdd(&bd->w[i], (1ull << 32) | (unsigned long long)mine[i]);
+                        if ((old >> 32) == 1ull) {
+                            dw[i] = (unsigned)old | mine[i];
+                            atomicExch(&bd->w[i], 0ull);
+                        }
+                    }
+                    continue;
+                }
+                *dst = v;
+            }
+        }
+    }
+    if (t1 == ntiles && threadIdx.x == 0) {
+        p.bit_counter[img] = G + T;
+        if (p.out_bits) p.out_bits[img] = G + T;
+    }
+}
+
+std::atomic<int> g_copyout_variant{0};
+
 int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t stream) {
     dim3 cgrid((p.tiles_per_image + kTilesPerGroup - 1) / kTilesPerGroup, images);
     // programmatic dependent launch: the copy-out grid is set up while the tile kernel drains and waits on the device
@@ -677,7 +815,10 @@ int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t str
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_kernel, p));
+    const int cv = g_copyout_variant.load();
+    if (cv == 1) IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_fast_kernel<1>, p));
+    else if (cv == 2) IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_fast_kernel<4>, p));
+    else IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_kernel, p));
     count_launch();
     IE_CUDA(cudaGetLastError());
     return IE_OK;
@@ -736,7 +877,10 @@ size_t encode_tile_slot_bytes(int N) {
 }
 
 std::atomic<int> g_exact_transform{0};
-std::atomic<int> g_encode_variant{0};      // experimental instantiations of the tile kernel (same results; A/B timing)
+// instantiation of the tile kernel for image blocks / I-frames: 2 = packed f32x2 transform + lean quantise bookkeeping
+// (transform_fast.cuh, lean::; the default since it measured 0.1298 -> 0.1119 ms on config 2, profiles/r1_ab_variants_v9.log),
+// 1 = lean quantise only, 0 = the scalar kernel of versions v0..v8 (kept for A/B and cross-checks)
+std::atomic<int> g_encode_variant{2};
 
 int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream) {
     const bool exact = g_exact_transform.load() != 0;

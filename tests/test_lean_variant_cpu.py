@@ -1,4 +1,4 @@
-"""CPU checks of the experimental encode variants (ie_set_option("encode_variant", 1|2)).
+"""CPU checks of the tile kernel's packed arithmetic (ie_set_option("encode_variant", 1|2); 2 is the default kernel).
 
 The variants change only per-lane register arithmetic of the tile kernel (imageencoder_b200/csrc/transform_fast.cuh, namespace
 ie::lean); that code is host+device, so tests/host/lean_check.cu runs the very same C++ on the CPU against a transcription of
@@ -36,4 +36,4 @@ def test_encode_variant_option_is_validated():
         assert L.ie_set_option(b"encode_variant", 3) != 0
         assert L.ie_set_option(b"encode_variant", -1) != 0
     finally:
-        assert L.ie_set_option(b"encode_variant", 0) == 0
+        assert L.ie_set_option(b"encode_variant", 2) == 0          # the default

@@ -1,9 +1,10 @@
-"""Experimental instantiations of the tile kernel (ie_set_option("encode_variant", 1|2)): byte-identical streams required.
+"""Instantiations of the tile kernel (ie_set_option("encode_variant", 0|1|2)): byte-identical streams required.
 
-The variants were written after this round's GPU budget was spent: their arithmetic is checked on the CPU
-(tests/test_lean_variant_cpu.py) and their SASS was inspected, but they have not yet run on a B200.  They are NOT the default
-path.  Until their first confirmed GPU run these tests are xfail(strict=False) -- a pass shows up as XPASS -- and each runs in
-its own process so that nothing it does can affect the parity tests of the default path.  Remove the xfail once confirmed."""
+Variant 2 (packed f32x2 transform + lean quantise bookkeeping, imageencoder_b200/csrc/transform_fast.cuh) is the default
+kernel; 0 is the scalar kernel it replaced and 1 the intermediate step, both kept for A/B timing (tools/ab_quick.py) and as
+cross-checks.  Each variant runs in its own process against the CPU oracle and against variant 0
+(tests/_variant_worker.py); the same arithmetic is also run on the CPU (tests/test_lean_variant_cpu.py).
+First confirmed on a B200 in profiles/r1_variant_parity_v9.log."""
 import subprocess
 import sys
 from pathlib import Path
@@ -14,10 +15,29 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 
 
-@pytest.mark.xfail(strict=False, reason="experimental kernel variant, not yet confirmed on hardware (not the default path)")
 @pytest.mark.parametrize("variant", [1, 2])
 def test_variant_streams_identical(variant):
     r = subprocess.run([sys.executable, str(ROOT / "tests" / "_variant_worker.py"), str(variant)], capture_output=True, text=True,
-                       timeout=600)
+                       timeout=900)
     print(r.stdout[-3000:], r.stderr[-3000:])
-    assert r.returncode == 0
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_copyout_variant_streams_identical(gpu, oracle_mod):
+    """ie_set_option("copyout_variant", 1): short path for interior chunks; must not change a byte."""
+    import numpy as np
+    from conftest import INPUTS
+    from imageencoder_b200.synth import synth_image
+    L = gpu.lib()
+    try:
+        for mat in ("matrix8_1.txt", "matrix4_2.txt"):
+            q = oracle_mod.read_matrix(INPUTS / mat)
+            n = q.shape[0]
+            for img in (synth_image(1024, 768, 31), synth_image(512, 384, 32, flat=True), np.full((64, 64), 128, np.uint8)):
+                h, w = img.shape
+                want = oracle_mod.image_encode(img, w, h, n, q, True, False)
+                for cv in (0, 1):
+                    assert L.ie_set_option(b"copyout_variant", cv) == 0
+                    assert gpu.encode_image(img, w, h, q, True, False) == want, (mat, img.shape, cv)
+    finally:
+        L.ie_set_option(b"copyout_variant", 0)

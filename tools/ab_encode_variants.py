@@ -37,4 +37,4 @@ for rnd in range(2):                     # two rounds: the second one is the fig
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); run(40); b.record(); torch.cuda.synchronize()
         print(f"round {rnd} variant {v}: {size}x{size} N={N}  {a.elapsed_time(b) / 40:.4f} ms/encode  identical_to_default={same}")
-_lib.check(L.ie_set_option(b"encode_variant", 0))
+_lib.check(L.ie_set_option(b"encode_variant", 2))
