@@ -673,17 +673,17 @@ __global__ void __launch_bounds__(kThreads) tile_copyout_kernel(const EncodePara
 // funnel shift ignores it; the slot has two chunks of slack), funnel shifts, one 128-bit store.  Every other chunk -- first
 // and last of the group, chunks that span two tiles -- takes the generic path of tile_write_chunks, chunk by chunk.
 // U = chunks per thread in flight (copyout_variant 1: U = 1, 2: U = 4).
-template <int U>
+template <int U, unsigned TPG>
 __global__ void __launch_bounds__(kThreads) tile_copyout_fast_kernel(const EncodeParams p) {
     __shared__ unsigned long long s_part[kThreads / 32];
-    __shared__ unsigned s_goff[kTilesPerGroup + 1];
+    __shared__ unsigned s_goff[TPG + 1];
     pdl_wait();
     const unsigned img = blockIdx.y, ntiles = p.tiles_per_image;
-    const unsigned t0 = blockIdx.x * kTilesPerGroup, t1 = min(t0 + kTilesPerGroup, ntiles);
+    const unsigned t0 = blockIdx.x * TPG, t1 = min(t0 + TPG, ntiles);
     const unsigned *tb = p.tile_bits + (size_t)img * ntiles;
     unsigned long long sum = 0;
     if ((reinterpret_cast<size_t>(tb) & 15) == 0) {
-        // earlier tiles' totals: 128-bit loads (t0 is a multiple of 8)
+        // earlier tiles' totals: 128-bit loads (t0 is a multiple of 4)
         const uint4 *tb4 = reinterpret_cast<const uint4 *>(tb);
         for (unsigned i = threadIdx.x; i < t0 / 4; i += kThreads) {
             const uint4 v = __ldg(tb4 + i);
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(kThreads) tile_copyout_fast_kernel(const Encod
         unsigned inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)threadIdx.x >= d) inc += o; }
-        if (threadIdx.x < kTilesPerGroup) s_goff[threadIdx.x + 1] = inc;      // entries past the group's last tile repeat its end
+        if (threadIdx.x < TPG) s_goff[threadIdx.x + 1] = inc;      // entries past the group's last tile repeat its end
         if (threadIdx.x == 0) s_goff[0] = 0;
     }
     __syncthreads();
@@ -741,10 +741,10 @@ __global__ void __launch_bounds__(kThreads) tile_copyout_fast_kernel(const Encod
                 unsigned j = 0;
                 const unsigned lo = (unsigned)ls;                             // k != 0: ls > 0
                 if (fast[u]) {
-                    // s_goff is non-decreasing and has kTilesPerGroup + 1 valid entries (the tail repeats the group's end)
-                    if (s_goff[4] <= lo) j = 4;
-                    if (s_goff[j + 2] <= lo) j += 2;
-                    if (s_goff[j + 1] <= lo) j += 1;
+                    // s_goff is non-decreasing and has TPG + 1 valid entries (the tail repeats the group's end)
+#pragma unroll
+                    for (unsigned step = TPG / 2; step >= 1; step >>= 1)
+                        if (s_goff[j + step] <= lo) j += step;
                     fast[u] = (j < g.n) && (lo + (unsigned)kChunkBits <= s_goff[j + 1]);   // the chunk ends inside tile j
                 }
                 if (fast[u]) {
@@ -803,9 +803,14 @@ __global__ void __launch_bounds__(kThreads) tile_copyout_fast_kernel(const Encod
     }
 }
 
-std::atomic<int> g_copyout_variant{0};
+// copy-out kernel: 2 = short path for interior chunks, four chunks per thread in flight (the default: 0.1125 -> 0.1068 ms on
+// config 2 with tile-kernel variant 2, profiles/r1_ab_copyout_v9.log), 1 = short path, one chunk at a time, 0 = the generic
+// kernel of versions v7/v8.  Eight chunks in flight and groups of 4 or 16 tiles measured slower
+// (profiles/r1_ab_copyout_groups_v9.log).
+std::atomic<int> g_copyout_variant{2};
 
 int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t stream) {
+    const int cv = g_copyout_variant.load();
     dim3 cgrid((p.tiles_per_image + kTilesPerGroup - 1) / kTilesPerGroup, images);
     // programmatic dependent launch: the copy-out grid is set up while the tile kernel drains and waits on the device
     // (griddepcontrol.wait) for its results instead of being launched after the tile kernel has completed
@@ -815,9 +820,8 @@ int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t str
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const int cv = g_copyout_variant.load();
-    if (cv == 1) IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_fast_kernel<1>, p));
-    else if (cv == 2) IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_fast_kernel<4>, p));
+    if (cv == 1) IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_fast_kernel<1, kTilesPerGroup>, p));
+    else if (cv == 2) IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_fast_kernel<4, kTilesPerGroup>, p));
     else IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_kernel, p));
     count_launch();
     IE_CUDA(cudaGetLastError());

@@ -24,7 +24,8 @@ def test_variant_streams_identical(variant):
 
 
 def test_copyout_variant_streams_identical(gpu, oracle_mod):
-    """ie_set_option("copyout_variant", 1): short path for interior chunks; must not change a byte."""
+    """ie_set_option("copyout_variant", 0|1|2): 2 (short path for interior chunks, four in flight) is the default kernel,
+    0 the generic one it replaced; none may change a byte."""
     import numpy as np
     from conftest import INPUTS
     from imageencoder_b200.synth import synth_image
@@ -36,8 +37,8 @@ def test_copyout_variant_streams_identical(gpu, oracle_mod):
             for img in (synth_image(1024, 768, 31), synth_image(512, 384, 32, flat=True), np.full((64, 64), 128, np.uint8)):
                 h, w = img.shape
                 want = oracle_mod.image_encode(img, w, h, n, q, True, False)
-                for cv in (0, 1):
+                for cv in (0, 1, 2):
                     assert L.ie_set_option(b"copyout_variant", cv) == 0
                     assert gpu.encode_image(img, w, h, q, True, False) == want, (mat, img.shape, cv)
     finally:
-        L.ie_set_option(b"copyout_variant", 0)
+        L.ie_set_option(b"copyout_variant", 2)
