@@ -163,8 +163,14 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
  * offsets can come straight from an NCCL all-gather + scan without a host round trip. */
 int ie_stream_shift_dev(const uint8_t *d_in, const uint64_t *d_params, uint8_t *d_out, size_t out_cap, void *stream);
 
-/* Diagnostics switch.  "exact_transform" = 1 makes the encoders evaluate every coefficient in the reference's exact
- * binary64 order instead of the guarded FP32 fast path (both produce identical streams; tests cross-check them). */
+/* Diagnostics switches (process-wide; every setting produces identical streams, tests cross-check them):
+ *   "exact_transform" = 1  the encoders evaluate every coefficient in the reference's exact binary64 order instead of the
+ *                          guarded FP32 fast path;
+ *   "encode_variant"  = 0 | 1 | 2 (default)  instantiation of the tile kernel: 2 = packed f32x2 transform + quantise,
+ *                          1 = packed quantise only, 0 = the scalar kernel they replaced (A/B timing, cross-checks);
+ *   "copyout_variant" = 0 | 1 | 2 (default)  copy-out kernel: 2 = short path for interior chunks with four chunks per
+ *                          thread in flight, 1 = short path one chunk at a time, 0 = the generic kernel.
+ * Returns IE_EINVAL for an unknown name or an out-of-range value. */
 int ie_set_option(const char *name, int value);
 
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
