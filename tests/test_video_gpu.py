@@ -104,3 +104,34 @@ def test_video_errors(gpu):
     from imageencoder_b200 import IEError
     with pytest.raises(IEError):
         gpu.encode_video(np.zeros(40 * 40 * 3 // 2, np.uint8), 40, 40, np.full(16, 2))   # not a multiple of 16
+
+
+@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: first run pending (the mvec fields inside the "
+                                        "stream are already compared bit for bit by every test above)")
+def test_motion_vectors_and_reconstruction_direct(gpu, oracle_mod):
+    """Motion vectors (Block.cpp:267-339) and the encoder-side reconstruction (Frame.cpp:218-242) compared directly, not only
+    through the stream: ie_encode_video_dev's optional mvec output [frames][MacroBlocks][2] and the Y planes it rebuilds in place."""
+    import torch
+    from imageencoder_b200 import device
+    from imageencoder_b200.synth import synth_video
+    W, H, F, gop, mer = 96, 64, 7, 3, 16
+    q = oracle_mod.read_matrix(INPUTS / "matrix.txt")
+    yuv = synth_video(W, H, F, 4100)
+    want, mv, rec = oracle_mod.video_encode(yuv, W, H, q, True, gop, mer, False, stages=True)
+    nmb = (W // 16) * (H // 16)
+    fsz = W * H * 3 // 2
+    d_yuv = torch.from_numpy(np.array(yuv, dtype=np.uint8).reshape(-1).copy()).cuda()
+    cap = int(gpu.lib().ie_max_encoded_bytes(W, H, 4, F)) + 4096
+    d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    d_bits = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_mv = torch.full((F * nmb * 2,), 77, dtype=torch.int16, device="cuda")
+    sess = device.Session(device.Session.VIDEO_ENCODE, W, H, 4, F)
+    device.encode_video_dev(sess, d_yuv, W, H, q, True, gop, mer, d_out, d_bits, lead_bit=True, d_mvecs=d_mv)
+    torch.cuda.synchronize()
+    nbytes = (int(d_bits.item()) + 7) // 8
+    assert d_out[:nbytes].cpu().numpy().tobytes() == want
+    got_mv = d_mv.cpu().numpy().reshape(F, nmb, 2)
+    assert np.array_equal(got_mv, np.asarray(mv).reshape(F, nmb, 2)), "motion vectors differ from the oracle's"
+    got = d_yuv.cpu().numpy().reshape(F, fsz)[:, : W * H]
+    exp = np.asarray(rec, dtype=np.uint8).reshape(F, fsz)[:, : W * H]
+    assert np.array_equal(got, exp), "encoder-side reconstruction (Y planes) differs from the oracle's"
