@@ -14,6 +14,7 @@ namespace ie {
 extern std::atomic<int> g_exact_transform;   // encode_image.cu
 extern std::atomic<int> g_encode_variant;
 extern std::atomic<int> g_copyout_variant;
+extern std::atomic<int> g_decode_variant;      // decode_image.cu
 static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
 
@@ -217,6 +218,11 @@ int ie_set_option(const char *name, int value) {
     if (name && !strcmp(name, "copyout_variant")) {
         if (value < 0 || value > 2) { ie::set_error("copyout_variant: 0 (generic kernel), 1 (short path for interior chunks) or 2 (1 + four chunks in flight, the default)"); return IE_EINVAL; }
         ie::g_copyout_variant.store(value);
+        return IE_OK;
+    }
+    if (name && !strcmp(name, "decode_variant")) {
+        if (value < 0 || value > 1) { ie::set_error("decode_variant: 0 (default) or 1 (packed f32x2 inverse transform, experimental)"); return IE_EINVAL; }
+        ie::g_decode_variant.store(value);
         return IE_OK;
     }
     ie::set_error("unknown option");

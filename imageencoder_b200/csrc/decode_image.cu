@@ -163,8 +163,8 @@ struct BitReader {
     }
 };
 
-template <int N, bool ADD>
-__global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodeParams p) {
+template <int N, bool ADD, int VAR>
+__device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
     pdl_wait();
     constexpr int NN = N * N;
     constexpr int STRIDE = NN + 2;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodePar
         x[uv] = d;
         S += fabsf(d);
     }
-    idct2d_fast<N>(x);
+    if (VAR != 1 || ADD) idct2d_fast<N>(x);
     const float delta = (32.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
     // unsure: |frac - 0.5| >= 0.5 - delta; absurd coefficients (delta >= 0.49) take the exact path everywhere
     const float hi_thr = (delta < 0.49f) ? 0.5f - delta : 0.f;
@@ -231,6 +231,18 @@ __global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodePar
     uint8_t *dst = p.out + (size_t)img * p.out_stride + (size_t)(byi * N) * p.pitch + (size_t)bxi * N;
     unsigned outw[N * (N / 4)];
     unsigned long long unsure = 0;
+    if (VAR == 1 && !ADD) {
+        // variant 1 (transform_fast.cuh, lean::): inverse transform and pixel stage in packed f32x2 operations, same bits
+        float2 x2[NN / 2], p2[NN / 2];
+#pragma unroll
+        for (int r2 = 0; r2 < N / 2; r2++)
+#pragma unroll
+            for (int v = 0; v < N; v++) x2[r2 * N + v] = make_float2(x[(2 * r2) * N + v], x[(2 * r2 + 1) * N + v]);
+        lean::idct2d_packed<N>(x2, p2);
+        unsigned ulo, uhi;
+        lean::pixel_stage<N>(p2, hi_thr, outw, ulo, uhi);
+        unsure = ((unsigned long long)uhi << 32) | ulo;
+    } else
 #pragma unroll
     for (int y = 0; y < N; y++) {
         unsigned curw[N / 4];
@@ -286,7 +298,20 @@ __global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodePar
     }
 }
 
+template <int N, bool ADD>
+__global__ void __launch_bounds__(128) decode_blocks_fast_kernel(const DecodeParams p) {
+    decode_blocks_fast_body<N, ADD, 0>(p);
+}
+// decode variant 1: same body with the packed inverse transform + pixel stage, held to 6 CTAs per SM like the default
+template <int N>
+__global__ void __launch_bounds__(128, 6) decode_blocks_lean_kernel(const DecodeParams p) {
+    decode_blocks_fast_body<N, false, 1>(p);
+}
+
 extern std::atomic<int> g_exact_transform;
+// 1 = inverse transform + pixel stage of the fast decode in packed f32x2 operations (experimental: its arithmetic is checked on
+// the CPU, tests/host/lean_check.cu, but it has not run on a B200 yet; image blocks and I-frames only)
+std::atomic<int> g_decode_variant{0};
 
 int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream) {
     parse_blocks_kernel<<<images, 32, 0, stream>>>(p);
@@ -298,7 +323,10 @@ int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t str
 int launch_decode_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream) {
     if (!g_exact_transform.load()) {
         dim3 gridf((p.nblocks + 127) / 128, images);
-        if (p.N == 8) IE_CUDA(launch_pdl(decode_blocks_fast_kernel<8, false>, gridf, dim3(128), 0, stream, p));
+        const bool lean_dec = g_decode_variant.load() == 1;
+        if (p.N == 8 && lean_dec) IE_CUDA(launch_pdl(decode_blocks_lean_kernel<8>, gridf, dim3(128), 0, stream, p));
+        else if (p.N == 4 && !p.add_mode && lean_dec) IE_CUDA(launch_pdl(decode_blocks_lean_kernel<4>, gridf, dim3(128), 0, stream, p));
+        else if (p.N == 8) IE_CUDA(launch_pdl(decode_blocks_fast_kernel<8, false>, gridf, dim3(128), 0, stream, p));
         else if (p.N == 4 && p.add_mode) IE_CUDA(launch_pdl(decode_blocks_fast_kernel<4, true>, gridf, dim3(128), 0, stream, p));
         else if (p.N == 4) IE_CUDA(launch_pdl(decode_blocks_fast_kernel<4, false>, gridf, dim3(128), 0, stream, p));
         else { set_error("block size must be 4 or 8"); return IE_EINVAL; }

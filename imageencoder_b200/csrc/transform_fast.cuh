@@ -389,5 +389,124 @@ IE_HD void quantise_block_packed(const float2 *Y2, const FastQuant &fq, int dc_d
     orbits = (unsigned)qmax | (unsigned)(qmin ^ (qmin >> 31));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Decode variant 1 (ie_set_option("decode_variant", 1), experimental): the inverse transform and the pixel stage of
+// decode_blocks_fast_kernel in packed f32x2 operations -- the operation DAG of idct8_inplace / idct4_inplace above, bit-identical
+// outputs.  Mirror image of the forward trick: pass 1 (along a row, rows 2r and 2r+1 in the two halves) is packed up to its LAST
+// butterfly stage, which is done on single halves and writes pairs of columns 2c and 2c+1 of one row; pass 2 (along a column)
+// is then packed over those column pairs and leaves pairs of neighbouring pixels of a row behind, which is what the pixel stage
+// wants.
+// ---------------------------------------------------------------------------------------------------------------------
+IE_HD float2 fmac2_rd_one(float2 a, float c) {            // a + c per half, rounded towards -infinity (a * 1 is exact)
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rd(a, make_float2(1.0f, 1.0f), make_float2(c, c));
+#else
+    // only used with a in [0.5, 255.5] and c = 2^23, where the result is exactly 2^23 + floor(a)
+    return make_float2(c + floorf(a.x), c + floorf(a.y));
+#endif
+}
+
+// everything of idct8_inplace / idct4_inplace before the final butterflies: e[i], o[i] with v[i] = e[i] + o[i],
+// v[N-1-i] = e[i] - o[i]
+template <int N>
+IE_HD void idct_head2(const float2 *y, float2 *e, float2 *o) {
+    if (N == 8) {
+        const float2 t4 = mulc2(y[4], IE_C4);
+        const float2 a = add2(y[0], t4), b = sub2(y[0], t4);
+        const float2 pp = fmac2(y[2], IE_C2, mulc2(y[6], IE_C6)), qq = fmac2(y[2], IE_C6, mulc2(y[6], -IE_C2));
+        e[0] = add2(a, pp); e[3] = sub2(a, pp); e[1] = add2(b, qq); e[2] = sub2(b, qq);
+        o[0] = fmac2(y[1], IE_C1, fmac2(y[3], IE_C3, fmac2(y[5], IE_C5, mulc2(y[7], IE_C7))));
+        o[1] = fmac2(y[1], IE_C3, fmac2(y[3], -IE_C7, fmac2(y[5], -IE_C1, mulc2(y[7], -IE_C5))));
+        o[2] = fmac2(y[1], IE_C5, fmac2(y[3], -IE_C1, fmac2(y[5], IE_C7, mulc2(y[7], IE_C3))));
+        o[3] = fmac2(y[1], IE_C7, fmac2(y[3], -IE_C5, fmac2(y[5], IE_C3, mulc2(y[7], -IE_C1))));
+    } else {
+        const float2 t2 = mulc2(y[2], IE_C4);
+        e[0] = add2(y[0], t2); e[1] = sub2(y[0], t2);                                           // a, b
+        o[0] = fmac2(y[1], IE_C2, mulc2(y[3], IE_C6)); o[1] = fmac2(y[1], IE_C6, mulc2(y[3], -IE_C2));   // p, q
+    }
+}
+
+// X2[r * N + v] = (x[2r][v], x[2r+1][v]): the dequantised coefficients, two rows per pair.
+// P2[i * (N/2) + c] = (X[i][2c], X[i][2c+1]): the block's samples before the +128, two neighbouring pixels per pair.
+template <int N>
+IE_HD void idct2d_packed(const float2 *X2, float2 *P2) {
+    constexpr int H = N / 2;
+    float2 C2[N][H];                                     // C2[u][c] = (T[u][2c], T[u][2c+1]) after pass 1
+IE_UNROLL
+    for (int r = 0; r < H; r++) {
+        float2 e[H], o[H];
+        idct_head2<N>(X2 + r * N, e, o);
+        // final butterflies on single halves: row 2r from the .x halves, row 2r+1 from the .y halves
+        float lo[N], hi[N];
+IE_UNROLL
+        for (int i = 0; i < H; i++) {
+            lo[i] = e[i].x + o[i].x; lo[N - 1 - i] = e[i].x - o[i].x;
+            hi[i] = e[i].y + o[i].y; hi[N - 1 - i] = e[i].y - o[i].y;
+        }
+IE_UNROLL
+        for (int c = 0; c < H; c++) {
+            C2[2 * r][c] = make_float2(lo[2 * c], lo[2 * c + 1]);
+            C2[2 * r + 1][c] = make_float2(hi[2 * c], hi[2 * c + 1]);
+        }
+    }
+IE_UNROLL
+    for (int c = 0; c < H; c++) {
+        float2 y[N], e[H], o[H];
+IE_UNROLL
+        for (int u = 0; u < N; u++) y[u] = C2[u][c];
+        idct_head2<N>(y, e, o);
+IE_UNROLL
+        for (int i = 0; i < H; i++) {
+            P2[i * H + c] = add2(e[i], o[i]);
+            P2[(N - 1 - i) * H + c] = sub2(e[i], o[i]);
+        }
+    }
+}
+
+// Pixel stage of the fast decode for two neighbouring pixels (decode_blocks_fast_kernel): v = x + 128, clamp to [0.5, 255.5],
+// floor by a round-down add of 2^23 (the pixel is the low byte of the result), `unsure` if an integer boundary lies within
+// the block's error bound.  Returns the two words whose low bytes are the pixels.
+template <unsigned BIT_A, unsigned BIT_B>
+IE_HD void pixel_pair(float2 x, float hi_thr, unsigned &fa, unsigned &fb, unsigned &unsure) {
+    const float2 v = add2(x, make_float2(128.0f, 128.0f));
+    float2 u;
+    u.x = fminf(fmaxf(v.x, 0.5f), 255.5f);
+    u.y = fminf(fmaxf(v.y, 0.5f), 255.5f);
+    const float2 fm = fmac2_rd_one(u, 8388608.0f);                                  // 2^23 + floor(u)
+    const float2 fl = add2(fm, make_float2(-8388608.0f, -8388608.0f));              // floor(u), exact
+    const float2 g = add2(sub2(u, fl), make_float2(-0.5f, -0.5f));                  // frac - 0.5 (both steps exact)
+    or_if_near<BIT_A>(unsure, g.x, hi_thr);
+    or_if_near<BIT_B>(unsure, g.y, hi_thr);
+    fa = f2u(fm.x); fb = f2u(fm.y);
+}
+
+// row y of the block: N pixels -> N/4 output words (4 pixels each) + the row's bits of the `unsure` mask (bit = raster index)
+template <int N, int Y, int Q4>
+IE_HD unsigned pixel_quad(const float2 *P2, float hi_thr, unsigned &unsure_lo, unsigned &unsure_hi) {
+    constexpr int ij = Y * N + Q4 * 4;                      // raster index of the quad's first pixel
+    unsigned f0, f1, f2, f3;
+    unsigned &un = (ij < 32) ? unsure_lo : unsure_hi;        // a quad never straddles bit 32
+    pixel_pair<(1u << (ij & 31)), (1u << ((ij + 1) & 31))>(P2[Y * (N / 2) + Q4 * 2], hi_thr, f0, f1, un);
+    pixel_pair<(1u << ((ij + 2) & 31)), (1u << ((ij + 3) & 31))>(P2[Y * (N / 2) + Q4 * 2 + 1], hi_thr, f2, f3, un);
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(__byte_perm(f0, f1, 0x0040), __byte_perm(f2, f3, 0x0040), 0x5410);
+#else
+    return (f0 & 0xffu) | ((f1 & 0xffu) << 8) | ((f2 & 0xffu) << 16) | ((f3 & 0xffu) << 24);
+#endif
+}
+
+template <int N, int... I>
+IE_HD void pixel_stage_impl(const float2 *P2, float hi_thr, unsigned *outw, unsigned &unsure_lo, unsigned &unsure_hi,
+                            std::integer_sequence<int, I...>) {
+    ((outw[I] = pixel_quad<N, I / (N / 4), I % (N / 4)>(P2, hi_thr, unsure_lo, unsure_hi)), ...);
+}
+
+// outw[y * (N/4) + q4]: the block's pixels, 4 per word (as decode_blocks_fast_kernel keeps them); unsure: bit = raster index
+template <int N>
+IE_HD void pixel_stage(const float2 *P2, float hi_thr, unsigned *outw, unsigned &unsure_lo, unsigned &unsure_hi) {
+    unsure_lo = 0; unsure_hi = 0;
+    pixel_stage_impl<N>(P2, hi_thr, outw, unsure_lo, unsure_hi, std::make_integer_sequence<int, N * (N / 4)>{});
+}
+
 }  // namespace lean
 }  // namespace ie

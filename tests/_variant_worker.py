@@ -1,5 +1,6 @@
 """Runs in its own process (tests/test_zz_variants_gpu.py): encodes with ie_set_option("encode_variant", V) and compares the
-stream with the default kernel's and with the CPU oracle's.  Exit code 0 = identical."""
+stream with the default kernel's and with the CPU oracle's; `dec<V>` does the same for ie_set_option("decode_variant", V)
+and the decoded pixels.  Exit code 0 = identical."""
 import sys
 from pathlib import Path
 
@@ -59,5 +60,60 @@ def main(variant: int) -> int:
     return 1 if bad else 0
 
 
+def main_decode(variant: int) -> int:
+    import imageencoder_b200 as ie
+    import oracle
+    from imageencoder_b200 import _lib
+    from imageencoder_b200.synth import synth_image, synth_video
+
+    L = ie.lib()
+    _lib.check(L.ie_init(0))
+    inputs = ROOT / "tests" / "golden" / "inputs"
+    rng = np.random.default_rng(6)
+    bad = 0
+
+    def both(stream, n):
+        _lib.check(L.ie_set_option(b"decode_variant", 0))
+        base = ie.decode_image(stream, n)
+        _lib.check(L.ie_set_option(b"decode_variant", variant))
+        return base, ie.decode_image(stream, n)
+
+    for mat in ("matrix8_1.txt", "matrix8_2.txt", "matrix.txt", "matrix4_2.txt"):
+        q = ie.read_matrix(inputs / mat)
+        n = q.shape[0]
+        cases = [("synth", synth_image(512, 384, 21)), ("flat", synth_image(512, 384, 22, flat=True)),
+                 ("noise", rng.integers(0, 256, (128, 96)).astype(np.uint8)),
+                 ("checker", ((np.indices((64, 64)).sum(0) & 1) * 255).astype(np.uint8)),
+                 ("all128", np.full((64, 64), 128, np.uint8)), ("extremes", (rng.integers(0, 2, (64, 128)) * 255).astype(np.uint8))]
+        for qq, qname in ((q, mat), (np.ones_like(q), "ones"), (np.full_like(q, 255), "255s")):
+            for name, img in cases:
+                h, w = img.shape
+                stream = oracle.image_encode(img, w, h, n, qq, True, False)
+                want = oracle.image_decode(stream, n)[0]
+                base, got = both(stream, n)
+                if not (np.array_equal(got, base) and np.array_equal(got, want)):
+                    print(f"decode variant {variant}: {qname} {name}: differs (default==oracle: {np.array_equal(base, want)})")
+                    bad += 1
+    # larger image: the variant against the default kernel only
+    q = ie.read_matrix(inputs / "matrix8_1.txt")
+    _lib.check(L.ie_set_option(b"decode_variant", 0))
+    stream = ie.encode_image(synth_image(4096, 2048, 1234), 4096, 2048, q, True, False)
+    base, got = both(stream, 8)
+    if not np.array_equal(base, got):
+        print(f"decode variant {variant}: 4096x2048 differs from the default kernel")
+        bad += 1
+    # video: I-frames take the variant, P-frames (add mode) stay on the default kernel
+    q = ie.read_matrix(inputs / "matrix.txt")
+    yuv = synth_video(64, 48, 5)
+    enc = oracle.video_encode(yuv, 64, 48, q, True, 3, 16, False)
+    if not np.array_equal(ie.decode_video(enc, True)[0], oracle.video_decode(enc, True)[0]):
+        print(f"decode variant {variant}: decoded video differs")
+        bad += 1
+    _lib.check(L.ie_set_option(b"decode_variant", 0))
+    print(f"decode variant {variant}: {'ok' if not bad else f'{bad} mismatches'}")
+    return 1 if bad else 0
+
+
 if __name__ == "__main__":
-    sys.exit(main(int(sys.argv[1])))
+    a = sys.argv[1]
+    sys.exit(main_decode(int(a[3:])) if a.startswith("dec") else main(int(a)))

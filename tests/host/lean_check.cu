@@ -6,6 +6,7 @@
 //   * variant 1 (scalar transform + lean::quantise_block_packed): staged zigzag coefficients, guard-band mask, max
 //     bits_needed, segment non-zero flags
 //   * variant 2 (lean::fdct2d_packed + quantise_block_packed): additionally the packed transform, bit for bit
+//   * decode variant 1 (lean::idct2d_packed + lean::pixel_stage): inverse transform bit for bit, output words, `unsure` mask
 // and the integer DC rounding against round_half_away(S / (4 Q00)) in exact integer arithmetic.
 #include <cstdio>
 #include <cstdlib>
@@ -202,10 +203,98 @@ static long long run(long long nblocks, unsigned seed) {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// decode variant 1: lean::idct2d_packed + lean::pixel_stage against a transcription of decode_blocks_fast_kernel<N, false>
+// (decode_image.cu: "fast inverse transform" and the pixel loop)
+// ---------------------------------------------------------------------------------------------------------------------
+template <int N>
+static void check_decode_block(const short *cf /*zigzag order*/, const float *k2 /*raster*/, long long id) {
+    constexpr int NN = N * N;
+    // ---- transcription of the default path
+    float x[NN];
+    float S = 0.f;
+    for (int uv = 0; uv < NN; uv++) {
+        const int k = (N == 8) ? kZigzagInv8[uv] : kZigzagInv4[uv];
+        const int c = cf[k];
+        const float d = (float)c * k2[uv];
+        x[uv] = d;
+        S += fabsf(d);
+    }
+    float xin[NN];
+    memcpy(xin, x, sizeof x);
+    idct2d_fast<N>(x);
+    const float delta = (32.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
+    const float hi_thr = (delta < 0.49f) ? 0.5f - delta : 0.f;
+    unsigned outw[N * (N / 4)];
+    unsigned long long unsure = 0;
+    for (int y = 0; y < N; y++)
+        for (int q4 = 0; q4 < N / 4; q4++) {
+            unsigned fl[4];
+            for (int b = 0; b < 4; b++) {
+                const int ij = y * N + q4 * 4 + b;
+                const float v = x[ij] + 128.f;
+                const float u = fminf(fmaxf(v, 0.5f), 255.5f);
+                const float fm = 8388608.0f + floorf(u);                       // __fadd_rd(u, 2^23) for u in [0.5, 255.5]
+                const float frac = u - (fm - 8388608.0f);
+                if (fabsf(frac - 0.5f) >= hi_thr) unsure |= 1ull << ij;
+                memcpy(&fl[b], &fm, 4);
+            }
+            outw[y * (N / 4) + q4] = (fl[0] & 0xffu) | ((fl[1] & 0xffu) << 8) | ((fl[2] & 0xffu) << 16) | ((fl[3] & 0xffu) << 24);
+        }
+    // ---- variant
+    float2 x2[NN / 2], p2[NN / 2];
+    for (int r = 0; r < N / 2; r++)
+        for (int v = 0; v < N; v++) x2[r * N + v] = make_float2(xin[(2 * r) * N + v], xin[(2 * r + 1) * N + v]);
+    lean::idct2d_packed<N>(x2, p2);
+    for (int i = 0; i < N; i++)
+        for (int c = 0; c < N / 2; c++) {
+            const float2 v = p2[i * (N / 2) + c];
+            CHECK(memcmp(&v.x, &x[i * N + 2 * c], 4) == 0 && memcmp(&v.y, &x[i * N + 2 * c + 1], 4) == 0,
+                  "decode block %lld: inverse transform output (%d,%d) differs: %a %a vs %a %a", id, i, 2 * c, v.x, v.y, x[i * N + 2 * c],
+                  x[i * N + 2 * c + 1]);
+        }
+    unsigned ow[N * (N / 4)], ulo, uhi;
+    lean::pixel_stage<N>(p2, hi_thr, ow, ulo, uhi);
+    const unsigned long long un = ((unsigned long long)uhi << 32) | ulo;
+    CHECK(un == unsure, "decode block %lld: unsure mask %llx != %llx", id, un, unsure);
+    for (int i = 0; i < N * (N / 4); i++) CHECK(ow[i] == outw[i], "decode block %lld: output word %d: %08x != %08x", id, i, ow[i], outw[i]);
+}
+
+template <int N>
+static void run_decode(long long nblocks, unsigned seed) {
+    constexpr int NN = N * N;
+    std::mt19937 rng(seed);
+    for (int qm = 0; qm < 4; qm++) {
+        float k2[64];
+        for (int i = 0; i < NN; i++) {
+            const int u = i / N, v = i % N;
+            const double cu = (u == 0) ? 0.5 : M_SQRT1_2, cv = (v == 0) ? 0.5 : M_SQRT1_2;
+            const int Q = (qm == 0) ? 1 : (qm == 1) ? 2 + 3 * (u + v) : (qm == 2) ? 16 + 11 * u * v + 7 * (u + v) : 255;
+            k2[i] = (float)((double)Q * (cu * cv));
+        }
+        for (long long b = 0; b < nblocks; b++) {
+            short cf[64] = {0};
+            const int mode = (int)(rng() % 5);
+            const int len = (mode == 0) ? 0 : (mode == 1) ? 1 : (int)(rng() % (NN + 1));
+            const int amp = (mode == 4) ? 32767 : (mode == 3) ? 600 : 24;
+            for (int k = 0; k < len; k++) {
+                if (mode == 2 && (rng() % 3)) continue;                           // sparse
+                cf[k] = (short)((int)(rng() % (2 * amp + 1)) - amp);
+            }
+            if (len && (rng() & 1)) cf[0] = (short)((int)(rng() % 1200) - 600);   // a DC that lands the pixels inside [0, 255]
+            check_decode_block<N>(cf, k2, b);
+        }
+    }
+}
+
 int main(int argc, char **argv) {
     const long long n = (argc > 1) ? atoll(argv[1]) : 200000;
     if (run<8>(n, 12345u) || run<4>(n, 54321u)) return 2;
+    run_decode<8>(n, 777u);
+    run_decode<4>(n, 888u);
     if (g_fail) { printf("lean_check: %lld failures\n", g_fail); return 1; }
-    printf("lean_check: ok (%lld blocks per block size, 6 quant matrices each, variants 1 and 2)\n", n * 6);
+    printf("lean_check: ok (%lld encode blocks per block size with 6 quant matrices, encode variants 1 and 2; %lld decode blocks per "
+           "block size with 4 matrices, decode variant 1)\n", n * 6, n * 4);
     return 0;
 }

@@ -23,6 +23,18 @@ def test_variant_streams_identical(variant):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.xfail(strict=False, reason="decode variant 1 was written after this round's GPU budget was spent: its arithmetic is "
+                                        "checked on the CPU (tests/host/lean_check.cu), its first run on a B200 is this one; "
+                                        "it is NOT the default kernel")
+def test_decode_variant_pixels_identical():
+    """ie_set_option("decode_variant", 1): packed f32x2 inverse transform + pixel stage (decode_blocks_lean_kernel); own process
+    so that a fault in the experimental kernel cannot poison this process's CUDA context."""
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "_variant_worker.py"), "dec1"], capture_output=True, text=True,
+                       timeout=900)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_copyout_variant_streams_identical(gpu, oracle_mod):
     """ie_set_option("copyout_variant", 0|1|2): 2 (short path for interior chunks, four in flight) is the default kernel,
     0 the generic one it replaced; none may change a byte."""
