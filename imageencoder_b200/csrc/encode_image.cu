@@ -95,20 +95,86 @@ __device__ __noinline__ int exact_coefficient(const ExactCtx p, unsigned gb, int
     return (int)(short)__double2int_rz(round_half_away(__ddiv_rn(e, m_uv)));
 }
 
+// The pack loop of encode_tiles_kernel's phase 3 (same statements) writing to any address space: used by the reduced-staging
+// instantiations (encode_variant 3 / 4) when a tile image is larger than their shared-memory staging area and is packed straight
+// into the tile's slot of the global scratch buffer instead.  Every lane writes its blocks' fields MSB-first into the image of
+// the tile's bits at `outw` (tile-local alignment, zero-filled by the caller): whole words with plain stores, the <= 2 words a
+// block shares with its neighbours with atomicOr.  (The kernel keeps its own inline copy of the loop for the shared-memory
+// case so that the default instantiations' SASS stays what was measured.)
+template <int NN, int BPL>
+__device__ __forceinline__ void pack_tile_blocks(unsigned *outw, const short *s_coef, const unsigned *s_off, const unsigned char *s_w,
+                                                 const unsigned char *s_len, int nblk, int use_rle) {
+    constexpr int STRIDE = NN + 2;
+#pragma unroll 1
+    for (int r = 0; r < BPL; r++) {
+        const int lb = threadIdx.x * BPL + r;
+        if (lb >= nblk) break;
+        const int w = s_w[lb], len = s_len[lb];
+        const unsigned pos = s_off[lb];
+        const unsigned bo = pos & 31u;
+        unsigned *ow = outw + (pos >> 5);
+        const unsigned *cw = reinterpret_cast<const unsigned *>(s_coef + (size_t)lb * STRIDE);
+        const unsigned mask = (1u << w) - 1u;                                             // w <= 16
+        // header: bit_len (low 4 bits survive, Block.cpp:381) and, with RLE, the length field (Block.cpp:393)
+        unsigned long long acc = use_rle ? ((((unsigned long long)w & 15ull) << w) | (unsigned long long)len) : ((unsigned long long)w & 15ull);
+        int nacc = (int)bo + 4 + (use_rle ? w : 0);
+        const int nfull = len >> 1;
+        const int s2 = 2 * w;
+        int j = 0;
+        bool odd_left = (len & 1) != 0;
+        // stage A: up to the first completed word -- the only one that can hold bits of the previous block(s)
+        while (nacc < 32 && j < nfull) {
+            const unsigned x2 = cw[j++];
+            acc = (acc << s2) | (((x2 & mask) << w) | ((x2 >> 16) & mask));
+            nacc += s2;
+        }
+        if (nacc < 32 && odd_left) { acc = (acc << w) | (cw[nfull] & mask); nacc += w; odd_left = false; }
+        if (nacc >= 32) {
+            const unsigned word = (unsigned)(acc >> (nacc - 32));
+            if (bo) atomicOr(ow, word); else *ow = word;
+            ow++;
+            nacc -= 32;
+            // stage B: whole words that belong to this block alone
+            for (; j < nfull; j++) {
+                const unsigned x2 = cw[j];
+                acc = (acc << s2) | (((x2 & mask) << w) | ((x2 >> 16) & mask));
+                nacc += s2;
+                if (nacc >= 32) { nacc -= 32; *ow++ = (unsigned)(acc >> nacc); }
+            }
+            if (odd_left) {
+                acc = (acc << w) | (cw[nfull] & mask);
+                nacc += w;
+                if (nacc >= 32) { nacc -= 32; *ow++ = (unsigned)(acc >> nacc); }
+            }
+        }
+        if (nacc > 0) atomicOr(ow, (unsigned)(acc << (32 - nacc)));                        // tail shared with the next block
+    }
+}
+
 constexpr int kQueueCap = 128;        // guard-band fallback entries per tile handled by the CTA-wide queue
 
+// VAR: 0 scalar transform, 1 lean quantise, 2 packed transform + lean quantise (default), 3 / 4 = 2 with a reduced staging area
+// for the tile image (kSmallOutChunks chunks instead of the worst case; larger tile images are packed in global memory) and
+// 7 / 8 CTAs per SM instead of 6 (experimental, not yet run on a B200)
+constexpr int kSmallOutChunks = 512;
+constexpr int encode_min_ctas(int N, bool PF, bool FAST, int VAR) {
+    return (N == 8 && !FAST) ? 1 : (FAST && !PF ? (VAR == 3 ? 7 : VAR == 4 ? 8 : 6) : 2);
+}
+
 template <int N, int BPL, bool PF, bool FAST, int VAR = 0>
-__global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF ? 6 : 2)) encode_tiles_kernel(const EncodeParams p) {
+__global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) encode_tiles_kernel(const EncodeParams p) {
     constexpr int NN = N * N;
     constexpr int TB = kThreads * BPL;            // blocks per tile
     constexpr int STRIDE = NN + 2;                // halfwords per block in the staging area: NN/2 + 1 words (odd -> bank spread)
     constexpr int NSEG = NN / 8;
     constexpr int MAXCHUNKS = (TB * (4 + 16 + 16 * NN) + 127) / 128 + 2;
+    constexpr bool SMALL_OUT = VAR >= 3;
+    constexpr int OUTCHUNKS = SMALL_OUT ? kSmallOutChunks : MAXCHUNKS;     // staging area for the tile image, in 128-bit chunks
     extern __shared__ __align__(16) unsigned char smem[];
     short *s_coef = reinterpret_cast<short *>(smem);
     unsigned *s_off = reinterpret_cast<unsigned *>(smem + (size_t)TB * STRIDE * sizeof(short));
     uint4 *s_out = reinterpret_cast<uint4 *>(smem + (((size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 15) & ~(size_t)15));
-    unsigned *s_queue = reinterpret_cast<unsigned *>(s_out + MAXCHUNKS);
+    unsigned *s_queue = reinterpret_cast<unsigned *>(s_out + OUTCHUNKS);
     unsigned char *s_w = reinterpret_cast<unsigned char *>(s_queue + kQueueCap + TB + (kQueueCap + TB) / 2);
     unsigned char *s_len = s_w + TB;
     unsigned char *s_dirty = s_len + TB;
@@ -166,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
         }
         if (FAST) {
             unsigned long long near = 0;
-            if (VAR == 2 && !PF) {
+            if (VAR >= 2 && !PF) {
             // variant 2: the whole block is loaded first, rows 2r and 2r+1 are converted and transformed as f32x2 pairs
             unsigned raw[N][N / 4];
 #pragma unroll
@@ -495,6 +561,14 @@ __global__ void __launch_bounds__(kThreads, (N == 8 && !FAST) ? 1 : (FAST && !PF
     // local alignment), whole words with plain stores, the <= 2 words it shares with its neighbours with shared-memory
     // atomicOr.  Then the tile's stream offset is resolved (look-back) and the image goes out re-aligned to the chunk
     // grid of the global stream with coalesced 128-bit stores.
+    if (SMALL_OUT && !p.bits_only && (T + 127) / 128 > (unsigned)OUTCHUNKS) {                 // uniform
+        // reduced staging area and a tile image that does not fit it (noise-like content, quantisers near 1): the image is
+        // packed straight into the tile's slot of the scratch buffer (global atomics instead of shared ones; rare)
+        uint4 *slot = reinterpret_cast<uint4 *>(p.tile_scratch + ((size_t)img * ntiles + tile) * p.slot_bytes);
+        for (unsigned c = threadIdx.x; c < (T + 127) / 128; c += kThreads) slot[c] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        pack_tile_blocks<NN, BPL>(reinterpret_cast<unsigned *>(slot), s_coef, s_off, s_w, s_len, nblk, p.use_rle);
+    } else
     if (!p.bits_only) {
         unsigned *s_outw = reinterpret_cast<unsigned *>(s_out);
         const unsigned nwords = (T + 31) / 32;
@@ -859,7 +933,8 @@ static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t strea
     constexpr int TB = kThreads * BPL;
     constexpr int STRIDE = N * N + 2;
     constexpr int MAXCHUNKS = (TB * (4 + 16 + 16 * N * N) + 127) / 128 + 2;
-    const size_t smem = (((size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 15) & ~(size_t)15) + (size_t)MAXCHUNKS * 16 +
+    constexpr int OUTCHUNKS = (VAR >= 3) ? kSmallOutChunks : MAXCHUNKS;
+    const size_t smem = (((size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 15) & ~(size_t)15) + (size_t)OUTCHUNKS * 16 +
                         (kQueueCap + TB + (kQueueCap + TB) / 2) * sizeof(unsigned) + 3 * TB;
     static bool configured = false;
     if (!configured) {
@@ -895,6 +970,12 @@ int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStrea
     } else if (var == 2) {
         if (N == 8) return launch_cfg<8, 1, false, true, 2>(p, images, stream);
         if (N == 4) return launch_cfg<4, 4, false, true, 2>(p, images, stream);
+    } else if (var == 3) {
+        if (N == 8) return launch_cfg<8, 1, false, true, 3>(p, images, stream);
+        if (N == 4) return launch_cfg<4, 4, false, true, 3>(p, images, stream);
+    } else if (var == 4) {
+        if (N == 8) return launch_cfg<8, 1, false, true, 4>(p, images, stream);
+        if (N == 4) return launch_cfg<4, 4, false, true, 4>(p, images, stream);
     }
     if (N == 8) return exact ? launch_cfg<8, 1, false, false>(p, images, stream) : launch_cfg<8, 1, false, true>(p, images, stream);
     if (N == 4) return exact ? launch_cfg<4, 4, false, false>(p, images, stream) : launch_cfg<4, 4, false, true>(p, images, stream);

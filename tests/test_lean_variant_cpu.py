@@ -33,7 +33,9 @@ def test_encode_variant_option_is_validated():
     try:
         assert L.ie_set_option(b"encode_variant", 1) == 0
         assert L.ie_set_option(b"encode_variant", 2) == 0
-        assert L.ie_set_option(b"encode_variant", 3) != 0
+        assert L.ie_set_option(b"encode_variant", 3) == 0
+        assert L.ie_set_option(b"encode_variant", 4) == 0
+        assert L.ie_set_option(b"encode_variant", 5) != 0
         assert L.ie_set_option(b"encode_variant", -1) != 0
     finally:
         assert L.ie_set_option(b"encode_variant", 2) == 0          # the default

@@ -23,6 +23,17 @@ def test_variant_streams_identical(variant):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.xfail(strict=False, reason="encode variants 3 / 4 (reduced staging area, 7 / 8 CTAs per SM) were written after this "
+                                        "round's GPU budget was spent; this is their first run on a B200; NOT the default kernel")
+@pytest.mark.parametrize("variant", [3, 4])
+def test_reduced_staging_variant_streams_identical(variant):
+    """the noise / quantiser-1 cases of the worker overflow the reduced staging area and take the global-memory pack"""
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "_variant_worker.py"), str(variant)], capture_output=True, text=True,
+                       timeout=900)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.xfail(strict=False, reason="decode variant 1 was written after this round's GPU budget was spent: its arithmetic is "
                                         "checked on the CPU (tests/host/lean_check.cu), its first run on a B200 is this one; "
                                         "it is NOT the default kernel")
