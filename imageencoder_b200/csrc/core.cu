@@ -211,9 +211,10 @@ uint64_t ie_kernel_launch_count(void) { return ie::g_launches.load(); }
 int ie_set_option(const char *name, int value) {
     if (name && !strcmp(name, "exact_transform")) { ie::g_exact_transform.store(value); return IE_OK; }
     if (name && !strcmp(name, "encode_variant")) {
-        if (value < 0 || value > 4) {
+        if (value < 0 || value > 7) {
             ie::set_error("encode_variant: 0 (scalar kernel), 1 (lean quantise), 2 (1 + packed f32x2 transform, the default), "
-                          "3 / 4 (2 with a reduced staging area and 7 / 8 CTAs per SM, experimental)");
+                          "3 / 4 (2 with a reduced staging area and 7 / 8 CTAs per SM), 5 (2 with the short-chain binary64 pre-check of "
+                          "the exact queue), 6 / 7 (3 / 4 with it); 3..7 are experimental");
             return IE_EINVAL;
         }
         ie::g_encode_variant.store(value);

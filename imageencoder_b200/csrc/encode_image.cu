@@ -95,6 +95,44 @@ __device__ __noinline__ int exact_coefficient(const ExactCtx p, unsigned gb, int
     return (int)(short)__double2int_rz(round_half_away(__ddiv_rn(e, m_uv)));
 }
 
+// Short-chain binary64 evaluation of one queued coefficient (transform_fast.cuh, "fast64"): true and q set if the quotient is
+// clear of every rounding boundary, false if only the exact-order chain (exact_coefficient) can decide.
+template <int N, bool PF>
+__device__ __forceinline__ bool fast64_coefficient(const ExactCtx &p, unsigned gb, int uv, double m_uv, int &q) {
+    const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
+    int rx = 0, ry = 0;
+    if (PF) {
+        const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
+        rx = p.res_coord[2 * mb] + (int)(bxi & 3) * 4;
+        ry = p.res_coord[2 * mb + 1] + (int)(byi & 3) * 4;
+    }
+    const int u = uv / N, v = uv % N;
+    const uint8_t *blk = p.src + (size_t)(byi * N) * p.pitch + (size_t)bxi * N;
+    unsigned lo[N], hi[N];
+    double a[N], b[N];
+#pragma unroll
+    for (int y = 0; y < N; y++) {
+        hi[y] = 0;
+        if (N == 8) { const uint2 w = *reinterpret_cast<const uint2 *>(blk + (size_t)y * p.pitch); lo[y] = w.x; hi[y] = w.y; }
+        else lo[y] = *reinterpret_cast<const unsigned *>(blk + (size_t)y * p.pitch);
+        a[y] = __ldg(p.tab->cs + y * N + u);
+        b[y] = __ldg(p.tab->cs + y * N + v);
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int y = 0; y < N; y++) {
+        int xr[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            int px = (int)(((k < 4 ? lo[y] : hi[y]) >> (8 * (k & 3))) & 0xffu);
+            if (PF) px -= (int)__ldg(p.ref + (size_t)(ry + y) * p.pitch + rx + k);                  // Block.cpp:262
+            xr[k] = px - 128;                                                                      // Block.cpp:141-143
+        }
+        acc = fma(a[y], lean::row_dot64<N>(b, xr), acc);
+    }
+    return lean::decide64(acc, p.tab->cc[uv], m_uv, q);
+}
+
 // The pack loop of encode_tiles_kernel's phase 3 (same statements) writing to any address space: used by the reduced-staging
 // instantiations (encode_variant 3 / 4) when a tile image is larger than their shared-memory staging area and is packed straight
 // into the tile's slot of the global scratch buffer instead.  Every lane writes its blocks' fields MSB-first into the image of
@@ -153,12 +191,15 @@ __device__ __forceinline__ void pack_tile_blocks(unsigned *outw, const short *s_
 
 constexpr int kQueueCap = 128;        // guard-band fallback entries per tile handled by the CTA-wide queue
 
-// VAR: 0 scalar transform, 1 lean quantise, 2 packed transform + lean quantise (default), 3 / 4 = 2 with a reduced staging area
-// for the tile image (kSmallOutChunks chunks instead of the worst case; larger tile images are packed in global memory) and
-// 7 / 8 CTAs per SM instead of 6 (experimental, not yet run on a B200)
+// VAR: 0 scalar transform, 1 lean quantise, 2 packed transform + lean quantise (default); experimental, not yet run on a B200:
+// 3 / 4 = 2 with a reduced staging area for the tile image (kSmallOutChunks chunks instead of the worst case; larger tile
+// images are packed in global memory) and 7 / 8 CTAs per SM instead of 6; 5 = 2 with the short-chain binary64 evaluation in
+// front of the exact queue ("fast64", transform_fast.cuh); 6 / 7 = 3 / 4 with fast64.
 constexpr int kSmallOutChunks = 512;
+constexpr bool var_small_out(int VAR) { return VAR == 3 || VAR == 4 || VAR == 6 || VAR == 7; }
+constexpr bool var_fast64(int VAR) { return VAR >= 5; }
 constexpr int encode_min_ctas(int N, bool PF, bool FAST, int VAR) {
-    return (N == 8 && !FAST) ? 1 : (FAST && !PF ? (VAR == 3 ? 7 : VAR == 4 ? 8 : 6) : 2);
+    return (N == 8 && !FAST) ? 1 : (FAST && !PF ? ((VAR == 3 || VAR == 6) ? 7 : (VAR == 4 || VAR == 7) ? 8 : 6) : 2);
 }
 
 template <int N, int BPL, bool PF, bool FAST, int VAR = 0>
@@ -168,7 +209,8 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
     constexpr int STRIDE = NN + 2;                // halfwords per block in the staging area: NN/2 + 1 words (odd -> bank spread)
     constexpr int NSEG = NN / 8;
     constexpr int MAXCHUNKS = (TB * (4 + 16 + 16 * NN) + 127) / 128 + 2;
-    constexpr bool SMALL_OUT = VAR >= 3;
+    constexpr bool SMALL_OUT = var_small_out(VAR);
+    constexpr bool FAST64 = var_fast64(VAR);
     constexpr int OUTCHUNKS = SMALL_OUT ? kSmallOutChunks : MAXCHUNKS;     // staging area for the tile image, in 128-bit chunks
     extern __shared__ __align__(16) unsigned char smem[];
     short *s_coef = reinterpret_cast<short *>(smem);
@@ -355,7 +397,13 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
             for (unsigned e = threadIdx.x; e < qn; e += kThreads) {
                 const unsigned ent = s_queue[e];
                 const int lb = (int)(ent >> 8), uv = (int)(ent & 0xff);
-                const int q = exact_coefficient<N, PF>(ex, first_blk + lb, uv, p.quant.m[uv]);
+                int q;
+                if (FAST64) {
+                    if (!fast64_coefficient<N, PF>(ex, first_blk + lb, uv, p.quant.m[uv], q))
+                        q = exact_coefficient<N, PF>(ex, first_blk + lb, uv, p.quant.m[uv]);
+                } else {
+                    q = exact_coefficient<N, PF>(ex, first_blk + lb, uv, p.quant.m[uv]);
+                }
                 short *cf = s_coef + (size_t)lb * STRIDE;
                 const int k = tab->izz[uv];
                 if (cf[k] != (short)q) {
@@ -933,7 +981,7 @@ static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t strea
     constexpr int TB = kThreads * BPL;
     constexpr int STRIDE = N * N + 2;
     constexpr int MAXCHUNKS = (TB * (4 + 16 + 16 * N * N) + 127) / 128 + 2;
-    constexpr int OUTCHUNKS = (VAR >= 3) ? kSmallOutChunks : MAXCHUNKS;
+    constexpr int OUTCHUNKS = var_small_out(VAR) ? kSmallOutChunks : MAXCHUNKS;
     const size_t smem = (((size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 15) & ~(size_t)15) + (size_t)OUTCHUNKS * 16 +
                         (kQueueCap + TB + (kQueueCap + TB) / 2) * sizeof(unsigned) + 3 * TB;
     static bool configured = false;
@@ -977,6 +1025,9 @@ int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStrea
         if (N == 8) return launch_cfg<8, 1, false, true, 4>(p, images, stream);
         if (N == 4) return launch_cfg<4, 4, false, true, 4>(p, images, stream);
     }
+    if (var == 5) { if (N == 8) return launch_cfg<8, 1, false, true, 5>(p, images, stream); if (N == 4) return launch_cfg<4, 4, false, true, 5>(p, images, stream); }
+    if (var == 6) { if (N == 8) return launch_cfg<8, 1, false, true, 6>(p, images, stream); if (N == 4) return launch_cfg<4, 4, false, true, 6>(p, images, stream); }
+    if (var == 7) { if (N == 8) return launch_cfg<8, 1, false, true, 7>(p, images, stream); if (N == 4) return launch_cfg<4, 4, false, true, 7>(p, images, stream); }
     if (N == 8) return exact ? launch_cfg<8, 1, false, false>(p, images, stream) : launch_cfg<8, 1, false, true>(p, images, stream);
     if (N == 4) return exact ? launch_cfg<4, 4, false, false>(p, images, stream) : launch_cfg<4, 4, false, true>(p, images, stream);
     set_error("block size must be 4 or 8");

@@ -508,5 +508,37 @@ IE_HD void pixel_stage(const float2 *P2, float hi_thr, unsigned *outw, unsigned 
     pixel_stage_impl<N>(P2, hi_thr, outw, unsure_lo, unsure_hi, std::make_integer_sequence<int, N * (N / 4)>{});
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Exact-queue variant "fast64" (encode_variant 5 / 6 / 7, experimental): a guard-band coefficient is first evaluated in binary64
+// in a SHORT chain -- N row dot products b . x[y] (independent chains of N fused multiply-adds), then their combination with
+// a[y] (N more) -- instead of the reference's 2*N*N sequentially rounded operations.  Both are evaluations of the same real
+// number sum_y sum_k a[y] b[k] x[y][k]; with |a|, |b| <= 1 and |x| <= 383 (P-frame residual - 128) the reference's chain
+// (algo.cpp:309-331: N*N rounded factor products, N*N rounded products with x, N*N rounded additions) deviates from it by at
+// most (N*N + 2) u S and this one by at most (2N + 2) u S, S = sum |a b x| <= N*N * 383, u = 2^-53: together < 2.2e-10 on the
+// sum at N = 8, < 1.2e-10 on the quotient t = sum * cc / m (cc <= 0.5, m >= 1; the three roundings of t add < 1e-11).  So when
+// t lies further than 1e-8 (80x that) from every rounding boundary k + 0.5, std::round of the reference's value and of this one
+// agree; otherwise -- true ties, SURVEY 0.3, and nothing else in practice -- the caller falls back to the exact-order chain.
+// tests/host/lean_check.cu runs this arithmetic on the CPU against the exact chain (random, tie-heavy and saturated blocks).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int N>
+IE_HD double row_dot64(const double *b, const int *xr) {
+    double r = 0.0;
+IE_UNROLL
+    for (int k = 0; k < N; k++) r = fma(b[k], (double)xr[k], r);
+    return r;
+}
+
+constexpr double kFast64Guard = 1e-8;
+
+// acc = the short-chain sum; returns false if the quotient is within the guard of a rounding boundary (q untouched)
+IE_HD bool decide64(double acc, double cc, double m, int &q) {
+    const double t = acc * cc / m;
+    const double at = fabs(t), fl = floor(at), fr = at - fl;           // fr exact
+    if (fabs(fr - 0.5) <= kFast64Guard) return false;
+    const double r = (fr > 0.5) ? fl + 1.0 : fl;
+    q = (int)(short)(int)(t < 0.0 ? -r : r);                            // Block.cpp:205: int16_t(double)
+    return true;
+}
+
 }  // namespace lean
 }  // namespace ie

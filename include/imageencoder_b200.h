@@ -166,8 +166,11 @@ int ie_stream_shift_dev(const uint8_t *d_in, const uint64_t *d_params, uint8_t *
 /* Diagnostics switches (process-wide; every setting produces identical streams, tests cross-check them):
  *   "exact_transform" = 1  the encoders evaluate every coefficient in the reference's exact binary64 order instead of the
  *                          guarded FP32 fast path;
- *   "encode_variant"  = 0 | 1 | 2 (default)  instantiation of the tile kernel: 2 = packed f32x2 transform + quantise,
+ *   "encode_variant"  = 0 | 1 | 2 (default) | 3..7  instantiation of the tile kernel: 2 = packed f32x2 transform + quantise,
  *                          1 = packed quantise only, 0 = the scalar kernel they replaced (A/B timing, cross-checks);
+ *                          experimental (arithmetic checked on the CPU, not yet timed): 3 / 4 = 2 with an 8 KiB staging area
+ *                          for the tile image and 7 / 8 CTAs per SM, 5 = 2 with a short-chain binary64 pre-check in front
+ *                          of the exact queue, 6 / 7 = 3 / 4 with that pre-check;
  *   "copyout_variant" = 0 | 1 | 2 (default)  copy-out kernel: 2 = short path for interior chunks with four chunks per
  *                          thread in flight, 1 = short path one chunk at a time, 0 = the generic kernel;
  *   "decode_variant"  = 0 (default) | 1  block-decode kernel of images and I-frames: 1 = inverse transform and pixel

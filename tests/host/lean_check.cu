@@ -7,6 +7,8 @@
 //     bits_needed, segment non-zero flags
 //   * variant 2 (lean::fdct2d_packed + quantise_block_packed): additionally the packed transform, bit for bit
 //   * decode variant 1 (lean::idct2d_packed + lean::pixel_stage): inverse transform bit for bit, output words, `unsure` mask
+//   * exact-queue variant "fast64" (lean::row_dot64 + lean::decide64): every coefficient it decides equals the reference's
+//     exact-order chain (algo.cpp:309-331, Block.cpp:152), the quotients differ by < 1e-9, true ties are left undecided
 // and the integer DC rounding against round_half_away(S / (4 Q00)) in exact integer arithmetic.
 #include <cstdio>
 #include <cstdlib>
@@ -288,13 +290,91 @@ static void run_decode(long long nblocks, unsigned seed) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// exact-queue variant "fast64": lean::row_dot64 + lean::decide64 against the reference's exact-order chain
+// (transcription of exact_coefficient, encode_image.cu; this file is compiled without FMA contraction)
+// ---------------------------------------------------------------------------------------------------------------------
+static long long g_f64_decided = 0, g_f64_undecided = 0;
+static double g_f64_maxdev = 0.0;
+
+template <int N>
+static void run_fast64(long long nblocks, unsigned seed) {
+    constexpr int NN = N * N;
+    std::mt19937 rng(seed);
+    double cs[NN], cc[NN];
+    const double f = M_PI_2 / double(N);
+    for (int i = 0; i < N; i++)
+        for (int u = 0; u < N; u++) cs[i * N + u] = std::cos(double(2.0 * i + 1.0) * double(u) * f);
+    for (int u = 0; u < N; u++)
+        for (int v = 0; v < N; v++) cc[u * N + v] = ((u == 0) ? 0.5 : M_SQRT1_2) * ((v == 0) ? 0.5 : M_SQRT1_2);
+    for (long long blk = 0; blk < nblocks; blk++) {
+        int x[NN];
+        const int mode = (int)(rng() % 7);
+        const int base = (int)(rng() % 256) - 128;
+        for (int i = 0; i < NN; i++) {
+            switch (mode) {
+            case 0: x[i] = (int)(rng() % 256) - 128; break;                               // pixels - 128
+            case 1: x[i] = (int)(rng() % 511) - 255 - 128; break;                         // P-frame residual - 128
+            case 2: x[i] = (rng() & 1) ? 8 : -8; break;                                   // two levels: ties at the rational positions
+            case 3: x[i] = (int)(rng() % 4) * 8 - 16; break;                              // four levels
+            case 4: x[i] = (rng() & 1) ? 127 : -383; break;                               // saturated
+            case 5: x[i] = base; break;                                                   // flat
+            default: x[i] = base + (int)(rng() % 5) - 2; break;                           // nearly flat
+            }
+        }
+        const int mq = (int)(rng() % 4);
+        for (int uv = 0; uv < NN; uv++) {
+            const int u = uv / N, v = uv % N;
+            const double m = (mq == 0) ? 1.0 : (mq == 1) ? 2.0 : (mq == 2) ? 16.0 : (double)(1 + rng() % 255);
+            // the reference's chain
+            double acc = 0.0;
+            for (int i = 0; i < N; i++)
+                for (int j = 0; j < N; j++) {
+                    volatile double ab = cs[i * N + u] * cs[j * N + v];
+                    volatile double t = ab * (double)x[i * N + j];
+                    volatile double sum = acc + t;
+                    acc = sum;
+                }
+            volatile double e = acc * cc[uv];
+            volatile double tq = e / m;
+            const double a0 = fabs(tq);
+            double r0 = floor(a0);
+            if (a0 - r0 >= 0.5) r0 += 1.0;                                                 // std::round: half away from zero
+            const int q_ref = (int)(short)(int)copysign(r0, tq);
+            // fast64
+            double a[N], b[N];
+            for (int y = 0; y < N; y++) { a[y] = cs[y * N + u]; b[y] = cs[y * N + v]; }
+            double acc2 = 0.0;
+            for (int y = 0; y < N; y++) acc2 = fma(a[y], lean::row_dot64<N>(b, x + y * N), acc2);
+            int q = 0x7fffffff;
+            const bool decided = lean::decide64(acc2, cc[uv], m, q);
+            const double dev = fabs(acc2 * cc[uv] / m - tq);
+            if (dev > g_f64_maxdev) g_f64_maxdev = dev;
+            CHECK(dev < 1e-9, "fast64 block %lld uv %d: quotient deviates by %g", blk, uv, dev);
+            if (decided) {
+                g_f64_decided++;
+                CHECK(q == q_ref, "fast64 block %lld uv %d (mode %d, m %g): decided %d, reference %d (t = %.17g)", blk, uv, mode, m, q, q_ref,
+                      (double)tq);
+            } else {
+                g_f64_undecided++;
+                const double fr = a0 - floor(a0);
+                CHECK(fabs(fr - 0.5) < 2e-8, "fast64 block %lld uv %d: undecided although t = %.17g is clear of a boundary", blk, uv, (double)tq);
+            }
+        }
+    }
+}
+
 int main(int argc, char **argv) {
     const long long n = (argc > 1) ? atoll(argv[1]) : 200000;
     if (run<8>(n, 12345u) || run<4>(n, 54321u)) return 2;
     run_decode<8>(n, 777u);
     run_decode<4>(n, 888u);
+    run_fast64<8>(n / 8 + 1, 4242u);
+    run_fast64<4>(n / 2 + 1, 2424u);
     if (g_fail) { printf("lean_check: %lld failures\n", g_fail); return 1; }
     printf("lean_check: ok (%lld encode blocks per block size with 6 quant matrices, encode variants 1 and 2; %lld decode blocks per "
-           "block size with 4 matrices, decode variant 1)\n", n * 6, n * 4);
+           "block size with 4 matrices, decode variant 1; fast64: %lld coefficients decided, %lld left to the exact chain, max "
+           "quotient deviation %.3g)\n", n * 6, n * 4, g_f64_decided, g_f64_undecided, g_f64_maxdev);
     return 0;
 }
