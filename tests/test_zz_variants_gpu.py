@@ -31,7 +31,7 @@ def test_experimental_variant_streams_identical(variant):
     """the noise / quantiser-1 cases of the worker overflow the reduced staging area and take the global-memory pack; the
     checker / two-level cases are tie-heavy (exact queue)"""
     r = subprocess.run([sys.executable, str(ROOT / "tests" / "_variant_worker.py"), str(variant)], capture_output=True, text=True,
-                       timeout=900)
+                       timeout=180)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
@@ -43,7 +43,7 @@ def test_decode_variant_pixels_identical():
     """ie_set_option("decode_variant", 1): packed f32x2 inverse transform + pixel stage (decode_blocks_lean_kernel); own process
     so that a fault in the experimental kernel cannot poison this process's CUDA context."""
     r = subprocess.run([sys.executable, str(ROOT / "tests" / "_variant_worker.py"), "dec1"], capture_output=True, text=True,
-                       timeout=900)
+                       timeout=180)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
