@@ -10,6 +10,7 @@
 //   huff_decode_kernel    table-driven decode (Huffman.cpp:190-204, 376-383)
 #include <algorithm>
 #include <cstring>
+#include <memory_resource>
 #include <queue>
 #include <unordered_map>
 #include <vector>
@@ -440,23 +441,26 @@ namespace {
 struct HNode { uint8_t data; size_t freq; HNode *left, *right; };
 struct HNodeCmp { bool operator()(const HNode *a, const HNode *b) const { return a->freq > b->freq; } };   // Huffman.hpp:70-74
 struct HCode { uint32_t word, len; };
+using HDict = std::pmr::unordered_map<uint8_t, HCode>;
 
-void walk(const HNode *n, uint32_t word, uint32_t len, std::unordered_map<uint8_t, HCode> &dict) {       // Huffman.cpp:79-104
+void walk(const HNode *n, uint32_t word, uint32_t len, HDict &dict) {                                    // Huffman.cpp:79-104
     if (!n) return;
     if (!n->left && !n->right) { dict[n->data] = HCode{word, len}; return; }
     walk(n->left, word << 1, len + 1, dict);
     walk(n->right, (word << 1) | 1u, len + 1, dict);
 }
-void destroy(HNode *n) { if (!n) return; destroy(n->left); destroy(n->right); delete n; }
 
 struct HostBitWriter {
     std::vector<uint8_t> buf;
     size_t pos = 0;
-    void put(unsigned len, uint32_t v) {
-        for (unsigned p = 0; p < len; p++) {
-            if ((pos >> 3) >= buf.size()) buf.resize(buf.size() + 256, 0);
-            if ((v >> (len - 1 - p)) & 1u) buf[pos >> 3] |= uint8_t(1u << (7 - (pos & 7)));
-            pos++;
+    void put(unsigned len, uint32_t v) {                        // BitStream.cpp:73-77, MSB first; up to a byte per step
+        if (((pos + len + 7) >> 3) > buf.size()) buf.resize(((pos + len + 7) >> 3) + 1024, 0);
+        while (len) {
+            const unsigned room = 8u - (unsigned)(pos & 7), take = len < room ? len : room;
+            const unsigned bits = (v >> (len - take)) & ((1u << take) - 1u);
+            buf[pos >> 3] |= uint8_t(bits << (room - take));
+            pos += take;
+            len -= take;
         }
     }
 };
@@ -464,28 +468,38 @@ struct HostBitWriter {
 
 // hist/first -> codes + dictionary header bits.  Returns IE_EINVAL when a code would exceed 32 bits (the reference's
 // uint32 code words overflow there, Huffman.cpp:86-88).
+// The reference's tie-breaking is whatever libstdc++'s unordered_map iteration order, priority_queue heap order and (unstable)
+// std::sort produce when fed in its order, so the containers and the sequence of operations on them are exactly
+// the reference's; only their storage comes from one stack arena (polymorphic allocators change neither hashing nor bucket
+// growth) and the tree nodes from a fixed pool -- 114 -> 26 us per call on the bench stream's histogram (tests/host/huffdict_check.cu compares
+// this function with the plain-allocator transcription it replaced on random histograms).
 static int build_dictionary(const unsigned *hist, const unsigned long long *first, HuffCodes &codes, HostBitWriter &hdr) {
-    std::vector<int> syms;
+    alignas(16) unsigned char arena[64 * 1024];
+    std::pmr::monotonic_buffer_resource pool(arena, sizeof arena);       // spills to the heap if ever exhausted
+    std::pmr::vector<int> syms(&pool);
+    syms.reserve(256);
     for (int i = 0; i < 256; i++) if (hist[i]) syms.push_back(i);
     if (syms.empty()) { set_error("empty input for the Huffman stage"); return IE_EINVAL; }
     std::sort(syms.begin(), syms.end(), [&](int a, int b) { return first[a] < first[b]; });
-    std::unordered_map<uint8_t, uint32_t> freqs;                           // Huffman.cpp:237-243 (insertion = first occurrence)
+    std::pmr::unordered_map<uint8_t, uint32_t> freqs(&pool);               // Huffman.cpp:237-243 (insertion = first occurrence)
     for (int s : syms) freqs[(uint8_t)s] = hist[s];
-    std::priority_queue<HNode *, std::vector<HNode *>, HNodeCmp> pq;       // Huffman.cpp:246-251
-    for (const auto &pr : freqs) pq.push(new HNode{pr.first, pr.second, nullptr, nullptr});
+    HNode nodes[511];                                                      // 256 leaves + 255 inner nodes at most
+    int nn = 0;
+    std::priority_queue<HNode *, std::pmr::vector<HNode *>, HNodeCmp> pq{HNodeCmp(), std::pmr::vector<HNode *>(&pool)};   // Huffman.cpp:246-251
+    for (const auto &pr : freqs) { nodes[nn] = HNode{pr.first, pr.second, nullptr, nullptr}; pq.push(&nodes[nn++]); }
     while (pq.size() > 1) {                                                // Huffman.cpp:253-260
         HNode *l = pq.top(); pq.pop();
         HNode *r = pq.top(); pq.pop();
-        pq.push(new HNode{0xFF, l->freq + r->freq, l, r});
+        nodes[nn] = HNode{0xFF, l->freq + r->freq, l, r};
+        pq.push(&nodes[nn++]);
     }
     HNode *root = pq.top();
-    std::unordered_map<uint8_t, HCode> dict;
+    HDict dict(&pool);
     walk(root, 0, 0, dict);                                                // Huffman.cpp:266
-    destroy(root);
-    std::vector<std::pair<uint8_t, HCode>> sorted(dict.begin(), dict.end());   // Huffman.cpp:269
+    std::pmr::vector<std::pair<uint8_t, HCode>> sorted(dict.begin(), dict.end(), &pool);   // Huffman.cpp:269
     std::sort(sorted.begin(), sorted.end(),                                 // Huffman.cpp:272 (unstable, len descending)
               [](const std::pair<uint8_t, HCode> &a, const std::pair<uint8_t, HCode> &b) { return a.second.len > b.second.len; });
-    std::unordered_map<uint32_t, uint32_t> bit_freqs;
+    std::pmr::unordered_map<uint32_t, uint32_t> bit_freqs(&pool);
     for (const auto &w : sorted) bit_freqs[w.second.len]++;
     uint32_t seq_len = 0, bit_len = 0;
     for (const auto &w : sorted) {                                         // Huffman.cpp:298-309
