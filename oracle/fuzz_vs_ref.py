@@ -25,8 +25,8 @@ import oracle  # noqa: E402
 
 def image_case(rng):
     N = int(rng.choice([4, 8]))
-    W = N * int(rng.integers(1, 20))
-    H = N * int(rng.integers(1, 20))
+    W = N * int(rng.integers(1, 20 if rng.integers(0, 4) else 64))
+    H = N * int(rng.integers(1, 20 if rng.integers(0, 4) else 64))
     kind = int(rng.integers(0, 6))
     if kind == 0:
         img = rng.integers(0, 256, (H, W))
