@@ -10,6 +10,7 @@
 //   mc_copy_kernel     decoder: out[MB] = ref[clamp(MB + mv)] (Block.cpp:481-496)
 // Frames are strictly sequential inside a GOP (each P-frame searches the reconstruction of its predecessor,
 // Frame.cpp:210-242); frames append to one stream through the device-resident bit counter (pack.cuh contract).
+#include <atomic>
 #include <cstring>
 #include <vector>
 
@@ -34,117 +35,17 @@ struct MEParams {
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __global__ void __launch_bounds__(256) me_search_kernel(MEParams p) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mb = blockIdx.x * 8 + warp;
-    if (mb >= p.nmb) return;
-    p.cur += (size_t)blockIdx.y * p.frame_stride; p.ref += (size_t)blockIdx.y * p.frame_stride;
-    p.mv += (size_t)blockIdx.y * p.mv_stride; p.res_coord += (size_t)blockIdx.y * p.mv_stride; p.copy_coord += (size_t)blockIdx.y * p.mv_stride;
-    const int mbx = (mb % p.mx) * kMB, mby = (mb / p.mx) * kMB;
-    const int row = lane >> 1, half = lane & 1;
-    const uint2 c = *reinterpret_cast<const uint2 *>(p.cur + (size_t)(mby + row) * p.W + mbx + half * 8);
-    // Search window of this MacroBlock in shared memory (per warp): every candidate of the log search lies within +-15
-    // pixels of the block (steps merange/2 .. 1 with merange <= 16) and inside the frame, i.e. in the 46 x 46 pixels from
-    // (mbx - 15, mby - 15); rows are kept 13 words apart (odd: the 16 rows a candidate touches fall into different banks).
-    // Candidates read straight from global memory cost 16 sectors per load instruction (one per row) -- 19x the traffic.
-    constexpr int kWinRows = 46, kWinWords = 13;
-    __shared__ unsigned s_win[8][kWinRows * kWinWords];
-    const bool staged = p.merange <= 16;
-    const int wy0 = max(mby - 15, 0), wxa = max(mbx - 15, 0) & ~3;
-    unsigned *win = s_win[warp];
-    if (staged) {
-        constexpr int kIters = (kWinRows * kWinWords + 31) / 32;
-        unsigned v[kIters];
-#pragma unroll
-        for (int i = 0; i < kIters; i++) {                  // all loads in flight before the first store
-            const int idx = lane + 32 * i;
-            const int r = idx / kWinWords, k = idx - r * kWinWords;
-            const int y = wy0 + r, x = wxa + 4 * k;
-            v[i] = (idx < kWinRows * kWinWords && y < p.H && x + 4 <= p.W) ? __ldg(reinterpret_cast<const unsigned *>(p.ref + (size_t)y * p.W + x)) : 0u;
-        }
-#pragma unroll
-        for (int i = 0; i < kIters; i++) {
-            const int idx = lane + 32 * i;
-            if (idx < kWinRows * kWinWords) win[idx] = v[i];
-        }
-        __syncwarp();
-    }
-    int best_x = 0, best_y = 0;
-    int bcx = 0, bcy = 0;                                  // Block.cpp:273: the initial block is the one at pixel (0,0)
-    unsigned best_d = 0xffffffffu;
-    for (int step = p.merange / 2; step > 0; step >>= 1) {  // algo.cpp:129,138
-        // the 9 candidates of a level are independent: all their loads are issued first, the 9 SAD partial sums are
-        // reduced two to a register (a MacroBlock's SAD is <= 256 * 255 < 2^16), and only the selection runs in the
-        // reference's order (Block.cpp:289-317)
-        // candidate coordinates come from three x and three y values (offset -step, 0, +step): clamp each once
-        int cx3[3], cy3[3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            cx3[j] = clampi((int)(short)(best_x + (j - 1) * step + mbx), 0, p.W - kMB);
-            cy3[j] = clampi((int)(short)(best_y + (j - 1) * step + mby), 0, p.H - kMB);
-        }
-        // compile-time candidate order (MER_SIGNS, algo.cpp:90-100): index into the three values
-        constexpr int kSX[9] = {1, 2, 2, 1, 0, 0, 0, 1, 2}, kSY[9] = {1, 1, 2, 2, 2, 1, 0, 0, 0};
-        int cpx[9], cpy[9];
-        unsigned w0[9], w1[9], w2[9], shq[9];
-        if (staged) {
-            int xw[3], rb[3];
-            unsigned xs[3];
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const int bx = cx3[j] - wxa + half * 8;                         // byte offset inside the window row
-                xw[j] = bx >> 2; xs[j] = (unsigned)(bx & 3) * 8;
-                rb[j] = (cy3[j] - wy0 + row) * kWinWords;
-            }
-#pragma unroll
-            for (int q = 0; q < 9; q++) {
-                cpx[q] = cx3[kSX[q]]; cpy[q] = cy3[kSY[q]];
-                const unsigned *wp = win + rb[kSY[q]] + xw[kSX[q]];
-                shq[q] = xs[kSX[q]];
-                w0[q] = wp[0]; w1[q] = wp[1]; w2[q] = wp[2];                    // word 2 is inside the window row (<= 12)
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 9; q++) {
-                cpx[q] = cx3[kSX[q]]; cpy[q] = cy3[kSY[q]];
-                const uint8_t *rp = p.ref + (size_t)(cpy[q] + row) * p.W + cpx[q] + half * 8;
-                const uintptr_t a = (uintptr_t)rp;
-                const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
-                shq[q] = (unsigned)(a & 3) * 8;
-                w0[q] = __ldg(wp); w1[q] = __ldg(wp + 1); w2[q] = shq[q] ? __ldg(wp + 2) : 0u;
-            }
-        }
-        unsigned d[9];
-#pragma unroll
-        for (int q = 0; q < 9; q++) {
-            const unsigned r0 = __funnelshift_r(w0[q], w1[q], shq[q]), r1 = __funnelshift_r(w1[q], w2[q], shq[q]);
-            d[q] = __vsadu4(c.x, r0) + __vsadu4(c.y, r1);                      // Block.cpp:241-254 (this lane's 8 pixels)
-        }
-        unsigned pk[5] = {d[0] | (d[1] << 16), d[2] | (d[3] << 16), d[4] | (d[5] << 16), d[6] | (d[7] << 16), d[8]};
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 5; k++) pk[k] += __shfl_xor_sync(0xffffffffu, pk[k], o);
-        }
-        int bq = -1, ncx = 0, ncy = 0;
-        unsigned nd = best_d;
-#pragma unroll
-        for (int q = 0; q < 9; q++) {
-            if (q > 0 && cpx[q] == mbx && cpy[q] == mby) continue;             // Block.cpp:297-301
-            const unsigned dq = (q == 8) ? pk[4] : ((q & 1) ? (pk[q >> 1] >> 16) : (pk[q >> 1] & 0xffffu));
-            if (dq <= nd) { bq = q; nd = dq; ncx = cpx[q]; ncy = cpy[q]; }     // Block.cpp:306
-        }
-        if (bq < 0) break;                                                      // Block.cpp:318-321 (never taken)
-        best_x += c_mer_sx[bq] * step; best_y += c_mer_sy[bq] * step; best_d = nd; bcx = ncx; bcy = ncy;
-    }
-    if (lane == 0) {
-        p.mv[2 * mb] = (short)best_x;
-        p.mv[2 * mb + 1] = (short)best_y;
-        p.res_coord[2 * mb] = (short)bcx;
-        p.res_coord[2 * mb + 1] = (short)bcy;
-        p.copy_coord[2 * mb] = (short)clampi((int)(short)(mbx + best_x), 0, p.W - kMB);
-        p.copy_coord[2 * mb + 1] = (short)clampi((int)(short)(mby + best_y), 0, p.H - kMB);
-    }
+#define IE_ME_REDUX 0
+#include "me_search_body.inc"
+#undef IE_ME_REDUX
 }
+// ie_set_option("me_variant", 1) (experimental, not yet run on a B200): SAD partial sums reduced with REDUX
+__global__ void __launch_bounds__(256) me_search_redux_kernel(MEParams p) {
+#define IE_ME_REDUX 1
+#include "me_search_body.inc"
+#undef IE_ME_REDUX
+}
+std::atomic<int> g_me_variant{0};
 
 // fixed-width fields: field i = low `bits` bits of val[i]
 struct FixedFieldTile {
@@ -412,7 +313,8 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
             me.cur = cur; me.ref = cur - fsz; me.W = (int)W; me.H = (int)H; me.mx = (int)(W / kMB); me.nmb = (int)nmb;
             me.merange = (int)merange; me.mv = vs.mv; me.res_coord = vs.res; me.copy_coord = vs.copy;
             me.frame_stride = p.img_stride; me.mv_stride = p.coord_stride;
-            me_search_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, st>>>(me);
+            if (g_me_variant.load() == 1) me_search_redux_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, st>>>(me);
+            else me_search_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, st>>>(me);
             count_launch();
             mvec_pack_kernel<<<dim3(1, act), kThreads, 0, st>>>(vs.mv, p.coord_stride, nmb * 2, mvbits, s->d_tmp, gop_cap, gop_cap, s->d_counter,
                                                                s->d_err);

@@ -15,6 +15,7 @@ extern std::atomic<int> g_exact_transform;   // encode_image.cu
 extern std::atomic<int> g_encode_variant;
 extern std::atomic<int> g_copyout_variant;
 extern std::atomic<int> g_decode_variant;      // decode_image.cu
+extern std::atomic<int> g_me_variant;          // api_video.cu
 static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
 
@@ -228,6 +229,11 @@ int ie_set_option(const char *name, int value) {
     if (name && !strcmp(name, "decode_variant")) {
         if (value < 0 || value > 1) { ie::set_error("decode_variant: 0 (default) or 1 (packed f32x2 inverse transform, experimental)"); return IE_EINVAL; }
         ie::g_decode_variant.store(value);
+        return IE_OK;
+    }
+    if (name && !strcmp(name, "me_variant")) {
+        if (value < 0 || value > 1) { ie::set_error("me_variant: 0 (default) or 1 (REDUX reduction of the SAD partial sums, experimental)"); return IE_EINVAL; }
+        ie::g_me_variant.store(value);
         return IE_OK;
     }
     ie::set_error("unknown option");

@@ -174,7 +174,9 @@ int ie_stream_shift_dev(const uint8_t *d_in, const uint64_t *d_params, uint8_t *
  *   "copyout_variant" = 0 | 1 | 2 (default)  copy-out kernel: 2 = short path for interior chunks with four chunks per
  *                          thread in flight, 1 = short path one chunk at a time, 0 = the generic kernel;
  *   "decode_variant"  = 0 (default) | 1  block-decode kernel of images and I-frames: 1 = inverse transform and pixel
- *                          stage in packed f32x2 operations (experimental; arithmetic checked on the CPU only so far).
+ *                          stage in packed f32x2 operations (experimental; arithmetic checked on the CPU only so far);
+ *   "me_variant"      = 0 (default) | 1  motion-search kernel: 1 = SAD partial sums reduced with warp-wide integer
+ *                          reductions (REDUX) instead of shuffle + add steps (experimental, not yet timed).
  * Returns IE_EINVAL for an unknown name or an out-of-range value. */
 int ie_set_option(const char *name, int value);
 

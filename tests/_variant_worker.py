@@ -114,6 +114,29 @@ def main_decode(variant: int) -> int:
     return 1 if bad else 0
 
 
+def main_me(variant: int) -> int:
+    """ie_set_option("me_variant", V): every motion vector is a field of the P-frame stream, so stream equality covers them"""
+    import imageencoder_b200 as ie
+    import oracle
+    from imageencoder_b200 import _lib
+    from imageencoder_b200.synth import synth_video
+
+    L = ie.lib()
+    _lib.check(L.ie_init(0))
+    q = ie.read_matrix(ROOT / "tests" / "golden" / "inputs" / "matrix.txt")
+    bad = 0
+    _lib.check(L.ie_set_option(b"me_variant", variant))
+    for W, H, F, gop, mer in ((64, 48, 7, 4, 16), (128, 96, 9, 3, 8), (176, 144, 6, 6, 32), (64, 48, 6, 7, 2), (96, 64, 6, 4, 10),
+                              (64, 48, 5, 4, 1)):
+        yuv = synth_video(W, H, F, 4000)
+        if ie.encode_video(yuv, W, H, q, True, gop, mer, False) != oracle.video_encode(yuv, W, H, q, True, gop, mer, False):
+            print(f"me variant {variant}: {W}x{H}x{F} gop {gop} merange {mer}: stream differs")
+            bad += 1
+    _lib.check(L.ie_set_option(b"me_variant", 0))
+    print(f"me variant {variant}: {'ok' if not bad else f'{bad} mismatches'}")
+    return 1 if bad else 0
+
+
 if __name__ == "__main__":
     a = sys.argv[1]
-    sys.exit(main_decode(int(a[3:])) if a.startswith("dec") else main(int(a)))
+    sys.exit(main_decode(int(a[3:])) if a.startswith("dec") else main_me(int(a[2:])) if a.startswith("me") else main(int(a)))

@@ -51,3 +51,13 @@ def test_decode_variant_option_is_validated():
         assert L.ie_set_option(b"decode_variant", -1) != 0
     finally:
         assert L.ie_set_option(b"decode_variant", 0) == 0          # the default
+
+
+def test_me_variant_option_is_validated():
+    import imageencoder_b200 as ie
+    L = ie.lib()
+    try:
+        assert L.ie_set_option(b"me_variant", 1) == 0
+        assert L.ie_set_option(b"me_variant", 2) != 0
+    finally:
+        assert L.ie_set_option(b"me_variant", 0) == 0              # the default

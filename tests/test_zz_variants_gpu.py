@@ -48,6 +48,15 @@ def test_decode_variant_pixels_identical():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.xfail(strict=False, reason="me_variant 1 (REDUX reduction in the motion search) was written after this round's GPU "
+                                        "budget was spent; first run on a B200; NOT the default kernel")
+def test_me_variant_streams_identical():
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "_variant_worker.py"), "me1"], capture_output=True, text=True,
+                       timeout=180)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_copyout_variant_streams_identical(gpu, oracle_mod):
     """ie_set_option("copyout_variant", 0|1|2): 2 (short path for interior chunks, four in flight) is the default kernel,
     0 the generic one it replaced; none may change a byte."""

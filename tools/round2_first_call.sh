@@ -13,6 +13,8 @@ timeout 300 python tools/ab_quick_rows.py > gpurun_out/r2_rows_default.log 2>&1;
 cp gpurun_out/ab_quick_rows.json gpurun_out/r2_rows_default.json 2>/dev/null
 timeout 300 python tools/ab_quick_rows.py --options decode_variant=1 > gpurun_out/r2_rows_dec1.log 2>&1; echo "rows(decode_variant=1) rc=$?" | tee -a gpurun_out/r2_steps.log
 cp gpurun_out/ab_quick_rows.json gpurun_out/r2_rows_dec1.json 2>/dev/null
+timeout 300 python tools/ab_quick_rows.py --options me_variant=1 > gpurun_out/r2_rows_me1.log 2>&1; echo "rows(me_variant=1) rc=$?" | tee -a gpurun_out/r2_steps.log
+cp gpurun_out/ab_quick_rows.json gpurun_out/r2_rows_me1.json 2>/dev/null
 timeout 600 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; echo "bench rc=$?" | tee -a gpurun_out/r2_steps.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_bench.log 2>&1; echo "ncu launches rc=$?" | tee -a gpurun_out/r2_steps.log
