@@ -1,5 +1,8 @@
 #include "codec.hpp"
 
+#include <algorithm>
+#include <cctype>
+
 #include <cstdio>
 #include <fstream>
 #include <iomanip>
@@ -85,29 +88,51 @@ std::string ConfigReader::toString() const {
 }
 
 // ---- MatrixReader ------------------------------------------------------------------------------------------------
+// util::lexical_cast<uint16_t> of the reference (utils.hpp:293-305), which both the matrix entries (MatrixReader.cpp:104) and the
+// numeric settings (main.cpp:91-98) go through: formatted stream extraction into a uint16_t -- hexadecimal if the text starts
+// with 0x / 0X, leading whitespace and a sign accepted ("-4" wraps to 65532), anything after the number ignored ("8px" is 8),
+// failure if there is no number or it does not fit.  Same libstdc++ call, so the same corner cases.
+bool lexicalCastU16(const std::string &text, uint16_t &out) {
+    std::stringstream cast;
+    if (text.size() >= 2 && text[0] == '0' && (text[1] == 'x' || text[1] == 'X')) cast << std::hex << text;
+    else cast << text;
+    uint16_t v;
+    if (!(cast >> v)) return false;
+    out = v;
+    return true;
+}
+
+// Text format as the reference reads it (MatrixReader.cpp:65-134): lines split at '\n', each trimmed of whitespace at both ends
+// (so CRLF files work) and with runs of spaces collapsed, items separated by SINGLE SPACES ONLY (a tab is not a separator), every
+// item through lexical_cast<uint16_t>; a blank line is a row without columns, i.e. an error, and so is a trailing blank line
+// (one row too many).  The only difference: the reference's matrix size is the compile-time BlockSize, here it is the number of
+// rows (4 or 8).
 bool MatrixReader::read(const std::string &file) {
     std::ifstream f(file);
     if (!f.good()) { fprintf(stderr, "[MatrixReader] cannot read '%s'\n", file.c_str()); return false; }
-    std::vector<std::vector<long>> rows;
-    std::string line;
-    while (std::getline(f, line)) {
-        std::istringstream is(line);
-        std::vector<long> r;
-        std::string tok;
-        while (is >> tok) {
-            char *end = nullptr;
-            const long v = strtol(tok.c_str(), &end, 10);
-            if (*end || v < 0 || v > 65535) { fprintf(stderr, "[MatrixReader] bad entry '%s'\n", tok.c_str()); return false; }
+    std::stringstream ss;
+    ss << f.rdbuf();
+    std::vector<std::vector<uint16_t>> rows;
+    std::string line, item;
+    while (std::getline(ss, line)) {
+        line.erase(line.begin(), std::find_if(line.begin(), line.end(), [](int c) { return !std::isspace(c); }));          // utils.hpp:33-56
+        line.erase(std::find_if(line.rbegin(), line.rend(), [](int c) { return !std::isspace(c); }).base(), line.end());
+        line.erase(std::unique(line.begin(), line.end(), [](char l, char r) { return l == ' ' && r == ' '; }), line.end());   // utils.hpp:88-94
+        std::vector<uint16_t> r;
+        std::stringstream iss(line);
+        while (std::getline(iss, item, ' ')) {
+            uint16_t v;
+            if (!lexicalCastU16(item, v)) { fprintf(stderr, "[MatrixReader] bad entry '%s'\n", item.c_str()); return false; }
             r.push_back(v);
         }
-        if (!r.empty()) rows.push_back(r);
+        rows.push_back(r);
     }
     const size_t n = rows.size();
     if (n != 4 && n != 8) { fprintf(stderr, "[MatrixReader] expected 4 or 8 rows, got %zu\n", n); return false; }
     m_.clear();
     for (const auto &r : rows) {
         if (r.size() != n) { fprintf(stderr, "[MatrixReader] expected %zu columns, got %zu\n", n, r.size()); return false; }
-        for (long v : r) m_.push_back((uint16_t)v);
+        for (uint16_t v : r) m_.push_back(v);
     }
     n_ = (unsigned)n;
     return true;

@@ -38,6 +38,9 @@ class ConfigReader {
 };
 
 // N x N quant matrix from a text file, N = 4 or 8 decided by the file (MatrixReader.cpp:65-134)
+// util::lexical_cast<uint16_t> of the reference (utils.hpp:293-305)
+bool lexicalCastU16(const std::string &text, uint16_t &out);
+
 class MatrixReader {
     std::vector<uint16_t> m_;
     unsigned n_ = 0;

@@ -11,14 +11,8 @@
 
 #include "codec.hpp"
 
-static bool to_u16(const std::string &s, uint16_t &out) {
-    if (s.empty()) return false;
-    char *end = nullptr;
-    const long v = strtol(s.c_str(), &end, 10);
-    if (*end || v < 0 || v > 65535) return false;
-    out = (uint16_t)v;
-    return true;
-}
+// numeric settings as main.cpp:91-98 reads them (util::lexical_cast<uint16_t>)
+static bool to_u16(const std::string &s, uint16_t &out) { return dc::lexicalCastU16(s, out); }
 
 int main(int argc, char **argv) {
     dc::Options opt;

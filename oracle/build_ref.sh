@@ -12,7 +12,9 @@
 #  * main.cpp is replaced by oracle/ref_harness.cpp (timing + _exit before the crashing dtor).
 #
 # Produces: oracle/_ref/ref_n{4,8}_{plain,huff}   (all OpenMP builds; OMP_NUM_THREADS=1 gives the serial order,
-#           which is byte-identical).
+#           which is byte-identical), and oracle/_ref/ref_cli_{encoder,decoder}: the reference's own
+#           CLIs (its main.cpp with -DENCODER / -DDECODER as its makefile builds them; 4x4, Huffman off), used only to pin the
+#           drop-in CLI contract: .conf / matrix parsing and exit codes (tests/test_cli_contract_cpu.py).
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${REFERENCE_DIR:-/root/reference}"
@@ -28,7 +30,8 @@ FLAGS="-std=c++17 -O3 -mlzcnt -fopenmp -DENABLE_OPENMP -DENCODER -DDECODER -w"
 stamp="$OUT/.stamp"
 newest=$(find "$REF" -maxdepth 1 \( -name '*.cpp' -o -name '*.hpp' \) -newer "$stamp" 2>/dev/null | head -1 || true)
 if [ -f "$stamp" ] && [ -z "$newest" ] && [ "$HERE/ref_harness.cpp" -ot "$stamp" ] && [ "$HERE/build_ref.sh" -ot "$stamp" ] \
-   && [ -x "$OUT/ref_n4_plain" ] && [ -x "$OUT/ref_n4_huff" ] && [ -x "$OUT/ref_n8_plain" ] && [ -x "$OUT/ref_n8_huff" ]; then
+   && [ -x "$OUT/ref_n4_plain" ] && [ -x "$OUT/ref_n4_huff" ] && [ -x "$OUT/ref_n8_plain" ] && [ -x "$OUT/ref_n8_huff" ] \
+   && [ -x "$OUT/ref_cli_encoder" ] && [ -x "$OUT/ref_cli_decoder" ]; then
     echo "[build_ref] up to date"
     exit 0
 fi
@@ -40,7 +43,7 @@ for N in 4 8; do
     d="$SCR/n$N"
     mkdir -p "$d"
     cp "$REF"/*.cpp "$REF"/*.hpp "$d"/
-    rm -f "$d/main.cpp"
+    mkdir -p "$d/cli" && mv "$d/main.cpp" "$d/cli/main.cpp"
     cp "$HERE/ref_harness.cpp" "$d/"
     if [ "$N" = 8 ]; then
         sed -i 's/BlockSize      =  4u/BlockSize      =  8u/' "$d/Block.hpp"
@@ -61,6 +64,10 @@ for N in 4 8; do
         done
     done
 done
+# the reference's CLIs (4x4, Huffman off): main.cpp once per target macro, as makefile:5-8 does
+CLIFLAGS="-std=c++17 -O3 -mlzcnt -fopenmp -DENABLE_OPENMP -w"
+( cd "$SCR/n4" && $CXX $CLIFLAGS -DENCODER -I. -c cli/main.cpp -o cli/main_encoder.o ) & pids+=($!)
+( cd "$SCR/n4" && $CXX $CLIFLAGS -DDECODER -I. -c cli/main.cpp -o cli/main_decoder.o ) & pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 for N in 4 8; do
     d="$SCR/n$N"
@@ -68,6 +75,10 @@ for N in 4 8; do
     for v in plain huff; do
         $CXX -fopenmp $common "$d"/ImageEncoder_$v.o "$d"/VideoEncoder_$v.o "$d"/ref_harness_$v.o -o "$OUT/ref_n${N}_$v"
     done
+done
+common4=$(ls "$SCR/n4"/*.o | grep -v -e '_plain.o' -e '_huff.o')
+for t in encoder decoder; do
+    $CXX -fopenmp $common4 "$SCR/n4"/ImageEncoder_plain.o "$SCR/n4"/VideoEncoder_plain.o "$SCR/n4/cli/main_$t.o" -o "$OUT/ref_cli_$t"
 done
 touch "$stamp"
 echo "[build_ref] built: $(ls "$OUT")"
