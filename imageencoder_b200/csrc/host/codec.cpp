@@ -18,7 +18,7 @@ static void check(int rc, const char *what) {
 
 std::vector<uint8_t> readBinaryFile(const std::string &file) {
     std::ifstream f(file, std::ios::binary | std::ios::ate);
-    if (!f.good()) throw CodecError(IE_EINVAL, "cannot read file '" + file + "'");
+    if (!f.good()) throw CodecError(kUnreadableInput, "cannot read file '" + file + "'");
     const std::streamsize n = f.tellg();
     std::vector<uint8_t> v((size_t)n);
     f.seekg(0);

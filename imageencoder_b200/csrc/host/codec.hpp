@@ -19,6 +19,10 @@ struct Options {
     unsigned block = 0;       // 0: take it from the quant matrix (encoder) / 4 (decoder)
 };
 
+// code of a CodecError raised because an input file cannot be read: the reference exit(-1)s there (ImageBase.cpp:24-27,
+// 103-106; VideoBase.cpp), which the CLIs mirror as exit status 255
+constexpr int kUnreadableInput = -1000;
+
 struct CodecError : std::runtime_error {
     int code;
     CodecError(int c, const std::string &m) : std::runtime_error(m), code(c) {}

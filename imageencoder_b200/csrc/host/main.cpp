@@ -79,7 +79,7 @@ int main(int argc, char **argv) {
 #endif
     } catch (const dc::CodecError &e) {
         std::cerr << "Error: " << e.what() << std::endl;
-        return 6;
+        return e.code == dc::kUnreadableInput ? 255 : 6;      // 255: the reference's exit(-1) on an unreadable input file
     }
     return 0;
 }

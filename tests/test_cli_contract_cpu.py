@@ -52,7 +52,8 @@ def encoder_cases():
           ("conf_two_eq", conf(dict(BASE, logfile="a=b.txt")), Q4, None),
           ("video_partial_gop", conf(dict(BASE, gop="4")), Q4, None), ("video_partial_mer", conf(dict(BASE, merange="16")), Q4, None),
           ("video_word", conf(dict(BASE, gop="four", merange="16", motioncompensation="1")), Q4, None),
-          ("video_mer_word", conf(dict(BASE, gop="4", merange="x", motioncompensation="1")), Q4, None)]
+          ("video_mer_word", conf(dict(BASE, gop="4", merange="x", motioncompensation="1")), Q4, None),
+          ("input_missing", conf(BASE), Q4, None)]
     return c
 
 
@@ -61,12 +62,12 @@ def decoder_cases():
     c += [(f"missing_{k}", conf(drop(BASE, k)), Q4, None) for k in BASE]
     c += [("same_enc_dec", conf(dict(BASE, decfile="a.enc")), Q4, None),
           ("video_mc_word", conf(dict(BASE, gop="4", merange="16", motioncompensation="yes")), Q4, None),
-          ("video_partial", conf(dict(BASE, motioncompensation="1")), Q4, None)]
+          ("video_partial", conf(dict(BASE, motioncompensation="1")), Q4, None), ("input_missing", conf(BASE), Q4, None)]
     return c
 
 
 def decision(rc):
-    return rc if rc in (1, 2, 3, 4, 5) else "process"
+    return rc if rc in (1, 2, 3, 4, 5, 255) else "process"       # 255 = exit(-1): unreadable input file (ImageBase.cpp:24-27)
 
 
 def run_battery(ref_exe, our_exe, cases):
@@ -80,8 +81,9 @@ def run_battery(ref_exe, our_exe, cases):
                     Path(d, "a.conf").write_bytes(ctext.encode())
                 if q is not None:
                     Path(d, "q.txt").write_bytes(q.encode())
-                Path(d, "a.raw").write_bytes(b"\x80" * 64)
-                Path(d, "a.enc").write_bytes(b"\x00" * 8)        # a stream the decoders can at least open
+                if name != "input_missing":
+                    Path(d, "a.raw").write_bytes(b"\x80" * 64)
+                    Path(d, "a.enc").write_bytes(b"\x00" * 8)    # a stream the decoders can at least open
                 r = subprocess.run([str(exe), *(["a.conf"] if args is None else args)], cwd=d, capture_output=True, timeout=120)
                 got[which] = decision(r.returncode)
             finally:
