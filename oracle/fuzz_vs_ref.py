@@ -4,6 +4,7 @@
 
     python oracle/fuzz_vs_ref.py image SECONDS [SEED]      random sizes / contents / quantisers / RLE / Huffman, both block sizes
     python oracle/fuzz_vs_ref.py video SECONDS [SEED]      random clips, gop 1..8, merange in {1..64, not only powers of two}
+    python oracle/fuzz_vs_ref.py corrupt SECONDS [SEED]    decode of truncated / bit-flipped / padded image streams
 
 A case counts as a REAL mismatch only where the reference's behaviour is defined.  Two regimes are the reference's own
 undefined behaviour and are reported separately ("avoid"):
@@ -12,6 +13,8 @@ undefined behaviour and are reported separately ("avoid"):
   * video streams longer than the raw Y planes: the output buffer is sized frames * W * H * 8 bits (VideoEncoder.cpp:35-53,
     Frame.cpp:23-29) and put_bit has no bounds check (BitStream.cpp:61-71) -- heap overflow, anything from a garbage last byte
     to corrupted later frames to a glibc abort.
+  * (corrupt mode) a block whose length field exceeds N*N: the reference indexes its zigzag table out of bounds
+    (Block.cpp:460-465); the oracle and the product ignore the surplus values.
 Prints one summary line; exit code 1 if there is a REAL mismatch."""
 import sys
 import time
@@ -149,7 +152,73 @@ def run_video(seconds, seed):
     return real
 
 
+def _has_overlong_block(enc: bytes, N: int) -> bool:
+    """plain image stream: does any block carry a length field > N*N (the reference's out-of-bounds case)?"""
+    bits = np.unpackbits(np.frombuffer(enc, np.uint8))
+    pos = 0
+
+    def get(n):
+        nonlocal pos
+        v = 0
+        for _ in range(n):
+            v = (v << 1) | (int(bits[pos]) if pos < len(bits) else 0)
+            pos += 1
+        return v
+
+    get(1)
+    qb = get(5)
+    for _ in range(N * N):
+        get(qb)
+    rle, W, H = get(1), get(15), get(15)
+    for _ in range((W // N) * (H // N)):
+        bl = get(4)
+        ln = get(bl) if rle else N * N
+        if ln > N * N:
+            return True
+        pos += ln * bl
+        if pos > len(bits) + 64:
+            break
+    return False
+
+
+def run_corrupt(seconds, seed):
+    rng = np.random.default_rng(seed)
+    t0 = time.time()
+    n = real = ub = crashed = 0
+    while time.time() - t0 < seconds:
+        N = int(rng.choice([4, 8]))
+        W, H = N * int(rng.integers(1, 12)), N * int(rng.integers(1, 12))
+        img = np.clip(rng.normal(128, rng.uniform(1, 80), (H, W)), 0, 255).astype(np.uint8)
+        q = rng.integers(1, 64, (N, N)).astype(np.uint16)
+        enc = bytearray(oracle.image_encode(img, W, H, N, q, bool(rng.integers(0, 2)), False))
+        hdr = (1 + 5 + N * N * 8 + 1 + 30 + 7) // 8 + 1            # the header stays intact: W and H pick the output size
+        mode = int(rng.integers(0, 3))
+        if mode == 0 and len(enc) > hdr + 1:
+            enc = enc[: int(rng.integers(hdr, len(enc)))]           # truncated: reads past the end return 0 (BitStream.cpp:17-20)
+        elif mode == 1 and len(enc) > hdr + 1:
+            for _ in range(int(rng.integers(1, 6))):                # bit flips in the body
+                enc[int(rng.integers(hdr, len(enc)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            enc = enc + bytes(rng.integers(0, 256, int(rng.integers(1, 40))).astype(np.uint8))      # trailing garbage
+        enc = bytes(enc)
+        try:
+            rdec, _ = oracle.ref_image_decode(enc, N, W, H, threads=1)
+        except Exception:
+            crashed += 1
+            continue
+        n += 1
+        if not np.array_equal(oracle.image_decode(enc, N)[0], rdec):
+            if _has_overlong_block(enc, N):
+                ub += 1
+            else:
+                real += 1
+                print("REAL corrupt-stream decode mismatch", dict(seed=seed, n=n, N=N, W=W, H=H, mode=mode), flush=True)
+    print(f"corrupt fuzz seed {seed}: {n} cases, {real} REAL mismatches, {ub} differ where a length field exceeds N*N, "
+          f"{crashed} reference crashes")
+    return real
+
+
 if __name__ == "__main__":
     mode, secs = sys.argv[1], float(sys.argv[2])
     seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-    sys.exit(1 if (run_image if mode == "image" else run_video)(secs, seed) else 0)
+    sys.exit(1 if {"image": run_image, "video": run_video, "corrupt": run_corrupt}[mode](secs, seed) else 0)
