@@ -5,6 +5,8 @@
     python oracle/fuzz_vs_ref.py image SECONDS [SEED]      random sizes / contents / quantisers / RLE / Huffman, both block sizes
     python oracle/fuzz_vs_ref.py video SECONDS [SEED]      random clips, gop 1..8, merange in {1..64, not only powers of two}
     python oracle/fuzz_vs_ref.py corrupt SECONDS [SEED]    decode of truncated / bit-flipped / padded image streams
+    python oracle/fuzz_vs_ref.py trunc SECONDS [SEED]      decode of truncated / padded Huffman-coded image streams and of
+                                                           truncated video streams (with and without motion compensation)
 
 A case counts as a REAL mismatch only where the reference's behaviour is defined.  Two regimes are the reference's own
 undefined behaviour and are reported separately ("avoid"):
@@ -152,7 +154,7 @@ def run_video(seconds, seed):
     return real
 
 
-def _has_overlong_block(enc: bytes, N: int) -> bool:
+def _has_overlong_block(enc: bytes, N: int, lead_bit: bool = True) -> bool:
     """plain image stream: does any block carry a length field > N*N (the reference's out-of-bounds case)?"""
     bits = np.unpackbits(np.frombuffer(enc, np.uint8))
     pos = 0
@@ -165,7 +167,8 @@ def _has_overlong_block(enc: bytes, N: int) -> bool:
             pos += 1
         return v
 
-    get(1)
+    if lead_bit:
+        get(1)
     qb = get(5)
     for _ in range(N * N):
         get(qb)
@@ -218,7 +221,70 @@ def run_corrupt(seconds, seed):
     return real
 
 
+def run_trunc(seconds, seed):
+    rng = np.random.default_rng(seed)
+    t0 = time.time()
+    n = real = ub = crashed = 0
+    while time.time() - t0 < seconds:
+        if rng.integers(0, 2):
+            N = int(rng.choice([4, 8]))
+            W, H = N * int(rng.integers(2, 16)), N * int(rng.integers(2, 16))
+            img = np.clip(rng.normal(128, rng.uniform(5, 60), (H, W)), 0, 255).astype(np.uint8)
+            q = rng.integers(2, 64, (N, N)).astype(np.uint16)
+            enc = oracle.image_encode(img, W, H, N, q, True, True)
+            if not (enc[0] & 0x80):
+                continue                                    # reverted: not a Huffman stream
+            if oracle.huffman_header_overflows(oracle.image_encode_plain(img, W, H, N, q, True, lead_bit=False)[0]):
+                continue                                    # the reference cannot decode its own output (Huffman.cpp:39-42)
+            if rng.integers(0, 2):
+                enc2 = enc[: int(rng.integers(len(enc) * 6 // 10, len(enc)))]
+            else:
+                enc2 = enc + bytes(rng.integers(0, 256, int(rng.integers(1, 40))).astype(np.uint8))
+            try:
+                rdec, _ = oracle.ref_image_decode(enc2, N, W, H, threads=1)
+            except Exception:
+                crashed += 1                                # missing tree branch: the reference dereferences nullptr (Huffman.cpp:197-200)
+                continue
+            n += 1
+            try:
+                same = np.array_equal(oracle.image_decode(enc2, N)[0], rdec)
+            except ValueError:
+                same = False
+            if not same:
+                if _has_overlong_block(oracle.huffman_decode(enc2)[0], N, lead_bit=False):
+                    ub += 1                                 # the garbage block at the cut carries a length field > N*N
+                else:
+                    real += 1
+                    print("REAL truncated Huffman decode mismatch", dict(seed=seed, n=n, N=N, W=W, H=H), flush=True)
+        else:
+            W, H, F = 16 * int(rng.integers(1, 5)), 16 * int(rng.integers(1, 4)), int(rng.integers(2, 7))
+            fsz = W * H * 3 // 2
+            yuv = np.full((F, fsz), 0x80, np.uint8)
+            big = np.clip(rng.normal(128, 50, (H + 32, W + 32)), 0, 255).astype(np.uint8)
+            for t in range(F):
+                x0, y0 = int(rng.integers(0, 32)), int(rng.integers(0, 32))
+                yuv[t, :W * H] = big[y0:y0 + H, x0:x0 + W].reshape(-1)
+            q = rng.integers(8, 64, (4, 4)).astype(np.uint16)
+            enc = oracle.video_encode(yuv.reshape(-1), W, H, q, True, int(rng.integers(1, 5)), int(rng.choice([4, 8, 16])), False)
+            if len(enc) <= 30:
+                continue
+            enc2 = enc[: int(rng.integers(28, len(enc)))]
+            mc = bool(rng.integers(0, 2))
+            try:
+                rdec, _ = oracle.ref_video_decode(enc2, mc, threads=1)
+            except Exception:
+                crashed += 1
+                continue
+            n += 1
+            if not np.array_equal(np.asarray(oracle.video_decode(enc2, mc)[0]).reshape(-1), rdec):
+                real += 1
+                print("REAL truncated video decode mismatch", dict(seed=seed, n=n, W=W, H=H, F=F, mc=mc), flush=True)
+    print(f"trunc fuzz seed {seed}: {n} cases, {real} REAL mismatches, {ub} differ where the block at the cut has a length field > N*N, "
+          f"{crashed} reference crashes")
+    return real
+
+
 if __name__ == "__main__":
     mode, secs = sys.argv[1], float(sys.argv[2])
     seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-    sys.exit(1 if {"image": run_image, "video": run_video, "corrupt": run_corrupt}[mode](secs, seed) else 0)
+    sys.exit(1 if {"image": run_image, "video": run_video, "corrupt": run_corrupt, "trunc": run_trunc}[mode](secs, seed) else 0)
