@@ -137,6 +137,50 @@ def main_me(variant: int) -> int:
     return 1 if bad else 0
 
 
+def main_corrupt() -> int:
+    """Damaged image streams (bit flips in the body, truncation, trailing garbage; oracle/fuzz_vs_ref.py's generator with a fixed
+    seed) through the default decode path: same pixels as the oracle, which equals the compiled reference wherever the
+    reference's behaviour is defined and ignores the surplus values of a length field > N*N (profiles/r1_oracle_fuzz.md)."""
+    import imageencoder_b200 as ie
+    import oracle
+    from imageencoder_b200 import _lib
+
+    _lib.check(ie.lib().ie_init(0))
+    rng = np.random.default_rng(777)
+    bad = n = 0
+    for _ in range(300):
+        N = int(rng.choice([4, 8]))
+        W, H = N * int(rng.integers(1, 24)), N * int(rng.integers(1, 24))
+        img = np.clip(rng.normal(128, rng.uniform(1, 80), (H, W)), 0, 255).astype(np.uint8)
+        q = rng.integers(1, 64, (N, N)).astype(np.uint16)
+        enc = bytearray(oracle.image_encode(img, W, H, N, q, bool(rng.integers(0, 2)), False))
+        hdr = (1 + 5 + N * N * 8 + 1 + 30 + 7) // 8 + 1
+        mode = int(rng.integers(0, 3))
+        if mode == 0 and len(enc) > hdr + 1:
+            enc = enc[: int(rng.integers(hdr, len(enc)))]
+        elif mode == 1 and len(enc) > hdr + 1:
+            for _k in range(int(rng.integers(1, 6))):
+                enc[int(rng.integers(hdr, len(enc)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            enc = enc + bytes(rng.integers(0, 256, int(rng.integers(1, 40))).astype(np.uint8))
+        enc = bytes(enc)
+        want = oracle.image_decode(enc, N)[0]
+        n += 1
+        try:
+            got = ie.decode_image(enc, N)
+        except ie.IEError as e:
+            print(f"corrupt case {n} (mode {mode}, {N}x{N}, {W}x{H}): decoder raised {e}")
+            bad += 1
+            continue
+        if got.shape != want.shape or not np.array_equal(got, want):
+            print(f"corrupt case {n} (mode {mode}, {N}x{N}, {W}x{H}): pixels differ from the oracle's")
+            bad += 1
+    print(f"corrupt streams: {'ok' if not bad else f'{bad} of {n} differ'}")
+    return 1 if bad else 0
+
+
 if __name__ == "__main__":
     a = sys.argv[1]
+    if a == "corrupt":
+        sys.exit(main_corrupt())
     sys.exit(main_decode(int(a[3:])) if a.startswith("dec") else main_me(int(a[2:])) if a.startswith("me") else main(int(a)))

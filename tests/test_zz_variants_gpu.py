@@ -57,6 +57,16 @@ def test_me_variant_streams_identical():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: first run pending (truncated and padded "
+                                        "streams are already covered by test_image_gpu.py; bit-flipped ones are new)")
+def test_damaged_streams_decode_like_the_oracle():
+    """300 damaged image streams (bit flips, truncation, trailing garbage) through the default decode path, in their own process"""
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "_variant_worker.py"), "corrupt"], capture_output=True, text=True,
+                       timeout=300)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_copyout_variant_streams_identical(gpu, oracle_mod):
     """ie_set_option("copyout_variant", 0|1|2): 2 (short path for interior chunks, four in flight) is the default kernel,
     0 the generic one it replaced; none may change a byte."""
