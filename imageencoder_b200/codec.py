@@ -8,6 +8,7 @@ through ``libimageencoder_b200.so``; nothing here computes a pixel or a bit on t
 from __future__ import annotations
 
 import ctypes as C
+import re
 from pathlib import Path
 
 import numpy as np
@@ -16,20 +17,36 @@ from . import _lib
 from ._lib import check, lib
 
 
+def _lexical_cast_u16(item: str) -> int:
+    """``util::lexical_cast<uint16_t>`` (utils.hpp:293-305): formatted stream extraction -- hexadecimal if the text starts with
+    0x / 0X, leading whitespace and a sign accepted (a negative value wraps), whatever follows the number ignored, failure if
+    there is no number or its magnitude does not fit 16 bits."""
+    hexmode = item[:2].upper() == "0X"
+    m = re.match(r"\s*([+-]?)(?:0[xX])?([0-9a-fA-F]+)" if hexmode else r"\s*([+-]?)([0-9]+)", item)
+    if not m:
+        raise ValueError(f"[MatrixReader] cannot cast '{item}' to uint16")
+    v = int(m.group(2), 16 if hexmode else 10)
+    if v > 65535:
+        raise ValueError(f"[MatrixReader] '{item}' does not fit uint16")
+    return (-v) & 0xFFFF if m.group(1) == "-" else v
+
+
 def read_matrix(path) -> np.ndarray:
-    """``MatrixReader<>::read`` (MatrixReader.cpp:65-134): N rows of N space separated u16 values."""
+    """``MatrixReader<>::read`` (MatrixReader.cpp:65-134), the same way ``csrc/host/codec.cpp`` mirrors it: lines split at newlines,
+    trimmed, runs of spaces collapsed, items separated by single spaces only (a tab is not a separator), each item through
+    ``lexical_cast<uint16_t>``; a blank line is a row without columns (an error).  The block size is the number of rows (4 or 8)."""
+    text = Path(path).read_bytes().decode("latin-1")
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()                                   # std::getline yields no empty line after a final newline
     rows = []
-    for line in Path(path).read_text().splitlines():
-        line = line.strip()
-        if line:
-            rows.append([int(v) for v in line.split()])
+    for line in lines:
+        line = re.sub(" +", " ", line.strip(" \t\n\v\f\r"))
+        rows.append([_lexical_cast_u16(item) for item in line.split(" ")] if line else [])
     n = len(rows)
     if n not in (4, 8) or any(len(r) != n for r in rows):
         raise ValueError(f"[MatrixReader] expected a 4x4 or 8x8 matrix in {path}")
-    m = np.array(rows, dtype=np.int64)
-    if (m < 0).any() or (m > 65535).any():
-        raise ValueError("[MatrixReader] entries must fit uint16")
-    return m.astype(np.uint16)
+    return np.array(rows, dtype=np.uint16)
 
 
 def _quant(quant, block=None) -> np.ndarray:

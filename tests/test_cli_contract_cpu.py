@@ -101,3 +101,30 @@ def test_encoder_cli_decisions_match_the_reference_binary():
 def test_decoder_cli_decisions_match_the_reference_binary():
     diffs = run_battery(REF / "ref_cli_decoder", ROOT / "bin" / "decoder", decoder_cases())
     assert not diffs, diffs
+
+
+def test_python_read_matrix_agrees_with_the_cli(tmp_path):
+    """imageencoder_b200.read_matrix (the Python mirror of MatrixReader) accepts / rejects the same matrix files as bin/encoder --
+    which the tests above tie to the reference's own binary -- and reads the same values"""
+    import numpy as np
+
+    import imageencoder_b200 as ie
+    enc = ROOT / "bin" / "encoder"
+    (tmp_path / "a.conf").write_text(conf(BASE))
+    (tmp_path / "a.raw").write_bytes(b"\x80" * 64)
+    for name, _c, q, _a in encoder_cases():
+        if not name.startswith("q_") or q is None:
+            continue
+        (tmp_path / "q.txt").write_bytes(q.encode())
+        r = subprocess.run([str(enc), "a.conf"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+        cli_ok = r.returncode != 4
+        try:
+            m = ie.read_matrix(tmp_path / "q.txt")
+            py_ok = True
+        except ValueError:
+            py_ok = False
+        assert py_ok == cli_ok, (name, r.returncode)
+        if cli_ok:
+            # the CLI prints the matrix it read with setw(4) per entry (codec.cpp: MatrixReader::toString)
+            printed = r.stdout.split("Quantization matrix:")[1].split("-------------------------")[1].strip("\n").split("\n")[: m.shape[0]]
+            assert printed == ["".join(f"{int(v):4d}" for v in row) for row in np.asarray(m)], name
