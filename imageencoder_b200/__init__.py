@@ -13,8 +13,10 @@ from .codec import (  # noqa: F401
     VideoDecoder,
     VideoEncoder,
     decode_image,
+    decode_images,
     decode_video,
     encode_image,
+    encode_images,
     encode_video,
     read_matrix,
 )

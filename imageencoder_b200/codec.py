@@ -100,6 +100,47 @@ def decode_image(enc, block: int = 4, out: np.ndarray | None = None) -> np.ndarr
     return buf[: w.value * h.value].reshape(h.value, w.value)
 
 
+def encode_images(raws, width: int, height: int, quant, rle: bool = True, huffman: bool = False, block: int | None = None) -> list:
+    """Batch of equally sized images (BASELINE config 4) through ``ie_encode_images``: every image is what
+    ``dc::ImageEncoder`` writes for it.  `raws`: (count, height, width) uint8.  Returns a list of ``.enc`` byte strings."""
+    q = _quant(quant, block)
+    block = 4 if q.size == 16 else 8
+    a = np.ascontiguousarray(raws, dtype=np.uint8)
+    npx = width * height
+    if a.size % npx:
+        raise ValueError("raws must hold a whole number of width*height images")
+    count = a.size // npx
+    a = a.reshape(-1)
+    slot = int(lib().ie_max_encoded_bytes(width, height, block, 1))
+    out = np.empty(count * slot, dtype=np.uint8)
+    sizes = (C.c_size_t * count)()
+    check(lib().ie_encode_images(_ptr(a), count, width, height, block, _u16(q), int(bool(rle)), int(bool(huffman)), _ptr(out),
+                                 slot, sizes))
+    return [out[i * slot: i * slot + sizes[i]].tobytes() for i in range(count)]
+
+
+def decode_images(encs, block: int = 4) -> list:
+    """Batch decode through ``ie_decode_images``: `encs` is a list of ``.enc`` byte strings of equally sized images."""
+    count = len(encs)
+    stride = (max(len(e) for e in encs) + 16 + 15) // 16 * 16
+    buf = np.zeros(count * stride, dtype=np.uint8)
+    sizes = (C.c_size_t * count)()
+    for i, e in enumerate(encs):
+        buf[i * stride: i * stride + len(e)] = np.frombuffer(e, dtype=np.uint8)
+        sizes[i] = len(e)
+    # the size of the images is in the first stream's header: ask for it with a zero-capacity call of the single-image entry
+    w, h = C.c_uint32(0), C.c_uint32(0)
+    probe = np.empty(1, dtype=np.uint8)
+    e0 = np.frombuffer(encs[0], dtype=np.uint8)
+    rc = lib().ie_decode_image(_ptr(e0), e0.size, block, _ptr(probe), 0, C.byref(w), C.byref(h))
+    if rc not in (_lib.IE_OK, _lib.IE_ENOSPC):
+        check(rc)
+    npx = w.value * h.value
+    raws = np.empty(count * npx, dtype=np.uint8)
+    check(lib().ie_decode_images(_ptr(buf), stride, sizes, count, block, _ptr(raws), npx, C.byref(w), C.byref(h)))
+    return [raws[i * npx: (i + 1) * npx].reshape(h.value, w.value) for i in range(count)]
+
+
 def encode_video(yuv, width: int, height: int, quant, rle: bool = True, gop: int = 4, merange: int = 16,
                  huffman: bool = False) -> bytes:
     """``dc::VideoEncoder::process`` + ``saveResult`` on a YUV420 planar buffer (only Y is coded)."""

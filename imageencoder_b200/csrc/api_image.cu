@@ -305,40 +305,66 @@ int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size
 }
 
 // ---- cached sessions for the host-buffer entry points -----------------------------------------------------------
+// A session owns scratch sized for its shape (tile scratch, staging buffers: hundreds of MB for large images), so sessions
+// are cached -- and LEASED: a host call holds its session exclusively from entry to return (SessionLease), so two threads
+// encoding images of the same shape never share staging buffers, streams or scan state.  A second concurrent call of a
+// shape gets a second session.  The cache is bounded: when it is full the least recently used IDLE session is destroyed
+// (a leased one never is).
 static std::mutex g_smu;
-// A session owns scratch sized for its shape (tile scratch, staging buffers: hundreds of MB for large images), so the cache
-// is bounded: the least recently used session is destroyed when a new shape arrives (the host entry points are
-// synchronous, so a cached session is idle between calls).
-struct CachedSession { ie_session *s; unsigned long long last_use; };
-static std::map<std::tuple<int, int, uint32_t, uint32_t, uint32_t, uint32_t>, CachedSession> g_sessions;
+struct CachedSession {
+    std::tuple<int, int, uint32_t, uint32_t, uint32_t, uint32_t> key;
+    ie_session *s;
+    unsigned long long last_use;
+    bool busy;
+};
+static std::vector<CachedSession> g_sessions;
 static unsigned long long g_session_clock = 0;
 constexpr size_t kMaxCachedSessions = 8;
 
-int cached_session(ie_session **out, int kind, uint32_t W, uint32_t H, uint32_t N, uint32_t frames) {
+int SessionLease::acquire(int kind, uint32_t W, uint32_t H, uint32_t N, uint32_t frames) {
+    release();
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_error("no CUDA device (this library has no CPU path)"); return IE_ENODEVICE; }
-    std::lock_guard<std::mutex> lk(g_smu);
-    auto key = std::make_tuple(dev, kind, W, H, N, frames);
-    auto it = g_sessions.find(key);
-    if (it != g_sessions.end()) { it->second.last_use = ++g_session_clock; *out = it->second.s; return IE_OK; }
-    if (g_sessions.size() >= kMaxCachedSessions) {
-        auto lru = g_sessions.begin();
-        for (auto jt = g_sessions.begin(); jt != g_sessions.end(); ++jt)
-            if (jt->second.last_use < lru->second.last_use) lru = jt;
-        ie_session_destroy(lru->second.s);
-        g_sessions.erase(lru);
+    DeviceState *ds = nullptr;
+    IE_TRY(get_device_state(&ds));                 // (re-)initialises the device tables, e.g. after ie_shutdown()
+    const auto key = std::make_tuple(dev, kind, W, H, N, frames);
+    {
+        std::lock_guard<std::mutex> lk(g_smu);
+        for (auto &c : g_sessions)
+            if (!c.busy && c.key == key) { c.busy = true; c.last_use = ++g_session_clock; s_ = c.s; s_->dev = ds; return IE_OK; }
+        // make room: destroy idle sessions, least recently used first
+        while (g_sessions.size() >= kMaxCachedSessions) {
+            int lru = -1;
+            for (size_t i = 0; i < g_sessions.size(); i++)
+                if (!g_sessions[i].busy && (lru < 0 || g_sessions[i].last_use < g_sessions[(size_t)lru].last_use)) lru = (int)i;
+            if (lru < 0) break;                    // every cached session is leased: grow past the bound for now
+            ie_session_destroy(g_sessions[(size_t)lru].s);
+            g_sessions.erase(g_sessions.begin() + lru);
+        }
     }
     ie_session *s = nullptr;
-    IE_TRY(ie_session_create(&s, kind, W, H, N, frames));
-    g_sessions[key] = CachedSession{s, ++g_session_clock};
-    *out = s;
+    IE_TRY(ie_session_create(&s, kind, W, H, N, frames));       // outside the lock: allocations can take milliseconds
+    std::lock_guard<std::mutex> lk(g_smu);
+    g_sessions.push_back(CachedSession{key, s, ++g_session_clock, true});
+    s_ = s;
     return IE_OK;
+}
+
+void SessionLease::release() {
+    if (!s_) return;
+    std::lock_guard<std::mutex> lk(g_smu);
+    for (auto &c : g_sessions)
+        if (c.s == s_) { c.busy = false; c.last_use = ++g_session_clock; }
+    s_ = nullptr;
 }
 
 void drop_cached_sessions() {
     std::lock_guard<std::mutex> lk(g_smu);
-    for (auto &kv : g_sessions) ie_session_destroy(kv.second.s);
-    g_sessions.clear();
+    for (auto it = g_sessions.begin(); it != g_sessions.end();) {
+        if (it->busy) { ++it; continue; }          // a call still in flight keeps its session
+        ie_session_destroy(it->s);
+        it = g_sessions.erase(it);
+    }
 }
 
 }  // namespace ie
@@ -445,8 +471,9 @@ int ie_encode_image(const uint8_t *raw, uint32_t W, uint32_t H, uint32_t N, cons
     if (!raw || !out || !out_bytes) { set_error("NULL argument"); return IE_EINVAL; }
     IE_TRY(check_dims(W, H, N));
     IE_TRY(check_quant(quant, (int)N));
-    ie_session *s = nullptr;
-    IE_TRY(cached_session(&s, 0, W, H, N, 1));
+    SessionLease lease;
+    IE_TRY(lease.acquire(0, W, H, N, 1));
+    ie_session *s = lease.get();
     const size_t npx = (size_t)W * H;
     const size_t cap = ie_max_encoded_bytes(W, H, N, 1);
     IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, npx));
@@ -514,8 +541,9 @@ int ie_encode_images(const uint8_t *raws, uint32_t count, uint32_t W, uint32_t H
     const size_t slot = ie_max_encoded_bytes(W, H, N, 1);
     // sub-batches keep the staging footprint bounded (<= ~8 GiB of raw pixels in flight)
     const uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(count, ((size_t)8 << 30) / (npx + slot)));
-    ie_session *s = nullptr;
-    IE_TRY(cached_session(&s, 0, W, H, N, sub));
+    SessionLease lease;
+    IE_TRY(lease.acquire(0, W, H, N, sub));
+    ie_session *s = lease.get();
     IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, npx * sub));
     IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, slot * sub));
     cudaStream_t st = s->stream;
@@ -567,8 +595,9 @@ int ie_decode_images(const uint8_t *encs, size_t enc_stride, const size_t *enc_b
         }
         return IE_OK;
     }
-    ie_session *s = nullptr;
-    IE_TRY(cached_session(&s, 1, 0, 0, N, 2));
+    SessionLease lease;
+    IE_TRY(lease.acquire(1, 0, 0, N, 2));
+    ie_session *s = lease.get();
     cudaStream_t st = s->stream;
     const size_t es = (maxb + 16 + 15) / 16 * 16;                                   // device stride of a stream
     const uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(count, ((size_t)4 << 30) / (es + raw_stride)));
@@ -602,10 +631,11 @@ int ie_decode_images_dev(ie_session *s, const uint8_t *d_encs, size_t enc_stride
     constexpr size_t kHdr = 160;
     const size_t first = (size_t)(start_bit / 8);
     std::vector<uint8_t> hb((size_t)count * kHdr, 0);
-    size_t minb = enc_bytes[0];
-    for (uint32_t i = 1; i < count; i++) minb = std::min(minb, enc_bytes[i]);
-    if (first >= minb) { set_error("start_bit beyond the stream"); return IE_EFORMAT; }
-    const size_t n = std::min(kHdr, std::min(minb - first, enc_stride - first));
+    for (uint32_t i = 0; i < count; i++)
+        if (first >= enc_bytes[i] || enc_bytes[i] > enc_stride) { set_error("start_bit beyond a stream / stream longer than enc_stride"); return IE_EFORMAT; }
+    // kHdr bytes of every row (bounded by the stride, which the caller owns in full); each header is then parsed from the
+    // bytes its own stream holds -- a short stream in the batch does not truncate its neighbours' headers
+    const size_t n = std::min(kHdr, enc_stride - first);
     IE_CUDA(cudaMemcpy2DAsync(hb.data(), kHdr, d_encs + first, enc_stride, n, count, cudaMemcpyDeviceToHost, st));
     IE_CUDA(cudaStreamSynchronize(st));
     if (!s->ev_fork) IE_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
@@ -620,7 +650,7 @@ int ie_decode_images_dev(ie_session *s, const uint8_t *d_encs, size_t enc_stride
     for (uint32_t i = 0; i < count && rc == IE_OK; i++) {
         ie_session *w = s->workers[i % nw];
         ParsedHeader h;
-        parse_header(hb.data() + (size_t)i * kHdr, n, (size_t)(start_bit % 8), N, h, 0);
+        parse_header(hb.data() + (size_t)i * kHdr, std::min(n, enc_bytes[i] - first), (size_t)(start_bit % 8), N, h, 0);
         h.end_bit += first * 8;
         if (W) W[i] = h.W;
         if (H) H[i] = h.H;
@@ -658,8 +688,9 @@ int ie_decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
 int ie_decode_image(const uint8_t *enc, size_t enc_bytes, uint32_t N, uint8_t *raw_out, size_t raw_cap, uint32_t *W, uint32_t *H) {
     if (!enc || !raw_out || enc_bytes == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
     if (N != 4 && N != 8) { set_error("block size must be 4 or 8"); return IE_EINVAL; }
-    ie_session *s = nullptr;
-    IE_TRY(cached_session(&s, 1, 0, 0, N, 1));
+    SessionLease lease;
+    IE_TRY(lease.acquire(1, 0, 0, N, 1));
+    ie_session *s = lease.get();
     cudaStream_t st = s->stream;
     IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, enc_bytes + 16));
     IE_CUDA(cudaMemcpyAsync(s->d_in, enc, enc_bytes, cudaMemcpyHostToDevice, st));

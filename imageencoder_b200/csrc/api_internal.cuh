@@ -29,7 +29,20 @@ int session_ensure_pipeline(ie_session *s);
 int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size_t start_bit, int N, const ParsedHeader &h,
                      uint8_t *d_out, size_t out_cap, cudaStream_t stream);
 int read_err_flag(ie_session *s, cudaStream_t stream);
-int cached_session(ie_session **out, int kind, uint32_t W, uint32_t H, uint32_t N, uint32_t frames);
+// Exclusive use of a cached session for the duration of one host-buffer call (api_image.cu).
+class SessionLease {
+  public:
+    SessionLease() = default;
+    SessionLease(const SessionLease &) = delete;
+    SessionLease &operator=(const SessionLease &) = delete;
+    ~SessionLease() { release(); }
+    int acquire(int kind, uint32_t W, uint32_t H, uint32_t N, uint32_t frames);
+    void release();
+    ie_session *get() const { return s_; }
+
+  private:
+    ie_session *s_ = nullptr;
+};
 void drop_cached_sessions();
 
 }  // namespace ie

@@ -350,8 +350,9 @@ int ie_encode_video(const uint8_t *yuv, size_t yuv_bytes, uint32_t W, uint32_t H
     IE_TRY(check_video_dims(W, H));
     const size_t fsz = (size_t)W * H * 3 / 2;
     const uint32_t frames = (uint32_t)(yuv_bytes / fsz);
-    ie_session *s = nullptr;
-    IE_TRY(cached_session(&s, 2, W, H, 4, frames));
+    SessionLease lease;
+    IE_TRY(lease.acquire(2, W, H, 4, frames));
+    ie_session *s = lease.get();
     const size_t cap = ie_max_encoded_bytes(W, H, 4, std::max(1u, frames));
     IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, std::max<size_t>(yuv_bytes, 16)));
     const size_t cap16 = (cap + 15) / 16 * 16;
@@ -456,8 +457,9 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
 int ie_decode_video(const uint8_t *enc, size_t enc_bytes, int motioncomp, uint8_t *yuv_out, size_t yuv_cap, size_t *yuv_bytes,
                     uint32_t *Wo, uint32_t *Ho, uint32_t *Fo) {
     if (!enc || !yuv_out || enc_bytes == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
-    ie_session *s = nullptr;
-    IE_TRY(cached_session(&s, 3, 0, 0, 4, 0));
+    SessionLease lease;
+    IE_TRY(lease.acquire(3, 0, 0, 4, 0));
+    ie_session *s = lease.get();
     cudaStream_t st = s->stream;
     IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, enc_bytes + 16));
     IE_CUDA(cudaMemcpyAsync(s->d_in, enc, enc_bytes, cudaMemcpyHostToDevice, st));

@@ -179,6 +179,7 @@ int get_device_state(DeviceState **out) {
     return IE_OK;
 }
 
+void drop_cached_sessions();      // api_image.cu: the host entry points' session cache
 }  // namespace ie
 
 extern "C" {
@@ -191,6 +192,8 @@ int ie_init(int device) {
 }
 
 void ie_shutdown(void) {
+    // the cached sessions of the host entry points hold device scratch and point at the tables freed below
+    ie::drop_cached_sessions();
     std::lock_guard<std::mutex> lk(ie::g_mu);
     int cur = -1;
     cudaGetDevice(&cur);

@@ -187,7 +187,11 @@ __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
     if (gb >= p.nblocks) return;
 
     // ---- fields (Block.cpp:441-472) -------------------------------------------------------------------------
-    unsigned pos = (unsigned)(off[gb] - st.base);
+    // a valid chain keeps the CTA's 128 blocks within 128 maximal blocks of its first one.  A malformed stream does not: once
+    // the parser meets a length field > N*N (IE_EFORMAT) every later block is placed at the end of the stream, which can lie
+    // far outside the staged span -- such a block reads (unspecified, the call fails) bits from inside the staging area
+    const unsigned long long rel = off[gb] - st.base;
+    unsigned pos = (unsigned)min(rel, (unsigned long long)(kStage * 32u - kMaxBlockBits - 64u));
     auto peek = [&](unsigned at) -> unsigned {                 // 32 stream bits starting at `at`, MSB first
         const unsigned i = at >> 5;
         return __funnelshift_l(__byte_perm(st.w[i + 1], 0, 0x0123), __byte_perm(st.w[i], 0, 0x0123), at & 31u);

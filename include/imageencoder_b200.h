@@ -14,6 +14,14 @@
  *   - block size (4|8) and Huffman on/off are compile-time in the reference (Block.hpp:13, makefile:13)
  *     and run-time arguments here.
  *   - there is NO CPU fallback: every call fails with IE_ENODEVICE when no sm_100 device is usable.
+ *   - threads: the HOST entry points (ie_encode_image, ie_decode_image, ie_encode_images, ie_decode_images,
+ *     ie_encode_video, ie_decode_video) may be called concurrently from any number of threads; each call holds its own
+ *     leased scratch session from entry to return (the reference is not re-entrant: file-static LUTs Block.cpp:30-31,
+ *     static Frame::MVEC_BIT_SIZE Frame.cpp:6).  A `_dev` entry point works on the ie_session the caller passes: one
+ *     session, one call at a time (use one session per thread / stream).
+ *   - malformed streams: reads past the end of the stream give zero bits (BitStream.cpp:17-20) and decode like the
+ *     reference; a block whose length field exceeds block*block -- where the reference indexes its zigzag table out of
+ *     bounds, Block.cpp:460-465 -- fails with IE_EFORMAT.
  */
 #ifndef IMAGEENCODER_B200_H
 #define IMAGEENCODER_B200_H
@@ -37,6 +45,7 @@ extern "C" {
 /* Select `device`, create the per-device state (LUTs: zigzag algo.cpp:68-87, cos/C tables algo.cpp:294-297,312,
  * MER pattern algo.cpp:90-139).  Idempotent per device; thread-safe. */
 int ie_init(int device);
+/* Frees the per-device tables and every idle cached session of the host entry points.  A later call re-initialises. */
 void ie_shutdown(void);
 const char *ie_last_error(void);
 /* "imageencoder_b200 x.y (sm_100a)" */

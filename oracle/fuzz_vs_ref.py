@@ -16,7 +16,8 @@ undefined behaviour and are reported separately ("avoid"):
     Frame.cpp:23-29) and put_bit has no bounds check (BitStream.cpp:61-71) -- heap overflow, anything from a garbage last byte
     to corrupted later frames to a glibc abort.
   * (corrupt mode) a block whose length field exceeds N*N: the reference indexes its zigzag table out of bounds
-    (Block.cpp:460-465); the oracle and the product ignore the surplus values.
+    (Block.cpp:460-465) -- undefined behaviour.  The oracle reads and discards the surplus values (so that it can keep
+    walking); the product rejects such a stream with IE_EFORMAT (tests/_variant_worker.py corrupt).
 Prints one summary line; exit code 1 if there is a REAL mismatch."""
 import sys
 import time

@@ -137,18 +137,11 @@ def main_me(variant: int) -> int:
     return 1 if bad else 0
 
 
-def main_corrupt() -> int:
-    """Damaged image streams (bit flips in the body, truncation, trailing garbage; oracle/fuzz_vs_ref.py's generator with a fixed
-    seed) through the default decode path: same pixels as the oracle, which equals the compiled reference wherever the
-    reference's behaviour is defined and ignores the surplus values of a length field > N*N (profiles/r1_oracle_fuzz.md)."""
-    import imageencoder_b200 as ie
+def corrupt_cases(count: int = 300, seed: int = 777):
+    """(N, W, H, mode, damaged stream) -- mode 0 truncated, 1 bit flips in the body, 2 trailing garbage"""
     import oracle
-    from imageencoder_b200 import _lib
-
-    _lib.check(ie.lib().ie_init(0))
-    rng = np.random.default_rng(777)
-    bad = n = 0
-    for _ in range(300):
+    rng = np.random.default_rng(seed)
+    for _ in range(count):
         N = int(rng.choice([4, 8]))
         W, H = N * int(rng.integers(1, 24)), N * int(rng.integers(1, 24))
         img = np.clip(rng.normal(128, rng.uniform(1, 80), (H, W)), 0, 255).astype(np.uint8)
@@ -163,19 +156,48 @@ def main_corrupt() -> int:
                 enc[int(rng.integers(hdr, len(enc)))] ^= 1 << int(rng.integers(0, 8))
         else:
             enc = enc + bytes(rng.integers(0, 256, int(rng.integers(1, 40))).astype(np.uint8))
-        enc = bytes(enc)
-        want = oracle.image_decode(enc, N)[0]
-        n += 1
+        yield N, W, H, mode, bytes(enc)
+
+
+def main_corrupt() -> int:
+    """Damaged image streams (bit flips in the body, truncation, trailing garbage; oracle/fuzz_vs_ref.py's generator with a fixed
+    seed) through the default decode path.  One contract (against Block.cpp:441-472):
+      * no block on the true chain carries a length field > N*N  ->  same pixels as the oracle (= the compiled reference,
+        profiles/r1_oracle_fuzz.md), reads past the end giving zero bits (BitStream.cpp:17-20);
+      * some block's length field exceeds N*N, where the reference indexes its zigzag table out of bounds (undefined
+        behaviour, Block.cpp:460-465)  ->  IE_EFORMAT, nothing else."""
+    import imageencoder_b200 as ie
+    import oracle
+    from imageencoder_b200 import _lib
+    from oracle.fuzz_vs_ref import _has_overlong_block
+
+    _lib.check(ie.lib().ie_init(0))
+    only = int(sys.argv[2]) if len(sys.argv) > 2 else 0          # replay one case (1-based), e.g. under compute-sanitizer
+    bad = n = n_over = 0
+    for n, (N, W, H, mode, enc) in enumerate(corrupt_cases(), 1):
+        if only and n != only:
+            continue
+        overlong = _has_overlong_block(enc, N)
+        n_over += overlong
         try:
             got = ie.decode_image(enc, N)
         except ie.IEError as e:
-            print(f"corrupt case {n} (mode {mode}, {N}x{N}, {W}x{H}): decoder raised {e}")
+            if not (overlong and e.code == _lib.IE_EFORMAT):
+                print(f"corrupt case {n} (mode {mode}, {N}x{N}, {W}x{H}, overlong={overlong}): decoder raised {e}", flush=True)
+                bad += 1
+                if e.code == _lib.IE_ECUDA:
+                    break                      # the CUDA context is gone: every later case would fail the same way
+            continue
+        if overlong:
+            print(f"corrupt case {n} (mode {mode}, {N}x{N}, {W}x{H}): length field > N*N accepted, IE_EFORMAT expected")
             bad += 1
             continue
+        want = oracle.image_decode(enc, N)[0]
         if got.shape != want.shape or not np.array_equal(got, want):
             print(f"corrupt case {n} (mode {mode}, {N}x{N}, {W}x{H}): pixels differ from the oracle's")
             bad += 1
-    print(f"corrupt streams: {'ok' if not bad else f'{bad} of {n} differ'}")
+    print(f"corrupt streams: {n} cases, {n_over} with a length field > N*N (IE_EFORMAT), "
+          f"{'ok' if not bad else f'{bad} wrong'}")
     return 1 if bad else 0
 
 

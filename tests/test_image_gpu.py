@@ -9,7 +9,7 @@ from conftest import GOLDEN, INPUTS
 
 pytestmark = pytest.mark.gpu
 
-SAMPLES = {"ex0": (8, 8), "ex3": (400, 400), "ex6": (512, 256)}
+SAMPLES = {"ex0": (8, 8), "ex1": (936, 936), "ex2": (512, 512), "ex3": (400, 400), "ex4": (4096, 912), "ex6": (512, 256)}
 
 
 def _mat(oracle_mod, name):
@@ -172,3 +172,57 @@ def test_errors(gpu):
         gpu.encode_image(np.zeros(60, np.uint8), 10, 6, np.full(16, 2))          # not a multiple of the block size
     with pytest.raises(IEError):
         gpu.encode_image(np.zeros(64, np.uint8), 8, 8, np.zeros(16))             # quant entry 0
+
+
+def test_host_entry_points_are_thread_safe(gpu, oracle_mod):
+    """include/imageencoder_b200.h: the host entry points may be called from several threads.  Two threads encode and decode
+    images of the SAME shape at the same time (the case where a shared cached session would hand both the same staging
+    buffers and streams); every result must be the oracle's."""
+    import threading
+    from imageencoder_b200.synth import synth_image
+    q = _mat(oracle_mod, "matrix8_1.txt")
+    W, H = 1024, 512
+    imgs = [synth_image(W, H, 500 + i) for i in range(4)]
+    want = [oracle_mod.image_encode(im, W, H, 8, q, True, False) for im in imgs]
+    want_dec = [oracle_mod.image_decode(w, 8)[0] for w in want]
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(12):
+                i = (tid + rep) % len(imgs)
+                enc = gpu.encode_image(imgs[i], W, H, q, True, False)
+                if enc != want[i]:
+                    errors.append(f"thread {tid} rep {rep}: stream differs")
+                    return
+                if not np.array_equal(gpu.decode_image(enc, 8), want_dec[i]):
+                    errors.append(f"thread {tid} rep {rep}: pixels differ")
+                    return
+        except Exception as e:      # noqa: BLE001
+            errors.append(f"thread {tid}: {e!r}")
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    gpu.lib().ie_shutdown()          # drops the idle cached sessions; the next call re-initialises the device tables
+    assert gpu.encode_image(imgs[0], W, H, q, True, False) == want[0]
+
+
+def test_batch_decode_with_one_short_stream(gpu, oracle_mod):
+    """ie_decode_images: a stream cut inside its header must not truncate the headers of the other streams of the batch"""
+    from imageencoder_b200.synth import synth_image
+    q = _mat(oracle_mod, "matrix8_1.txt")
+    W, H = 256, 128
+    imgs = [synth_image(W, H, 600 + i) for i in range(3)]
+    encs = [oracle_mod.image_encode(im, W, H, 8, q, True, False) for im in imgs]
+    good = gpu.decode_images(encs, 8)
+    for d, e in zip(good, encs):
+        assert np.array_equal(d, oracle_mod.image_decode(e, 8)[0])
+    # the header of an 8x8 stream with 8-bit quantiser entries is 549 bits = 69 bytes: cut the middle stream to 70 bytes
+    cut = [encs[0], encs[1][:70], encs[2]]
+    got = gpu.decode_images(cut, 8)
+    for d, e in zip(got, cut):
+        assert np.array_equal(d, oracle_mod.image_decode(e, 8)[0])

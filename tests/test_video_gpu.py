@@ -106,8 +106,6 @@ def test_video_errors(gpu):
         gpu.encode_video(np.zeros(40 * 40 * 3 // 2, np.uint8), 40, 40, np.full(16, 2))   # not a multiple of 16
 
 
-@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: first run pending (the mvec fields inside the "
-                                        "stream are already compared bit for bit by every test above)")
 def test_motion_vectors_and_reconstruction_direct(gpu, oracle_mod):
     """Motion vectors (Block.cpp:267-339) and the encoder-side reconstruction (Frame.cpp:218-242) compared directly, not only
     through the stream: ie_encode_video_dev's optional mvec output [frames][MacroBlocks][2] and the Y planes it rebuilds in place."""

@@ -1,10 +1,11 @@
-"""Instantiations of the tile kernel (ie_set_option("encode_variant", 0|1|2)): byte-identical streams required.
+"""Instantiations of the tile kernel (ie_set_option("encode_variant", 0..7)): byte-identical streams required.
 
 Variant 2 (packed f32x2 transform + lean quantise bookkeeping, imageencoder_b200/csrc/transform_fast.cuh) is the default
 kernel; 0 is the scalar kernel it replaced and 1 the intermediate step, both kept for A/B timing (tools/ab_quick.py) and as
 cross-checks.  Each variant runs in its own process against the CPU oracle and against variant 0
 (tests/_variant_worker.py); the same arithmetic is also run on the CPU (tests/test_lean_variant_cpu.py).
-First confirmed on a B200 in profiles/r1_variant_parity_v9.log."""
+First confirmed on a B200 in profiles/r1_variant_parity_v9.log; the variants 3..7, decode_variant 1 and me_variant 1
+all passed their first B200 run at the end of round 1 (GPUTEST_r01.json) and are strict since."""
 import subprocess
 import sys
 from pathlib import Path
@@ -23,9 +24,6 @@ def test_variant_streams_identical(variant):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.xfail(strict=False, reason="encode variants 3..7 (reduced staging area with 7 / 8 CTAs per SM, short-chain binary64 pre-check "
-                                        "of the exact queue) were written after this round's GPU budget was spent; this is their "
-                                        "first run on a B200; NOT the default kernel")
 @pytest.mark.parametrize("variant", [3, 4, 5, 6, 7])
 def test_experimental_variant_streams_identical(variant):
     """the noise / quantiser-1 cases of the worker overflow the reduced staging area and take the global-memory pack; the
@@ -36,9 +34,6 @@ def test_experimental_variant_streams_identical(variant):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.xfail(strict=False, reason="decode variant 1 was written after this round's GPU budget was spent: its arithmetic is "
-                                        "checked on the CPU (tests/host/lean_check.cu), its first run on a B200 is this one; "
-                                        "it is NOT the default kernel")
 def test_decode_variant_pixels_identical():
     """ie_set_option("decode_variant", 1): packed f32x2 inverse transform + pixel stage (decode_blocks_lean_kernel); own process
     so that a fault in the experimental kernel cannot poison this process's CUDA context."""
@@ -48,8 +43,6 @@ def test_decode_variant_pixels_identical():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.xfail(strict=False, reason="me_variant 1 (REDUX reduction in the motion search) was written after this round's GPU "
-                                        "budget was spent; first run on a B200; NOT the default kernel")
 def test_me_variant_streams_identical():
     r = subprocess.run([sys.executable, str(ROOT / "tests" / "_variant_worker.py"), "me1"], capture_output=True, text=True,
                        timeout=180)
@@ -57,8 +50,6 @@ def test_me_variant_streams_identical():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: first run pending (truncated and padded "
-                                        "streams are already covered by test_image_gpu.py; bit-flipped ones are new)")
 def test_damaged_streams_decode_like_the_oracle():
     """300 damaged image streams (bit flips, truncation, trailing garbage) through the default decode path, in their own process"""
     r = subprocess.run([sys.executable, str(ROOT / "tests" / "_variant_worker.py"), "corrupt"], capture_output=True, text=True,
