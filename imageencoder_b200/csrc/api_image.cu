@@ -30,11 +30,11 @@ int session_ensure_scan(ie_session *s, unsigned images, unsigned tiles) {
     const size_t n = (size_t)images * tiles;
     IE_CUDA(cudaMalloc(&s->d_tile_state, n * sizeof(unsigned long long)));
     IE_CUDA(cudaMalloc(&s->d_bnd, n * sizeof(TileBoundary)));
-    IE_CUDA(cudaMalloc(&s->d_ticket, images * sizeof(unsigned)));
+    IE_CUDA(cudaMalloc(&s->d_ticket, (images + 2) * sizeof(unsigned)));      // + the fused encoder's CTA id / finished-CTA words
     IE_CUDA(cudaMalloc(&s->d_counter, images * sizeof(unsigned long long)));
     IE_CUDA(cudaMemset(s->d_tile_state, 0, n * sizeof(unsigned long long)));
     IE_CUDA(cudaMemset(s->d_bnd, 0, n * sizeof(TileBoundary)));
-    IE_CUDA(cudaMemset(s->d_ticket, 0, images * sizeof(unsigned)));
+    IE_CUDA(cudaMemset(s->d_ticket, 0, (images + 2) * sizeof(unsigned)));
     IE_CUDA(cudaMemset(s->d_counter, 0, images * sizeof(unsigned long long)));
     // cudaMemset on device memory is asynchronous on the legacy default stream, which the sessions' non-blocking streams
     // do not wait for: make the zeroes visible before any kernel can touch these arrays
@@ -159,7 +159,11 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     const unsigned nblocks = (W / N) * (H / N);
     const unsigned TB = encode_tile_blocks(N);
     const unsigned tiles = (nblocks + TB - 1) / TB;
-    IE_TRY(session_ensure_scan(s, images, tiles));
+    // the fused stream kernel (encode_fused.cu): one image, one launch, no scratch round trip
+    const bool fused = g_encode_variant.load() == 8 && !g_exact_transform.load() && images == 1 && !bits_only && !split;
+    unsigned n_wtiles = 0, n_ctatiles = 0;
+    if (fused) encode_fused_sizes(N, nblocks, n_wtiles, n_ctatiles);
+    IE_TRY(session_ensure_scan(s, images, std::max(tiles, n_wtiles)));
     IE_TRY(session_ensure_err(s));
 
     HeaderParam hdr;
@@ -192,6 +196,11 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
     p.hdr = hdr;
     p.out_bits = reinterpret_cast<unsigned long long *>(d_out_bits);
     p.scan = s->scan_state();
+    if (fused) {
+        p.tiles_per_image = n_wtiles;
+        p.scan.ticket = s->d_ticket + s->images;
+        return launch_encode_fused(N, p, append ? 1 : 0, s->dev->sm_count, stream);
+    }
     {
         const size_t ntot = (size_t)images * tiles;
         p.slot_bytes = encode_tile_slot_bytes(N);

@@ -14,6 +14,7 @@ namespace ie {
 extern std::atomic<int> g_exact_transform;   // encode_image.cu
 extern std::atomic<int> g_encode_variant;
 extern std::atomic<int> g_copyout_variant;
+extern std::atomic<int> g_fused_debug;
 extern std::atomic<int> g_decode_variant;      // decode_image.cu
 extern std::atomic<int> g_me_variant;          // api_video.cu
 static thread_local std::string t_error;
@@ -215,15 +216,16 @@ uint64_t ie_kernel_launch_count(void) { return ie::g_launches.load(); }
 int ie_set_option(const char *name, int value) {
     if (name && !strcmp(name, "exact_transform")) { ie::g_exact_transform.store(value); return IE_OK; }
     if (name && !strcmp(name, "encode_variant")) {
-        if (value < 0 || value > 7) {
+        if (value < 0 || value > 8) {
             ie::set_error("encode_variant: 0 (scalar kernel), 1 (lean quantise), 2 (1 + packed f32x2 transform, the default), "
                           "3 / 4 (2 with a reduced staging area and 7 / 8 CTAs per SM), 5 (2 with the short-chain binary64 pre-check of "
-                          "the exact queue), 6 / 7 (3 / 4 with it); 3..7 are experimental");
+                          "the exact queue), 6 / 7 (3 / 4 with it), 8 (fused persistent stream kernel, encode_fused.cu; other launch shapes fall back to 2)");
             return IE_EINVAL;
         }
         ie::g_encode_variant.store(value);
         return IE_OK;
     }
+    if (name && !strcmp(name, "fused_debug")) { ie::g_fused_debug.store(value); return IE_OK; }      // timing experiments, wrong output
     if (name && !strcmp(name, "copyout_variant")) {
         if (value < 0 || value > 2) { ie::set_error("copyout_variant: 0 (generic kernel), 1 (short path for interior chunks) or 2 (1 + four chunks in flight, the default)"); return IE_EINVAL; }
         ie::g_copyout_variant.store(value);

@@ -55,9 +55,13 @@ size_t encode_tile_slot_bytes(int N);      // bytes of scratch per tile
 extern std::atomic<int> g_exact_transform;
 extern std::atomic<int> g_encode_variant;
 extern std::atomic<int> g_copyout_variant;
+extern std::atomic<int> g_fused_debug;
 // max_abs_sample: 128 for pixels - 128, 383 for P-frame residuals - 128
 void make_fast_quant(FastQuant &fq, const uint16_t *quant, int N, double max_abs_sample);
 int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream);
+// fused stream kernel (encode_fused.cu): sizes of the scan arrays it needs, and the launch (one image, whole stream)
+void encode_fused_sizes(int N, unsigned nblocks, unsigned &n_wtiles, unsigned &n_ctatiles);
+int launch_encode_fused(int N, const EncodeParams &p, int append, int sm_count, cudaStream_t stream);
 int launch_pframe_tiles(const EncodeParams &p, unsigned images, cudaStream_t stream);
 int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t stream);          // phase 2 of a split encode
 int launch_tile_totals(const unsigned *tile_bits, unsigned ntiles, unsigned images, unsigned long long add, unsigned long long *d_total,

@@ -21,7 +21,11 @@ t_start = time.time()
 L = ie.lib()
 _lib.check(L.ie_init(0))
 res = {"parity_small": {}, "timing": {}}
-COMBOS = [(0, 0), (2, 0), (2, 1), (2, 2), (3, 2), (4, 2), (5, 2), (6, 2), (7, 2)]          # (encode_variant, copyout_variant)
+COMBOS = [(0, 0), (2, 0), (2, 1), (2, 2), (3, 2), (4, 2), (5, 2), (6, 2), (7, 2), (8, 2)]          # (encode_variant, copyout_variant)
+if "--combos" in sys.argv:                       # e.g. --combos 2:2,8:2
+    i = sys.argv.index("--combos")
+    COMBOS = [tuple(int(x) for x in c.split(":")) for c in sys.argv[i + 1].split(",")]
+    del sys.argv[i:i + 2]
 
 # ---- 1. parity on small images against the oracle
 import oracle

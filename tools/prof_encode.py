@@ -15,6 +15,8 @@ _lib.check(L.ie_init(0))
 rt = C.CDLL("libcudart.so.12")
 size, N = 8192, 8
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+if len(sys.argv) > 2:                                  # python tools/prof_encode.py 4 8  -> encode_variant 8
+    _lib.check(L.ie_set_option(b"encode_variant", int(sys.argv[2])))
 q = np.ascontiguousarray(ie.read_matrix('tests/golden/inputs/matrix8_1.txt'), dtype=np.uint16).reshape(-1)
 qp = q.ctypes.data_as(C.POINTER(C.c_uint16))
 img = np.ascontiguousarray(synth_image(size, size, 1234))
