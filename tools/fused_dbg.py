@@ -28,7 +28,7 @@ def run(n):
     for i in range(n):
         k = i % RING
         _lib.check(L.ie_encode_image_dev(sess, d_raw[k], size, size, qp, 1, 1, 1, 0, d_out[k], C.c_size_t(cap), C.c_void_p(d_bits.value + 8 * k), None))
-for var, dbg in ((2, 0), (8, 0), (8, 1), (8, 2), (8, 3)):
+for var, dbg in ((2, 0), (8, 0), (8, 4), (8, 1), (8, 5)):
     _lib.check(L.ie_set_option(b"encode_variant", var)); _lib.check(L.ie_set_option(b"fused_debug", dbg))
     run(RING); assert rt.cudaDeviceSynchronize() == 0
     rt.cudaEventRecord(e0, None); run(40); rt.cudaEventRecord(e1, None); rt.cudaEventSynchronize(e1)
