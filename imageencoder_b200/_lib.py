@@ -55,6 +55,19 @@ SIGNATURES = {
     "ie_session_set_video_shard": (C.c_int, [_vp, C.c_uint32, C.c_int]),
     "ie_decode_video_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, C.c_int, _vp, C.c_size_t, _u32p, _u32p, _u32p, _vp]),
     "ie_stream_shift_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp]),
+    "ie_comm_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_size_t]),
+    "ie_comm_handle_bytes": (C.c_size_t, []),
+    "ie_comm_export": (C.c_int, [_vp, _vp]),
+    "ie_comm_connect": (C.c_int, [_vp, _vp]),
+    "ie_comm_destroy": (None, [_vp]),
+    "ie_comm_exchange_totals_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "ie_comm_totals_dev": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "ie_comm_copy_totals": (C.c_int, [_vp, _vp, _vp]),
+    "ie_encode_image_shard_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _u16p, C.c_int, C.c_int, _vp,
+                                            C.c_size_t, _vp, _vp, _vp]),
+    "ie_comm_stitch_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "ie_comm_stitched_stream": (C.c_int, [_vp, C.POINTER(_vp), _szp]),
+    "ie_comm_copy_stitched": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "ie_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "ie_kernel_launch_count": (C.c_uint64, []),
 }

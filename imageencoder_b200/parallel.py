@@ -135,6 +135,72 @@ def exchange_bit_totals(local_bits, group=None):
     return totals, offsets
 
 
+class Comm:
+    """ie_comm (csrc/comm.cu): the library's own multi-GPU exchange -- peer-mapped mailboxes written over NVLink, no NCCL on the
+    data path.  `torch.distributed` is used ONCE, at set-up, to swap the CUDA IPC handles (any all-gather of bytes would do)."""
+
+    def __init__(self, rank: int, world: int, stitch_bytes: int = 0, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from ._lib import check, lib
+        self.rank, self.world = rank, world
+        self.h = C.c_void_p()
+        check(lib().ie_comm_create(C.byref(self.h), rank, world, stitch_bytes if rank == 0 else 0))
+        n = int(lib().ie_comm_handle_bytes())
+        blob = C.create_string_buffer(n)
+        check(lib().ie_comm_export(self.h, blob))
+        blobs = [bytes(blob.raw)]
+        if world > 1:
+            blobs = [None] * world
+            dist.all_gather_object(blobs, bytes(blob.raw), group=group)
+        allb = C.create_string_buffer(b"".join(blobs), n * world)
+        check(lib().ie_comm_connect(self.h, allb))
+
+    def close(self):
+        from ._lib import lib
+        if self.h:
+            lib().ie_comm_destroy(self.h)
+            self.h = None
+
+    def encode_image_shard(self, sess, d_raw, width, height_shard, height_total, quant, rle, d_out, d_bits, d_first, lead_bit=True):
+        """block-row shard of one image stream: tile kernel -> mailbox exchange of the shard totals -> copy-out at the global
+        offset (ie_encode_image_shard_dev).  Asynchronous on the current stream."""
+        from . import device
+        from ._lib import check, lib
+        _q, qp = device._q(quant)
+        check(lib().ie_encode_image_shard_dev(sess.h, self.h, device._dp(d_raw), width, height_shard, height_total, qp, int(bool(rle)),
+                                              int(bool(lead_bit)), device._dp(d_out), d_out.numel(), device._dp(d_bits), device._dp(d_first),
+                                              device._stream()))
+
+    def totals(self):
+        """the bit totals of the last exchange: torch int64 tensor [world] on the device (a copy, stream-ordered)"""
+        import torch
+
+        from . import device
+        from ._lib import check, lib
+        out = torch.empty(self.world, dtype=torch.int64, device="cuda")
+        check(lib().ie_comm_copy_totals(self.h, device._dp(out), device._stream()))
+        return out
+
+    def stitch(self, d_shard, d_bits, d_first):
+        """every rank: its chunks -> rank 0's stitch buffer over NVLink (ie_comm_stitch_dev).  Asynchronous."""
+        from . import device
+        from ._lib import check, lib
+        check(lib().ie_comm_stitch_dev(self.h, device._dp(d_shard), device._dp(d_bits), device._dp(d_first), device._stream()))
+
+    def stitched(self, nbytes: int):
+        """rank 0: the first nbytes of the stitched stream as a device tensor (a copy)"""
+        import torch
+
+        from . import device
+        from ._lib import check, lib
+        out = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        check(lib().ie_comm_copy_stitched(self.h, device._dp(out), nbytes, device._stream()))
+        return out
+
+
 class ShardedImageEncoder:
     """Encodes this rank's block-row shard of one large image straight into its place in the single output stream.
 

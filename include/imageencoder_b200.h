@@ -172,6 +172,46 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
  * offsets can come straight from an NCCL all-gather + scan without a host round trip. */
 int ie_stream_shift_dev(const uint8_t *d_in, const uint64_t *d_params, uint8_t *d_out, size_t out_cap, void *stream);
 
+/* ---- multi-GPU exchange: one ie_comm per rank -- one process per GPU, or several GPUs in one process.
+ * The reference is single-process, single-device (ImageEncoder.cpp:121-138); what these replace is the hand-over between its
+ * parallel block loop and its serial writer loop when the block rows of one image live on different GPUs.  A rank owns a
+ * mailbox in its HBM that the peers write over NVLink (CUDA IPC between processes, peer access inside one); nothing here
+ * needs NCCL, MPI or torch.  Set-up is three calls because the processes have to swap handles through whatever plumbing
+ * the host has (torch.distributed.all_gather_object, MPI_Allgather, a file ...):
+ *   ie_comm_create        on every rank (after ie_init on its device); stitch_bytes > 0 on rank 0 allocates the buffer the
+ *                         single output stream is assembled in
+ *   ie_comm_export        this rank's handle blob (ie_comm_handle_bytes() bytes)
+ *   ie_comm_connect       `world` blobs in rank order (all-gathered by the caller)
+ * All calls below are collective: every rank makes them, in the same order. */
+typedef struct ie_comm ie_comm;
+int ie_comm_create(ie_comm **c, int rank, int world, size_t stitch_bytes);
+size_t ie_comm_handle_bytes(void);
+int ie_comm_export(ie_comm *c, void *blob_out);
+int ie_comm_connect(ie_comm *c, const void *blobs);
+void ie_comm_destroy(ie_comm *c);
+/* All-gather of one u64 per rank through the mailboxes (a one-CTA kernel: P2P stores, then a spin on this rank's mailbox):
+ * d_totals_out[world] (device; NULL: kept inside the communicator, see ie_comm_totals_dev). */
+int ie_comm_exchange_totals_dev(ie_comm *c, const uint64_t *d_total, uint64_t *d_totals_out, void *stream);
+int ie_comm_totals_dev(ie_comm *c, const uint64_t **d_totals);
+/* the totals of the last exchange -> dst[world] (host or device memory), asynchronous on `stream` */
+int ie_comm_copy_totals(ie_comm *c, uint64_t *dst, void *stream);
+/* Block-row shard of ONE image stream (BASELINE config 3): ie_encode_image_begin_dev -> mailbox exchange of the shard totals
+ * -> ie_encode_image_end_dev.  This rank's rows [its share of height_total] are at d_raw; d_out receives its bytes of the
+ * global stream from the chunk that holds its first bit; *d_out_bits = (first % 128) + shard bits, *d_first_bit = first
+ * (device).  Rank 0 writes the header, announcing height_total.  Every rank needs at least one block row. */
+int ie_encode_image_shard_dev(ie_session *s, ie_comm *c, const uint8_t *d_raw, uint32_t width, uint32_t height_shard,
+                              uint32_t height_total, const uint16_t *quant, int use_rle, int lead_bit, uint8_t *d_out,
+                              size_t out_cap, uint64_t *d_out_bits, uint64_t *d_first_bit, void *stream);
+/* Device-side stitch: every rank stores its chunks into rank 0's stitch buffer over NVLink at their final position; the
+ * chunk two neighbouring shards share is completed by the right neighbour (it receives the left one's bits through its
+ * mailbox).  d_shard / d_bits / d_first_bit: what ie_encode_image_shard_dev (or ie_stream_shift_dev) left.  The stream's
+ * length is the sum of the exchanged totals. */
+int ie_comm_stitch_dev(ie_comm *c, const uint8_t *d_shard, const uint64_t *d_bits, const uint64_t *d_first_bit, void *stream);
+/* rank 0: the buffer the stitch wrote (device pointer, valid until ie_comm_destroy) */
+int ie_comm_stitched_stream(ie_comm *c, uint8_t **d_stream, size_t *capacity);
+/* rank 0: the first nbytes of the stitched stream -> dst (host or device memory), asynchronous on `stream` */
+int ie_comm_copy_stitched(ie_comm *c, void *dst, size_t nbytes, void *stream);
+
 /* Diagnostics switches (process-wide; every setting produces identical streams, tests cross-check them):
  *   "exact_transform" = 1  the encoders evaluate every coefficient in the reference's exact binary64 order instead of the
  *                          guarded FP32 fast path;

@@ -43,8 +43,46 @@ def main():
     torch.cuda.synchronize()
     hshards = [None] * world
     dist.all_gather_object(hshards, d_h.cpu().numpy().tobytes())
+    # ---- the library's own exchange (ie_comm, csrc/comm.cu): P2P mailboxes instead of the NCCL all-gather, and the single
+    #      output stream assembled ON THE DEVICE in rank 0's stitch buffer (no host merge).  Several sizes and both block sizes;
+    #      repeated calls on one communicator exercise the epoch / parity logic of the mailboxes.
+    from imageencoder_b200 import device
+    from imageencoder_b200.parallel import Comm
+    comm = Comm(rank, world, stitch_bytes=int(ie.lib().ie_max_encoded_bytes(2048, 2048, 8, 1)))
+    comm_results = []
+    for (cw, ch, cn, mat, seed) in ((1024, 1024, 8, "matrix8_2.txt", 4242), (2048, 2048, 8, "matrix8_1.txt", 77), (512, 256, 4, "matrix4_2.txt", 78),
+                                    (64, 8 * world, 8, "matrix8_1.txt", 79), (1024, 1024, 8, "matrix8_2.txt", 4242)):
+        cq = ie.read_matrix(ROOT / "tests" / "golden" / "inputs" / mat)
+        cimg = synth_image(cw, ch, seed)
+        cy0, cy1 = shard_block_rows(ch, cn, world, rank)
+        d_r = torch.from_numpy(cimg[cy0:cy1].copy()).cuda().reshape(-1)
+        sess = device.Session(device.Session.IMAGE_ENCODE, cw, cy1 - cy0, cn)
+        cap = int(ie.lib().ie_max_encoded_bytes(cw, cy1 - cy0, cn, 1)) + 64
+        d_o = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        d_b = torch.zeros(1, dtype=torch.int64, device="cuda")
+        d_f = torch.zeros(1, dtype=torch.int64, device="cuda")
+        for rep in range(3):
+            comm.encode_image_shard(sess, d_r, cw, cy1 - cy0, ch, cq, True, d_o, d_b, d_f)
+            comm.stitch(d_o, d_b, d_f)
+        tot = comm.totals()
+        torch.cuda.synchronize()
+        dist.barrier()                     # every rank's stitch kernel has finished: the root's buffer is complete
+        nbytes = (int(tot.sum().item()) + 7) // 8
+        if rank == 0:
+            got = comm.stitched(nbytes).cpu().numpy().tobytes()
+            comm_results.append((cw, ch, cn, mat, seed, got))
+        dist.barrier()
+        sess.close()
+    comm.close()
     if rank == 0:
         import oracle
+        for (cw, ch, cn, mat, seed, got) in comm_results:
+            cq = ie.read_matrix(ROOT / "tests" / "golden" / "inputs" / mat)
+            want = oracle.image_encode(synth_image(cw, ch, seed), cw, ch, cn, cq, True, False)
+            if got != want:
+                ok = False
+                msg.append(f"ie_comm stitch {cw}x{ch} {cn}x{cn}: {len(got)} vs {len(want)} bytes, first diff at "
+                           f"{next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), -1)}")
         for name, parts, places, huff in (("plain", shards, pl, False), ("huffman", hshards, hpl, True)):
             stream = bytearray()
             for r in range(world):
