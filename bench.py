@@ -3,10 +3,18 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A "step" is one encode of one synthetic raw image shard (per rank) through the fused sm_100a kernel.  Workload at N=1:
-BASELINE config 2 -- synthetic 8192x8192, 8x8 blocks, matrix8_1.txt, RLE on, Huffman off.  At N>1 every rank encodes
-its own 8192x8192 block-row stripe of an 8192 x (8192*N) image (weak scaling; block rows are independent, the only
-exchange is the all-gather of one bit total per rank).  Prints ONE JSON line (contract in the task).
+N = 1  BASELINE config 2 (the configuration the metric is quoted on for one B200): synthetic 8192x8192, 8x8 blocks,
+       matrix8_1.txt, RLE on, Huffman off.  A step = one encode of one image (pixels in HBM -> final stream in HBM);
+       successive images alternate between two sessions / CUDA streams, so one image's copy-out kernel overlaps the next
+       image's tile kernel.  The line also carries the decode half of the metric, the end-to-end figures through the
+       host-buffer C-ABI calls, the reference's CPU time and `parity_sha_ok`: the sha256 of the encoded stream and of the
+       decoded pixels against what the UNMODIFIED reference wrote for the same input (tests/golden/golden_configs.json).
+N > 1  BASELINE config 3 (the sharded configuration): synthetic 16384x16384, 8x8 blocks, matrix8_2.txt, block rows sharded
+       over the ranks, STRONG scaling.  A step = every rank encodes its rows straight into its place of the ONE output
+       stream: tile kernel -> exchange of one u64 per rank through peer-mapped mailboxes over NVLink (ie_comm, no NCCL on the
+       data path) -> copy-out at the global bit offset.  `value` is the plain (pre-Huffman) stage; the device-side stitch of
+       the shards into rank 0's buffer and the Huffman stage are timed separately (extra keys), and the stitched stream's
+       sha256 is checked against the reference's once, outside the timed region.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref, the unmodified reference compiled by
 oracle/build_ref.sh, all host threads) on a bounded sample of the same workload.
@@ -14,6 +22,7 @@ oracle/build_ref.sh, all host threads) on a bounded sample of the same workload.
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -28,11 +37,35 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-W, H, BLOCK = 8192, 8192, 8
-MATRIX = "matrix8_1.txt"
-SEED = 1234
+BLOCK = 8
 RING = 4                       # distinct input/output buffers cycled through (> L2 in total)
-WORKLOAD = "config2: synthetic 8192x8192 raw image, 8x8 blocks (matrix8_1.txt), RLE on, Huffman off"
+CONFIGS = {
+    2: dict(W=8192, H=8192, matrix="matrix8_1.txt", seed=1234, golden="C2|8192x8192|matrix8_1|seed1234",
+            workload="config2: synthetic 8192x8192 raw image, 8x8 blocks (matrix8_1.txt), RLE on, Huffman off"),
+    3: dict(W=16384, H=16384, matrix="matrix8_2.txt", seed=1235, golden="C3|16384x16384|matrix8_2|seed1235",
+            workload="config3: synthetic 16384x16384 raw image, 8x8 blocks (matrix8_2.txt), RLE on, block rows sharded over the "
+                     "ranks; value = plain stage, Huffman stage timed separately"),
+}
+sha = lambda b: hashlib.sha256(bytes(b)).hexdigest()
+
+
+def golden(cfg):
+    p = ROOT / "tests" / "golden" / "golden_configs.json"
+    return json.loads(p.read_text())[cfg["golden"]] if p.exists() else None
+
+
+def bench_config(cfg, world):
+    """The `config` object of the JSON line: identical for both arms."""
+    g = golden(cfg)
+    px = cfg["W"] * cfg["H"]
+    enc = g["plain"]["enc_bytes"] if g else None
+    if world == 1:
+        return {"workload": cfg["workload"], "image": f"{cfg['W']}x{cfg['H']}", "encoded_bytes_per_image": enc,
+                "l2": f"ring of {RING} distinct input/output buffers ({RING * (px + (enc or 0)) >> 20} MiB) > L2, no flush needed",
+                "parallelism": "1 GPU, two sessions on two CUDA streams"}
+    return {"workload": cfg["workload"], "image": f"{cfg['W']}x{cfg['H']}", "encoded_bytes_per_image": enc,
+            "l2": f"ring of {RING} distinct input/output buffers per rank ({RING * (px + (enc or 0)) // world >> 20} MiB) > L2, no flush needed",
+            "parallelism": f"block-row shards x{world} ({cfg['H'] // world} pixel rows per rank), ie_comm mailboxes over NVLink"}
 
 
 def load_peaks():
@@ -96,40 +129,53 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def quant_matrix():
+def quant_matrix(cfg):
     from imageencoder_b200 import read_matrix
-    return read_matrix(ROOT / "tests" / "golden" / "inputs" / MATRIX)
+    return read_matrix(ROOT / "tests" / "golden" / "inputs" / cfg["matrix"])
 
 
-def shard_image(rank: int):
-    """Rows [rank*H, (rank+1)*H) of the 8192 x (8192*N) synthetic image."""
-    from imageencoder_b200.synth import synth_rows
-    return synth_rows(W, rank * H, (rank + 1) * H, SEED)
+def pin_to_gpu_numa_node(local: int):
+    """CPU affinity of this rank = the cores next to its GPU, so that pinned staging memory is first touched on that NUMA
+    node (eight ranks copying through one node's memory controller is what capped the end-to-end figure in round 1)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [i * 64 + b for i, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the unmodified reference (oracle/_ref) on the host cores
 # ----------------------------------------------------------------------------------------------------------------
-def run_reference_sample(rows: int, reps: int = 1):
+def run_reference_sample(cfg, rows: int, reps: int = 1):
     """Encodes the first `rows` pixel rows of the workload image with the compiled reference (all host threads).
-    Returns (Mpixels/s by process() time, threads, per-rep ms)."""
+    Returns (Mpixels/s by process() time per rep, threads, per-rep ms)."""
     import oracle
     from imageencoder_b200.synth import synth_rows
-    img = synth_rows(W, 0, rows, SEED)
+    W = cfg["W"]
+    img = synth_rows(W, 0, rows, cfg["seed"])
     workdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
-    _, res = oracle.ref_image_encode(img, W, rows, BLOCK, quant_matrix(), True, False, threads=os.cpu_count(), reps=reps,
+    _, res = oracle.ref_image_encode(img, W, rows, BLOCK, quant_matrix(cfg), True, False, threads=os.cpu_count(), reps=reps,
                                      workdir=workdir)
     ms = res["process_ms"]
     return [W * rows / (m / 1e3) / 1e6 for m in ms], res["threads"], ms
 
 
-def run_port_sample(rows: int, reps: int = 1):
-    """The oracle port (oracle/oracle_block.c, one thread) on the first `rows` pixel rows of the workload image: used only
-    when the compiled reference (oracle/_ref) is missing.  Returns (Mpixels/s per rep, 1, per-rep ms)."""
+def run_port_sample(cfg, rows: int, reps: int = 1):
+    """The oracle port (oracle/oracle_block.c, one thread): used only when the compiled reference (oracle/_ref) is missing."""
     import oracle
     from imageencoder_b200.synth import synth_rows
-    img = synth_rows(W, 0, rows, SEED)
-    q = quant_matrix()
+    W = cfg["W"]
+    img = synth_rows(W, 0, rows, cfg["seed"])
+    q = quant_matrix(cfg)
     ms = []
     for _ in range(reps):
         t = time.perf_counter()
@@ -138,225 +184,503 @@ def run_port_sample(rows: int, reps: int = 1):
     return [W * rows / (m / 1e3) / 1e6 for m in ms], 1, ms
 
 
+def reference_decode_sample(cfg, rows: int):
+    """reference ImageDecoder::process() (ImageDecoder.cpp:55-122) on the stream of the first `rows` rows; (Mpixels/s, threads, ms)"""
+    import oracle
+    from imageencoder_b200.synth import synth_rows
+    W = cfg["W"]
+    img = synth_rows(W, 0, rows, cfg["seed"])
+    enc = oracle.image_encode(img, W, rows, BLOCK, quant_matrix(cfg), True, False)
+    workdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    _, res = oracle.ref_image_decode(enc, BLOCK, W, rows, threads=os.cpu_count(), workdir=workdir)
+    ms = res["process_ms"][-1]
+    return W * rows / (ms / 1e3) / 1e6, res["threads"], ms
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if rank != 0:
         return
     import oracle
+    cfg = CONFIGS[2 if world == 1 else 3]
+    W, H = cfg["W"], cfg["H"]
     kind = "reference" if oracle.ref_available(BLOCK, False) else "port"
     sample = run_reference_sample if kind == "reference" else run_port_sample
-    # size the sample so that warmup + steps end within a few minutes: probe with 256 rows first
-    probe, threads, pms = sample(256)
-    mpx = probe[0]
-    budget_s = 120.0 / max(1, args.steps + args.warmup)
-    rows = int(min(H, max(256, (mpx * 1e6 * min(budget_s, 20.0)) / W)) // 8 * 8)
-    vals, threads, ms = sample(rows, reps=args.steps + args.warmup)
-    vals, ms = vals[args.warmup:], ms[args.warmup:]
+    # a step = the whole image when warmup + steps of it end within a few minutes, else its first rows (probe with 256 rows)
+    probe, threads, pms = sample(cfg, 256)
+    reps = max(1, args.steps + args.warmup)
+    budget_s = 200.0 / reps
+    rows = int(min(H, max(256, probe[0] * 1e6 * budget_s / W)) // 8 * 8)
+    vals, threads, ms = sample(cfg, rows, reps=reps)
+    vals, ms = vals[args.warmup:] or vals, ms[args.warmup:] or ms
     value = W * rows * len(ms) / (sum(ms) / 1e3) / 1e6
     what = ("reference ImageEncoder::process() (OpenMP)" if kind == "reference"
             else "oracle port (oracle_block.c, single thread; oracle/_ref missing)")
+    whole = "the whole image" if rows == H else f"the first {rows} of {H} pixel rows"
     line = {
         "impl": "reference", "metric": "image encode Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"first {rows} of {H} pixel rows per step, process() only"},
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(cfg, world),
         "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": threads, "kind": kind,
-                         "sample": f"{W}x{rows} stripe of the workload image, {len(ms)} reps, {what}"},
+                         "sample": f"{whole} per step, {len(ms)} reps, process() only, {what}"},
         "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+def cpu_baseline_objects(cfg):
+    """encode (and decode) of a bounded stripe by the compiled reference on the box's host cores: ~10-30 s of CPU work"""
+    out = {}
+    try:
+        import oracle
+        W = cfg["W"]
+        if oracle.ref_available(BLOCK, False):
+            probe, threads, _ = run_reference_sample(cfg, 256)
+            rows = int(min(cfg["H"], max(256, probe[0] * 1e6 * 12.0 / W)) // 8 * 8)
+            vals, threads, ms = run_reference_sample(cfg, rows)
+            out["cpu_baseline"] = {"value": vals[0], "unit": "Mpixels/s", "cores": threads, "kind": "reference",
+                                   "sample": f"{W}x{rows} stripe of the workload image, reference ImageEncoder::process() "
+                                             f"(OpenMP, {ms[0]:.0f} ms)"}
+            drows = int(min(cfg["H"], max(256, rows // 2)) // 8 * 8)
+            dv, dthreads, dms = reference_decode_sample(cfg, drows)
+            out["decode_cpu_baseline"] = {"value": dv, "unit": "Mpixels/s", "cores": dthreads, "kind": "reference",
+                                          "sample": f"stream of a {W}x{drows} stripe of the workload image, reference "
+                                                    f"ImageDecoder::process() (OpenMP, {dms:.0f} ms)"}
+        else:       # oracle/_ref did not travel: the oracle port, one thread, on a smaller stripe
+            probe, threads, _ = run_port_sample(cfg, 64)
+            rows = int(min(cfg["H"], max(64, probe[0] * 1e6 * 12.0 / W)) // 8 * 8)
+            vals, threads, ms = run_port_sample(cfg, rows)
+            out["cpu_baseline"] = {"value": vals[0], "unit": "Mpixels/s", "cores": threads, "kind": "port",
+                                   "sample": f"{W}x{rows} stripe of the workload image, oracle port (oracle_block.c, "
+                                             f"single thread, {ms[0]:.0f} ms; oracle/_ref missing)"}
+    except Exception as e:      # the baseline is a reported number; never fail the bench on it
+        out.setdefault("cpu_baseline", {"value": None, "unit": "Mpixels/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"})
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------
-# our arm
+# our arm, one GPU: config 2
 # ----------------------------------------------------------------------------------------------------------------
-def ours(args):
+def ours_single(args):
+    import torch
+
+    import imageencoder_b200 as ie
+    from imageencoder_b200 import _lib, device
+    from imageencoder_b200.synth import synth_image
+
+    cfg = CONFIGS[2]
+    W, H = cfg["W"], cfg["H"]
+    px = W * H
+    torch.cuda.set_device(0)
+    _lib.check(ie.lib().ie_init(0))
+    q = quant_matrix(cfg)
+    g = golden(cfg)
+
+    # inputs: RING distinct variants (rolled by whole block rows) so that successive steps never find their input in L2
+    base = synth_image(W, H, cfg["seed"])
+    cap = int(ie.lib().ie_max_encoded_bytes(W, H, BLOCK, 1))
+    d_raw = [torch.from_numpy(np.roll(base, 8 * 37 * i, axis=0).copy()).cuda().reshape(-1) for i in range(RING)]
+    d_out = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in range(RING)]
+    d_bits = torch.zeros(RING, dtype=torch.int64, device="cuda")
+    NS = 2                                                             # sessions / streams alternated by successive images
+    sess = [device.Session(device.Session.IMAGE_ENCODE, W, H, BLOCK) for _ in range(NS)]
+    streams = [torch.cuda.Stream() for _ in range(NS)]
+
+    # one C-ABI call per step, arguments prepared once (the GPU step is ~0.1 ms: Python overhead per call must stay far below)
+    import ctypes as C
+    L = ie.lib()
+    qa, qp = device._q(q)
+    calls = {}
+    for k in range(RING):
+        for j in range(NS):
+            calls[(k, j)] = (sess[j].h, C.c_void_p(d_raw[k].data_ptr()), W, H, qp, 1, 1, 1, 0, C.c_void_p(d_out[k].data_ptr()),
+                             C.c_size_t(cap), C.c_void_p(d_bits[k:k + 1].data_ptr()), C.c_void_p(streams[j].cuda_stream))
+
+    def step(i):
+        rc = L.ie_encode_image_dev(*calls[(i % RING, i % NS)])
+        if rc:
+            _lib.check(rc)
+
+    def sync():
+        torch.cuda.synchronize()
+
+    for k in range(2 * RING):      # set-up, not warm-up: sessions allocate their scratch on first use
+        step(k)
+    sync()
+    for i in range(args.warmup):
+        step(i)
+    sync()
+    out_bytes = [int((int(b) + 7) // 8) for b in d_bits.cpu().tolist()]
+    if 0 in out_bytes:
+        raise SystemExit("warm-up produced an empty stream")
+
+    # ---- parity: slot 0 holds the un-rolled workload image -> its stream and its decoded pixels against the reference's
+    parity = {"parity_sha_ok": None}
+    stream0 = d_out[0][: out_bytes[0]].cpu().numpy().tobytes()
+    if g:
+        dec = ie.decode_image(stream0, BLOCK)
+        parity = {"parity_sha_ok": bool(sha(stream0) == g["plain"]["enc_sha256"] and sha(dec.tobytes()) == g["plain"]["dec_sha256"]
+                                        and sha(base) == g["input_sha256"]),
+                  "parity": {"encoded_sha256": sha(stream0), "reference_sha256": g["plain"]["enc_sha256"],
+                             "decoded_matches_reference": bool(sha(dec.tobytes()) == g["plain"]["dec_sha256"]),
+                             "source": "tests/golden/golden_configs.json (unmodified reference, oracle/_ref)"}}
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = ie.launch_count()
+    sync()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(streams[0])
+    for s in streams[1:]:
+        s.wait_stream(streams[0])                                      # nothing starts before t0
+    for i in range(args.steps):
+        step(args.warmup + i)
+    for s in streams[1:]:
+        streams[0].wait_stream(s)
+    t1.record(streams[0])
+    sync()
+    total_ms = t0.elapsed_time(t1)
+    launches = ie.launch_count() - launches0
+
+    # one image at a time on one stream: the duration of the two kernels of a step without any overlap
+    iso = []
+    for i in range(6):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(streams[0])
+        _lib.check(L.ie_encode_image_dev(*calls[(i % RING, 0)]))
+        b.record(streams[0])
+        sync()
+        iso.append(a.elapsed_time(b))
+    iso_ms = statistics.median(iso)
+
+    # ---- decode of the same stream (second half of BASELINE's "encode/decode Mpixels/s"), device-resident
+    sess_d = device.Session(device.Session.IMAGE_DECODE, W, H, BLOCK)
+    d_dec = torch.empty(px, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        device.decode_image_dev(sess_d, d_out[0], out_bytes[0], d_dec, 1)
+    sync()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dreps = 10
+    a.record()
+    for _ in range(dreps):
+        device.decode_image_dev(sess_d, d_out[0], out_bytes[0], d_dec, 1)
+    b.record()
+    sync()
+    dec_ms = a.elapsed_time(b) / dreps
+
+    # ---- e2e: the public host-buffer calls (pinned host memory in, pinned host memory out), copies inside the region
+    h_raw = torch.from_numpy(base).reshape(-1).pin_memory()
+    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    h_raw_np, h_out_np = h_raw.numpy(), h_out.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        n_e2e = ie.encode_image(h_raw_np, W, H, q, True, False, out=h_out_np)      # warm-up (allocates staging)
+    sync()
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        n_e2e = ie.encode_image(h_raw_np, W, H, q, True, False, out=h_out_np)
+    e2e_s = time.perf_counter() - te
+    h_dec = torch.empty(px, dtype=torch.uint8).pin_memory()
+    h_dec_np = h_dec.numpy()
+    enc_np = h_out_np[:n_e2e]
+    for _ in range(2):
+        ie.decode_image(enc_np, BLOCK, out=h_dec_np)
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        ie.decode_image(enc_np, BLOCK, out=h_dec_np)
+    e2e_dec_s = time.perf_counter() - te
+    clocks = sampler.stop()
+
+    peak, peak_src, _ = load_peaks()
+    value = px * args.steps / (total_ms / 1e3) / 1e6
+    step_ms = total_ms / args.steps
+    s_out = out_bytes[0]
+    alg_bytes = px + s_out                                   # SURVEY 8d: W*H in + stream out
+    achieved = alg_bytes / (step_ms / 1e3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("encode_step_dram_bytes")
+        except Exception:
+            traffic = None
+    dec_alg = s_out + px
+    line = {
+        "metric": "image encode Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(cfg, 1),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "encode step = encode_tiles_kernel<8,1,0,1,2> + tile_copyout_fast_kernel<4,8>; achieved = algorithmic "
+                               "bytes / device time per step with the copy-out of one image overlapping the tile kernel of the next "
+                               "(two streams); kernel_ms_isolated = the same two kernels for one image alone on one stream",
+                     "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": step_ms, "kernel_ms_isolated": iso_ms,
+                     "frac_isolated": alg_bytes / (iso_ms / 1e3) / 1e9 / peak},
+        "e2e": {"value": px * e2e_steps / e2e_s / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": px,
+                "d2h_bytes_per_step": int(n_e2e), "steps": e2e_steps,
+                "api": "ie_encode_image (C-ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "decode": {"value": px / (dec_ms / 1e3) / 1e6, "unit": "Mpixels/s", "ms": dec_ms, "n_gpus": 1,
+                   "what": "ie_decode_image_dev of the workload stream (parallel parse + guarded inverse transform), HBM-resident, "
+                           "includes one 160-byte header read-back",
+                   "roofline": {"bound": "hbm", "achieved": dec_alg / (dec_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": dec_alg / (dec_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(dec_alg),
+                                "kernel": "parse_spec_* (4 launches) + decode_blocks_fast_kernel<8,0>"},
+                   "e2e": {"value": px * e2e_steps / e2e_dec_s / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int(n_e2e),
+                           "d2h_bytes_per_step": px, "steps": e2e_steps, "api": "ie_decode_image (C-ABI, pinned host buffers)"}},
+    }
+    line.update(parity)
+    if not args.no_cpu_baseline:
+        cb = cpu_baseline_objects(cfg)
+        line["cpu_baseline"] = cb.get("cpu_baseline")
+        if "decode_cpu_baseline" in cb:
+            line["decode"]["cpu_baseline"] = cb["decode_cpu_baseline"]
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm, N GPUs: config 3, block rows sharded, strong scaling
+# ----------------------------------------------------------------------------------------------------------------
+def ours_sharded(args):
     import torch
     import torch.distributed as dist
 
     import imageencoder_b200 as ie
     from imageencoder_b200 import _lib, device
+    from imageencoder_b200.parallel import (Comm, ShardedHuffmanStage, ShardedImageEncoder, merge_shard_into, shard_block_rows,
+                                            sharded_image_encode_huffman, total_bytes)
+    from imageencoder_b200.synth import synth_rows
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    ncpu = pin_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _lib.check(ie.lib().ie_init(local))
-    q = quant_matrix()
-
-    # ---- inputs: this rank's stripe, RING distinct variants (rolled by whole block rows) so that successive steps
-    #      never find their input in L2 (ring footprint >> 126 MB)
-    base = shard_image(rank)
-    cap = int(ie.lib().ie_max_encoded_bytes(W, H, BLOCK, 1))
-    d_raw = [torch.from_numpy(np.roll(base, 8 * 37 * i, axis=0).copy()).cuda().reshape(-1) for i in range(RING)]
+    cfg = CONFIGS[3]
+    W, H = cfg["W"], cfg["H"]
+    q = quant_matrix(cfg)
+    g = golden(cfg)
+    y0, y1 = shard_block_rows(H, BLOCK, world, rank)
+    hs = y1 - y0
+    base = synth_rows(W, y0, y1, cfg["seed"])
+    cap = int(ie.lib().ie_max_encoded_bytes(W, hs, BLOCK, 1)) + 64
+    d_raw = [torch.from_numpy(np.roll(base, 8 * 37 * i, axis=0).copy() if i else base).cuda().reshape(-1) for i in range(RING)]
     d_out = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in range(RING)]
     d_bits = torch.zeros(RING, dtype=torch.int64, device="cuda")
-    sess = device.Session(device.Session.IMAGE_ENCODE, W, H, BLOCK)
-    sharded = None
-    if world > 1:
-        # block-row shards of one 8192 x (8192*world) image: encode, all-gather of ONE u64 per rank, offset scan,
-        # re-alignment of the shard to the chunk grid of the single output stream (imageencoder_b200/parallel.py)
-        from imageencoder_b200.parallel import ShardedImageEncoder
-        if H * world > 32767:
-            full_h = None          # > 15-bit header field: the shards are still encoded/placed, only the header height saturates
-        else:
-            full_h = H * world
-        sharded = [ShardedImageEncoder(W, H, BLOCK, full_h) for _ in range(RING)]
+    d_first = torch.zeros(RING, dtype=torch.int64, device="cuda")
+    NS = 2                                                             # sessions / streams alternated by successive steps
+    sessions = [device.Session(device.Session.IMAGE_ENCODE, W, hs, BLOCK) for _ in range(NS)]
+    sess = sessions[0]
+    streams = [torch.cuda.Stream() for _ in range(NS)]
+    comm = Comm(rank, world, stitch_bytes=int(ie.lib().ie_max_encoded_bytes(W, H, BLOCK, 1)))
+    # one C-ABI call per step, arguments prepared once.  Successive steps alternate between two sessions / streams (every rank
+    # in the same order), so one shard's copy-out overlaps the next step's tile kernel; the mailboxes are double-buffered
+    import ctypes as C
+    L = ie.lib()
+    qa, qp = device._q(q)
+    calls = {}
+    for k in range(RING):
+        for j in range(NS):
+            calls[(k, j)] = (sessions[j].h, comm.h, C.c_void_p(d_raw[k].data_ptr()), W, hs, H, qp, 1, 1, C.c_void_p(d_out[k].data_ptr()),
+                             C.c_size_t(cap), C.c_void_p(d_bits[k:k + 1].data_ptr()), C.c_void_p(d_first[k:k + 1].data_ptr()),
+                             C.c_void_p(streams[j].cuda_stream))
 
     def step(i):
-        k = i % RING
-        if sharded is None:
-            device.encode_image_dev(sess, d_raw[k], q, True, d_out[k], d_bits[k:k + 1])
-        else:
-            sharded[k].encode(d_raw[k], q, True, rank)
+        rc = L.ie_encode_image_shard_dev(*calls[(i % RING, i % NS)])
+        if rc:
+            _lib.check(rc)
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(RING):          # set-up, not warm-up: every ring slot allocates its session scratch on first use
+    for k in range(RING):
         step(k)
     barrier()
     for i in range(args.warmup):
         step(i)
     barrier()
-    if sharded is not None:
-        d_bits = torch.cat([sh.d_total for sh in sharded])
-    out_bytes = [int((int(b) + 7) // 8) for b in d_bits.cpu().tolist()]
-    if 0 in out_bytes[: min(RING, args.warmup)]:
-        raise SystemExit("warm-up produced an empty stream")
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = ie.launch_count()
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
+    t0.record(streams[0])
+    for st in streams[1:]:
+        st.wait_stream(streams[0])                                     # nothing starts before t0
     for i in range(args.steps):
-        ev[i][0].record()
         step(args.warmup + i)
-        ev[i][1].record()
-    t1.record()
+    for st in streams[1:]:
+        streams[0].wait_stream(st)
+    t1.record(streams[0])
     barrier()
     total_ms = t0.elapsed_time(t1)
     launches = ie.launch_count() - launches0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    if world > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
 
-    # ---- decode of the same stream (second half of BASELINE's "encode/decode Mpixels/s"), device-resident, rank-local
-    dec_ms = None
+    # ---- the ONE output stream, outside the timed region: slot 0 (the un-rolled image) encoded once more, every rank stores
+    #      its chunks into rank 0's buffer over NVLink, rank 0 hashes the result against the reference's file
+    comm.encode_image_shard(sess, d_raw[0], W, hs, H, q, True, d_out[0], d_bits[0:1], d_first[0:1])       # torch's current stream
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    comm.stitch(d_out[0], d_bits[0:1], d_first[0:1])
+    b.record()
+    tot = comm.totals()
+    barrier()
+    stitch_ms = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(stitch_ms, op=dist.ReduceOp.MAX)
+    total_bits = int(tot.sum().item())
+    nbytes = (total_bits + 7) // 8
+    parity_ok = None
+    if rank == 0 and g:
+        got = comm.stitched(nbytes).cpu().numpy().tobytes()
+        parity_ok = bool(sha(got) == g["plain"]["enc_sha256"] and len(got) == g["plain"]["enc_bytes"])
+    barrier()
+
+    # ---- Huffman stage of the sharded stream (BASELINE config 3 asks for RLE + Huffman): parallel.py's exchange (byte shared by
+    #      two shards, all-reduce of histogram / first occurrences, per-rank coding with the global dictionary), wall clock
+    huff = None
     try:
-        sess_d = device.Session(device.Session.IMAGE_DECODE, W, H, BLOCK)
-        d_dec = torch.empty(W * H, dtype=torch.uint8, device="cuda")
-        # (multi-GPU runs: a shard is not a stream of its own, the decode figure is reported by the N=1 run)
-        if sharded is None:
-            d_stream, nb = d_out[0], out_bytes[0]
-            for _ in range(2):
-                device.decode_image_dev(sess_d, d_stream, nb, d_dec, 1)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 5
-            a.record()
-            for _ in range(reps):
-                device.decode_image_dev(sess_d, d_stream, nb, d_dec, 1)
-            b.record()
-            torch.cuda.synchronize()
-            dec_ms = a.elapsed_time(b) / reps
-    except Exception as e:      # decode is an extra figure; never fail the encode bench on it
-        dec_ms = None
-        dec_err = str(e)
+        enc2 = ShardedImageEncoder(W, hs, BLOCK, H)
+        stage = ShardedHuffmanStage(enc2)
+        hpl, d_h = sharded_image_encode_huffman(enc2, stage, d_raw[0], q, True, rank)       # warm-up
+        barrier()
+        th = time.perf_counter()
+        hreps = 3
+        for _ in range(hreps):
+            hpl, d_h = sharded_image_encode_huffman(enc2, stage, d_raw[0], q, True, rank)
+        barrier()
+        h_ms = (time.perf_counter() - th) / hreps * 1e3
+        hshards = [None] * world
+        dist.all_gather_object(hshards, d_h.cpu().numpy().tobytes())
+        if rank == 0:
+            stream = bytearray()
+            for r in range(world):
+                merge_shard_into(stream, hshards[r], hpl[r])
+            hgot = bytes(stream[: total_bytes(hpl)])
+            huff = {"ms_per_image_plain_plus_huffman": h_ms, "encoded_bytes": len(hgot),
+                    "parity_sha_ok": (bool(sha(hgot) == g["huff"]["enc_sha256"]) if g else None),
+                    "what": "block-row sharded encode + Huffman stage over the global histogram (parallel.py, NCCL all-reduce of "
+                            "256 bins + first occurrences; host tree), wall clock incl. its host synchronisations"}
+        del enc2, stage
+    except Exception as e:      # an extra figure; never fail the encode bench on it
+        huff = {"failed": str(e)}
+    barrier()
 
-    # ---- e2e: the public host-buffer call (pinned host memory in, pinned host memory out), copies inside the region
+    # ---- strong-scaling base: the same image on ONE GPU (rank 0 alone, the others idle), same two-stream schedule
+    base1 = None
+    if rank == 0:
+        try:
+            from imageencoder_b200.synth import synth_image
+            full = torch.from_numpy(synth_image(W, H, cfg["seed"])).cuda().reshape(-1)
+            cap1 = int(ie.lib().ie_max_encoded_bytes(W, H, BLOCK, 1))
+            o1 = [torch.empty(cap1, dtype=torch.uint8, device="cuda") for _ in range(NS)]
+            b1 = torch.zeros(NS, dtype=torch.int64, device="cuda")
+            s1 = [device.Session(device.Session.IMAGE_ENCODE, W, H, BLOCK) for _ in range(NS)]
+            c1 = [(s1[j].h, C.c_void_p(full.data_ptr()), W, H, qp, 1, 1, 1, 0, C.c_void_p(o1[j].data_ptr()), C.c_size_t(cap1),
+                   C.c_void_p(b1[j:j + 1].data_ptr()), C.c_void_p(streams[j].cuda_stream)) for j in range(NS)]
+            for i in range(4):
+                _lib.check(L.ie_encode_image_dev(*c1[i % NS]))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n1 = 6
+            e0.record(streams[0])
+            streams[1].wait_stream(streams[0])
+            for i in range(n1):
+                _lib.check(L.ie_encode_image_dev(*c1[i % NS]))
+            streams[0].wait_stream(streams[1])
+            e1.record(streams[0])
+            torch.cuda.synchronize()
+            ms1 = e0.elapsed_time(e1) / n1
+            ok1 = bool(g and sha(o1[0][: (int(b1[0].item()) + 7) // 8].cpu().numpy().tobytes()) == g["plain"]["enc_sha256"])
+            base1 = {"n_gpus": 1, "value": W * H / (ms1 / 1e3) / 1e6, "unit": "Mpixels/s", "ms_per_step": ms1, "parity_sha_ok": ok1,
+                     "what": "the same 16384x16384 image encoded on rank 0's GPU alone (ie_encode_image_dev, two sessions / streams): "
+                             "the base of this strong-scaling series (bench.py --gpus 1 measures config 2)"}
+            del full, o1, s1
+        except Exception as e:
+            base1 = {"failed": str(e)}
+    barrier()
+
+    # ---- e2e: pinned host rows in -> shard encode -> this rank's bytes of the stream back in pinned host memory
     h_raw = torch.from_numpy(base).reshape(-1).pin_memory()
     h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
-    h_raw_np, h_out_np = h_raw.numpy(), h_out.numpy()
     e2e_steps = max(3, min(args.steps, 10))
-    n_e2e = ie.encode_image(h_raw_np, W, H, q, True, False, out=h_out_np)      # warm-up (allocates staging)
-    ie.encode_image(h_raw_np, W, H, q, True, False, out=h_out_np)
+    d_in = torch.empty(W * hs, dtype=torch.uint8, device="cuda")
+    d_bits_h = torch.zeros(1, dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        d_in.copy_(h_raw, non_blocking=True)
+        comm.encode_image_shard(sess, d_in, W, hs, H, q, True, d_out[0], d_bits[0:1], d_first[0:1])
+        d_bits_h.copy_(d_bits[0:1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n = (int(d_bits_h.item()) + 127) // 128 * 16
+        h_out[:n].copy_(d_out[0][:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return n
+
+    n_e2e = e2e_step()
     barrier()
     te = time.perf_counter()
     for _ in range(e2e_steps):
-        n_e2e = ie.encode_image(h_raw_np, W, H, q, True, False, out=h_out_np)
-    torch.cuda.synchronize()
+        n_e2e = e2e_step()
     e2e_s = time.perf_counter() - te
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    t = torch.tensor([e2e_s, float(n_e2e)], device="cuda", dtype=torch.float64)
+    tm = t.clone()
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    e2e_s = float(tm[0].item())
+    d2h_total = int(t[1].item())
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        peak, peak_src, peaks = load_peaks()
+        peak, peak_src, _ = load_peaks()
         px = W * H
-        value = px * world * args.steps / (total_ms / 1e3) / 1e6
-        kernel_ms = statistics.mean(step_ms)
-        s_out = statistics.mean(out_bytes[: min(RING, max(1, args.warmup))]) if args.warmup else out_bytes[0]
-        alg_bytes = px + s_out                                   # W*H in + stream out
-        achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
-        traffic = None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
-            try:
-                traffic = json.loads(tp.read_text()).get("encode_step_dram_bytes")
-            except Exception:
-                traffic = None
+        step_ms = total_ms / args.steps
+        value = px * args.steps / (total_ms / 1e3) / 1e6
+        alg_bytes = px + nbytes                                   # whole image in + whole stream out, all ranks
+        achieved = alg_bytes / (step_ms / 1e3) / 1e9
         line = {
             "metric": "image encode Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_rank": f"{W}x{H} block-row stripe of an {W}x{H * world} image",
-                       "l2": f"ring of {RING} distinct input/output buffers ({RING * (px + cap) >> 20} MiB) > L2, no flush needed",
-                       "encoded_bytes_per_image": int(s_out), "parallelism": f"block-row shards x{world}"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "encode step = encode_tiles_kernel<8,1,0,1,2> + tile_copyout_fast_kernel<4,8> (the tile kernel is "
-                                   "~80 % of it, profiles/r1_launches_v9.csv)",
-                         "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": kernel_ms},
-            "e2e": {"value": px * world * e2e_steps / e2e_s / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": px,
-                    "d2h_bytes_per_step": int(n_e2e) + 16, "steps": e2e_steps,
-                    "api": "ie_encode_image (C-ABI, pinned host buffers)"},
+            "config": bench_config(cfg, world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                         "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
+                         "kernel": "per rank: encode_tiles_kernel + tile_totals_kernel + shard_exchange_kernel (P2P mailboxes) + "
+                                   "stream_init_shard_kernel + tile_copyout_fast_kernel",
+                         "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": step_ms},
+            "e2e": {"value": px * e2e_steps / e2e_s / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": px,
+                    "d2h_bytes_per_step": d2h_total, "steps": e2e_steps,
+                    "api": "ie_encode_image_shard_dev per rank around pinned-host copies of its rows / its bytes of the stream",
+                    "cpu_affinity": (f"{ncpu} cores next to each rank's GPU" if ncpu else "not set")},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "decode": ({"value": px / (dec_ms / 1e3) / 1e6, "unit": "Mpixels/s", "ms": dec_ms, "n_gpus": 1,
-                        "what": "ie_decode_image_dev of rank 0's stream (parallel parse + guarded inverse transform), HBM-resident, "
-                                "includes one 160-byte header read-back"} if dec_ms else None),
+            "parity_sha_ok": parity_ok,
+            "stitch": {"ms": float(stitch_ms.item()), "bytes": nbytes,
+                       "what": "ie_comm_stitch_dev: every rank's chunks -> rank 0's buffer over NVLink, outside the timed region; the "
+                               "sha256 of that buffer is what parity_sha_ok compares with the reference's file"},
+            "huffman_stage": huff,
+            "strong_scaling_base": base1,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                import oracle
-                if oracle.ref_available(BLOCK, False):
-                    probe, threads, _ = run_reference_sample(256)
-                    rows = int(min(H, max(256, probe[0] * 1e6 * 12.0 / W)) // 8 * 8)
-                    vals, threads, ms = run_reference_sample(rows)
-                    line["cpu_baseline"] = {"value": vals[0], "unit": "Mpixels/s", "cores": threads, "kind": "reference",
-                                            "sample": f"{W}x{rows} stripe of the workload image, reference ImageEncoder::process() "
-                                                      f"(OpenMP, {ms[0]:.0f} ms)"}
-                else:       # oracle/_ref did not travel: the oracle port, one thread, on a smaller stripe
-                    probe, threads, _ = run_port_sample(64)
-                    rows = int(min(H, max(64, probe[0] * 1e6 * 12.0 / W)) // 8 * 8)
-                    vals, threads, ms = run_port_sample(rows)
-                    line["cpu_baseline"] = {"value": vals[0], "unit": "Mpixels/s", "cores": threads, "kind": "port",
-                                            "sample": f"{W}x{rows} stripe of the workload image, oracle port (oracle_block.c, "
-                                                      f"single thread, {ms[0]:.0f} ms; oracle/_ref missing)"}
-            except Exception as e:      # the baseline is a reported number; never fail the bench on it
-                line["cpu_baseline"] = {"value": None, "unit": "Mpixels/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    comm.close()
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():
@@ -370,8 +694,18 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         reference_arm(args)
+        return
+    try:
+        import torch
+        ok = torch.cuda.is_available()
+    except Exception:
+        ok = False
+    if not ok:
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        ours_sharded(args)
     else:
-        ours(args)
+        ours_single(args)
 
 
 if __name__ == "__main__":

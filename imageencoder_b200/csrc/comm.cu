@@ -121,7 +121,8 @@ struct ie_comm {
     uint8_t *root_stitch = nullptr;                          // mapped pointer to the root's buffer (root: == stitch)
     size_t root_stitch_bytes = 0;
     bool opened_stitch = false;
-    unsigned long long *d_totals = nullptr;                  // [kMaxRanks + 1]: totals of the last exchange, stream length
+    unsigned long long *d_totals = nullptr;                  // [2][kMaxRanks + 1] by epoch parity: the exchanged totals, this rank's own total
+    unsigned long long *totals_of_epoch() const { return d_totals + (epoch & 1u) * (kMaxRanks + 1); }
     bool connected = false;
 
     CommDev dev() const {
@@ -143,8 +144,8 @@ int ie_comm_create(ie_comm **out, int rank, int world, size_t stitch_bytes) {
     c->rank = rank; c->world = world; c->device = ds->device;
     IE_CUDA(cudaMalloc(&c->box, kMailboxWords * sizeof(unsigned long long)));
     IE_CUDA(cudaMemset(c->box, 0, kMailboxWords * sizeof(unsigned long long)));
-    IE_CUDA(cudaMalloc(&c->d_totals, (kMaxRanks + 1) * sizeof(unsigned long long)));
-    IE_CUDA(cudaMemset(c->d_totals, 0, (kMaxRanks + 1) * sizeof(unsigned long long)));
+    IE_CUDA(cudaMalloc(&c->d_totals, 2 * (kMaxRanks + 1) * sizeof(unsigned long long)));
+    IE_CUDA(cudaMemset(c->d_totals, 0, 2 * (kMaxRanks + 1) * sizeof(unsigned long long)));
     if (rank == 0 && stitch_bytes) {
         c->stitch_bytes = (stitch_bytes + 15) / 16 * 16 + 16;
         IE_CUDA(cudaMalloc(&c->stitch, c->stitch_bytes));
@@ -223,7 +224,7 @@ int ie_comm_exchange_totals_dev(ie_comm *c, const uint64_t *d_total, uint64_t *d
     if (!c->connected) { set_error("ie_comm_connect has not run"); return IE_EINVAL; }
     c->epoch = (c->epoch + 1) & 0xffffu;
     if (c->epoch == 0) c->epoch = 2;                         // 0 is the value of a fresh mailbox; keep the parity sequence
-    unsigned long long *totals = d_totals_out ? reinterpret_cast<unsigned long long *>(d_totals_out) : c->d_totals;
+    unsigned long long *totals = d_totals_out ? reinterpret_cast<unsigned long long *>(d_totals_out) : c->totals_of_epoch();
     IE_CUDA(launch_pdl(shard_exchange_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, c->dev(),
                        reinterpret_cast<const unsigned long long *>(d_total), totals, (int *)nullptr));
     count_launch();
@@ -236,11 +237,15 @@ int ie_encode_image_shard_dev(ie_session *s, ie_comm *c, const uint8_t *d_raw, u
     if (!s || !c || !d_raw || !d_out) { set_error("NULL argument"); return IE_EINVAL; }
     if (H_shard == 0) { set_error("every rank needs at least one block row"); return IE_EINVAL; }
     IE_TRY(ie_session_set_header_height(s, H_total));
-    IE_TRY(ie_encode_image_begin_dev(s, d_raw, W, H_shard, quant, use_rle, lead_bit, c->rank == 0, reinterpret_cast<uint64_t *>(c->d_totals + kMaxRanks),
+    // Two calls may be in flight at once (a caller alternating two sessions / streams so that one shard's copy-out overlaps
+    // the next tile kernel): mailbox slots and the totals arrays go by the parity of the call's epoch.
+    unsigned long long *next = c->d_totals + ((c->epoch + 1) & 1u) * (kMaxRanks + 1);
+    if (((c->epoch + 1) & 0xffffu) == 0) next = c->d_totals;                                   // epoch 0 is skipped: the call gets epoch 2
+    IE_TRY(ie_encode_image_begin_dev(s, d_raw, W, H_shard, quant, use_rle, lead_bit, c->rank == 0, reinterpret_cast<uint64_t *>(next + kMaxRanks),
                                      stream));
-    IE_TRY(ie_comm_exchange_totals_dev(c, reinterpret_cast<const uint64_t *>(c->d_totals + kMaxRanks), nullptr, stream));
-    return ie_encode_image_end_dev(s, reinterpret_cast<const uint64_t *>(c->d_totals), (uint32_t)c->rank, d_out, out_cap, d_out_bits, d_first_bit,
-                                   stream);
+    IE_TRY(ie_comm_exchange_totals_dev(c, reinterpret_cast<const uint64_t *>(next + kMaxRanks), nullptr, stream));
+    return ie_encode_image_end_dev(s, reinterpret_cast<const uint64_t *>(c->totals_of_epoch()), (uint32_t)c->rank, d_out, out_cap, d_out_bits,
+                                   d_first_bit, stream);
 }
 
 int ie_comm_stitch_dev(ie_comm *c, const uint8_t *d_shard, const uint64_t *d_bits, const uint64_t *d_first_bit, void *stream) {
@@ -259,13 +264,13 @@ int ie_comm_stitch_dev(ie_comm *c, const uint8_t *d_shard, const uint64_t *d_bit
 
 int ie_comm_totals_dev(ie_comm *c, const uint64_t **d_totals) {
     if (!c || !d_totals) { set_error("NULL argument"); return IE_EINVAL; }
-    *d_totals = reinterpret_cast<const uint64_t *>(c->d_totals);
+    *d_totals = reinterpret_cast<const uint64_t *>(c->totals_of_epoch());
     return IE_OK;
 }
 
 int ie_comm_copy_totals(ie_comm *c, uint64_t *dst, void *stream) {
     if (!c || !dst) { set_error("NULL argument"); return IE_EINVAL; }
-    IE_CUDA(cudaMemcpyAsync(dst, c->d_totals, (size_t)c->world * sizeof(uint64_t), cudaMemcpyDefault, (cudaStream_t)stream));
+    IE_CUDA(cudaMemcpyAsync(dst, c->totals_of_epoch(), (size_t)c->world * sizeof(uint64_t), cudaMemcpyDefault, (cudaStream_t)stream));
     return IE_OK;
 }
 
