@@ -694,6 +694,29 @@ int ie_decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
     return decode_image_dev(s, d_enc, enc_bytes, (size_t)start_bit, N, h, d_raw_out, raw_cap, st);
 }
 
+int ie_parse_image_header(const uint8_t *bytes, size_t nbytes, uint64_t start_bit, uint32_t N, ie_image_header *out) {
+    if (!bytes || !out || nbytes == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    if (N != 4 && N != 8) { set_error("block size must be 4 or 8"); return IE_EINVAL; }
+    ParsedHeader h;
+    parse_header(bytes, nbytes, (size_t)start_bit, (int)N, h, 0);
+    memset(out, 0, sizeof *out);
+    out->block = N; out->width = h.W; out->height = h.H; out->use_rle = (uint32_t)h.use_rle;
+    out->first_block_bit = (uint64_t)h.end_bit;
+    for (uint32_t i = 0; i < N * N; i++) out->quant[i] = h.quant[i];
+    return IE_OK;
+}
+
+int ie_decode_image_with_header_dev(ie_session *s, const ie_image_header *hdr, const uint8_t *d_enc, size_t enc_bytes, uint8_t *d_raw_out,
+                                    size_t raw_cap, void *stream) {
+    if (!s || !hdr || !d_enc || !d_raw_out) { set_error("NULL argument"); return IE_EINVAL; }
+    if (hdr->block != s->N) { set_error("header block size differs from the session's"); return IE_EINVAL; }
+    ParsedHeader h;
+    memset(&h, 0, sizeof h);
+    for (uint32_t i = 0; i < hdr->block * hdr->block; i++) h.quant[i] = hdr->quant[i];
+    h.use_rle = (int)hdr->use_rle; h.W = hdr->width; h.H = hdr->height; h.end_bit = (size_t)hdr->first_block_bit;
+    return decode_image_dev(s, d_enc, enc_bytes, 0, (int)s->N, h, d_raw_out, raw_cap, (cudaStream_t)stream);
+}
+
 int ie_decode_image(const uint8_t *enc, size_t enc_bytes, uint32_t N, uint8_t *raw_out, size_t raw_cap, uint32_t *W, uint32_t *H) {
     if (!enc || !raw_out || enc_bytes == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
     if (N != 4 && N != 8) { set_error("block size must be 4 or 8"); return IE_EINVAL; }

@@ -313,9 +313,10 @@ __global__ void __launch_bounds__(128, 6) decode_blocks_lean_kernel(const Decode
 }
 
 extern std::atomic<int> g_exact_transform;
-// 1 = inverse transform + pixel stage of the fast decode in packed f32x2 operations (experimental: its arithmetic is checked on
-// the CPU, tests/host/lean_check.cu, but it has not run on a B200 yet; image blocks and I-frames only)
-std::atomic<int> g_decode_variant{0};
+// 1 = inverse transform + pixel stage of the fast decode in packed f32x2 operations (image blocks and I-frames; the default since
+// round 2: arithmetic checked on the CPU, tests/host/lean_check.cu, pixel-identical on the B200 in every decode test, 3 % faster),
+// 0 = the scalar kernel
+std::atomic<int> g_decode_variant{1};
 
 int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream) {
     parse_blocks_kernel<<<images, 32, 0, stream>>>(p);

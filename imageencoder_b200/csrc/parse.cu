@@ -24,6 +24,9 @@
 
 namespace ie {
 
+// 1 = the speculative parse's verdict is ignored and the exact transfer-function path produces the offsets (tests)
+std::atomic<int> g_parse_variant{0};
+
 // Sub-span boundaries inside a group: short spans first, so that the E hypothetical chains of a group are merged after
 // a block or two instead of each being walked through kilobits of stream.
 constexpr int kSubsPerGroup = 9;
@@ -53,6 +56,7 @@ struct ParseParams {
     uint2 *spec_exit;                       // [nspec] (exit offset | kDead, blocks started in the group)
     unsigned *spec_flags;                   // [0] CTA ticket of parse_spec_check, [1] spec_ok, [2] unused, [3] first inconsistent group
     unsigned *walk_base;                    // [nwalk] block count per walk CTA, then (in place) its exclusive scan
+    int force_exact;                        // ie_set_option("parse_variant", 1): ignore the speculation, take the exact path
 };
 
 __device__ __forceinline__ unsigned parse_read_bits(const uint8_t *__restrict__ s, unsigned long long total_bits, unsigned long long p, int n) {
@@ -86,15 +90,16 @@ __device__ __forceinline__ unsigned block_bits_at(const uint8_t *s, unsigned lon
     return 4u + (rle ? w : 0u) + len * w;
 }
 
-__global__ void __launch_bounds__(64) parse_group_tables(const ParseParams p) {
-    pdl_wait();
+// The exact path as ONE kernel (parse_exact_kernel below): its five phases used to be five launches, each returning at once in
+// the normal case (speculation verified) -- 10 us of launch gaps per image for nothing.  Phases are separated by a grid barrier
+// (every CTA is resident: the grid is sized to the SM count).
+__device__ __forceinline__ void parse_group_tables(const ParseParams &p) {
     extern __shared__ unsigned s_parse[];
     const int E = p.E;
     unsigned *s_cnt = s_parse;                                            // [E]
     unsigned *s_memo = s_cnt + E;                                         // [E] exit << 16 | blocks
     unsigned short *s_cur = reinterpret_cast<unsigned short *>(s_memo + E);   // [E]
     unsigned char *s_need = reinterpret_cast<unsigned char *>(s_cur + E + (E & 1));   // [E]
-    if (p.spec_flags[1]) return;                                          // the speculative parse verified: nothing to do
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
     for (unsigned g = blockIdx.x; g < p.ngroups; g += gridDim.x) {
@@ -135,42 +140,39 @@ __global__ void __launch_bounds__(64) parse_group_tables(const ParseParams p) {
     }
 }
 
-__global__ void __launch_bounds__(256) parse_super_tables(const ParseParams p) {
-    pdl_wait();
-    const unsigned sg = blockIdx.x;
-    if (p.spec_flags[1]) return;
-    const unsigned g0 = sg * kSuper, g1 = min(g0 + kSuper, p.ngroups);
-    for (int e = threadIdx.x; e < p.E; e += blockDim.x) {
-        unsigned cur = (unsigned)e, cnt = 0;
-        for (unsigned g = g0; g < g1 && cur != kDead; g++) {
-            const uint2 t = __ldg(p.group_table + (size_t)g * p.E + cur);
-            cur = t.x;
-            cnt += t.y;
+__device__ __forceinline__ void parse_super_tables(const ParseParams &p) {
+    for (unsigned sg = blockIdx.x; sg < p.nsuper; sg += gridDim.x) {
+        const unsigned g0 = sg * kSuper, g1 = min(g0 + kSuper, p.ngroups);
+        for (int e = threadIdx.x; e < p.E; e += blockDim.x) {
+            unsigned cur = (unsigned)e, cnt = 0;
+            for (unsigned g = g0; g < g1 && cur != kDead; g++) {
+                const uint2 t = __ldcg(p.group_table + (size_t)g * p.E + cur);
+                cur = t.x;
+                cnt += t.y;
+            }
+            p.super_table[(size_t)sg * p.E + e] = make_uint2(cur, cnt);
         }
-        p.super_table[(size_t)sg * p.E + e] = make_uint2(cur, cnt);
     }
 }
 
-__global__ void parse_top_walk(const ParseParams p) {
-    pdl_wait();
-    if (threadIdx.x != 0 || blockIdx.x != 0 || p.spec_flags[1]) return;
+__device__ __forceinline__ void parse_top_walk(const ParseParams &p) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     unsigned cur = 0, cnt = 0;
     for (unsigned sg = 0; sg < p.nsuper; sg++) {
         p.super_entry[sg] = make_uint2(cur, cnt);
-        if (cur != kDead) { const uint2 t = p.super_table[(size_t)sg * p.E + cur]; cur = t.x; cnt += t.y; }
+        if (cur != kDead) { const uint2 t = __ldcg(p.super_table + (size_t)sg * p.E + cur); cur = t.x; cnt += t.y; }
     }
 }
 
-__global__ void __launch_bounds__(64) parse_down_super(const ParseParams p) {
-    pdl_wait();
-    const unsigned sg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sg >= p.nsuper || p.spec_flags[1]) return;
-    const uint2 se = p.super_entry[sg];
-    unsigned cur = se.x, cnt = se.y;
-    const unsigned g0 = sg * kSuper, g1 = min(g0 + kSuper, p.ngroups);
-    for (unsigned g = g0; g < g1; g++) {
-        p.group_entry[g] = make_uint2(cur, cnt);
-        if (cur != kDead) { const uint2 t = __ldg(p.group_table + (size_t)g * p.E + cur); cur = t.x; cnt += t.y; }
+__device__ __forceinline__ void parse_down_super(const ParseParams &p) {
+    for (unsigned sg = blockIdx.x * blockDim.x + threadIdx.x; sg < p.nsuper; sg += gridDim.x * blockDim.x) {
+        const uint2 se = __ldcg(p.super_entry + sg);
+        unsigned cur = se.x, cnt = se.y;
+        const unsigned g0 = sg * kSuper, g1 = min(g0 + kSuper, p.ngroups);
+        for (unsigned g = g0; g < g1; g++) {
+            p.group_entry[g] = make_uint2(cur, cnt);
+            if (cur != kDead) { const uint2 t = __ldcg(p.group_table + (size_t)g * p.E + cur); cur = t.x; cnt += t.y; }
+        }
     }
 }
 
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(TH) parse_spec_check(const ParseParams p) {
             for (unsigned gg = firstbad / TH * TH; gg < firstbad; gg++) base += p.spec_exit[gg].y;
             if (base < p.nblocks) ok = 0;
         }
-        p.spec_flags[1] = ok;
+        p.spec_flags[1] = p.force_exact ? 0u : ok;
     }
 }
 
@@ -446,32 +448,57 @@ __global__ void __launch_bounds__(TH) parse_spec_emit(const ParseParams p) {
     }
 }
 
-// block_off[] from the exact kernels' group entries (only when the speculative parse did not verify)
-__global__ void __launch_bounds__(64) parse_emit_offsets(const ParseParams p) {
-    pdl_wait();
-    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.ngroups || p.spec_flags[1]) return;
-    const uint2 ge = p.group_entry[g];
-    if (ge.x == kDead) return;
+// block_off[] from the exact path's group entries (only when the speculative parse did not verify)
+__device__ __forceinline__ void parse_emit_offsets(const ParseParams &p) {
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
-    const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
-    unsigned long long pos = g_start + ge.x;
-    unsigned idx = ge.y;
-    while (pos < g_end && pos < total && idx < p.nblocks) {
-        const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
-        if (bits == kBadBlock) { if (p.err) atomicExch(p.err, IE_EFORMAT); pos = total; break; }   // malformed stream
-        p.block_off[idx++] = pos;
-        pos = min(pos + bits, total);
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < p.ngroups; g += gridDim.x * blockDim.x) {
+        const uint2 ge = __ldcg(p.group_entry + g);
+        if (ge.x == kDead) continue;
+        const unsigned long long g_start = B0 + (unsigned long long)g * kGroupBits, g_end = g_start + kGroupBits;
+        unsigned long long pos = g_start + ge.x;
+        unsigned idx = ge.y;
+        while (pos < g_end && pos < total && idx < p.nblocks) {
+            const unsigned bits = block_bits_at(p.enc, total, pos, p.NN, p.use_rle);
+            if (bits == kBadBlock) { if (p.err) atomicExch(p.err, IE_EFORMAT); pos = total; break; }   // malformed stream
+            p.block_off[idx++] = pos;
+            pos = min(pos + bits, total);
+        }
+        if (idx <= p.nblocks && pos >= total) {
+            for (; idx < p.nblocks; idx++) p.block_off[idx] = total;
+            p.block_off[p.nblocks] = total;
+            *p.cursor_next = total;
+        } else if (idx == p.nblocks && ge.y < p.nblocks) {
+            p.block_off[idx] = pos;                 // this thread emitted the last block
+            *p.cursor_next = pos;
+        }
     }
-    if (idx <= p.nblocks && pos >= total) {
-        for (; idx < p.nblocks; idx++) p.block_off[idx] = total;
-        p.block_off[p.nblocks] = total;
-        *p.cursor_next = total;
-    } else if (idx == p.nblocks && ge.y < p.nblocks) {
-        p.block_off[idx] = pos;                 // this thread emitted the last block
-        *p.cursor_next = pos;
+}
+
+// grid barrier of parse_exact_kernel: spec_flags[2] counts arrivals (zeroed by parse_spec_walk at the start of every parse)
+__device__ __forceinline__ void parse_grid_barrier(const ParseParams &p, unsigned phase) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&p.spec_flags[2], 1u);
+        while (ld_relaxed_u32(&p.spec_flags[2]) < phase * gridDim.x) __nanosleep(100);
+        __threadfence();
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(64) parse_exact_kernel(const ParseParams p) {
+    pdl_wait();
+    if (p.spec_flags[1]) return;                            // the speculative parse verified (every CTA sees the same flag)
+    parse_group_tables(p);
+    parse_grid_barrier(p, 1);
+    parse_super_tables(p);
+    parse_grid_barrier(p, 2);
+    parse_top_walk(p);
+    parse_grid_barrier(p, 3);
+    parse_down_super(p);
+    parse_grid_barrier(p, 4);
+    parse_emit_offsets(p);
 }
 
 __global__ void parse_commit_cursor(const ParseParams p) {
@@ -536,6 +563,7 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     p.block_off = d.block_off;
     p.cursor_out = d.cursor;
     p.err = d.err;
+    p.force_exact = g_parse_variant.load() == 1;
     const size_t smem = (size_t)E * (4 + 4 + 2 + 1) + 16;
     static const bool dbg = getenv("IE_DEBUG_SYNC") != nullptr;
 #define IE_DBG_STEP(name) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(stream); if (e_ != cudaSuccess) { fprintf(stderr, "[ie] %s failed: %s\n", name, cudaGetErrorString(e_)); return cuda_fail(e_, name, __FILE__, __LINE__); } } } while (0)
@@ -544,19 +572,18 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     if (d.N == 8) IE_TRY((launch_spec<8192, 64>(p, stream)));
     else IE_TRY((launch_spec<2048, 256>(p, stream)));
     IE_DBG_STEP("parse_spec");
-    IE_CUDA(launch_pdl(parse_group_tables, dim3(std::min(p.ngroups, 148u * 8u)), dim3(64), smem, stream, p));
-    IE_DBG_STEP("parse_group_tables");
-    IE_CUDA(launch_pdl(parse_super_tables, dim3(p.nsuper), dim3(256), 0, stream, p));
-    IE_DBG_STEP("parse_super_tables");
-    IE_CUDA(launch_pdl(parse_top_walk, dim3(1), dim3(32), 0, stream, p));
-    IE_DBG_STEP("parse_top_walk");
-    IE_CUDA(launch_pdl(parse_down_super, dim3((p.nsuper + 63) / 64), dim3(64), 0, stream, p));
-    IE_DBG_STEP("parse_down_super");
-    IE_CUDA(launch_pdl(parse_emit_offsets, dim3((p.ngroups + 63) / 64), dim3(64), 0, stream, p));
-    IE_DBG_STEP("parse_emit_offsets");
+    {
+        // one launch for the whole exact path; every CTA must be resident for its grid barriers: 2 CTAs of 64 threads per SM
+        static int sms = 0;
+        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        static bool configured = false;
+        if (!configured) { IE_CUDA(cudaFuncSetAttribute(parse_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024)); configured = true; }
+        IE_CUDA(launch_pdl(parse_exact_kernel, dim3(2u * (unsigned)sms), dim3(64), smem, stream, p));
+        IE_DBG_STEP("parse_exact_kernel");
+    }
     if (p.cursor_out) { IE_CUDA(launch_pdl(parse_commit_cursor, dim3(1), dim3(1), 0, stream, p)); count_launch(); }
 #undef IE_DBG_STEP
-    count_launch(9);
+    count_launch(5);
     IE_CUDA(cudaGetLastError());
     return IE_OK;
 }

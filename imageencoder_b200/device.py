@@ -90,6 +90,24 @@ def decode_image_dev(s: Session, d_enc: torch.Tensor, enc_bytes: int, d_raw_out:
     return w.value, h.value
 
 
+class ImageHeader(C.Structure):
+    """ie_image_header (include/imageencoder_b200.h)"""
+    _fields_ = [("block", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("use_rle", C.c_uint32),
+                ("first_block_bit", C.c_uint64), ("quant", C.c_uint16 * 64)]
+
+
+def parse_image_header(first_bytes: bytes, block: int, start_bit: int = 1) -> ImageHeader:
+    h = ImageHeader()
+    buf = (C.c_uint8 * len(first_bytes)).from_buffer_copy(first_bytes)
+    check(lib().ie_parse_image_header(buf, len(first_bytes), start_bit, block, C.byref(h)))
+    return h
+
+
+def decode_image_with_header_dev(s: Session, hdr: ImageHeader, d_enc: torch.Tensor, enc_bytes: int, d_raw_out: torch.Tensor) -> None:
+    """fully asynchronous on torch's current stream (no header read-back)"""
+    check(lib().ie_decode_image_with_header_dev(s.h, C.byref(hdr), _dp(d_enc), enc_bytes, _dp(d_raw_out), d_raw_out.numel(), _stream()))
+
+
 def decode_images_dev(s: Session, d_encs: torch.Tensor, enc_stride: int, enc_bytes, d_raws_out: torch.Tensor, raw_stride: int,
                       start_bit: int = 1):
     """Batch decode of device-resident plain streams on the session's worker streams; returns the (W, H) lists."""

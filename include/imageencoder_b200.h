@@ -130,6 +130,18 @@ int ie_image_bits_dev(ie_session *s, const uint8_t *d_raw, uint32_t width, uint3
  * d_enc must be 16-byte aligned (cudaMalloc'ed buffers are) and readable up to enc_bytes rounded up to 4. */
 int ie_decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, uint64_t start_bit,
                         uint8_t *d_raw_out, size_t raw_cap, uint32_t *width, uint32_t *height, void *stream);
+/* The same without the header read-back (and the stream synchronisation it costs): a caller that holds the first bytes of
+ * the plain stream on the host -- the file reader does (ImageBase.cpp:98-129) -- parses the header once
+ * (ie_parse_image_header: MatrixReader.cpp:45-57, ImageBase.cpp:122-128; start_bit = 1 behind the '0' "no Huffman" bit)
+ * and every decode of that stream is then fully asynchronous on `stream`. */
+typedef struct ie_image_header {
+    uint32_t block, width, height, use_rle;
+    uint64_t first_block_bit;          /* bit of the stream at which the first block starts */
+    uint16_t quant[64];
+} ie_image_header;
+int ie_parse_image_header(const uint8_t *bytes, size_t nbytes, uint64_t start_bit, uint32_t block, ie_image_header *out);
+int ie_decode_image_with_header_dev(ie_session *s, const ie_image_header *hdr, const uint8_t *d_enc, size_t enc_bytes,
+                                    uint8_t *d_raw_out, size_t raw_cap, void *stream);
 /* Byte-wise Huffman stage over a device-resident, byte-rounded plain stream (Huffman.cpp:232-344).
  * Synchronises `stream` once (the 256-entry tree is built on the host exactly as the reference does). */
 /* Batch of device-resident plain streams (stream i at d_encs + i * enc_stride, enc_bytes[i] bytes; enc_stride a multiple
@@ -222,8 +234,8 @@ int ie_comm_copy_stitched(ie_comm *c, void *dst, size_t nbytes, void *stream);
  *                          of the exact queue, 6 / 7 = 3 / 4 with that pre-check;
  *   "copyout_variant" = 0 | 1 | 2 (default)  copy-out kernel: 2 = short path for interior chunks with four chunks per
  *                          thread in flight, 1 = short path one chunk at a time, 0 = the generic kernel;
- *   "decode_variant"  = 0 (default) | 1  block-decode kernel of images and I-frames: 1 = inverse transform and pixel
- *                          stage in packed f32x2 operations (experimental; arithmetic checked on the CPU only so far);
+ *   "decode_variant"  = 0 | 1 (default)  block-decode kernel of images and I-frames: 1 = inverse transform and pixel
+ *                          stage in packed f32x2 operations, 0 = the scalar kernel it replaced;
  *   "me_variant"      = 0 (default) | 1  motion-search kernel: 1 = SAD partial sums reduced with warp-wide integer
  *                          reductions (REDUX) instead of shuffle + add steps (experimental, not yet timed).
  * Returns IE_EINVAL for an unknown name or an out-of-range value. */

@@ -109,7 +109,7 @@ def main_decode(variant: int) -> int:
     if not np.array_equal(ie.decode_video(enc, True)[0], oracle.video_decode(enc, True)[0]):
         print(f"decode variant {variant}: decoded video differs")
         bad += 1
-    _lib.check(L.ie_set_option(b"decode_variant", 0))
+    _lib.check(L.ie_set_option(b"decode_variant", 1))
     print(f"decode variant {variant}: {'ok' if not bad else f'{bad} mismatches'}")
     return 1 if bad else 0
 

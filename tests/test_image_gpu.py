@@ -226,3 +226,26 @@ def test_batch_decode_with_one_short_stream(gpu, oracle_mod):
     got = gpu.decode_images(cut, 8)
     for d, e in zip(got, cut):
         assert np.array_equal(d, oracle_mod.image_decode(e, 8)[0])
+
+
+def test_decode_with_header_parsed_on_the_host(gpu, oracle_mod):
+    """ie_parse_image_header + ie_decode_image_with_header_dev: no header read-back, same pixels"""
+    import torch
+    from imageencoder_b200 import device
+    from imageencoder_b200.synth import synth_image
+    for mat, (W, H) in (("matrix8_1.txt", (512, 384)), ("matrix4_2.txt", (256, 128))):
+        q = _mat(oracle_mod, mat)
+        N = q.shape[0]
+        img = synth_image(W, H, 700)
+        for rle in (True, False):
+            enc = oracle_mod.image_encode(img, W, H, N, q, rle, False)
+            hdr = device.parse_image_header(enc[:160], N)
+            assert (hdr.width, hdr.height, hdr.block, hdr.use_rle) == (W, H, N, int(rle))
+            assert list(hdr.quant[: N * N]) == [int(v) for v in np.asarray(q).reshape(-1)]
+            d_enc = torch.zeros(len(enc) + 32, dtype=torch.uint8, device="cuda")
+            d_enc[: len(enc)] = torch.frombuffer(bytearray(enc), dtype=torch.uint8).cuda()
+            d_raw = torch.zeros(W * H, dtype=torch.uint8, device="cuda")
+            sess = device.Session(device.Session.IMAGE_DECODE, W, H, N)
+            device.decode_image_with_header_dev(sess, hdr, d_enc, len(enc), d_raw)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_raw.cpu().numpy().reshape(H, W), oracle_mod.image_decode(enc, N)[0])

@@ -51,7 +51,7 @@ def test_decode_variant_option_is_validated():
         assert L.ie_set_option(b"decode_variant", 2) != 0
         assert L.ie_set_option(b"decode_variant", -1) != 0
     finally:
-        assert L.ie_set_option(b"decode_variant", 0) == 0          # the default
+        assert L.ie_set_option(b"decode_variant", 1) == 0          # the default
 
 
 def test_me_variant_option_is_validated():

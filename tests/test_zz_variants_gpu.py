@@ -77,3 +77,40 @@ def test_copyout_variant_streams_identical(gpu, oracle_mod):
                     assert gpu.encode_image(img, w, h, q, True, False) == want, (mat, img.shape, cv)
     finally:
         L.ie_set_option(b"copyout_variant", 2)
+
+
+def test_exact_parse_path_matches_oracle(gpu, oracle_mod):
+    """ie_set_option("parse_variant", 1): the speculative parse's verdict is ignored, the exact transfer-function path
+    (parse_exact_kernel: five phases behind grid barriers in one launch) finds the block offsets.  Images, a video (cursor mode,
+    one parse per frame) and truncated streams."""
+    import numpy as np
+    from conftest import INPUTS
+    from imageencoder_b200.synth import synth_image, synth_video
+    L = gpu.lib()
+    assert L.ie_set_option(b"parse_variant", 1) == 0
+    try:
+        for mat in ("matrix8_1.txt", "matrix8_2.txt", "matrix4_2.txt"):
+            q = oracle_mod.read_matrix(INPUTS / mat)
+            n = q.shape[0]
+            for img in (synth_image(1024, 768, 41), synth_image(512, 384, 42, flat=True), np.full((64, 64), 128, np.uint8),
+                        np.random.default_rng(9).integers(0, 256, (128, 96)).astype(np.uint8)):
+                h, w = img.shape
+                for rle in (True, False):
+                    enc = oracle_mod.image_encode(img, w, h, n, q, rle, False)
+                    want = oracle_mod.image_decode(enc, n)[0]
+                    assert np.array_equal(gpu.decode_image(enc, n), want), (mat, img.shape, rle)
+                    cut = enc[: max(160, len(enc) * 2 // 3)]            # the header stays whole
+                    assert np.array_equal(gpu.decode_image(cut, n), oracle_mod.image_decode(cut, n)[0]), (mat, img.shape, rle, "cut")
+        q = oracle_mod.read_matrix(INPUTS / "matrix8_1.txt")
+        big = synth_image(4096, 2048, 1234)
+        enc = gpu.encode_image(big, 4096, 2048, q, True, False)
+        L.ie_set_option(b"parse_variant", 0)
+        want = gpu.decode_image(enc, 8)
+        L.ie_set_option(b"parse_variant", 1)
+        assert np.array_equal(gpu.decode_image(enc, 8), want)
+        q4 = oracle_mod.read_matrix(INPUTS / "matrix.txt")
+        yuv = synth_video(64, 48, 5)
+        venc = oracle_mod.video_encode(yuv, 64, 48, q4, True, 3, 16, False)
+        assert np.array_equal(gpu.decode_video(venc, True)[0], oracle_mod.video_decode(venc, True)[0])
+    finally:
+        L.ie_set_option(b"parse_variant", 0)
