@@ -16,6 +16,7 @@ extern std::atomic<int> g_encode_variant;
 extern std::atomic<int> g_copyout_variant;
 extern std::atomic<int> g_fused_debug;
 extern std::atomic<int> g_parse_variant;       // parse.cu
+extern std::atomic<int> g_huffman_variant;     // huffman.cu
 extern std::atomic<int> g_decode_variant;      // decode_image.cu
 extern std::atomic<int> g_me_variant;          // api_video.cu
 static thread_local std::string t_error;
@@ -227,6 +228,11 @@ int ie_set_option(const char *name, int value) {
         return IE_OK;
     }
     if (name && !strcmp(name, "fused_debug")) { ie::g_fused_debug.store(value); return IE_OK; }      // timing experiments, wrong output
+    if (name && !strcmp(name, "huffman_variant")) {
+        if (value < 0 || value > 1) { ie::set_error("huffman_variant: 1 (span histogram + bits / scan / pack kernels, default) or 0 (the round-1 kernels)"); return IE_EINVAL; }
+        ie::g_huffman_variant.store(value);
+        return IE_OK;
+    }
     if (name && !strcmp(name, "parse_variant")) {
         if (value < 0 || value > 1) { ie::set_error("parse_variant: 0 (speculate + verify, exact path as fallback; default) or 1 (always the exact path)"); return IE_EINVAL; }
         ie::g_parse_variant.store(value);

@@ -19,6 +19,9 @@
 
 namespace ie {
 
+// 1 (default) = the round-2 kernels (span histogram, bits / scan / input-centric pack), 0 = the round-1 kernels (cross-check)
+std::atomic<int> g_huffman_variant{1};
+
 constexpr int kHuffTileBytes = kThreads * 16;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -189,6 +192,215 @@ __global__ void __launch_bounds__(kThreads) huff_encode_kernel(const HuffEncodeP
         *p.bit_counter = G + T;
         atomicExch(st.ticket, 0u);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Round 2: the Huffman stage as bandwidth-shaped kernels (the kernels above took 128 + 188 us on the 27.7 MB stream of
+// config 2; they stay as the cross-check: ie_set_option("huffman_variant", 0)).
+//   byte_hist_span_kernel  every CTA counts one contiguous span of the input in per-warp shared-memory histograms (plain
+//                          shared atomics: the stream's bytes are close to uniform) and notes, per symbol, the first CTA
+//                          that saw it
+//   byte_first_kernel      a warp per symbol scans that CTA's span for the symbol's first position -- the reference's
+//                          tie-breaking depends on first-occurrence order (Huffman.cpp:236-243)
+//   huff_bits_kernel       code bits per 4 KiB tile              (the dictionary is known by now: built on the host)
+//   huff_scan_kernel       one CTA: exclusive scan of the tile totals -> every tile's first bit, the stream's length
+//   huff_pack_kernel       input-centric: a thread concatenates the codes of its 16 bytes in registers and writes whole words
+//                          into a shared-memory image of the tile's bits (shared atomicOr only where two threads meet); the
+//                          image goes out through the same chunk writer as the block encoder.  No look-back: the offsets
+//                          are known before the kernel starts.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kHist2Threads = 256;
+__global__ void __launch_bounds__(kHist2Threads) byte_hist_span_kernel(const uint8_t *__restrict__ in, size_t n, size_t span, unsigned *hist,
+                                                                     unsigned *first_cta) {
+    __shared__ unsigned s_h[kHist2Threads / 32][256];
+    for (int i = threadIdx.x; i < (kHist2Threads / 32) * 256; i += kHist2Threads) (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const size_t b0 = (size_t)blockIdx.x * span, b1 = min(n, b0 + span);           // span is a multiple of 16
+    unsigned *h = s_h[threadIdx.x >> 5];
+    for (size_t b = b0 + (size_t)threadIdx.x * 16; b < b1; b += (size_t)kHist2Threads * 16) {
+        if (b + 16 <= b1) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(in + b));
+            const unsigned words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 16; i++) atomicAdd(&h[(words[i >> 2] >> (8 * (i & 3))) & 0xffu], 1u);
+        } else {
+            for (size_t i = b; i < b1; i++) atomicAdd(&h[in[i]], 1u);
+        }
+    }
+    __syncthreads();
+    unsigned c = 0;
+#pragma unroll
+    for (int w = 0; w < kHist2Threads / 32; w++) c += s_h[w][threadIdx.x];
+    if (c) {
+        atomicAdd(&hist[threadIdx.x], c);
+        atomicMin(&first_cta[threadIdx.x], blockIdx.x);
+    }
+}
+
+// first_pos[sym] = position of the symbol's first occurrence: it lies in the span of the first CTA that counted it
+__global__ void __launch_bounds__(256) byte_first_kernel(const uint8_t *__restrict__ in, size_t n, size_t span, const unsigned *first_cta,
+                                                         unsigned long long *first_pos) {
+    const unsigned sym = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (sym >= 256) return;
+    const unsigned cta = first_cta[sym];
+    if (cta == 0xFFFFFFFFu) { if (lane == 0) first_pos[sym] = ~0ull; return; }
+    const size_t b0 = (size_t)cta * span, b1 = min(n, b0 + span);
+    for (size_t b = b0 + (size_t)lane * 16; b - (size_t)lane * 16 < b1; b += 512) {
+        unsigned hit = 16;
+        if (b + 16 <= b1) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(in + b));
+            const unsigned words[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 15; i >= 0; i--) if (((words[i >> 2] >> (8 * (i & 3))) & 0xffu) == sym) hit = i;
+        } else {
+            for (size_t i = b; i < b1; i++) if (in[i] == sym) { hit = (unsigned)(i - b); break; }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit < 16);
+        if (m) {
+            const int src = __ffs((int)m) - 1;
+            const unsigned h = __shfl_sync(0xffffffffu, hit, src);
+            if (lane == 0) first_pos[sym] = (unsigned long long)(b0 + (b - b0 - (size_t)lane * 16) + (size_t)src * 16 + h);
+            return;
+        }
+    }
+    if (lane == 0) first_pos[sym] = ~0ull;                 // cannot happen: the CTA counted the symbol
+}
+
+constexpr int kPackThreads = 256;
+constexpr int kPackTileBytes = kPackThreads * 16;                           // 4 KiB of input per CTA
+constexpr int kPackImageWords = kPackTileBytes;                            // worst case: 32-bit codes -> 32 bits per input byte
+
+struct HuffPackParams {
+    const uint8_t *in;
+    size_t n;
+    unsigned ntiles;
+    const HuffCodes *codes;
+    unsigned *tile_bits;                 // [ntiles]
+    unsigned long long *tile_off;        // [ntiles] first bit of the tile in the stream
+    uint8_t *out;
+    size_t out_cap;
+    unsigned long long *bit_counter;     // in: first free bit of the stream; out: one past the last bit
+    int *err;
+    ScanState scan;                      // tile-boundary hand-off records
+};
+
+__device__ __forceinline__ uint4 load_tile_bytes(const uint8_t *in, size_t base_byte, int nbytes, int b0) {
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (b0 + 16 <= nbytes && ((uintptr_t)(in + base_byte) % 16 == 0)) {
+        q = __ldg(reinterpret_cast<const uint4 *>(in + base_byte) + (b0 >> 4));
+    } else if (b0 < nbytes) {
+        unsigned w[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 16 && b0 + i < nbytes; i++) w[i >> 2] |= (unsigned)in[base_byte + b0 + i] << (8 * (i & 3));
+        q = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return q;
+}
+
+__global__ void __launch_bounds__(kPackThreads) huff_bits_kernel(const HuffPackParams p) {
+    __shared__ unsigned char s_len[256];
+    __shared__ unsigned s_part[kPackThreads / 32];
+    s_len[threadIdx.x] = p.codes->len[threadIdx.x];
+    __syncthreads();
+    for (unsigned tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const size_t base_byte = (size_t)tile * kPackTileBytes;
+        const int nbytes = (int)min((size_t)kPackTileBytes, p.n - base_byte);
+        const int b0 = threadIdx.x * 16;
+        const uint4 q = load_tile_bytes(p.in, base_byte, nbytes, b0);
+        const unsigned words[4] = {q.x, q.y, q.z, q.w};
+        unsigned bits = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (b0 + i < nbytes) bits += s_len[(words[i >> 2] >> (8 * (i & 3))) & 0xffu];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = bits;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned t = 0;
+            for (int w = 0; w < kPackThreads / 32; w++) t += s_part[w];
+            p.tile_bits[tile] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) huff_scan_kernel(const HuffPackParams p) {
+    __shared__ unsigned long long s_sum[1024];
+    const unsigned per = (p.ntiles + 1023) / 1024;
+    const unsigned t0 = threadIdx.x * per, t1 = min(t0 + per, p.ntiles);
+    unsigned long long sum = 0;
+    for (unsigned t = t0; t < t1; t++) sum += p.tile_bits[t];
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned long long v = (threadIdx.x >= (unsigned)d) ? s_sum[threadIdx.x - d] : 0ull;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const unsigned long long start = *p.bit_counter;
+    unsigned long long base = start + s_sum[threadIdx.x] - sum;
+    for (unsigned t = t0; t < t1; t++) { p.tile_off[t] = base; base += p.tile_bits[t]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) *p.bit_counter = start + s_sum[1023];
+}
+
+__global__ void __launch_bounds__(kPackThreads) huff_pack_kernel(const HuffPackParams p) {
+    __shared__ __align__(16) unsigned s_img[kPackImageWords + 8];
+    __shared__ unsigned s_word[256];
+    __shared__ unsigned char s_len[256];
+    __shared__ unsigned s_warp[kPackThreads / 32];
+    s_word[threadIdx.x] = p.codes->word[threadIdx.x];
+    s_len[threadIdx.x] = p.codes->len[threadIdx.x];
+    const unsigned tile = blockIdx.x;
+    const size_t base_byte = (size_t)tile * kPackTileBytes;
+    const int nbytes = (int)min((size_t)kPackTileBytes, p.n - base_byte);
+    const int b0 = threadIdx.x * 16;
+    const uint4 q = load_tile_bytes(p.in, base_byte, nbytes, b0);
+    const unsigned words[4] = {q.x, q.y, q.z, q.w};
+    const unsigned T = p.tile_bits[tile];
+    const unsigned nw = (T + 31) / 32;
+    for (unsigned i = threadIdx.x; i < (nw + 3) / 4; i += kPackThreads) reinterpret_cast<uint4 *>(s_img)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    // this thread's bits and where they start inside the tile
+    unsigned bits = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        if (b0 + i < nbytes) bits += s_len[(words[i >> 2] >> (8 * (i & 3))) & 0xffu];
+    unsigned inc = bits;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    unsigned pos = inc - bits;
+    for (int w = 0; w < wid; w++) pos += s_warp[w];
+    // concatenate the codes (<= 32 bits each, Huffman.cpp:86-88) and write whole words; the first and the last word may be
+    // shared with the neighbouring threads
+    unsigned *ow = s_img + (pos >> 5);
+    unsigned long long acc = 0;
+    int nacc = (int)(pos & 31u);
+    bool first = nacc != 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (b0 + i < nbytes) {
+            const unsigned sym = (words[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            const int l = s_len[sym];
+            acc = (acc << l) | (unsigned long long)s_word[sym];
+            nacc += l;
+            if (nacc >= 32) {
+                nacc -= 32;
+                const unsigned w = (unsigned)(acc >> nacc);
+                if (first) { atomicOr(ow, w); first = false; } else *ow = w;
+                ow++;
+            }
+        }
+    }
+    if (nacc > 0) atomicOr(ow, (unsigned)(acc << (32 - nacc)));
+    __syncthreads();
+    SmemStreamTile t;
+    t.words = s_img; t.nwords = nw;
+    tile_write_chunks_n<kPackThreads>(t, p.scan, tile, tile == 0, tile + 1 == p.ntiles, p.tile_off[tile], T, p.out, p.out_cap, p.err);
 }
 
 // out bits [shift, shift + 8 n) = in bytes; out bits [0, shift) = 0; whole 32-bit words, zero padded.
@@ -522,6 +734,29 @@ static int build_dictionary(const unsigned *hist, const unsigned long long *firs
 
 static int ensure_scratch(ie_session *s, size_t need) { return session_reserve(&s->d_scratch, &s->scratch_cap, need); }
 
+// hist[256] (u32) and first[256] (u64) of n bytes, on the device; d_first_cta: 256 u32 of scratch (variant 1 only)
+static int launch_byte_histogram(const uint8_t *d_in, size_t n, unsigned *d_hist, unsigned long long *d_first, unsigned *d_first_cta,
+                                 int sm_count, cudaStream_t st) {
+    IE_CUDA(cudaMemsetAsync(d_hist, 0, 256 * 4, st));
+    if (g_huffman_variant.load() == 0 || !d_first_cta || ((uintptr_t)d_in % 16)) {
+        IE_CUDA(cudaMemsetAsync(d_first, 0xff, 256 * 8, st));
+        const int grid = (int)std::min<size_t>((n / 16 + 255) / 256 + 1, (size_t)sm_count * 8);
+        byte_hist_kernel<<<grid, 256, 0, st>>>(d_in, n, d_hist, d_first);
+        count_launch();
+    } else {
+        IE_CUDA(cudaMemsetAsync(d_first_cta, 0xff, 256 * 4, st));
+        const size_t want = (size_t)sm_count * 8;
+        size_t span = ((n + want - 1) / want + 15) / 16 * 16;
+        span = std::max<size_t>(span, 4096);
+        const unsigned grid = (unsigned)((n + span - 1) / span);
+        byte_hist_span_kernel<<<grid, kHist2Threads, 0, st>>>(d_in, n, span, d_hist, d_first_cta);
+        byte_first_kernel<<<32, 256, 0, st>>>(d_in, n, span, d_first_cta, d_first);
+        count_launch(2);
+    }
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
 // Dictionary from a (global) histogram, then the scan-pack of `n` bytes behind it (write_dict) or from bit 0 (a later shard of
 // a multi-GPU stream).  Leaves the stream's bit count in s->d_counter[0].  The scratch must be ensured by the caller.
 static int huffman_pack_dev(ie_session *s, const uint8_t *d_in, size_t n, const unsigned *hist, const unsigned long long *first,
@@ -536,15 +771,31 @@ static int huffman_pack_dev(ie_session *s, const uint8_t *d_in, size_t n, const 
     if (out_cap < hdr_bytes16 + 16) { set_error("output buffer too small"); return IE_ENOSPC; }
     IE_CUDA(cudaMemcpyAsync(d_out, hdr.buf.data(), hdr_bytes16, cudaMemcpyHostToDevice, st));
     IE_CUDA(cudaMemcpyAsync(d_codes, &codes, sizeof codes, cudaMemcpyHostToDevice, st));
-    const unsigned ntiles = (unsigned)((n + kHuffTileBytes - 1) / kHuffTileBytes);
-    IE_TRY(session_ensure_scan(s, 1, ntiles));
+    const bool v0 = g_huffman_variant.load() == 0;
+    // (the scan arrays -- the stream's bit counter among them -- may be re-allocated here: before the counter is set)
+    IE_TRY(session_ensure_scan(s, 1, (unsigned)((n + (v0 ? kHuffTileBytes : kPackTileBytes) - 1) / (v0 ? kHuffTileBytes : kPackTileBytes))));
     const unsigned long long hb = hdr.pos;
     IE_CUDA(cudaMemcpyAsync(s->d_counter, &hb, sizeof hb, cudaMemcpyHostToDevice, st));
-    HuffEncodeParams p;
-    p.in = d_in; p.n = n; p.ntiles = ntiles; p.codes = d_codes; p.out = d_out; p.out_cap = out_cap;
-    p.bit_counter = s->d_counter; p.err = s->d_err; p.scan = s->scan_state();
-    huff_encode_kernel<<<ntiles, kThreads, 0, st>>>(p);
-    count_launch();
+    if (v0) {
+        const unsigned ntiles = (unsigned)((n + kHuffTileBytes - 1) / kHuffTileBytes);
+        HuffEncodeParams p;
+        p.in = d_in; p.n = n; p.ntiles = ntiles; p.codes = d_codes; p.out = d_out; p.out_cap = out_cap;
+        p.bit_counter = s->d_counter; p.err = s->d_err; p.scan = s->scan_state();
+        huff_encode_kernel<<<ntiles, kThreads, 0, st>>>(p);
+        count_launch();
+    } else {
+        const unsigned ntiles = (unsigned)((n + kPackTileBytes - 1) / kPackTileBytes);
+        IE_TRY(session_reserve(&s->d_tile_meta, &s->tile_meta_cap, (size_t)ntiles * (sizeof(unsigned long long) + sizeof(unsigned)) + 64));
+        HuffPackParams p;
+        p.in = d_in; p.n = n; p.ntiles = ntiles; p.codes = d_codes; p.out = d_out; p.out_cap = out_cap;
+        p.tile_off = reinterpret_cast<unsigned long long *>(s->d_tile_meta);
+        p.tile_bits = reinterpret_cast<unsigned *>(s->d_tile_meta + (size_t)ntiles * sizeof(unsigned long long));
+        p.bit_counter = s->d_counter; p.err = s->d_err; p.scan = s->scan_state();
+        huff_bits_kernel<<<std::min<unsigned>(ntiles, (unsigned)s->dev->sm_count * 8u), kPackThreads, 0, st>>>(p);
+        huff_scan_kernel<<<1, 1024, 0, st>>>(p);
+        huff_pack_kernel<<<ntiles, kPackThreads, 0, st>>>(p);
+        count_launch(3);
+    }
     IE_CUDA(cudaGetLastError());
     IE_CUDA(cudaStreamSynchronize(st));            // `codes` / `hdr` are host objects of this frame
     return IE_OK;
@@ -562,14 +813,13 @@ int ie_byte_histogram_dev(const uint8_t *d_in, size_t n, uint32_t *hist, uint64_
     DeviceState *dev;
     IE_TRY(get_device_state(&dev));
     uint8_t *d = nullptr;
-    IE_CUDA(cudaMalloc(&d, 256 * 4 + 256 * 8));
+    IE_CUDA(cudaMalloc(&d, 256 * 4 + 256 * 8 + 256 * 4));
     unsigned *d_hist = reinterpret_cast<unsigned *>(d + 256 * 8);
     unsigned long long *d_first = reinterpret_cast<unsigned long long *>(d);
-    cudaMemsetAsync(d_hist, 0, 256 * 4, st);
-    cudaMemsetAsync(d_first, 0xff, 256 * 8, st);
-    const int grid = (int)std::min<size_t>((n / 16 + 255) / 256 + 1, (size_t)dev->sm_count * 8);
-    byte_hist_kernel<<<grid, 256, 0, st>>>(d_in, n, d_hist, d_first);
-    count_launch();
+    {
+        const int rc = launch_byte_histogram(d_in, n, d_hist, d_first, reinterpret_cast<unsigned *>(d + 256 * 8 + 256 * 4), dev->sm_count, st);
+        if (rc != IE_OK) { cudaFree(d); return rc; }
+    }
     cudaMemcpyAsync(hist, d_hist, 256 * 4, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(first_pos, d_first, 256 * 8, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
@@ -583,19 +833,14 @@ int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
     if (!s || !d_in || !d_out || !out_bytes || n == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
     if ((uintptr_t)d_out % 16) { set_error("stream buffers must be 16-byte aligned"); return IE_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
-    // scratch layout: first[256] u64 | hist[256] u32 | HuffCodes | counter u64
-    const size_t need = 256 * 8 + 256 * 4 + sizeof(HuffCodes) + 64;
+    // scratch layout: first[256] u64 | hist[256] u32 | HuffCodes | 64 | first_cta[256] u32
+    const size_t need = 256 * 8 + 256 * 4 + sizeof(HuffCodes) + 64 + 256 * 4;
     IE_TRY(ensure_scratch(s, need));
     unsigned long long *d_first = reinterpret_cast<unsigned long long *>(s->d_scratch);
     unsigned *d_hist = reinterpret_cast<unsigned *>(s->d_scratch + 256 * 8);
+    unsigned *d_first_cta = reinterpret_cast<unsigned *>(s->d_scratch + 256 * 8 + 256 * 4 + sizeof(HuffCodes) + 64);
     IE_TRY(session_ensure_err(s));
-
-    IE_CUDA(cudaMemsetAsync(d_hist, 0, 256 * 4, st));
-    IE_CUDA(cudaMemsetAsync(d_first, 0xff, 256 * 8, st));
-    const int grid = (int)std::min<size_t>((n / 16 + 255) / 256 + 1, (size_t)s->dev->sm_count * 8);
-    byte_hist_kernel<<<grid, 256, 0, st>>>(d_in, n, d_hist, d_first);
-    count_launch();
-    IE_CUDA(cudaGetLastError());
+    IE_TRY(launch_byte_histogram(d_in, n, d_hist, d_first, d_first_cta, s->dev->sm_count, st));
     unsigned hist[256];
     unsigned long long first[256];
     IE_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, st));
@@ -623,7 +868,7 @@ int ie_huffman_encode_shard_dev(ie_session *s, const uint8_t *d_in, size_t n, co
     if (!s || !d_in || !d_out || !hist || !first_pos || n == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
     if ((uintptr_t)d_out % 16) { set_error("stream buffers must be 16-byte aligned"); return IE_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
-    IE_TRY(ensure_scratch(s, 256 * 8 + 256 * 4 + sizeof(HuffCodes) + 64));
+    IE_TRY(ensure_scratch(s, 256 * 8 + 256 * 4 + sizeof(HuffCodes) + 64 + 256 * 4));
     IE_TRY(session_ensure_err(s));
     unsigned h[256];
     unsigned long long f[256];

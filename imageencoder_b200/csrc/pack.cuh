@@ -176,15 +176,15 @@ __device__ __forceinline__ uint4 gather_chunk(const SmemStreamTile &t, long long
 }
 
 // Writes the tile's bits [G, G+T) into `out`.  first_tile/last_tile refer to the launch.  See the contract above.
-template <class Tile>
-__device__ __forceinline__ void tile_write_chunks(const Tile &t, const ScanState &st, unsigned tile, bool first_tile, bool last_tile,
-                                                  unsigned long long G, unsigned T, uint8_t *out, unsigned long long out_cap_bytes,
-                                                  int *d_err) {
+template <int THREADS, class Tile>
+__device__ __forceinline__ void tile_write_chunks_n(const Tile &t, const ScanState &st, unsigned tile, bool first_tile, bool last_tile,
+                                                    unsigned long long G, unsigned T, uint8_t *out, unsigned long long out_cap_bytes,
+                                                    int *d_err) {
     if (T == 0) return;
     const unsigned long long c0 = G / kChunkBits, c1 = (G + T - 1) / kChunkBits;
     const bool head_shared = (G % kChunkBits) != 0;
     const bool tail_shared = ((G + T) % kChunkBits) != 0 && !last_tile;
-    for (unsigned long long c = c0 + threadIdx.x; c <= c1; c += kThreads) {
+    for (unsigned long long c = c0 + threadIdx.x; c <= c1; c += THREADS) {
         const long long ls = (long long)(c * kChunkBits) - (long long)G;
         uint4 v = gather_chunk(t, ls);
         if ((c + 1) * 16ull > out_cap_bytes) { if (d_err) atomicExch(d_err, IE_ENOSPC); continue; }
@@ -213,6 +213,13 @@ __device__ __forceinline__ void tile_write_chunks(const Tile &t, const ScanState
         }
         *dst = v;
     }
+}
+
+template <class Tile>
+__device__ __forceinline__ void tile_write_chunks(const Tile &t, const ScanState &st, unsigned tile, bool first_tile, bool last_tile,
+                                                  unsigned long long G, unsigned T, uint8_t *out, unsigned long long out_cap_bytes,
+                                                  int *d_err) {
+    tile_write_chunks_n<kThreads>(t, st, tile, first_tile, last_tile, G, T, out, out_cap_bytes, d_err);
 }
 
 #endif  // __CUDACC__
