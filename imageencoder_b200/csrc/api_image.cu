@@ -406,6 +406,7 @@ void ie_session_destroy(ie_session *s) {
     cudaFree(s->d_tile_state); cudaFree(s->d_bnd); cudaFree(s->d_ticket); cudaFree(s->d_counter); cudaFree(s->d_err);
     cudaFree(s->d_block_off); cudaFree(s->d_parse); cudaFree(s->d_tile_scratch); cudaFree(s->d_tile_meta); cudaFree(s->d_scratch); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_tmp);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->h_huff) cudaFreeHost(s->h_huff);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->stream_in) {
         cudaStreamDestroy(s->stream_in); cudaStreamDestroy(s->stream_out);

@@ -245,21 +245,28 @@ __global__ void __launch_bounds__(256) byte_first_kernel(const uint8_t *__restri
     const unsigned cta = first_cta[sym];
     if (cta == 0xFFFFFFFFu) { if (lane == 0) first_pos[sym] = ~0ull; return; }
     const size_t b0 = (size_t)cta * span, b1 = min(n, b0 + span);
-    for (size_t b = b0 + (size_t)lane * 16; b - (size_t)lane * 16 < b1; b += 512) {
-        unsigned hit = 16;
-        if (b + 16 <= b1) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(in + b));
-            const unsigned words[4] = {q.x, q.y, q.z, q.w};
+    // 2 KiB of the span per iteration: lane l looks at bytes [64 l, 64 l + 64) of it
+    for (size_t wb = b0; wb < b1; wb += 2048) {
+        const size_t b = wb + (size_t)lane * 64;
+        unsigned hit = 64;
+        if (b + 64 <= b1) {
+            uint4 q[4];
 #pragma unroll
-            for (int i = 15; i >= 0; i--) if (((words[i >> 2] >> (8 * (i & 3))) & 0xffu) == sym) hit = i;
+            for (int k = 0; k < 4; k++) q[k] = __ldg(reinterpret_cast<const uint4 *>(in + b) + k);
+#pragma unroll
+            for (int k = 3; k >= 0; k--) {
+                const unsigned words[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+                for (int i = 15; i >= 0; i--) if (((words[i >> 2] >> (8 * (i & 3))) & 0xffu) == sym) hit = 16 * k + i;
+            }
         } else {
             for (size_t i = b; i < b1; i++) if (in[i] == sym) { hit = (unsigned)(i - b); break; }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, hit < 16);
+        const unsigned m = __ballot_sync(0xffffffffu, hit < 64);
         if (m) {
             const int src = __ffs((int)m) - 1;
             const unsigned h = __shfl_sync(0xffffffffu, hit, src);
-            if (lane == 0) first_pos[sym] = (unsigned long long)(b0 + (b - b0 - (size_t)lane * 16) + (size_t)src * 16 + h);
+            if (lane == 0) first_pos[sym] = (unsigned long long)(wb + (size_t)src * 64 + h);
             return;
         }
     }
@@ -762,19 +769,26 @@ static int launch_byte_histogram(const uint8_t *d_in, size_t n, unsigned *d_hist
 static int huffman_pack_dev(ie_session *s, const uint8_t *d_in, size_t n, const unsigned *hist, const unsigned long long *first,
                             int write_dict, uint8_t *d_out, size_t out_cap, cudaStream_t st) {
     HuffCodes *d_codes = reinterpret_cast<HuffCodes *>(s->d_scratch + 256 * 8 + 256 * 4);
-    HuffCodes codes;
+    // dictionary header, codes and the stream's first bit travel from pinned memory the session owns: the copies are truly
+    // asynchronous and nothing on this frame has to outlive them (no stream synchronisation in here)
+    constexpr size_t kHuffPinned = 2048 + sizeof(HuffCodes) + 16;
+    if (!s->h_huff) IE_CUDA(cudaMallocHost(&s->h_huff, kHuffPinned));
+    HuffCodes &codes = *reinterpret_cast<HuffCodes *>(s->h_huff + 2048);
+    unsigned long long &hb = *reinterpret_cast<unsigned long long *>(s->h_huff + 2048 + sizeof(HuffCodes));
     HostBitWriter hdr;
     IE_TRY(build_dictionary(hist, first, codes, hdr));
     if (!write_dict) { hdr.pos = 0; hdr.buf.assign(16, 0); }
     const size_t hdr_bytes16 = std::max<size_t>(16, (hdr.pos + 127) / 128 * 16);
     hdr.buf.resize(hdr_bytes16, 0);
+    if (hdr_bytes16 > 2048) { set_error("Huffman dictionary header larger than 2 KiB"); return IE_EINVAL; }
     if (out_cap < hdr_bytes16 + 16) { set_error("output buffer too small"); return IE_ENOSPC; }
-    IE_CUDA(cudaMemcpyAsync(d_out, hdr.buf.data(), hdr_bytes16, cudaMemcpyHostToDevice, st));
+    memcpy(s->h_huff, hdr.buf.data(), hdr_bytes16);
+    IE_CUDA(cudaMemcpyAsync(d_out, s->h_huff, hdr_bytes16, cudaMemcpyHostToDevice, st));
     IE_CUDA(cudaMemcpyAsync(d_codes, &codes, sizeof codes, cudaMemcpyHostToDevice, st));
     const bool v0 = g_huffman_variant.load() == 0;
     // (the scan arrays -- the stream's bit counter among them -- may be re-allocated here: before the counter is set)
     IE_TRY(session_ensure_scan(s, 1, (unsigned)((n + (v0 ? kHuffTileBytes : kPackTileBytes) - 1) / (v0 ? kHuffTileBytes : kPackTileBytes))));
-    const unsigned long long hb = hdr.pos;
+    hb = hdr.pos;
     IE_CUDA(cudaMemcpyAsync(s->d_counter, &hb, sizeof hb, cudaMemcpyHostToDevice, st));
     if (v0) {
         const unsigned ntiles = (unsigned)((n + kHuffTileBytes - 1) / kHuffTileBytes);
@@ -797,7 +811,6 @@ static int huffman_pack_dev(ie_session *s, const uint8_t *d_in, size_t n, const 
         count_launch(3);
     }
     IE_CUDA(cudaGetLastError());
-    IE_CUDA(cudaStreamSynchronize(st));            // `codes` / `hdr` are host objects of this frame
     return IE_OK;
 }
 
