@@ -549,8 +549,62 @@ int ie_encode_images(const uint8_t *raws, uint32_t count, uint32_t W, uint32_t H
     IE_TRY(check_quant(quant, (int)N));
     const size_t npx = (size_t)W * H;
     const size_t slot = ie_max_encoded_bytes(W, H, N, 1);
-    // sub-batches keep the staging footprint bounded (<= ~8 GiB of raw pixels in flight)
-    const uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(count, ((size_t)8 << 30) / (npx + slot)));
+    if (!huffman) {
+        // Three-stage pipeline over chunks of ~128 MiB of pixels (double-buffered staging): chunk c+1 is copied in on stream_in
+        // while chunk c is encoded on the session's stream (one launch of each kernel for the whole chunk) and the streams of
+        // chunk c-1 leave on stream_out -- PCIe busy in both directions, the kernels hidden behind it.  The only host waits
+        // are for a chunk's bit counts (the copies out are as long as the streams, not as long as their worst case).
+        const uint32_t nc = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(count, 32), ((size_t)128 << 20) / npx));
+        SessionLease lease;
+        IE_TRY(lease.acquire(0, W, H, N, nc));
+        ie_session *s = lease.get();
+        IE_TRY(session_ensure_pipeline(s));
+        IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, 2 * npx * nc));
+        IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, 2 * slot * nc));
+        IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, 2 * 32 * sizeof(unsigned long long)));
+        cudaStream_t st = s->stream;
+        unsigned long long *d_bits = reinterpret_cast<unsigned long long *>(s->d_tmp);
+        cudaEvent_t *ev_in = s->ev_in, *ev_done = s->ev_done, *ev_out = s->ev_in + 2;       // [2] each: staged, encoded, copied out
+        const uint32_t nchunks = (count + nc - 1) / nc;
+        int rc = IE_OK;
+        for (uint32_t c = 0; c <= nchunks && rc == IE_OK; c++) {
+            const int b = (int)(c & 1);
+            if (c < nchunks) {
+                const uint32_t first = c * nc, n = std::min(nc, count - first);
+                if (c >= 2) IE_CUDA(cudaStreamWaitEvent(s->stream_in, ev_done[b], 0));        // chunk c-2 no longer reads this d_in half
+                IE_CUDA(cudaMemcpyAsync(s->d_in + (size_t)b * npx * nc, raws + (size_t)first * npx, npx * n, cudaMemcpyHostToDevice, s->stream_in));
+                IE_CUDA(cudaEventRecord(ev_in[b], s->stream_in));
+                IE_CUDA(cudaStreamWaitEvent(st, ev_in[b], 0));
+                if (c >= 2) IE_CUDA(cudaStreamWaitEvent(st, ev_out[b], 0));                   // chunk c-2's streams have left this d_out half
+                rc = encode_images_dev(s, s->d_in + (size_t)b * npx * nc, npx, n, W, H, (int)N, quant, use_rle, 1, 1, 0, 0,
+                                       s->d_out + (size_t)b * slot * nc, slot, slot, st, 0, 0, 0, reinterpret_cast<uint64_t *>(d_bits + b * 32));
+                if (rc != IE_OK) break;
+                IE_CUDA(cudaMemcpyAsync(s->h_pinned + b * 32, d_bits + b * 32, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                IE_CUDA(cudaEventRecord(ev_done[b], st));
+            }
+            if (c >= 1) {
+                const int pb = b ^ 1;
+                const uint32_t first = (c - 1) * nc, n = std::min(nc, count - first);
+                IE_CUDA(cudaEventSynchronize(ev_done[pb]));
+                IE_CUDA(cudaStreamWaitEvent(s->stream_out, ev_done[pb], 0));
+                for (uint32_t i = 0; i < n; i++) {
+                    const size_t bytes = (size_t)((s->h_pinned[pb * 32 + i] + 7) / 8);
+                    out_bytes[first + i] = bytes;
+                    if (bytes > out_stride) { set_error("output slot too small"); rc = IE_ENOSPC; break; }
+                    IE_CUDA(cudaMemcpyAsync(out + (size_t)(first + i) * out_stride, s->d_out + (size_t)pb * slot * nc + (size_t)i * slot, bytes,
+                                            cudaMemcpyDeviceToHost, s->stream_out));
+                }
+                IE_CUDA(cudaEventRecord(ev_out[pb], s->stream_out));
+            }
+        }
+        IE_CUDA(cudaStreamSynchronize(s->stream_in));
+        IE_CUDA(cudaStreamSynchronize(st));
+        IE_CUDA(cudaStreamSynchronize(s->stream_out));
+        if (rc != IE_OK) return rc;
+        return read_err_flag(s, st);
+    }
+    // Huffman-coded batch: the Huffman stage synchronises per image (host-built dictionary), one image after the other
+    const uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(count, ((size_t)2 << 30) / (npx + slot)));
     SessionLease lease;
     IE_TRY(lease.acquire(0, W, H, N, sub));
     ie_session *s = lease.get();
@@ -561,25 +615,19 @@ int ie_encode_images(const uint8_t *raws, uint32_t count, uint32_t W, uint32_t H
     for (uint32_t first = 0; first < count; first += sub) {
         const uint32_t n = std::min(sub, count - first);
         IE_CUDA(cudaMemcpyAsync(s->d_in, raws + (size_t)first * npx, npx * n, cudaMemcpyHostToDevice, st));
-        IE_TRY(encode_images_dev(s, s->d_in, npx, n, W, H, (int)N, quant, use_rle, huffman ? 0 : 1, 1, 0, 0, s->d_out, slot, slot, st));
+        IE_TRY(encode_images_dev(s, s->d_in, npx, n, W, H, (int)N, quant, use_rle, 0, 1, 0, 0, s->d_out, slot, slot, st));
         IE_CUDA(cudaMemcpyAsync(bits.data(), s->d_counter, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         IE_TRY(read_err_flag(s, st));
         for (uint32_t i = 0; i < n; i++) {
             size_t bytes = (size_t)((bits[i] + 7) / 8);
-            const uint8_t *d_result = s->d_out + (size_t)i * slot;
-            if (huffman) {
-                IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, slot + 4096));
-                size_t hb = 0;
-                IE_TRY(ie_huffman_encode_dev(s, d_result, bytes, s->d_tmp, s->d_tmp_cap, &hb, st));
-                bytes = hb;
-                d_result = s->d_tmp;
-            }
-            out_bytes[first + i] = bytes;
-            if (bytes > out_stride) { set_error("output slot too small"); return IE_ENOSPC; }
-            IE_CUDA(cudaMemcpyAsync(out + (size_t)(first + i) * out_stride, d_result, bytes, cudaMemcpyDeviceToHost, st));
-            if (huffman) IE_CUDA(cudaStreamSynchronize(st));     // d_tmp is reused by the next image
+            IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, slot + 4096));
+            size_t hb = 0;
+            IE_TRY(ie_huffman_encode_dev(s, s->d_out + (size_t)i * slot, bytes, s->d_tmp, s->d_tmp_cap, &hb, st));
+            out_bytes[first + i] = hb;
+            if (hb > out_stride) { set_error("output slot too small"); return IE_ENOSPC; }
+            IE_CUDA(cudaMemcpyAsync(out + (size_t)(first + i) * out_stride, s->d_tmp, hb, cudaMemcpyDeviceToHost, st));
+            IE_CUDA(cudaStreamSynchronize(st));     // d_tmp is reused by the next image
         }
-        IE_CUDA(cudaStreamSynchronize(st));
     }
     return IE_OK;
 }
@@ -605,29 +653,78 @@ int ie_decode_images(const uint8_t *encs, size_t enc_stride, const size_t *enc_b
         }
         return IE_OK;
     }
+    // Headers are parsed from the host copy of the streams (no read-back).  Three-stage pipeline over chunks of streams,
+    // double-buffered: chunk c+1 goes in on stream_in while chunk c is decoded (streams of a chunk spread over the worker
+    // sessions' streams, so the latency-bound parse kernels of one overlap the block decode of another) and the pixels of chunk
+    // c-1 leave on stream_out.
+    std::vector<ParsedHeader> hdrs(count);
+    size_t maxpx = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        parse_header(encs + (size_t)i * enc_stride, enc_bytes[i], 1, (int)N, hdrs[i], 0);
+        IE_TRY(check_dims(hdrs[i].W, hdrs[i].H, N));
+        const size_t px = (size_t)hdrs[i].W * hdrs[i].H;
+        if (px > raw_stride) { set_error("raw_stride smaller than a decoded image"); return IE_ENOSPC; }
+        maxpx = std::max(maxpx, px);
+    }
+    if (W) *W = hdrs[count - 1].W;
+    if (H) *H = hdrs[count - 1].H;
     SessionLease lease;
     IE_TRY(lease.acquire(1, 0, 0, N, 2));
     ie_session *s = lease.get();
+    IE_TRY(session_ensure_pipeline(s));
     cudaStream_t st = s->stream;
     const size_t es = (maxb + 16 + 15) / 16 * 16;                                   // device stride of a stream
-    const uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(count, ((size_t)4 << 30) / (es + raw_stride)));
-    IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, es * sub));
-    IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, raw_stride * sub));
-    std::vector<uint32_t> ws(sub), hs(sub);
-    for (uint32_t first = 0; first < count; first += sub) {
-        const uint32_t n = std::min(sub, count - first);
-        IE_CUDA(cudaMemcpy2DAsync(s->d_in, es, encs + (size_t)first * enc_stride, enc_stride, std::min(es, enc_stride), n, cudaMemcpyHostToDevice, st));
-        IE_TRY(ie_decode_images_dev(s, s->d_in, es, enc_bytes + first, n, 1, s->d_out, raw_stride, ws.data(), hs.data(), st));
-        for (uint32_t i = 0; i < n; i++) {
-            const size_t px = (size_t)ws[i] * hs[i];
-            IE_CUDA(cudaMemcpyAsync(raws_out + (size_t)(first + i) * raw_stride, s->d_out + (size_t)i * raw_stride, px, cudaMemcpyDeviceToHost, st));
-        }
-        IE_CUDA(cudaStreamSynchronize(st));
-        for (int k = 0; k < ie_session::kDecodeWorkers; k++)
-            if (s->workers[k]) IE_TRY(read_err_flag(s->workers[k], s->workers[k]->stream));
-        if (W) *W = ws[n - 1];
-        if (H) *H = hs[n - 1];
+    const size_t rs = (maxpx + 15) / 16 * 16;
+    const uint32_t nc = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(count, 32), ((size_t)128 << 20) / rs));
+    IE_TRY(session_reserve(&s->d_in, &s->d_in_cap, 2 * es * nc));
+    IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, 2 * rs * nc));
+    const int nw = (int)std::min<uint32_t>(nc, ie_session::kDecodeWorkers);
+    for (int k = 0; k < nw; k++) {
+        if (!s->workers[k]) IE_TRY(ie_session_create(&s->workers[k], 1, 0, 0, N, 1));
+        if (!s->ev_join[k]) IE_CUDA(cudaEventCreateWithFlags(&s->ev_join[k], cudaEventDisableTiming));
     }
+    cudaEvent_t *ev_in = s->ev_in, *ev_done = s->ev_done, *ev_out = s->ev_in + 2;
+    const uint32_t nchunks = (count + nc - 1) / nc;
+    int rc = IE_OK;
+    for (uint32_t c = 0; c <= nchunks && rc == IE_OK; c++) {
+        const int b = (int)(c & 1);
+        if (c < nchunks) {
+            const uint32_t first = c * nc, n = std::min(nc, count - first);
+            uint8_t *d_in = s->d_in + (size_t)b * es * nc, *d_out = s->d_out + (size_t)b * rs * nc;
+            if (c >= 2) IE_CUDA(cudaStreamWaitEvent(s->stream_in, ev_done[b], 0));
+            IE_CUDA(cudaMemcpy2DAsync(d_in, es, encs + (size_t)first * enc_stride, enc_stride, std::min(es, enc_stride), n, cudaMemcpyHostToDevice,
+                                      s->stream_in));
+            IE_CUDA(cudaEventRecord(ev_in[b], s->stream_in));
+            for (int k = 0; k < nw; k++) {
+                IE_CUDA(cudaStreamWaitEvent(s->workers[k]->stream, ev_in[b], 0));
+                if (c >= 2) IE_CUDA(cudaStreamWaitEvent(s->workers[k]->stream, ev_out[b], 0));
+            }
+            for (uint32_t i = 0; i < n && rc == IE_OK; i++) {
+                ie_session *w = s->workers[i % nw];
+                rc = decode_image_dev(w, d_in + (size_t)i * es, enc_bytes[first + i], 1, (int)N, hdrs[first + i], d_out + (size_t)i * rs, rs, w->stream);
+            }
+            for (int k = 0; k < nw; k++) {                       // join on the session's stream
+                IE_CUDA(cudaEventRecord(s->ev_join[k], s->workers[k]->stream));
+                IE_CUDA(cudaStreamWaitEvent(st, s->ev_join[k], 0));
+            }
+            IE_CUDA(cudaEventRecord(ev_done[b], st));
+        }
+        if (c >= 1 && rc == IE_OK) {
+            const int pb = b ^ 1;
+            const uint32_t first = (c - 1) * nc, n = std::min(nc, count - first);
+            IE_CUDA(cudaStreamWaitEvent(s->stream_out, ev_done[pb], 0));
+            for (uint32_t i = 0; i < n; i++)
+                IE_CUDA(cudaMemcpyAsync(raws_out + (size_t)(first + i) * raw_stride, s->d_out + (size_t)pb * rs * nc + (size_t)i * rs,
+                                        (size_t)hdrs[first + i].W * hdrs[first + i].H, cudaMemcpyDeviceToHost, s->stream_out));
+            IE_CUDA(cudaEventRecord(ev_out[pb], s->stream_out));
+        }
+    }
+    IE_CUDA(cudaStreamSynchronize(s->stream_in));
+    for (int k = 0; k < nw; k++) IE_CUDA(cudaStreamSynchronize(s->workers[k]->stream));
+    IE_CUDA(cudaStreamSynchronize(st));
+    IE_CUDA(cudaStreamSynchronize(s->stream_out));
+    if (rc != IE_OK) return rc;
+    for (int k = 0; k < nw; k++) IE_TRY(read_err_flag(s->workers[k], s->workers[k]->stream));
     return IE_OK;
 }
 

@@ -174,6 +174,17 @@ class Comm:
                                               int(bool(lead_bit)), device._dp(d_out), d_out.numel(), device._dp(d_bits), device._dp(d_first),
                                               device._stream()))
 
+    def exchange(self, d_total):
+        """all-gather of one int64 per rank through the mailboxes (ie_comm_exchange_totals_dev); returns a device tensor [world].
+        Asynchronous on the current stream."""
+        import torch
+
+        from . import device
+        from ._lib import check, lib
+        out = torch.empty(self.world, dtype=torch.int64, device="cuda")
+        check(lib().ie_comm_exchange_totals_dev(self.h, device._dp(d_total), device._dp(out), device._stream()))
+        return out
+
     def totals(self):
         """the bit totals of the last exchange: torch int64 tensor [world] on the device (a copy, stream-ordered)"""
         import torch
@@ -293,8 +304,16 @@ class ShardedHuffmanStage:
         p = pl[rank]
         self.b0, self.b1 = shard_byte_range(pl, rank)
         self.n = self.b1 - self.b0
-        if rank + 1 < len(pl) and pl[rank + 1].global_bit % 8 and self.n:
-            self.enc.d_aligned[self.b1 - 1 - p.byte_offset] |= heads[rank + 1]
+        if self.n:
+            # the last byte of this rank may be shared with the ranks behind it -- with several of them when their shards are
+            # shorter than a byte (a one-block-wide image of all-zero blocks: 4 bits per block row): OR in the bits of every rank
+            # that starts inside that byte
+            last = self.b1 - 1
+            r = rank + 1
+            while r < len(pl) and pl[r].global_bit // 8 == last and pl[r].global_bit % 8:
+                if pl[r].nbits:
+                    self.enc.d_aligned[last - p.byte_offset] |= heads[r]
+                r += 1
         if self.n == 0:
             import numpy as np
             return np.zeros(256, np.uint32), np.full(256, ABSENT, np.uint64)

@@ -100,11 +100,16 @@ def test_sharded_huffman_stage_matches_single_stream(gpu, oracle_mod):
     from imageencoder_b200.parallel import (ShardedHuffmanStage, ShardedImageEncoder, merge_shard_into, place_shards, reduce_histograms,
                                             shard_block_rows, total_bytes)
     from imageencoder_b200.synth import synth_image
-    W, H = 512, 384
-    for matrix, world, seed, flat in (("matrix8_2.txt", 3, 81, True), ("matrix.txt", 4, 82, False), ("matrix8_1.txt", 2, 83, True)):
+    cases = [(m, w, synth_image(512, 384, seed, flat=flat)) for m, w, seed, flat in
+             (("matrix8_2.txt", 3, 81, True), ("matrix.txt", 4, 82, False), ("matrix8_1.txt", 2, 83, True))]
+    # shards shorter than a byte: a one-block-wide image of all-zero blocks is 4 bits per block row, so one byte of the plain
+    # stream holds bits of three ranks
+    cases.append(("matrix8_1.txt", 4, np.full((32, 8), 128, np.uint8)))
+    cases.append(("matrix.txt", 3, np.full((12, 4), 128, np.uint8)))
+    for matrix, world, img in cases:
         q = oracle_mod.read_matrix(INPUTS / matrix)
         N = q.shape[0]
-        img = synth_image(W, H, seed, flat=flat)
+        H, W = img.shape
         want = oracle_mod.image_encode(img, W, H, N, q, True, True)
         encs, d_totals = [], []
         for r in range(world):
