@@ -17,6 +17,7 @@ extern std::atomic<int> g_copyout_variant;
 extern std::atomic<int> g_fused_debug;
 extern std::atomic<int> g_parse_variant;       // parse.cu
 extern std::atomic<int> g_huffman_variant;     // huffman.cu
+extern std::atomic<int> g_parse_grid4;         // parse.cu
 extern std::atomic<int> g_decode_variant;      // decode_image.cu
 extern std::atomic<int> g_me_variant;          // api_video.cu
 static thread_local std::string t_error;
@@ -228,6 +229,11 @@ int ie_set_option(const char *name, int value) {
         return IE_OK;
     }
     if (name && !strcmp(name, "fused_debug")) { ie::g_fused_debug.store(value); return IE_OK; }      // timing experiments, wrong output
+    if (name && !strcmp(name, "parse_grid4")) {
+        if (value < -1 || value > 2) { ie::set_error("parse_grid4: -1 (default: images 0, video frames 1), 0 (2048-bit groups, 4096-bit lead-in), 1 (1024 / 2048) or 2 (512 / 1024)"); return IE_EINVAL; }
+        ie::g_parse_grid4.store(value);
+        return IE_OK;
+    }
     if (name && !strcmp(name, "huffman_variant")) {
         if (value < 0 || value > 1) { ie::set_error("huffman_variant: 1 (span histogram + bits / scan / pack kernels, default) or 0 (the round-1 kernels)"); return IE_EINVAL; }
         ie::g_huffman_variant.store(value);

@@ -26,6 +26,8 @@ namespace ie {
 
 // 1 = the speculative parse's verdict is ignored and the exact transfer-function path produces the offsets (tests)
 std::atomic<int> g_parse_variant{0};
+// speculative grid of 4x4 streams: 0 = 2048-bit groups with a 4096-bit lead-in, 1 = 1024-bit groups with a 2048-bit lead-in
+std::atomic<int> g_parse_grid4{-1};             // -1 = by kind of stream (g4_bits)
 
 // Sub-span boundaries inside a group: short spans first, so that the E hypothetical chains of a group are merged after
 // a block or two instead of each being walked through kilobits of stream.
@@ -238,7 +240,7 @@ __device__ __forceinline__ uint2 walk_group(const ParseParams &p, unsigned long 
 // 64 per CTA, lead-in 8192 (4096 leaves 3 % of the groups unsynchronised).  4x4 streams (blocks <= 276 bits, ~50 typical):
 // 2048-bit groups, 256 per CTA, lead-in 4096 -- a thread's serial chain is what the kernels' time is made of.
 template <int GB, int TH> struct SpecCfg {
-    static constexpr unsigned kLead = (GB == 8192) ? 8192u : 4096u;
+    static constexpr unsigned kLead = (GB == 8192) ? 8192u : (GB == 2048 ? 4096u : (GB == 1024 ? 2048u : 1024u));
     static constexpr unsigned kStageWords = (TH * GB + kLead) / 32 + 16;             // groups + lead-in + window/alignment slack
 };
 
@@ -513,12 +515,14 @@ static void parse_sizes(size_t span_bits, int N, unsigned &E, unsigned &ngroups,
     nsuper = (ngroups + kSuper - 1) / kSuper;
 }
 
-static unsigned spec_groups(size_t span_bits, int N) { const size_t gb = (N == 8) ? 8192 : 2048; return (unsigned)((span_bits + gb - 1) / gb + 1); }
+// 4x4 streams: images walk 2048-bit groups; video frames (cursor mode: one short parse per frame, pure latency) finer ones
+static int g4_bits(bool video) { const int v = g_parse_grid4.load(); return v == 2 ? 512 : v == 1 ? 1024 : v == 0 ? 2048 : (video ? 1024 : 2048); }
+static unsigned spec_groups(size_t span_bits, int N, bool video = true) { const size_t gb = (N == 8) ? 8192 : (size_t)g4_bits(video); return (unsigned)((span_bits + gb - 1) / gb + 1); }
 
 size_t parse_scratch_bytes(size_t enc_bytes, int N) {
     unsigned E, ng, ns;
     parse_sizes(enc_bytes * 8, N, E, ng, ns);
-    const size_t nspec = spec_groups(enc_bytes * 8, N);
+    const size_t nspec = (N == 8) ? spec_groups(enc_bytes * 8, N) : (enc_bytes * 8 + 511) / 512 + 1;      // the finest grid any setting uses
     return ((size_t)ng * E + (size_t)ns * E + ns + ng + 8) * sizeof(uint2) + nspec * 2 * sizeof(uint2) + (nspec / 64 + 16) * sizeof(unsigned) + 256;
 }
 
@@ -554,7 +558,7 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     p.super_table = s; s += (size_t)p.nsuper * E;
     p.super_entry = s; s += p.nsuper;
     p.group_entry = s; s += p.ngroups;
-    p.nspec = spec_groups(span_bits, d.N);
+    p.nspec = spec_groups(span_bits, d.N, d.cursor != nullptr);
     p.spec_entry = s; s += p.nspec;
     p.spec_exit = s; s += p.nspec;
     p.spec_flags = reinterpret_cast<unsigned *>(s);
@@ -570,6 +574,8 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     IE_DBG_STEP("before parse");
     if ((uintptr_t)d.enc % 16) { set_error("encoded stream must be 16-byte aligned on the device"); return IE_EINVAL; }
     if (d.N == 8) IE_TRY((launch_spec<8192, 64>(p, stream)));
+    else if (g4_bits(d.cursor != nullptr) == 512) IE_TRY((launch_spec<512, 256>(p, stream)));
+    else if (g4_bits(d.cursor != nullptr) == 1024) IE_TRY((launch_spec<1024, 256>(p, stream)));
     else IE_TRY((launch_spec<2048, 256>(p, stream)));
     IE_DBG_STEP("parse_spec");
     {
