@@ -219,10 +219,11 @@ uint64_t ie_kernel_launch_count(void) { return ie::g_launches.load(); }
 int ie_set_option(const char *name, int value) {
     if (name && !strcmp(name, "exact_transform")) { ie::g_exact_transform.store(value); return IE_OK; }
     if (name && !strcmp(name, "encode_variant")) {
-        if (value < 0 || value > 8) {
+        if (value < 0 || value > 9) {
             ie::set_error("encode_variant: 0 (scalar kernel), 1 (lean quantise), 2 (1 + packed f32x2 transform, the default), "
                           "3 / 4 (2 with a reduced staging area and 7 / 8 CTAs per SM), 5 (2 with the short-chain binary64 pre-check of "
-                          "the exact queue), 6 / 7 (3 / 4 with it), 8 (fused persistent stream kernel, encode_fused.cu; other launch shapes fall back to 2)");
+                          "the exact queue), 6 / 7 (3 / 4 with it), 8 (fused persistent stream kernel, encode_fused.cu; other launch shapes fall back to 2), 9 (2 with the guard-band "
+                          "coefficients evaluated by their owning lanes, no exact queue)");
             return IE_EINVAL;
         }
         ie::g_encode_variant.store(value);

@@ -103,6 +103,9 @@ constexpr int kQueueCap = 128;        // guard-band fallback entries per tile ha
 constexpr int kSmallOutChunks = 512;
 constexpr bool var_small_out(int VAR) { return VAR == 3 || VAR == 4 || VAR == 6 || VAR == 7; }
 constexpr bool var_fast64(int VAR) { return VAR >= 5; }
+// 9 = 2 with the guard-band coefficients evaluated by the lanes that own them, all lanes of a warp that have one at the same
+// time (short binary64 chain, then the exact chain for the ties): no CTA-wide queue, no barrier behind it
+constexpr bool var_inwarp(int VAR) { return VAR == 9; }
 constexpr int encode_min_ctas(int N, bool PF, bool FAST, int VAR) {
     return (N == 8 && !FAST) ? 1 : (FAST && !PF ? ((VAR == 3 || VAR == 6) ? 7 : (VAR == 4 || VAR == 7) ? 8 : 6) : 2);
 }
@@ -116,6 +119,7 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
     constexpr int MAXCHUNKS = (TB * (4 + 16 + 16 * NN) + 127) / 128 + 2;
     constexpr bool SMALL_OUT = var_small_out(VAR);
     constexpr bool FAST64 = var_fast64(VAR);
+    constexpr bool INWARP = var_inwarp(VAR) && FAST && !PF;
     constexpr int OUTCHUNKS = SMALL_OUT ? kSmallOutChunks : MAXCHUNKS;     // staging area for the tile image, in 128-bit chunks
     extern __shared__ __align__(16) unsigned char smem[];
     short *s_coef = reinterpret_cast<short *>(smem);
@@ -160,9 +164,11 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
     // ---- phase 1: transform + quantise, lane per block ---------------------------------------------------
     unsigned r_orbits[BPL];
     unsigned r_orseg[BPL][NSEG];
+    unsigned long long r_near[INWARP ? BPL : 1];
 #pragma unroll
     for (int r = 0; r < BPL; r++) {
         const int lb = threadIdx.x * BPL + r;
+        if (INWARP) r_near[r] = 0;
         r_orbits[r] = 0;
 #pragma unroll
         for (int s = 0; s < NSEG; s++) r_orseg[r][s] = 0;
@@ -265,7 +271,9 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
                 r_orbits[r] |= (unsigned)(q ^ (q >> 31));                   // bits_needed of the widest value (-1 -> 0)
             }
             }
-            if (near) {
+            if (INWARP) {
+                r_near[INWARP ? r : 0] = near;
+            } else if (near) {
                 // hand the guard-band coefficients to the CTA-wide queue (filled lanes instead of one lane per warp)
                 const int n = __popcll(near);
                 unsigned slot = atomicAdd(&s_qn, (unsigned)n);
@@ -293,10 +301,57 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
             }
         }
     }
-    __syncthreads();
+    if (INWARP) {
+        // ---- phase 1b (variant 9): the owning lanes evaluate their guard-band coefficients, one per lane at a time, and fold
+        // the result into the RLE info they hold in registers; nothing is shared with another lane, so no barrier follows
+#pragma unroll
+        for (int r = 0; r < BPL; r++) {
+            while (__ballot_sync(0xffffffffu, r_near[INWARP ? r : 0] != 0)) {            // warp-uniform
+                unsigned long long &nr = r_near[INWARP ? r : 0];
+                const bool have = nr != 0;
+                const int uv = have ? (__ffsll((long long)nr) - 1) : 0;
+                nr &= nr - 1;
+                const int lb = threadIdx.x * BPL + r;
+                const unsigned gb = first_blk + lb;
+                const double m_uv = p.quant.m[uv];
+                int q = 0;
+                bool undecided = false;
+                if (have) undecided = !fast64_coefficient<N, PF>(ex, gb, uv, m_uv, q);
+                if (__ballot_sync(0xffffffffu, undecided)) {
+                    if (undecided) q = exact_coefficient<N, PF>(ex, gb, uv, m_uv);
+                }
+                if (have) {
+                    short *cf = s_coef + (size_t)lb * STRIDE;
+                    const int k = tab->izz[uv];
+                    const int q_old = cf[k];
+                    q = (int)(short)q;
+                    if (q_old != q) {
+                        cf[k] = (short)q;
+                        const unsigned bo = (unsigned)(q_old ^ (q_old >> 31)), bn = (unsigned)(q ^ (q >> 31));
+                        if (s_dirty[lb] || (__clz(bn) > __clz(bo) && __clz(bo) == __clz(r_orbits[r]))) {
+                            // the patched coefficient alone carried the widest value: rescan the block
+                            int lastnz, prevnz;
+                            unsigned ob;
+                            block_stats_from_staging<NN>(cf, lastnz, prevnz, ob);
+                            s_stats[lb] = (unsigned)lastnz | ((unsigned)prevnz << 8) | (ob << 16);
+                            s_dirty[lb] = 1;
+                        } else {
+                            r_orbits[r] |= bn;
+                            const unsigned *cw = reinterpret_cast<const unsigned *>(cf) + (k >> 3) * 4;
+                            const unsigned any = cw[0] | cw[1] | cw[2] | cw[3];
+#pragma unroll
+                            for (int s2 = 0; s2 < NSEG; s2++) if (s2 == (k >> 3)) r_orseg[r][s2] = any;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        __syncthreads();
+    }
 
     // ---- phase 1b: exact recomputation of the queued guard-band coefficients, one per thread -------------------
-    if (FAST) {
+    if (FAST && !INWARP) {
         const unsigned qn = min(s_qn, (unsigned)kQueueCap);
         if (qn) {                                                              // uniform
             for (unsigned e = threadIdx.x; e < qn; e += kThreads) {
@@ -931,6 +986,7 @@ int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStrea
         if (N == 8) return launch_cfg<8, 1, false, true, 4>(p, images, stream);
         if (N == 4) return launch_cfg<4, 4, false, true, 4>(p, images, stream);
     }
+    if (var == 9) { if (N == 8) return launch_cfg<8, 1, false, true, 9>(p, images, stream); if (N == 4) return launch_cfg<4, 4, false, true, 9>(p, images, stream); }
     if (var == 5) { if (N == 8) return launch_cfg<8, 1, false, true, 5>(p, images, stream); if (N == 4) return launch_cfg<4, 4, false, true, 5>(p, images, stream); }
     if (var == 6) { if (N == 8) return launch_cfg<8, 1, false, true, 6>(p, images, stream); if (N == 4) return launch_cfg<4, 4, false, true, 6>(p, images, stream); }
     if (var == 7) { if (N == 8) return launch_cfg<8, 1, false, true, 7>(p, images, stream); if (N == 4) return launch_cfg<4, 4, false, true, 7>(p, images, stream); }

@@ -37,7 +37,8 @@ def test_encode_variant_option_is_validated():
         assert L.ie_set_option(b"encode_variant", 4) == 0
         assert L.ie_set_option(b"encode_variant", 7) == 0
         assert L.ie_set_option(b"encode_variant", 8) == 0          # fused stream kernel (encode_fused.cu)
-        assert L.ie_set_option(b"encode_variant", 9) != 0
+        assert L.ie_set_option(b"encode_variant", 9) == 0          # in-warp exact evaluation
+        assert L.ie_set_option(b"encode_variant", 10) != 0
         assert L.ie_set_option(b"encode_variant", -1) != 0
     finally:
         assert L.ie_set_option(b"encode_variant", 2) == 0          # the default

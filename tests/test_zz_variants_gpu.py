@@ -24,7 +24,7 @@ def test_variant_streams_identical(variant):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("variant", [3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("variant", [3, 4, 5, 6, 7, 8, 9])
 def test_experimental_variant_streams_identical(variant):
     """the noise / quantiser-1 cases of the worker overflow the reduced staging area and take the global-memory pack; the
     checker / two-level cases are tie-heavy (exact queue); 8 = the fused persistent stream kernel (encode_fused.cu)"""
