@@ -68,6 +68,63 @@ __global__ void __launch_bounds__(32) shard_exchange_kernel(const CommDev c, con
     totals[r] = v & 0xffffffffffffull;
 }
 
+// The three one-CTA steps between the tile kernel and the copy-out of a shard, in ONE launch (they were tile_totals_kernel,
+// shard_exchange_kernel and stream_init_shard_kernel: two launch gaps of a 70 us step at 8 GPUs): this shard's bit total from its
+// tile totals (+ the header on rank 0) -> every peer's mailbox; the peers' totals <- this rank's mailbox; the shard's first bit;
+// the stream prefix (first % 128 zero bits, then the header on rank 0) and the bit counters the copy-out kernel starts from.
+__global__ void __launch_bounds__(256) shard_totals_exchange_init_kernel(const CommDev c, const unsigned *__restrict__ tile_bits, unsigned ntiles,
+                                                                        unsigned long long add, unsigned long long *totals, uint8_t *out,
+                                                                        HeaderParam hdr, unsigned long long *counter, unsigned long long *bit_base,
+                                                                        unsigned long long *first_out, int *err) {
+    pdl_wait();
+    __shared__ unsigned long long s_part[8];
+    __shared__ unsigned long long s_tot[kMaxRanks];
+    unsigned long long sum = 0;
+    for (unsigned i = threadIdx.x; i < ntiles; i += 256) sum += tile_bits[i];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < (unsigned)c.world) {
+        unsigned long long mine = add;
+        for (int w = 0; w < 8; w++) mine += s_part[w];
+        const int r = threadIdx.x;
+        const unsigned long long tag = (unsigned long long)(c.epoch & 0xffffu) << 48;
+        const unsigned slot = (c.epoch & 1u) * kMaxRanks;
+        st_sys_u64(c.peer_box[r] + slot + c.rank, tag | (mine & 0xffffffffffffull));
+        const long long t0 = clock64();
+        unsigned long long v;
+        while (((v = ld_sys_u64(c.box + slot + r)) >> 48) != (c.epoch & 0xffffu)) {
+            if (clock64() - t0 > kSpinLimit) { if (err) atomicExch(err, IE_ECUDA); v = 0; break; }
+            __nanosleep(100);
+        }
+        v &= 0xffffffffffffull;
+        totals[r] = v;
+        s_tot[r] = v;
+    }
+    __syncthreads();
+    unsigned long long first = 0;
+    for (int i = 0; i < c.rank; i++) first += s_tot[i];
+    const unsigned first_bit = (unsigned)(first % 128);
+    const unsigned total = first_bit + hdr.bits;
+    const unsigned nwords = ((total + 127) / 128) * 4;
+    unsigned *o = reinterpret_cast<unsigned *>(out);
+    for (unsigned i = threadIdx.x; i < max(nwords, 4u); i += 256) {
+        const long long hb = (long long)i * 32 - (long long)first_bit;
+        const int sh = (int)(((hb % 32) + 32) % 32);
+        const long long wi = (hb - sh) / 32;               // floor division
+        const unsigned hi = (wi >= 0 && wi < kHdrWordsMax) ? hdr.words[wi] : 0u;
+        const unsigned lo = (wi + 1 >= 0 && wi + 1 < kHdrWordsMax) ? hdr.words[wi + 1] : 0u;
+        const unsigned v = sh ? ((hi << sh) | (lo >> (32 - sh))) : hi;
+        o[i] = __byte_perm(v, 0, 0x0123);
+    }
+    if (threadIdx.x == 0) {
+        counter[0] = total;
+        bit_base[0] = total;
+        if (first_out) *first_out = first;
+    }
+}
+
 // This rank's chunks of the global stream -> the root's buffer.  d_shard: the rank's bytes from the chunk that holds its first
 // bit (what ie_encode_image_end_dev leaves); *d_bits = (first % 128) + shard bits; *d_first = first bit in the global stream.
 __global__ void __launch_bounds__(256) stitch_kernel(const CommDev c, const uint4 *__restrict__ d_shard, const unsigned long long *d_bits,
@@ -236,16 +293,26 @@ int ie_encode_image_shard_dev(ie_session *s, ie_comm *c, const uint8_t *d_raw, u
                               uint64_t *d_out_bits, uint64_t *d_first_bit, void *stream) {
     if (!s || !c || !d_raw || !d_out) { set_error("NULL argument"); return IE_EINVAL; }
     if (H_shard == 0) { set_error("every rank needs at least one block row"); return IE_EINVAL; }
+    if (!c->connected) { set_error("ie_comm_connect has not run"); return IE_EINVAL; }
+    if ((uintptr_t)d_out % 16) { set_error("stream buffers must be 16-byte aligned"); return IE_EINVAL; }
     IE_TRY(ie_session_set_header_height(s, H_total));
+    cudaStream_t st = (cudaStream_t)stream;
+    // tile kernel: the shard's packed tiles stay in the session's scratch (split encode, as ie_encode_image_begin_dev)
+    IE_TRY(encode_images_dev(s, d_raw, 0, 1, W, H_shard, (int)s->N, quant, use_rle, lead_bit, c->rank == 0, 0, 0, nullptr, 0, 0, st, 0, 0, 1));
+    if (out_cap < ((size_t)128 + s->split_hdr.bits + 127) / 128 * 16) { set_error("output buffer too small for the header"); return IE_ENOSPC; }
     // Two calls may be in flight at once (a caller alternating two sessions / streams so that one shard's copy-out overlaps
     // the next tile kernel): mailbox slots and the totals arrays go by the parity of the call's epoch.
-    unsigned long long *next = c->d_totals + ((c->epoch + 1) & 1u) * (kMaxRanks + 1);
-    if (((c->epoch + 1) & 0xffffu) == 0) next = c->d_totals;                                   // epoch 0 is skipped: the call gets epoch 2
-    IE_TRY(ie_encode_image_begin_dev(s, d_raw, W, H_shard, quant, use_rle, lead_bit, c->rank == 0, reinterpret_cast<uint64_t *>(next + kMaxRanks),
-                                     stream));
-    IE_TRY(ie_comm_exchange_totals_dev(c, reinterpret_cast<const uint64_t *>(next + kMaxRanks), nullptr, stream));
-    return ie_encode_image_end_dev(s, reinterpret_cast<const uint64_t *>(c->totals_of_epoch()), (uint32_t)c->rank, d_out, out_cap, d_out_bits,
-                                   d_first_bit, stream);
+    c->epoch = (c->epoch + 1) & 0xffffu;
+    if (c->epoch == 0) c->epoch = 2;                         // 0 is the value of a fresh mailbox; keep the parity sequence
+    EncodeParams p = s->split_params;
+    s->split_pending = false;
+    p.out = d_out; p.out_stride = 0; p.out_cap = out_cap;
+    p.out_bits = reinterpret_cast<unsigned long long *>(d_out_bits);          // written by the copy-out kernel itself
+    IE_CUDA(launch_pdl(shard_totals_exchange_init_kernel, dim3(1), dim3(256), 0, st, c->dev(), (const unsigned *)p.tile_bits, p.tiles_per_image,
+                       (unsigned long long)s->split_hdr.bits, c->totals_of_epoch(), d_out, s->split_hdr, s->d_counter, p.bit_base,
+                       reinterpret_cast<unsigned long long *>(d_first_bit), s->d_err));
+    count_launch();
+    return launch_tile_copyout(p, 1, st);
 }
 
 int ie_comm_stitch_dev(ie_comm *c, const uint8_t *d_shard, const uint64_t *d_bits, const uint64_t *d_first_bit, void *stream) {
