@@ -128,6 +128,42 @@ __global__ void __launch_bounds__(256) mc_copy_kernel(const MCParams p) {
     *reinterpret_cast<uint2 *>(dp) = make_uint2(lo, hi);
 }
 
+// the same for frame `first_frame + blockIdx.y * gop` of a whole-stream decode: the frame's motion vectors end where its first
+// block starts (VFrameRec::first), the reference frame is the one before it in the output
+struct MCBatchParams {
+    const uint8_t *enc;
+    unsigned long long enc_bits;
+    const VFrameRec *rec;
+    unsigned first_frame, gop, mvbits;
+    uint8_t *out;
+    size_t fsz;
+    int W, H, mx, nmb;
+};
+__global__ void __launch_bounds__(256) mc_copy_batch_kernel(const MCBatchParams p) {
+    pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * 8 + warp;
+    if (mb >= p.nmb) return;
+    const unsigned f = p.first_frame + blockIdx.y * p.gop;
+    const uint8_t *ref = p.out + (size_t)(f - 1) * p.fsz;
+    uint8_t *cur = p.out + (size_t)f * p.fsz;
+    const int mbx = (mb % p.mx) * kMB, mby = (mb / p.mx) * kMB;
+    const unsigned long long base = p.rec[f].first - (unsigned long long)p.nmb * 2 * p.mvbits + (unsigned long long)mb * 2 * p.mvbits;
+    const int sh = 16 - (int)p.mvbits;
+    const int vx = (int)(short)(unsigned short)(read_bits_dev(p.enc, p.enc_bits, min(base, p.enc_bits), p.mvbits) << sh) >> sh;   // Block.cpp:484-485
+    const int vy = (int)(short)(unsigned short)(read_bits_dev(p.enc, p.enc_bits, min(base + p.mvbits, p.enc_bits), p.mvbits) << sh) >> sh;
+    const int cx = clampi((int)(short)(mbx + vx), 0, p.W - kMB), cy = clampi((int)(short)(mby + vy), 0, p.H - kMB);
+    const int row = lane >> 1, half = lane & 1;
+    const uint8_t *rp = ref + (size_t)(cy + row) * p.W + cx + half * 8;
+    uint8_t *dp = cur + (size_t)(mby + row) * p.W + mbx + half * 8;
+    // 8 source bytes at any alignment from three aligned words
+    const uintptr_t a = reinterpret_cast<uintptr_t>(rp);
+    const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
+    const unsigned sel = 0x3210u + 0x1111u * (unsigned)(a & 3);
+    const unsigned w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = (a & 3) ? __ldg(wp + 2) : 0u;
+    *reinterpret_cast<uint2 *>(dp) = make_uint2(__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel));
+}
+
 __global__ void fill_uv_kernel(uint8_t *yuv, size_t ysz, size_t fsz, unsigned frames) {
     const size_t uv = fsz - ysz;
     const size_t total = uv * frames;
@@ -380,6 +416,75 @@ int ie_encode_video(const uint8_t *yuv, size_t yuv_bytes, uint32_t W, uint32_t H
     return IE_OK;
 }
 
+}  // extern "C"
+
+namespace ie {
+// 1 = whole-stream parse + frame k of every GOP per launch (default), 0 = frame by frame (also the fallback for truncated and
+// damaged streams)
+std::atomic<int> g_video_decode_variant{1};
+
+// Returns IE_OK with done = false when the stream is not a plain well-formed one (the caller then decodes frame by frame).
+static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, const ParsedHeader &h, int motioncomp, uint8_t *d_out,
+                              cudaStream_t st, bool &done) {
+    done = false;
+    const uint32_t W = h.W, H = h.H, frames = h.frames, gop = h.gop;
+    const size_t ysz = (size_t)W * H, fsz = ysz + ysz / 2;
+    const unsigned nblocks = (W / 4) * (H / 4), nmb = (W / kMB) * (H / kMB);
+    const unsigned mvbits = host_bits_needed((int)(short)h.merange);
+    const uint32_t ngops = (frames + gop - 1) / gop;
+    if (frames == 0 || !s->h_pinned) return IE_OK;
+    if ((unsigned long long)enc_bytes * 8ull >= (1ull << 41)) return IE_OK;          // group indices are 32 bits
+    const VideoParseSizes z = video_parse_sizes(enc_bytes, frames, s->dev->sm_count);
+    IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, z.bytes));
+    // block offsets of one frame slot (frame k of every GOP), then the stream's size once per GOP and the first frame's bit
+    const size_t need_off = ((size_t)ngops * (nblocks + 1) + ngops + 2) * sizeof(unsigned long long) + 64;
+    if (s->block_off_cap < need_off) {
+        if (s->d_block_off) IE_CUDA(cudaFree(s->d_block_off));
+        s->d_block_off = nullptr; s->block_off_cap = 0;
+        IE_CUDA(cudaMalloc(&s->d_block_off, need_off));
+        s->block_off_cap = need_off;
+    }
+    unsigned long long *d_totals = s->d_block_off + (size_t)ngops * (nblocks + 1);
+    std::vector<unsigned long long> consts(ngops + 1, (unsigned long long)enc_bytes * 8ull);
+    consts[ngops] = (unsigned long long)h.end_bit;
+    IE_CUDA(cudaMemcpyAsync(d_totals, consts.data(), consts.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    VideoParse v;
+    ParseParamsOpaque po;
+    IE_TRY(launch_video_parse(d_enc, d_totals, d_totals + ngops, h.use_rle, nblocks, nmb * 2 * mvbits, frames, gop, z, s->d_parse, v, po, st));
+    IE_CUDA(cudaMemcpyAsync(&s->h_pinned[8], v.result, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));                       // consts is read by the copy above until here
+    if ((unsigned)(s->h_pinned[8] & 0xffffffffu) != 1u) return IE_OK;
+
+    DecodeParams p;
+    memset(&p, 0, sizeof p);
+    p.enc = d_enc; p.enc_stride = 0; p.enc_bits = d_totals; p.start_bit = d_totals; p.block_off = s->d_block_off; p.nblocks = nblocks;
+    p.bx = W / 4; p.N = 4; p.use_rle = h.use_rle; make_quant(p.quant, h.quant, 4); make_k2(p.k2, h.quant, 4); p.tab = s->dev->d_t4; p.pitch = W; p.err = s->d_err;
+    p.out_stride = (size_t)gop * fsz;
+    for (uint32_t k = 0; k < gop && k < frames; k++) {
+        const uint32_t nimg = (frames - k + gop - 1) / gop;                       // GOPs that have a frame k
+        p.out = d_out + (size_t)k * fsz;
+        if (k > 0) {
+            MCBatchParams mc;
+            mc.enc = d_enc; mc.enc_bits = consts[0]; mc.rec = v.rec; mc.first_frame = k; mc.gop = gop; mc.mvbits = mvbits; mc.out = d_out; mc.fsz = fsz;
+            mc.W = (int)W; mc.H = (int)H; mc.mx = (int)(W / kMB); mc.nmb = (int)nmb;
+            IE_CUDA(launch_pdl(mc_copy_batch_kernel, dim3((nmb + 7) / 8, nimg), dim3(256), 0, st, mc));
+            count_launch();
+            if (!motioncomp) continue;                                            // Frame.cpp:107-117
+        }
+        p.add_mode = k > 0 ? 1 : 0;
+        IE_TRY(launch_video_emit(v, po, k, nimg, s->d_block_off, st));
+        IE_TRY(launch_decode_blocks(p, nimg, st));
+    }
+    fill_uv_kernel<<<256, 256, 0, st>>>(d_out, ysz, fsz, frames);                   // Frame.cpp:122-124
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    done = true;
+    return IE_OK;
+}
+}  // namespace ie
+
+extern "C" {
+
 int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, uint64_t start_bit, int motioncomp, uint8_t *d_out,
                         size_t out_cap, uint32_t *Wo, uint32_t *Ho, uint32_t *Fo, void *stream) {
     if (!s || !d_enc || !d_out) { set_error("NULL argument"); return IE_EINVAL; }
@@ -404,6 +509,11 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
     const unsigned nblocks = (W / 4) * (H / 4), nmb = (W / kMB) * (H / kMB);
     const unsigned mvbits = host_bits_needed((int)(short)h.merange);
     IE_TRY(session_ensure_err(s));
+    if (g_video_decode_variant.load() == 1) {
+        bool done = false;
+        IE_TRY(decode_video_whole(s, d_enc, enc_bytes, h, motioncomp, d_out, st, done));
+        if (done) return IE_OK;
+    }
     VideoScratch vs;
     IE_TRY(video_scratch(s, nmb, 1, vs));
     const size_t need_off = ((size_t)nblocks + 1) * sizeof(unsigned long long) + 64;

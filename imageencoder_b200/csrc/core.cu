@@ -15,11 +15,13 @@ extern std::atomic<int> g_exact_transform;   // encode_image.cu
 extern std::atomic<int> g_encode_variant;
 extern std::atomic<int> g_copyout_variant;
 extern std::atomic<int> g_fused_debug;
+extern std::atomic<int> g_encode_pad_smem;
 extern std::atomic<int> g_parse_variant;       // parse.cu
 extern std::atomic<int> g_huffman_variant;     // huffman.cu
 extern std::atomic<int> g_parse_grid4;         // parse.cu
 extern std::atomic<int> g_decode_variant;      // decode_image.cu
 extern std::atomic<int> g_me_variant;          // api_video.cu
+extern std::atomic<int> g_video_decode_variant;
 static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
 
@@ -229,6 +231,11 @@ int ie_set_option(const char *name, int value) {
         ie::g_encode_variant.store(value);
         return IE_OK;
     }
+    if (name && !strcmp(name, "encode_pad_smem")) {     // occupancy experiments: extra dynamic shared memory per tile-kernel CTA
+        if (value < 0 || value > 150000) { ie::set_error("encode_pad_smem: 0 .. 150000 bytes"); return IE_EINVAL; }
+        ie::g_encode_pad_smem.store(value);
+        return IE_OK;
+    }
     if (name && !strcmp(name, "fused_debug")) { ie::g_fused_debug.store(value); return IE_OK; }      // timing experiments, wrong output
     if (name && !strcmp(name, "parse_grid4")) {
         if (value < -1 || value > 2) { ie::set_error("parse_grid4: -1 (default: images 0, video frames 1), 0 (2048-bit groups, 4096-bit lead-in), 1 (1024 / 2048) or 2 (512 / 1024)"); return IE_EINVAL; }
@@ -253,6 +260,11 @@ int ie_set_option(const char *name, int value) {
     if (name && !strcmp(name, "decode_variant")) {
         if (value < 0 || value > 1) { ie::set_error("decode_variant: 0 (default) or 1 (packed f32x2 inverse transform, experimental)"); return IE_EINVAL; }
         ie::g_decode_variant.store(value);
+        return IE_OK;
+    }
+    if (name && !strcmp(name, "video_decode_variant")) {
+        if (value < 0 || value > 1) { ie::set_error("video_decode_variant: 1 (whole-stream parse, frame k of every GOP per launch; default) or 0 (frame by frame)"); return IE_EINVAL; }
+        ie::g_video_decode_variant.store(value);
         return IE_OK;
     }
     if (name && !strcmp(name, "me_variant")) {

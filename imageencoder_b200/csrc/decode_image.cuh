@@ -26,6 +26,37 @@ struct DecodeParams {
     int add_mode;                           // 1: pixel = (u8)clamp(cur + (X + 128))   (Block.cpp:110-119, P-frames)
 };
 
+// ---- whole-stream video parse (parse.cu) ----
+constexpr unsigned kVMaxPieces = 8;
+struct VFramePiece {
+    unsigned kind;          // 0 HEAD: pool[a .. a + b) are the starts of blocks idx_base ..; 1 SPEC: groups a .. b (inclusive)
+    unsigned a, b;
+    unsigned idx_base;      // index (within the frame) of the piece's first block
+    unsigned pm;            // SPEC: pq[a].x
+};
+struct VFrameRec {
+    unsigned long long first;      // first bit of the frame's first block (a P-frame's motion vectors end here)
+    unsigned long long end;        // first bit after the frame's last block
+    unsigned npieces;
+    VFramePiece piece[kVMaxPieces];
+};
+struct VideoParse {
+    unsigned nblocks, mv_bits, frames, gop;
+    uint2 *pq, *partial;
+    unsigned long long *pool;
+    unsigned pool_cap;
+    VFrameRec *rec;
+    unsigned *result;              // [0] 1 = the records are valid, [1] pool entries used
+};
+struct VideoParseSizes { size_t nspec, pool_cap, bytes; unsigned scan_ctas; };
+struct ParseParamsOpaque { unsigned long long raw[32]; };
+VideoParseSizes video_parse_sizes(size_t enc_bytes, unsigned frames, int sm_count);
+int launch_video_parse(const uint8_t *d_enc, const unsigned long long *d_enc_bits, const unsigned long long *d_start, int use_rle,
+                       unsigned nblocks, unsigned mv_bits, unsigned frames, unsigned gop, const VideoParseSizes &z, uint8_t *scratch,
+                       VideoParse &v, ParseParamsOpaque &popaque, cudaStream_t stream);
+int launch_video_emit(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned first_frame, unsigned nimg, unsigned long long *block_off,
+                      cudaStream_t stream);
+
 int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream);
 int launch_decode_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream);
 size_t parse_scratch_bytes(size_t enc_bytes, int N);

@@ -936,18 +936,20 @@ int launch_tile_totals(const unsigned *tile_bits, unsigned ntiles, unsigned imag
     return IE_OK;
 }
 
+std::atomic<int> g_encode_pad_smem{0};
 template <int N, int BPL, bool PF, bool FAST, int VAR = 0>
 static int launch_cfg(const EncodeParams &p, unsigned images, cudaStream_t stream) {
     constexpr int TB = kThreads * BPL;
     constexpr int STRIDE = N * N + 2;
     constexpr int MAXCHUNKS = (TB * (4 + 16 + 16 * N * N) + 127) / 128 + 2;
     constexpr int OUTCHUNKS = var_small_out(VAR) ? kSmallOutChunks : MAXCHUNKS;
-    const size_t smem = (((size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 15) & ~(size_t)15) + (size_t)OUTCHUNKS * 16 +
-                        (kQueueCap + TB + (kQueueCap + TB) / 2) * sizeof(unsigned) + 3 * TB;
-    static bool configured = false;
-    if (!configured) {
+    size_t smem = (((size_t)TB * STRIDE * sizeof(short) + (TB + 1) * sizeof(unsigned) + 15) & ~(size_t)15) + (size_t)OUTCHUNKS * 16 +
+                  (kQueueCap + TB + (kQueueCap + TB) / 2) * sizeof(unsigned) + 3 * TB;
+    static size_t configured = 0;
+    smem += (size_t)g_encode_pad_smem.load();     // occupancy experiments only (ie_set_option("encode_pad_smem", bytes)); 0 by default
+    if (configured != smem) {
         IE_CUDA(cudaFuncSetAttribute(encode_tiles_kernel<N, BPL, PF, FAST, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured = smem;
     }
     dim3 grid(p.tiles_per_image, images);
     encode_tiles_kernel<N, BPL, PF, FAST, VAR><<<grid, kThreads, smem, stream>>>(p);

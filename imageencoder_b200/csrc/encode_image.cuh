@@ -56,6 +56,7 @@ extern std::atomic<int> g_exact_transform;
 extern std::atomic<int> g_encode_variant;
 extern std::atomic<int> g_copyout_variant;
 extern std::atomic<int> g_fused_debug;
+extern std::atomic<int> g_encode_pad_smem;
 // max_abs_sample: 128 for pixels - 128, 383 for P-frame residuals - 128
 void make_fast_quant(FastQuant &fq, const uint16_t *quant, int N, double max_abs_sample);
 int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStream_t stream);

@@ -17,6 +17,7 @@
 // do not advance (BitStream.cpp:17-20): a chain that reaches the end is DEAD and every remaining block starts at `total`.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <algorithm>
 
 #include "decode_image.cuh"
@@ -590,6 +591,349 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     if (p.cursor_out) { IE_CUDA(launch_pdl(parse_commit_cursor, dim3(1), dim3(1), 0, stream, p)); count_launch(); }
 #undef IE_DBG_STEP
     count_launch(5);
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Whole-stream parse of a video (Frame.cpp:47-127, VideoDecoder.cpp:33-62).  The reference reads the frames strictly in
+// sequence: frame f+1 starts where frame f's last block ends, and a P-frame's blocks start a fixed number of bits (the
+// motion-vector section, Block.cpp:415-423) after that.  The per-frame path above follows that chain with one parse (six short
+// launches) per frame.  Here:
+//   1. parse_spec_walk over the WHOLE stream (one launch): every 1024-bit group gets a speculative entry, exit and block
+//      count.  Inside a frame's block section the speculation is right as soon as the walkers have synchronised; across a
+//      motion-vector section it is garbage -- which is harmless, because nothing below trusts a group before an exact walk has
+//      arrived at precisely its entry.
+//   2. vparse_scan_kernel: prefix sums over the groups of (blocks started, bad seams), one launch.
+//   3. vparse_chain_kernel (one CTA, the only sequential part: a few microseconds per frame): from a frame's true first
+//      bit it walks until its position at a group boundary equals that group's speculative entry (from there on the
+//      speculative chain IS the true chain, the walk being deterministic), jumps over all groups whose seams are verified
+//      (prefix sums: a cooperative search for the group that holds the frame's last block, a check that no bad seam lies in
+//      between), walks inside that last group to the exact end of the frame.  What it finds is a list of pieces per frame:
+//      HEAD pieces (block starts found by its own walk, kept in a pool) and SPEC pieces (runs of verified groups).
+//   4. vparse_emit_kernel: block_off[] of frame k of every GOP at once from the pieces (parallel over groups).
+// Anything unusual (stream ends inside a frame, invalid length field on the true chain, no re-synchronisation within the
+// limits) clears the ok flag and the caller takes the per-frame path, which implements the reference's behaviour for
+// truncated and damaged streams.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kVG = 1024;              // bits per group of the whole-stream grid
+constexpr int kVTH = 256;              // groups per walk / emit CTA
+constexpr unsigned kVHeadGroups = 16;  // groups staged per window of a head walk
+constexpr unsigned kVMaxWindows = 64;  // head walk gives up after this many windows without meeting the speculative chain
+constexpr unsigned kVChainThreads = 512;
+
+__device__ __forceinline__ bool vseam_bad(const uint2 *spec_entry, const uint2 *spec_exit, unsigned g) {
+    if (g == 0) return false;
+    const unsigned e = spec_entry[g].x;
+    return e == kDead || spec_exit[g - 1].x != e;
+}
+
+// pq[g] = (blocks started in groups < g, bad seams with index <= g), g = 0 .. nspec (pq[nspec].y repeats the last).
+// One launch: per-CTA totals, grid barrier, every CTA adds up the totals in front of it and rescans its own span.
+__global__ void __launch_bounds__(256) vparse_scan_kernel(const ParseParams p, uint2 *pq, uint2 *partial) {
+    pdl_wait();
+    __shared__ unsigned s_a[8], s_b[8];
+    __shared__ unsigned s_base_a, s_base_b;
+    const unsigned n = p.nspec;
+    const unsigned per = ((n + gridDim.x - 1) / gridDim.x + 255u) / 256u * 256u;
+    const unsigned g0 = blockIdx.x * per, g1 = min(n, g0 + per);
+    unsigned a = 0, b = 0;
+    for (unsigned g = g0 + threadIdx.x; g < g1; g += 256) { a += p.spec_exit[g].y; b += vseam_bad(p.spec_entry, p.spec_exit, g) ? 1u : 0u; }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned ta = 0, tb = 0;
+        for (int w = 0; w < 8; w++) { ta += s_a[w]; tb += s_b[w]; }
+        partial[blockIdx.x] = make_uint2(ta, tb);
+    }
+    parse_grid_barrier(p, 1);
+    a = 0; b = 0;
+    for (unsigned c = threadIdx.x; c < blockIdx.x; c += 256) { const uint2 t = __ldcg(partial + c); a += t.x; b += t.y; }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned ta = 0, tb = 0;
+        for (int w = 0; w < 8; w++) { ta += s_a[w]; tb += s_b[w]; }
+        s_base_a = ta; s_base_b = tb;
+    }
+    __syncthreads();
+    unsigned run_a = s_base_a, run_b = s_base_b;
+    for (unsigned c0 = g0; c0 < g1; c0 += 256) {
+        const unsigned g = c0 + threadIdx.x;
+        const unsigned va = (g < g1) ? p.spec_exit[g].y : 0u;
+        const unsigned vb = (g < g1 && vseam_bad(p.spec_entry, p.spec_exit, g)) ? 1u : 0u;
+        unsigned ia = va, ib = vb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned oa = __shfl_up_sync(0xffffffffu, ia, d), ob = __shfl_up_sync(0xffffffffu, ib, d);
+            if ((int)(threadIdx.x & 31) >= d) { ia += oa; ib += ob; }
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 31) { s_a[threadIdx.x >> 5] = ia; s_b[threadIdx.x >> 5] = ib; }
+        __syncthreads();
+        unsigned ba = run_a, bb = run_b;
+        for (unsigned w = 0; w < (threadIdx.x >> 5); w++) { ba += s_a[w]; bb += s_b[w]; }
+        if (g < g1) pq[g] = make_uint2(ba + ia - va, bb + ib);         // exclusive block count, inclusive bad-seam count
+        for (int w = 0; w < 8; w++) { run_a += s_a[w]; run_b += s_b[w]; }
+        if (g + 1 == n) pq[n] = make_uint2(ba + ia, bb + ib);
+    }
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) pq[0] = make_uint2(0u, 0u);
+}
+
+// largest g in [lo, hi] for which pred(g) holds; pred is monotone (true ... true false ... false) and pred(lo) is true.
+// All threads of the CTA call it with the same arguments and get the same answer.
+template <typename Pred>
+__device__ __forceinline__ unsigned vsearch_last_true(unsigned lo, unsigned hi, Pred pred) {
+    while (hi > lo) {
+        const unsigned n = hi - lo;
+        const unsigned step = (n + kVChainThreads - 1) / kVChainThreads;
+        const unsigned long long idx = (unsigned long long)lo + (unsigned long long)(threadIdx.x + 1) * step;
+        const int ok = (idx <= hi) && pred((unsigned)idx);
+        const unsigned k = (unsigned)__syncthreads_count(ok);
+        const unsigned nlo = lo + k * step;
+        hi = min(hi, nlo + step - 1);
+        lo = nlo;
+    }
+    return lo;
+}
+
+struct VChainShared {
+    unsigned long long pos;
+    unsigned cnt, pool_n, merged, m, fail;
+};
+
+__global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const ParseParams p, const VideoParse v) {
+    pdl_wait();
+    constexpr unsigned kMaxBlock = 4 + 16 + 16 * 16;
+    constexpr unsigned kWinWords = (kVHeadGroups * kVG + kVG + kMaxBlock) / 32 + 32;
+    __shared__ __align__(16) unsigned s_win[kWinWords];
+    __shared__ unsigned s_ent[kVHeadGroups];
+    __shared__ VChainShared sh;
+    const unsigned long long total = *p.enc_bits;
+    const unsigned long long B0 = *p.start;
+    const unsigned B = v.nblocks;
+    const unsigned max_fg = (unsigned)(((unsigned long long)B * kMaxBlock) / kVG) + 4u;
+    unsigned long long pos = B0;
+    unsigned pool_n = 0;
+    bool fail = (B0 >= total) && v.frames != 0;
+    for (unsigned f = 0; f < v.frames && !fail; f++) {
+        const bool is_p = (f % v.gop) != 0;
+        if (is_p) pos += v.mv_bits;
+        if (pos >= total) { fail = true; break; }
+        VFrameRec *rec = v.rec + f;
+        if (threadIdx.x == 0) rec->first = pos;
+        unsigned cnt = 0, npieces = 0;
+        unsigned long long E = pos;
+        while (cnt < B && !fail) {
+            // ---- HEAD piece: exact walk from `pos` until a group boundary is met at that group's speculative entry
+            const unsigned pool_start = pool_n, head_base = cnt;
+            bool merged = false;
+            unsigned m = 0;
+            for (unsigned win = 0; win < kVMaxWindows && !merged && cnt < B && !fail; win++) {
+                const unsigned long long g = (pos - B0) / kVG;
+                if (g + 1 >= p.nspec) { fail = true; break; }
+                const unsigned long long w_end = B0 + (g + 1 + kVHeadGroups) * (unsigned long long)kVG;
+                __syncthreads();
+                const StagedStream st = stage_stream(s_win, kWinWords, p.enc, total, pos, min(total, w_end) + kMaxBlock);
+                if (threadIdx.x < kVHeadGroups) {
+                    const unsigned long long gg = g + 1 + threadIdx.x;
+                    s_ent[threadIdx.x] = (gg < p.nspec) ? p.spec_entry[gg].x : kDead;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    unsigned rel = (unsigned)(pos - st.base);
+                    unsigned c = cnt, pn = pool_n, mg = 0, mm = 0, fl = 0;
+                    for (unsigned j = 0; j < kVHeadGroups && !fl; j++) {
+                        const unsigned long long gend = B0 + (g + 1 + j) * (unsigned long long)kVG;
+                        const unsigned gend_rel = (unsigned)(gend - st.base);
+                        const unsigned lim = min(gend_rel, st.total_rel);
+                        while (rel < lim && c < B) {
+                            unsigned nb;
+                            const unsigned bits = staged_step(st, rel, lim, p.NN, p.use_rle, nb);
+                            if (nb == 0) { fl = 1; break; }                                  // invalid length field on the true chain
+                            const unsigned take = min(nb, B - c);
+                            if (pn + take > v.pool_cap) { fl = 1; break; }
+                            for (unsigned q = 0; q < take; q++) v.pool[pn + q] = st.base + rel + 4u * q;
+                            pn += take; c += take;
+                            rel += (take < nb) ? 4u * take : bits;
+                        }
+                        if (fl || c >= B) break;
+                        if (rel >= st.total_rel) { fl = 1; break; }                         // the stream ends inside the frame
+                        if (rel - gend_rel == s_ent[j]) { mg = 1; mm = (unsigned)(g + 1 + j); break; }
+                    }
+                    sh.pos = st.base + rel; sh.cnt = c; sh.pool_n = pn; sh.merged = mg; sh.m = mm; sh.fail = fl;
+                }
+                __syncthreads();
+                pos = sh.pos; cnt = sh.cnt; pool_n = sh.pool_n; merged = sh.merged != 0; m = sh.m; fail = sh.fail != 0;
+            }
+            if (fail) break;
+            if (pool_n > pool_start) {
+                if (npieces >= kVMaxPieces) { fail = true; break; }
+                if (threadIdx.x == 0) rec->piece[npieces] = VFramePiece{0u, pool_start, pool_n - pool_start, head_base, 0u};
+                npieces++;
+            }
+            if (cnt >= B) { E = pos; break; }
+            if (!merged) { fail = true; break; }
+            // ---- SPEC piece: groups m .. glast, all seams verified
+            const unsigned R = B - cnt;
+            const uint2 pqm = __ldcg(v.pq + m);
+            const unsigned hi = (unsigned)min((unsigned long long)p.nspec - 1ull, (unsigned long long)m + max_fg);
+            const uint2 *pq = v.pq;
+            unsigned gs = vsearch_last_true(m, hi, [&](unsigned g) { return (__ldcg(pq + g).x - pqm.x) < R; });
+            const uint2 pqs = __ldcg(pq + gs);
+            if (npieces >= kVMaxPieces) { fail = true; break; }
+            if (pqs.y != pqm.y) {
+                // a bad seam before the frame's last group: take the verified groups, go on with an exact walk from there
+                const unsigned glast = vsearch_last_true(m, gs, [&](unsigned g) { return __ldcg(pq + g).y == pqm.y; });
+                const unsigned xe = p.spec_exit[glast].x;
+                if (xe == kDead) { fail = true; break; }
+                if (threadIdx.x == 0) rec->piece[npieces] = VFramePiece{1u, m, glast, cnt, pqm.x};
+                npieces++;
+                cnt += __ldcg(pq + glast + 1).x - pqm.x;
+                pos = B0 + (unsigned long long)(glast + 1) * kVG + xe;
+                continue;
+            }
+            const unsigned r = R - (pqs.x - pqm.x);                                        // blocks to take in group gs (>= 1)
+            if (r > __ldcg(pq + gs + 1).x - pqs.x) { fail = true; break; }                 // the stream ends inside the frame
+            const unsigned es = p.spec_entry[gs].x;
+            if (es == kDead) { fail = true; break; }
+            if (threadIdx.x == 0) rec->piece[npieces] = VFramePiece{1u, m, gs, cnt, pqm.x};
+            npieces++;
+            const unsigned long long gpos = B0 + (unsigned long long)gs * kVG + es;
+            __syncthreads();
+            const StagedStream st = stage_stream(s_win, kWinWords, p.enc, total, gpos, min(total, gpos + kVG + kMaxBlock) + kMaxBlock);
+            if (threadIdx.x == 0) {
+                unsigned rel = (unsigned)(gpos - st.base), left = r, fl = 0;
+                while (left) {
+                    if (rel >= st.total_rel) { fl = 1; break; }
+                    unsigned nb;
+                    const unsigned bits = staged_step(st, rel, st.total_rel, p.NN, p.use_rle, nb);
+                    if (nb == 0) { fl = 1; break; }
+                    const unsigned take = min(nb, left);
+                    rel += (take < nb) ? 4u * take : bits;
+                    left -= take;
+                }
+                if (rel > st.total_rel) fl = 1;
+                sh.pos = st.base + rel; sh.fail = fl;
+            }
+            __syncthreads();
+            fail = sh.fail != 0;
+            E = sh.pos; pos = E; cnt = B;
+        }
+        if (fail) break;
+        if (threadIdx.x == 0) { rec->end = E; rec->npieces = npieces; }
+        pos = E;
+    }
+    if (threadIdx.x == 0) { v.result[0] = fail ? 0u : 1u; v.result[1] = pool_n; }
+}
+
+// block_off[img][0 .. nblocks] of frame slot + img * gop (img = blockIdx.y) from the frame's pieces
+__global__ void __launch_bounds__(kVTH) vparse_emit_kernel(const ParseParams p, const VideoParse v, unsigned first_frame, unsigned long long *block_off) {
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned s_stage[];
+    const unsigned f = first_frame + blockIdx.y * v.gop;
+    const VFrameRec *rec = v.rec + f;
+    unsigned long long *off = block_off + (size_t)blockIdx.y * (v.nblocks + 1);
+    const unsigned long long total = *p.enc_bits;
+    const unsigned long long B0 = *p.start;
+    const unsigned np = rec->npieces;
+    if (blockIdx.x == 0 && threadIdx.x == 0) off[v.nblocks] = rec->end;
+    for (unsigned i = 0; i < np; i++) {
+        const VFramePiece pc = rec->piece[i];
+        if (pc.kind == 0) {
+            for (unsigned j = blockIdx.x * kVTH + threadIdx.x; j < pc.b; j += gridDim.x * kVTH) off[pc.idx_base + j] = v.pool[pc.a + j];
+            continue;
+        }
+        for (unsigned g0 = pc.a + blockIdx.x * kVTH; g0 <= pc.b; g0 += gridDim.x * kVTH) {      // uniform
+            const unsigned long long c_start = B0 + (unsigned long long)g0 * kVG;
+            __syncthreads();
+            const StagedStream st = stage_stream(s_stage, SpecCfg<kVG, kVTH>::kStageWords, p.enc, total, c_start,
+                                                 min(total, c_start + (unsigned long long)kVTH * kVG));
+            const unsigned g = g0 + threadIdx.x;
+            if (g > pc.b) continue;
+            const unsigned entry = p.spec_entry[g].x;
+            if (entry == kDead) continue;
+            unsigned idx = pc.idx_base + (v.pq[g].x - pc.pm);
+            const unsigned g_rel = (unsigned)(c_start + (unsigned long long)threadIdx.x * kVG - st.base);
+            unsigned rel = g_rel + entry;
+            const unsigned lim = min(g_rel + kVG, st.total_rel);
+            while (rel < lim && idx < v.nblocks) {
+                unsigned nb;
+                const unsigned bits = staged_step(st, rel, lim, p.NN, p.use_rle, nb);
+                if (nb == 0) { if (p.err) atomicExch(p.err, IE_EFORMAT); break; }
+                for (unsigned j = 0; j < nb && idx < v.nblocks; j++) off[idx++] = st.base + rel + 4u * j;
+                rel += bits;
+            }
+        }
+    }
+}
+
+static void video_parse_layout(const VideoParseSizes &z, uint8_t *scratch, ParseParams &p, VideoParse &v) {
+    uint2 *s = reinterpret_cast<uint2 *>(scratch);
+    p.spec_entry = s; s += z.nspec;
+    p.spec_exit = s; s += z.nspec;
+    v.pq = s; s += z.nspec + 1;
+    v.partial = s; s += z.scan_ctas;
+    p.spec_flags = reinterpret_cast<unsigned *>(s);
+    p.cursor_next = reinterpret_cast<unsigned long long *>(p.spec_flags + 8);
+    v.result = p.spec_flags + 12;
+    p.walk_base = p.spec_flags + 16;
+    uint8_t *b = reinterpret_cast<uint8_t *>(p.spec_flags + 32);
+    v.pool = reinterpret_cast<unsigned long long *>(b); b += z.pool_cap * sizeof(unsigned long long);
+    v.rec = reinterpret_cast<VFrameRec *>(b);
+    v.pool_cap = (unsigned)z.pool_cap;
+}
+
+VideoParseSizes video_parse_sizes(size_t enc_bytes, unsigned frames, int sm_count) {
+    VideoParseSizes z;
+    z.nspec = (enc_bytes * 8 + kVG - 1) / kVG + 1;
+    z.scan_ctas = (unsigned)std::max(1, sm_count);
+    z.pool_cap = (size_t)frames * 4096 + 65536;
+    z.bytes = (2 * z.nspec + z.nspec + 1 + z.scan_ctas) * sizeof(uint2) + 32 * sizeof(unsigned) + z.pool_cap * sizeof(unsigned long long) +
+              (size_t)frames * sizeof(VFrameRec) + 256;
+    return z;
+}
+
+// steps 1-3: after this (on `stream`) v.result[0] says whether the frame records are valid
+int launch_video_parse(const uint8_t *d_enc, const unsigned long long *d_enc_bits, const unsigned long long *d_start, int use_rle,
+                       unsigned nblocks, unsigned mv_bits, unsigned frames, unsigned gop, const VideoParseSizes &z, uint8_t *scratch,
+                       VideoParse &v, ParseParamsOpaque &popaque, cudaStream_t stream) {
+    static_assert(sizeof(ParseParamsOpaque) >= sizeof(ParseParams), "opaque storage too small");
+    ParseParams &p = *reinterpret_cast<ParseParams *>(&popaque);
+    memset(&p, 0, sizeof p);
+    memset(&v, 0, sizeof v);
+    p.enc = d_enc; p.enc_bits = d_enc_bits; p.start = d_start; p.skip_bits = 0;
+    p.NN = 16; p.use_rle = use_rle; p.E = 4 + 16 + 16 * 16;
+    p.nblocks = nblocks;
+    p.nspec = (unsigned)z.nspec;
+    v.nblocks = nblocks; v.mv_bits = mv_bits; v.frames = frames; v.gop = gop;
+    video_parse_layout(z, scratch, p, v);
+    if ((uintptr_t)d_enc % 16) { set_error("encoded stream must be 16-byte aligned on the device"); return IE_EINVAL; }
+    const unsigned nwalk = (p.nspec + kVTH - 1) / kVTH;
+    const size_t stage_bytes = (size_t)SpecCfg<kVG, kVTH>::kStageWords * sizeof(unsigned);
+    IE_CUDA(cudaFuncSetAttribute(parse_spec_walk<kVG, kVTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    IE_CUDA(launch_pdl(parse_spec_walk<kVG, kVTH>, dim3(nwalk), dim3(kVTH), stage_bytes, stream, p));
+    IE_CUDA(launch_pdl(vparse_scan_kernel, dim3(z.scan_ctas), dim3(256), 0, stream, p, v.pq, v.partial));
+    IE_CUDA(launch_pdl(vparse_chain_kernel, dim3(1), dim3(kVChainThreads), 0, stream, p, v));
+    count_launch(3);
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
+int launch_video_emit(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned first_frame, unsigned nimg, unsigned long long *block_off,
+                      cudaStream_t stream) {
+    const ParseParams &p = *reinterpret_cast<const ParseParams *>(&popaque);
+    const size_t stage_bytes = (size_t)SpecCfg<kVG, kVTH>::kStageWords * sizeof(unsigned);
+    static bool configured = false;
+    if (!configured) { IE_CUDA(cudaFuncSetAttribute(vparse_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes)); configured = true; }
+    IE_CUDA(launch_pdl(vparse_emit_kernel, dim3(48, nimg), dim3(kVTH), stage_bytes, stream, p, v, first_frame, block_off));
+    count_launch();
     IE_CUDA(cudaGetLastError());
     return IE_OK;
 }

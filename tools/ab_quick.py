@@ -27,6 +27,12 @@ if "--combos" in sys.argv:                       # e.g. --combos 2:2,8:2
     COMBOS = [tuple(int(x) for x in c.split(":")) for c in sys.argv[i + 1].split(",")]
     del sys.argv[i:i + 2]
 
+PADS = [0]
+if "--pads" in sys.argv:                         # occupancy experiment: extra dynamic shared memory per tile-kernel CTA
+    i = sys.argv.index("--pads")
+    PADS = [int(x) for x in sys.argv[i + 1].split(",")]
+    del sys.argv[i:i + 2]
+
 # ---- 1. parity on small images against the oracle
 import oracle
 for mat in ("matrix8_1.txt", "matrix4_2.txt"):
@@ -114,6 +120,23 @@ def fetch():
 
 
 ref = None
+for pad in PADS[1:] + PADS[:1]:
+    _lib.check(L.ie_set_option(b"encode_pad_smem", pad))
+    if len(PADS) == 1:
+        break
+    _lib.check(L.ie_set_option(b"encode_variant", 2))
+    _lib.check(L.ie_set_option(b"copyout_variant", 2))
+    run(RING)
+    ck(rt.cudaDeviceSynchronize(), "sync")
+    reps = 40
+    ck(rt.cudaEventRecord(e0, None), "record")
+    run(reps)
+    ck(rt.cudaEventRecord(e1, None), "record")
+    ck(rt.cudaEventSynchronize(e1), "sync")
+    ms = C.c_float()
+    ck(rt.cudaEventElapsedTime(C.byref(ms), e0, e1), "elapsed")
+    res["timing"][f"pad{pad}"] = ms.value / reps
+    print(f"encode_pad_smem {pad}: {ms.value / reps:.4f} ms/encode", flush=True)
 for rnd in range(2):
     for v, cv in COMBOS:
         _lib.check(L.ie_set_option(b"encode_variant", v))
