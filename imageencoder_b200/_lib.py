@@ -72,6 +72,7 @@ SIGNATURES = {
     "ie_comm_copy_stitched": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "ie_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "ie_kernel_launch_count": (C.c_uint64, []),
+    "ie_stat": (C.c_uint64, [C.c_char_p]),
 }
 
 

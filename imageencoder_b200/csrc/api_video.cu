@@ -45,7 +45,150 @@ __global__ void __launch_bounds__(256) me_search_redux_kernel(MEParams p) {
 #include "me_search_body.inc"
 #undef IE_ME_REDUX
 }
-std::atomic<int> g_me_variant{0};
+
+// me_variant 2 (the default): eight lanes per MacroBlock (two pixel rows each), four horizontally adjacent MacroBlocks per warp
+// on one shared search window.  The selection logic, the reduction and the address arithmetic of a level cost the same per
+// warp whatever the number of MacroBlocks in it, so four per warp cut the instructions per MacroBlock by ~3x; the window of
+// four neighbours (46 rows x 100 pixels) is staged once instead of four times (46 x 52 each).  Same candidates, same order,
+// same tie rule as me_search_kernel (Block.cpp:267-339).
+__device__ __forceinline__ unsigned sad4_acc(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
+    constexpr int kWinRows = 46, kWinWords = 25;
+    __shared__ unsigned s_win[8][kWinRows * kWinWords];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gx = (p.mx + 3) >> 2;                                     // groups of four MacroBlocks per MacroBlock row
+    const int grp = blockIdx.x * 8 + warp;
+    if (grp >= gx * (p.nmb / p.mx)) return;
+    p.cur += (size_t)blockIdx.y * p.frame_stride; p.ref += (size_t)blockIdx.y * p.frame_stride;
+    p.mv += (size_t)blockIdx.y * p.mv_stride; p.res_coord += (size_t)blockIdx.y * p.mv_stride; p.copy_coord += (size_t)blockIdx.y * p.mv_stride;
+    const int gy = grp / gx, g0x = (grp - gy * gx) * 4;
+    const int sub = lane >> 3, li = lane & 7;
+    const bool live = g0x + sub < p.mx;
+    const int mbi = min(g0x + sub, p.mx - 1);                           // lanes of a missing MacroBlock shadow the row's last one
+    const int mbx = mbi * kMB, mby = gy * kMB;
+    const int mb = gy * p.mx + mbi;
+    const uint4 c0 = *reinterpret_cast<const uint4 *>(p.cur + (size_t)(mby + 2 * li) * p.W + mbx);
+    const uint4 c1 = *reinterpret_cast<const uint4 *>(p.cur + (size_t)(mby + 2 * li + 1) * p.W + mbx);
+    const bool staged = p.merange <= 16;
+    const int wy0 = max(mby - 15, 0), wxa = max(g0x * kMB - 15, 0) & ~3;
+    unsigned *win = s_win[warp];
+    if (staged) {
+        constexpr int kIters = (kWinRows * kWinWords + 31) / 32, kHalf = (kIters + 1) / 2;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            unsigned v[kHalf];
+#pragma unroll
+            for (int i = 0; i < kHalf; i++) {                          // half of the loads in flight before the first store
+                const int idx = lane + 32 * (h * kHalf + i);
+                const int r = idx / kWinWords, k = idx - r * kWinWords;
+                const int y = wy0 + r, x = wxa + 4 * k;
+                v[i] = (idx < kWinRows * kWinWords && y < p.H && x + 4 <= p.W) ? __ldg(reinterpret_cast<const unsigned *>(p.ref + (size_t)y * p.W + x)) : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < kHalf; i++) {
+                const int idx = lane + 32 * (h * kHalf + i);
+                if (idx < kWinRows * kWinWords) win[idx] = v[i];
+            }
+        }
+        __syncwarp();
+    }
+    int best_x = 0, best_y = 0;
+    int bcx = 0, bcy = 0;                                               // Block.cpp:273: the initial block is the one at pixel (0,0)
+    unsigned best_d = 0xffffffffu;
+    for (int step = p.merange / 2; step > 0; step >>= 1) {              // algo.cpp:129,138
+        int cx3[3], cy3[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            cx3[j] = clampi((int)(short)(best_x + (j - 1) * step + mbx), 0, p.W - kMB);
+            cy3[j] = clampi((int)(short)(best_y + (j - 1) * step + mby), 0, p.H - kMB);
+        }
+        constexpr int kSX[9] = {1, 2, 2, 1, 0, 0, 0, 1, 2}, kSY[9] = {1, 1, 2, 2, 2, 1, 0, 0, 0};      // MER_SIGNS, algo.cpp:90-100
+        unsigned d[9];
+        if (staged) {
+            int xw[3], rb[3];
+            unsigned xs[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int bx = cx3[j] - wxa;
+                xw[j] = bx >> 2; xs[j] = (unsigned)(bx & 3) * 8;
+                rb[j] = (cy3[j] - wy0 + 2 * li) * kWinWords;
+            }
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                const unsigned *wp = win + rb[kSY[q]] + xw[kSX[q]];
+                const unsigned sh = xs[kSX[q]];
+                unsigned a[5], b[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) { a[k] = wp[k]; b[k] = wp[kWinWords + k]; }     // word 4 is inside the window row (<= 24)
+                unsigned acc = 0;
+                acc = sad4_acc(c0.x, __funnelshift_r(a[0], a[1], sh), acc);
+                acc = sad4_acc(c0.y, __funnelshift_r(a[1], a[2], sh), acc);
+                acc = sad4_acc(c0.z, __funnelshift_r(a[2], a[3], sh), acc);
+                acc = sad4_acc(c0.w, __funnelshift_r(a[3], a[4], sh), acc);
+                acc = sad4_acc(c1.x, __funnelshift_r(b[0], b[1], sh), acc);
+                acc = sad4_acc(c1.y, __funnelshift_r(b[1], b[2], sh), acc);
+                acc = sad4_acc(c1.z, __funnelshift_r(b[2], b[3], sh), acc);
+                acc = sad4_acc(c1.w, __funnelshift_r(b[3], b[4], sh), acc);
+                d[q] = acc;                                                               // Block.cpp:241-254 (this lane's 32 pixels)
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                const uint8_t *rp = p.ref + (size_t)(cy3[kSY[q]] + 2 * li) * p.W + cx3[kSX[q]];
+                const uintptr_t ad = (uintptr_t)rp;
+                const unsigned *wp = reinterpret_cast<const unsigned *>(ad & ~(uintptr_t)3);
+                const unsigned sh = (unsigned)(ad & 3) * 8;
+                const unsigned *wq = wp + (p.W >> 2);
+                unsigned a[5], b[5];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { a[k] = __ldg(wp + k); b[k] = __ldg(wq + k); }
+                a[4] = sh ? __ldg(wp + 4) : 0u; b[4] = sh ? __ldg(wq + 4) : 0u;
+                unsigned acc = 0;
+                acc = sad4_acc(c0.x, __funnelshift_r(a[0], a[1], sh), acc);
+                acc = sad4_acc(c0.y, __funnelshift_r(a[1], a[2], sh), acc);
+                acc = sad4_acc(c0.z, __funnelshift_r(a[2], a[3], sh), acc);
+                acc = sad4_acc(c0.w, __funnelshift_r(a[3], a[4], sh), acc);
+                acc = sad4_acc(c1.x, __funnelshift_r(b[0], b[1], sh), acc);
+                acc = sad4_acc(c1.y, __funnelshift_r(b[1], b[2], sh), acc);
+                acc = sad4_acc(c1.z, __funnelshift_r(b[2], b[3], sh), acc);
+                acc = sad4_acc(c1.w, __funnelshift_r(b[3], b[4], sh), acc);
+                d[q] = acc;
+            }
+        }
+        // a MacroBlock's SAD is <= 256 * 255 < 2^16: two partial sums per register, reduced over the MacroBlock's eight lanes
+        unsigned pk[5] = {d[0] | (d[1] << 16), d[2] | (d[3] << 16), d[4] | (d[5] << 16), d[6] | (d[7] << 16), d[8]};
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) pk[k] += __shfl_xor_sync(0xffffffffu, pk[k], o);
+        }
+        int bq = -1, ncx = 0, ncy = 0;
+        unsigned nd = best_d;
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            const int cpx = cx3[kSX[q]], cpy = cy3[kSY[q]];
+            if (q > 0 && cpx == mbx && cpy == mby) continue;                   // Block.cpp:297-301
+            const unsigned dq = (q == 8) ? pk[4] : ((q & 1) ? (pk[q >> 1] >> 16) : (pk[q >> 1] & 0xffffu));
+            if (dq <= nd) { bq = q; nd = dq; ncx = cpx; ncy = cpy; }           // Block.cpp:306
+        }
+        // Block.cpp:318-321: no candidate at all -- cannot happen (candidate 0 is never skipped and d <= best_d holds for it:
+        // the centre of a level is the previous level's best); lanes must stay together for the shuffles, so no early exit
+        if (bq >= 0) { best_x += c_mer_sx[bq] * step; best_y += c_mer_sy[bq] * step; best_d = nd; bcx = ncx; bcy = ncy; }
+    }
+    if (li == 0 && live) {
+        p.mv[2 * mb] = (short)best_x;
+        p.mv[2 * mb + 1] = (short)best_y;
+        p.res_coord[2 * mb] = (short)bcx;
+        p.res_coord[2 * mb + 1] = (short)bcy;
+        p.copy_coord[2 * mb] = (short)clampi((int)(short)(mbx + best_x), 0, p.W - kMB);
+        p.copy_coord[2 * mb + 1] = (short)clampi((int)(short)(mby + best_y), 0, p.H - kMB);
+    }
+}
+std::atomic<int> g_me_variant{2};
 
 // fixed-width fields: field i = low `bits` bits of val[i]
 struct FixedFieldTile {
@@ -87,6 +230,38 @@ __global__ void __launch_bounds__(kThreads) mvec_pack_kernel(const short *mv, si
     tile_write_chunks(t, st, 0, true, true, G, T, out, out_cap, err);
     __syncthreads();
     if (threadIdx.x == 0) *bit_counter = G + T;
+}
+
+
+// The same, a thread per 128-bit chunk of the motion-vector section over as many CTAs as it takes (mvec_pack_kernel walks the
+// section with one CTA per GOP: 43 us per frame slot on config 5).  The chunk that holds the section's first bit already holds
+// the end of the previous frame: its owner merges (stream order: that frame's copy-out has completed); bits past the section
+// in the last chunk are zero, the tile copy-out that follows merges into it.  The last CTA of a GOP to finish advances the
+// GOP's bit counter (ticket; every CTA has read the counter before it takes one) and resets the ticket.
+__global__ void __launch_bounds__(256) mvec_pack2_kernel(const short *mv, size_t mv_stride, unsigned nfields, unsigned bits, uint8_t *out,
+                                                         size_t out_stride, size_t out_cap, unsigned long long *bit_counter, unsigned *ticket, int *err) {
+    mv += (size_t)blockIdx.y * mv_stride; out += (size_t)blockIdx.y * out_stride; bit_counter += blockIdx.y; ticket += blockIdx.y;
+    const FixedFieldTile t{mv, nfields, bits};
+    const unsigned long long G = *bit_counter;
+    const unsigned T = nfields * bits;
+    if (T != 0) {
+        const unsigned long long c0 = G / kChunkBits, c1 = (G + T - 1) / kChunkBits;
+        const unsigned long long c = c0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (c <= c1) {
+            if ((c + 1) * 16ull > out_cap) { if (err) atomicExch(err, IE_ENOSPC); }
+            else {
+                uint4 v = gather_chunk(t, (long long)(c * kChunkBits) - (long long)G);
+                uint4 *dst = reinterpret_cast<uint4 *>(out) + c;
+                if (c == c0 && (G % kChunkBits) != 0) { const uint4 o = *dst; v.x |= o.x; v.y |= o.y; v.z |= o.z; v.w |= o.w; }
+                *dst = v;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *bit_counter = G + T; *ticket = 0u; }
+    }
 }
 
 struct MCParams {
@@ -249,17 +424,18 @@ __global__ void __launch_bounds__(256) gop_append_kernel(const uint8_t *gop_stre
     }
 }
 
-struct VideoScratch { short *mv, *res, *copy; unsigned long long *cursor, *gop_off; };
+struct VideoScratch { short *mv, *res, *copy; unsigned long long *cursor, *gop_off; unsigned *ticket; };
 // motion vectors / residual / copy coordinates of `ngops` frames in flight ([gop][nmb][2] each), the stream's bit cursor and
 // the GOP offsets of a batch
 static int video_scratch(ie_session *s, size_t nmb, size_t ngops, VideoScratch &v) {
     const size_t sec = (nmb * 2 * sizeof(short) * ngops + 63) / 64 * 64;
-    IE_TRY(session_reserve(&s->d_scratch, &s->scratch_cap, 3 * sec + 64 + ngops * sizeof(unsigned long long)));
+    IE_TRY(session_reserve(&s->d_scratch, &s->scratch_cap, 3 * sec + 64 + ngops * (sizeof(unsigned long long) + sizeof(unsigned))));
     v.mv = reinterpret_cast<short *>(s->d_scratch);
     v.res = reinterpret_cast<short *>(s->d_scratch + sec);
     v.copy = reinterpret_cast<short *>(s->d_scratch + 2 * sec);
     v.cursor = reinterpret_cast<unsigned long long *>(s->d_scratch + 3 * sec);
     v.gop_off = v.cursor + 8;
+    v.ticket = reinterpret_cast<unsigned *>(v.gop_off + ngops);
     return IE_OK;
 }
 
@@ -297,6 +473,7 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     VideoScratch vs;
     IE_TRY(video_scratch(s, nmb, batch, vs));
     IE_TRY(session_reserve(&s->d_tmp, &s->d_tmp_cap, (size_t)batch * gop_cap));          // the GOP streams of a batch
+    IE_CUDA(cudaMemsetAsync(vs.ticket, 0, batch * sizeof(unsigned), st));
 
     HeaderParam hdr, nohdr;
     memset(&nohdr, 0, sizeof nohdr);
@@ -349,11 +526,15 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
             me.cur = cur; me.ref = cur - fsz; me.W = (int)W; me.H = (int)H; me.mx = (int)(W / kMB); me.nmb = (int)nmb;
             me.merange = (int)merange; me.mv = vs.mv; me.res_coord = vs.res; me.copy_coord = vs.copy;
             me.frame_stride = p.img_stride; me.mv_stride = p.coord_stride;
-            if (g_me_variant.load() == 1) me_search_redux_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, st>>>(me);
+            if (g_me_variant.load() == 2) me_search8_kernel<<<dim3((((W / kMB + 3) / 4) * (H / kMB) + 7) / 8, act), 256, 0, st>>>(me);
+            else if (g_me_variant.load() == 1) me_search_redux_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, st>>>(me);
             else me_search_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, st>>>(me);
             count_launch();
-            mvec_pack_kernel<<<dim3(1, act), kThreads, 0, st>>>(vs.mv, p.coord_stride, nmb * 2, mvbits, s->d_tmp, gop_cap, gop_cap, s->d_counter,
-                                                               s->d_err);
+            {
+                const unsigned mv_chunks = (nmb * 2 * mvbits + 127) / 128 + 1;
+                mvec_pack2_kernel<<<dim3((mv_chunks + 255) / 256, act), 256, 0, st>>>(vs.mv, p.coord_stride, nmb * 2, mvbits, s->d_tmp, gop_cap, gop_cap,
+                                                                                     s->d_counter, vs.ticket, s->d_err);
+            }
             count_launch();
             IE_CUDA(cudaGetLastError());
             if (d_mvecs) IE_CUDA(cudaMemcpy2DAsync(d_mvecs + (size_t)f * nmb * 2, (size_t)gop * nmb * 2 * sizeof(short), vs.mv,
@@ -422,6 +603,7 @@ namespace ie {
 // 1 = whole-stream parse + frame k of every GOP per launch (default), 0 = frame by frame (also the fallback for truncated and
 // damaged streams)
 std::atomic<int> g_video_decode_variant{1};
+std::atomic<uint64_t> g_stat_video_whole{0}, g_stat_video_frames{0};
 
 // Returns IE_OK with done = false when the stream is not a plain well-formed one (the caller then decodes frame by frame).
 static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, const ParsedHeader &h, int motioncomp, uint8_t *d_out,
@@ -512,8 +694,9 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
     if (g_video_decode_variant.load() == 1) {
         bool done = false;
         IE_TRY(decode_video_whole(s, d_enc, enc_bytes, h, motioncomp, d_out, st, done));
-        if (done) return IE_OK;
+        if (done) { g_stat_video_whole.fetch_add(1); return IE_OK; }
     }
+    g_stat_video_frames.fetch_add(1);
     VideoScratch vs;
     IE_TRY(video_scratch(s, nmb, 1, vs));
     const size_t need_off = ((size_t)nblocks + 1) * sizeof(unsigned long long) + 64;

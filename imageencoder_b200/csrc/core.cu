@@ -22,6 +22,7 @@ extern std::atomic<int> g_parse_grid4;         // parse.cu
 extern std::atomic<int> g_decode_variant;      // decode_image.cu
 extern std::atomic<int> g_me_variant;          // api_video.cu
 extern std::atomic<int> g_video_decode_variant;
+extern std::atomic<uint64_t> g_stat_video_whole, g_stat_video_frames;
 static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
 
@@ -217,6 +218,11 @@ void ie_shutdown(void) {
 const char *ie_last_error(void) { return ie::t_error.c_str(); }
 const char *ie_version(void) { return "imageencoder_b200 0.1 (sm_100a)"; }
 uint64_t ie_kernel_launch_count(void) { return ie::g_launches.load(); }
+uint64_t ie_stat(const char *name) {
+    if (name && !strcmp(name, "video_decode_whole_stream")) return ie::g_stat_video_whole.load();
+    if (name && !strcmp(name, "video_decode_frame_by_frame")) return ie::g_stat_video_frames.load();
+    return 0;
+}
 
 int ie_set_option(const char *name, int value) {
     if (name && !strcmp(name, "exact_transform")) { ie::g_exact_transform.store(value); return IE_OK; }
@@ -268,7 +274,7 @@ int ie_set_option(const char *name, int value) {
         return IE_OK;
     }
     if (name && !strcmp(name, "me_variant")) {
-        if (value < 0 || value > 1) { ie::set_error("me_variant: 0 (default) or 1 (REDUX reduction of the SAD partial sums, experimental)"); return IE_EINVAL; }
+        if (value < 0 || value > 2) { ie::set_error("me_variant: 2 (eight lanes per MacroBlock, four MacroBlocks per warp; default), 0 (warp per MacroBlock) or 1 (0 with REDUX reductions)"); return IE_EINVAL; }
         ie::g_me_variant.store(value);
         return IE_OK;
     }

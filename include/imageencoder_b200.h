@@ -236,6 +236,9 @@ int ie_comm_copy_stitched(ie_comm *c, void *dst, size_t nbytes, void *stream);
  *                          thread in flight, 1 = short path one chunk at a time, 0 = the generic kernel;
  *   "decode_variant"  = 0 | 1 (default)  block-decode kernel of images and I-frames: 1 = inverse transform and pixel
  *                          stage in packed f32x2 operations, 0 = the scalar kernel it replaced;
+ *   "video_decode_variant" = 0 | 1 (default)  video decode: 1 = one speculative parse over the whole stream, a short
+ *                          sequential frame chain, then frame k of every GOP per launch (streams that end inside a frame or
+ *                          hold an invalid length field fall back to 0); 0 = frame by frame;
  *   "me_variant"      = 0 (default) | 1  motion-search kernel: 1 = SAD partial sums reduced with warp-wide integer
  *                          reductions (REDUX) instead of shuffle + add steps (experimental, not yet timed).
  * Returns IE_EINVAL for an unknown name or an out-of-range value. */
@@ -243,6 +246,11 @@ int ie_set_option(const char *name, int value);
 
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 uint64_t ie_kernel_launch_count(void);
+
+/* Counters since load, for tests that must know which path ran: "video_decode_whole_stream" (video decodes that took the
+ * whole-stream parse), "video_decode_frame_by_frame" (decodes that took, or fell back to, the per-frame path).  Unknown
+ * names give 0. */
+uint64_t ie_stat(const char *name);
 
 #ifdef __cplusplus
 }

@@ -32,13 +32,22 @@ def test_video_matches_oracle(gpu, oracle_mod, W, H, F, gop, mer, huffman):
         plain = oracle_mod.video_encode(yuv, W, H, q, True, gop, mer, False)
         if gold and gold["dec_mc1_sha256"] is None:
             return
-    for mc in (True, False):
-        dec, w, h, f = gpu.decode_video(got, mc)
-        odec = oracle_mod.video_decode(want, mc)[0]
-        assert (w, h, f) == (W, H, F)
-        assert np.array_equal(dec, odec), f"decoded frames differ (motioncompensation={mc})"
-        if gold:
-            assert hashlib.sha256(dec.tobytes()).hexdigest() == gold["dec_mc1_sha256" if mc else "dec_mc0_sha256"]
+    L = gpu.lib()
+    try:
+        for variant in (1, 0):              # whole-stream parse (default) and the frame-by-frame path it falls back to
+            assert L.ie_set_option(b"video_decode_variant", variant) == 0
+            for mc in (True, False):
+                before = L.ie_stat(b"video_decode_whole_stream")
+                dec, w, h, f = gpu.decode_video(got, mc)
+                if variant == 1:        # a well-formed stream must take the whole-stream path, not silently fall back
+                    assert L.ie_stat(b"video_decode_whole_stream") == before + 1
+                odec = oracle_mod.video_decode(want, mc)[0]
+                assert (w, h, f) == (W, H, F)
+                assert np.array_equal(dec, odec), f"decoded frames differ (motioncompensation={mc}, variant={variant})"
+                if gold:
+                    assert hashlib.sha256(dec.tobytes()).hexdigest() == gold["dec_mc1_sha256" if mc else "dec_mc0_sha256"]
+    finally:
+        L.ie_set_option(b"video_decode_variant", 1)
 
 
 def test_video_rle_off_and_other_matrix(gpu, oracle_mod):
