@@ -56,6 +56,48 @@ __device__ __forceinline__ unsigned sad4_acc(unsigned a, unsigned b, unsigned c)
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+
+// One level of the search on the staged window when no candidate of any lane is clamped and the step is 8, 4, 2 or 1: the
+// three candidates of a row (x - S, x, x + S) lie in one span of 16 + 2 S bytes, which is read once, aligned to the first
+// candidate with one funnel shift per word, and then used at compile-time offsets (shared-memory reads per level: 6 rows of
+// 9 / 7 / 6 / 6 words instead of 18 rows of 5 -- the kernel is bound by shared-memory bandwidth).
+template <int S>
+__device__ __forceinline__ void me_level_span(const unsigned *win, int row_words, int rb0, int rb1, int rb2, int xw0, unsigned sh, const uint4 &c0,
+                                              const uint4 &c1, unsigned (&d)[9]) {
+    constexpr int W = (16 + 2 * S + 3 + 3) / 4;          // words that hold bytes a .. a + 16 + 2 S, a = 0 .. 3
+    unsigned acc[3][3];
+#pragma unroll
+    for (int jy = 0; jy < 3; jy++)
+#pragma unroll
+        for (int jx = 0; jx < 3; jx++) acc[jy][jx] = 0;
+#pragma unroll
+    for (int jy = 0; jy < 3; jy++) {
+        const int rb = (jy == 0) ? rb0 : (jy == 1 ? rb1 : rb2);
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const unsigned *wp = win + rb + rr * row_words + xw0;
+            unsigned w[W], n[W - 1];
+#pragma unroll
+            for (int k = 0; k < W; k++) w[k] = wp[k];
+#pragma unroll
+            for (int k = 0; k < W - 1; k++) n[k] = __funnelshift_r(w[k], w[k + 1], sh);
+            const unsigned cr[4] = {rr ? c1.x : c0.x, rr ? c1.y : c0.y, rr ? c1.z : c0.z, rr ? c1.w : c0.w};
+#pragma unroll
+            for (int jx = 0; jx < 3; jx++) {
+                constexpr int dummy = 0; (void)dummy;
+                const int o = jx * S, ow = o >> 2, os = (o & 3) * 8;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned r = os ? __funnelshift_r(n[ow + k], n[(ow + k + 1 < W - 1) ? ow + k + 1 : W - 2], (unsigned)os) : n[ow + k];
+                    acc[jy][jx] = sad4_acc(cr[k], r, acc[jy][jx]);
+                }
+            }
+        }
+    }
+    constexpr int kSX[9] = {1, 2, 2, 1, 0, 0, 0, 1, 2}, kSY[9] = {1, 1, 2, 2, 2, 1, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 9; q++) d[q] = acc[kSY[q]][kSX[q]];
+}
 __global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
     constexpr int kWinRows = 46, kWinWords = 25;
     __shared__ unsigned s_win[8][kWinRows * kWinWords];
@@ -108,7 +150,19 @@ __global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
         }
         constexpr int kSX[9] = {1, 2, 2, 1, 0, 0, 0, 1, 2}, kSY[9] = {1, 1, 2, 2, 2, 1, 0, 0, 0};      // MER_SIGNS, algo.cpp:90-100
         unsigned d[9];
-        if (staged) {
+        // span path: every lane's three x (and y) candidates are exactly step apart (nothing clamped)
+        const bool regular = staged && (step == 8 || step == 4 || step == 2 || step == 1) && cx3[1] - cx3[0] == step && cx3[2] - cx3[1] == step &&
+                             cy3[1] - cy3[0] == step && cy3[2] - cy3[1] == step;
+        if (__all_sync(0xffffffffu, regular)) {
+            const int bx = cx3[0] - wxa;
+            const int xw0 = bx >> 2;
+            const unsigned sh = (unsigned)(bx & 3) * 8;
+            const int rb0 = (cy3[0] - wy0 + 2 * li) * kWinWords, rb1 = (cy3[1] - wy0 + 2 * li) * kWinWords, rb2 = (cy3[2] - wy0 + 2 * li) * kWinWords;
+            if (step == 8) me_level_span<8>(win, kWinWords, rb0, rb1, rb2, xw0, sh, c0, c1, d);
+            else if (step == 4) me_level_span<4>(win, kWinWords, rb0, rb1, rb2, xw0, sh, c0, c1, d);
+            else if (step == 2) me_level_span<2>(win, kWinWords, rb0, rb1, rb2, xw0, sh, c0, c1, d);
+            else me_level_span<1>(win, kWinWords, rb0, rb1, rb2, xw0, sh, c0, c1, d);
+        } else if (staged) {
             int xw[3], rb[3];
             unsigned xs[3];
 #pragma unroll
