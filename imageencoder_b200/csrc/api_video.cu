@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) me_search_redux_kernel(MEParams p) {
 #undef IE_ME_REDUX
 }
 
-// me_variant 2 (the default): eight lanes per MacroBlock (two pixel rows each), four horizontally adjacent MacroBlocks per warp
+// me_variant 2 (the default): eight lanes per MacroBlock (two pixel rows each: li and li + 8), four horizontally adjacent MacroBlocks per warp
 // on one shared search window.  The selection logic, the reduction and the address arithmetic of a level cost the same per
 // warp whatever the number of MacroBlocks in it, so four per warp cut the instructions per MacroBlock by ~3x; the window of
 // four neighbours (46 rows x 100 pixels) is staged once instead of four times (46 x 52 each).  Same candidates, same order,
@@ -75,7 +75,7 @@ __device__ __forceinline__ void me_level_span(const unsigned *win, int row_words
         const int rb = (jy == 0) ? rb0 : (jy == 1 ? rb1 : rb2);
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
-            const unsigned *wp = win + rb + rr * row_words + xw0;
+            const unsigned *wp = win + rb + rr * 8 * row_words + xw0;
             unsigned w[W], n[W - 1];
 #pragma unroll
             for (int k = 0; k < W; k++) w[k] = wp[k];
@@ -99,7 +99,7 @@ __device__ __forceinline__ void me_level_span(const unsigned *win, int row_words
     for (int q = 0; q < 9; q++) d[q] = acc[kSY[q]][kSX[q]];
 }
 __global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
-    constexpr int kWinRows = 46, kWinWords = 25;
+    constexpr int kWinRows = 46, kWinWords = 27;        // 27: lanes 0..7 of a MacroBlock (rows li, li + 8) and its neighbours spread over the banks
     __shared__ unsigned s_win[8][kWinRows * kWinWords];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gx = (p.mx + 3) >> 2;                                     // groups of four MacroBlocks per MacroBlock row
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
     const int mbi = min(g0x + sub, p.mx - 1);                           // lanes of a missing MacroBlock shadow the row's last one
     const int mbx = mbi * kMB, mby = gy * kMB;
     const int mb = gy * p.mx + mbi;
-    const uint4 c0 = *reinterpret_cast<const uint4 *>(p.cur + (size_t)(mby + 2 * li) * p.W + mbx);
-    const uint4 c1 = *reinterpret_cast<const uint4 *>(p.cur + (size_t)(mby + 2 * li + 1) * p.W + mbx);
+    const uint4 c0 = *reinterpret_cast<const uint4 *>(p.cur + (size_t)(mby + li) * p.W + mbx);          // rows li and li + 8
+    const uint4 c1 = *reinterpret_cast<const uint4 *>(p.cur + (size_t)(mby + li + 8) * p.W + mbx);
     const bool staged = p.merange <= 16;
     const int wy0 = max(mby - 15, 0), wxa = max(g0x * kMB - 15, 0) & ~3;
     unsigned *win = s_win[warp];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
                 const int idx = lane + 32 * (h * kHalf + i);
                 const int r = idx / kWinWords, k = idx - r * kWinWords;
                 const int y = wy0 + r, x = wxa + 4 * k;
-                v[i] = (idx < kWinRows * kWinWords && y < p.H && x + 4 <= p.W) ? __ldg(reinterpret_cast<const unsigned *>(p.ref + (size_t)y * p.W + x)) : 0u;
+                v[i] = (idx < kWinRows * kWinWords && k < 25 && y < p.H && x + 4 <= p.W) ? __ldg(reinterpret_cast<const unsigned *>(p.ref + (size_t)y * p.W + x)) : 0u;
             }
 #pragma unroll
             for (int i = 0; i < kHalf; i++) {
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
             const int bx = cx3[0] - wxa;
             const int xw0 = bx >> 2;
             const unsigned sh = (unsigned)(bx & 3) * 8;
-            const int rb0 = (cy3[0] - wy0 + 2 * li) * kWinWords, rb1 = (cy3[1] - wy0 + 2 * li) * kWinWords, rb2 = (cy3[2] - wy0 + 2 * li) * kWinWords;
+            const int rb0 = (cy3[0] - wy0 + li) * kWinWords, rb1 = (cy3[1] - wy0 + li) * kWinWords, rb2 = (cy3[2] - wy0 + li) * kWinWords;
             if (step == 8) me_level_span<8>(win, kWinWords, rb0, rb1, rb2, xw0, sh, c0, c1, d);
             else if (step == 4) me_level_span<4>(win, kWinWords, rb0, rb1, rb2, xw0, sh, c0, c1, d);
             else if (step == 2) me_level_span<2>(win, kWinWords, rb0, rb1, rb2, xw0, sh, c0, c1, d);
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
             for (int j = 0; j < 3; j++) {
                 const int bx = cx3[j] - wxa;
                 xw[j] = bx >> 2; xs[j] = (unsigned)(bx & 3) * 8;
-                rb[j] = (cy3[j] - wy0 + 2 * li) * kWinWords;
+                rb[j] = (cy3[j] - wy0 + li) * kWinWords;
             }
 #pragma unroll
             for (int q = 0; q < 9; q++) {
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
                 const unsigned sh = xs[kSX[q]];
                 unsigned a[5], b[5];
 #pragma unroll
-                for (int k = 0; k < 5; k++) { a[k] = wp[k]; b[k] = wp[kWinWords + k]; }     // word 4 is inside the window row (<= 24)
+                for (int k = 0; k < 5; k++) { a[k] = wp[k]; b[k] = wp[8 * kWinWords + k]; }     // word 4 is inside the window row (<= 24)
                 unsigned acc = 0;
                 acc = sad4_acc(c0.x, __funnelshift_r(a[0], a[1], sh), acc);
                 acc = sad4_acc(c0.y, __funnelshift_r(a[1], a[2], sh), acc);
@@ -192,11 +192,11 @@ __global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
         } else {
 #pragma unroll
             for (int q = 0; q < 9; q++) {
-                const uint8_t *rp = p.ref + (size_t)(cy3[kSY[q]] + 2 * li) * p.W + cx3[kSX[q]];
+                const uint8_t *rp = p.ref + (size_t)(cy3[kSY[q]] + li) * p.W + cx3[kSX[q]];
                 const uintptr_t ad = (uintptr_t)rp;
                 const unsigned *wp = reinterpret_cast<const unsigned *>(ad & ~(uintptr_t)3);
                 const unsigned sh = (unsigned)(ad & 3) * 8;
-                const unsigned *wq = wp + (p.W >> 2);
+                const unsigned *wq = wp + 8 * (p.W >> 2);
                 unsigned a[5], b[5];
 #pragma unroll
                 for (int k = 0; k < 4; k++) { a[k] = __ldg(wp + k); b[k] = __ldg(wq + k); }

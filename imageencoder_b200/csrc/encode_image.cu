@@ -94,6 +94,15 @@ __device__ __forceinline__ void pack_tile_blocks(unsigned *outw, const short *s_
     }
 }
 
+// four bytes at any alignment from the two aligned words that hold them (the second is not touched when the address is aligned)
+__device__ __forceinline__ unsigned load_u8x4_unaligned(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
+    const unsigned k = (unsigned)(a & 3);
+    const unsigned w0 = __ldg(wp), w1 = k ? __ldg(wp + 1) : 0u;
+    return __byte_perm(w0, w1, 0x3210u + 0x1111u * k);
+}
+
 constexpr int kQueueCap = 128;        // guard-band fallback entries per tile handled by the CTA-wide queue
 
 // VAR: 0 scalar transform, 1 lean quantise, 2 packed transform + lean quantise (default); experimental, not yet run on a B200:
@@ -185,9 +194,10 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
         }
         if (FAST) {
             unsigned long long near = 0;
-            if (VAR >= 2 && !PF) {
+            if (VAR >= 2) {
             // variant 2: the whole block is loaded first, rows 2r and 2r+1 are converted and transformed as f32x2 pairs
             unsigned raw[N][N / 4];
+            unsigned rraw[PF ? N : 1];          // P-frames (N = 4): the four reference pixels of each row of the residual's source block
 #pragma unroll
             for (int y = 0; y < N; y++) {
                 const uint8_t *row = src + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N;
@@ -195,8 +205,9 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
                     const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row));
                     raw[y][0] = v.x; raw[y][N / 4 - 1] = v.y;
                 } else {
-                    raw[y][0] = __ldg(reinterpret_cast<const unsigned *>(row));
+                    raw[y][0] = PF ? *reinterpret_cast<const unsigned *>(row) : __ldg(reinterpret_cast<const unsigned *>(row));
                 }
+                if (PF) rraw[PF ? y : 0] = load_u8x4_unaligned(ref_i + (size_t)(ry + y) * p.pitch + rx);
             }
             float2 x2[NN / 2], y2[NN / 2];
 #pragma unroll
@@ -206,7 +217,14 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
                     // bytes -> floats by planting them in the mantissa of 2^23, then one packed subtraction of 2^23 + 128 (exact)
                     const float a = __uint_as_float(__byte_perm(raw[2 * r2][k >> 2], 0x4B000000u, 0x7650u | (unsigned)(k & 3)));
                     const float b = __uint_as_float(__byte_perm(raw[2 * r2 + 1][k >> 2], 0x4B000000u, 0x7650u | (unsigned)(k & 3)));
-                    x2[r2 * N + k] = lean::add2(make_float2(a, b), make_float2(-8388736.0f, -8388736.0f));
+                    if (!PF) {
+                        x2[r2 * N + k] = lean::add2(make_float2(a, b), make_float2(-8388736.0f, -8388736.0f));
+                    } else {
+                        // residual (Block.cpp:262) and the -128 of the second pass: (2^23 + c) - (2^23 + r) - 128, all exact
+                        const float ra = __uint_as_float(__byte_perm(rraw[PF ? 2 * r2 : 0], 0x4B000000u, 0x7650u | (unsigned)(k & 3)));
+                        const float rb = __uint_as_float(__byte_perm(rraw[PF ? 2 * r2 + 1 : 0], 0x4B000000u, 0x7650u | (unsigned)(k & 3)));
+                        x2[r2 * N + k] = lean::add2(lean::sub2(make_float2(a, b), make_float2(ra, rb)), make_float2(-128.0f, -128.0f));
+                    }
                 }
             lean::fdct2d_packed<N>(x2, y2);
             unsigned nlo, nhi;
@@ -453,7 +471,71 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
             const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
             const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
             const int kx = copy_coord_i[2 * mb] + (int)(bxi & 3) * 4, ky = copy_coord_i[2 * mb + 1] + (int)(byi & 3) * 4;
-            if (FAST && N == 4) {
+            if (FAST && N == 4 && VAR >= 2) {
+                // the same in packed f32x2 operations (lean::idct2d_packed, transform_fast.cuh); the prediction is added as
+                // x + (ref + 128) -- one rounding instead of two, inside the same bound; a pixel within the bound of an integer
+                // boundary takes the exact path below, so the result does not depend on how the fast value was rounded
+                float2 X2[NN / 2], P2[NN / 2];
+                float S = 0.f;
+                unsigned nzmask = 0;
+#pragma unroll
+                for (int r2 = 0; r2 < N / 2; r2++)
+#pragma unroll
+                    for (int v = 0; v < N; v++) {
+                        const int ua = (2 * r2) * N + v, ub = (2 * r2 + 1) * N + v;
+                        const int ca = cf[kZigzagInv4[ua]], cb = cf[kZigzagInv4[ub]];
+                        if (ca != 0) nzmask |= 1u << ua;
+                        if (cb != 0) nzmask |= 1u << ub;
+                        const float da = (float)ca * p.k2[ua], db = (float)cb * p.k2[ub];
+                        X2[r2 * N + v] = make_float2(da, db);
+                        S += fabsf(da) + fabsf(db);
+                    }
+                lean::idct2d_packed<4>(X2, P2);
+                const float delta = (32.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
+                const float hi_thr = (delta < 0.49f) ? 0.5f - delta : 0.f;
+                unsigned outw[4];
+                unsigned rpxw[4];
+                unsigned unsure = 0;
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    rpxw[y] = load_u8x4_unaligned(ref_i + (size_t)(ky + y) * p.pitch + kx);
+                    unsigned fl[4];
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const float ra = __uint_as_float(__byte_perm(rpxw[y], 0x4B000000u, 0x7650u | (unsigned)(2 * c)));
+                        const float rb = __uint_as_float(__byte_perm(rpxw[y], 0x4B000000u, 0x7650u | (unsigned)(2 * c + 1)));
+                        const float2 addend = lean::add2(make_float2(ra, rb), make_float2(-8388480.0f, -8388480.0f));      // ref + 128, exact
+                        unsigned un = 0;
+                        lean::pixel_pair_add<1u, 2u>(P2[y * 2 + c], addend, hi_thr, fl[2 * c], fl[2 * c + 1], un);
+                        unsure |= un << (y * 4 + 2 * c);
+                    }
+                    outw[y] = __byte_perm(__byte_perm(fl[0], fl[1], 0x0040), __byte_perm(fl[2], fl[3], 0x0040), 0x5410);
+                }
+                while (unsure) {
+                    const int ij = __ffs((int)unsure) - 1;
+                    unsure &= unsure - 1;
+                    double acc = 0.0;
+                    unsigned nz = nzmask;
+                    while (nz) {
+                        const int uv = __ffs((int)nz) - 1;
+                        nz &= nz - 1;
+                        const double d = __dmul_rn((double)(int)cf[tab->izz[uv]], p.quant.m[uv]);       // Block.cpp:165-168
+                        acc = __dadd_rn(acc, __dmul_rn(__ldg(tab->inv + uv * NN + ij), d));             // algo.cpp:352-355
+                    }
+                    const int yy = ij >> 2, kk = ij & 3;
+                    unsigned rrow = 0, orow = 0;
+#pragma unroll
+                    for (int r4 = 0; r4 < 4; r4++) if (r4 == yy) { rrow = rpxw[r4]; orow = outw[r4]; }
+                    const double rpx = (double)(int)((rrow >> (8 * kk)) & 0xffu);
+                    const unsigned px = clamp_trunc_u8(__dadd_rn(rpx, __dadd_rn(acc, 128.0)));           // Frame.cpp:218-242
+                    orow = (orow & ~(0xffu << (8 * kk))) | (px << (8 * kk));
+#pragma unroll
+                    for (int r4 = 0; r4 < 4; r4++) if (r4 == yy) outw[r4] = orow;
+                }
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+                    *reinterpret_cast<unsigned *>(cur_rw_i + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N) = outw[y];
+            } else if (FAST && N == 4) {
                 // fast reconstruction as in decode_blocks_fast_kernel<4, ADD>: FP32 inverse transform, and every pixel whose
                 // value lies within the block's error bound of an integer boundary is recomputed in the reference's exact
                 // order over the non-zero coefficients (transform bound: decode_image.cu)
@@ -998,8 +1080,13 @@ int launch_encode_tiles(int N, const EncodeParams &p, unsigned images, cudaStrea
     return IE_EINVAL;
 }
 
+// P-frame tiles: 2 = residual, transform, quantisation and reconstruction in packed f32x2 operations, reference rows read as
+// words (default); 0 = the scalar kernel it replaced
+std::atomic<int> g_pframe_variant{2};
 int launch_pframe_tiles(const EncodeParams &p, unsigned images, cudaStream_t stream) {
-    return g_exact_transform.load() ? launch_cfg<4, 4, true, false>(p, images, stream) : launch_cfg<4, 4, true, true>(p, images, stream);
+    if (g_exact_transform.load()) return launch_cfg<4, 4, true, false>(p, images, stream);
+    if (g_pframe_variant.load() == 2) return launch_cfg<4, 4, true, true, 2>(p, images, stream);
+    return launch_cfg<4, 4, true, true>(p, images, stream);
 }
 
 }  // namespace ie

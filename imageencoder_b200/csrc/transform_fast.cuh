@@ -480,6 +480,21 @@ IE_HD void pixel_pair(float2 x, float hi_thr, unsigned &fa, unsigned &fb, unsign
     fa = f2u(fm.x); fb = f2u(fm.y);
 }
 
+// the same with a per-pixel addend in place of the 128 (P-frames: reference pixel + 128, Block.cpp:110-119)
+template <unsigned BIT_A, unsigned BIT_B>
+IE_HD void pixel_pair_add(float2 x, float2 addend, float hi_thr, unsigned &fa, unsigned &fb, unsigned &unsure) {
+    const float2 v = add2(x, addend);
+    float2 u;
+    u.x = fminf(fmaxf(v.x, 0.5f), 255.5f);
+    u.y = fminf(fmaxf(v.y, 0.5f), 255.5f);
+    const float2 fm = fmac2_rd_one(u, 8388608.0f);
+    const float2 fl = add2(fm, make_float2(-8388608.0f, -8388608.0f));
+    const float2 g = add2(sub2(u, fl), make_float2(-0.5f, -0.5f));
+    or_if_near<BIT_A>(unsure, g.x, hi_thr);
+    or_if_near<BIT_B>(unsure, g.y, hi_thr);
+    fa = f2u(fm.x); fb = f2u(fm.y);
+}
+
 // row y of the block: N pixels -> N/4 output words (4 pixels each) + the row's bits of the `unsure` mask (bit = raster index)
 template <int N, int Y, int Q4>
 IE_HD unsigned pixel_quad(const float2 *P2, float hi_thr, unsigned &unsure_lo, unsigned &unsure_hi) {
