@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-source-line view of an ncu report (needs -lineinfo + --import-source on):
-     python tools/ncu_lines.py report.ncu-rep [top N]
+     python tools/ncu_lines.py report.ncu-rep [top N] [ncu import filters, e.g. --launch-skip 1 --launch-count 1]
    prints executed warp instructions and stall samples per file:line, largest first, and per file."""
 import csv
 import io
@@ -10,7 +10,8 @@ from collections import defaultdict
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+extra = sys.argv[3:]            # e.g. --launch-skip 1 --launch-count 1 to look at one kernel of the report
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + extra, capture_output=True, text=True).stdout
 cur = None
 hdr = None
 lines = {}
