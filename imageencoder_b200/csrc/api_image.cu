@@ -279,7 +279,7 @@ int parse_header(const uint8_t *bytes, size_t n, size_t start_bit, int N, Parsed
 }
 
 int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size_t start_bit, int N, const ParsedHeader &h,
-                     uint8_t *d_out, size_t out_cap, cudaStream_t stream) {
+                     uint8_t *d_out, size_t out_cap, cudaStream_t stream, uint8_t *host_out) {
     const uint32_t W = h.W, H = h.H;
     IE_TRY(check_dims(W, H, N));
     if ((uintptr_t)d_enc % 16) { set_error("encoded stream must be 16-byte aligned (and readable up to its size rounded up to 4)"); return IE_EINVAL; }
@@ -310,7 +310,26 @@ int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size
     p.out = d_out; p.out_stride = 0; p.pitch = W; p.err = s->d_err;
     IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, parse_scratch_bytes(enc_bytes, N)));
     IE_TRY(launch_parallel_parse(p, enc_bytes * 8, s->d_parse, stream));
-    return launch_decode_blocks(p, 1, stream);
+    if (!host_out) return launch_decode_blocks(p, 1, stream);
+    // host entry point: stripes of whole block rows (>= 4 MiB of pixels); stripe i's pixels travel to the host on stream_out
+    // while stripe i + 1 is decoded -- the read-back (2.4x the stream's size on config 2) is what the call's time is made of
+    IE_TRY(session_ensure_pipeline(s));
+    const uint32_t block_rows = H / N;
+    const size_t npx = (size_t)W * H;
+    uint32_t stripes = (uint32_t)std::min<size_t>(ie_session::kMaxStripes, std::max<size_t>(1, npx / ((size_t)4 << 20)));
+    stripes = std::min(stripes, block_rows);
+    const uint32_t rows_per = (block_rows + stripes - 1) / stripes;
+    stripes = (block_rows + rows_per - 1) / rows_per;
+    for (uint32_t i = 0; i < stripes; i++) {
+        const uint32_t r0 = i * rows_per, r1 = std::min(block_rows, r0 + rows_per);
+        p.block_base = r0 * (W / N); p.block_end = r1 * (W / N);
+        IE_TRY(launch_decode_blocks(p, 1, stream));
+        IE_CUDA(cudaEventRecord(s->ev_done[i], stream));
+        IE_CUDA(cudaStreamWaitEvent(s->stream_out, s->ev_done[i], 0));
+        const size_t o = (size_t)r0 * N * W, n = (size_t)(r1 - r0) * N * W;
+        IE_CUDA(cudaMemcpyAsync(host_out + o, d_out + o, n, cudaMemcpyDeviceToHost, s->stream_out));
+    }
+    return IE_OK;
 }
 
 // ---- cached sessions for the host-buffer entry points -----------------------------------------------------------
@@ -837,21 +856,24 @@ int ie_decode_image(const uint8_t *enc, size_t enc_bytes, uint32_t N, uint8_t *r
     // decode straight into a device buffer sized after the header is known
     uint8_t hb[160];
     const size_t n = std::min(sizeof hb, plain_bytes);
-    IE_CUDA(cudaMemcpyAsync(hb, d_plain, n, cudaMemcpyDeviceToHost, st));
-    IE_CUDA(cudaStreamSynchronize(st));
     ParsedHeader ph;
-    parse_header(hb, n, (size_t)start_bit, (int)N, ph, 0);
+    if (d_plain == s->d_in) {
+        parse_header(enc, n, (size_t)start_bit, (int)N, ph, 0);     // plain stream: the header is in the caller's buffer
+    } else {
+        IE_CUDA(cudaMemcpyAsync(hb, d_plain, n, cudaMemcpyDeviceToHost, st));
+        IE_CUDA(cudaStreamSynchronize(st));
+        parse_header(hb, n, (size_t)start_bit, (int)N, ph, 0);
+    }
     w = ph.W; h = ph.H;
     if (W) *W = w;
     if (H) *H = h;
     IE_TRY(check_dims(w, h, N));
     if ((size_t)w * h > raw_cap) { set_error("raw_out too small"); return IE_ENOSPC; }
     IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, (size_t)w * h));
-    IE_TRY(decode_image_dev(s, d_plain, plain_bytes, (size_t)start_bit, (int)N, ph, s->d_out, s->d_out_cap, st));
-    IE_TRY(read_err_flag(s, st));
-    IE_CUDA(cudaMemcpyAsync(raw_out, s->d_out, (size_t)w * h, cudaMemcpyDeviceToHost, st));
-    IE_CUDA(cudaStreamSynchronize(st));
-    return IE_OK;
+    IE_TRY(decode_image_dev(s, d_plain, plain_bytes, (size_t)start_bit, (int)N, ph, s->d_out, s->d_out_cap, st, raw_out));
+    const int rc = read_err_flag(s, st);                           // synchronises st: every stripe has been decoded
+    IE_CUDA(cudaStreamSynchronize(s->stream_out));                 // ... and has arrived
+    return rc;
 }
 
 }  // extern "C"

@@ -26,8 +26,9 @@ int encode_images_dev(ie_session *s, const uint8_t *d_raw, size_t img_stride, un
                       uint8_t *d_out, size_t out_stride, size_t out_cap, cudaStream_t stream, int append = 0, uint32_t header_H = 0, int split = 0,
                       uint64_t *d_out_bits = nullptr);
 int session_ensure_pipeline(ie_session *s);
+// host_out != NULL: the decoded pixels are also copied to that (host) buffer, stripe by stripe on the session's stream_out
 int decode_image_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, size_t start_bit, int N, const ParsedHeader &h,
-                     uint8_t *d_out, size_t out_cap, cudaStream_t stream);
+                     uint8_t *d_out, size_t out_cap, cudaStream_t stream, uint8_t *host_out = nullptr);
 int read_err_flag(ie_session *s, cudaStream_t stream);
 // Exclusive use of a cached session for the duration of one host-buffer call (api_image.cu).
 class SessionLease {

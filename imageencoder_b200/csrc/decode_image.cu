@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecodeParams p
     constexpr int STRIDE = NN + 2;
     __shared__ short s_coef[256 * STRIDE];
     const unsigned img = blockIdx.y;
-    const unsigned gb = blockIdx.x * 256 + threadIdx.x;
-    if (gb >= p.nblocks) return;
+    const unsigned gb = p.block_base + blockIdx.x * 256 + threadIdx.x;
+    if (gb >= (p.block_end ? p.block_end : p.nblocks)) return;
     const uint8_t *s = p.enc + (size_t)img * p.enc_stride;
     const unsigned long long total = p.enc_bits[img];
     const unsigned long long *off = p.block_off + (size_t)img * (p.nblocks + 1);
@@ -177,14 +177,15 @@ __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
     __shared__ short s_coef[128 * STRIDE];
     __shared__ __align__(16) unsigned s_bits[kStage];
     const unsigned img = blockIdx.y;
-    const unsigned first = blockIdx.x * 128;
+    const unsigned first = p.block_base + blockIdx.x * 128;
     const unsigned gb = first + threadIdx.x;
+    const unsigned range_end = p.block_end ? p.block_end : p.nblocks;
     const uint8_t *s = p.enc + (size_t)img * p.enc_stride;
     const unsigned long long total = p.enc_bits[img];
     const unsigned long long *off = p.block_off + (size_t)img * (p.nblocks + 1);
     const BlockTables *tab = p.tab;
-    const StagedStream st = stage_stream(s_bits, kStage, s, total, off[first], off[min(first + 128u, p.nblocks)] + kMaxBlockBits);
-    if (gb >= p.nblocks) return;
+    const StagedStream st = stage_stream(s_bits, kStage, s, total, off[first], off[min(first + 128u, range_end)] + kMaxBlockBits);
+    if (gb >= range_end) return;
 
     // ---- fields (Block.cpp:441-472) -------------------------------------------------------------------------
     // a valid chain keeps the CTA's 128 blocks within 128 maximal blocks of its first one.  A malformed stream does not: once
@@ -327,7 +328,8 @@ int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t str
 
 int launch_decode_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream) {
     if (!g_exact_transform.load()) {
-        dim3 gridf((p.nblocks + 127) / 128, images);
+        const unsigned nrange = (p.block_end ? p.block_end : p.nblocks) - p.block_base;
+        dim3 gridf((nrange + 127) / 128, images);
         const bool lean_dec = g_decode_variant.load() == 1;
         if (p.N == 8 && lean_dec) IE_CUDA(launch_pdl(decode_blocks_lean_kernel<8>, gridf, dim3(128), 0, stream, p));
         else if (p.N == 4 && !p.add_mode && lean_dec) IE_CUDA(launch_pdl(decode_blocks_lean_kernel<4>, gridf, dim3(128), 0, stream, p));
@@ -339,7 +341,7 @@ int launch_decode_blocks(const DecodeParams &p, unsigned images, cudaStream_t st
         IE_CUDA(cudaGetLastError());
         return IE_OK;
     }
-    dim3 grid((p.nblocks + 255) / 256, images);
+    dim3 grid(((p.block_end ? p.block_end : p.nblocks) - p.block_base + 255) / 256, images);
     if (p.N == 8) decode_blocks_kernel<8, false><<<grid, 256, 0, stream>>>(p);
     else if (p.N == 4 && p.add_mode) decode_blocks_kernel<4, true><<<grid, 256, 0, stream>>>(p);
     else if (p.N == 4) decode_blocks_kernel<4, false><<<grid, 256, 0, stream>>>(p);

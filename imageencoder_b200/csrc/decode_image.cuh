@@ -24,6 +24,9 @@ struct DecodeParams {
     unsigned long long *cursor;             // device; NULL for images
     unsigned skip_bits;                     // bits between the cursor and the first block (the mvec section of a P-frame)
     int add_mode;                           // 1: pixel = (u8)clamp(cur + (X + 128))   (Block.cpp:110-119, P-frames)
+    // launch_decode_blocks decodes blocks [block_base, block_end) of every image; block_end = 0 means nblocks (stripes of the
+    // host entry point: a stripe's pixels leave for the host while the next stripe is decoded)
+    unsigned block_base, block_end;
 };
 
 // ---- whole-stream video parse (parse.cu) ----
