@@ -47,6 +47,9 @@ SIGNATURES = {
     "ie_decode_image_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, C.c_size_t, _u32p, _u32p, _vp]),
     "ie_parse_image_header": (C.c_int, [_vp, C.c_size_t, C.c_uint64, C.c_uint32, _vp]),
     "ie_decode_image_with_header_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _vp, C.c_size_t, _vp]),
+    "ie_decode_shard_spec_bytes": (C.c_size_t, [C.c_size_t, C.c_uint32, C.c_uint32, _szp]),
+    "ie_decode_image_shard_begin_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "ie_decode_image_shard_end_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_uint32, C.c_uint32, _vp, C.c_size_t, _vp]),
     "ie_decode_images_dev": (C.c_int, [_vp, _vp, C.c_size_t, _szp, C.c_uint32, C.c_uint64, _vp, C.c_size_t, _u32p, _u32p, _vp]),
     "ie_huffman_encode_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _szp, _vp]),
     "ie_huffman_decode_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _szp, _u64p, _vp]),

@@ -834,6 +834,76 @@ int ie_decode_image_with_header_dev(ie_session *s, const ie_image_header *hdr, c
     return decode_image_dev(s, d_enc, enc_bytes, 0, (int)s->N, h, d_raw_out, raw_cap, (cudaStream_t)stream);
 }
 
+
+// ---- sharded decode of one stream: every rank holds the stream, walks 1 / parts of it, decodes its own block rows ----------
+namespace ie {
+static int shard_decode_params(ie_session *s, const ie_image_header *hdr, const uint8_t *d_enc, size_t enc_bytes, DecodeParams &p, cudaStream_t st) {
+    const int N = (int)s->N;
+    const uint32_t W = hdr->width, H = hdr->height;
+    IE_TRY(check_dims(W, H, N));
+    if ((uintptr_t)d_enc % 16) { set_error("encoded stream must be 16-byte aligned (and readable up to its size rounded up to 4)"); return IE_EINVAL; }
+    const unsigned nblocks = (W / N) * (H / N);
+    IE_TRY(session_ensure_scan(s, 1, 1));
+    IE_TRY(session_ensure_err(s));
+    const size_t need_off = ((size_t)nblocks + 1) * sizeof(unsigned long long) + 64;
+    if (s->block_off_cap < need_off) {
+        if (s->d_block_off) IE_CUDA(cudaFree(s->d_block_off));
+        s->d_block_off = nullptr; s->block_off_cap = 0;
+        IE_CUDA(cudaMalloc(&s->d_block_off, need_off));
+        s->block_off_cap = need_off;
+    }
+    if (!s->h_pinned) { set_error("session without pinned staging"); return IE_EINVAL; }
+    unsigned long long *consts = s->h_pinned + 16;                    // pinned: the copy below is asynchronous
+    consts[0] = (unsigned long long)enc_bytes * 8ull; consts[1] = (unsigned long long)hdr->first_block_bit;
+    unsigned long long *d_consts = s->d_block_off + (nblocks + 1);
+    IE_CUDA(cudaMemcpyAsync(d_consts, consts, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    memset(&p, 0, sizeof p);
+    p.enc = d_enc; p.enc_stride = 0; p.enc_bits = d_consts; p.start_bit = d_consts + 1;
+    p.block_off = s->d_block_off; p.nblocks = nblocks; p.bx = W / N; p.N = N; p.use_rle = (int)hdr->use_rle;
+    make_quant(p.quant, hdr->quant, N);
+    make_k2(p.k2, hdr->quant, N);
+    p.tab = (N == 8) ? s->dev->d_t8 : s->dev->d_t4;
+    p.pitch = W; p.err = s->d_err;
+    IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, parse_scratch_bytes(enc_bytes, N)));
+    return IE_OK;
+}
+}  // namespace ie
+
+size_t ie_decode_shard_spec_bytes(size_t enc_bytes, uint32_t N, uint32_t parts, size_t *chunk_bytes) {
+    if ((N != 4 && N != 8) || parts == 0) return 0;
+    const ShardedParseGeom g = sharded_parse_geom(enc_bytes, (int)N, parts);
+    if (chunk_bytes) *chunk_bytes = g.chunk_bytes;
+    return g.spec_bytes;
+}
+
+int ie_decode_image_shard_begin_dev(ie_session *s, const ie_image_header *hdr, const uint8_t *d_enc, size_t enc_bytes, uint32_t part,
+                                    uint32_t parts, uint8_t *d_spec, void *stream) {
+    if (!s || !hdr || !d_enc || !d_spec) { set_error("NULL argument"); return IE_EINVAL; }
+    if (hdr->block != s->N) { set_error("header block size differs from the session's"); return IE_EINVAL; }
+    if (parts == 0 || parts > 64 || part >= parts) { set_error("part / parts out of range (1 .. 64 parts)"); return IE_EINVAL; }
+    DecodeParams p;
+    IE_TRY(shard_decode_params(s, hdr, d_enc, enc_bytes, p, (cudaStream_t)stream));
+    return launch_parse_walk_part(p, enc_bytes * 8, s->d_parse, d_spec, part, parts, (cudaStream_t)stream);
+}
+
+int ie_decode_image_shard_end_dev(ie_session *s, const ie_image_header *hdr, const uint8_t *d_enc, size_t enc_bytes, uint32_t parts,
+                                  uint8_t *d_spec, uint32_t block_row0, uint32_t block_row1, uint8_t *d_rows_out, size_t out_cap, void *stream) {
+    if (!s || !hdr || !d_enc || !d_spec || !d_rows_out) { set_error("NULL argument"); return IE_EINVAL; }
+    if (hdr->block != s->N) { set_error("header block size differs from the session's"); return IE_EINVAL; }
+    if (parts == 0 || parts > 64) { set_error("parts out of range (1 .. 64)"); return IE_EINVAL; }
+    const uint32_t N = s->N;
+    if (block_row0 >= block_row1 || block_row1 > hdr->height / N) { set_error("block rows out of range"); return IE_EINVAL; }
+    if ((size_t)(block_row1 - block_row0) * N * hdr->width > out_cap) { set_error("decoded rows do not fit the output buffer"); return IE_ENOSPC; }
+    DecodeParams p;
+    cudaStream_t st = (cudaStream_t)stream;
+    IE_TRY(shard_decode_params(s, hdr, d_enc, enc_bytes, p, st));
+    p.block_base = block_row0 * (hdr->width / N); p.block_end = block_row1 * (hdr->width / N);
+    IE_TRY(launch_parse_finish_range(p, enc_bytes * 8, s->d_parse, d_spec, parts, p.block_base, p.block_end, st));
+    // the kernels address pixels by absolute block row: the band's buffer starts at row block_row0 * N
+    p.out = d_rows_out - (size_t)block_row0 * N * hdr->width;
+    return launch_decode_blocks(p, 1, st);
+}
+
 int ie_decode_image(const uint8_t *enc, size_t enc_bytes, uint32_t N, uint8_t *raw_out, size_t raw_cap, uint32_t *W, uint32_t *H) {
     if (!enc || !raw_out || enc_bytes == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
     if (N != 4 && N != 8) { set_error("block size must be 4 or 8"); return IE_EINVAL; }

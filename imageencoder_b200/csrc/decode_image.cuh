@@ -60,6 +60,14 @@ int launch_video_parse(const uint8_t *d_enc, const unsigned long long *d_enc_bit
 int launch_video_emit(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned first_frame, unsigned nimg, unsigned long long *block_off,
                       cudaStream_t stream);
 
+// ---- sharded decode of one image stream (parse.cu) ----
+struct ShardedParseGeom { unsigned ctas_per_part, groups_per_part; size_t chunk_bytes, spec_bytes; };
+ShardedParseGeom sharded_parse_geom(size_t enc_bytes, int N, unsigned parts);
+int launch_parse_walk_part(const DecodeParams &d, size_t span_bits, uint8_t *scratch, uint8_t *d_spec, unsigned part, unsigned parts,
+                           cudaStream_t stream);
+int launch_parse_finish_range(const DecodeParams &d, size_t span_bits, uint8_t *scratch, uint8_t *d_spec, unsigned parts, unsigned lo, unsigned hi,
+                              cudaStream_t stream);
+
 int launch_parse_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream);
 int launch_decode_blocks(const DecodeParams &p, unsigned images, cudaStream_t stream);
 size_t parse_scratch_bytes(size_t enc_bytes, int N);

@@ -764,6 +764,15 @@ static int launch_byte_histogram(const uint8_t *d_in, size_t n, unsigned *d_hist
     return IE_OK;
 }
 
+// pinned staging of the stage: [0, 2048) dictionary header | HuffCodes | first bit (u64) | pad | first[256] u64 + hist[256] u32 as
+// they come back from the device | stream bits (u64) + error flag
+constexpr size_t kHuffPinnedRecv = (2048 + sizeof(HuffCodes) + 16 + 63) / 64 * 64;
+constexpr size_t kHuffPinned = kHuffPinnedRecv + 256 * 8 + 256 * 4 + 64;
+static int ensure_huff_pinned(ie_session *s) {
+    if (!s->h_huff) IE_CUDA(cudaMallocHost(&s->h_huff, kHuffPinned));
+    return IE_OK;
+}
+
 // Dictionary from a (global) histogram, then the scan-pack of `n` bytes behind it (write_dict) or from bit 0 (a later shard of
 // a multi-GPU stream).  Leaves the stream's bit count in s->d_counter[0].  The scratch must be ensured by the caller.
 static int huffman_pack_dev(ie_session *s, const uint8_t *d_in, size_t n, const unsigned *hist, const unsigned long long *first,
@@ -771,8 +780,7 @@ static int huffman_pack_dev(ie_session *s, const uint8_t *d_in, size_t n, const 
     HuffCodes *d_codes = reinterpret_cast<HuffCodes *>(s->d_scratch + 256 * 8 + 256 * 4);
     // dictionary header, codes and the stream's first bit travel from pinned memory the session owns: the copies are truly
     // asynchronous and nothing on this frame has to outlive them (no stream synchronisation in here)
-    constexpr size_t kHuffPinned = 2048 + sizeof(HuffCodes) + 16;
-    if (!s->h_huff) IE_CUDA(cudaMallocHost(&s->h_huff, kHuffPinned));
+    IE_TRY(ensure_huff_pinned(s));
     HuffCodes &codes = *reinterpret_cast<HuffCodes *>(s->h_huff + 2048);
     unsigned long long &hb = *reinterpret_cast<unsigned long long *>(s->h_huff + 2048 + sizeof(HuffCodes));
     HostBitWriter hdr;
@@ -854,16 +862,27 @@ int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
     unsigned *d_first_cta = reinterpret_cast<unsigned *>(s->d_scratch + 256 * 8 + 256 * 4 + sizeof(HuffCodes) + 64);
     IE_TRY(session_ensure_err(s));
     IE_TRY(launch_byte_histogram(d_in, n, d_hist, d_first, d_first_cta, s->dev->sm_count, st));
-    unsigned hist[256];
-    unsigned long long first[256];
-    IE_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, st));
-    IE_CUDA(cudaMemcpyAsync(first, d_first, sizeof first, cudaMemcpyDeviceToHost, st));
+    // first[] and hist[] are neighbours in the scratch: one copy into pinned memory, one synchronisation
+    IE_TRY(ensure_huff_pinned(s));
+    const unsigned long long *first = reinterpret_cast<const unsigned long long *>(s->h_huff + kHuffPinnedRecv);
+    const unsigned *hist = reinterpret_cast<const unsigned *>(s->h_huff + kHuffPinnedRecv + 256 * 8);
+    IE_CUDA(cudaMemcpyAsync(s->h_huff + kHuffPinnedRecv, d_first, 256 * 8 + 256 * 4, cudaMemcpyDeviceToHost, st));
     IE_CUDA(cudaStreamSynchronize(st));
 
     IE_TRY(huffman_pack_dev(s, d_in, n, hist, first, 1, d_out, out_cap, st));
-    IE_CUDA(cudaMemcpyAsync(s->h_pinned, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    IE_TRY(read_err_flag(s, st));
-    size_t total = (size_t)((s->h_pinned[0] + 7) / 8);
+    // the stream's size and the error flag come back together
+    unsigned long long *h_bits = reinterpret_cast<unsigned long long *>(s->h_huff + kHuffPinnedRecv + 256 * 8 + 256 * 4);
+    int *h_err = reinterpret_cast<int *>(h_bits + 1);
+    IE_CUDA(cudaMemcpyAsync(h_bits, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaMemcpyAsync(h_err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    IE_CUDA(cudaStreamSynchronize(st));
+    if (*h_err != 0) {
+        const int e = *h_err;
+        IE_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), st));
+        set_error(e == IE_ENOSPC ? "output buffer too small" : "device-side error");
+        return e;
+    }
+    size_t total = (size_t)((*h_bits + 7) / 8);
     if (n < total) {                                                       // Huffman.cpp:329-341
         total = n + 1;
         if (out_cap < (total + 3) / 4 * 4) { set_error("output buffer too small"); return IE_ENOSPC; }

@@ -60,6 +60,9 @@ struct ParseParams {
     unsigned *spec_flags;                   // [0] CTA ticket of parse_spec_check, [1] spec_ok, [2] unused, [3] first inconsistent group
     unsigned *walk_base;                    // [nwalk] block count per walk CTA, then (in place) its exclusive scan
     int force_exact;                        // ie_set_option("parse_variant", 1): ignore the speculation, take the exact path
+    // sharded decode of one stream (ie_decode_image_shard_*): a rank's walk launch covers the CTAs from walk_cta0 on; the
+    // emit kernel only has to produce block_off[emit_lo .. emit_hi] (emit_hi = 0: everything)
+    unsigned walk_cta0, emit_lo, emit_hi;
 };
 
 __device__ __forceinline__ unsigned parse_read_bits(const uint8_t *__restrict__ s, unsigned long long total_bits, unsigned long long p, int n) {
@@ -253,12 +256,13 @@ __global__ void __launch_bounds__(TH) parse_spec_walk(const ParseParams p) {
     pdl_wait();
     extern __shared__ __align__(16) unsigned s_stage[];
     __shared__ unsigned s_entry[TH], s_exit[TH];
-    const unsigned g = blockIdx.x * TH + threadIdx.x;
-    if (g == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; p.spec_flags[2] = 0; p.spec_flags[3] = 0xFFFFFFFFu; *p.cursor_next = ~0ull; }
+    const unsigned cta = blockIdx.x + p.walk_cta0;
+    const unsigned g = cta * TH + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { p.spec_flags[0] = 0; p.spec_flags[1] = 0; p.spec_flags[2] = 0; p.spec_flags[3] = 0xFFFFFFFFu; *p.cursor_next = ~0ull; }
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start + p.skip_bits;
     constexpr unsigned lead = SpecCfg<GB, TH>::kLead;
-    const unsigned long long c_start = B0 + (unsigned long long)blockIdx.x * TH * GB;
+    const unsigned long long c_start = B0 + (unsigned long long)cta * TH * GB;
     const unsigned long long c_first = (c_start < B0 + lead) ? B0 : c_start - lead;
     const unsigned long long c_end = min(total, c_start + (unsigned long long)TH * GB);
     if (c_first >= total) {                                 // uniform: nothing of the stream in this CTA's range
@@ -427,6 +431,7 @@ __global__ void __launch_bounds__(TH) parse_spec_emit(const ParseParams p) {
     if (g >= p.nspec || g >= p.spec_flags[3]) return;        // unverified tail: holds no block of this stream
     const unsigned entry = p.spec_entry[g].x;
     if (entry == kDead) return;
+    if (p.emit_hi && (idx > p.emit_hi || idx + cnt < p.emit_lo)) return;      // sharded decode: none of this rank's blocks
     const unsigned first_idx = idx;
     const unsigned long long g_start = B0 + (unsigned long long)g * GB;
     const unsigned g_end_rel = (unsigned)(g_start - st.base) + GB;
@@ -524,7 +529,8 @@ size_t parse_scratch_bytes(size_t enc_bytes, int N) {
     unsigned E, ng, ns;
     parse_sizes(enc_bytes * 8, N, E, ng, ns);
     const size_t nspec = (N == 8) ? spec_groups(enc_bytes * 8, N) : (enc_bytes * 8 + 511) / 512 + 1;      // the finest grid any setting uses
-    return ((size_t)ng * E + (size_t)ns * E + ns + ng + 8) * sizeof(uint2) + nspec * 2 * sizeof(uint2) + (nspec / 64 + 16) * sizeof(unsigned) + 256;
+    // (+ slack for the padded grid of a sharded decode: up to 64 parts x one walk CTA)
+    return ((size_t)ng * E + (size_t)ns * E + ns + ng + 8) * sizeof(uint2) + nspec * 2 * sizeof(uint2) + (nspec / 64 + 16 + 64 * 256) * sizeof(unsigned) + 256;
 }
 
 template <int GB, int TH>
@@ -545,9 +551,8 @@ static int launch_spec(const ParseParams &p, cudaStream_t stream) {
 // `span_bits`: how far past the first block the chain is followed (the whole stream for images; a per-frame budget for
 // video, where the caller retries with a larger span if the cursor did not move).  `scratch`: parse_scratch_bytes(bytes
 // of the whole stream) bytes, 16-aligned.
-int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scratch, cudaStream_t stream) {
-    ParseParams p;
-    unsigned E;
+static void parse_setup(const DecodeParams &d, size_t span_bits, uint8_t *scratch, ParseParams &p, unsigned &E) {
+    memset(&p, 0, sizeof p);
     parse_sizes(span_bits, d.N, E, p.ngroups, p.nsuper);
     p.enc = d.enc; p.enc_bits = d.enc_bits;
     p.start = d.cursor ? d.cursor : d.start_bit;
@@ -569,6 +574,12 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     p.cursor_out = d.cursor;
     p.err = d.err;
     p.force_exact = g_parse_variant.load() == 1;
+}
+
+int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scratch, cudaStream_t stream) {
+    ParseParams p;
+    unsigned E;
+    parse_setup(d, span_bits, scratch, p, E);
     const size_t smem = (size_t)E * (4 + 4 + 2 + 1) + 16;
     static const bool dbg = getenv("IE_DEBUG_SYNC") != nullptr;
 #define IE_DBG_STEP(name) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(stream); if (e_ != cudaSuccess) { fprintf(stderr, "[ie] %s failed: %s\n", name, cudaGetErrorString(e_)); return cuda_fail(e_, name, __FILE__, __LINE__); } } } while (0)
@@ -595,6 +606,97 @@ int launch_parallel_parse(const DecodeParams &d, size_t span_bits, uint8_t *scra
     return IE_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Sharded decode of ONE image stream (ImageDecoder.cpp:88-112): every rank holds the stream; rank `part` walks only
+// its share of the speculative grid (the walk is the expensive step of the parse), the ranks all-gather the per-group results
+// (16 bytes per group: the caller's collective, in place on d_spec), and every rank then verifies the seams, counts, and
+// emits the offsets of its own block rows only.  d_spec = [entry: parts x chunk][exit: parts x chunk].
+// ---------------------------------------------------------------------------------------------------------
+ShardedParseGeom sharded_parse_geom(size_t enc_bytes, int N, unsigned parts) {
+    ShardedParseGeom g;
+    const size_t gb = (N == 8) ? 8192 : 2048, th = (N == 8) ? 64 : 256;
+    const size_t nspec = (enc_bytes * 8 + gb - 1) / gb + 1;
+    const size_t nwalk = (nspec + th - 1) / th;
+    g.ctas_per_part = (unsigned)((nwalk + parts - 1) / parts);
+    g.groups_per_part = g.ctas_per_part * (unsigned)th;
+    g.chunk_bytes = (size_t)g.groups_per_part * sizeof(uint2);
+    g.spec_bytes = 2 * (size_t)parts * g.chunk_bytes;
+    return g;
+}
+
+__global__ void fill_off_kernel(unsigned long long *off, unsigned n, const unsigned long long *value) {
+    pdl_wait();
+    const unsigned long long v = *value;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) off[i] = v;
+}
+
+template <int GB, int TH>
+static int launch_walk_part(ParseParams &p, const ShardedParseGeom &g, unsigned part, cudaStream_t stream) {
+    const size_t stage_bytes = (size_t)SpecCfg<GB, TH>::kStageWords * sizeof(unsigned);
+    IE_CUDA(cudaFuncSetAttribute(parse_spec_walk<GB, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    p.walk_cta0 = part * g.ctas_per_part;
+    IE_CUDA(launch_pdl(parse_spec_walk<GB, TH>, dim3(g.ctas_per_part), dim3(TH), stage_bytes, stream, p));
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
+template <int GB, int TH>
+static int launch_finish(const ParseParams &p, cudaStream_t stream) {
+    const unsigned nwalk = (p.nspec + TH - 1) / TH;
+    const size_t stage_bytes = (size_t)SpecCfg<GB, TH>::kStageWords * sizeof(unsigned);
+    IE_CUDA(cudaFuncSetAttribute(parse_spec_emit<GB, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    IE_CUDA(launch_pdl(parse_spec_boundary<GB, TH>, dim3((nwalk + 63) / 64), dim3(64), 0, stream, p));
+    IE_CUDA(launch_pdl(parse_spec_check<GB, TH>, dim3(nwalk), dim3(TH), 0, stream, p));
+    IE_CUDA(launch_pdl(parse_spec_emit<GB, TH>, dim3(nwalk), dim3(TH), stage_bytes, stream, p));
+    count_launch(3);
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
+static void sharded_setup(const DecodeParams &d, size_t span_bits, uint8_t *scratch, uint8_t *d_spec, unsigned parts, ParseParams &p, unsigned &E,
+                          ShardedParseGeom &g) {
+    parse_setup(d, span_bits, scratch, p, E);
+    g = sharded_parse_geom(span_bits / 8, d.N, parts);
+    p.nspec = parts * g.groups_per_part;
+    p.spec_entry = reinterpret_cast<uint2 *>(d_spec);
+    p.spec_exit = reinterpret_cast<uint2 *>(d_spec + (size_t)parts * g.chunk_bytes);
+}
+
+int launch_parse_walk_part(const DecodeParams &d, size_t span_bits, uint8_t *scratch, uint8_t *d_spec, unsigned part, unsigned parts,
+                           cudaStream_t stream) {
+    ParseParams p;
+    unsigned E;
+    ShardedParseGeom g;
+    sharded_setup(d, span_bits, scratch, d_spec, parts, p, E, g);
+    if ((uintptr_t)d.enc % 16 || (uintptr_t)d_spec % 16) { set_error("stream and spec buffers must be 16-byte aligned on the device"); return IE_EINVAL; }
+    if (d.N == 8) return launch_walk_part<8192, 64>(p, g, part, stream);
+    return launch_walk_part<2048, 256>(p, g, part, stream);
+}
+
+// after the all-gather of d_spec: seams, counts, block_off[lo .. hi] (hi inclusive), exact path if the speculation failed
+int launch_parse_finish_range(const DecodeParams &d, size_t span_bits, uint8_t *scratch, uint8_t *d_spec, unsigned parts, unsigned lo, unsigned hi,
+                              cudaStream_t stream) {
+    ParseParams p;
+    unsigned E;
+    ShardedParseGeom g;
+    sharded_setup(d, span_bits, scratch, d_spec, parts, p, E, g);
+    p.emit_lo = lo; p.emit_hi = hi;
+    // blocks the chain never reaches (a truncated stream) start and end at the end of the stream (BitStream.cpp:17-20)
+    IE_CUDA(launch_pdl(fill_off_kernel, dim3(64), dim3(256), 0, stream, p.block_off + lo, hi - lo + 1, p.enc_bits));
+    count_launch();
+    if (d.N == 8) IE_TRY((launch_finish<8192, 64>(p, stream)));
+    else IE_TRY((launch_finish<2048, 256>(p, stream)));
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    IE_CUDA(cudaFuncSetAttribute(parse_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
+    const size_t smem = (size_t)E * (4 + 4 + 2 + 1) + 16;
+    IE_CUDA(launch_pdl(parse_exact_kernel, dim3(2u * (unsigned)sms), dim3(64), smem, stream, p));
+    count_launch();
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Whole-stream parse of a video (Frame.cpp:47-127, VideoDecoder.cpp:33-62).  The reference reads the frames strictly in

@@ -108,6 +108,24 @@ def decode_image_with_header_dev(s: Session, hdr: ImageHeader, d_enc: torch.Tens
     check(lib().ie_decode_image_with_header_dev(s.h, C.byref(hdr), _dp(d_enc), enc_bytes, _dp(d_raw_out), d_raw_out.numel(), _stream()))
 
 
+def decode_shard_spec_bytes(enc_bytes: int, block: int, parts: int) -> tuple[int, int]:
+    """(bytes of the spec buffer of a sharded decode, bytes of one part's chunk in either half of it)"""
+    chunk = C.c_size_t(0)
+    total = int(lib().ie_decode_shard_spec_bytes(enc_bytes, block, parts, C.byref(chunk)))
+    return total, int(chunk.value)
+
+
+def decode_image_shard_begin_dev(s: Session, hdr: ImageHeader, d_enc: torch.Tensor, enc_bytes: int, part: int, parts: int,
+                                 d_spec: torch.Tensor) -> None:
+    check(lib().ie_decode_image_shard_begin_dev(s.h, C.byref(hdr), _dp(d_enc), enc_bytes, part, parts, _dp(d_spec), _stream()))
+
+
+def decode_image_shard_end_dev(s: Session, hdr: ImageHeader, d_enc: torch.Tensor, enc_bytes: int, parts: int, d_spec: torch.Tensor,
+                               block_row0: int, block_row1: int, d_rows_out: torch.Tensor) -> None:
+    check(lib().ie_decode_image_shard_end_dev(s.h, C.byref(hdr), _dp(d_enc), enc_bytes, parts, _dp(d_spec), block_row0, block_row1,
+                                              _dp(d_rows_out), d_rows_out.numel(), _stream()))
+
+
 def decode_images_dev(s: Session, d_encs: torch.Tensor, enc_stride: int, enc_bytes, d_raws_out: torch.Tensor, raw_stride: int,
                       start_bit: int = 1):
     """Batch decode of device-resident plain streams on the session's worker streams; returns the (W, H) lists."""

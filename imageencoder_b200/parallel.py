@@ -390,6 +390,61 @@ def sharded_image_encode_huffman(enc: ShardedImageEncoder, stage: ShardedHuffman
     return hpl, stage.d_out[: hpl[rank].nbytes]
 
 
+class ShardedImageDecoder:
+    """Decode of ONE image stream on `world` ranks (ImageDecoder.cpp:88-112): every rank holds the stream, walks
+    1 / world of its speculative parse grid (ie_decode_image_shard_begin_dev), the per-group results (16 bytes per group) are
+    all-gathered -- the one exchange step of this path -- and every rank decodes its own block rows
+    (ie_decode_image_shard_end_dev).  `gather` is the collective: a callable (tensor_out, tensor_in) -> None, by default
+    torch.distributed.all_gather_into_tensor on `group`; tests with emulated ranks on one GPU pass their own."""
+
+    def __init__(self, block: int, world: int, rank: int):
+        from . import device
+        self.block, self.world, self.rank = block, world, rank
+        self.sess = device.Session(device.Session.IMAGE_DECODE, 0, 0, block)
+        self.d_spec = None
+
+    def begin(self, hdr, d_enc, enc_bytes: int):
+        import torch
+
+        from . import device
+        total, chunk = device.decode_shard_spec_bytes(enc_bytes, self.block, self.world)
+        if self.d_spec is None or self.d_spec.numel() < total:
+            self.d_spec = torch.empty(total, dtype=torch.uint8, device="cuda")
+        self.chunk, self.total = chunk, total
+        device.decode_image_shard_begin_dev(self.sess, hdr, d_enc, enc_bytes, self.rank, self.world, self.d_spec)
+
+    def halves(self):
+        """the two arrays to all-gather: [(whole half, this rank's chunk of it)] x 2, views of the spec buffer"""
+        half = self.world * self.chunk
+        out = []
+        for k in range(2):
+            whole = self.d_spec[k * half:(k + 1) * half]
+            out.append((whole, whole[self.rank * self.chunk:(self.rank + 1) * self.chunk]))
+        return out
+
+    def end(self, hdr, d_enc, enc_bytes: int, d_rows_out=None):
+        import torch
+
+        from . import device
+        r0, r1 = shard_block_rows(hdr.height, self.block, self.world, self.rank)
+        rows0, rows1 = r0 // self.block, r1 // self.block
+        if d_rows_out is None:
+            d_rows_out = torch.empty((r1 - r0) * hdr.width, dtype=torch.uint8, device="cuda")
+        if rows0 == rows1:                      # more ranks than block rows: nothing to decode here
+            return d_rows_out
+        device.decode_image_shard_end_dev(self.sess, hdr, d_enc, enc_bytes, self.world, self.d_spec, rows0, rows1, d_rows_out)
+        return d_rows_out
+
+    def decode(self, hdr, d_enc, enc_bytes: int, d_rows_out=None, group=None):
+        """this rank's rows of the image (device tensor); asynchronous on the current stream"""
+        import torch.distributed as dist
+        self.begin(hdr, d_enc, enc_bytes)
+        if self.world > 1:
+            for whole, mine in self.halves():
+                dist.all_gather_into_tensor(whole, mine.clone(), group=group)
+        return self.end(hdr, d_enc, enc_bytes, d_rows_out)
+
+
 class ShardedVideoEncoder:
     """Encodes this rank's whole GOPs of a clip (BASELINE config 5) and re-aligns the result for the single output stream.
     GOPs are independent (VideoBase.hpp:32), so the only exchange is the all-gather of one u64 per rank."""

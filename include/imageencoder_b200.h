@@ -142,6 +142,22 @@ typedef struct ie_image_header {
 int ie_parse_image_header(const uint8_t *bytes, size_t nbytes, uint64_t start_bit, uint32_t block, ie_image_header *out);
 int ie_decode_image_with_header_dev(ie_session *s, const ie_image_header *hdr, const uint8_t *d_enc, size_t enc_bytes,
                                     uint8_t *d_raw_out, size_t raw_cap, void *stream);
+/* Sharded decode of ONE plain stream over several GPUs (replaces the serial block loop of
+ * ImageDecoder.cpp:88-112 for an image too large for one GPU's share of the time).  Every rank holds the whole stream.
+ *   begin: rank `part` of `parts` walks its share of the stream's speculative parse grid and leaves the per-group results in
+ *          its chunk of d_spec (ie_decode_shard_spec_bytes bytes: [entry: parts x chunk_bytes][exit: parts x chunk_bytes];
+ *          part r's chunks are at r * chunk_bytes of either half);
+ *   the caller all-gathers both halves of d_spec in place (its own collective: NCCL all-gather, peer copies, ...);
+ *   end:   verifies the seams of the gathered grid, emits the offsets of the blocks of block rows [block_row0, block_row1)
+ *          and decodes them into d_rows_out (pitch = width: the band's pixels only).  If the speculation does not verify
+ *          the exact parse runs on every rank (whole stream) -- same result, no scaling.
+ * Both calls are asynchronous on `stream`; hdr from ie_parse_image_header. */
+size_t ie_decode_shard_spec_bytes(size_t enc_bytes, uint32_t block, uint32_t parts, size_t *chunk_bytes);
+int ie_decode_image_shard_begin_dev(ie_session *s, const ie_image_header *hdr, const uint8_t *d_enc, size_t enc_bytes,
+                                    uint32_t part, uint32_t parts, uint8_t *d_spec, void *stream);
+int ie_decode_image_shard_end_dev(ie_session *s, const ie_image_header *hdr, const uint8_t *d_enc, size_t enc_bytes,
+                                  uint32_t parts, uint8_t *d_spec, uint32_t block_row0, uint32_t block_row1,
+                                  uint8_t *d_rows_out, size_t out_cap, void *stream);
 /* Byte-wise Huffman stage over a device-resident, byte-rounded plain stream (Huffman.cpp:232-344).
  * Synchronises `stream` once (the 256-entry tree is built on the host exactly as the reference does). */
 /* Batch of device-resident plain streams (stream i at d_encs + i * enc_stride, enc_bytes[i] bytes; enc_stride a multiple

@@ -343,3 +343,57 @@ def test_fast_decode_equals_exact_decode_at_scale(gpu, oracle_mod):
         L.ie_set_option(b"exact_transform", 0)
     assert np.array_equal(fast, exact)
     assert np.array_equal(fast, oracle_mod.video_decode(enc, True)[0])
+
+
+def _emulated_sharded_decode(stream: bytes, N: int, world: int):
+    """`world` ranks one after the other on one GPU: begin on every rank, the all-gather done by hand, end on every rank"""
+    import torch
+    from imageencoder_b200 import device
+    from imageencoder_b200.parallel import ShardedImageDecoder
+    hdr = device.parse_image_header(stream[:160], N)
+    pad = (-len(stream)) % 16 + 16
+    d_enc = torch.from_numpy(np.frombuffer(stream + bytes(pad), np.uint8).copy()).cuda()
+    ranks = [ShardedImageDecoder(N, world, r) for r in range(world)]
+    for d in ranks:
+        d.begin(hdr, d_enc, len(stream))
+    torch.cuda.synchronize()
+    for k in range(2):                                  # "all-gather": every rank's chunk into every rank's buffer
+        for dst in ranks:
+            for src in ranks:
+                if src is not dst:
+                    dst.halves()[k][0][src.rank * src.chunk:(src.rank + 1) * src.chunk].copy_(src.halves()[k][1])
+    bands = [d.end(hdr, d_enc, len(stream)) for d in ranks]
+    torch.cuda.synchronize()
+    return hdr, np.concatenate([b.cpu().numpy() for b in bands])
+
+
+@pytest.mark.parametrize("matrix,W,H,world", [("matrix8_1.txt", 512, 384, 1), ("matrix8_1.txt", 512, 384, 3), ("matrix8_2.txt", 1024, 768, 8),
+                                              ("matrix.txt", 512, 384, 2), ("matrix4_2.txt", 640, 256, 5), ("matrix8_1.txt", 64, 16, 4)])
+def test_sharded_single_stream_decode_matches_oracle(gpu, oracle_mod, matrix, W, H, world):
+    """one stream, `world` ranks: every rank walks its share of the parse grid and decodes its own block rows"""
+    from imageencoder_b200.synth import synth_image
+    q = oracle_mod.read_matrix(INPUTS / matrix)
+    N = q.shape[0]
+    img = synth_image(W, H, 91, flat=True)
+    stream = oracle_mod.image_encode(img, W, H, N, q, True, False)
+    want = oracle_mod.image_decode(stream, N)[0]
+    hdr, got = _emulated_sharded_decode(stream, N, world)
+    assert (hdr.width, hdr.height) == (W, H)
+    assert np.array_equal(got.reshape(H, W), want.reshape(H, W))
+    # a truncated stream: blocks the chain never reaches read as zero bits (BitStream.cpp:17-20), on every rank
+    cut = stream[:len(stream) * 2 // 3]
+    want_cut = oracle_mod.image_decode(cut, N)[0]
+    _, got_cut = _emulated_sharded_decode(cut, N, world)
+    assert np.array_equal(got_cut.reshape(H, W), want_cut.reshape(H, W))
+
+
+def test_sharded_single_stream_decode_at_scale(gpu, oracle_mod):
+    """4096 x 4096, 8 ranks: the sharded decode equals the one-GPU decode of the same stream"""
+    from imageencoder_b200.synth import synth_image
+    q = oracle_mod.read_matrix(INPUTS / "matrix8_2.txt")
+    W = H = 4096
+    img = synth_image(W, H, 1235)
+    stream = gpu.encode_image(img, W, H, q, True, False)
+    want = gpu.decode_image(stream, 8)
+    _, got = _emulated_sharded_decode(stream, 8, 8)
+    assert np.array_equal(got.reshape(H, W), np.asarray(want).reshape(H, W))
