@@ -573,6 +573,62 @@ def ours_sharded(args):
         parity_ok = bool(sha(got) == g["plain"]["enc_sha256"] and len(got) == g["plain"]["enc_bytes"])
     barrier()
 
+    # ---- sharded DECODE of that one stream (the other half of the metric): the stitched stream is handed to every rank (file
+    #      reader work, outside the timed region); timed: every rank walks its share of the parse grid, one NCCL all-gather of
+    #      the per-group results, every rank decodes its own block rows.  The gathered pixels are hashed against the reference's.
+    dec = None
+    try:
+        from imageencoder_b200.parallel import ShardedImageDecoder
+        d_stream = torch.zeros((nbytes + 15) // 16 * 16 + 64, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            d_stream[:nbytes].copy_(comm.stitched(nbytes))
+        dist.broadcast(d_stream, src=0)
+        hdr = device.parse_image_header(d_stream[:160].cpu().numpy().tobytes(), BLOCK)
+        sd = ShardedImageDecoder(BLOCK, world, rank)
+        band = torch.empty(W * hs, dtype=torch.uint8, device="cuda")
+        for _ in range(3):
+            sd.decode(hdr, d_stream, nbytes, band)
+        barrier()
+        dreps = 10
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(dreps):
+            sd.decode(hdr, d_stream, nbytes, band)
+        b.record()
+        barrier()
+        dms = torch.tensor([a.elapsed_time(b) / dreps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+        bands = [torch.empty_like(band) for _ in range(world)] if rank == 0 else None
+        dist.gather(band, bands, dst=0)
+        if rank == 0:
+            import hashlib
+            hh = hashlib.sha256()
+            for t in bands:
+                hh.update(t.cpu().numpy().tobytes())
+            # the same stream on ONE GPU (rank 0 alone): the base of the decode's strong scaling
+            s1d = device.Session(device.Session.IMAGE_DECODE, 0, 0, BLOCK)
+            full_out = torch.empty(W * H, dtype=torch.uint8, device="cuda")
+            for _ in range(2):
+                device.decode_image_with_header_dev(s1d, hdr, d_stream, nbytes, full_out)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(5):
+                device.decode_image_with_header_dev(s1d, hdr, d_stream, nbytes, full_out)
+            b.record()
+            torch.cuda.synchronize()
+            ms1d = a.elapsed_time(b) / 5
+            dec = {"value": W * H / (float(dms.item()) / 1e3) / 1e6, "unit": "Mpixels/s", "ms": float(dms.item()), "n_gpus": world,
+                   "parity_sha_ok": (bool(hh.hexdigest() == g["plain"]["dec_sha256"]) if g else None),
+                   "one_gpu": {"ms": ms1d, "value": W * H / (ms1d / 1e3) / 1e6},
+                   "what": "ie_decode_image_shard_begin_dev / _end_dev (parallel.ShardedImageDecoder): each rank walks 1/N of the "
+                           "speculative parse grid, NCCL all-gather of 16 bytes per group, each rank decodes its own block rows; "
+                           "one stream (sessions alternate in the encode figure, not here)"}
+            del full_out, s1d
+        del d_stream, band, sd
+    except Exception as e:      # an extra figure; never fail the encode bench on it
+        dec = {"failed": repr(e)}
+    barrier()
+
     # ---- Huffman stage of the sharded stream (BASELINE config 3 asks for RLE + Huffman): parallel.py's exchange (byte shared by
     #      two shards, all-reduce of histogram / first occurrences, per-rank coding with the global dictionary), wall clock
     huff = None
@@ -695,6 +751,7 @@ def ours_sharded(args):
             "stitch": {"ms": float(stitch_ms.item()), "bytes": nbytes,
                        "what": "ie_comm_stitch_dev: every rank's chunks -> rank 0's buffer over NVLink, outside the timed region; the "
                                "sha256 of that buffer is what parity_sha_ok compares with the reference's file"},
+            "decode": dec,
             "huffman_stage": huff,
             "strong_scaling_base": base1,
         }

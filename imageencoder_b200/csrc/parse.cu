@@ -192,7 +192,7 @@ __device__ __forceinline__ void parse_down_super(const ParseParams &p) {
 // transfer-function kernels above do the work instead (they return immediately when spec_ok is 1).
 // ---------------------------------------------------------------------------------------------------------
 // lead-in before a group's first bit (measured on 8x8 streams: 4096 bits leave 3 % of the groups unsynchronised, 8192 none)
-constexpr int kSpecRounds = 3;            // repair rounds inside a CTA
+constexpr int kSpecRounds = 3;            // parallel repair rounds inside a CTA (a serial pass settles what they leave)
 
 // One step of a walk on the staged copy, `rel` < lim relative to the view's base.  Returns the bits consumed and the number
 // of blocks they hold: an all-zero block is 4 zero bits (bit_len 0, no length/values), so a run of zero nibbles is a run of
@@ -295,7 +295,10 @@ __global__ void __launch_bounds__(TH) parse_spec_walk(const ParseParams p) {
         const int t = (int)threadIdx.x;
         bool redo = false;
         unsigned want = 0;
-        if (t >= 1 && g < p.nspec && (t < 2 || s_exit[t - 2] == s_entry[t - 1])) {
+        // (the CTA's first group has no predecessor here, so nothing vouches for it: its successor is left to
+        // parse_spec_boundary -- adopting the exit of an unsynchronised first group used to cascade through the CTA, one group
+        // per round, and leave the boundary kernel a long serial re-walk)
+        if (t >= 2 && g < p.nspec && s_exit[t - 2] == s_entry[t - 1]) {
             want = s_exit[t - 1];
             redo = (want != s_entry[t]);
         }
@@ -309,6 +312,29 @@ __global__ void __launch_bounds__(TH) parse_spec_walk(const ParseParams p) {
         if (redo) { s_entry[t] = entry; s_exit[t] = ex.x; }
         __syncthreads();
     }
+    // What the rounds left (runs of unsynchronised groups, groups behind one that nothing vouches for): one thread goes through
+    // the CTA's seams in order and re-walks every group whose entry disagrees with its predecessor's exit.  If the CTA's first
+    // group is itself wrong this follows its false chain -- until that chain meets the true one, as chains do after a block
+    // or two; parse_spec_boundary then repairs exactly those groups.  A dead predecessor (a false chain that ran into an invalid
+    // length field) is never followed: the group keeps what its own lead-in found.
+    __shared__ unsigned s_cnt[TH];
+    __shared__ unsigned char s_fix[TH];
+    s_fix[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < TH; t++) {
+            const unsigned gt = cta * TH + (unsigned)t;
+            const unsigned long long gt_start = B0 + (unsigned long long)gt * GB;
+            if (gt >= p.nspec || gt_start >= total) break;
+            const unsigned want = s_exit[t - 1];
+            if (want == s_entry[t] || want == kDead || want >= (unsigned)GB) continue;
+            const unsigned gr = (unsigned)(gt_start - st.base);
+            const uint2 e2 = walk_group_staged(st, p.NN, p.use_rle, gr + want, gr + GB);
+            s_entry[t] = want; s_exit[t] = e2.x; s_cnt[t] = e2.y; s_fix[t] = 1;
+        }
+    }
+    __syncthreads();
+    if (s_fix[threadIdx.x]) { entry = s_entry[threadIdx.x]; ex = make_uint2(s_exit[threadIdx.x], s_cnt[threadIdx.x]); }
     if (g < p.nspec) { p.spec_entry[g] = make_uint2(entry, 0u); p.spec_exit[g] = ex; }
 }
 
@@ -325,7 +351,13 @@ __global__ void __launch_bounds__(TH) parse_spec_boundary(const ParseParams p) {
     const unsigned long long B0 = *p.start + p.skip_bits;
     unsigned want = p.spec_exit[g - 1].x;
     for (unsigned n = 0; n < (unsigned)TH && g < p.nspec; n++, g++) {
-        if (p.spec_entry[g].x == want) break;
+        if (p.spec_entry[g].x == want) {
+            // the CTA's first seam agrees: its second one is this kernel's too (parse_spec_walk does not touch it); from the
+            // third group on an agreeing seam ends the repair
+            if (n >= 1) break;
+            want = p.spec_exit[g].x;
+            continue;
+        }
         const unsigned long long g_start = B0 + (unsigned long long)g * GB, g_end = g_start + GB;
         const uint2 ex = (want == kDead || want >= (unsigned)GB) ? make_uint2(kDead, 0u)
                                                                        : walk_group(p, total, g_start + want, g_end);
