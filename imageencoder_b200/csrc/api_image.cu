@@ -426,6 +426,7 @@ void ie_session_destroy(ie_session *s) {
     cudaFree(s->d_block_off); cudaFree(s->d_parse); cudaFree(s->d_tile_scratch); cudaFree(s->d_tile_meta); cudaFree(s->d_scratch); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_tmp);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->h_huff) cudaFreeHost(s->h_huff);
+    if (s->huff_ctx) free(s->huff_ctx);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->stream_in) {
         cudaStreamDestroy(s->stream_in); cudaStreamDestroy(s->stream_out);

@@ -57,6 +57,7 @@ struct ie_session {
     uint8_t *d_tmp = nullptr; size_t d_tmp_cap = 0;
     unsigned long long *h_pinned = nullptr;       // small pinned read-back area (64 u64)
     uint8_t *h_huff = nullptr;                    // pinned staging of the Huffman stage: dictionary header, codes, first bit
+    void *huff_ctx = nullptr;                     // argument block of the stage's host callback (huffman.cu), malloc'ed
     cudaStream_t stream = nullptr;                // used by the host-buffer entry points
 
     // copy/compute pipeline of the host-buffer image entry points: pixels come in by stripes on stream_in, the encoded

@@ -161,6 +161,11 @@ def huffman_encode_dev(s: Session, d_in: torch.Tensor, in_bytes: int, d_out: tor
     return n.value
 
 
+def huffman_encode_async_dev(s: Session, d_in: torch.Tensor, in_bytes: int, d_out: torch.Tensor, d_out_bytes: torch.Tensor) -> None:
+    """the stage without a host synchronisation (host callback in stream order); d_out_bytes: int64 device tensor [1]"""
+    check(lib().ie_huffman_encode_async_dev(s.h, _dp(d_in), in_bytes, _dp(d_out), d_out.numel(), _dp(d_out_bytes), _stream()))
+
+
 def huffman_encode_shard_dev(s: Session, d_in: torch.Tensor, in_bytes: int, hist, first_pos, write_dictionary: bool,
                              d_out: torch.Tensor, d_out_bits: torch.Tensor) -> None:
     """Huffman stage of one shard with the GLOBAL histogram / first-occurrence positions (host arrays)."""

@@ -169,6 +169,13 @@ int ie_decode_images_dev(ie_session *s, const uint8_t *d_encs, size_t enc_stride
                          void *stream);
 int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes,
                           uint8_t *d_out, size_t out_cap, size_t *out_bytes, void *stream);
+/* The same stage without any host synchronisation: the reference's dictionary build runs as a host callback in stream
+ * order (cudaLaunchHostFunc) between the histogram kernels and the pack kernels, the revert rule (Huffman.cpp:329-341) is
+ * decided on the device, the file's size in bytes is left in *d_out_bytes (device).  The call returns at once; errors (output
+ * too small, a code longer than 32 bits) surface as the session's device-side error at the next synchronising call.  One call
+ * in flight per session; out_cap >= 2080. */
+int ie_huffman_encode_async_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes, uint8_t *d_out, size_t out_cap,
+                                uint64_t *d_out_bytes, void *stream);
 int ie_huffman_decode_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes,
                           uint8_t *d_out, size_t out_cap, size_t *out_bytes, uint64_t *start_bit, void *stream);
 /* Huffman stage of one shard of a multi-GPU stream: the dictionary is built from the GLOBAL histogram and

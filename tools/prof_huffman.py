@@ -26,3 +26,29 @@ for _ in range(reps):
     nb = device.huffman_encode_dev(sess, d_plain, n, d_out)
 torch.cuda.synchronize()
 print(f"huffman encode of {n} bytes -> {nb} bytes: {(time.perf_counter() - t) / reps * 1e3:.3f} ms wall per call")
+# the stage without host synchronisation, two sessions on two streams: one call's dictionary build (host callback) overlaps the
+# other's kernels
+sess2 = device.Session(device.Session.IMAGE_ENCODE, W, H, 8)
+d_out2 = torch.zeros(cap + 4096, dtype=torch.uint8, device="cuda")
+nbytes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(2)]
+streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+pairs = [(sess, d_out), (sess2, d_out2)]
+def run(k):
+    for i in range(k):
+        j = i % 2
+        with torch.cuda.stream(streams[j]):
+            device.huffman_encode_async_dev(pairs[j][0], d_plain, n, pairs[j][1], nbytes[j])
+run(4)
+torch.cuda.synchronize()
+t = time.perf_counter()
+reps = 20
+run(reps)
+torch.cuda.synchronize()
+print(f"async, two sessions / streams: {(time.perf_counter() - t) / reps * 1e3:.3f} ms per call; bytes {int(nbytes[0].item())} {int(nbytes[1].item())} "
+      f"identical outputs: {bool(torch.equal(d_out[:nb], d_out2[:nb]))}")
+with torch.cuda.stream(streams[0]):
+    t = time.perf_counter()
+    for _ in range(reps):
+        device.huffman_encode_async_dev(sess, d_plain, n, d_out, nbytes[0])
+    streams[0].synchronize()
+print(f"async, one stream: {(time.perf_counter() - t) / reps * 1e3:.3f} ms per call")
