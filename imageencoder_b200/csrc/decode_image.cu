@@ -209,9 +209,16 @@ __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
     for (int j = 0; j < NN / 2; j++) cfw[j] = 0u;
     if (w != 0) {
         const int sh = 32 - w;
-        for (int k = 0; k < len; k++) {
-            const int v = (int)peek(pos) >> sh;                    // util::shift_signed<int16_t>: the top w bits, sign extended
-            pos += (unsigned)w;
+        // two fields per 32-bit window (w <= 16), stored as one word: util::shift_signed<int16_t> = the top w bits, sign extended
+        int k = 0;
+        for (; k + 1 < len; k += 2) {
+            const unsigned x = peek(pos);
+            const int v0 = (int)x >> sh, v1 = (int)(x << w) >> sh;
+            pos += 2u * (unsigned)w;
+            cfw[k >> 1] = __byte_perm((unsigned)v0, (unsigned)v1, 0x5410);
+        }
+        if (k < len) {
+            const int v = (int)peek(pos) >> sh;
             if (v != 0) cf[k] = (short)v;
         }
     }
