@@ -122,9 +122,15 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecodeParams p
 // Fast decode: fields through a 64-bit bit buffer fed by aligned word loads; separable FP32 inverse DCT; every pixel
 // whose fast value lies within the block's error bound of an integer boundary (where the reference's truncation,
 // Block.cpp:103, could go either way) is recomputed in the reference's exact order over the non-zero coefficients.
-//   error bound: |X_fast - X_real| <= 14 u S with S = sum |C(u)C(v) Q c| (8 u S_row from pass 1 carried through pass 2,
-//   6 u S from pass 2, u = 2^-24); the +128 / +prediction add rounds at <= u (S + 383).  delta = 32 u S + 2 u (S + 383)
-//   + 2e-6 is used (> 2x margin).  Pixels that are certainly clamped (v < -delta or v > 255 + delta) need no check.
+//   error bound, u = 2^-24, S = sum |C(u)C(v) Q c| (the dequantised inputs), |cos| <= 1:
+//     one 1-D pass on inputs y with A = sum |y_i|: the even part carries <= 4 u A_even (stored constant + product + two sums),
+//     the odd fma chain <= 5 u A_odd, the final butterfly adds u A -- at most 6 u A per output.  Pass 2 adds 6 u S of its own
+//     and carries pass 1's 6 u (row sums) through |cos| <= 1: 12 u S; the inputs themselves (float(Q C C) times the
+//     coefficient) are off by <= 2 u each: |X_fast - X_real| <= 14 u S (1 + O(u)).
+//     Measured worst case over 2 M random / sparse / single-coefficient / sign-aligned blocks: 2.8 u S on exact inputs (tools/idct_error_bound.py).
+//   The +128 / +prediction adds round at <= u (S + 383) each.  delta = 18 u S + 2 u (S + 383) + 2e-6 is used (round 1 used
+//   32 u S: twice as many pixels took the exact path, a third of this kernel's stall samples).
+//   Pixels that are certainly clamped (v < -delta or v > 255 + delta) need no check.
 // ---------------------------------------------------------------------------------------------------------
 __constant__ unsigned char c_zz4[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
 __constant__ unsigned char c_zz8[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
@@ -236,7 +242,7 @@ __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
         S += fabsf(d);
     }
     if (VAR != 1 || ADD) idct2d_fast<N>(x);
-    const float delta = (32.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
+    const float delta = (18.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
     // unsure: |frac - 0.5| >= 0.5 - delta; absurd coefficients (delta >= 0.49) take the exact path everywhere
     const float hi_thr = (delta < 0.49f) ? 0.5f - delta : 0.f;
     const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;

@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
                         S += fabsf(da) + fabsf(db);
                     }
                 lean::idct2d_packed<4>(X2, P2);
-                const float delta = (32.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
+                const float delta = (18.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;      // decode_image.cu: <= 14 u S
                 const float hi_thr = (delta < 0.49f) ? 0.5f - delta : 0.f;
                 unsigned outw[4];
                 unsigned rpxw[4];
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
                     S += fabsf(d);
                 }
                 idct2d_fast<4>(xf);
-                const float delta = (32.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
+                const float delta = (18.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;      // decode_image.cu: <= 14 u S
                 const float hi_thr = (delta < 0.49f) ? 0.5f - delta : 0.f;
                 unsigned outw[4];
                 unsigned rpxw[4];                                     // the four reference pixels of each row, one per byte

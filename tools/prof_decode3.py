@@ -7,8 +7,8 @@ from imageencoder_b200 import _lib, device
 from imageencoder_b200.synth import synth_image
 _lib.check(ie.lib().ie_init(0))
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-q = ie.read_matrix('tests/golden/inputs/matrix8_2.txt')
-img = torch.from_numpy(synth_image(size, size, 1235)).cuda().reshape(-1)
+q = ie.read_matrix('tests/golden/inputs/' + (sys.argv[2] if len(sys.argv) > 2 else 'matrix8_2.txt'))
+img = torch.from_numpy(synth_image(size, size, 1234 if len(sys.argv) > 2 else 1235)).cuda().reshape(-1)
 cap = int(ie.lib().ie_max_encoded_bytes(size, size, 8, 1))
 d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
 d_bits = torch.zeros(1, dtype=torch.int64, device="cuda")
