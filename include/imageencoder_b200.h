@@ -262,8 +262,13 @@ int ie_comm_copy_stitched(ie_comm *c, void *dst, size_t nbytes, void *stream);
  *   "video_decode_variant" = 0 | 1 (default)  video decode: 1 = one speculative parse over the whole stream, a short
  *                          sequential frame chain, then frame k of every GOP per launch (streams that end inside a frame or
  *                          hold an invalid length field fall back to 0); 0 = frame by frame;
- *   "me_variant"      = 0 (default) | 1  motion-search kernel: 1 = SAD partial sums reduced with warp-wide integer
- *                          reductions (REDUX) instead of shuffle + add steps (experimental, not yet timed).
+ *   "me_variant"      = 0 | 1 | 2 (default)  motion-search kernel: 2 = eight lanes per MacroBlock, four MacroBlocks per warp
+ *                          on one shared search window; 0 = a warp per MacroBlock (round 1); 1 = 0 with the SAD partial sums
+ *                          reduced by warp-wide integer reductions (REDUX);
+ *   "pframe_variant"  = 0 | 2 (default)  P-frame tiles: 2 = residual, transform, quantisation and reconstruction in packed
+ *                          f32x2 operations, reference rows read as words; 0 = the scalar kernel it replaced;
+ *   "encode_pad_smem" = bytes (default 0)  extra dynamic shared memory per CTA of the tile kernel: lowers its occupancy for
+ *                          measurements (tools/ab_quick.py --pads), never useful otherwise.
  * Returns IE_EINVAL for an unknown name or an out-of-range value. */
 int ie_set_option(const char *name, int value);
 
