@@ -462,7 +462,28 @@ def ours_single(args):
         line["cpu_baseline"] = cb.get("cpu_baseline")
         if "decode_cpu_baseline" in cb:
             line["decode"]["cpu_baseline"] = cb["decode_cpu_baseline"]
+    if not args.no_other_configs:
+        # the other BASELINE configurations on this GPU, outside everything timed above (own processes, bounded): config 5
+        # (video, device-resident, sha256 of stream and frames checked) and a 16-image sample of config 4 (host entry points, end
+        # to end).  Extra evidence only: a failure or a time-out never fails the bench.
+        del d_raw, d_out
+        torch.cuda.empty_cache()
+        line["other_configs"] = {"c5_video": run_tool(["tools/bench_sharded.py", "video", "--reps", "3"], 150),
+                                 "c4_batch_sample": run_tool(["tools/bench_sharded.py", "batch", "--images", "16", "--reps", "2"], 120)}
     print(json.dumps(line))
+
+
+def run_tool(argv, timeout_s):
+    """last line of a tool's stdout as JSON (the tools print one object), or why there is none"""
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable] + argv, cwd=str(ROOT), capture_output=True, text=True, timeout=timeout_s)
+        lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"failed": (r.stderr or r.stdout)[-300:]}
+        return json.loads(lines[-1])
+    except Exception as e:
+        return {"failed": repr(e)}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -768,6 +789,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="N = 1: skip the config-4 / config-5 figures appended to the line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -840,6 +840,7 @@ __device__ __forceinline__ unsigned vsearch_last_true(unsigned lo, unsigned hi, 
 struct VChainShared {
     unsigned long long pos;
     unsigned cnt, pool_n, merged, m, fail;
+    uint2 pqm;
 };
 
 __global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const ParseParams p, const VideoParse v) {
@@ -848,6 +849,7 @@ __global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const Pars
     constexpr unsigned kWinWords = (kVHeadGroups * kVG + kVG + kMaxBlock) / 32 + 32;
     __shared__ __align__(16) unsigned s_win[kWinWords];
     __shared__ unsigned s_ent[kVHeadGroups];
+    __shared__ uint2 s_pq[kVHeadGroups];
     __shared__ VChainShared sh;
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start;
@@ -878,6 +880,9 @@ __global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const Pars
                 if (threadIdx.x < kVHeadGroups) {
                     const unsigned long long gg = g + 1 + threadIdx.x;
                     s_ent[threadIdx.x] = (gg < p.nspec) ? p.spec_entry[gg].x : kDead;
+                } else if (threadIdx.x < 2 * kVHeadGroups) {                                   // the prefix sums of the same groups:
+                    const unsigned long long gg = g + 1 + (threadIdx.x - kVHeadGroups);          // one of them is the merge group's
+                    s_pq[threadIdx.x - kVHeadGroups] = (gg <= p.nspec) ? __ldcg(v.pq + gg) : make_uint2(0u, 0u);
                 }
                 __syncthreads();
                 if (threadIdx.x == 0) {
@@ -902,6 +907,7 @@ __global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const Pars
                         if (rel - gend_rel == s_ent[j]) { mg = 1; mm = (unsigned)(g + 1 + j); break; }
                     }
                     sh.pos = st.base + rel; sh.cnt = c; sh.pool_n = pn; sh.merged = mg; sh.m = mm; sh.fail = fl;
+                    if (mg) sh.pqm = s_pq[mm - (unsigned)(g + 1)];
                 }
                 __syncthreads();
                 pos = sh.pos; cnt = sh.cnt; pool_n = sh.pool_n; merged = sh.merged != 0; m = sh.m; fail = sh.fail != 0;
@@ -916,11 +922,12 @@ __global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const Pars
             if (!merged) { fail = true; break; }
             // ---- SPEC piece: groups m .. glast, all seams verified
             const unsigned R = B - cnt;
-            const uint2 pqm = __ldcg(v.pq + m);
+            const uint2 pqm = sh.pqm;                                                     // staged with the merge group's entry
             const unsigned hi = (unsigned)min((unsigned long long)p.nspec - 1ull, (unsigned long long)m + max_fg);
             const uint2 *pq = v.pq;
             unsigned gs = vsearch_last_true(m, hi, [&](unsigned g) { return (__ldcg(pq + g).x - pqm.x) < R; });
-            const uint2 pqs = __ldcg(pq + gs);
+            const uint2 pqs = __ldcg(pq + gs), pqs1 = __ldcg(pq + gs + 1);               // gs + 1 <= nspec: pq has nspec + 1 entries
+            const unsigned es = p.spec_entry[gs].x;
             if (npieces >= kVMaxPieces) { fail = true; break; }
             if (pqs.y != pqm.y) {
                 // a bad seam before the frame's last group: take the verified groups, go on with an exact walk from there
@@ -934,8 +941,7 @@ __global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const Pars
                 continue;
             }
             const unsigned r = R - (pqs.x - pqm.x);                                        // blocks to take in group gs (>= 1)
-            if (r > __ldcg(pq + gs + 1).x - pqs.x) { fail = true; break; }                 // the stream ends inside the frame
-            const unsigned es = p.spec_entry[gs].x;
+            if (r > pqs1.x - pqs.x) { fail = true; break; }                                // the stream ends inside the frame
             if (es == kDead) { fail = true; break; }
             if (threadIdx.x == 0) rec->piece[npieces] = VFramePiece{1u, m, gs, cnt, pqm.x};
             npieces++;
