@@ -450,6 +450,13 @@ __global__ void __launch_bounds__(TH) parse_spec_emit(const ParseParams p) {
     }
     const unsigned long long c_start = B0 + (unsigned long long)blockIdx.x * TH * GB;
     if (c_start >= total) return;                            // uniform
+    if (p.emit_hi) {
+        // sharded decode: a CTA none of whose blocks this rank decodes has nothing to stage (walk_base = the exclusive scan
+        // of the per-CTA block counts, final since parse_spec_check)
+        const unsigned lo_c = p.walk_base[blockIdx.x];
+        const unsigned hi_c = (blockIdx.x + 1 < gridDim.x) ? p.walk_base[blockIdx.x + 1] : 0xFFFFFFFFu;
+        if (lo_c > p.emit_hi || hi_c < p.emit_lo) return;   // uniform
+    }
     const StagedStream st = stage_stream(s_stage, SpecCfg<GB, TH>::kStageWords, p.enc, total, c_start,
                                          min(total, c_start + (unsigned long long)TH * GB));
     const unsigned cnt = (g < p.nspec) ? p.spec_exit[g].y : 0u;
