@@ -687,29 +687,57 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
     VideoParse v;
     ParseParamsOpaque po;
     IE_TRY(launch_video_parse(d_enc, d_totals, d_totals + ngops, h.use_rle, nblocks, nmb * 2 * mvbits, frames, gop, z, s->d_parse, v, po, st));
-    IE_CUDA(cudaMemcpyAsync(&s->h_pinned[8], v.result, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    IE_CUDA(cudaStreamSynchronize(st));                       // consts is read by the copy above until here
-    if ((unsigned)(s->h_pinned[8] & 0xffffffffu) != 1u) return IE_OK;
 
     DecodeParams p;
     memset(&p, 0, sizeof p);
     p.enc = d_enc; p.enc_stride = 0; p.enc_bits = d_totals; p.start_bit = d_totals; p.block_off = s->d_block_off; p.nblocks = nblocks;
     p.bx = W / 4; p.N = 4; p.use_rle = h.use_rle; make_quant(p.quant, h.quant, 4); make_k2(p.k2, h.quant, 4); p.tab = s->dev->d_t4; p.pitch = W; p.err = s->d_err;
     p.out_stride = (size_t)gop * fsz;
-    for (uint32_t k = 0; k < gop && k < frames; k++) {
-        const uint32_t nimg = (frames - k + gop - 1) / gop;                       // GOPs that have a frame k
-        p.out = d_out + (size_t)k * fsz;
-        if (k > 0) {
-            MCBatchParams mc;
-            mc.enc = d_enc; mc.enc_bits = consts[0]; mc.rec = v.rec; mc.first_frame = k; mc.gop = gop; mc.mvbits = mvbits; mc.out = d_out; mc.fsz = fsz;
-            mc.W = (int)W; mc.H = (int)H; mc.mx = (int)(W / kMB); mc.nmb = (int)nmb;
-            IE_CUDA(launch_pdl(mc_copy_batch_kernel, dim3((nmb + 7) / 8, nimg), dim3(256), 0, st, mc));
-            count_launch();
-            if (!motioncomp) continue;                                            // Frame.cpp:107-117
+    // The frame chain is sequential (one CTA, ~9 us per frame); the reconstruction is not.  GOPs go in up to five batches: the
+    // chain of batch b runs on the caller's stream, the reconstruction of batch b on a second stream as soon as the chain has
+    // passed it, i.e. next to the chain of batch b + 1.  Everything is enqueued before the one synchronisation below; if the
+    // chain gives up (truncated / damaged stream) the batches already enqueued decode empty records (harmless) and the caller
+    // decodes frame by frame over their output.
+    IE_TRY(session_ensure_pipeline(s));
+    cudaStream_t st2 = s->stream_in;
+    const uint32_t nbatches = std::min<uint32_t>(5, ngops), gpb = (ngops + nbatches - 1) / nbatches;
+    cudaEvent_t ev_join = nullptr;
+    IE_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    int rc = IE_OK;
+    for (uint32_t g0 = 0; g0 < ngops && rc == IE_OK; g0 += gpb) {
+        const uint32_t g1 = std::min(ngops, g0 + gpb);
+        const uint32_t f0 = g0 * gop, f1 = std::min(frames, g1 * gop);
+        rc = launch_video_chain(v, po, f0, f1, st);
+        cudaEvent_t ev = s->ev_in[(g0 / gpb) % ie_session::kMaxStripes];
+        if (rc == IE_OK && cudaEventRecord(ev, st) != cudaSuccess) rc = IE_ECUDA;
+        if (rc == IE_OK && cudaStreamWaitEvent(st2, ev, 0) != cudaSuccess) rc = IE_ECUDA;
+        for (uint32_t k = 0; k < gop && f0 + k < f1 && rc == IE_OK; k++) {
+            const uint32_t nimg = (f1 - f0 - k + gop - 1) / gop;                  // GOPs of the batch that have a frame k
+            p.out = d_out + (size_t)(f0 + k) * fsz;
+            if (k > 0) {
+                MCBatchParams mc;
+                mc.enc = d_enc; mc.enc_bits = consts[0]; mc.rec = v.rec; mc.first_frame = f0 + k; mc.gop = gop; mc.mvbits = mvbits; mc.out = d_out; mc.fsz = fsz;
+                mc.W = (int)W; mc.H = (int)H; mc.mx = (int)(W / kMB); mc.nmb = (int)nmb;
+                if (launch_pdl(mc_copy_batch_kernel, dim3((nmb + 7) / 8, nimg), dim3(256), 0, st2, mc) != cudaSuccess) { rc = IE_ECUDA; break; }
+                count_launch();
+                if (!motioncomp) continue;                                        // Frame.cpp:107-117
+            }
+            p.add_mode = k > 0 ? 1 : 0;
+            rc = launch_video_emit(v, po, f0 + k, nimg, s->d_block_off, st2);
+            if (rc == IE_OK) rc = launch_decode_blocks(p, nimg, st2);
         }
-        p.add_mode = k > 0 ? 1 : 0;
-        IE_TRY(launch_video_emit(v, po, k, nimg, s->d_block_off, st));
-        IE_TRY(launch_decode_blocks(p, nimg, st));
+    }
+    // join: the caller's stream continues after the second stream's last kernel
+    if (cudaEventRecord(ev_join, st2) != cudaSuccess || cudaStreamWaitEvent(st, ev_join, 0) != cudaSuccess) rc = (rc == IE_OK) ? IE_ECUDA : rc;
+    cudaError_t ce = cudaMemcpyAsync(&s->h_pinned[8], v.result, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);                // consts is read by the copy at the top until here
+    cudaEventDestroy(ev_join);
+    if (rc != IE_OK) { if (rc == IE_ECUDA) set_error("CUDA error in the whole-stream video decode"); return rc; }
+    IE_CUDA(ce);
+    if ((unsigned)(s->h_pinned[8] & 0xffffffffu) != 1u) {
+        // a device-side error flag raised by the batches that decoded empty records must not outlive this attempt
+        IE_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), st));
+        return IE_OK;
     }
     fill_uv_kernel<<<256, 256, 0, st>>>(d_out, ysz, fsz, frames);                   // Frame.cpp:122-124
     count_launch();

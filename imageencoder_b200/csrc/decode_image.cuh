@@ -50,6 +50,7 @@ struct VideoParse {
     unsigned pool_cap;
     VFrameRec *rec;
     unsigned *result;              // [0] 1 = the records are valid, [1] pool entries used
+    unsigned long long *state;     // chain state between launches: next bit, pool entries used, failed
 };
 struct VideoParseSizes { size_t nspec, pool_cap, bytes; unsigned scan_ctas; };
 struct ParseParamsOpaque { unsigned long long raw[32]; };
@@ -57,6 +58,7 @@ VideoParseSizes video_parse_sizes(size_t enc_bytes, unsigned frames, int sm_coun
 int launch_video_parse(const uint8_t *d_enc, const unsigned long long *d_enc_bits, const unsigned long long *d_start, int use_rle,
                        unsigned nblocks, unsigned mv_bits, unsigned frames, unsigned gop, const VideoParseSizes &z, uint8_t *scratch,
                        VideoParse &v, ParseParamsOpaque &popaque, cudaStream_t stream);
+int launch_video_chain(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned f0, unsigned f1, cudaStream_t stream);
 int launch_video_emit(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned first_frame, unsigned nimg, unsigned long long *block_off,
                       cudaStream_t stream);
 

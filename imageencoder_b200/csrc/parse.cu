@@ -850,7 +850,11 @@ struct VChainShared {
     uint2 pqm;
 };
 
-__global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const ParseParams p, const VideoParse v) {
+// Frames [f0, f1) of the clip; the chain's state (next bit, pool fill, failure) travels from launch to launch in v.state, so that
+// the reconstruction of a batch of GOPs (second stream) can start while the chain works on the next batch.  After a failure the
+// remaining frames get empty records that point at the end of the stream (the reconstruction kernels of the batches already
+// enqueued stay well-defined; the caller discards their output and decodes frame by frame).
+__global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const ParseParams p, const VideoParse v, unsigned f0, unsigned f1) {
     pdl_wait();
     constexpr unsigned kMaxBlock = 4 + 16 + 16 * 16;
     constexpr unsigned kWinWords = (kVHeadGroups * kVG + kVG + kMaxBlock) / 32 + 32;
@@ -862,10 +866,12 @@ __global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const Pars
     const unsigned long long B0 = *p.start;
     const unsigned B = v.nblocks;
     const unsigned max_fg = (unsigned)(((unsigned long long)B * kMaxBlock) / kVG) + 4u;
-    unsigned long long pos = B0;
-    unsigned pool_n = 0;
-    bool fail = (B0 >= total) && v.frames != 0;
-    for (unsigned f = 0; f < v.frames && !fail; f++) {
+    unsigned long long pos = (f0 == 0) ? B0 : v.state[0];
+    unsigned pool_n = (f0 == 0) ? 0u : (unsigned)v.state[1];
+    bool fail = (f0 == 0) ? ((B0 >= total) && v.frames != 0) : (v.state[2] != 0);
+    __syncthreads();                                        // everyone has read the state before thread 0 rewrites it
+    unsigned f = f0;
+    for (; f < f1 && !fail; f++) {
         const bool is_p = (f % v.gop) != 0;
         if (is_p) pos += v.mv_bits;
         if (pos >= total) { fail = true; break; }
@@ -977,7 +983,18 @@ __global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const Pars
         if (threadIdx.x == 0) { rec->end = E; rec->npieces = npieces; }
         pos = E;
     }
-    if (threadIdx.x == 0) { v.result[0] = fail ? 0u : 1u; v.result[1] = pool_n; }
+    if (fail) {
+        // f = the frame that failed (or the first one of this launch): it and everything behind it in this launch decodes nothing
+        for (unsigned ff = f0 + threadIdx.x; ff < f1; ff += kVChainThreads) {
+            if (ff < f) continue;
+            VFrameRec *rec = v.rec + ff;
+            rec->first = total; rec->end = total; rec->npieces = 0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        v.state[0] = pos; v.state[1] = pool_n; v.state[2] = fail ? 1ull : 0ull;
+        v.result[0] = fail ? 0u : 1u; v.result[1] = pool_n;
+    }
 }
 
 // block_off[img][0 .. nblocks] of frame slot + img * gop (img = blockIdx.y) from the frame's pieces
@@ -989,8 +1006,12 @@ __global__ void __launch_bounds__(kVTH) vparse_emit_kernel(const ParseParams p, 
     unsigned long long *off = block_off + (size_t)blockIdx.y * (v.nblocks + 1);
     const unsigned long long total = *p.enc_bits;
     const unsigned long long B0 = *p.start;
-    const unsigned np = rec->npieces;
+    const unsigned np = min(rec->npieces, kVMaxPieces);
     if (blockIdx.x == 0 && threadIdx.x == 0) off[v.nblocks] = rec->end;
+    if (np == 0) {                                           // a frame the chain did not reach (failed parse): every block at the frame's end
+        for (unsigned j = blockIdx.x * kVTH + threadIdx.x; j < v.nblocks; j += gridDim.x * kVTH) off[j] = rec->end;
+        return;
+    }
     for (unsigned i = 0; i < np; i++) {
         const VFramePiece pc = rec->piece[i];
         if (pc.kind == 0) {
@@ -1031,6 +1052,7 @@ static void video_parse_layout(const VideoParseSizes &z, uint8_t *scratch, Parse
     p.cursor_next = reinterpret_cast<unsigned long long *>(p.spec_flags + 8);
     v.result = p.spec_flags + 12;
     p.walk_base = p.spec_flags + 16;
+    v.state = reinterpret_cast<unsigned long long *>(p.spec_flags + 24);      // 3 x u64
     uint8_t *b = reinterpret_cast<uint8_t *>(p.spec_flags + 32);
     v.pool = reinterpret_cast<unsigned long long *>(b); b += z.pool_cap * sizeof(unsigned long long);
     v.rec = reinterpret_cast<VFrameRec *>(b);
@@ -1047,7 +1069,7 @@ VideoParseSizes video_parse_sizes(size_t enc_bytes, unsigned frames, int sm_coun
     return z;
 }
 
-// steps 1-3: after this (on `stream`) v.result[0] says whether the frame records are valid
+// steps 1-2 (walk + prefix sums); the chain is launched batch by batch with launch_video_chain
 int launch_video_parse(const uint8_t *d_enc, const unsigned long long *d_enc_bits, const unsigned long long *d_start, int use_rle,
                        unsigned nblocks, unsigned mv_bits, unsigned frames, unsigned gop, const VideoParseSizes &z, uint8_t *scratch,
                        VideoParse &v, ParseParamsOpaque &popaque, cudaStream_t stream) {
@@ -1067,8 +1089,17 @@ int launch_video_parse(const uint8_t *d_enc, const unsigned long long *d_enc_bit
     IE_CUDA(cudaFuncSetAttribute(parse_spec_walk<kVG, kVTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
     IE_CUDA(launch_pdl(parse_spec_walk<kVG, kVTH>, dim3(nwalk), dim3(kVTH), stage_bytes, stream, p));
     IE_CUDA(launch_pdl(vparse_scan_kernel, dim3(z.scan_ctas), dim3(256), 0, stream, p, v.pq, v.partial));
-    IE_CUDA(launch_pdl(vparse_chain_kernel, dim3(1), dim3(kVChainThreads), 0, stream, p, v));
-    count_launch(3);
+    count_launch(2);
+    IE_CUDA(cudaGetLastError());
+    return IE_OK;
+}
+
+// step 3 for frames [f0, f1); launches must be made in frame order on one stream.  After the last one v.result[0] says whether
+// the frame records are valid.
+int launch_video_chain(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned f0, unsigned f1, cudaStream_t stream) {
+    const ParseParams &p = *reinterpret_cast<const ParseParams *>(&popaque);
+    IE_CUDA(launch_pdl(vparse_chain_kernel, dim3(1), dim3(kVChainThreads), 0, stream, p, v, f0, f1));
+    count_launch();
     IE_CUDA(cudaGetLastError());
     return IE_OK;
 }
