@@ -52,6 +52,8 @@ SIGNATURES = {
     "ie_decode_image_shard_end_dev": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_uint32, C.c_uint32, _vp, C.c_size_t, _vp]),
     "ie_decode_images_dev": (C.c_int, [_vp, _vp, C.c_size_t, _szp, C.c_uint32, C.c_uint64, _vp, C.c_size_t, _u32p, _u32p, _vp]),
     "ie_huffman_encode_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _szp, _vp]),
+    "ie_byte_histogram_async_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "ie_huffman_encode_shard_async_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, C.c_int, _vp, C.c_size_t, _vp, _vp]),
     "ie_huffman_encode_async_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp]),
     "ie_huffman_decode_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, _szp, _u64p, _vp]),
     "ie_huffman_encode_shard_dev": (C.c_int, [_vp, _vp, C.c_size_t, _u32p, _u64p, C.c_int, _vp, C.c_size_t, _vp, _vp]),

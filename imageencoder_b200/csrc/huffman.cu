@@ -830,7 +830,7 @@ static int huffman_pack_dev(ie_session *s, const uint8_t *d_in, size_t n, const 
 // the host side: the caller's thread returns at once, two sessions on two streams overlap one call's dictionary build with the
 // other's kernels.  One call in flight per session (the pinned staging is the session's).
 constexpr size_t kHuffScratch = 256 * 8 + 256 * 4 + sizeof(HuffCodes) + 64 + 256 * 4 + 64;
-struct HuffAsyncCtx { uint8_t *h_huff; };
+struct HuffAsyncCtx { uint8_t *h_huff; int write_dict; };
 
 static void CUDART_CB huff_build_cb(void *ud) {
     HuffAsyncCtx *c = static_cast<HuffAsyncCtx *>(ud);
@@ -841,6 +841,7 @@ static void CUDART_CB huff_build_cb(void *ud) {
     int *status = reinterpret_cast<int *>(c->h_huff + kHuffPinnedRecv + 256 * 8 + 256 * 4 + 16);
     HostBitWriter hdr;
     const int rc = build_dictionary(hist, first, codes, hdr);
+    if (!c->write_dict) { hdr.pos = 0; hdr.buf.assign(16, 0); }           // a later shard of a multi-GPU stream: codes only
     memset(c->h_huff, 0, 2048);
     if (rc != IE_OK || (hdr.pos + 7) / 8 > 2048) {
         memset(&codes, 0, sizeof codes);
@@ -881,8 +882,11 @@ __global__ void __launch_bounds__(256) huff_revert_kernel(const uint8_t *__restr
     }
 }
 
+// d_hist_in / d_first_in != NULL: the (global) histogram and first occurrences are given, on the device (a shard of a multi-GPU
+// stream): no histogram kernels, no revert rule (the caller decides it over all shards), the shard's bit count goes to d_out_bits.
 static int huffman_encode_async(ie_session *s, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap, unsigned long long *d_final_bytes,
-                                cudaStream_t st) {
+                                cudaStream_t st, const unsigned *d_hist_in = nullptr, const unsigned long long *d_first_in = nullptr,
+                                int write_dict = 1, unsigned long long *d_out_bits = nullptr) {
     if (out_cap < 2048 + 32) { set_error("output buffer too small"); return IE_ENOSPC; }
     IE_TRY(ensure_scratch(s, kHuffScratch));
     unsigned long long *d_first = reinterpret_cast<unsigned long long *>(s->d_scratch);
@@ -896,13 +900,19 @@ static int huffman_encode_async(ie_session *s, const uint8_t *d_in, size_t n, ui
         if (!s->huff_ctx) { set_error("out of memory"); return IE_ECUDA; }
     }
     static_cast<HuffAsyncCtx *>(s->huff_ctx)->h_huff = s->h_huff;
+    static_cast<HuffAsyncCtx *>(s->huff_ctx)->write_dict = write_dict;
     // every allocation before the first launch: nothing below may re-allocate what an enqueued operation uses
     const unsigned ntiles = (unsigned)((n + kPackTileBytes - 1) / kPackTileBytes);
     IE_TRY(session_ensure_scan(s, 1, ntiles));
     IE_TRY(session_reserve(&s->d_tile_meta, &s->tile_meta_cap, (size_t)ntiles * (sizeof(unsigned long long) + sizeof(unsigned)) + 64));
 
-    IE_TRY(launch_byte_histogram(d_in, n, d_hist, d_first, d_first_cta, s->dev->sm_count, st));
-    IE_CUDA(cudaMemcpyAsync(s->h_huff + kHuffPinnedRecv, d_first, 256 * 8 + 256 * 4, cudaMemcpyDeviceToHost, st));
+    if (d_hist_in) {
+        IE_CUDA(cudaMemcpyAsync(s->h_huff + kHuffPinnedRecv, d_first_in, 256 * 8, cudaMemcpyDeviceToHost, st));
+        IE_CUDA(cudaMemcpyAsync(s->h_huff + kHuffPinnedRecv + 256 * 8, d_hist_in, 256 * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+        IE_TRY(launch_byte_histogram(d_in, n, d_hist, d_first, d_first_cta, s->dev->sm_count, st));
+        IE_CUDA(cudaMemcpyAsync(s->h_huff + kHuffPinnedRecv, d_first, 256 * 8 + 256 * 4, cudaMemcpyDeviceToHost, st));
+    }
     IE_CUDA(cudaLaunchHostFunc(st, huff_build_cb, s->huff_ctx));
     HuffCodes *h_codes = reinterpret_cast<HuffCodes *>(s->h_huff + 2048);
     unsigned long long *h_hb = reinterpret_cast<unsigned long long *>(s->h_huff + 2048 + sizeof(HuffCodes));
@@ -919,8 +929,12 @@ static int huffman_encode_async(ie_session *s, const uint8_t *d_in, size_t n, ui
     huff_bits_kernel<<<std::min<unsigned>(ntiles, (unsigned)s->dev->sm_count * 8u), kPackThreads, 0, st>>>(p);
     huff_scan_kernel<<<1, 1024, 0, st>>>(p);
     huff_pack_kernel<<<ntiles, kPackThreads, 0, st>>>(p);
-    huff_revert_kernel<<<(unsigned)std::min<size_t>(((n * 8 + 32) / 32 + 255) / 256, (size_t)s->dev->sm_count * 8), 256, 0, st>>>(
-        d_in, n, d_out, out_cap, s->d_counter, d_final_bytes, s->d_err);
+    if (d_out_bits) {
+        IE_CUDA(cudaMemcpyAsync(d_out_bits, s->d_counter, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    } else {
+        huff_revert_kernel<<<(unsigned)std::min<size_t>(((n * 8 + 32) / 32 + 255) / 256, (size_t)s->dev->sm_count * 8), 256, 0, st>>>(
+            d_in, n, d_out, out_cap, s->d_counter, d_final_bytes, s->d_err);
+    }
     count_launch(5);
     IE_CUDA(cudaGetLastError());
     return IE_OK;
@@ -1008,6 +1022,21 @@ int ie_huffman_encode_dev(ie_session *s, const uint8_t *d_in, size_t n, uint8_t 
     // the 27.7 MB stream; through the stream-ordered callback of ie_huffman_encode_async_dev one isolated call takes 0.25 ms,
     // but two sessions overlap to 0.144 ms per call)
     return huffman_encode_sync(s, d_in, n, d_out, out_cap, out_bytes, st);
+}
+
+int ie_byte_histogram_async_dev(ie_session *s, const uint8_t *d_in, size_t n, uint32_t *d_hist, uint64_t *d_first, void *stream) {
+    if (!s || !d_in || !d_hist || !d_first || n == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    IE_TRY(ensure_scratch(s, kHuffScratch));
+    unsigned *d_first_cta = reinterpret_cast<unsigned *>(s->d_scratch + 256 * 8 + 256 * 4 + sizeof(HuffCodes) + 64);
+    return launch_byte_histogram(d_in, n, d_hist, reinterpret_cast<unsigned long long *>(d_first), d_first_cta, s->dev->sm_count, (cudaStream_t)stream);
+}
+
+int ie_huffman_encode_shard_async_dev(ie_session *s, const uint8_t *d_in, size_t n, const uint32_t *d_hist, const uint64_t *d_first,
+                                      int write_dictionary, uint8_t *d_out, size_t out_cap, uint64_t *d_out_bits, void *stream) {
+    if (!s || !d_in || !d_out || !d_hist || !d_first || !d_out_bits || n == 0) { set_error("NULL/empty argument"); return IE_EINVAL; }
+    if ((uintptr_t)d_out % 16) { set_error("stream buffers must be 16-byte aligned"); return IE_EINVAL; }
+    return huffman_encode_async(s, d_in, n, d_out, out_cap, nullptr, (cudaStream_t)stream, d_hist, reinterpret_cast<const unsigned long long *>(d_first),
+                                write_dictionary, reinterpret_cast<unsigned long long *>(d_out_bits));
 }
 
 int ie_huffman_encode_shard_dev(ie_session *s, const uint8_t *d_in, size_t n, const uint32_t *hist, const uint64_t *first_pos,

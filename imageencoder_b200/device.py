@@ -166,6 +166,17 @@ def huffman_encode_async_dev(s: Session, d_in: torch.Tensor, in_bytes: int, d_ou
     check(lib().ie_huffman_encode_async_dev(s.h, _dp(d_in), in_bytes, _dp(d_out), d_out.numel(), _dp(d_out_bytes), _stream()))
 
 
+def byte_histogram_async_dev(s: Session, d_in: torch.Tensor, n: int, d_hist: torch.Tensor, d_first: torch.Tensor) -> None:
+    """histogram (int32 tensor [256]) and first occurrences (int64 tensor [256], -1 = absent) on the device, no synchronisation"""
+    check(lib().ie_byte_histogram_async_dev(s.h, _dp(d_in), n, _dp(d_hist), _dp(d_first), _stream()))
+
+
+def huffman_encode_shard_async_dev(s: Session, d_in: torch.Tensor, n: int, d_hist: torch.Tensor, d_first: torch.Tensor, write_dictionary: bool,
+                                   d_out: torch.Tensor, d_out_bits: torch.Tensor) -> None:
+    check(lib().ie_huffman_encode_shard_async_dev(s.h, _dp(d_in), n, _dp(d_hist), _dp(d_first), int(bool(write_dictionary)), _dp(d_out),
+                                                  d_out.numel(), _dp(d_out_bits), _stream()))
+
+
 def huffman_encode_shard_dev(s: Session, d_in: torch.Tensor, in_bytes: int, hist, first_pos, write_dictionary: bool,
                              d_out: torch.Tensor, d_out_bits: torch.Tensor) -> None:
     """Huffman stage of one shard with the GLOBAL histogram / first-occurrence positions (host arrays)."""

@@ -332,6 +332,101 @@ class ShardedHuffmanStage:
         torch.cuda.synchronize()
         return int(self.d_bits.item())
 
+    # -- steps 1-4 on the device: nothing here reads a value back.  dev_head / dev_histogram / dev_encode / dev_place are the
+    #    four steps between the three exchanges (tests with emulated ranks call them rank by rank); run_device strings them
+    #    together with the caller's collectives.
+    def dev_head(self, pl: list[ShardPlacement], rank: int):
+        """int64 device tensor [1]: the bits this rank has of the byte it shares with its left neighbour(s)"""
+        import torch
+        p = pl[rank]
+        self.b0, self.b1 = shard_byte_range(pl, rank)
+        self.n = self.b1 - self.b0
+        if rank > 0 and p.global_bit % 8 and p.nbits:
+            i = p.global_bit // 8 - p.byte_offset
+            return self.enc.d_aligned[i:i + 1].to(torch.int64)
+        return torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def dev_histogram(self, pl: list[ShardPlacement], rank: int, heads):
+        """heads: int64 device tensor [world].  Returns (histogram, first occurrences in stream coordinates; 2^62 = absent),
+        int64 device tensors [256]: what the sum / min all-reduce takes"""
+        import torch
+
+        from . import device
+        world, p, n = len(pl), pl[rank], self.n
+        BIG = 1 << 62
+        if n:
+            last = self.b1 - 1
+            r = rank + 1
+            while r < world and pl[r].global_bit // 8 == last and pl[r].global_bit % 8:
+                if pl[r].nbits:
+                    self.enc.d_aligned[last - p.byte_offset] |= heads[r].to(torch.uint8)
+                r += 1
+        if not hasattr(self, "d_hist"):
+            self.d_hist = torch.zeros(256, dtype=torch.int32, device="cuda")
+            self.d_first = torch.zeros(256, dtype=torch.int64, device="cuda")
+            self.d_cb = torch.zeros(1, dtype=torch.int64, device="cuda")
+            self.d_params2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+        if not n:
+            return torch.zeros(256, dtype=torch.int64, device="cuda"), torch.full((256,), BIG, dtype=torch.int64, device="cuda")
+        self.d_plain[:n].copy_(self.enc.d_aligned[self.b0 - p.byte_offset: self.b1 - p.byte_offset])
+        device.byte_histogram_async_dev(self.sess, self.d_plain, n, self.d_hist, self.d_first)
+        f = torch.where(self.d_first < 0, torch.full_like(self.d_first, BIG), self.d_first + self.b0)
+        return self.d_hist.to(torch.int64), f
+
+    def dev_encode(self, rank: int, hist_g, first_g):
+        """codes this rank's bytes with the dictionary of the whole stream (built by a host callback in stream order); returns its
+        code bit count, int64 device tensor [1]"""
+        import torch
+
+        from . import device
+        if self.n:
+            device.huffman_encode_shard_async_dev(self.sess, self.d_plain, self.n, hist_g.to(torch.int32).contiguous(), first_g.contiguous(),
+                                                  rank == 0, self.d_code, self.d_cb)
+        else:
+            self.d_cb.zero_()
+        return self.d_cb
+
+    def dev_place(self, pl: list[ShardPlacement], rank: int, cb) -> None:
+        """cb: the ranks' code bit counts, int64 device tensor [world].  Shifts this rank's shard to its place in self.d_out --
+        or, by the revert rule over all shards (Huffman.cpp:329-341), its raw bytes behind the '0' bit"""
+        import torch
+
+        from . import device
+        excl = torch.cumsum(cb, 0) - cb
+        reverted = (cb.sum() + 7) // 8 > total_bytes(pl)
+        zero2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+        par_code = torch.stack([cb[rank], excl[rank]])
+        par_rev = torch.tensor([8 * self.n, 1 + 8 * self.b0], dtype=torch.int64, device="cuda")
+        # both shifts are enqueued; the one that does not apply gets (0 bits at offset 0) and writes nothing
+        self.d_params.copy_(torch.where(reverted, zero2, par_code))
+        device.stream_shift_dev(self.d_code, self.d_params, self.d_out)
+        self.d_params2.copy_(torch.where(reverted, par_rev, zero2))
+        device.stream_shift_dev(self.d_plain, self.d_params2, self.d_out)
+
+    def run_device(self, pl: list[ShardPlacement], rank: int, gather=None, reduce_=None):
+        """`gather(out, t)`: all-gather of an int64 tensor [1] per rank into out [world]; `reduce_(t, "sum" | "min")`: in-place
+        all-reduce of an int64 tensor [256]; both None for a single rank.  Returns the ranks' code bit counts (int64 device
+        tensor [world]); the shifted shard is in self.d_out."""
+        import torch
+        world = len(pl)
+
+        def all_gather(t):
+            out = torch.empty(world, dtype=torch.int64, device="cuda")
+            if gather:
+                gather(out, t)
+            else:
+                out.copy_(t)
+            return out
+
+        heads = all_gather(self.dev_head(pl, rank))                         # exchange 1
+        h, f = self.dev_histogram(pl, rank, heads)
+        if reduce_:                                                         # exchange 2
+            reduce_(h, "sum")
+            reduce_(f, "min")
+        cb = all_gather(self.dev_encode(rank, h, f))                        # exchange 3
+        self.dev_place(pl, rank, cb)
+        return cb
+
     # -- step 4: place the shard (or, by the reference's revert rule, the raw bytes behind a '0' bit) -----------------------
     def place(self, code_bits: list[int], plain_pl: list[ShardPlacement], rank: int) -> tuple[list[ShardPlacement], bool]:
         from . import device
@@ -354,7 +449,33 @@ class ShardedHuffmanStage:
 
 
 def sharded_image_encode_huffman(enc: ShardedImageEncoder, stage: ShardedHuffmanStage, d_raw, quant, rle: bool, rank: int, group=None):
-    """Block-row sharded encode + Huffman stage over `torch.distributed`.  Returns (placements of the Huffman shards, this
+    """Block-row sharded encode + Huffman stage over `torch.distributed`, device-resident: the host reads the shards' plain bit
+    totals once (every size below follows from them) and the code bit totals once at the end (the caller needs the placements);
+    the three exchanges in between run on device tensors, the dictionary is built by a stream-ordered host callback
+    (ie_huffman_encode_shard_async_dev).  Returns (placements of the Huffman shards, this rank's aligned shard bytes as a
+    device tensor view)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    totals = enc.encode(d_raw, quant, rle, rank, lead_bit=False, group=group)
+    pl = place_shards([int(b) for b in totals.cpu().tolist()])                  # synchronisation 1 of 2
+    gather = (lambda out, t: dist.all_gather_into_tensor(out, t, group=group)) if world > 1 else None
+    reduce_ = (lambda t, op: dist.all_reduce(t, op=(dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN), group=group)) if world > 1 else None
+    cb = stage.run_device(pl, rank, gather, reduce_)
+    code_bits = [int(x) for x in cb.cpu().tolist()]                             # synchronisation 2 of 2
+    reverted = total_bytes(pl) < (sum(code_bits) + 7) // 8
+    if reverted:
+        ranges = [shard_byte_range(pl, r) for r in range(len(pl))]
+        hpl = place_shards([8 * (b1 - b0) + (1 if r == 0 else 0) for r, (b0, b1) in enumerate(ranges)])
+    else:
+        hpl = place_shards(code_bits)
+    return hpl, stage.d_out[: hpl[rank].nbytes]
+
+
+def sharded_image_encode_huffman_host(enc: ShardedImageEncoder, stage: ShardedHuffmanStage, d_raw, quant, rle: bool, rank: int, group=None):
+    """The round-1 orchestration of the same stage (every exchange visits the host; eight synchronisations per image), kept as a
+    cross-check of sharded_image_encode_huffman.  Block-row sharded encode + Huffman stage over `torch.distributed`.  Returns (placements of the Huffman shards, this
     rank's aligned shard bytes as a device tensor view)."""
     import numpy as np
     import torch

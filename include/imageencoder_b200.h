@@ -189,6 +189,15 @@ int ie_huffman_encode_shard_dev(ie_session *s, const uint8_t *d_in, size_t in_by
 /* Device histogram + first-occurrence positions of a byte stream (Huffman.cpp:236-243); hist[256] u32,
  * first_pos[256] u64 (UINT64_MAX = absent).  HOST outputs; synchronises `stream`. */
 int ie_byte_histogram_dev(const uint8_t *d_in, size_t in_bytes, uint32_t *hist, uint64_t *first_pos, void *stream);
+/* The same two steps with everything on the device and no host synchronisation: histogram and first occurrences into device
+ * arrays (absent symbols: first = UINT64_MAX), so that the caller's collective (sum of the histograms, minimum of the offset
+ * first occurrences) runs on them directly; the shard is then coded from the reduced device arrays -- the dictionary is built by
+ * a stream-ordered host callback, as in ie_huffman_encode_async_dev -- and its bit count is left in *d_out_bits (device).
+ * The revert rule (Huffman.cpp:329-341) is the caller's: it needs every shard's count.  out_cap >= 2080. */
+int ie_byte_histogram_async_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes, uint32_t *d_hist, uint64_t *d_first, void *stream);
+int ie_huffman_encode_shard_async_dev(ie_session *s, const uint8_t *d_in, size_t in_bytes, const uint32_t *d_hist,
+                                      const uint64_t *d_first, int write_dictionary, uint8_t *d_out, size_t out_cap,
+                                      uint64_t *d_out_bits, void *stream);
 
 int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv420, size_t yuv_bytes, uint32_t width, uint32_t height,
                         const uint16_t *quant, int use_rle, uint32_t gop, uint32_t merange, int lead_bit,

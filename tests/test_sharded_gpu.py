@@ -137,6 +137,23 @@ def test_sharded_huffman_stage_matches_single_stream(gpu, oracle_mod):
             merge_shard_into(stream, stages[r].d_out[: hpl[r].nbytes].cpu().numpy().tobytes(), hpl[r])
         got = bytes(stream[: total_bytes(hpl)])
         assert got == want, f"{matrix} x{world}: sharded Huffman stream differs ({len(got)} vs {len(want)} bytes, reverted={reverted})"
+        # the same stage device-resident (what sharded_image_encode_huffman runs): the four steps between the three exchanges,
+        # rank by rank, the exchanges done with torch ops -- nothing is read back before the placements
+        stages2 = [ShardedHuffmanStage(e) for e in encs]
+        heads_d = torch.cat([stages2[r].dev_head(pl, r) for r in range(world)])
+        hf_d = [stages2[r].dev_histogram(pl, r, heads_d) for r in range(world)]
+        h_g = torch.stack([h for h, _ in hf_d]).sum(0)
+        f_g = torch.stack([f for _, f in hf_d]).min(0).values
+        cb = torch.cat([stages2[r].dev_encode(r, h_g, f_g).clone() for r in range(world)])
+        for r in range(world):
+            stages2[r].dev_place(pl, r, cb)
+        torch.cuda.synchronize()
+        code_bits2 = [int(x) for x in cb.cpu().tolist()]
+        assert code_bits2 == code_bits
+        stream2 = bytearray()
+        for r in range(world):
+            merge_shard_into(stream2, stages2[r].d_out[: hpl[r].nbytes].cpu().numpy().tobytes(), hpl[r])
+        assert bytes(stream2[: total_bytes(hpl)]) == want, f"{matrix} x{world}: device-resident sharded Huffman stage differs"
 
 
 def test_gop_shards_stitch_to_single_video_stream(gpu, oracle_mod):
