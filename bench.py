@@ -673,8 +673,10 @@ def ours_sharded(args):
             hgot = bytes(stream[: total_bytes(hpl)])
             huff = {"ms_per_image_plain_plus_huffman": h_ms, "encoded_bytes": len(hgot),
                     "parity_sha_ok": (bool(sha(hgot) == g["huff"]["enc_sha256"]) if g else None),
-                    "what": "block-row sharded encode + Huffman stage over the global histogram (parallel.py, NCCL all-reduce of "
-                            "256 bins + first occurrences; host tree), wall clock incl. its host synchronisations"}
+                    "what": "block-row sharded encode + Huffman stage over the global histogram (parallel.py: NCCL all-gather of the "
+                            "shared-byte bits, all-reduce of 256 bins + first occurrences, all-gather of the code bit counts, all on "
+                            "device tensors; dictionary by stream-ordered host callback), wall clock incl. its two host "
+                            "synchronisations (plain bit totals, code bit totals)"}
         del enc2, stage
     except Exception as e:      # an extra figure; never fail the encode bench on it
         huff = {"failed": str(e)}
