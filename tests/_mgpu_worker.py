@@ -18,7 +18,7 @@ def main():
     import imageencoder_b200 as ie
     from imageencoder_b200 import _lib
     from imageencoder_b200.parallel import (ShardedHuffmanStage, ShardedImageEncoder, merge_shard_into, place_shards, shard_block_rows,
-                                            sharded_image_encode_huffman, total_bytes)
+                                            sharded_image_encode_huffman, sharded_image_encode_huffman_dev, total_bytes)
     from imageencoder_b200.synth import synth_image
     _lib.check(ie.lib().ie_init(local))
     W, H, N = 1024, 1024, 8
@@ -43,6 +43,14 @@ def main():
     torch.cuda.synchronize()
     hshards = [None] * world
     dist.all_gather_object(hshards, d_h.cpu().numpy().tobytes())
+    # the same stage device-resident (exchanges on device tensors, dictionary by stream-ordered host callback)
+    enc3 = ShardedImageEncoder(W, y1 - y0, N, H)
+    stage3 = ShardedHuffmanStage(enc3)
+    for _ in range(2):
+        hpl3, d_h3 = sharded_image_encode_huffman_dev(enc3, stage3, d_raw, q, True, rank)
+    torch.cuda.synchronize()
+    hshards3 = [None] * world
+    dist.all_gather_object(hshards3, d_h3.cpu().numpy().tobytes())
     # ---- the library's own exchange (ie_comm, csrc/comm.cu): P2P mailboxes instead of the NCCL all-gather, and the single
     #      output stream assembled ON THE DEVICE in rank 0's stitch buffer (no host merge).  Several sizes and both block sizes;
     #      repeated calls on one communicator exercise the epoch / parity logic of the mailboxes.
@@ -104,7 +112,7 @@ def main():
                 ok = False
                 msg.append(f"ie_comm stitch {cw}x{ch} {cn}x{cn}: {len(got)} vs {len(want)} bytes, first diff at "
                            f"{next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), -1)}")
-        for name, parts, places, huff in (("plain", shards, pl, False), ("huffman", hshards, hpl, True)):
+        for name, parts, places, huff in (("plain", shards, pl, False), ("huffman", hshards, hpl, True), ("huffman, device-resident", hshards3, hpl3, True)):
             stream = bytearray()
             for r in range(world):
                 merge_shard_into(stream, parts[r], places[r])

@@ -137,7 +137,7 @@ def test_sharded_huffman_stage_matches_single_stream(gpu, oracle_mod):
             merge_shard_into(stream, stages[r].d_out[: hpl[r].nbytes].cpu().numpy().tobytes(), hpl[r])
         got = bytes(stream[: total_bytes(hpl)])
         assert got == want, f"{matrix} x{world}: sharded Huffman stream differs ({len(got)} vs {len(want)} bytes, reverted={reverted})"
-        # the same stage device-resident (what sharded_image_encode_huffman runs): the four steps between the three exchanges,
+        # the same stage device-resident (what sharded_image_encode_huffman_dev runs): the four steps between the three exchanges,
         # rank by rank, the exchanges done with torch ops -- nothing is read back before the placements
         stages2 = [ShardedHuffmanStage(e) for e in encs]
         heads_d = torch.cat([stages2[r].dev_head(pl, r) for r in range(world)])
