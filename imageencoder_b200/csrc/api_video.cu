@@ -393,6 +393,23 @@ __global__ void __launch_bounds__(256) mc_copy_batch_kernel(const MCBatchParams 
     *reinterpret_cast<uint2 *>(dp) = make_uint2(__byte_perm(w0, w1, sel), __byte_perm(w1, w2, sel));
 }
 
+// the same without the copy: clamp(MB + mv) of every MacroBlock, for the block decoder that reads its prediction from the
+// reference frame itself (DecodeParams::mc_coord)
+__global__ void __launch_bounds__(256) mc_coord_batch_kernel(const MCBatchParams p, short *coord) {
+    pdl_wait();
+    const int mb = blockIdx.x * 256 + threadIdx.x;
+    if (mb >= p.nmb) return;
+    const unsigned f = p.first_frame + blockIdx.y * p.gop;
+    const int mbx = (mb % p.mx) * kMB, mby = (mb / p.mx) * kMB;
+    const unsigned long long base = p.rec[f].first - (unsigned long long)p.nmb * 2 * p.mvbits + (unsigned long long)mb * 2 * p.mvbits;
+    const int sh = 16 - (int)p.mvbits;
+    const int vx = (int)(short)(unsigned short)(read_bits_dev(p.enc, p.enc_bits, min(base, p.enc_bits), p.mvbits) << sh) >> sh;   // Block.cpp:484-485
+    const int vy = (int)(short)(unsigned short)(read_bits_dev(p.enc, p.enc_bits, min(base + p.mvbits, p.enc_bits), p.mvbits) << sh) >> sh;
+    short *c = coord + ((size_t)blockIdx.y * p.nmb + mb) * 2;
+    c[0] = (short)clampi((int)(short)(mbx + vx), 0, p.W - kMB);
+    c[1] = (short)clampi((int)(short)(mby + vy), 0, p.H - kMB);
+}
+
 __global__ void fill_uv_kernel(uint8_t *yuv, size_t ysz, size_t fsz, unsigned frames) {
     const size_t uv = fsz - ysz;
     const size_t total = uv * frames;
@@ -684,6 +701,8 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
     std::vector<unsigned long long> consts(ngops + 1, (unsigned long long)enc_bytes * 8ull);
     consts[ngops] = (unsigned long long)h.end_bit;
     IE_CUDA(cudaMemcpyAsync(d_totals, consts.data(), consts.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    VideoScratch vs;
+    IE_TRY(video_scratch(s, nmb, ngops, vs));                 // vs.copy: clamped prediction coordinates of a frame slot
     VideoParse v;
     ParseParamsOpaque po;
     IE_TRY(launch_video_parse(d_enc, d_totals, d_totals + ngops, h.use_rle, nblocks, nmb * 2 * mvbits, frames, gop, z, s->d_parse, v, po, st));
@@ -718,11 +737,17 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
                 MCBatchParams mc;
                 mc.enc = d_enc; mc.enc_bits = consts[0]; mc.rec = v.rec; mc.first_frame = f0 + k; mc.gop = gop; mc.mvbits = mvbits; mc.out = d_out; mc.fsz = fsz;
                 mc.W = (int)W; mc.H = (int)H; mc.mx = (int)(W / kMB); mc.nmb = (int)nmb;
-                if (launch_pdl(mc_copy_batch_kernel, dim3((nmb + 7) / 8, nimg), dim3(256), 0, st2, mc) != cudaSuccess) { rc = IE_ECUDA; break; }
+                if (!motioncomp) {                                                // Frame.cpp:107-117: the motion-compensated copy only
+                    if (launch_pdl(mc_copy_batch_kernel, dim3((nmb + 7) / 8, nimg), dim3(256), 0, st2, mc) != cudaSuccess) { rc = IE_ECUDA; break; }
+                    count_launch();
+                    continue;
+                }
+                // with residuals the copy is folded into the block decoder: only the clamped coordinates are prepared here
+                if (launch_pdl(mc_coord_batch_kernel, dim3((nmb + 255) / 256, nimg), dim3(256), 0, st2, mc, vs.copy) != cudaSuccess) { rc = IE_ECUDA; break; }
                 count_launch();
-                if (!motioncomp) continue;                                        // Frame.cpp:107-117
             }
             p.add_mode = k > 0 ? 1 : 0;
+            p.mc_coord = k > 0 ? vs.copy : nullptr; p.ref_delta = fsz; p.mbx = W / kMB; p.mc_stride = nmb;
             rc = launch_video_emit(v, po, f0 + k, nimg, s->d_block_off, st2);
             if (rc == IE_OK) rc = launch_decode_blocks(p, nimg, st2);
         }

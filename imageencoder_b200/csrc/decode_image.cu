@@ -137,6 +137,15 @@ __constant__ unsigned char c_zz8[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 
                                         41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                         30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
+// four bytes at any alignment from the two aligned words that hold them
+__device__ __forceinline__ unsigned load_u8x4_any(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
+    const unsigned k = (unsigned)(a & 3);
+    const unsigned w0 = __ldg(wp), w1 = k ? __ldg(wp + 1) : 0u;
+    return __byte_perm(w0, w1, 0x3210u + 0x1111u * k);
+}
+
 struct BitReader {
     const unsigned *words;
     unsigned long long nwords, total;
@@ -249,6 +258,14 @@ __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
     uint8_t *dst = p.out + (size_t)img * p.out_stride + (size_t)(byi * N) * p.pitch + (size_t)bxi * N;
     unsigned outw[N * (N / 4)];
     unsigned long long unsure = 0;
+    // ADD mode (N = 4, P-frames): where the prediction comes from, and the four words read from there (the exact path needs them)
+    const uint8_t *pred = nullptr;
+    unsigned predw[N];
+    if (ADD && N == 4 && p.mc_coord) {
+        const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
+        const short *mc = p.mc_coord + ((size_t)img * p.mc_stride + mb) * 2;
+        pred = p.out + (size_t)img * p.out_stride - p.ref_delta + (size_t)(mc[1] + (int)(byi & 3) * 4) * p.pitch + (mc[0] + (int)(bxi & 3) * 4);
+    }
     if (VAR == 1 && !ADD) {
         // variant 1 (transform_fast.cuh, lean::): inverse transform and pixel stage in packed f32x2 operations, same bits
         float2 x2[NN / 2], p2[NN / 2];
@@ -266,7 +283,9 @@ __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
         unsigned curw[N / 4];
         if (ADD) {
             if (N == 8) { const uint2 c2 = *reinterpret_cast<const uint2 *>(dst + (size_t)y * p.pitch); curw[0] = c2.x; curw[N / 4 - 1] = c2.y; }
+            else if (pred) curw[0] = load_u8x4_any(pred + (size_t)y * p.pitch);            // Block.cpp:481-496 folded in
             else curw[0] = *reinterpret_cast<const unsigned *>(dst + (size_t)y * p.pitch);
+            if (N == 4) predw[y] = curw[0];
         }
 #pragma unroll
         for (int q4 = 0; q4 < N / 4; q4++) {
@@ -302,7 +321,15 @@ __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
             acc = __dadd_rn(acc, __dmul_rn(__ldg(tab->inv + uv * NN + ij), d));         // algo.cpp:352-355
         }
         double v = __dadd_rn(acc, 128.0);                                               // Block.cpp:173-175
-        if (ADD) v = __dadd_rn((double)(int)dst[(size_t)(ij / N) * p.pitch + (ij % N)], v);   // Block.cpp:114-116
+        if (ADD) {                                                                       // Block.cpp:114-116
+            unsigned pw = 0;
+            if (N == 4) {
+#pragma unroll
+                for (int r = 0; r < N; r++) if (r == ij / N) pw = predw[r];
+            }
+            const int pp = (N == 4) ? (int)((pw >> (8 * (ij % N))) & 0xffu) : (int)dst[(size_t)(ij / N) * p.pitch + (ij % N)];
+            v = __dadd_rn((double)pp, v);
+        }
         const unsigned px = clamp_trunc_u8(v);
         const int wi = ij >> 2, bsh = 8 * (ij & 3);
 #pragma unroll

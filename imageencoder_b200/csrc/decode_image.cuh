@@ -27,6 +27,13 @@ struct DecodeParams {
     // launch_decode_blocks decodes blocks [block_base, block_end) of every image; block_end = 0 means nblocks (stripes of the
     // host entry point: a stripe's pixels leave for the host while the next stripe is decoded)
     unsigned block_base, block_end;
+    // add_mode with the motion-compensated copy folded in (whole-stream video decode): the prediction of a block is read from
+    // the reference frame at the MacroBlock's clamped coordinate instead of from the output (where mc_copy_kernel would have
+    // put it).  mc_coord: [images][nmb][2] shorts (x, y), NULL = predict from the output; the reference frame of image i
+    // starts ref_delta bytes before its own pixels; mbx = MacroBlocks per row.
+    const short *mc_coord;
+    size_t ref_delta;
+    unsigned mbx, mc_stride;
 };
 
 // ---- whole-stream video parse (parse.cu) ----
