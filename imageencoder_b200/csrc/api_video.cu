@@ -690,14 +690,16 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
     const VideoParseSizes z = video_parse_sizes(enc_bytes, frames, s->dev->sm_count);
     IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, z.bytes));
     // block offsets of one frame slot (frame k of every GOP), then the stream's size once per GOP and the first frame's bit
-    const size_t need_off = ((size_t)ngops * (nblocks + 1) + ngops + 2) * sizeof(unsigned long long) + 64;
+    const uint32_t nbatches = std::min<uint32_t>(5, ngops), gpb = (ngops + nbatches - 1) / nbatches;      // GOP batches (below)
+    const size_t batch_frames = (size_t)gpb * gop;
+    const size_t need_off = (batch_frames * (nblocks + 1) + ngops + 2) * sizeof(unsigned long long) + 64;
     if (s->block_off_cap < need_off) {
         if (s->d_block_off) IE_CUDA(cudaFree(s->d_block_off));
         s->d_block_off = nullptr; s->block_off_cap = 0;
         IE_CUDA(cudaMalloc(&s->d_block_off, need_off));
         s->block_off_cap = need_off;
     }
-    unsigned long long *d_totals = s->d_block_off + (size_t)ngops * (nblocks + 1);
+    unsigned long long *d_totals = s->d_block_off + batch_frames * (nblocks + 1);
     std::vector<unsigned long long> consts(ngops + 1, (unsigned long long)enc_bytes * 8ull);
     consts[ngops] = (unsigned long long)h.end_bit;
     IE_CUDA(cudaMemcpyAsync(d_totals, consts.data(), consts.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
@@ -719,7 +721,6 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
     // decodes frame by frame over their output.
     IE_TRY(session_ensure_pipeline(s));
     cudaStream_t st2 = s->stream_in;
-    const uint32_t nbatches = std::min<uint32_t>(5, ngops), gpb = (ngops + nbatches - 1) / nbatches;
     cudaEvent_t ev_join = nullptr;
     IE_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     int rc = IE_OK;
@@ -730,6 +731,11 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
         cudaEvent_t ev = s->ev_in[(g0 / gpb) % ie_session::kMaxStripes];
         if (rc == IE_OK && cudaEventRecord(ev, st) != cudaSuccess) rc = IE_ECUDA;
         if (rc == IE_OK && cudaStreamWaitEvent(st2, ev, 0) != cudaSuccess) rc = IE_ECUDA;
+        // the offsets of every frame of the batch in one launch (frame f0 + i -> array i); a frame slot then reads every gop-th
+        // (without motion compensation only the I-frames are decoded: array i = the first frame of the batch's GOP i)
+        if (rc == IE_OK) rc = motioncomp ? launch_video_emit(v, po, f0, 1, f1 - f0, s->d_block_off, st2)
+                                         : launch_video_emit(v, po, f0, gop, (f1 - f0 + gop - 1) / gop, s->d_block_off, st2);
+        p.block_off_stride = motioncomp ? (size_t)gop * (nblocks + 1) : 0;
         for (uint32_t k = 0; k < gop && f0 + k < f1 && rc == IE_OK; k++) {
             const uint32_t nimg = (f1 - f0 - k + gop - 1) / gop;                  // GOPs of the batch that have a frame k
             p.out = d_out + (size_t)(f0 + k) * fsz;
@@ -748,8 +754,8 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
             }
             p.add_mode = k > 0 ? 1 : 0;
             p.mc_coord = k > 0 ? vs.copy : nullptr; p.ref_delta = fsz; p.mbx = W / kMB; p.mc_stride = nmb;
-            rc = launch_video_emit(v, po, f0 + k, nimg, s->d_block_off, st2);
-            if (rc == IE_OK) rc = launch_decode_blocks(p, nimg, st2);
+            p.block_off = s->d_block_off + (size_t)k * (nblocks + 1);
+            rc = launch_decode_blocks(p, nimg, st2);
         }
     }
     // join: the caller's stream continues after the second stream's last kernel

@@ -40,7 +40,7 @@ __global__ void parse_blocks_kernel(const DecodeParams p) {
     const uint8_t *s = p.enc + (size_t)img * p.enc_stride;
     const unsigned long long total = p.enc_bits[img];
     unsigned long long pos = p.cursor ? (*p.cursor + p.skip_bits) : p.start_bit[img];
-    unsigned long long *off = p.block_off + (size_t)img * (p.nblocks + 1);
+    unsigned long long *off = p.block_off + (size_t)img * (p.block_off_stride ? p.block_off_stride : (size_t)p.nblocks + 1);
     const int NN = p.N * p.N;
     for (unsigned k = 0; k < p.nblocks; k++) {
         off[k] = pos;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecodeParams p
     if (gb >= (p.block_end ? p.block_end : p.nblocks)) return;
     const uint8_t *s = p.enc + (size_t)img * p.enc_stride;
     const unsigned long long total = p.enc_bits[img];
-    const unsigned long long *off = p.block_off + (size_t)img * (p.nblocks + 1);
+    const unsigned long long *off = p.block_off + (size_t)img * (p.block_off_stride ? p.block_off_stride : (size_t)p.nblocks + 1);
     const BlockTables *tab = p.tab;
 
     unsigned long long pos = off[gb];
@@ -197,7 +197,7 @@ __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
     const unsigned range_end = p.block_end ? p.block_end : p.nblocks;
     const uint8_t *s = p.enc + (size_t)img * p.enc_stride;
     const unsigned long long total = p.enc_bits[img];
-    const unsigned long long *off = p.block_off + (size_t)img * (p.nblocks + 1);
+    const unsigned long long *off = p.block_off + (size_t)img * (p.block_off_stride ? p.block_off_stride : (size_t)p.nblocks + 1);
     const BlockTables *tab = p.tab;
     const StagedStream st = stage_stream(s_bits, kStage, s, total, off[first], off[min(first + 128u, range_end)] + kMaxBlockBits);
     if (gb >= range_end) return;

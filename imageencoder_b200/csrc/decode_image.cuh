@@ -34,6 +34,7 @@ struct DecodeParams {
     const short *mc_coord;
     size_t ref_delta;
     unsigned mbx, mc_stride;
+    size_t block_off_stride;                // entries between the offset arrays of consecutive images; 0 = nblocks + 1
 };
 
 // ---- whole-stream video parse (parse.cu) ----
@@ -66,8 +67,8 @@ int launch_video_parse(const uint8_t *d_enc, const unsigned long long *d_enc_bit
                        unsigned nblocks, unsigned mv_bits, unsigned frames, unsigned gop, const VideoParseSizes &z, uint8_t *scratch,
                        VideoParse &v, ParseParamsOpaque &popaque, cudaStream_t stream);
 int launch_video_chain(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned f0, unsigned f1, cudaStream_t stream);
-int launch_video_emit(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned first_frame, unsigned nimg, unsigned long long *block_off,
-                      cudaStream_t stream);
+int launch_video_emit(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned first_frame, unsigned frame_step, unsigned nimg,
+                      unsigned long long *block_off, cudaStream_t stream);
 
 // ---- sharded decode of one image stream (parse.cu) ----
 struct ShardedParseGeom { unsigned ctas_per_part, groups_per_part; size_t chunk_bytes, spec_bytes; };

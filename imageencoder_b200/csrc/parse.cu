@@ -997,11 +997,12 @@ __global__ void __launch_bounds__(kVChainThreads) vparse_chain_kernel(const Pars
     }
 }
 
-// block_off[img][0 .. nblocks] of frame slot + img * gop (img = blockIdx.y) from the frame's pieces
-__global__ void __launch_bounds__(kVTH) vparse_emit_kernel(const ParseParams p, const VideoParse v, unsigned first_frame, unsigned long long *block_off) {
+// block_off[img][0 .. nblocks] of frame first_frame + img * frame_step (img = blockIdx.y) from the frame's pieces
+__global__ void __launch_bounds__(kVTH) vparse_emit_kernel(const ParseParams p, const VideoParse v, unsigned first_frame, unsigned frame_step,
+                                                           unsigned long long *block_off) {
     pdl_wait();
     extern __shared__ __align__(16) unsigned s_stage[];
-    const unsigned f = first_frame + blockIdx.y * v.gop;
+    const unsigned f = first_frame + blockIdx.y * frame_step;
     const VFrameRec *rec = v.rec + f;
     unsigned long long *off = block_off + (size_t)blockIdx.y * (v.nblocks + 1);
     const unsigned long long total = *p.enc_bits;
@@ -1104,13 +1105,13 @@ int launch_video_chain(const VideoParse &v, const ParseParamsOpaque &popaque, un
     return IE_OK;
 }
 
-int launch_video_emit(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned first_frame, unsigned nimg, unsigned long long *block_off,
-                      cudaStream_t stream) {
+int launch_video_emit(const VideoParse &v, const ParseParamsOpaque &popaque, unsigned first_frame, unsigned frame_step, unsigned nimg,
+                      unsigned long long *block_off, cudaStream_t stream) {
     const ParseParams &p = *reinterpret_cast<const ParseParams *>(&popaque);
     const size_t stage_bytes = (size_t)SpecCfg<kVG, kVTH>::kStageWords * sizeof(unsigned);
     static bool configured = false;
     if (!configured) { IE_CUDA(cudaFuncSetAttribute(vparse_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes)); configured = true; }
-    IE_CUDA(launch_pdl(vparse_emit_kernel, dim3(48, nimg), dim3(kVTH), stage_bytes, stream, p, v, first_frame, block_off));
+    IE_CUDA(launch_pdl(vparse_emit_kernel, dim3(48, nimg), dim3(kVTH), stage_bytes, stream, p, v, first_frame, frame_step, block_off));
     count_launch();
     IE_CUDA(cudaGetLastError());
     return IE_OK;
