@@ -674,6 +674,7 @@ namespace ie {
 // 1 = whole-stream parse + frame k of every GOP per launch (default), 0 = frame by frame (also the fallback for truncated and
 // damaged streams)
 std::atomic<int> g_video_decode_variant{1};
+std::atomic<int> g_video_decode_batches{4};      // GOP batches of the whole-stream decode (chain of batch b+1 next to the reconstruction of batch b)
 std::atomic<uint64_t> g_stat_video_whole{0}, g_stat_video_frames{0};
 
 // Returns IE_OK with done = false when the stream is not a plain well-formed one (the caller then decodes frame by frame).
@@ -690,7 +691,7 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
     const VideoParseSizes z = video_parse_sizes(enc_bytes, frames, s->dev->sm_count);
     IE_TRY(session_reserve(&s->d_parse, &s->parse_cap, z.bytes));
     // block offsets of one frame slot (frame k of every GOP), then the stream's size once per GOP and the first frame's bit
-    const uint32_t nbatches = std::min<uint32_t>(5, ngops), gpb = (ngops + nbatches - 1) / nbatches;      // GOP batches (below)
+    const uint32_t nbatches = std::min<uint32_t>((uint32_t)g_video_decode_batches.load(), ngops), gpb = (ngops + nbatches - 1) / nbatches;      // GOP batches (below)
     const size_t batch_frames = (size_t)gpb * gop;
     const size_t need_off = (batch_frames * (nblocks + 1) + ngops + 2) * sizeof(unsigned long long) + 64;
     if (s->block_off_cap < need_off) {
@@ -714,7 +715,7 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
     p.enc = d_enc; p.enc_stride = 0; p.enc_bits = d_totals; p.start_bit = d_totals; p.block_off = s->d_block_off; p.nblocks = nblocks;
     p.bx = W / 4; p.N = 4; p.use_rle = h.use_rle; make_quant(p.quant, h.quant, 4); make_k2(p.k2, h.quant, 4); p.tab = s->dev->d_t4; p.pitch = W; p.err = s->d_err;
     p.out_stride = (size_t)gop * fsz;
-    // The frame chain is sequential (one CTA, ~9 us per frame); the reconstruction is not.  GOPs go in up to five batches: the
+    // The frame chain is sequential (one CTA, ~9 us per frame); the reconstruction is not.  GOPs go in up to four batches (tools/ab_video_batches.py: 1 / 2 / 3 / 4 / 5 / 8 / 20 batches = 4.58 / 3.92 / 3.84 / 3.84 / 3.92 / 4.16 / 5.74 ms): the
     // chain of batch b runs on the caller's stream, the reconstruction of batch b on a second stream as soon as the chain has
     // passed it, i.e. next to the chain of batch b + 1.  Everything is enqueued before the one synchronisation below; if the
     // chain gives up (truncated / damaged stream) the batches already enqueued decode empty records (harmless) and the caller
