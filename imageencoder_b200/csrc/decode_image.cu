@@ -55,6 +55,15 @@ __global__ void parse_blocks_kernel(const DecodeParams p) {
     if (p.cursor) *p.cursor = pos;
 }
 
+// four bytes at any alignment from the two aligned words that hold them
+__device__ __forceinline__ unsigned load_u8x4_any(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
+    const unsigned k = (unsigned)(a & 3);
+    const unsigned w0 = __ldg(wp), w1 = k ? __ldg(wp + 1) : 0u;
+    return __byte_perm(w0, w1, 0x3210u + 0x1111u * k);
+}
+
 template <int N, bool ADD>
 __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecodeParams p) {
     constexpr int NN = N * N;
@@ -100,12 +109,19 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecodeParams p
     }
     const unsigned byi = gb / p.bx, bxi = gb - byi * p.bx;
     uint8_t *dst = p.out + (size_t)img * p.out_stride;
+    // P-frames of the whole-stream video decode: the prediction comes from the reference frame (DecodeParams::mc_coord)
+    const uint8_t *pred = nullptr;
+    if (ADD && N == 4 && p.mc_coord) {
+        const unsigned mb = (byi >> 2) * p.mbx + (bxi >> 2);
+        const short *mc = p.mc_coord + ((size_t)img * p.mc_stride + mb) * 2;
+        pred = dst - p.ref_delta + (size_t)(mc[1] + (int)(byi & 3) * 4) * p.pitch + (mc[0] + (int)(bxi & 3) * 4);
+    }
 #pragma unroll
     for (int y = 0; y < N; y++) {
         unsigned lo = 0, hi = 0;
         uint8_t *row = dst + (size_t)(byi * N + y) * p.pitch + (size_t)bxi * N;
         unsigned cur_lo = 0;
-        if (ADD) cur_lo = *reinterpret_cast<const unsigned *>(row);
+        if (ADD) cur_lo = pred ? load_u8x4_any(pred + (size_t)y * p.pitch) : *reinterpret_cast<const unsigned *>(row);
 #pragma unroll
         for (int x = 0; x < N; x++) {
             double v = __dadd_rn(X[y * N + x], 128.0);                           // Block.cpp:173-175
@@ -136,15 +152,6 @@ __constant__ unsigned char c_zz4[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7
 __constant__ unsigned char c_zz8[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                                         41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                         30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-
-// four bytes at any alignment from the two aligned words that hold them
-__device__ __forceinline__ unsigned load_u8x4_any(const uint8_t *p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const unsigned *wp = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
-    const unsigned k = (unsigned)(a & 3);
-    const unsigned w0 = __ldg(wp), w1 = k ? __ldg(wp + 1) : 0u;
-    return __byte_perm(w0, w1, 0x3210u + 0x1111u * k);
-}
 
 struct BitReader {
     const unsigned *words;
