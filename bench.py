@@ -166,6 +166,7 @@ def run_reference_sample(cfg, rows: int, reps: int = 1):
     _, res = oracle.ref_image_encode(img, W, rows, BLOCK, quant_matrix(cfg), True, False, threads=os.cpu_count(), reps=reps,
                                      workdir=workdir)
     ms = res["process_ms"]
+    run_reference_sample.last_io_ms = float(res.get("ctor_ms", 0.0)) + float(res.get("save_ms", 0.0))     # file read + file write
     return [W * rows / (m / 1e3) / 1e6 for m in ms], res["threads"], ms
 
 
@@ -194,6 +195,7 @@ def reference_decode_sample(cfg, rows: int):
     workdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
     _, res = oracle.ref_image_decode(enc, BLOCK, W, rows, threads=os.cpu_count(), workdir=workdir)
     ms = res["process_ms"][-1]
+    reference_decode_sample.last_io_ms = float(res.get("ctor_ms", 0.0)) + float(res.get("save_ms", 0.0))
     return W * rows / (ms / 1e3) / 1e6, res["threads"], ms
 
 
@@ -241,14 +243,20 @@ def cpu_baseline_objects(cfg):
             probe, threads, _ = run_reference_sample(cfg, 256)
             rows = int(min(cfg["H"], max(256, probe[0] * 1e6 * 12.0 / W)) // 8 * 8)
             vals, threads, ms = run_reference_sample(cfg, rows)
+            io = getattr(run_reference_sample, "last_io_ms", 0.0)
             out["cpu_baseline"] = {"value": vals[0], "unit": "Mpixels/s", "cores": threads, "kind": "reference",
                                    "sample": f"{W}x{rows} stripe of the workload image, reference ImageEncoder::process() "
-                                             f"(OpenMP, {ms[0]:.0f} ms)"}
+                                             f"(OpenMP, {ms[0]:.0f} ms)",
+                                   # SURVEY 8d timing (i): what the reference's own "Elapsed time" covers (main.cpp:68, 111-112):
+                                   # constructor (file read) + process() + saveResult() (file write), files on /dev/shm
+                                   "value_incl_file_io": W * rows / ((ms[0] + io) / 1e3) / 1e6, "file_io_ms": io}
             drows = int(min(cfg["H"], max(256, rows // 2)) // 8 * 8)
             dv, dthreads, dms = reference_decode_sample(cfg, drows)
+            dio = getattr(reference_decode_sample, "last_io_ms", 0.0)
             out["decode_cpu_baseline"] = {"value": dv, "unit": "Mpixels/s", "cores": dthreads, "kind": "reference",
                                           "sample": f"stream of a {W}x{drows} stripe of the workload image, reference "
-                                                    f"ImageDecoder::process() (OpenMP, {dms:.0f} ms)"}
+                                                    f"ImageDecoder::process() (OpenMP, {dms:.0f} ms)",
+                                          "value_incl_file_io": W * drows / ((dms + dio) / 1e3) / 1e6, "file_io_ms": dio}
         else:       # oracle/_ref did not travel: the oracle port, one thread, on a smaller stripe
             probe, threads, _ = run_port_sample(cfg, 64)
             rows = int(min(cfg["H"], max(64, probe[0] * 1e6 * 12.0 / W)) // 8 * 8)

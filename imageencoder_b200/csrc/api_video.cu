@@ -5,7 +5,7 @@
 //                      order around the current best; candidate coordinate clamped into the frame (ImageBase.cpp:253-254);
 //                      for p>0 skip when the clamped coordinate is the block's own (Block.cpp:297-301); `<=` so the
 //                      later candidate wins ties (Block.cpp:306); the UNCLAMPED offset is stored (Block.cpp:333-334).
-//   mvec_pack_kernel   all motion vectors of the frame, MVEC_BIT_SIZE bits each, x then y (Block.cpp:415-423)
+//   mvec_pack2_kernel  all motion vectors of the frame, MVEC_BIT_SIZE bits each, x then y (Block.cpp:415-423)
 //   P-frame blocks     encode_tiles_kernel<4,4,PF=true> (encode_image.cu)
 //   mc_copy_kernel     decoder: out[MB] = ref[clamp(MB + mv)] (Block.cpp:481-496)
 // Frames are strictly sequential inside a GOP (each P-frame searches the reconstruction of its predecessor,
@@ -274,21 +274,9 @@ __device__ __forceinline__ uint4 gather_chunk(const FixedFieldTile &t, long long
     return make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
-__global__ void __launch_bounds__(kThreads) mvec_pack_kernel(const short *mv, size_t mv_stride, unsigned nfields, unsigned bits, uint8_t *out,
-                                                             size_t out_stride, size_t out_cap, unsigned long long *bit_counter, int *err) {
-    mv += (size_t)blockIdx.y * mv_stride; out += (size_t)blockIdx.y * out_stride; bit_counter += blockIdx.y;
-    FixedFieldTile t{mv, nfields, bits};
-    ScanState st{};
-    const unsigned long long G = *bit_counter;
-    const unsigned T = nfields * bits;
-    tile_write_chunks(t, st, 0, true, true, G, T, out, out_cap, err);
-    __syncthreads();
-    if (threadIdx.x == 0) *bit_counter = G + T;
-}
-
-
-// The same, a thread per 128-bit chunk of the motion-vector section over as many CTAs as it takes (mvec_pack_kernel walks the
-// section with one CTA per GOP: 43 us per frame slot on config 5).  The chunk that holds the section's first bit already holds
+// All motion vectors of the frame, MVEC_BIT_SIZE bits each, x then y (Block.cpp:415-423): a thread per 128-bit chunk of the
+// motion-vector section over as many CTAs as it takes (the round-1 kernel walked the section with one CTA per GOP: 43 us per
+// frame slot on config 5).  The chunk that holds the section's first bit already holds
 // the end of the previous frame: its owner merges (stream order: that frame's copy-out has completed); bits past the section
 // in the last chunk are zero, the tile copy-out that follows merges into it.  The last CTA of a GOP to finish advances the
 // GOP's bit counter (ticket; every CTA has read the counter before it takes one) and resets the ticket.
