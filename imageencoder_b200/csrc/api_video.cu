@@ -243,6 +243,8 @@ __global__ void __launch_bounds__(256) me_search8_kernel(MEParams p) {
     }
 }
 std::atomic<int> g_me_variant{2};
+// 2 = the GOPs of a batch in two halves on two streams (default), 1 = all on the caller's stream
+std::atomic<int> g_video_encode_streams{2};
 
 // fixed-width fields: field i = low `bits` bits of val[i]
 struct FixedFieldTile {
@@ -562,45 +564,75 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     p.tile_scratch = s->d_tile_scratch;
     p.bit_base = reinterpret_cast<unsigned long long *>(s->d_tile_meta);
     p.tile_bits = reinterpret_cast<unsigned *>(s->d_tile_meta + ntot * sizeof(unsigned long long));
+    // One frame slot of `act` GOPs starting at GOP `gb` of the batch (every per-GOP array is addressed from its element gb), on
+    // stream `sx`.  Two halves of a batch run on two streams: the P-frame tiles of one half (issue-bound) next to the motion
+    // search of the other (shared-memory / XU bound), and one half's tail next to the other's next kernel.
+    auto launch_slot = [&](uint32_t g0, uint32_t gb, uint32_t act, uint32_t k, cudaStream_t sx) -> int {
+        EncodeParams q = p;
+        const uint32_t f = (g0 + gb) * gop + k;                                          // frame k of the half's first GOP
+        uint8_t *cur = d_yuv + (size_t)f * fsz;
+        q.src = cur;
+        q.out = s->d_tmp + (size_t)gb * gop_cap;
+        q.bit_counter = s->d_counter + gb;
+        q.tile_scratch = p.tile_scratch + (size_t)gb * tiles * p.slot_bytes;
+        q.bit_base = p.bit_base + (size_t)gb * tiles;
+        q.tile_bits = p.tile_bits + (size_t)gb * tiles;
+        q.scan = s->scan_state();
+        q.scan.tile_state += (size_t)gb * tiles; q.scan.bnd += (size_t)gb * tiles; q.scan.ticket += gb;
+        short *mv = vs.mv + (size_t)gb * p.coord_stride, *res = vs.res + (size_t)gb * p.coord_stride, *cpy = vs.copy + (size_t)gb * p.coord_stride;
+        if (k == 0) {                                                                    // VideoBase.hpp:32, Frame.cpp:130-159
+            q.fq = fq_i;
+            IE_TRY(launch_encode_tiles(4, q, act, sx));
+            if (d_mvecs) IE_CUDA(cudaMemset2DAsync(d_mvecs + (size_t)f * nmb * 2, (size_t)gop * nmb * 2 * sizeof(short), 0,
+                                                   nmb * 2 * sizeof(short), act, sx));
+            return IE_OK;
+        }
+        MEParams me;
+        me.cur = cur; me.ref = cur - fsz; me.W = (int)W; me.H = (int)H; me.mx = (int)(W / kMB); me.nmb = (int)nmb;
+        me.merange = (int)merange; me.mv = mv; me.res_coord = res; me.copy_coord = cpy;
+        me.frame_stride = p.img_stride; me.mv_stride = p.coord_stride;
+        if (g_me_variant.load() == 2) me_search8_kernel<<<dim3((((W / kMB + 3) / 4) * (H / kMB) + 7) / 8, act), 256, 0, sx>>>(me);
+        else if (g_me_variant.load() == 1) me_search_redux_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, sx>>>(me);
+        else me_search_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, sx>>>(me);
+        count_launch();
+        {
+            const unsigned mv_chunks = (nmb * 2 * mvbits + 127) / 128 + 1;
+            mvec_pack2_kernel<<<dim3((mv_chunks + 255) / 256, act), 256, 0, sx>>>(mv, p.coord_stride, nmb * 2, mvbits, q.out, gop_cap, gop_cap,
+                                                                                 q.bit_counter, vs.ticket + gb, s->d_err);
+        }
+        count_launch();
+        IE_CUDA(cudaGetLastError());
+        if (d_mvecs) IE_CUDA(cudaMemcpy2DAsync(d_mvecs + (size_t)f * nmb * 2, (size_t)gop * nmb * 2 * sizeof(short), mv,
+                                               nmb * 2 * sizeof(short), nmb * 2 * sizeof(short), act, cudaMemcpyDeviceToDevice, sx));
+        q.fq = fq_p;
+        q.ref = me.ref; q.res_coord = res; q.copy_coord = cpy; q.cur_rw = cur;
+        return launch_pframe_tiles(q, act, sx);
+    };
+    const bool two_streams = g_video_encode_streams.load() == 2;
+    cudaStream_t st2 = st;
+    if (two_streams) { IE_TRY(session_ensure_pipeline(s)); st2 = s->stream_in; }
     for (uint32_t g0 = 0; g0 < ngops; g0 += batch) {
         const uint32_t nb = std::min(batch, ngops - g0);
         IE_TRY(launch_stream_init(s->d_tmp, gop_cap, nb, nohdr, 0, s->d_counter, st));   // empty GOP streams, counters = 0
+        // halves: GOPs [0, nA) on the caller's stream, [nA, nb) on the second one (fork after the initialisation, join before
+        // the GOP streams are appended)
+        const uint32_t nA = (two_streams && nb >= 2) ? (nb + 1) / 2 : nb;
+        if (nA < nb) {
+            IE_CUDA(cudaEventRecord(s->ev_in[0], st));
+            IE_CUDA(cudaStreamWaitEvent(st2, s->ev_in[0], 0));
+        }
+        const uint32_t last_len = frames - (g0 + nb - 1) * gop;                          // frames of the batch's last GOP (>= 1)
         for (uint32_t k = 0; k < gop; k++) {
             // GOPs of this batch that have a frame k (only the clip's last GOP can be short)
-            const uint32_t last_len = frames - (g0 + nb - 1) * gop;                      // >= 1
             const uint32_t act = (k < last_len) ? nb : nb - 1;
             if (act == 0) break;
-            const uint32_t f = g0 * gop + k;                                             // frame of the batch's first GOP
-            uint8_t *cur = d_yuv + (size_t)f * fsz;
-            p.src = cur;
-            p.scan = s->scan_state();
-            if (k == 0) {                                                                // VideoBase.hpp:32, Frame.cpp:130-159
-                p.fq = fq_i;
-                IE_TRY(launch_encode_tiles(4, p, act, st));
-                if (d_mvecs) IE_CUDA(cudaMemset2DAsync(d_mvecs + (size_t)f * nmb * 2, (size_t)gop * nmb * 2 * sizeof(short), 0,
-                                                       nmb * 2 * sizeof(short), act, st));
-                continue;
-            }
-            MEParams me;
-            me.cur = cur; me.ref = cur - fsz; me.W = (int)W; me.H = (int)H; me.mx = (int)(W / kMB); me.nmb = (int)nmb;
-            me.merange = (int)merange; me.mv = vs.mv; me.res_coord = vs.res; me.copy_coord = vs.copy;
-            me.frame_stride = p.img_stride; me.mv_stride = p.coord_stride;
-            if (g_me_variant.load() == 2) me_search8_kernel<<<dim3((((W / kMB + 3) / 4) * (H / kMB) + 7) / 8, act), 256, 0, st>>>(me);
-            else if (g_me_variant.load() == 1) me_search_redux_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, st>>>(me);
-            else me_search_kernel<<<dim3((nmb + 7) / 8, act), 256, 0, st>>>(me);
-            count_launch();
-            {
-                const unsigned mv_chunks = (nmb * 2 * mvbits + 127) / 128 + 1;
-                mvec_pack2_kernel<<<dim3((mv_chunks + 255) / 256, act), 256, 0, st>>>(vs.mv, p.coord_stride, nmb * 2, mvbits, s->d_tmp, gop_cap, gop_cap,
-                                                                                     s->d_counter, vs.ticket, s->d_err);
-            }
-            count_launch();
-            IE_CUDA(cudaGetLastError());
-            if (d_mvecs) IE_CUDA(cudaMemcpy2DAsync(d_mvecs + (size_t)f * nmb * 2, (size_t)gop * nmb * 2 * sizeof(short), vs.mv,
-                                                   nmb * 2 * sizeof(short), nmb * 2 * sizeof(short), act, cudaMemcpyDeviceToDevice, st));
-            p.fq = fq_p;
-            p.ref = me.ref; p.res_coord = vs.res; p.copy_coord = vs.copy; p.cur_rw = cur;
-            IE_TRY(launch_pframe_tiles(p, act, st));
+            const uint32_t actA = std::min(act, nA), actB = act - actA;
+            IE_TRY(launch_slot(g0, 0, actA, k, st));
+            if (actB) IE_TRY(launch_slot(g0, nA, actB, k, st2));
+        }
+        if (nA < nb) {
+            IE_CUDA(cudaEventRecord(s->ev_in[1], st2));
+            IE_CUDA(cudaStreamWaitEvent(st, s->ev_in[1], 0));
         }
         // the batch's GOP streams, in order, onto the video stream
         gop_offsets_kernel<<<1, 32, 0, st>>>(s->d_counter, nb, vs.cursor, vs.gop_off, d_out, out_cap);

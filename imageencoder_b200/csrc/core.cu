@@ -23,6 +23,7 @@ extern std::atomic<int> g_decode_variant;      // decode_image.cu
 extern std::atomic<int> g_me_variant;          // api_video.cu
 extern std::atomic<int> g_video_decode_variant;
 extern std::atomic<int> g_video_decode_batches;
+extern std::atomic<int> g_video_encode_streams;
 extern std::atomic<int> g_pframe_variant;       // encode_image.cu
 extern std::atomic<uint64_t> g_stat_video_whole, g_stat_video_frames;
 static thread_local std::string t_error;
@@ -273,6 +274,11 @@ int ie_set_option(const char *name, int value) {
     if (name && !strcmp(name, "pframe_variant")) {
         if (value != 0 && value != 2) { ie::set_error("pframe_variant: 2 (packed f32x2 P-frame tiles, default) or 0 (scalar)"); return IE_EINVAL; }
         ie::g_pframe_variant.store(value);
+        return IE_OK;
+    }
+    if (name && !strcmp(name, "video_encode_streams")) {
+        if (value < 1 || value > 2) { ie::set_error("video_encode_streams: 2 (the GOPs of a batch in two halves on two streams, default) or 1"); return IE_EINVAL; }
+        ie::g_video_encode_streams.store(value);
         return IE_OK;
     }
     if (name && !strcmp(name, "video_decode_batches")) {

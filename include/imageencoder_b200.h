@@ -271,6 +271,8 @@ int ie_comm_copy_stitched(ie_comm *c, void *dst, size_t nbytes, void *stream);
  *   "video_decode_variant" = 0 | 1 (default)  video decode: 1 = one speculative parse over the whole stream, a short
  *                          sequential frame chain, then frame k of every GOP per launch (streams that end inside a frame or
  *                          hold an invalid length field fall back to 0); 0 = frame by frame;
+ *   "video_encode_streams" = 1 | 2 (default)  video encode: the GOPs of a batch in two halves on two streams (one half's P-frame
+ *                          tiles next to the other half's motion search) or all on the caller's stream;
  *   "video_decode_batches" = 1 .. 32 (default 4)  GOP batches of the whole-stream video decode: the sequential frame chain of
  *                          batch b + 1 runs next to the reconstruction of batch b (second stream);
  *   "me_variant"      = 0 | 1 | 2 (default)  motion-search kernel: 2 = eight lanes per MacroBlock, four MacroBlocks per warp
