@@ -227,6 +227,9 @@ int session_ensure_pipeline(ie_session *s) {
     if (s->stream_in) return IE_OK;
     IE_CUDA(cudaStreamCreateWithFlags(&s->stream_in, cudaStreamNonBlocking));
     IE_CUDA(cudaStreamCreateWithFlags(&s->stream_out, cudaStreamNonBlocking));
+    IE_CUDA(cudaStreamCreateWithFlags(&s->stream_aux, cudaStreamNonBlocking));
+    IE_CUDA(cudaEventCreateWithFlags(&s->ev_aux_fork, cudaEventDisableTiming));
+    IE_CUDA(cudaEventCreateWithFlags(&s->ev_aux_join, cudaEventDisableTiming));
     for (int i = 0; i < ie_session::kMaxStripes; i++) {
         IE_CUDA(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
         IE_CUDA(cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming));
@@ -430,6 +433,9 @@ void ie_session_destroy(ie_session *s) {
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->stream_in) {
         cudaStreamDestroy(s->stream_in); cudaStreamDestroy(s->stream_out);
+        if (s->stream_aux) cudaStreamDestroy(s->stream_aux);
+        if (s->ev_aux_fork) cudaEventDestroy(s->ev_aux_fork);
+        if (s->ev_aux_join) cudaEventDestroy(s->ev_aux_join);
         for (int i = 0; i < ie_session::kMaxStripes; i++) { cudaEventDestroy(s->ev_in[i]); cudaEventDestroy(s->ev_done[i]); }
     }
     delete s;

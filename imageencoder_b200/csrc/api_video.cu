@@ -485,6 +485,24 @@ __global__ void __launch_bounds__(256) gop_append_kernel(const uint8_t *gop_stre
     }
 }
 
+// Copy / compute pipeline of the host entry point ie_encode_video: the device entry point encodes the clip in batches of at
+// most max_batch GOPs and calls before_batch (wait for the upload of the batch's frames) / after_batch (the stream up to here
+// is final: read the cursor back, let the download start) around each.
+struct VideoEncodeHooks {
+    uint32_t max_batch;
+    uint32_t used_batch;      // out: the GOPs per batch the device entry point settled on (<= max_batch)
+    int (*before_batch)(void *ctx, uint32_t g0, uint32_t nb, cudaStream_t st);
+    int (*after_batch)(void *ctx, uint32_t index, const unsigned long long *d_cursor, cudaStream_t st);
+    void *ctx;
+};
+
+// ie_decode_video's side of the same idea: once a GOP batch is reconstructed (chroma filled), its frames can go down.
+struct VideoDecodeHooks {
+    int (*after_batch)(void *ctx, uint32_t index, size_t byte0, size_t byte1, cudaStream_t st);
+    void *ctx;
+    bool whole_done;          // out: the whole-stream path produced the frames (the early copies are valid)
+};
+
 struct VideoScratch { short *mv, *res, *copy; unsigned long long *cursor, *gop_off; unsigned *ticket; };
 // motion vectors / residual / copy coordinates of `ngops` frames in flight ([gop][nmb][2] each), the stream's bit cursor and
 // the GOP offsets of a batch
@@ -528,7 +546,9 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     const size_t gop_cap = ((frame_cap_bits * std::min<size_t>(gop, std::max<uint32_t>(frames, 1)) + 127) / 128 + 2) * 16;
     constexpr uint32_t kMaxGopBatch = 64;
     const uint32_t mem_batch = (uint32_t)std::max<size_t>(1, ((size_t)2 << 30) / gop_cap);
-    const uint32_t batch = std::max<uint32_t>(1, std::min(std::min(ngops, kMaxGopBatch), mem_batch));
+    uint32_t batch = std::max<uint32_t>(1, std::min(std::min(ngops, kMaxGopBatch), mem_batch));
+    VideoEncodeHooks *hooks = static_cast<VideoEncodeHooks *>(s->video_hooks);
+    if (hooks) { batch = std::max<uint32_t>(1, std::min(batch, hooks->max_batch)); hooks->used_batch = batch; }
     IE_TRY(session_ensure_scan(s, batch, tiles));
     IE_TRY(session_ensure_err(s));
     VideoScratch vs;
@@ -610,16 +630,17 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
     };
     const bool two_streams = g_video_encode_streams.load() == 2;
     cudaStream_t st2 = st;
-    if (two_streams) { IE_TRY(session_ensure_pipeline(s)); st2 = s->stream_in; }
+    if (two_streams) { IE_TRY(session_ensure_pipeline(s)); st2 = s->stream_aux; }
     for (uint32_t g0 = 0; g0 < ngops; g0 += batch) {
         const uint32_t nb = std::min(batch, ngops - g0);
+        if (hooks) IE_TRY(hooks->before_batch(hooks->ctx, g0, nb, st));
         IE_TRY(launch_stream_init(s->d_tmp, gop_cap, nb, nohdr, 0, s->d_counter, st));   // empty GOP streams, counters = 0
         // halves: GOPs [0, nA) on the caller's stream, [nA, nb) on the second one (fork after the initialisation, join before
         // the GOP streams are appended)
         const uint32_t nA = (two_streams && nb >= 2) ? (nb + 1) / 2 : nb;
         if (nA < nb) {
-            IE_CUDA(cudaEventRecord(s->ev_in[0], st));
-            IE_CUDA(cudaStreamWaitEvent(st2, s->ev_in[0], 0));
+            IE_CUDA(cudaEventRecord(s->ev_aux_fork, st));
+            IE_CUDA(cudaStreamWaitEvent(st2, s->ev_aux_fork, 0));
         }
         const uint32_t last_len = frames - (g0 + nb - 1) * gop;                          // frames of the batch's last GOP (>= 1)
         for (uint32_t k = 0; k < gop; k++) {
@@ -631,14 +652,15 @@ int ie_encode_video_dev(ie_session *s, uint8_t *d_yuv, size_t yuv_bytes, uint32_
             if (actB) IE_TRY(launch_slot(g0, nA, actB, k, st2));
         }
         if (nA < nb) {
-            IE_CUDA(cudaEventRecord(s->ev_in[1], st2));
-            IE_CUDA(cudaStreamWaitEvent(st, s->ev_in[1], 0));
+            IE_CUDA(cudaEventRecord(s->ev_aux_join, st2));
+            IE_CUDA(cudaStreamWaitEvent(st, s->ev_aux_join, 0));
         }
         // the batch's GOP streams, in order, onto the video stream
         gop_offsets_kernel<<<1, 32, 0, st>>>(s->d_counter, nb, vs.cursor, vs.gop_off, d_out, out_cap);
         gop_append_kernel<<<dim3(s->dev->sm_count * 2, nb), 256, 0, st>>>(s->d_tmp, gop_cap, s->d_counter, vs.gop_off, nb, d_out, out_cap, s->d_err);
         count_launch(2);
         IE_CUDA(cudaGetLastError());
+        if (hooks) IE_TRY(hooks->after_batch(hooks->ctx, g0 / batch, vs.cursor, st));
     }
     if (frames == 0) { /* header only */ }
     if (d_out_bits) IE_CUDA(cudaMemcpyAsync(d_out_bits, vs.cursor, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
@@ -656,6 +678,7 @@ int ie_encode_video(const uint8_t *yuv, size_t yuv_bytes, uint32_t W, uint32_t H
                     uint32_t merange, int huffman, uint8_t *out, size_t out_cap, size_t *out_bytes) {
     if (!yuv || !out || !out_bytes) { set_error("NULL argument"); return IE_EINVAL; }
     IE_TRY(check_video_dims(W, H));
+    if (gop < 1) gop = 1;
     const size_t fsz = (size_t)W * H * 3 / 2;
     const uint32_t frames = (uint32_t)(yuv_bytes / fsz);
     SessionLease lease;
@@ -667,9 +690,57 @@ int ie_encode_video(const uint8_t *yuv, size_t yuv_bytes, uint32_t W, uint32_t H
     IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, cap16 + 64));
     uint64_t *d_total = reinterpret_cast<uint64_t *>(s->d_out + cap16);           // the stream's bit count, behind the stream
     cudaStream_t st = s->stream;
-    IE_CUDA(cudaMemcpyAsync(s->d_in, yuv, yuv_bytes, cudaMemcpyHostToDevice, st));
-    IE_TRY(ie_encode_video_dev(s, s->d_in, yuv_bytes, W, H, quant, use_rle, gop, merange, huffman ? 0 : 1, s->d_out, cap16,
-                               d_total, nullptr, st));
+    IE_TRY(session_ensure_pipeline(s));
+    // Copy / compute pipeline: the clip goes up in batches of GOPs on stream_in, a batch is encoded as soon as it has arrived,
+    // and -- without Huffman -- the part of the stream that a batch completed goes down on stream_out while later batches are
+    // still on their way up / being encoded.  PCIe runs in both directions at once.
+    const uint32_t ngops = (frames + gop - 1) / gop;
+    const uint32_t want = std::min<uint32_t>(std::max<uint32_t>(ngops, 1), 8);                // batches
+    const uint32_t gpb = std::max<uint32_t>(1, (ngops + want - 1) / want);                   // GOPs per batch
+    const uint32_t nbatches = ngops ? (ngops + gpb - 1) / gpb : 0;
+    struct Ctx { ie_session *s; uint32_t gpb; } ctx{s, gpb};
+    VideoEncodeHooks hooks;
+    hooks.max_batch = gpb;
+    hooks.ctx = &ctx;
+    hooks.used_batch = 0;
+    hooks.before_batch = [](void *c, uint32_t g0, uint32_t nb, cudaStream_t stx) -> int {
+        Ctx *x = static_cast<Ctx *>(c);
+        // uploads complete in order: the event of the upload batch that holds this batch's last GOP covers all of it
+        IE_CUDA(cudaStreamWaitEvent(stx, x->s->ev_in[((g0 + nb - 1) / x->gpb) % ie_session::kMaxStripes], 0));
+        return IE_OK;
+    };
+    hooks.after_batch = [](void *c, uint32_t index, const unsigned long long *d_cursor, cudaStream_t stx) -> int {
+        Ctx *x = static_cast<Ctx *>(c);
+        IE_CUDA(cudaMemcpyAsync(&x->s->h_pinned[16 + index % 32], d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stx));
+        IE_CUDA(cudaEventRecord(x->s->ev_done[index % ie_session::kMaxStripes], stx));
+        return IE_OK;
+    };
+    for (uint32_t b = 0; b < nbatches; b++) {
+        const size_t f0 = (size_t)b * gpb * gop, f1 = std::min<size_t>(frames, (size_t)(b + 1) * gpb * gop);
+        IE_CUDA(cudaMemcpyAsync(s->d_in + f0 * fsz, yuv + f0 * fsz, (f1 - f0) * fsz, cudaMemcpyHostToDevice, s->stream_in));
+        IE_CUDA(cudaEventRecord(s->ev_in[b % ie_session::kMaxStripes], s->stream_in));
+    }
+    s->video_hooks = (nbatches > 0 && nbatches <= 32) ? &hooks : nullptr;
+    if (!s->video_hooks && frames) IE_CUDA(cudaStreamWaitEvent(st, s->ev_in[(nbatches - 1) % ie_session::kMaxStripes], 0));
+    const int rc = ie_encode_video_dev(s, s->d_in, yuv_bytes, W, H, quant, use_rle, gop, merange, huffman ? 0 : 1, s->d_out, cap16,
+                                       d_total, nullptr, st);
+    // the stream can go down batch by batch only if the device entry point encoded exactly the upload batches
+    const bool piped = s->video_hooks != nullptr && hooks.used_batch == gpb;
+    s->video_hooks = nullptr;
+    if (rc != IE_OK) { cudaStreamSynchronize(s->stream_in); cudaStreamSynchronize(st); return rc; }
+    size_t sent = 0;                                                               // bytes of the stream already on their way down
+    if (piped && !huffman) {
+        for (uint32_t b = 0; b + 1 < nbatches; b++) {
+            IE_CUDA(cudaEventSynchronize(s->ev_done[b % ie_session::kMaxStripes]));
+            // whole 128-bit chunks below the batch's last bit are final (the chunk that holds it is shared with the next batch)
+            const size_t safe = (size_t)(s->h_pinned[16 + b % 32] / 128) * 16;
+            if (safe > out_cap) break;                                             // reported below, once the size is known
+            if (safe > sent) {
+                IE_CUDA(cudaMemcpyAsync(out + sent, s->d_out + sent, safe - sent, cudaMemcpyDeviceToHost, s->stream_out));
+                sent = safe;
+            }
+        }
+    }
     IE_CUDA(cudaMemcpyAsync(s->h_pinned, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     IE_TRY(read_err_flag(s, st));
     size_t bytes = (size_t)((s->h_pinned[0] + 7) / 8);
@@ -680,11 +751,13 @@ int ie_encode_video(const uint8_t *yuv, size_t yuv_bytes, uint32_t W, uint32_t H
         IE_TRY(ie_huffman_encode_dev(s, s->d_out, bytes, s->d_tmp, s->d_tmp_cap, &hb, st));
         bytes = hb;
         d_result = s->d_tmp;
+        sent = 0;
     }
     *out_bytes = bytes;
-    if (bytes > out_cap) { set_error("output buffer too small"); return IE_ENOSPC; }
-    IE_CUDA(cudaMemcpyAsync(out, d_result, bytes, cudaMemcpyDeviceToHost, st));
+    if (bytes > out_cap) { cudaStreamSynchronize(s->stream_out); set_error("output buffer too small"); return IE_ENOSPC; }
+    if (bytes > sent) IE_CUDA(cudaMemcpyAsync(out + sent, d_result + sent, bytes - sent, cudaMemcpyDeviceToHost, st));
     IE_CUDA(cudaStreamSynchronize(st));
+    IE_CUDA(cudaStreamSynchronize(s->stream_out));
     return IE_OK;
 }
 
@@ -741,7 +814,8 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
     // chain gives up (truncated / damaged stream) the batches already enqueued decode empty records (harmless) and the caller
     // decodes frame by frame over their output.
     IE_TRY(session_ensure_pipeline(s));
-    cudaStream_t st2 = s->stream_in;
+    VideoDecodeHooks *dhooks = static_cast<VideoDecodeHooks *>(s->video_dec_hooks);
+    cudaStream_t st2 = s->stream_aux;
     cudaEvent_t ev_join = nullptr;
     IE_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     int rc = IE_OK;
@@ -778,6 +852,11 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
             p.block_off = s->d_block_off + (size_t)k * (nblocks + 1);
             rc = launch_decode_blocks(p, nimg, st2);
         }
+        if (dhooks && rc == IE_OK) {
+            fill_uv_kernel<<<256, 256, 0, st2>>>(d_out + (size_t)f0 * fsz, ysz, fsz, f1 - f0);       // Frame.cpp:122-124
+            count_launch();
+            rc = dhooks->after_batch(dhooks->ctx, g0 / gpb, (size_t)f0 * fsz, (size_t)f1 * fsz, st2);
+        }
     }
     // join: the caller's stream continues after the second stream's last kernel
     if (cudaEventRecord(ev_join, st2) != cudaSuccess || cudaStreamWaitEvent(st, ev_join, 0) != cudaSuccess) rc = (rc == IE_OK) ? IE_ECUDA : rc;
@@ -791,8 +870,10 @@ static int decode_video_whole(ie_session *s, const uint8_t *d_enc, size_t enc_by
         IE_CUDA(cudaMemsetAsync(s->d_err, 0, sizeof(int), st));
         return IE_OK;
     }
-    fill_uv_kernel<<<256, 256, 0, st>>>(d_out, ysz, fsz, frames);                   // Frame.cpp:122-124
-    count_launch();
+    if (!dhooks) {
+        fill_uv_kernel<<<256, 256, 0, st>>>(d_out, ysz, fsz, frames);               // Frame.cpp:122-124
+        count_launch();
+    }
     IE_CUDA(cudaGetLastError());
     done = true;
     return IE_OK;
@@ -828,7 +909,11 @@ int ie_decode_video_dev(ie_session *s, const uint8_t *d_enc, size_t enc_bytes, u
     if (g_video_decode_variant.load() == 1) {
         bool done = false;
         IE_TRY(decode_video_whole(s, d_enc, enc_bytes, h, motioncomp, d_out, st, done));
-        if (done) { g_stat_video_whole.fetch_add(1); return IE_OK; }
+        if (done) {
+            g_stat_video_whole.fetch_add(1);
+            if (s->video_dec_hooks) static_cast<VideoDecodeHooks *>(s->video_dec_hooks)->whole_done = true;
+            return IE_OK;
+        }
     }
     g_stat_video_frames.fetch_add(1);
     VideoScratch vs;
@@ -913,10 +998,35 @@ int ie_decode_video(const uint8_t *enc, size_t enc_bytes, int motioncomp, uint8_
     if (total > yuv_cap) { set_error("yuv_out too small"); return IE_ENOSPC; }
     IE_TRY(session_reserve(&s->d_out, &s->d_out_cap, std::max<size_t>(total, 16)));
     uint32_t w, hh, ff;
-    IE_TRY(ie_decode_video_dev(s, d_plain, plain_bytes, start_bit, motioncomp, s->d_out, s->d_out_cap, &w, &hh, &ff, st));
-    IE_TRY(read_err_flag(s, st));
-    IE_CUDA(cudaMemcpyAsync(yuv_out, s->d_out, total, cudaMemcpyDeviceToHost, st));
-    IE_CUDA(cudaStreamSynchronize(st));
+    // Copy / compute pipeline: the frames of a reconstructed GOP batch go down on stream_out while later batches are still
+    // being decoded.  If the whole-stream decode gives up (damaged stream: frame-by-frame fallback over the same buffer), the
+    // early copies are discarded and everything goes down again at the end.
+    IE_TRY(session_ensure_pipeline(s));
+    struct Ctx { ie_session *s; uint8_t *host; size_t sent; bool contiguous; } ctx{s, yuv_out, 0, true};
+    VideoDecodeHooks hooks;
+    hooks.ctx = &ctx;
+    hooks.whole_done = false;
+    hooks.after_batch = [](void *c, uint32_t index, size_t b0, size_t b1, cudaStream_t stx) -> int {
+        Ctx *x = static_cast<Ctx *>(c);
+        if (!x->contiguous || b0 != x->sent || index >= (uint32_t)ie_session::kMaxStripes) { x->contiguous = false; return IE_OK; }
+        IE_CUDA(cudaEventRecord(x->s->ev_done[index], stx));
+        IE_CUDA(cudaStreamWaitEvent(x->s->stream_out, x->s->ev_done[index], 0));
+        IE_CUDA(cudaMemcpyAsync(x->host + b0, x->s->d_out + b0, b1 - b0, cudaMemcpyDeviceToHost, x->s->stream_out));
+        x->sent = b1;
+        return IE_OK;
+    };
+    s->video_dec_hooks = &hooks;
+    const int rc = ie_decode_video_dev(s, d_plain, plain_bytes, start_bit, motioncomp, s->d_out, s->d_out_cap, &w, &hh, &ff, st);
+    s->video_dec_hooks = nullptr;
+    const bool early = rc == IE_OK && hooks.whole_done && ctx.contiguous && ctx.sent == total;
+    if (rc != IE_OK) { cudaStreamSynchronize(s->stream_out); cudaStreamSynchronize(st); return rc; }
+    const int erc = read_err_flag(s, st);
+    if (erc != IE_OK) { cudaStreamSynchronize(s->stream_out); return erc; }
+    IE_CUDA(cudaStreamSynchronize(s->stream_out));
+    if (!early) {
+        IE_CUDA(cudaMemcpyAsync(yuv_out, s->d_out, total, cudaMemcpyDeviceToHost, st));
+        IE_CUDA(cudaStreamSynchronize(st));
+    }
     return IE_OK;
 }
 

@@ -58,6 +58,8 @@ struct ie_session {
     unsigned long long *h_pinned = nullptr;       // small pinned read-back area (64 u64)
     uint8_t *h_huff = nullptr;                    // pinned staging of the Huffman stage: dictionary header, codes, first bit
     void *huff_ctx = nullptr;                     // argument block of the stage's host callback (huffman.cu), malloc'ed
+    void *video_hooks = nullptr;                  // ie_encode_video's copy / compute pipeline (api_video.cu), set during one call
+    void *video_dec_hooks = nullptr;              // ie_decode_video's (frames of a finished GOP batch go down next to later batches)
     cudaStream_t stream = nullptr;                // used by the host-buffer entry points
 
     // copy/compute pipeline of the host-buffer image entry points: pixels come in by stripes on stream_in, the encoded
@@ -65,6 +67,10 @@ struct ie_session {
     static constexpr int kMaxStripes = 32;
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
     cudaEvent_t ev_in[kMaxStripes] = {}, ev_done[kMaxStripes] = {};
+    // second compute stream of the video entry points (half of a batch's GOPs / the reconstruction next to the frame chain):
+    // never the copy streams, or kernels would queue behind every copy already enqueued there
+    cudaStream_t stream_aux = nullptr;
+    cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
 
     ie::ScanState scan_state() {
         ie::ScanState st;

@@ -60,6 +60,8 @@ def test_me_variant_option_is_validated():
     L = ie.lib()
     try:
         assert L.ie_set_option(b"me_variant", 1) == 0
-        assert L.ie_set_option(b"me_variant", 2) != 0
+        assert L.ie_set_option(b"me_variant", 0) == 0
+        assert L.ie_set_option(b"me_variant", 3) != 0
+        assert L.ie_set_option(b"me_variant", -1) != 0
     finally:
-        assert L.ie_set_option(b"me_variant", 0) == 0              # the default
+        assert L.ie_set_option(b"me_variant", 2) == 0              # the default
