@@ -50,6 +50,49 @@ struct BlockTables {
     uint8_t izz[kMaxNN];
 };
 
+// One pixel of the inverse transform in the reference's order and precision (algo.cpp:343-363: u outer, v inner; Block.cpp:165-168
+// multiplies the coefficient by the quantiser first; zero coefficients contribute exact zeroes and are skipped).  `nzmask` holds
+// the raster positions of the block's non-zero coefficients, `cf` its zigzag-ordered staging row.  The additions are one
+// dependent chain in the reference's order; everything else of a term (zigzag index, coefficient, quantiser, table entry: the
+// table read goes to L2) does not depend on the running sum, so the terms are fetched R per round and their latencies overlap
+// (R = 4 pays for 8x8 blocks and in the P-frame tiles; the 4x4 block decoder, few non-zeros per block, is fastest with R = 1).
+#ifdef __CUDACC__
+template <int NN, int R, typename MaskT, typename QuantT>
+__device__ __forceinline__ double exact_inverse_pixel(MaskT nzmask, int ij, const short *cf, const BlockTables *tab, const QuantT &quant) {
+    double acc = 0.0;
+    MaskT nz = nzmask;
+    if constexpr (R == 1) {                                                                     // term by term
+        while (nz) {
+            const int uv = (sizeof(MaskT) == 8 ? __ffsll((long long)nz) : __ffs((int)nz)) - 1;
+            nz &= nz - 1;
+            const double d = __dmul_rn((double)(int)cf[tab->izz[uv]], quant.m[uv]);            // Block.cpp:165-168
+            acc = __dadd_rn(acc, __dmul_rn(__ldg(tab->inv + uv * NN + ij), d));                 // algo.cpp:352-355
+        }
+        return acc;
+    } else {
+    while (nz) {
+        int uv[R];
+#pragma unroll
+        for (int t = 0; t < R; t++) {
+            uv[t] = (sizeof(MaskT) == 8 ? __ffsll((long long)nz) : __ffs((int)nz)) - 1;      // -1 once the mask is empty
+            nz &= nz - 1;
+        }
+        double a[R], d[R];
+#pragma unroll
+        for (int t = 0; t < R; t++) {
+            const int k = max(uv[t], 0);
+            a[t] = __ldg(tab->inv + k * NN + ij);
+            d[t] = __dmul_rn((double)(int)cf[tab->izz[k]], quant.m[k]);                        // Block.cpp:165-168
+        }
+#pragma unroll
+        for (int t = 0; t < R; t++)
+            if (uv[t] >= 0) acc = __dadd_rn(acc, __dmul_rn(a[t], d[t]));                       // algo.cpp:352-355
+    }
+    return acc;
+    }
+}
+#endif
+
 struct HostTables {
     BlockTables t4, t8;
 };

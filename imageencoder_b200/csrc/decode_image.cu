@@ -185,6 +185,16 @@ struct BitReader {
     }
 };
 
+#ifndef IE_DEC_R8
+#define IE_DEC_R8 4
+#endif
+#ifndef IE_DEC_R4
+#define IE_DEC_R4 1
+#endif
+#define IE_DEC_R(N) ((N) == 8 ? IE_DEC_R8 : IE_DEC_R4)
+#ifndef IE_DEC_LOWSPLIT
+#define IE_DEC_LOWSPLIT 1
+#endif
 template <int N, bool ADD, int VAR>
 __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
     pdl_wait();
@@ -248,14 +258,31 @@ __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
     float x[NN];
     float S = 0.f;
     unsigned long long nzmask = 0;
+    // 8x8: the first 36 zigzag positions are the diagonals u + v <= 7.  When no block of the warp is longer (the usual case with
+    // RLE), the other 28 coefficients are known zeroes: their conversion is skipped (warp-uniform branch).
+    constexpr int kLow = (N == 8 && IE_DEC_LOWSPLIT) ? 36 : NN;
+    const bool any_high = (kLow < NN) ? (__any_sync(__activemask(), len > kLow) != 0) : true;
 #pragma unroll
     for (int uv = 0; uv < NN; uv++) {
         const int k = (N == 8) ? kZigzagInvD8[uv] : kZigzagInvD4[uv];
+        if (k >= kLow) { x[uv] = 0.f; continue; }
         const int c = cf[k];
         if (c != 0) nzmask |= 1ull << uv;                                     // raster positions of the non-zero coefficients
         const float d = (float)c * p.k2[uv];                                  // coefficient * Q * C(u)C(v)
         x[uv] = d;
         S += fabsf(d);
+    }
+    if (kLow < NN && any_high) {
+#pragma unroll
+        for (int uv = 0; uv < NN; uv++) {
+            const int k = (N == 8) ? kZigzagInvD8[uv] : kZigzagInvD4[uv];
+            if (k < kLow) continue;
+            const int c = cf[k];
+            if (c != 0) nzmask |= 1ull << uv;
+            const float d = (float)c * p.k2[uv];
+            x[uv] = d;
+            S += fabsf(d);
+        }
     }
     if (VAR != 1 || ADD) idct2d_fast<N>(x);
     const float delta = (18.f * S + 2.f * (S + 383.f)) * 5.9604645e-8f * 1.0001f + 2e-6f;
@@ -319,14 +346,7 @@ __device__ __forceinline__ void decode_blocks_fast_body(const DecodeParams &p) {
     while (unsure) {
         const int ij = __ffsll((long long)unsure) - 1;
         unsure &= unsure - 1;
-        double acc = 0.0;
-        unsigned long long nz = nzmask;
-        while (nz) {
-            const int uv = __ffsll((long long)nz) - 1;
-            nz &= nz - 1;
-            const double d = __dmul_rn((double)(int)cf[tab->izz[uv]], p.quant.m[uv]);   // Block.cpp:165-168
-            acc = __dadd_rn(acc, __dmul_rn(__ldg(tab->inv + uv * NN + ij), d));         // algo.cpp:352-355
-        }
+        const double acc = exact_inverse_pixel<NN, IE_DEC_R(N)>(nzmask, ij, cf, tab, p.quant);
         double v = __dadd_rn(acc, 128.0);                                               // Block.cpp:173-175
         if (ADD) {                                                                       // Block.cpp:114-116
             unsigned pw = 0;

@@ -514,14 +514,7 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
                 while (unsure) {
                     const int ij = __ffs((int)unsure) - 1;
                     unsure &= unsure - 1;
-                    double acc = 0.0;
-                    unsigned nz = nzmask;
-                    while (nz) {
-                        const int uv = __ffs((int)nz) - 1;
-                        nz &= nz - 1;
-                        const double d = __dmul_rn((double)(int)cf[tab->izz[uv]], p.quant.m[uv]);       // Block.cpp:165-168
-                        acc = __dadd_rn(acc, __dmul_rn(__ldg(tab->inv + uv * NN + ij), d));             // algo.cpp:352-355
-                    }
+                    const double acc = exact_inverse_pixel<NN, 4>(nzmask, ij, cf, tab, p.quant);
                     const int yy = ij >> 2, kk = ij & 3;
                     unsigned rrow = 0, orow = 0;
 #pragma unroll
@@ -576,14 +569,7 @@ __global__ void __launch_bounds__(kThreads, encode_min_ctas(N, PF, FAST, VAR)) e
                 while (unsure) {
                     const int ij = __ffs((int)unsure) - 1;
                     unsure &= unsure - 1;
-                    double acc = 0.0;
-                    unsigned nz = nzmask;
-                    while (nz) {
-                        const int uv = __ffs((int)nz) - 1;
-                        nz &= nz - 1;
-                        const double d = __dmul_rn((double)(int)cf[tab->izz[uv]], p.quant.m[uv]);       // Block.cpp:165-168
-                        acc = __dadd_rn(acc, __dmul_rn(__ldg(tab->inv + uv * NN + ij), d));             // algo.cpp:352-355
-                    }
+                    const double acc = exact_inverse_pixel<NN, 4>(nzmask, ij, cf, tab, p.quant);
                     const int yy = ij >> 2, kk = ij & 3;
                     unsigned rrow = 0, orow = 0;
 #pragma unroll
