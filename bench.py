@@ -460,7 +460,7 @@ def ours_single(args):
                            "sessions / streams, header parsed once on the host (ie_decode_image_with_header_dev)",
                    "roofline": {"bound": "hbm", "achieved": dec_alg / (dec_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                 "frac": dec_alg / (dec_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(dec_alg),
-                                "kernel": "parse_spec_* (4 launches) + decode_blocks_fast_kernel<8,0>"},
+                                "kernel": "parse_spec_* (4 launches) + decode_blocks_lean_kernel<8>"},
                    "e2e": {"value": px * e2e_steps / e2e_dec_s / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int(n_e2e),
                            "d2h_bytes_per_step": px, "steps": e2e_steps, "api": "ie_decode_image (C-ABI, pinned host buffers)"}},
     }

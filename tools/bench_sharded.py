@@ -174,6 +174,35 @@ def main():
             out["decode_ms_one_gpu"] = dec_ms
             out["decode_gpx_s_one_gpu"] = W * H * F / dec_ms / 1e6
             out["decode_sha_ok"] = bool(sha(d_dec.cpu().numpy().tobytes()) == g["dec_mc1_sha256"])
+            if world == 1:
+                # end to end through the host entry points (VideoEncoder / VideoDecoder drop-in boundary): pinned host buffers,
+                # the copies inside the timed region (GOP batches go up / come down next to the kernels)
+                import ctypes as C
+                del d_enc, d_dec
+                qa = np.ascontiguousarray(q, dtype=np.uint16).reshape(-1)
+                qp = qa.ctypes.data_as(C.POINTER(C.c_uint16))
+                h_yuv = torch.from_numpy(np.ascontiguousarray(synth_video(W, H, F, g["seed"])).reshape(-1)).pin_memory()
+                cap = int(L.ie_max_encoded_bytes(W, H, 4, F))
+                h_enc = torch.empty(cap, dtype=torch.uint8).pin_memory()
+                h_dec = torch.empty(h_yuv.numel(), dtype=torch.uint8).pin_memory()
+                nb, nby = C.c_size_t(0), C.c_size_t(0)
+                w_, h_, f_ = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+                te, td = [], []
+                for _ in range(1 + args.reps):
+                    t = time.perf_counter()
+                    _lib.check(L.ie_encode_video(C.c_void_p(h_yuv.data_ptr()), h_yuv.numel(), W, H, qp, 1, gop, mer, 0,
+                                                 C.c_void_p(h_enc.data_ptr()), cap, C.byref(nb)))
+                    te.append((time.perf_counter() - t) * 1e3)
+                    t = time.perf_counter()
+                    _lib.check(L.ie_decode_video(C.c_void_p(h_enc.data_ptr()), nb.value, 1, C.c_void_p(h_dec.data_ptr()), h_dec.numel(),
+                                                 C.byref(nby), C.byref(w_), C.byref(h_), C.byref(f_)))
+                    td.append((time.perf_counter() - t) * 1e3)
+                e_ms, d_ms = float(np.median(te[1:])), float(np.median(td[1:]))
+                out["e2e"] = {"api": "ie_encode_video / ie_decode_video (C-ABI, pinned host buffers)",
+                              "encode_ms": e_ms, "decode_ms": d_ms, "encode_gpx_s": W * H * F / e_ms / 1e6, "decode_gpx_s": W * H * F / d_ms / 1e6,
+                              "h2d_bytes_encode": h_yuv.numel(), "d2h_bytes_encode": nb.value,
+                              "parity_sha_ok": bool(sha(h_enc[:nb.value].numpy().tobytes()) == g["enc_sha256"]
+                                                    and sha(h_dec.numpy().tobytes()) == g["dec_mc1_sha256"])}
             print(json.dumps(out))
         barrier()
         comm.close()
