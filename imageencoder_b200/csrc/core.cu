@@ -262,7 +262,7 @@ int ie_set_option(const char *name, int value) {
         return IE_OK;
     }
     if (name && !strcmp(name, "copyout_variant")) {
-        if (value < 0 || value > 2) { ie::set_error("copyout_variant: 0 (generic kernel), 1 (short path for interior chunks) or 2 (1 + four chunks in flight, the default)"); return IE_EINVAL; }
+        if (value < 0 || value > 3) { ie::set_error("copyout_variant: 0 (generic kernel), 1 (short path for interior chunks), 2 (1 + four chunks in flight, the default) or 3 (a warp per tile image, word by word)"); return IE_EINVAL; }
         ie::g_copyout_variant.store(value);
         return IE_OK;
     }

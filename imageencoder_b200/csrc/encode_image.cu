@@ -953,11 +953,119 @@ __global__ void __launch_bounds__(kThreads) tile_copyout_fast_kernel(const Encod
     }
 }
 
+// Copy-out by tile and by 32-bit word (copyout_variant 3).  The chunk-centric kernels above search, for every 128-bit chunk of the
+// stream, the tile it comes from; here a warp takes a whole tile image: its shift against the stream's word grid is one constant,
+// consecutive lanes read consecutive words of the image and write consecutive words of the stream (two loads, one funnel shift, one
+// byte swap, one store per word -- about a quarter of the instructions per byte of the chunk-centric path).
+// Ownership: a stream word belongs to the tile that holds its FIRST bit.  The owner of a word that ends in the next tile ORs in that
+// tile's first bits, read from its image in the scratch buffer (complete: the tile kernel has finished) -- so neither inside a group
+// nor between groups is there a hand-off, an atomic or a pre-zeroed stream.  (A full tile holds >= 512 bits, so a word never spans
+// three tiles; only the stream's last tile can be shorter than a word, and nothing follows it.)  The word that the stream's first
+// tile shares with what precedes it (header / earlier appends: zero padded, pack.cuh) is read, merged and written by that tile; the
+// stream's last tile pads its last 128-bit chunk with zeroes as the append contract wants.
+#ifndef IE_WORDS_U
+#define IE_WORDS_U 8
+#endif
+template <unsigned TPG, unsigned NT>
+__global__ void __launch_bounds__(NT) tile_copyout_words_kernel(const EncodeParams p) {
+    __shared__ unsigned long long s_part[NT / 32];
+    __shared__ unsigned s_goff[TPG + 1];
+    pdl_wait();
+    const unsigned img = blockIdx.y, ntiles = p.tiles_per_image;
+    const unsigned t0 = blockIdx.x * TPG, t1 = min(t0 + TPG, ntiles);
+    const unsigned *tb = p.tile_bits + (size_t)img * ntiles;
+    unsigned long long sum = 0;
+    if ((reinterpret_cast<size_t>(tb) & 15) == 0) {
+        const uint4 *tb4 = reinterpret_cast<const uint4 *>(tb);            // earlier tiles' totals (t0 is a multiple of 4)
+        for (unsigned i = threadIdx.x; i < t0 / 4; i += NT) {
+            const uint4 v = __ldg(tb4 + i);
+            sum += (unsigned long long)v.x + v.y + v.z + v.w;
+        }
+    } else {
+        for (unsigned i = threadIdx.x; i < t0; i += NT) sum += tb[i];
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = sum;
+    if (threadIdx.x < 32) {
+        const unsigned t = t0 + threadIdx.x;
+        const unsigned v = (t < t1) ? tb[t] : 0u;
+        unsigned inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if ((int)threadIdx.x >= d) inc += o; }
+        if (threadIdx.x < TPG) s_goff[threadIdx.x + 1] = inc;
+        if (threadIdx.x == 0) s_goff[0] = 0;
+    }
+    __syncthreads();
+    unsigned long long G = p.bit_base[img];
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) G += s_part[w];
+    const unsigned n = t1 - t0;
+    const unsigned slot_words = (unsigned)(p.slot_bytes / 4);
+    const unsigned *slot0 = reinterpret_cast<const unsigned *>(p.tile_scratch + ((size_t)img * ntiles + t0) * p.slot_bytes);
+    unsigned *out = reinterpret_cast<unsigned *>(p.out + (size_t)img * p.out_stride);
+    const unsigned long long cap_words = (p.out_cap / 16ull) * 4ull;       // whole chunks only, as the chunk-centric kernels
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    bool overflow = false;
+    for (unsigned j = warp; j < n; j += NT / 32) {
+        const unsigned Tj = s_goff[j + 1] - s_goff[j];
+        if (Tj == 0) continue;
+        const unsigned long long B0 = G + s_goff[j], B1 = B0 + Tj;         // the tile's bits in the stream
+        const unsigned long long q0 = (B0 + 31) >> 5, q1 = (B1 + 31) >> 5; // words whose first bit lies in the tile
+        const unsigned sh = (unsigned)((32u - (unsigned)(B0 & 31u)) & 31u);// image bit of word q0's first bit
+        const unsigned nw = (Tj + 31) >> 5;                                // words of the image (zero beyond the last bit)
+        const unsigned *I = slot0 + (size_t)j * slot_words;
+        const bool has_next = (t0 + j + 1) < ntiles;
+        const unsigned tail = (unsigned)(B1 & 31u);                        // bits of the tile in its last, shared word (0: none shared)
+        if (lane == 0 && t0 + j == 0 && (B0 & 31u) != 0) {
+            // the word the stream's first tile shares with the header / the earlier appends
+            const unsigned long long q = B0 >> 5;
+            if (q < cap_words) out[q] |= __byte_perm(__ldg(I) >> (unsigned)(B0 & 31u), 0, 0x0123);
+            else overflow = true;
+        }
+        const unsigned cnt = (unsigned)(q1 - q0);
+        for (unsigned k0 = 0; k0 < cnt; k0 += 32 * IE_WORDS_U) {
+            unsigned lo[IE_WORDS_U], hi[IE_WORDS_U];
+#pragma unroll
+            for (int u = 0; u < IE_WORDS_U; u++) {
+                const unsigned k = k0 + (unsigned)u * 32u + lane;          // word q0 + k <- image words k, k + 1
+                lo[u] = (k < nw && k < cnt) ? __ldg(I + k) : 0u;
+                hi[u] = (k + 1 < nw && k < cnt) ? __ldg(I + k + 1) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < IE_WORDS_U; u++) {
+                const unsigned k = k0 + (unsigned)u * 32u + lane;
+                if (k >= cnt) break;
+                unsigned v = __funnelshift_l(hi[u], lo[u], sh);
+                if (k + 1 == cnt && tail != 0 && has_next) v |= __ldg(I + slot_words) >> tail;      // first bits of the next tile
+                const unsigned long long q = q0 + k;
+                if (q < cap_words) out[q] = __byte_perm(v, 0, 0x0123);
+                else overflow = true;
+            }
+        }
+        if (!has_next && lane < 4) {
+            // end of the stream: the rest of its last chunk is zero
+            const unsigned long long q = q1 + lane, qe = ((B1 + 127) >> 7) << 2;
+            if (q < qe) { if (q < cap_words) out[q] = 0u; else overflow = true; }
+        }
+    }
+    if (overflow && p.err) atomicExch(p.err, IE_ENOSPC);
+    if (t1 == ntiles && threadIdx.x == 0) {
+        const unsigned long long total = G + s_goff[n];
+        p.bit_counter[img] = total;
+        if (p.out_bits) p.out_bits[img] = total;
+    }
+}
+
 // copy-out kernel: 2 = short path for interior chunks, four chunks per thread in flight (the default: 0.1125 -> 0.1068 ms on
 // config 2 with tile-kernel variant 2, profiles/r1_ab_copyout_v9.log), 1 = short path, one chunk at a time, 0 = the generic
 // kernel of versions v7/v8.  Eight chunks in flight and groups of 4 or 16 tiles measured slower
 // (profiles/r1_ab_copyout_groups_v9.log).
-std::atomic<int> g_copyout_variant{2};
+std::atomic<int> g_copyout_variant{3};
+#ifndef IE_WORDS_THREADS
+#define IE_WORDS_THREADS 128
+#endif
+constexpr unsigned kWordsThreads = IE_WORDS_THREADS;
 
 int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t stream) {
     const int cv = g_copyout_variant.load();
@@ -972,6 +1080,7 @@ int launch_tile_copyout(const EncodeParams &p, unsigned images, cudaStream_t str
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (cv == 1) IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_fast_kernel<1, kTilesPerGroup>, p));
     else if (cv == 2) IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_fast_kernel<4, kTilesPerGroup>, p));
+    else if (cv == 3) { cfg.blockDim = dim3(kWordsThreads); IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_words_kernel<kTilesPerGroup, kWordsThreads>, p)); }
     else IE_CUDA(cudaLaunchKernelEx(&cfg, tile_copyout_kernel, p));
     count_launch();
     IE_CUDA(cudaGetLastError());

@@ -264,8 +264,9 @@ int ie_comm_copy_stitched(ie_comm *c, void *dst, size_t nbytes, void *stream);
  *                          experimental (arithmetic checked on the CPU, not yet timed): 3 / 4 = 2 with an 8 KiB staging area
  *                          for the tile image and 7 / 8 CTAs per SM, 5 = 2 with a short-chain binary64 pre-check in front
  *                          of the exact queue, 6 / 7 = 3 / 4 with that pre-check;
- *   "copyout_variant" = 0 | 1 | 2 (default)  copy-out kernel: 2 = short path for interior chunks with four chunks per
- *                          thread in flight, 1 = short path one chunk at a time, 0 = the generic kernel;
+ *   "copyout_variant" = 0 | 1 | 2 | 3 (default)  copy-out kernel: 3 = a warp per tile image, word by word (no search, no
+ *                          hand-off between groups), 2 = chunk-centric with a short path for interior chunks and four chunks
+ *                          per thread in flight, 1 = short path one chunk at a time, 0 = the generic kernel;
  *   "decode_variant"  = 0 | 1 (default)  block-decode kernel of images and I-frames: 1 = inverse transform and pixel
  *                          stage in packed f32x2 operations, 0 = the scalar kernel it replaced;
  *   "video_decode_variant" = 0 | 1 (default)  video decode: 1 = one speculative parse over the whole stream, a short

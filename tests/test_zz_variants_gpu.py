@@ -59,7 +59,7 @@ def test_damaged_streams_decode_like_the_oracle():
 
 
 def test_copyout_variant_streams_identical(gpu, oracle_mod):
-    """ie_set_option("copyout_variant", 0|1|2): 2 (short path for interior chunks, four in flight) is the default kernel,
+    """ie_set_option("copyout_variant", 0|1|2|3): 3 (a warp per tile image, word by word) is the default kernel, 2 (chunk-centric, four in flight) and
     0 the generic one it replaced; none may change a byte."""
     import numpy as np
     from conftest import INPUTS
@@ -72,11 +72,11 @@ def test_copyout_variant_streams_identical(gpu, oracle_mod):
             for img in (synth_image(1024, 768, 31), synth_image(512, 384, 32, flat=True), np.full((64, 64), 128, np.uint8)):
                 h, w = img.shape
                 want = oracle_mod.image_encode(img, w, h, n, q, True, False)
-                for cv in (0, 1, 2):
+                for cv in (0, 1, 2, 3):
                     assert L.ie_set_option(b"copyout_variant", cv) == 0
                     assert gpu.encode_image(img, w, h, q, True, False) == want, (mat, img.shape, cv)
     finally:
-        L.ie_set_option(b"copyout_variant", 2)
+        L.ie_set_option(b"copyout_variant", 3)
 
 
 def test_exact_parse_path_matches_oracle(gpu, oracle_mod):

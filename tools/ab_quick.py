@@ -48,7 +48,7 @@ for mat in ("matrix8_1.txt", "matrix4_2.txt"):
             got = ie.encode_image(img, w, h, q, True, False)
             res["parity_small"][f"{mat}/{name}/v{v}c{cv}"] = (got == want)
 _lib.check(L.ie_set_option(b"encode_variant", 2))
-_lib.check(L.ie_set_option(b"copyout_variant", 2))
+_lib.check(L.ie_set_option(b"copyout_variant", 3))
 if not all(res["parity_small"].values()):
     print("PARITY FAILURE on small images")
 print("parity (small, vs oracle): all identical =", all(res["parity_small"].values()), flush=True)
@@ -125,7 +125,7 @@ for pad in PADS[1:] + PADS[:1]:
     if len(PADS) == 1:
         break
     _lib.check(L.ie_set_option(b"encode_variant", 2))
-    _lib.check(L.ie_set_option(b"copyout_variant", 2))
+    _lib.check(L.ie_set_option(b"copyout_variant", 3))
     run(RING)
     ck(rt.cudaDeviceSynchronize(), "sync")
     reps = 40
@@ -158,7 +158,7 @@ for rnd in range(2):
         print(f"round {rnd} encode_variant {v} copyout_variant {cv}: {size}x{size}  {ms.value / reps:.4f} ms/encode  identical_to_default={same}",
               flush=True)
 _lib.check(L.ie_set_option(b"encode_variant", 2))
-_lib.check(L.ie_set_option(b"copyout_variant", 2))
+_lib.check(L.ie_set_option(b"copyout_variant", 3))
 res["wall_s"] = time.time() - t_start
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/ab_quick.json", "w") as f:
