@@ -444,7 +444,7 @@ def ours_single(args):
         "config": bench_config(cfg, 1),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "encode step = encode_tiles_kernel<8,1,0,1,2> + tile_copyout_fast_kernel<4,8>; achieved = algorithmic "
+                     "kernel": "encode step = encode_tiles_kernel<8,1,0,1,2> + tile_copyout_words_kernel<8,128>; achieved = algorithmic "
                                "bytes / device time per step with the copy-out of one image overlapping the tile kernel of the next "
                                "(two streams); kernel_ms_isolated = the same two kernels for one image alone on one stream",
                      "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": step_ms, "kernel_ms_isolated": iso_ms,
@@ -785,7 +785,7 @@ def ours_sharded(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
                          "kernel": "per rank: encode_tiles_kernel + tile_totals_kernel + shard_exchange_kernel (P2P mailboxes) + "
-                                   "stream_init_shard_kernel + tile_copyout_fast_kernel",
+                                   "stream_init_shard_kernel + tile_copyout_words_kernel",
                          "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": step_ms},
             "e2e": {"value": px * e2e_steps / e2e_s / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": px,
                     "d2h_bytes_per_step": d2h_total, "steps": e2e_steps,
