@@ -976,8 +976,17 @@ __global__ void __launch_bounds__(NT) tile_copyout_words_kernel(const EncodePara
     const unsigned *tb = p.tile_bits + (size_t)img * ntiles;
     unsigned long long sum = 0;
     if ((reinterpret_cast<size_t>(tb) & 15) == 0) {
-        const uint4 *tb4 = reinterpret_cast<const uint4 *>(tb);            // earlier tiles' totals (t0 is a multiple of 4)
-        for (unsigned i = threadIdx.x; i < t0 / 4; i += NT) {
+        // earlier tiles' totals (t0 is a multiple of 4), four 128-bit loads per thread in flight: the groups at the end of a large
+        // image read 32 KiB here, and a load per round trip made their CTAs the kernel's critical path
+        const uint4 *tb4 = reinterpret_cast<const uint4 *>(tb);
+        const unsigned n4 = t0 / 4;
+        unsigned i = threadIdx.x;
+        for (; i + 3 * NT < n4; i += 4 * NT) {
+            const uint4 a = __ldg(tb4 + i), b = __ldg(tb4 + i + NT), c = __ldg(tb4 + i + 2 * NT), d = __ldg(tb4 + i + 3 * NT);
+            sum += ((unsigned long long)a.x + a.y + a.z + a.w) + ((unsigned long long)b.x + b.y + b.z + b.w)
+                 + ((unsigned long long)c.x + c.y + c.z + c.w) + ((unsigned long long)d.x + d.y + d.z + d.w);
+        }
+        for (; i < n4; i += NT) {
             const uint4 v = __ldg(tb4 + i);
             sum += (unsigned long long)v.x + v.y + v.z + v.w;
         }
@@ -1024,7 +1033,21 @@ __global__ void __launch_bounds__(NT) tile_copyout_words_kernel(const EncodePara
             else overflow = true;
         }
         const unsigned cnt = (unsigned)(q1 - q0);
-        for (unsigned k0 = 0; k0 < cnt; k0 += 32 * IE_WORDS_U) {
+        const bool fits = q1 <= cap_words;                                 // uniform
+        unsigned *ow = out + q0;
+        unsigned k0 = 0;
+        // whole rounds of 32 * U words well inside the image: no bounds, no neighbour (32-bit indices throughout)
+        if (fits) {
+            for (; k0 + 32u * IE_WORDS_U < cnt && k0 + 32u * IE_WORDS_U < nw; k0 += 32u * IE_WORDS_U) {
+                unsigned lo[IE_WORDS_U], hi[IE_WORDS_U];
+                const unsigned *Ik = I + k0 + lane;
+#pragma unroll
+                for (int u = 0; u < IE_WORDS_U; u++) { lo[u] = __ldg(Ik + 32 * u); hi[u] = __ldg(Ik + 32 * u + 1); }
+#pragma unroll
+                for (int u = 0; u < IE_WORDS_U; u++) ow[k0 + lane + 32u * u] = __byte_perm(__funnelshift_l(hi[u], lo[u], sh), 0, 0x0123);
+            }
+        }
+        for (; k0 < cnt; k0 += 32u * IE_WORDS_U) {
             unsigned lo[IE_WORDS_U], hi[IE_WORDS_U];
 #pragma unroll
             for (int u = 0; u < IE_WORDS_U; u++) {
@@ -1038,8 +1061,7 @@ __global__ void __launch_bounds__(NT) tile_copyout_words_kernel(const EncodePara
                 if (k >= cnt) break;
                 unsigned v = __funnelshift_l(hi[u], lo[u], sh);
                 if (k + 1 == cnt && tail != 0 && has_next) v |= __ldg(I + slot_words) >> tail;      // first bits of the next tile
-                const unsigned long long q = q0 + k;
-                if (q < cap_words) out[q] = __byte_perm(v, 0, 0x0123);
+                if (fits || q0 + k < cap_words) ow[k] = __byte_perm(v, 0, 0x0123);
                 else overflow = true;
             }
         }
