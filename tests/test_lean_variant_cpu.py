@@ -65,3 +65,15 @@ def test_me_variant_option_is_validated():
         assert L.ie_set_option(b"me_variant", -1) != 0
     finally:
         assert L.ie_set_option(b"me_variant", 2) == 0              # the default
+
+
+def test_copyout_variant_option_is_validated():
+    import imageencoder_b200 as ie
+    L = ie.lib()
+    try:
+        for v in (0, 1, 2, 3):
+            assert L.ie_set_option(b"copyout_variant", v) == 0
+        assert L.ie_set_option(b"copyout_variant", 4) != 0
+        assert L.ie_set_option(b"copyout_variant", -1) != 0
+    finally:
+        assert L.ie_set_option(b"copyout_variant", 3) == 0         # the default
