@@ -1015,7 +1015,12 @@ int ie_decode_video(const uint8_t *enc, size_t enc_bytes, int motioncomp, uint8_
         x->sent = b1;
         return IE_OK;
     };
-    s->video_dec_hooks = &hooks;
+    // early copies only into page-locked memory: a device-to-host copy into pageable memory blocks the calling thread until it has
+    // completed, which would stall the enqueueing of the later batches behind the reconstruction of the earlier ones
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, yuv_out) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    s->video_dec_hooks = pinned ? &hooks : nullptr;
     const int rc = ie_decode_video_dev(s, d_plain, plain_bytes, start_bit, motioncomp, s->d_out, s->d_out_cap, &w, &hh, &ff, st);
     s->video_dec_hooks = nullptr;
     const bool early = rc == IE_OK && hooks.whole_done && ctx.contiguous && ctx.sent == total;
