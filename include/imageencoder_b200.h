@@ -78,7 +78,11 @@ int ie_decode_images(const uint8_t *encs, size_t enc_stride, const size_t *enc_b
 /* ---- video: replaces dc::VideoEncoder::process (VideoEncoder.cpp:22-111 + Frame.cpp:129-247) and
  *      dc::VideoDecoder (VideoBase.cpp:45-85 + VideoDecoder.cpp:33-62 + Frame.cpp:47-127) -------------------- */
 /* yuv420: frames * (w*h*3/2) bytes, planar; only Y is coded.  Block size is 4, MacroBlock 16 (Block.hpp:13-14).
- * recon_out (optional, may be NULL): receives the encoder-side reconstruction the reference leaves in its raw buffer. */
+ * recon_out (optional, may be NULL): receives the encoder-side reconstruction the reference leaves in its raw buffer.
+ * Both calls run as copy / compute pipelines: the clip goes up in batches of GOPs while earlier batches are encoded and the
+ * finished part of the stream comes down; the decoder sends the frames of a reconstructed GOP batch down next to the decode of
+ * the following ones.  Pass page-locked buffers (cudaHostAlloc / cudaHostRegister) for full PCIe speed in both directions; with
+ * pageable buffers the calls are correct but the copies serialise (and the decoder's early copies are switched off). */
 int ie_encode_video(const uint8_t *yuv420, size_t yuv_bytes, uint32_t width, uint32_t height,
                     const uint16_t *quant, int use_rle, uint32_t gop, uint32_t merange, int huffman,
                     uint8_t *out, size_t out_cap, size_t *out_bytes);
