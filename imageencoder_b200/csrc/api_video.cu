@@ -742,7 +742,10 @@ int ie_encode_video(const uint8_t *yuv, size_t yuv_bytes, uint32_t W, uint32_t H
         }
     }
     IE_CUDA(cudaMemcpyAsync(s->h_pinned, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    IE_TRY(read_err_flag(s, st));
+    {
+        const int erc = read_err_flag(s, st);
+        if (erc != IE_OK) { cudaStreamSynchronize(s->stream_out); return erc; }     // no copy into the caller's buffer outlives the call
+    }
     size_t bytes = (size_t)((s->h_pinned[0] + 7) / 8);
     const uint8_t *d_result = s->d_out;
     if (huffman) {
