@@ -678,7 +678,7 @@ int ie_encode_video(const uint8_t *yuv, size_t yuv_bytes, uint32_t W, uint32_t H
                     uint32_t merange, int huffman, uint8_t *out, size_t out_cap, size_t *out_bytes) {
     if (!yuv || !out || !out_bytes) { set_error("NULL argument"); return IE_EINVAL; }
     IE_TRY(check_video_dims(W, H));
-    if (gop < 1) gop = 1;
+    if (gop < 1) gop = 1;                                                      // VideoBase.cpp:34 (as ie_encode_video_dev)
     const size_t fsz = (size_t)W * H * 3 / 2;
     const uint32_t frames = (uint32_t)(yuv_bytes / fsz);
     SessionLease lease;
